@@ -1,0 +1,17 @@
+"""grmp_b200 -- B200-native assembly engine behind the GradientRobustMultiPhysics.jl
+assembly API (BilinearForm / LinearForm AssemblyPatterns).
+
+Layout:
+  csrc/          CUDA kernels + the C-ABI library libgrmp_cuda.so (include/grmp.h)
+  grid.py        ExtendableGrid components the path reads (input producer stand-in)
+  quadrature.py  QuadratureRule tables           (src/quadrature.jl)
+  fedefs.py      FETypes + reference bases       (src/fedefs/*.jl)
+  fespace.py     FESpace / CellDofs / FEVector / FEMatrix
+  assembly.py    AssemblyPattern, assemble!      (src/assemblypatterns/*.jl)
+  operators.py   LaplaceOperator ... assemble_operator!   (src/pdeoperators.jl)
+"""
+from .grid import (ExtendableGrid, grid_unitsquare, grid_unitcube, reference_domain, uniform_refine,
+                   perturb_interior_nodes)
+from .quadrature import QuadratureRule
+from .fedefs import H1P1, H1P2, H1Pk, H1BR, HDIVRT0, HDIVBDM1, L2P0, reference_tables
+from .fespace import FESpace, FEVector, FEMatrix, FEMatrixBlock, FEVectorBlock
