@@ -1,0 +1,412 @@
+"""AssemblyPattern / assemble! (host mirror of src/assemblypatterns.jl,
+src/assemblypatterns/bilinearform.jl, src/assemblypatterns/linearform.jl).
+
+Same names, argument meaning and error behaviour as the reference; the cell loop itself
+runs in libgrmp_cuda (include/grmp.h) -- there is no CPU fallback:
+
+  DiscreteBilinearForm / DiscreteSymmetricBilinearForm / DiscreteLumpedBilinearForm
+                                                (bilinearform.jl:38-75)
+  DiscreteLinearForm                            (linearform.jl:29-33)
+  prepare_assembly(AP)                          (assemblypatterns.jl:467-671: quadrature order
+                                                 bonus + sum(polyorder + shift), evaluator tables)
+  assemble(A, AP; factor, transposed_assembly, transpose_copy, skip_preps)   (bilinearform.jl:92-400)
+  assemble(b, AP; factor, offset, skip_preps)                                (linearform.jl:47-251)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .fedefs import FEType, HDIVBDM1, HDIVRT0, H1BR, reference_tables
+from .fespace import FEMatrix, FEMatrixBlock, FESpace, FEVectorBlock
+from .quadrature import QuadratureRule
+
+# ---- function operators (src/functionoperators.jl:13-153) ---------------------------------------
+
+
+class AbstractFunctionOperator:
+    code = 0
+    needed_derivative = 0          # NeededDerivative4Operator (206-225)
+    name = "??"
+
+    def __repr__(self):
+        return self.name
+
+    def __eq__(self, o):
+        return type(self) is type(o) and self.__dict__ == o.__dict__
+
+    def __hash__(self):
+        return hash(type(self).__name__)
+
+
+class _Identity(AbstractFunctionOperator):
+    code, name = 1, "id"
+
+
+class _Gradient(AbstractFunctionOperator):
+    code, needed_derivative, name = 2, 1, "∇"
+
+
+class _SymmetricGradient(AbstractFunctionOperator):
+    """SymmetricGradient{offdiagval}; only offdiagval = 1 is on the ported path (pdeoperators.jl:260)"""
+    code, needed_derivative, name = 3, 1, "ϵ"
+
+    def __init__(self, offdiagval=1):
+        if offdiagval != 1:
+            raise NotImplementedError("SymmetricGradient{offdiagval != 1} is not on the ported path")
+        self.offdiagval = offdiagval
+
+
+class _Divergence(AbstractFunctionOperator):
+    code, needed_derivative, name = 4, 1, "div"
+
+
+class ReconstructionIdentity(AbstractFunctionOperator):
+    """ReconstructionIdentity{FETypeReconst} (feevaluator.jl:142-217)"""
+    name = "R"
+
+    def __init__(self, FETypeReconst: FEType):
+        if not isinstance(FETypeReconst, (HDIVRT0, HDIVBDM1)):
+            raise NotImplementedError("ReconstructionIdentity is ported for HDIVRT0 / HDIVBDM1 targets")
+        self.FETypeReconst = FETypeReconst
+        self.code = 5 if isinstance(FETypeReconst, HDIVRT0) else 6
+
+    def __hash__(self):
+        return hash(("R", self.code))
+
+
+Identity = _Identity()
+Gradient = _Gradient()
+SymmetricGradient = _SymmetricGradient
+Divergence = _Divergence()
+
+
+def _op(o):
+    return o() if isinstance(o, type) else o
+
+
+# ---- actions (src/actions.jl) -------------------------------------------------------------------
+class NoAction:
+    code = 0
+    params = None
+
+    def __init__(self, name="no action", bonus_quadorder=0):
+        self.name, self.bonus_quadorder = name, bonus_quadorder
+
+
+class HookeAction:
+    """the tensor_apply_2d / tensor_apply_3d kernels of HookStiffnessOperator2D/3D
+    (pdeoperators.jl:265-270, 304-312), evaluated on the device"""
+
+    def __init__(self, dim, mu, lam):
+        self.code = 1 if dim == 2 else 2
+        self.params = np.array([mu, lam], dtype=np.float64)
+        self.argsizes = [3, 3] if dim == 2 else [6, 6]
+        self.bonus_quadorder = 0
+        self.name = "hooke tensor"
+
+
+class Action:
+    """Action(kernel, argsizes; ...) with a user closure (actions.jl:53-63) cannot cross the C ABI."""
+
+    def __init__(self, *a, **k):
+        raise NotImplementedError("arbitrary Action kernels are host closures; only NoAction and the Hooke tensors run on the device "
+                                  "(SURVEY.md 7, hard part 4). Use DataFunction for linear-form data.")
+
+
+class DataFunction:
+    """DataFunction(f, argsizes; dependencies, bonus_quadorder) (userdata.jl:35-63); `f` may be a
+    constant vector or a callable x -> values evaluated by the host at the quadrature points."""
+
+    def __init__(self, f, argsizes=None, dependencies="", bonus_quadorder=0, name="user data"):
+        self.name, self.bonus_quadorder = name, bonus_quadorder
+        if callable(f):
+            self.kernel, self.constant = f, None
+            self.argsizes = argsizes
+            self.dependencies = dependencies or "X"
+        else:
+            self.constant = np.atleast_1d(np.asarray(f, dtype=np.float64))
+            self.kernel = None
+            self.argsizes = [self.constant.size, 0]
+            self.dependencies = ""
+
+
+class _FDotAction:
+    """fdot_action(data) (actions.jl:119-128)"""
+    code = 0
+
+    def __init__(self, data: DataFunction):
+        self.data = data
+        self.bonus_quadorder = data.bonus_quadorder
+        self.name = data.name
+
+
+def fdot_action(data):
+    return _FDotAction(data)
+
+
+# ---- device mirrors of grid / space ---------------------------------------------------------------
+def device_grid(xgrid, need_faces=False):
+    L = _lib.lib()
+    d = getattr(xgrid, "_dev", None)
+    if d is None:
+        h = C.c_void_p()
+        vol = np.ascontiguousarray(xgrid.cellvolumes)
+        _lib.check(L.grmp_grid_create(_lib.context(), xgrid.dim, xgrid.nnodes, _lib.ptr(xgrid.coords), xgrid.ncells,
+                                      _lib.ptr(xgrid.cellnodes), _lib.ptr(vol), _lib.ptr(xgrid.cellregions), C.byref(h)))
+        d = {"h": h, "faces": False}
+        xgrid._dev = d
+    if need_faces and not d["faces"]:
+        ori = np.ascontiguousarray(xgrid.cellfaceorientations) if xgrid.dim == 3 else None
+        _lib.check(L.grmp_grid_set_faces(d["h"], xgrid.nfaces, _lib.ptr(xgrid.cellfaces), _lib.ptr(xgrid.cellfacesigns),
+                                         _lib.ptr(ori), _lib.ptr(xgrid.facenormals), _lib.ptr(xgrid.facevolumes)))
+        d["faces"] = True
+    return d["h"]
+
+
+def device_space(FES: FESpace):
+    need_faces = FES.fetype.code in (3, 4, 5)
+    gh = device_grid(FES.xgrid, need_faces)
+    d = getattr(FES, "_dev", None)
+    if d is None:
+        h = C.c_void_p()
+        dofs = FES.celldofs
+        _lib.check(_lib.lib().grmp_space_create(gh, FES.fetype.code, FES.fetype.ncomponents, FES.ndofs, dofs.shape[1], _lib.ptr(dofs),
+                                                C.byref(h)))
+        FES._dev = d = h
+    return d
+
+
+# ---- assembly patterns ---------------------------------------------------------------------------
+APT_BilinearForm, APT_SymmetricBilinearForm, APT_LumpedBilinearForm, APT_LinearForm = 0, 1, 2, 10
+
+
+class AssemblyPattern:
+    """AssemblyPattern{APT,T,AT} (assemblypatterns.jl:312-326), AT = ON_CELLS only"""
+
+    def __init__(self, APT, name, FES, operators, action, apply_action_to, regions):
+        self.APT, self.name, self.FES = APT, name, list(FES)
+        self.operators = [_op(o) for o in operators]
+        self.action, self.apply_action_to, self.regions = action, apply_action_to, list(regions)
+        self.last_allocations = 0
+        self.AM = None                      # prepared state (quadrature, tables, device handle)
+
+    def __repr__(self):
+        return f"AssemblyPattern({self.name}, {self.FES}, {self.operators})"
+
+
+def DiscreteBilinearForm(operators, FES, action=None, name="BLF", regions=(0,), apply_action_to=(1,)):
+    assert len(operators) == len(FES) == 2, "each FESpace needs an operator and vice versa"
+    assert list(apply_action_to) == [1], "the ported path applies the action to argument 1 (all operators on the path do)"
+    return AssemblyPattern(APT_BilinearForm, name, FES, operators, action or NoAction(), [1], regions)
+
+
+def DiscreteSymmetricBilinearForm(operators, FES, action=None, name="symBLF", regions=(0,), apply_action_to=(1,)):
+    assert len(operators) == len(FES) == 2, "each FESpace needs an operator and vice versa"
+    return AssemblyPattern(APT_SymmetricBilinearForm, name, FES, operators, action or NoAction(), [1], regions)
+
+
+def DiscreteLumpedBilinearForm(operators, FES, action=None, name="lumpedBLF", regions=(0,), apply_action_to=(1,)):
+    assert len(operators) == len(FES) == 2, "each FESpace needs an operator and vice versa"
+    return AssemblyPattern(APT_LumpedBilinearForm, name, FES, operators, action or NoAction(), [1], regions)
+
+
+def DiscreteLinearForm(operators, FES, action=None, name="LF", regions=(0,)):
+    assert len(operators) == len(FES), "each FESpace needs an operator and vice versa"
+    if len(FES) != 1:
+        raise NotImplementedError("LinearForms with FEB coefficient arguments are a 'next' row (SURVEY.md 8f N4)")
+    return AssemblyPattern(APT_LinearForm, name, FES, operators, action or NoAction(), [1], regions)
+
+
+def _geometry(xgrid):
+    return "Triangle2D" if xgrid.dim == 2 else "Tetrahedron3D"
+
+
+def _tables(FES: FESpace, op, qf):
+    """reference tables of FEEvaluator(FES, op, qf) as a grmp_evaltab (+ arrays kept alive)"""
+    edim = FES.xgrid.dim
+    fe = op.FETypeReconst if isinstance(op, ReconstructionIdentity) else FES.fetype
+    vals, der = reference_tables(fe, edim, qf.xref, op.needed_derivative > 0)
+    vals = np.ascontiguousarray(vals)
+    der = None if der is None else np.ascontiguousarray(der)
+    tab = _lib.EvalTab(fe.ndofs_all(edim), fe.ncomponents, _lib.ptr(vals), _lib.ptr(der))
+    return tab, (vals, der)
+
+
+class _Prepared:
+    pass
+
+
+def quadrature_order(AP: AssemblyPattern):
+    """assemblypatterns.jl:559-565"""
+    edim = AP.FES[0].xgrid.dim
+    q = AP.action.bonus_quadorder
+    for F, o in zip(AP.FES, AP.operators):
+        q += F.fetype.polynomialorder(edim) - o.needed_derivative
+    return max(q, 0)
+
+
+def prepare_assembly(AP: AssemblyPattern, transposed_assembly=False):
+    """prepare_assembly!(AP): quadrature rule, evaluator tables, device-side pattern object"""
+    L = _lib.lib()
+    P = _Prepared()
+    xgrid = AP.FES[0].xgrid
+    P.quadorder = quadrature_order(AP)
+    P.qf = QuadratureRule(_geometry(xgrid), P.quadorder)
+    P.keep = []
+    regions = np.ascontiguousarray(AP.regions, dtype=np.int32)
+    w = np.ascontiguousarray(P.qf.w)
+    h = C.c_void_p()
+    if AP.APT == APT_LinearForm:
+        sp = device_space(AP.FES[0])
+        tab, keep = _tables(AP.FES[0], AP.operators[0], P.qf)
+        P.keep.append(keep)
+        _lib.check(L.grmp_lf_create(sp, AP.operators[0].code, _lib.ptr(regions), regions.size, len(P.qf), _lib.ptr(w), C.byref(tab),
+                                    C.byref(h)))
+        P.kind = "lf"
+    else:
+        s1, s2 = device_space(AP.FES[0]), device_space(AP.FES[1])
+        t1, k1 = _tables(AP.FES[0], AP.operators[0], P.qf)
+        t2, k2 = _tables(AP.FES[1], AP.operators[1], P.qf)
+        P.keep += [k1, k2]
+        act = AP.action
+        if not isinstance(act, (NoAction, HookeAction)):
+            raise NotImplementedError("bilinear forms support NoAction and the Hooke tensor actions on the device")
+        _lib.check(L.grmp_blf_create(s1, s2, AP.operators[0].code, AP.operators[1].code, act.code, _lib.ptr(act.params), AP.APT,
+                                     int(bool(transposed_assembly)), _lib.ptr(regions), regions.size, len(P.qf), _lib.ptr(w), C.byref(t1), C.byref(t2), C.byref(h)))
+        P.kind = "blf"
+        P.have_pattern = False
+        P.transposed = bool(transposed_assembly) and AP.APT != APT_SymmetricBilinearForm
+    P.h = h
+    AP.AM = P
+    return P
+
+
+def blf_set_path(AP: AssemblyPattern, path: int):
+    if AP.AM is None:
+        prepare_assembly(AP)
+    _lib.check(_lib.lib().grmp_blf_set_path(AP.AM.h, path))
+
+
+def blf_stats(AP):
+    st = _lib.Stats()
+    fn = _lib.lib().grmp_blf_stats if AP.AM.kind == "blf" else _lib.lib().grmp_lf_stats
+    _lib.check(fn(AP.AM.h, C.byref(st)))
+    return st
+
+
+def assemble_csc(AP: AssemblyPattern, factor=1.0, skip_preps=False, transposed_assembly=False, fetch=True):
+    """numeric core of assemble!(A, AP): returns the operator's own CSC (colptr, rowval, nzval),
+    1-based Int64 -- SparseMatrixCSC{Float64,Int64} of a fresh ExtendableSparseMatrix after flush!."""
+    L = _lib.lib()
+    tr = bool(transposed_assembly) and AP.APT != APT_SymmetricBilinearForm
+    if AP.AM is None or AP.AM.kind != "blf" or AP.AM.transposed != tr:
+        prepare_assembly(AP, tr)        # transposed_assembly is a creation-time property of the device pattern
+    P = AP.AM
+    if not P.have_pattern or not skip_preps:
+        nnz = C.c_int64(0)
+        _lib.check(L.grmp_blf_symbolic(P.h, float(factor), C.byref(nnz)))
+        P.nnz = nnz.value
+        ncols = AP.FES[0].ndofs if P.transposed else AP.FES[1].ndofs
+        P.colptr = np.zeros(ncols + 1, np.int64)
+        P.rowval = np.zeros(P.nnz, np.int64)
+        _lib.check(L.grmp_blf_get_pattern(P.h, _lib.ptr(P.colptr), _lib.ptr(P.rowval)))
+        P.have_pattern = True
+    nzval = np.zeros(P.nnz) if fetch else None
+    _lib.check(L.grmp_blf_numeric(P.h, float(factor), _lib.ptr(nzval)))
+    return P.colptr, P.rowval, nzval
+
+
+def _embed(block: FEMatrixBlock, colptr, rowval, nzval):
+    """place a block CSC at (offsetX, offsetY) of the parent matrix"""
+    par = block.parent
+    cp = np.full(par.n + 1, 1, dtype=np.int64)
+    counts = np.zeros(par.n, np.int64)
+    counts[block.offsetY:block.last_indexY] = np.diff(colptr)
+    cp[1:] = 1 + np.cumsum(counts)
+    return cp, rowval + block.offsetX, nzval
+
+
+def assemble(target, AP: AssemblyPattern, FEB=(), factor=1, factor_transpose=None, transposed_assembly=False, transpose_copy=None,
+             skip_preps=False, fixed_arguments=None, offset=0, fdata=None):
+    """assemble!(A::FEMatrixBlock, AP; ...) / assemble!(b::FEVectorBlock | Vector, AP; ...)"""
+    if len(FEB) != 0:
+        raise NotImplementedError("assembly with FEB coefficient arguments is a 'next' row (SURVEY.md 8f N4)")
+    if AP.APT == APT_LinearForm:
+        return _assemble_lf(target, AP, factor=factor, skip_preps=skip_preps, offset=offset)
+    assert isinstance(target, FEMatrixBlock), "assemble into an FEMatrixBlock (A[j,k])"
+    tr = bool(transposed_assembly) and AP.APT != APT_SymmetricBilinearForm
+    fx, fy = (AP.FES[1], AP.FES[0]) if tr else (AP.FES[0], AP.FES[1])
+    assert target.FESX is fx and target.FESY is fy, "pattern spaces must match the block"
+    if tr and transpose_copy is not None:
+        raise NotImplementedError("transposed_assembly together with transpose_copy")
+    cp, rv, nz = assemble_csc(AP, factor, skip_preps, transposed_assembly)
+    target.parent.add_csc(*_embed(target, cp, rv, nz))
+    if transpose_copy is not None:
+        ft = factor if factor_transpose is None else factor_transpose
+        L = _lib.lib()
+        nrows = AP.FES[0].ndofs
+        cpt = np.zeros(nrows + 1, np.int64)
+        rvt = np.zeros(rv.size, np.int64)
+        nzt = np.zeros(rv.size)
+        _lib.check(L.grmp_blf_transpose_copy(AP.AM.h, float(factor), float(ft), _lib.ptr(cpt), _lib.ptr(rvt), _lib.ptr(nzt)))
+        assert isinstance(transpose_copy, FEMatrixBlock)
+        transpose_copy.parent.add_csc(*_embed(transpose_copy, cpt, rvt, nzt))
+    AP.last_allocations = 0
+    return None
+
+
+def _qp_table(AP, P):
+    """host evaluation of the DataFunction at x = b + A*xref (eval_trafo!, linearform.jl:197-201)"""
+    data = AP.action.data
+    g = AP.FES[0].xgrid
+    if data.constant is not None:
+        return 1, data.constant
+    x = g.coords
+    cn = g.cellnodes.astype(np.int64) - 1
+    b = x[cn[:, 0]]
+    xq = np.repeat(b[:, None, :], len(P.qf), axis=1).copy()
+    for j in range(g.dim):
+        Aj = x[cn[:, j + 1]] - b                     # column j of A
+        xq += Aj[:, None, :] * P.qf.xref[None, :, j, None]
+    flat = xq.reshape(-1, g.dim)
+    try:
+        vals = np.asarray(data.kernel(flat.T), dtype=np.float64)       # vectorised: f(x[dim, npts]) -> [ncomp, npts]
+        vals = vals.reshape(-1, flat.shape[0]).T
+    except Exception:
+        vals = np.array([np.atleast_1d(data.kernel(p)) for p in flat], dtype=np.float64)
+    return 2, np.ascontiguousarray(vals.reshape(g.ncells, len(P.qf), -1))
+
+
+def _assemble_lf(b, AP, factor=1, skip_preps=False, offset=0):
+    L = _lib.lib()
+    if AP.AM is None or not skip_preps:
+        if AP.AM is None or AP.AM.kind != "lf":
+            prepare_assembly(AP)
+    P = AP.AM
+    if isinstance(b, FEVectorBlock):
+        assert b.FES is AP.FES[0]
+        entries, offset = b.entries, b.offset
+    else:
+        entries = b
+    assert entries.dtype == np.float64 and entries.flags.c_contiguous
+    if isinstance(AP.action, _FDotAction):
+        fsrc, fd = _qp_table(AP, P)
+        rd = AP.operators[0]
+        if fd.shape[-1] != _resultdim(AP):
+            raise ValueError(f"data has {fd.shape[-1]} components, operator result has {_resultdim(AP)}")
+    elif isinstance(AP.action, NoAction):
+        fsrc, fd = 0, None
+    else:
+        raise NotImplementedError("linear forms support NoAction and fdot_action(DataFunction)")
+    _lib.check(L.grmp_lf_assemble(P.h, float(factor), fsrc, _lib.ptr(fd), _lib.ptr(entries), int(offset)))
+    AP.last_allocations = 0
+    return None
+
+
+def _resultdim(AP):
+    F, o = AP.FES[-1], AP.operators[-1]
+    edim, nc = F.xgrid.dim, F.fetype.ncomponents
+    return {1: nc, 5: nc, 6: nc, 2: edim * nc, 3: (3 if edim == 2 else 6), 4: max(1, nc // edim)}[o.code]

@@ -1,0 +1,473 @@
+// api.cu -- the C ABI of libgrmp_cuda (include/grmp.h): handles, uploads, dispatch.
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+#include "fastpath.cuh"
+#include "symbolic.cuh"
+
+namespace grmp {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+int op_resultdim(int op, int ncomp, int edim) {   // Length4Operator, src/functionoperators.jl:260-278
+  switch (op) {
+    case GRMP_OP_ID: case GRMP_OP_RECON_ID_RT0: case GRMP_OP_RECON_ID_BDM1: return ncomp;
+    case GRMP_OP_GRAD: return edim * ncomp;
+    case GRMP_OP_SYMGRAD: return ((edim == 2) ? 3 : 6) * ((ncomp + edim - 1) / edim);
+    case GRMP_OP_DIV: return (ncomp + edim - 1) / edim;
+  }
+  return -1;
+}
+
+static int fe_family(int fetype) {
+  switch (fetype) {
+    case GRMP_FE_H1P1: case GRMP_FE_H1P2: case GRMP_FE_L2P0: return FAM_H1;
+    case GRMP_FE_H1BR: return FAM_H1BR;
+    case GRMP_FE_HDIVRT0: return FAM_RT0;
+    case GRMP_FE_HDIVBDM1: return FAM_BDM1;
+  }
+  return -1;
+}
+
+static int fe_local_dofs(int fetype, int ncomp, int edim, int* nd, int* nd_all, int* ncomp_eff) {
+  const int nn = edim + 1, nf = edim + 1, ne = (edim == 2) ? 3 : 6;
+  *ncomp_eff = ncomp;
+  switch (fetype) {
+    case GRMP_FE_H1P1: *nd = *nd_all = nn * ncomp; return GRMP_OK;
+    case GRMP_FE_H1P2: *nd = *nd_all = (nn + ne) * ncomp; return GRMP_OK;
+    case GRMP_FE_H1BR: *ncomp_eff = edim; *nd = *nd_all = nf + nn * edim; return GRMP_OK;
+    case GRMP_FE_HDIVRT0: *ncomp_eff = edim; *nd = *nd_all = nf; return GRMP_OK;
+    case GRMP_FE_HDIVBDM1: *ncomp_eff = edim; *nd = edim * nf; *nd_all = (edim == 2) ? 2 * nf : 4 * nf; return GRMP_OK;
+    case GRMP_FE_L2P0: *nd = *nd_all = ncomp; return GRMP_OK;
+  }
+  return fail(GRMP_EUNSUPPORTED, "unknown FEType code");
+}
+
+int make_evalview(const grmp_space* sp, int op, const EvalTables& tab, EvalView* out) {
+  const int edim = sp->grid->dim;
+  EvalView e{};
+  int nd, nd_all, nc;
+  GRMP_TRY(fe_local_dofs(sp->fetype, sp->ncomp, edim, &nd, &nd_all, &nc));
+  e.fam = fe_family(sp->fetype);
+  e.op = op; e.ncomp = nc; e.nd = nd; e.nd_all = nd_all;
+  e.rd = op_resultdim(op, nc, edim);
+  if (e.rd < 0) return fail(GRMP_EUNSUPPORTED, "unknown operator code");
+  if (e.rd > 9) return fail(GRMP_EUNSUPPORTED, "operator result dimension > 9");
+  const bool hdiv = (e.fam == FAM_RT0 || e.fam == FAM_BDM1);
+  if (hdiv && !(op == GRMP_OP_ID || op == GRMP_OP_DIV)) return fail(GRMP_EUNSUPPORTED, "Hdiv elements: Identity / Divergence only");
+  if (sp->fetype == GRMP_FE_L2P0 && op != GRMP_OP_ID) return fail(GRMP_EUNSUPPORTED, "L2P0: Identity only");
+  if (op == GRMP_OP_SYMGRAD && nc != edim) return fail(GRMP_EINVAL, "SymmetricGradient requires ncomponents == dim");
+  const bool recon = (op == GRMP_OP_RECON_ID_RT0 || op == GRMP_OP_RECON_ID_BDM1);
+  if (recon && sp->fetype != GRMP_FE_H1BR) return fail(GRMP_EUNSUPPORTED, "ReconstructionIdentity is ported for H1BR only");
+  if ((hdiv || sp->fetype == GRMP_FE_H1BR) && !sp->grid->has_faces)
+    return fail(GRMP_ESTATE, "grid face data missing: call grmp_grid_set_faces first");
+  if (e.fam == FAM_BDM1 && edim == 3 && sp->grid->orient.n == 0) return fail(GRMP_ESTATE, "CellFaceOrientations missing (BDM1 3D)");
+  if (recon && op == GRMP_OP_RECON_ID_BDM1 && edim == 3 && sp->grid->orient.n == 0)
+    return fail(GRMP_ESTATE, "CellFaceOrientations missing (BR->BDM1 3D)");
+  e.tab_nd = nd_all; e.tab_nc = nc;
+  if (recon) {
+    e.rfam = (op == GRMP_OP_RECON_ID_RT0) ? FAM_RT0 : FAM_BDM1;
+    int nd2, nd2_all, nc2;
+    GRMP_TRY(fe_local_dofs(op == GRMP_OP_RECON_ID_RT0 ? GRMP_FE_HDIVRT0 : GRMP_FE_HDIVBDM1, edim, edim, &nd2, &nd2_all, &nc2));
+    e.nd2 = nd2; e.tab_nd = nd2_all; e.tab_nc = nc2;
+  }
+  if (tab.nd_all != e.tab_nd || tab.ncomp != e.tab_nc) return fail(GRMP_EINVAL, "evaluator table shape does not match FEType/operator");
+  const bool need_deriv = (op == GRMP_OP_GRAD || op == GRMP_OP_SYMGRAD || op == GRMP_OP_DIV);
+  if (need_deriv && tab.refderivs.n == 0) return fail(GRMP_EINVAL, "operator needs refderivs");
+  if (!need_deriv && tab.refvals.n == 0) return fail(GRMP_EINVAL, "operator needs refvals");
+  e.refvals = tab.refvals.p; e.refderivs = tab.refderivs.p;
+  e.celldofs = sp->celldofs.p;
+  *out = e;
+  return GRMP_OK;
+}
+
+static int upload_tables(const grmp_evaltab* t, int nq, int edim, cudaStream_t s, EvalTables* out) {
+  if (!t) return fail(GRMP_EINVAL, "evaluator table missing");
+  out->nd_all = t->nd_all; out->ncomp = t->ncomp;
+  if (t->refvals) GRMP_TRY(out->refvals.upload(t->refvals, (size_t)nq * t->nd_all * t->ncomp, s));
+  if (t->refderivs) GRMP_TRY(out->refderivs.upload(t->refderivs, (size_t)nq * edim * t->nd_all * t->ncomp, s));
+  return GRMP_OK;
+}
+
+static int make_regions(const int32_t* regions, int nregions, RegionFilter* r) {
+  r->n = 0;
+  if (nregions <= 0 || !regions || (nregions == 1 && regions[0] == 0)) return GRMP_OK;   // regions == [0]
+  if (nregions > 8) return fail(GRMP_EUNSUPPORTED, "more than 8 regions");
+  r->n = nregions;
+  for (int k = 0; k < nregions; k++) r->r[k] = regions[k];
+  return GRMP_OK;
+}
+
+}  // namespace grmp
+
+using namespace grmp;
+
+GridView grmp_grid::view() const {
+  GridView v{};
+  v.dim = dim; v.nnodes = nnodes; v.ncells = ncells; v.nfaces = nfaces;
+  v.coords = coords.p; v.cellnodes = cellnodes.p; v.vol = vol.p; v.regions = has_regions ? regions.p : nullptr;
+  v.cellfaces = cellfaces.p; v.signs = signs.p; v.orient = orient.p; v.fnormals = fnormals.p; v.fvol = fvol.p;
+  return v;
+}
+
+struct grmp_blf {
+  grmp_space *s1, *s2;
+  int op1, op2, action, apt, transposed, nq, path_req = GRMP_PATH_AUTO, path = 0;
+  double act_p[2] = {0, 0};
+  RegionFilter reg;
+  bool same_eval;
+  DevBuf<double> w;
+  EvalTables t1, t2;
+  std::vector<double> w_host;
+  std::vector<double> t1_derivs_host;     // kept for the fast path's reference integrals
+  Pattern pat;
+  bool have_pattern = false, have_values = false;
+  DevBuf<double> lbuf, nzval;
+  FastP2Tet fast;
+  grmp_stats st{};
+  i64 out_rows() const { return (apt != GRMP_APT_SYMMETRIC && transposed) ? s2->ndofs : s1->ndofs; }
+  i64 out_cols() const { return (apt != GRMP_APT_SYMMETRIC && transposed) ? s1->ndofs : s2->ndofs; }
+};
+
+struct grmp_lf {
+  grmp_space* sp;
+  int op, nq;
+  RegionFilter reg;
+  DevBuf<double> w, lbuf, b, fdata;
+  DevBuf<unsigned char> active;
+  EvalTables tab;
+  DofGather dg;
+  grmp_stats st{};
+};
+
+static int fill_blf_params(grmp_blf* b, double factor, BlfLocalParams* p) {
+  p->g = b->s1->grid->view();
+  GRMP_TRY(make_evalview(b->s1, b->op1, b->t1, &p->e1));
+  if (b->same_eval) p->e2 = p->e1; else GRMP_TRY(make_evalview(b->s2, b->op2, b->t2, &p->e2));
+  p->same_eval = b->same_eval ? 1 : 0;
+  p->action = b->action; p->act_p[0] = b->act_p[0]; p->act_p[1] = b->act_p[1];
+  p->apt = b->apt; p->transposed = b->transposed; p->reg = b->reg; p->nq = b->nq; p->w = b->w.p; p->factor = factor;
+  p->nrows_key = b->out_rows();
+  p->keys = nullptr; p->lbuf = nullptr;
+  return GRMP_OK;
+}
+
+extern "C" {
+
+const char* grmp_last_error(void) { return g_err.c_str(); }
+
+int grmp_init(int device, grmp_ctx** out) {
+  if (!out) return fail(GRMP_EINVAL, "out == NULL");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(GRMP_ECUDA, std::string("no CUDA device available (the assembly path has no CPU fallback): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(GRMP_EINVAL, "device index out of range");
+  GRMP_CUDA(cudaSetDevice(device));
+  grmp_ctx* c = new grmp_ctx();
+  c->device = device;
+  GRMP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  GRMP_CUDA(cudaEventCreate(&c->ev0));
+  GRMP_CUDA(cudaEventCreate(&c->ev1));
+  cudaDeviceProp prop;
+  GRMP_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  *out = c;
+  return GRMP_OK;
+}
+
+int grmp_finalize(grmp_ctx* ctx) {
+  if (!ctx) return GRMP_OK;
+  cudaStreamSynchronize(ctx->stream);
+  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return GRMP_OK;
+}
+
+int grmp_device_synchronize(grmp_ctx* ctx) {
+  if (!ctx) return fail(GRMP_EINVAL, "ctx == NULL");
+  GRMP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GRMP_OK;
+}
+
+int grmp_grid_create(grmp_ctx* ctx, int dim, int64_t nnodes, const double* coords, int64_t ncells, const int32_t* cellnodes,
+                     const double* cellvolumes, const int32_t* cellregions, grmp_grid** out) {
+  if (!ctx || !out || !coords || !cellnodes || !cellvolumes) return fail(GRMP_EINVAL, "grmp_grid_create: NULL argument");
+  if (dim != 2 && dim != 3) return fail(GRMP_EUNSUPPORTED, "only Triangle2D / Tetrahedron3D grids are on the ported path");
+  if (nnodes < 0 || ncells < 0) return fail(GRMP_EINVAL, "negative size");
+  GRMP_CUDA(cudaSetDevice(ctx->device));
+  grmp_grid* g = new grmp_grid();
+  g->ctx = ctx; g->dim = dim; g->nnodes = nnodes; g->ncells = ncells; g->nfaces = 0;
+  int rc = g->coords.upload(coords, (size_t)nnodes * dim, ctx->stream);
+  if (!rc) rc = g->cellnodes.upload(cellnodes, (size_t)ncells * (dim + 1), ctx->stream);
+  if (!rc) rc = g->vol.upload(cellvolumes, (size_t)ncells, ctx->stream);
+  if (!rc && cellregions) { rc = g->regions.upload(cellregions, (size_t)ncells, ctx->stream); g->has_regions = true; }
+  if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(GRMP_ECUDA, "upload failed");
+  if (rc) { delete g; return rc; }
+  *out = g;
+  return GRMP_OK;
+}
+
+int grmp_grid_set_faces(grmp_grid* g, int64_t nfaces, const int32_t* cellfaces, const int32_t* cellfacesigns,
+                        const int32_t* cellfaceorient, const double* facenormals, const double* facevolumes) {
+  if (!g || !cellfaces || !cellfacesigns || !facenormals || !facevolumes) return fail(GRMP_EINVAL, "grmp_grid_set_faces: NULL argument");
+  cudaStream_t s = g->ctx->stream;
+  const size_t nf = g->dim + 1;
+  GRMP_TRY(g->cellfaces.upload(cellfaces, (size_t)g->ncells * nf, s));
+  GRMP_TRY(g->signs.upload(cellfacesigns, (size_t)g->ncells * nf, s));
+  if (cellfaceorient) GRMP_TRY(g->orient.upload(cellfaceorient, (size_t)g->ncells * nf, s));
+  GRMP_TRY(g->fnormals.upload(facenormals, (size_t)nfaces * g->dim, s));
+  GRMP_TRY(g->fvol.upload(facevolumes, (size_t)nfaces, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  g->nfaces = nfaces; g->has_faces = true;
+  return GRMP_OK;
+}
+
+int grmp_grid_update_geometry(grmp_grid* g, const double* coords, const double* cellvolumes) {
+  if (!g || !coords || !cellvolumes) return fail(GRMP_EINVAL, "grmp_grid_update_geometry: NULL argument");
+  cudaStream_t s = g->ctx->stream;
+  GRMP_TRY(g->coords.upload(coords, (size_t)g->nnodes * g->dim, s));
+  GRMP_TRY(g->vol.upload(cellvolumes, (size_t)g->ncells, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  return GRMP_OK;
+}
+
+int grmp_grid_destroy(grmp_grid* g) { delete g; return GRMP_OK; }
+
+int grmp_space_create(grmp_grid* grid, int fetype, int ncomp, int64_t ndofs, int nd_cell, const int32_t* celldofs, grmp_space** out) {
+  if (!grid || !celldofs || !out) return fail(GRMP_EINVAL, "grmp_space_create: NULL argument");
+  int nd, nd_all, nc;
+  GRMP_TRY(fe_local_dofs(fetype, ncomp, grid->dim, &nd, &nd_all, &nc));
+  if (nd != nd_cell) return fail(GRMP_EINVAL, "nd_cell does not match the FEType on this geometry");
+  grmp_space* s = new grmp_space();
+  s->grid = grid; s->fetype = fetype; s->ncomp = ncomp; s->nd = nd; s->ndofs = ndofs;
+  int rc = s->celldofs.upload(celldofs, (size_t)grid->ncells * nd, grid->ctx->stream);
+  if (!rc && cudaStreamSynchronize(grid->ctx->stream) != cudaSuccess) rc = fail(GRMP_ECUDA, "upload failed");
+  if (rc) { delete s; return rc; }
+  *out = s;
+  return GRMP_OK;
+}
+int grmp_space_destroy(grmp_space* s) { delete s; return GRMP_OK; }
+
+int grmp_blf_create(grmp_space* s1, grmp_space* s2, int op1, int op2, int action, const double* act_params, int apt,
+                    int transposed_assembly, const int32_t* regions, int nregions, int nq, const double* qweights,
+                    const grmp_evaltab* tab1, const grmp_evaltab* tab2, grmp_blf** out) {
+  if (!s1 || !s2 || !qweights || !tab1 || !out || nq <= 0) return fail(GRMP_EINVAL, "grmp_blf_create: bad argument");
+  if (s1->grid != s2->grid) return fail(GRMP_EINVAL, "spaces live on different grids");
+  if (apt < 0 || apt > 2) return fail(GRMP_EINVAL, "unknown assembly pattern type");
+  if (action != GRMP_ACT_NONE && !act_params) return fail(GRMP_EINVAL, "action parameters missing");
+  grmp_blf* b = new grmp_blf();
+  cudaStream_t st = s1->grid->ctx->stream;
+  b->s1 = s1; b->s2 = s2; b->op1 = op1; b->op2 = op2; b->action = action; b->apt = apt; b->transposed = transposed_assembly ? 1 : 0;
+  b->nq = nq;
+  if (act_params) { b->act_p[0] = act_params[0]; b->act_p[1] = act_params[1]; }
+  b->same_eval = (s1 == s2 && op1 == op2);
+  int rc = make_regions(regions, nregions, &b->reg);
+  if (!rc) rc = b->w.upload(qweights, nq, st);
+  b->w_host.assign(qweights, qweights + nq);
+  if (!rc) rc = upload_tables(tab1, nq, s1->grid->dim, st, &b->t1);
+  if (!rc && tab1->refderivs) b->t1_derivs_host.assign(tab1->refderivs, tab1->refderivs + (size_t)nq * s1->grid->dim * tab1->nd_all * tab1->ncomp);
+  if (!rc && !b->same_eval) rc = upload_tables(tab2 ? tab2 : tab1, nq, s1->grid->dim, st, &b->t2);
+  BlfLocalParams p;
+  if (!rc) rc = fill_blf_params(b, 1.0, &p);   // validates the combination
+  if (!rc) {
+    const int ar = (action == GRMP_ACT_NONE) ? p.e1.rd : (action == GRMP_ACT_HOOKE2D ? 3 : 6);
+    if (action != GRMP_ACT_NONE && p.e1.rd != ar) rc = fail(GRMP_EINVAL, "action input size does not match the operator");
+    else if (ar != p.e2.rd) rc = fail(GRMP_EINVAL, "operator result dimensions do not match");
+    else if (apt == GRMP_APT_SYMMETRIC && p.e1.nd != p.e2.nd) rc = fail(GRMP_EINVAL, "symmetric form needs equal local dof counts");
+  }
+  if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(GRMP_ECUDA, "upload failed");
+  if (rc) { delete b; return rc; }
+  *out = b;
+  return GRMP_OK;
+}
+
+int grmp_blf_destroy(grmp_blf* b) { delete b; return GRMP_OK; }
+
+int grmp_blf_set_path(grmp_blf* b, int path) {
+  if (!b || path < 0 || path > 2) return fail(GRMP_EINVAL, "grmp_blf_set_path: bad argument");
+  b->path_req = path;
+  return GRMP_OK;
+}
+
+int grmp_blf_symbolic(grmp_blf* b, double factor, int64_t* nnz_out) {
+  if (!b) return fail(GRMP_EINVAL, "blf == NULL");
+  grmp_ctx* ctx = b->s1->grid->ctx;
+  cudaStream_t s = ctx->stream;
+  GRMP_CUDA(cudaSetDevice(ctx->device));
+  BlfLocalParams p;
+  GRMP_TRY(fill_blf_params(b, factor, &p));
+  const i64 ncells = p.g.ncells;
+  const int nloc = p.e1.nd * p.e2.nd;
+  const bool fast_ok = fast_p2tet_applicable(p);
+  if (b->path_req == GRMP_PATH_FAST && !fast_ok) return fail(GRMP_EUNSUPPORTED, "no fast path for this form");
+  const bool want_fast = fast_ok && b->path_req != GRMP_PATH_GENERIC;
+  GRMP_CUDA(cudaEventRecord(ctx->ev0, s));
+  DevBuf<u64> keys;
+  GRMP_TRY(keys.alloc((size_t)ncells * nloc));
+  p.keys = keys.p;
+  GRMP_TRY(launch_blf_local(p, s));
+  GRMP_TRY(build_pattern(s, keys, ncells * nloc, b->out_rows(), b->out_cols(), ncells, p.e1.nd, p.e2.nd, b->apt == GRMP_APT_SYMMETRIC,
+                         want_fast, &b->pat));
+  GRMP_TRY(b->nzval.alloc(b->pat.nnz));
+  b->path = GRMP_PATH_GENERIC;
+  if (want_fast) {
+    GRMP_TRY(fast_p2tet_build(ctx, p, b->pat, b->w_host, b->t1_derivs_host, &b->fast));
+    b->pat.slotmap.release();
+    b->path = GRMP_PATH_FAST;
+  }
+  GRMP_CUDA(cudaEventRecord(ctx->ev1, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  b->st.last_symbolic_ms = ms; b->st.nnz = b->pat.nnz; b->st.ncontrib = b->pat.ncontrib; b->st.path = b->path;
+  b->st.ntiles = b->fast.ntiles;
+  b->have_pattern = true; b->have_values = false;
+  if (nnz_out) *nnz_out = b->pat.nnz;
+  return GRMP_OK;
+}
+
+int grmp_blf_get_pattern(grmp_blf* b, int64_t* colptr, int64_t* rowval) {
+  if (!b || !colptr || (!rowval && b->pat.nnz)) return fail(GRMP_EINVAL, "grmp_blf_get_pattern: NULL argument");
+  if (!b->have_pattern) return fail(GRMP_ESTATE, "grmp_blf_symbolic has not been called");
+  cudaStream_t s = b->s1->grid->ctx->stream;
+  GRMP_CUDA(cudaMemcpyAsync(colptr, b->pat.colptr.p, (size_t)(b->pat.ncols + 1) * 8, cudaMemcpyDeviceToHost, s));
+  if (b->pat.nnz) GRMP_CUDA(cudaMemcpyAsync(rowval, b->pat.rowval.p, (size_t)b->pat.nnz * 8, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  return GRMP_OK;
+}
+
+int grmp_blf_numeric(grmp_blf* b, double factor, double* nzval_host) {
+  if (!b) return fail(GRMP_EINVAL, "blf == NULL");
+  if (!b->have_pattern) return fail(GRMP_ESTATE, "grmp_blf_symbolic has not been called");
+  grmp_ctx* ctx = b->s1->grid->ctx;
+  cudaStream_t s = ctx->stream;
+  GRMP_CUDA(cudaSetDevice(ctx->device));
+  BlfLocalParams p;
+  GRMP_TRY(fill_blf_params(b, factor, &p));
+  GRMP_CUDA(cudaEventRecord(ctx->ev0, s));
+  if (b->path == GRMP_PATH_FAST) {
+    GRMP_TRY(fast_p2tet_numeric(ctx, p, b->pat, b->fast, b->nzval.p));
+    b->st.kernel_launches = 1;
+  } else {
+    const size_t nl = (size_t)p.e1.nd * p.e2.nd * p.g.ncells;
+    if (b->lbuf.n != nl) GRMP_TRY(b->lbuf.alloc(nl));
+    p.lbuf = b->lbuf.p;
+    GRMP_TRY(launch_blf_local(p, s));
+    GRMP_TRY(launch_gather(s, b->pat, b->lbuf.p, b->nzval.p));
+    b->st.kernel_launches = 2;
+  }
+  GRMP_CUDA(cudaEventRecord(ctx->ev1, s));
+  if (nzval_host && b->pat.nnz) GRMP_CUDA(cudaMemcpyAsync(nzval_host, b->nzval.p, (size_t)b->pat.nnz * 8, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  b->st.last_numeric_ms = ms;
+  b->have_values = true;
+  return GRMP_OK;
+}
+
+int grmp_blf_get_values(grmp_blf* b, double* nzval_host) {
+  if (!b || (!nzval_host && b->pat.nnz)) return fail(GRMP_EINVAL, "grmp_blf_get_values: NULL argument");
+  if (!b->have_values) return fail(GRMP_ESTATE, "grmp_blf_numeric has not been called");
+  cudaStream_t s = b->s1->grid->ctx->stream;
+  if (b->pat.nnz) GRMP_CUDA(cudaMemcpyAsync(nzval_host, b->nzval.p, (size_t)b->pat.nnz * 8, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  return GRMP_OK;
+}
+
+int grmp_blf_transpose_copy(grmp_blf* b, double factor, double factor_transpose, int64_t* colptr_t, int64_t* rowval_t, double* nzval_t) {
+  if (!b || !colptr_t) return fail(GRMP_EINVAL, "grmp_blf_transpose_copy: NULL argument");
+  if (!b->have_values || b->path != GRMP_PATH_GENERIC || b->lbuf.n == 0)
+    return fail(GRMP_ESTATE, "transpose copy needs a prior generic-path grmp_blf_numeric with the same factor");
+  if (b->apt == GRMP_APT_SYMMETRIC) return fail(GRMP_EUNSUPPORTED, "transpose_copy is only assembled by the general branch (bilinearform.jl:347-367)");
+  cudaStream_t s = b->s1->grid->ctx->stream;
+  DevBuf<i64> cpt, rvt; DevBuf<i32> perm; DevBuf<double> tv, tvp;
+  GRMP_TRY(build_transposed(s, b->pat, cpt, rvt, perm));
+  GRMP_TRY(tv.alloc(b->pat.nnz)); GRMP_TRY(tvp.alloc(b->pat.nnz));
+  GRMP_TRY(launch_gather_transposed(s, b->pat, b->lbuf.p, factor, factor_transpose, tv.p));
+  GRMP_TRY(launch_permute(s, tv.p, perm.p, b->pat.nnz, tvp.p));
+  GRMP_CUDA(cudaMemcpyAsync(colptr_t, cpt.p, (size_t)(b->pat.nrows + 1) * 8, cudaMemcpyDeviceToHost, s));
+  if (b->pat.nnz) {
+    GRMP_CUDA(cudaMemcpyAsync(rowval_t, rvt.p, (size_t)b->pat.nnz * 8, cudaMemcpyDeviceToHost, s));
+    GRMP_CUDA(cudaMemcpyAsync(nzval_t, tvp.p, (size_t)b->pat.nnz * 8, cudaMemcpyDeviceToHost, s));
+  }
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  return GRMP_OK;
+}
+
+int grmp_blf_stats(grmp_blf* b, grmp_stats* out) {
+  if (!b || !out) return fail(GRMP_EINVAL, "NULL argument");
+  *out = b->st;
+  return GRMP_OK;
+}
+
+int grmp_blf_device_values(grmp_blf* b, void** dptr) {
+  if (!b || !dptr) return fail(GRMP_EINVAL, "NULL argument");
+  *dptr = b->nzval.p;
+  return GRMP_OK;
+}
+
+int grmp_lf_create(grmp_space* sp, int op, const int32_t* regions, int nregions, int nq, const double* qweights, const grmp_evaltab* tab,
+                   grmp_lf** out) {
+  if (!sp || !qweights || !tab || !out || nq <= 0) return fail(GRMP_EINVAL, "grmp_lf_create: bad argument");
+  grmp_lf* l = new grmp_lf();
+  cudaStream_t s = sp->grid->ctx->stream;
+  l->sp = sp; l->op = op; l->nq = nq;
+  int rc = make_regions(regions, nregions, &l->reg);
+  if (!rc) rc = l->w.upload(qweights, nq, s);
+  if (!rc) rc = upload_tables(tab, nq, sp->grid->dim, s, &l->tab);
+  EvalView e;
+  if (!rc) rc = make_evalview(sp, op, l->tab, &e);
+  if (!rc) rc = build_dofgather(s, sp->celldofs.p, sp->grid->ncells, sp->nd, sp->ndofs, &l->dg);
+  if (!rc) rc = l->lbuf.alloc((size_t)sp->nd * sp->grid->ncells);
+  if (!rc) rc = l->active.alloc((size_t)sp->grid->ncells);
+  if (!rc) rc = l->b.alloc((size_t)sp->ndofs);
+  if (!rc && cudaStreamSynchronize(s) != cudaSuccess) rc = fail(GRMP_ECUDA, "upload failed");
+  if (rc) { delete l; return rc; }
+  *out = l;
+  return GRMP_OK;
+}
+int grmp_lf_destroy(grmp_lf* l) { delete l; return GRMP_OK; }
+
+int grmp_lf_assemble(grmp_lf* l, double factor, int fsrc, const double* fdata, double* b_host, int64_t offset) {
+  if (!l || !b_host) return fail(GRMP_EINVAL, "grmp_lf_assemble: NULL argument");
+  if (fsrc != GRMP_F_NONE && !fdata) return fail(GRMP_EINVAL, "fdata missing");
+  grmp_space* sp = l->sp;
+  grmp_ctx* ctx = sp->grid->ctx;
+  cudaStream_t s = ctx->stream;
+  GRMP_CUDA(cudaSetDevice(ctx->device));
+  LfLocalParams p{};
+  p.g = sp->grid->view();
+  GRMP_TRY(make_evalview(sp, l->op, l->tab, &p.e));
+  p.reg = l->reg; p.nq = l->nq; p.w = l->w.p; p.factor = factor; p.fsrc = fsrc;
+  if (fsrc == GRMP_F_CONST) GRMP_TRY(l->fdata.upload(fdata, (size_t)p.e.rd, s));
+  else if (fsrc == GRMP_F_QP_TABLE) GRMP_TRY(l->fdata.upload(fdata, (size_t)sp->grid->ncells * l->nq * p.e.rd, s));
+  p.fdata = l->fdata.p; p.lbuf = l->lbuf.p; p.active = l->active.p;
+  GRMP_CUDA(cudaMemcpyAsync(l->b.p, b_host + offset, (size_t)sp->ndofs * 8, cudaMemcpyHostToDevice, s));
+  GRMP_CUDA(cudaEventRecord(ctx->ev0, s));
+  GRMP_TRY(launch_lf_local(p, s));
+  GRMP_TRY(launch_lf_gather(s, l->dg, l->lbuf.p, l->active.p, l->b.p));
+  GRMP_CUDA(cudaEventRecord(ctx->ev1, s));
+  GRMP_CUDA(cudaMemcpyAsync(b_host + offset, l->b.p, (size_t)sp->ndofs * 8, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  l->st.last_numeric_ms = ms; l->st.kernel_launches = 2; l->st.path = GRMP_PATH_GENERIC;
+  return GRMP_OK;
+}
+
+int grmp_lf_stats(grmp_lf* l, grmp_stats* out) {
+  if (!l || !out) return fail(GRMP_EINVAL, "NULL argument");
+  *out = l->st;
+  return GRMP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,27 @@
+// fastpath.cuh -- owner-computes roofline kernel for the metric configuration
+// (3D P2 Laplace stiffness, BASELINE.json): see fastpath_p2tet.cu
+#pragma once
+#include "common.cuh"
+#include "symbolic.cuh"
+
+namespace grmp {
+
+struct FastP2Tet {
+  int ntiles = 0;
+  i64 npairs = 0;
+  int smem_bytes = 0;
+  int max_tile_cells = 0;
+  DevBuf<i32> tile_colbeg;     // [ntiles+1] first (permuted) column of a tile
+  DevBuf<i32> tile_cellbeg;    // [ntiles+1] range into tile_cells
+  DevBuf<i32> tile_cells;      // distinct cells of every tile
+  DevBuf<i64> col_pairbeg;     // [ncols+1] pairs of a column
+  DevBuf<uint4> pairs;         // packed (local cell, permutation, 10 slot offsets)
+  DevBuf<double> ktab;         // reference integrals
+};
+
+bool fast_p2tet_applicable(const BlfLocalParams& p);
+int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const std::vector<double>& w,
+                     const std::vector<double>& derivs, FastP2Tet* out);
+int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const FastP2Tet& f, double* nzval);
+
+}  // namespace grmp

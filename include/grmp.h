@@ -1,0 +1,162 @@
+/* grmp.h -- C ABI of libgrmp_cuda, the B200-native replacement for the assembly hot path
+ * of GradientRobustMultiPhysics.jl (BilinearForm / LinearForm AssemblyPatterns).
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * reference repository).  The Julia glue that binds these with `ccall` is shown in
+ * INTEGRATION.md / julia/GRMPCuda.jl; the in-container binding is ctypes
+ * (gradientrobustmultiphysics.jl_b200/_lib.py).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all host arrays are owned by the caller and copied
+ *     to the device inside the call; outputs are written into caller-allocated arrays.
+ *   - indices on the wire are 1-based and laid out like Julia's column-major arrays
+ *     (Coordinates dim x nnodes, CellNodes (dim+1) x ncells, CellDofs nd x ncells, ...):
+ *     grid integers Int32 (ExtendableGrid{Float64,Int32}), matrix indices Int64
+ *     (FEMatrix{Float64,Int64}, src/fematrix.jl:148-150).
+ *   - every function returns 0 on success or a negative GRMP_E* code; the message is
+ *     available from grmp_last_error() (thread-local).  Nothing throws or aborts.
+ *   - calls are synchronous (the stream is synchronised before returning) unless the
+ *     name ends in _async.
+ *   - one context per process and device (one process per GPU; multi-GPU runs shard
+ *     cells/columns over ranks on the host side, see DESIGN.md "multi-GPU").
+ */
+#ifndef GRMP_H
+#define GRMP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRMP_OK 0
+#define GRMP_EINVAL (-1)       /* bad argument */
+#define GRMP_EUNSUPPORTED (-2) /* element / operator / action combination not on the ported path */
+#define GRMP_ECUDA (-3)        /* CUDA runtime error (message carries cudaGetErrorString) */
+#define GRMP_ENOMEM (-4)
+#define GRMP_ESTATE (-5)       /* call order violated (e.g. numeric before symbolic) */
+
+/* FEType codes (src/fedefs/{h1_p1,h1_p2,h1v_br,hdiv_rt0,hdiv_bdm1,l2_p0}.jl) */
+enum { GRMP_FE_H1P1 = 1, GRMP_FE_H1P2 = 2, GRMP_FE_H1BR = 3, GRMP_FE_HDIVRT0 = 4, GRMP_FE_HDIVBDM1 = 5, GRMP_FE_L2P0 = 6 };
+/* function operators (src/functionoperators.jl:13-153) */
+enum { GRMP_OP_ID = 1, GRMP_OP_GRAD = 2, GRMP_OP_SYMGRAD = 3, GRMP_OP_DIV = 4, GRMP_OP_RECON_ID_RT0 = 5, GRMP_OP_RECON_ID_BDM1 = 6 };
+/* actions evaluated on the device (src/actions.jl:96-110 NoAction; src/pdeoperators.jl:265-270, 304-312 Hooke tensors) */
+enum { GRMP_ACT_NONE = 0, GRMP_ACT_HOOKE2D = 1, GRMP_ACT_HOOKE3D = 2 };
+/* assembly pattern types (src/assemblypatterns/bilinearform.jl:7-21) */
+enum { GRMP_APT_BILINEARFORM = 0, GRMP_APT_SYMMETRIC = 1, GRMP_APT_LUMPED = 2 };
+/* right-hand side data of a LinearForm (fdot_action, src/actions.jl:119-128) */
+enum { GRMP_F_NONE = 0, GRMP_F_CONST = 1, GRMP_F_QP_TABLE = 2 };
+/* numeric back ends of a bilinear form */
+enum { GRMP_PATH_AUTO = 0, GRMP_PATH_GENERIC = 1, GRMP_PATH_FAST = 2 };
+
+typedef struct grmp_ctx grmp_ctx;
+typedef struct grmp_grid grmp_grid;
+typedef struct grmp_space grmp_space;
+typedef struct grmp_blf grmp_blf;
+typedef struct grmp_lf grmp_lf;
+
+/* Reference-cell tables of one FEEvaluator (src/feevaluator.jl:34-138; reconstruction
+ * constructor 142-217): in production they are taken from the Julia FEEvaluator
+ * (`refbasisvals`, `refbasisderivvals`), so ForwardDiff's bits travel unchanged.
+ *   refvals   [nq][nd_all][ncomp]            (refbasisvals[i][dof,comp]); for the
+ *             ReconstructionIdentity operators: values of the Hdiv reconstruction basis
+ *   refderivs [nq][edim][nd_all*ncomp]       (refbasisderivvals[dof+comp*nd_all, j, i]);
+ *             NULL for operators that need no derivatives */
+typedef struct grmp_evaltab {
+  int32_t nd_all;
+  int32_t ncomp;
+  const double* refvals;
+  const double* refderivs;
+} grmp_evaltab;
+
+/* timing / traffic counters of the last numeric call on a handle (the
+ * library-side analogue of AP.last_allocations / SC.LHS_AssemblyTimes) */
+typedef struct grmp_stats {
+  double last_numeric_ms;   /* CUDA-event time of the last numeric phase */
+  double last_symbolic_ms;
+  int64_t nnz;
+  int64_t ncontrib;         /* non-zero local contributions kept by the symbolic pass */
+  int64_t kernel_launches;  /* kernels launched by the last numeric call */
+  int32_t path;             /* GRMP_PATH_GENERIC or GRMP_PATH_FAST actually used */
+  int32_t ntiles;
+} grmp_stats;
+
+const char* grmp_last_error(void);
+
+/* context: selects the device, creates the stream */
+int grmp_init(int device, grmp_ctx** out);
+int grmp_finalize(grmp_ctx* ctx);
+int grmp_device_synchronize(grmp_ctx* ctx);
+
+/* Device-resident grid: what the assembly loop reads from `xgrid`
+ * (bilinearform.jl:113-114: CellVolumes, CellRegions; feevaluator.jl:371-390: Coordinates,
+ * CellNodes through the L2GTransformer).  cellregions may be NULL (all 1). */
+int grmp_grid_create(grmp_ctx* ctx, int dim, int64_t nnodes, const double* coords, int64_t ncells,
+                     const int32_t* cellnodes, const double* cellvolumes, const int32_t* cellregions,
+                     grmp_grid** out);
+/* CellFaces / CellFaceSigns / CellFaceOrientations / FaceNormals / FaceVolumes
+ * (hdiv_rt0.jl:106-116, hdiv_bdm1.jl coefficient + subset closures, h1v_br.jl:150-162,
+ * 253-273, reconstructions.jl:27-30).  cellfaceorient may be NULL in 2D. */
+int grmp_grid_set_faces(grmp_grid* grid, int64_t nfaces, const int32_t* cellfaces, const int32_t* cellfacesigns,
+                        const int32_t* cellfaceorient, const double* facenormals, const double* facevolumes);
+/* re-upload coordinates / volumes of an existing grid (moving meshes, the e2e bench step) */
+int grmp_grid_update_geometry(grmp_grid* grid, const double* coords, const double* cellvolumes);
+int grmp_grid_destroy(grmp_grid* grid);
+
+/* FESpace + CellDofs (src/finiteelements.jl:42-49, src/dofmaps.jl:201-363): the dof map is
+ * produced by the host (Julia: FES[CellDofs].colentries) */
+int grmp_space_create(grmp_grid* grid, int fetype, int ncomp, int64_t ndofs, int nd_cell, const int32_t* celldofs,
+                      grmp_space** out);
+int grmp_space_destroy(grmp_space* space);
+
+/* AssemblyPattern{APT_BilinearForm...} + prepare_assembly! (bilinearform.jl:60-64,
+ * assemblypatterns.jl:467-671): operators, action, regions, quadrature weights
+ * (qf.w, nq of them) and the evaluator tables for both arguments.
+ * space_row/op_row is the first ("ansatz", matrix row) argument: FES = [A.FESX, A.FESY]
+ * (pdeoperators.jl:926-927).  transposed_assembly swaps row/column on output
+ * (bilinearform.jl:353-357). */
+int grmp_blf_create(grmp_space* space_row, grmp_space* space_col, int op_row, int op_col, int action,
+                    const double* act_params, int apt, int transposed_assembly, const int32_t* regions, int nregions,
+                    int nq, const double* qweights, const grmp_evaltab* tab_row, const grmp_evaltab* tab_col,
+                    grmp_blf** out);
+int grmp_blf_destroy(grmp_blf* blf);
+/* choose the numeric back end before grmp_blf_symbolic (default GRMP_PATH_AUTO: the fast
+ * owner-computes kernel where one exists for the form, else the generic two-phase path) */
+int grmp_blf_set_path(grmp_blf* blf, int path);
+
+/* One-time symbolic pass on the GPU = what rawupdateindex! + flush! build on first
+ * assembly (fematrix.jl:54-58, pdeoperators.jl:992): the pattern is the union of local
+ * contributions with value != 0 (evaluated in the reference's operation order, no FMA),
+ * which depends on `factor`.  Also builds the per-cell local->nnz map / gather lists. */
+int grmp_blf_symbolic(grmp_blf* blf, double factor, int64_t* nnz_out);
+/* SparseMatrixCSC{Float64,Int64} pattern: colptr[ncols+1], rowval[nnz], 1-based, rows ascending */
+int grmp_blf_get_pattern(grmp_blf* blf, int64_t* colptr, int64_t* rowval);
+/* Numeric assembly on the frozen pattern = assemble!(A, AP; factor, skip_preps = true) after
+ * fill!(A, 0) (bilinearform.jl:92-380, solvers.jl:556).  nzval_host may be NULL (values stay
+ * on the device; fetch later with grmp_blf_get_values). */
+int grmp_blf_numeric(grmp_blf* blf, double factor, double* nzval_host);
+int grmp_blf_get_values(grmp_blf* blf, double* nzval_host);
+/* transpose_copy block (bilinearform.jl:358-364): CSC of the mirrored block with values
+ * v * itemfactor / factor * factor_transpose * (-1), summed per entry in cell order.
+ * Sizes: colptr_t[nrows+1], rowval_t[nnz], nzval_t[nnz]. Requires a prior numeric call. */
+int grmp_blf_transpose_copy(grmp_blf* blf, double factor, double factor_transpose, int64_t* colptr_t,
+                            int64_t* rowval_t, double* nzval_t);
+int grmp_blf_stats(grmp_blf* blf, grmp_stats* out);
+/* raw device pointer of nzval (for device-side consumers / benchmarks; owned by the library) */
+int grmp_blf_device_values(grmp_blf* blf, void** dptr);
+
+/* AssemblyPattern{APT_LinearForm} (linearform.jl:29-33) with a single test-function argument */
+int grmp_lf_create(grmp_space* space, int op, const int32_t* regions, int nregions, int nq, const double* qweights,
+                   const grmp_evaltab* tab, grmp_lf** out);
+int grmp_lf_destroy(grmp_lf* lf);
+/* assemble!(b, AP; factor, offset) (linearform.jl:47-237): b[dof+offset] += contributions in
+ * cell order.  fsrc = GRMP_F_NONE (no action: input = ones, 74-75), GRMP_F_CONST
+ * (fdata[resultdim]) or GRMP_F_QP_TABLE (fdata[ncells][nq][resultdim], the host-evaluated
+ * DataFunction).  b_host has length >= ndofs + offset and is updated in place. */
+int grmp_lf_assemble(grmp_lf* lf, double factor, int fsrc, const double* fdata, double* b_host, int64_t offset);
+int grmp_lf_stats(grmp_lf* lf, grmp_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRMP_H */

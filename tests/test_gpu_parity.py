@@ -1,0 +1,263 @@
+"""GPU parity tests (run with -m gpu on the B200 box): libgrmp_cuda through the C ABI vs the
+CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): colptr/rowval bit-identical, every nzval within 1e-12
+relative (denominator max(|ref|, 1e-12*max|A|)).  The generic path is
+stricter: it replays the reference's operation and summation order, so its values are
+compared for exact equality.
+"""
+import numpy as np
+import pytest
+
+import grmp_b200 as G
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def rel_err(val, ref):
+    den = np.maximum(np.abs(ref), 1e-12 * max(np.abs(ref).max(), 1e-300))
+    return (np.abs(val - ref) / den).max() if ref.size else 0.0
+
+
+def tri_grid(L, perturbed=False):
+    g = G.uniform_refine(G.grid_unitsquare("Triangle2D"), L)
+    return G.perturb_interior_nodes(g) if perturbed else g
+
+
+def tet_grid(L, perturbed=False):
+    g = G.uniform_refine(G.grid_unitcube("Tetrahedron3D"), L)
+    return G.perturb_interior_nodes(g) if perturbed else g
+
+
+_APT = {G.assembly.APT_BilinearForm: O.APT_GENERAL, G.assembly.APT_SymmetricBilinearForm: O.APT_SYMMETRIC,
+        G.assembly.APT_LumpedBilinearForm: O.APT_LUMPED}
+
+
+def oracle_blf(AP, factor, transpose_copy=False, **kw):
+    """oracle assemble! on the same quadrature table the host hands to the library (the eigen-generated
+    Stroud rules agree between generators only to rounding; hard-coded rules are identical)"""
+    s1, s2 = AP.FES
+    A = O.OracleMatrix(s1.ndofs, s2.ndofs)
+    At = O.OracleMatrix(s2.ndofs, s1.ndofs) if transpose_copy else None
+    act = AP.action
+    dim = s1.xgrid.dim
+    qo = G.quadrature_order(AP)
+    qf = G.QuadratureRule("Triangle2D" if dim == 2 else "Tetrahedron3D", qo)
+    O.qrule_override(dim, qo, qf.xref, qf.w)
+    try:
+        O.blf_assemble(A, s1.xgrid, s1, s2, AP.operators[0].code, AP.operators[1].code, action=act.code, act_params=act.params,
+                       apt=_APT[AP.APT], regions=AP.regions, factor=factor, transpose_copy=At, bonus_quadorder=act.bonus_quadorder, **kw)
+    finally:
+        O.qrule_override(dim, qo)
+    return (A.csc(), At.csc()) if transpose_copy else A.csc()
+
+
+def check_blf(AP, factor=1.0, exact=True, path=None):
+    if path is not None:
+        G.blf_set_path(AP, path)
+    cp, rv, nz = G.assemble_csc(AP, factor)
+    ocp, orv, onz = oracle_blf(AP, factor)
+    assert np.array_equal(cp, ocp), "colptr differs"
+    assert np.array_equal(rv, orv), "rowval differs"
+    if exact:
+        assert np.array_equal(nz, onz), f"nzval not bit-identical (max rel {rel_err(nz, onz):.3e})"
+    else:
+        assert rel_err(nz, onz) <= RTOL, rel_err(nz, onz)
+    # reassembly on the frozen pattern with another factor (skip_preps = true, solvers.jl:556)
+    cp2, rv2, nz2 = G.assemble_csc(AP, 0.5 * factor, skip_preps=True)
+    assert cp2 is cp or np.array_equal(cp2, cp)
+    assert rel_err(nz2, 0.5 * onz) <= RTOL
+    return cp, rv, nz
+
+
+CASES = [
+    # (name, grid fn, fetype ctor, operator pair, apt)
+    ("P1 tri Laplace", lambda: tri_grid(3), lambda g: G.H1P1(1), (G.Gradient, G.Gradient), "sym"),
+    ("P2 tri Laplace (C1)", lambda: tri_grid(4), lambda g: G.H1P2(1, 2), (G.Gradient, G.Gradient), "sym"),
+    ("P2 tri mass", lambda: tri_grid(3), lambda g: G.H1P2(1, 2), (G.Identity, G.Identity), "sym"),
+    ("P1 tet Laplace (C2)", lambda: tet_grid(2), lambda g: G.H1P1(1), (G.Gradient, G.Gradient), "sym"),
+    ("P2 tet Laplace (C2*)", lambda: tet_grid(2), lambda g: G.H1P2(1, 3), (G.Gradient, G.Gradient), "sym"),
+    ("P2 tet Laplace perturbed", lambda: tet_grid(2, True), lambda g: G.H1P2(1, 3), (G.Gradient, G.Gradient), "sym"),
+    ("P2 tet mass", lambda: tet_grid(1), lambda g: G.H1P2(1, 3), (G.Identity, G.Identity), "sym"),
+    ("P2 tet general BLF", lambda: tet_grid(1), lambda g: G.H1P2(1, 3), (G.Gradient, G.Gradient), "gen"),
+    ("P1 tri lumped mass", lambda: tri_grid(2), lambda g: G.H1P1(1), (G.Identity, G.Identity), "lump"),
+    ("RT0 tri mass", lambda: tri_grid(3), lambda g: G.HDIVRT0(2), (G.Identity, G.Identity), "sym"),
+    ("BDM1 tri mass", lambda: tri_grid(3, True), lambda g: G.HDIVBDM1(2), (G.Identity, G.Identity), "sym"),
+    ("RT0 tet mass (C5)", lambda: tet_grid(1), lambda g: G.HDIVRT0(3), (G.Identity, G.Identity), "sym"),
+    ("BDM1 tet mass (C5)", lambda: tet_grid(1, True), lambda g: G.HDIVBDM1(3), (G.Identity, G.Identity), "sym"),
+    ("RT0 tet div-div", lambda: tet_grid(1), lambda g: G.HDIVRT0(3), (G.Divergence, G.Divergence), "sym"),
+    ("BR tri Laplace (C4)", lambda: tri_grid(3), lambda g: G.H1BR(2), (G.Gradient, G.Gradient), "sym"),
+    ("BR tet Laplace", lambda: tet_grid(1, True), lambda g: G.H1BR(3), (G.Gradient, G.Gradient), "sym"),
+    ("BR tri mass", lambda: tri_grid(2), lambda g: G.H1BR(2), (G.Identity, G.Identity), "sym"),
+    ("BR tri recon RT0 mass (C4)", lambda: tri_grid(2), lambda g: G.H1BR(2),
+     (G.ReconstructionIdentity(G.HDIVRT0(2)), G.ReconstructionIdentity(G.HDIVRT0(2))), "sym"),
+    ("BR tri recon BDM1 mass (C4)", lambda: tri_grid(2, True), lambda g: G.H1BR(2),
+     (G.ReconstructionIdentity(G.HDIVBDM1(2)), G.ReconstructionIdentity(G.HDIVBDM1(2))), "sym"),
+    ("BR tet recon BDM1 mass", lambda: tet_grid(0), lambda g: G.H1BR(3),
+     (G.ReconstructionIdentity(G.HDIVBDM1(3)), G.ReconstructionIdentity(G.HDIVBDM1(3))), "sym"),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_blf_parity_generic(case):
+    _, gridf, fef, ops, apt = case
+    g = gridf()
+    s = G.FESpace(fef(g), g)
+    ctor = {"sym": G.DiscreteSymmetricBilinearForm, "gen": G.DiscreteBilinearForm, "lump": G.DiscreteLumpedBilinearForm}[apt]
+    AP = ctor(list(ops), [s, s])
+    check_blf(AP, factor=1.0, exact=True, path=G._lib.PATH_GENERIC)
+
+
+def test_laplace_kappa_and_regions():
+    g = tri_grid(3)
+    g.cellregions[::3] = 2
+    s = G.FESpace(G.H1P2(1, 2), g)
+    AP = G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [s, s], regions=[2])
+    check_blf(AP, factor=1e-3, path=G._lib.PATH_GENERIC)
+
+
+def test_hooke2d_parity():
+    g = tri_grid(3, True)
+    s = G.FESpace(G.H1P2(2, 2), g)
+    mu = 1000 / 1.4
+    lam = 0.4 * mu / 0.2
+    AP = G.DiscreteBilinearForm([G.SymmetricGradient(1), G.SymmetricGradient(1)], [s, s], G.HookeAction(2, mu, lam))
+    check_blf(AP, path=G._lib.PATH_GENERIC)
+    g2 = tri_grid(2)          # axis-aligned: pattern hinges on exact zeros
+    s2 = G.FESpace(G.H1P1(2), g2)
+    AP2 = G.DiscreteBilinearForm([G.SymmetricGradient(1), G.SymmetricGradient(1)], [s2, s2], G.HookeAction(2, mu, lam))
+    check_blf(AP2, path=G._lib.PATH_GENERIC)
+
+
+def test_hooke3d_parity():
+    g = tet_grid(1)
+    s = G.FESpace(G.H1P1(3), g)
+    AP = G.DiscreteBilinearForm([G.SymmetricGradient(1), G.SymmetricGradient(1)], [s, s], G.HookeAction(3, 2.0, 3.0))
+    check_blf(AP, path=G._lib.PATH_GENERIC)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_stokes_divergence_block_with_transpose_copy(dim):
+    g = tri_grid(3) if dim == 2 else tet_grid(1)
+    sv = G.FESpace(G.H1BR(dim), g)
+    sp = G.FESpace(G.L2P0(1), g)
+    A = G.FEMatrix([sv, sp])
+    O_ = G.LagrangeMultiplier(G.Divergence)
+    G.assemble_operator(A[1, 2], O_, At=A[2, 1])
+    (ocp, orv, onz), (tcp, trv, tnz) = oracle_blf(O_._pattern, -1.0, transpose_copy=True)
+    # compare the two blocks of the device-assembled FEMatrix with the oracle's B and transpose copy
+    M = A.tocsc().toarray() if A.m < 3000 else None
+    import scipy.sparse as sp_
+    B = sp_.csc_matrix((onz, orv - 1, ocp - 1), shape=(sv.ndofs, sp.ndofs))
+    Bt = sp_.csc_matrix((tnz, trv - 1, tcp - 1), shape=(sp.ndofs, sv.ndofs))
+    full = A.tocsc()
+    assert abs(full[: sv.ndofs, sv.ndofs:] - B).max() == 0
+    assert abs(full[sv.ndofs:, : sv.ndofs] - Bt).max() == 0
+    assert full.nnz == B.nnz + Bt.nnz
+
+
+def test_rectangular_p2_p1_divergence_transposed_assembly():
+    g = tri_grid(2, True)
+    su = G.FESpace(G.H1P2(2, 2), g)
+    sp = G.FESpace(G.H1P1(1), g)
+    AP = G.DiscreteBilinearForm([G.Divergence, G.Identity], [su, sp])
+    cp, rv, nz = G.assemble_csc(AP, 1.0)
+    ocp, orv, onz = oracle_blf(AP, 1.0)
+    assert np.array_equal(cp, ocp) and np.array_equal(rv, orv) and np.array_equal(nz, onz)
+    cpT, rvT, nzT = G.assemble_csc(AP, 1.0, transposed_assembly=True)
+    At = O.OracleMatrix(sp.ndofs, su.ndofs)
+    O.blf_assemble(At, g, su, sp, O.OP_DIV, O.OP_ID, transposed_assembly=True)
+    tcp, trv, tnz = At.csc()
+    assert np.array_equal(cpT, tcp) and np.array_equal(rvT, trv) and np.array_equal(nzT, tnz)
+
+
+LF_CASES = [
+    ("P2 tri id f=1 region 1 (C1)", lambda: tri_grid(4), lambda: G.H1P2(1, 2), G.Identity, "const", [1]),
+    ("P2 tet id f(x)", lambda: tet_grid(1), lambda: G.H1P2(1, 3), G.Identity, "fun", [0]),
+    ("P1 tri id none", lambda: tri_grid(2), lambda: G.H1P1(1), G.Identity, "none", [0]),
+    ("RT0 tet id f(x)", lambda: tet_grid(1), lambda: G.HDIVRT0(3), G.Identity, "vfun", [0]),
+    ("BDM1 tri id f(x)", lambda: tri_grid(2), lambda: G.HDIVBDM1(2), G.Identity, "vfun", [0]),
+    ("BR tri recon RT0 (C4)", lambda: tri_grid(3), lambda: G.H1BR(2), G.ReconstructionIdentity(G.HDIVRT0(2)), "vfun2", [0]),
+    ("BR tri recon BDM1 (C4)", lambda: tri_grid(3, True), lambda: G.H1BR(2), G.ReconstructionIdentity(G.HDIVBDM1(2)), "vfun2", [0]),
+    ("BR tet recon RT0", lambda: tet_grid(1), lambda: G.H1BR(3), G.ReconstructionIdentity(G.HDIVRT0(3)), "vfun2", [0]),
+    ("BR tet recon BDM1", lambda: tet_grid(1, True), lambda: G.H1BR(3), G.ReconstructionIdentity(G.HDIVBDM1(3)), "vfun2", [0]),
+]
+
+
+@pytest.mark.parametrize("case", LF_CASES, ids=[c[0] for c in LF_CASES])
+def test_lf_parity(case):
+    _, gridf, fef, op, kind, regions = case
+    g = gridf()
+    s = G.FESpace(fef(), g)
+    dim = g.dim
+    nc = s.fetype.ncomponents
+    bonus = 0
+    if kind == "const":
+        data = G.DataFunction([1.0])
+    elif kind == "none":
+        data = None
+    elif kind == "fun":
+        data = G.DataFunction(lambda x: np.sin(x[0]) * x[1] + (x[2] if len(x) > 2 else 0.0), [1, dim], bonus_quadorder=2)
+        bonus = 2
+    elif kind == "vfun":
+        data = G.DataFunction(lambda x: np.stack([x[k] ** 2 + x[(k + 1) % len(x)] for k in range(len(x))]), [nc, dim], bonus_quadorder=1)
+        bonus = 1
+    else:   # gradient of x^3+y^3(-1/2): Example222-style right-hand side (bonus 2 -> Stroud rule in 2D)
+        data = G.DataFunction(lambda x: np.stack([3 * x[k] ** 2 for k in range(len(x))]), [nc, dim], bonus_quadorder=2)
+        bonus = 2
+    Op = G.LinearForm(op, data, regions=regions, factor=2.0)
+    b = G.FEVector([s])
+    b.entries[:] = 0.25            # += semantics
+    AP = G.assemble_operator(b[1], Op)
+    # oracle on the same quadrature rule and the same host-evaluated table
+    qo = G.quadrature_order(AP)
+    P = AP.AM
+    O.qrule_override(dim, qo, P.qf.xref, P.qf.w)
+    try:
+        ob = np.full(s.ndofs, 0.25)
+        if kind == "const":
+            O.lf_assemble(ob, g, s, op.code, fsrc=O.F_CONST, fdata=[1.0], regions=regions, factor=2.0, bonus_quadorder=bonus)
+        elif kind == "none":
+            O.lf_assemble(ob, g, s, op.code, fsrc=O.F_NONE, regions=regions, factor=2.0)
+        else:
+            xq = O.quadpoints(g, qo)
+            flat = xq.reshape(-1, dim)
+            vals = np.asarray(data.kernel(flat.T), dtype=np.float64).reshape(-1, flat.shape[0]).T
+            table = vals.reshape(g.ncells, len(P.qf), -1)
+            O.lf_assemble(ob, g, s, op.code, fsrc=O.F_QP_TABLE, fdata=table, regions=regions, factor=2.0, bonus_quadorder=bonus)
+    finally:
+        O.qrule_override(dim, qo)
+    assert np.array_equal(b.entries, ob), f"max abs diff {np.abs(b.entries - ob).max():.3e}"
+
+
+def test_lf_offset_into_block_vector():
+    g = tri_grid(2)
+    s1 = G.FESpace(G.H1P1(1), g)
+    s2 = G.FESpace(G.H1P2(1, 2), g)
+    b = G.FEVector([s1, s2])
+    G.assemble_operator(b[2], G.LinearForm(G.Identity, G.DataFunction([3.0])))
+    assert np.all(b.entries[: s1.ndofs] == 0)
+    assert abs(b.entries[s1.ndofs:].sum() - 3.0) < 1e-13
+
+
+def test_error_behaviour():
+    g = tri_grid(1)
+    s = G.FESpace(G.H1P1(1), g)
+    sp = G.FESpace(G.HDIVRT0(2), g)
+    with pytest.raises(G._lib.GrmpError):
+        G.assemble_csc(G.DiscreteBilinearForm([G.Gradient, G.Gradient], [sp, sp]))      # Hdiv gradient is not ported
+    with pytest.raises(G._lib.GrmpError):
+        G.assemble_csc(G.DiscreteBilinearForm([G.Gradient, G.Identity], [s, s]))        # result dims differ
+    with pytest.raises(NotImplementedError):
+        G.Action(lambda r, i: None, [1, 1])
+
+
+def test_determinism_two_runs_bit_equal():
+    g = tet_grid(2)
+    s = G.FESpace(G.H1P2(1, 3), g)
+    AP = G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [s, s])
+    _, _, a = G.assemble_csc(AP, 1.0)
+    _, _, b = G.assemble_csc(AP, 1.0, skip_preps=True)
+    assert np.array_equal(a, b)
