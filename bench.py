@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- assembled nnz/s for the 3D P2 Laplace stiffness matrix (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--level L] [--impl reference]
+
+A "step" is one numeric assembly of LaplaceOperator(1.0) for H1P2{1,3} on
+uniform_refine(grid_unitcube(Tetrahedron3D), L) on a frozen sparsity pattern -- the analogue
+of fill!(A,0) + assemble!(A, AP; skip_preps = true).  L = 6 (6 291 456 cells,
+~2.4e8 non-zeros) is the BASELINE configuration (configs[1]).
+
+  value   device-resident throughput: K steps bracketed by one pair of CUDA events on the library's
+          launching stream (grmp_blf_numeric_steps), inputs resident in HBM; the working set
+          (nzval 1.9 GB + maps) is far larger than the 126 MB L2, so no explicit flush is needed.
+  e2e     the same metric through the reference-facing call with HOST buffers: per step the grid
+          arrays (Coordinates, CellVolumes, CellNodes, CellDofs) are copied from pinned host memory,
+          the matrix is assembled and nzval is copied back to pinned host memory.
+  roofline  algorithmic bytes (8 nnz + 4 ncells (nn + nd) + 8 dim nnodes) / kernel time
+          against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+  cpu_baseline  the oracle's restatement of the reference loop (1 thread: the reference cell loop is
+          serial) on a bounded sample (level 5 unless --cpu-level is given).
+
+N > 1 (torchrun): strong scaling -- the cells of the SAME grid are partitioned into N contiguous
+(spatially compact) ranges; a rank owns the dofs whose lowest-numbered cell it holds, assembles the
+columns it owns from its cells plus the halo cells touching them (owner-computes, no numeric-phase
+exchange), and `value` = global nnz * K / max-over-ranks device time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(index), "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, mx = [], set(), None
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = mx
+            out["reasons"] = sorted(reasons)
+            out["samples"] = len(sm)
+        return out
+
+
+def build_problem(level):
+    import grmp_b200 as G
+    t = time.time()
+    g = G.uniform_refine(G.grid_unitcube("Tetrahedron3D"), level)
+    s = G.FESpace(G.H1P2(1, 3), g)
+    s.celldofs
+    g.cellvolumes
+    return G, g, s, time.time() - t
+
+
+def partition(G, g, s, rank, world):
+    """cells [rank*nc/P, (rank+1)*nc/P) ; a dof is owned by the rank of its lowest-numbered cell;
+    local problem = own cells + halo cells touching owned dofs, owned dofs numbered first."""
+    nc = g.ncells
+    bounds = [(nc * r) // world for r in range(world + 1)]
+    dofs = s.celldofs.astype(np.int64) - 1
+    first_cell = np.full(s.ndofs, nc, dtype=np.int64)
+    np.minimum.at(first_cell, dofs.ravel(), np.repeat(np.arange(nc, dtype=np.int64), dofs.shape[1]))
+    owner = np.searchsorted(np.array(bounds[1:]), first_cell, side="right")
+    owned = owner == rank
+    cell_mask = owned[dofs].any(axis=1)
+    cells = np.nonzero(cell_mask)[0]
+    ldofs = dofs[cells]
+    used = np.zeros(s.ndofs, bool)
+    used[ldofs.ravel()] = True
+    order = np.concatenate([np.nonzero(used & owned)[0], np.nonzero(used & ~owned)[0]])
+    newid = np.full(s.ndofs, -1, dtype=np.int64)
+    newid[order] = np.arange(order.size)
+    n_owned = int((used & owned).sum())
+    # local grid (node renumbering keeps the library's inputs compact)
+    cn = g.cellnodes[cells].astype(np.int64) - 1
+    nodes = np.unique(cn)
+    nmap = np.full(g.nnodes, -1, dtype=np.int64)
+    nmap[nodes] = np.arange(nodes.size)
+    lg = G.ExtendableGrid(g.coords[nodes], nmap[cn] + 1, g.cellregions[cells])
+    lg._cache["vol"] = np.ascontiguousarray(g.cellvolumes[cells])
+    ls = G.FESpace(G.H1P2(1, 3), lg)
+    ls._celldofs = np.ascontiguousarray(newid[ldofs] + 1, dtype=np.int32)
+    ls.ndofs = int(order.size)
+    return lg, ls, n_owned, order
+
+
+def run_gpu(args):
+    import ctypes as C
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    G, g, s, t_grid = build_problem(args.level)
+    L = G._lib.lib()
+    if world > 1:
+        lg, ls, n_owned, order = partition(G, g, s, rank, world)
+    else:
+        lg, ls, n_owned = g, s, s.ndofs
+    AP = G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [ls, ls])
+    G.prepare_assembly(AP)
+    h = AP.AM.h
+    if args.path != "auto":
+        G._lib.check(L.grmp_blf_set_path(h, {"generic": 1, "fast": 2}[args.path]))
+    if world > 1:
+        G._lib.check(L.grmp_blf_set_owned_columns(h, n_owned))
+    nnz = C.c_int64(0)
+    t0 = time.time()
+    G._lib.check(L.grmp_blf_symbolic(h, 1.0, C.byref(nnz)))
+    t_sym = time.time() - t0
+    colptr = np.zeros(ls.ndofs + 1, np.int64)
+    rowval = np.zeros(nnz.value, np.int64)
+    G._lib.check(L.grmp_blf_get_pattern(h, G._lib.ptr(colptr), G._lib.ptr(rowval)))
+    nnz_owned = int(colptr[n_owned] - 1)
+    del rowval
+    st = G.blf_stats(AP)
+    # warm-up
+    ms = C.c_double(0)
+    G._lib.check(L.grmp_blf_numeric_steps(h, 1.0, max(args.warmup, 3), C.byref(ms)))
+    # ---- timed region: K steps, barrier + synchronize on both sides, CUDA events on the launching stream ----
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    w0 = time.time()
+    G._lib.check(L.grmp_blf_numeric_steps(h, 1.0, args.steps, C.byref(ms)))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.time() - w0
+    clocks = sampler.stop() if sampler else None
+    dev_ms = ms.value
+    launches = int(G.blf_stats(AP).kernel_launches) * args.steps
+    # ---- e2e: host buffers in, host nzval out, every step ----
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+    h_coords, h_vol, h_cn, h_dofs = pin(lg.coords), pin(lg.cellvolumes), pin(lg.cellnodes), pin(ls.celldofs)
+    h_nz = torch.empty(nnz.value, dtype=torch.float64).pin_memory()
+    gh, sh = G.device_grid(lg), G.device_space(ls)
+    e2e_steps = max(2, min(args.steps, 5))
+
+    def e2e_step():
+        G._lib.check(L.grmp_grid_update_geometry(gh, h_coords.data_ptr(), h_vol.data_ptr()))
+        G._lib.check(L.grmp_grid_update_cells(gh, h_cn.data_ptr()))
+        G._lib.check(L.grmp_space_update_dofs(sh, h_dofs.data_ptr()))
+        G._lib.check(L.grmp_blf_numeric(h, 1.0, h_nz.data_ptr()))
+    e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0 = time.time()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_s = (time.time() - e0) / e2e_steps
+    checksum = float(h_nz[:nnz_owned].sum())
+    h2d = sum(t.numel() * t.element_size() for t in (h_coords, h_vol, h_cn, h_dofs))
+    d2h = h_nz.numel() * 8
+    # ---- reduce over ranks ----
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_s, wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s, wall = [float(x) for x in t.cpu()]
+        c = torch.tensor([nnz_owned, h2d, d2h, launches, lg.ncells], dtype=torch.float64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        nnz_total, h2d, d2h, launches, cells_total = [int(x) for x in c.cpu()]
+    else:
+        nnz_total, cells_total = nnz_owned, lg.ncells
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_step = dev_ms / args.steps
+    value = nnz_total / (ms_step * 1e-3)
+    peak, peak_src = _peaks()
+    # algorithmic bytes of ONE launch on rank 0 (per-launch, like the kernel time it is divided by)
+    b_alg = 8 * nnz_owned + lg.ncells * 4 * (4 + 10) + 8 * 3 * lg.nnodes
+    achieved = b_alg / (ms_step * 1e-3) / 1e9
+    tr = _traffic()
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": (tr or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                "kernel": "p2tet_tile_kernel" if st.path == 2 else "blf_local_kernel+gather_kernel",
+                "algorithmic_bytes_per_launch": int(b_alg), "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)}
+    cpu = cpu_baseline(args.cpu_level) if world == 1 or True else None
+    out = {
+        "metric": "assembled nnz/s, 3D P2 Laplace stiffness (numeric assembly on a frozen pattern)",
+        "value": value, "unit": "nnz/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (uniform_refine(grid_unitcube(Tetrahedron3D), %d), H1P2{1,3}, LaplaceOperator(1.0))" % args.level,
+        "config": {"workload": "Example301 Poisson 3D: H1P2 Laplace stiffness on uniform_refine(grid_unitcube(Tetrahedron3D),%d)" % args.level,
+                   "level": args.level, "ncells": int(g.ncells), "ndofs": int(s.ndofs), "nnz": int(nnz_total),
+                   "cells_assembled_all_ranks": int(cells_total), "partition": "cell ranges, owner-computes columns" if world > 1 else "none",
+                   "l2": "inputs+outputs (%.2f GB) >> 126 MB L2, no explicit flush" % ((b_alg + 16 * 10 * lg.ncells) / 1e9),
+                   "path": {1: "generic", 2: "fast"}[int(st.path)], "tiles": int(st.ntiles)},
+        "e2e": {"value": nnz_total / e2e_s, "unit": "nnz/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_s * 1e3, "steps": e2e_steps},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+        "timing": {"wall_s_timed_region": wall, "grid_build_s": t_grid, "symbolic_s": t_sym, "symbolic_device_ms": st.last_symbolic_ms},
+        "checksum": checksum,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _oracle_problem(level):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    G, g, s, _ = build_problem(level)
+    A = O.OracleMatrix(s.ndofs, s.ndofs)
+    t = time.time()
+    O.blf_assemble(A, g, s, s, O.OP_GRAD, O.OP_GRAD, apt=O.APT_SYMMETRIC, factor=1.0)
+    A.flush()
+    t_first = time.time() - t
+    nnz = A.csc()[1].size
+    return O, g, s, A, nnz, t_first
+
+
+def cpu_baseline(level):
+    """oracle (port of the reference loop) on a bounded sample: first assembly (pattern + values, LNK
+    insertion + flush!) and reassembly on the frozen pattern (CSC binary-search updates)"""
+    try:
+        O, g, s, A, nnz, t_first = _oracle_problem(level)
+        A.fill_zero()
+        t = time.time()
+        O.blf_assemble(A, g, s, s, O.OP_GRAD, O.OP_GRAD, apt=O.APT_SYMMETRIC, factor=1.0)
+        t_re = time.time() - t
+        return {"value": nnz / t_re, "unit": "nnz/s", "cores": 1, "kind": "port",
+                "sample": "same workload at level %d (%d cells, %d nnz): reassembly on the frozen pattern %.2f s; first assembly "
+                          "(pattern+values) %.2f s = %.3g nnz/s" % (level, g.ncells, nnz, t_re, t_first, nnz / t_first),
+                "host_cpus": os.cpu_count()}
+    except Exception as e:  # the baseline must never take the bench line down
+        return {"value": None, "unit": "nnz/s", "cores": 1, "kind": "port", "sample": "failed: %r" % (e,)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is Julia (not
+    installable here: no julia binary, no network), so this arm times the oracle's op-for-op port of
+    its serial cell loop on the host, 1 thread (the reference loop is serial)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    level = args.cpu_level
+    if (args.steps + args.warmup) > 30:
+        level = min(level, 4)
+    O, g, s, A, nnz, t_first = _oracle_problem(level)
+    for _ in range(args.warmup):
+        A.fill_zero()
+        O.blf_assemble(A, g, s, s, O.OP_GRAD, O.OP_GRAD, apt=O.APT_SYMMETRIC, factor=1.0)
+    t = time.time()
+    for _ in range(args.steps):
+        A.fill_zero()
+        O.blf_assemble(A, g, s, s, O.OP_GRAD, O.OP_GRAD, apt=O.APT_SYMMETRIC, factor=1.0)
+    dt = (time.time() - t) / args.steps
+    value = nnz / dt
+    sample = "level %d (%d cells, %d nnz) per step; first assembly %.2f s" % (level, g.ncells, nnz, t_first)
+    print(json.dumps({
+        "impl": "reference", "metric": "assembled nnz/s, 3D P2 Laplace stiffness (numeric assembly on a frozen pattern)",
+        "value": value, "unit": "nnz/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Example301 Poisson 3D: H1P2 Laplace stiffness on uniform_refine(grid_unitcube(Tetrahedron3D),%d) "
+                               "(bounded sample of the level-%d workload)" % (level, args.level), "level": level,
+                   "ncells": int(g.ncells), "nnz": int(nnz)},
+        "cpu_baseline": {"value": value, "unit": "nnz/s", "cores": 1, "kind": "port", "sample": sample,
+                         "note": "Julia reference not runnable in this image; oracle port of bilinearform.jl:226-377, serial like the reference"},
+        "e2e": {"value": value, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--level", type=int, default=6)
+    ap.add_argument("--cpu-level", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--path", default="auto", choices=["auto", "generic", "fast"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

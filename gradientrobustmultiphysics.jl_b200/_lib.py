@@ -18,7 +18,8 @@ PATH_AUTO, PATH_GENERIC, PATH_FAST = 0, 1, 2
 
 EXPORTS = [
     "grmp_last_error", "grmp_init", "grmp_finalize", "grmp_device_synchronize", "grmp_grid_create", "grmp_grid_set_faces",
-    "grmp_grid_update_geometry", "grmp_grid_destroy", "grmp_space_create", "grmp_space_destroy", "grmp_blf_create",
+    "grmp_grid_update_geometry", "grmp_grid_update_cells", "grmp_grid_destroy", "grmp_space_update_dofs",
+    "grmp_blf_numeric_steps", "grmp_blf_set_owned_columns", "grmp_space_create", "grmp_space_destroy", "grmp_blf_create",
     "grmp_blf_destroy", "grmp_blf_set_path", "grmp_blf_symbolic", "grmp_blf_get_pattern", "grmp_blf_numeric",
     "grmp_blf_get_values", "grmp_blf_transpose_copy", "grmp_blf_stats", "grmp_blf_device_values", "grmp_lf_create",
     "grmp_lf_destroy", "grmp_lf_assemble", "grmp_lf_stats",
@@ -65,6 +66,10 @@ def lib():
         L.grmp_grid_set_faces.argtypes = [vp, i64, vp, vp, vp, vp, vp]
         L.grmp_grid_update_geometry.argtypes = [vp, vp, vp]
         L.grmp_grid_destroy.argtypes = [vp]
+        L.grmp_grid_update_cells.argtypes = [vp, vp]
+        L.grmp_space_update_dofs.argtypes = [vp, vp]
+        L.grmp_blf_numeric_steps.argtypes = [vp, dbl, i32, C.POINTER(dbl)]
+        L.grmp_blf_set_owned_columns.argtypes = [vp, i64]
         L.grmp_space_create.argtypes = [vp, i32, i32, i64, i32, vp, C.POINTER(vp)]
         L.grmp_space_destroy.argtypes = [vp]
         L.grmp_blf_create.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp, i32, i32, vp, C.POINTER(EvalTab), C.POINTER(EvalTab),

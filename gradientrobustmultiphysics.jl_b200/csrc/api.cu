@@ -130,6 +130,7 @@ struct grmp_blf {
   bool have_pattern = false, have_values = false;
   DevBuf<double> lbuf, nzval;
   FastP2Tet fast;
+  i64 ncols_owned = -1;
   grmp_stats st{};
   i64 out_rows() const { return (apt != GRMP_APT_SYMMETRIC && transposed) ? s2->ndofs : s1->ndofs; }
   i64 out_cols() const { return (apt != GRMP_APT_SYMMETRIC && transposed) ? s1->ndofs : s2->ndofs; }
@@ -146,6 +147,8 @@ struct grmp_lf {
   grmp_stats st{};
 };
 
+static int blf_numeric_launch(grmp_blf* b, BlfLocalParams& p, cudaStream_t s);
+
 static int fill_blf_params(grmp_blf* b, double factor, BlfLocalParams* p) {
   p->g = b->s1->grid->view();
   GRMP_TRY(make_evalview(b->s1, b->op1, b->t1, &p->e1));
@@ -155,6 +158,22 @@ static int fill_blf_params(grmp_blf* b, double factor, BlfLocalParams* p) {
   p->apt = b->apt; p->transposed = b->transposed; p->reg = b->reg; p->nq = b->nq; p->w = b->w.p; p->factor = factor;
   p->nrows_key = b->out_rows();
   p->keys = nullptr; p->lbuf = nullptr;
+  return GRMP_OK;
+}
+
+static int blf_numeric_launch(grmp_blf* b, BlfLocalParams& p, cudaStream_t s) {
+  grmp_ctx* ctx = b->s1->grid->ctx;
+  if (b->path == GRMP_PATH_FAST) {
+    GRMP_TRY(fast_p2tet_numeric(ctx, p, b->pat, b->fast, b->nzval.p));
+    b->st.kernel_launches = 1;
+  } else {
+    const size_t nl = (size_t)p.e1.nd * p.e2.nd * p.g.ncells;
+    if (b->lbuf.n != nl) GRMP_TRY(b->lbuf.alloc(nl));
+    p.lbuf = b->lbuf.p;
+    GRMP_TRY(launch_blf_local(p, s));
+    GRMP_TRY(launch_gather(s, b->pat, b->lbuf.p, b->nzval.p));
+    b->st.kernel_launches = 2;
+  }
   return GRMP_OK;
 }
 
@@ -239,6 +258,14 @@ int grmp_grid_update_geometry(grmp_grid* g, const double* coords, const double* 
   return GRMP_OK;
 }
 
+int grmp_grid_update_cells(grmp_grid* g, const int32_t* cellnodes) {
+  if (!g || !cellnodes) return fail(GRMP_EINVAL, "grmp_grid_update_cells: NULL argument");
+  cudaStream_t s = g->ctx->stream;
+  GRMP_TRY(g->cellnodes.upload(cellnodes, (size_t)g->ncells * (g->dim + 1), s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  return GRMP_OK;
+}
+
 int grmp_grid_destroy(grmp_grid* g) { delete g; return GRMP_OK; }
 
 int grmp_space_create(grmp_grid* grid, int fetype, int ncomp, int64_t ndofs, int nd_cell, const int32_t* celldofs, grmp_space** out) {
@@ -252,6 +279,13 @@ int grmp_space_create(grmp_grid* grid, int fetype, int ncomp, int64_t ndofs, int
   if (!rc && cudaStreamSynchronize(grid->ctx->stream) != cudaSuccess) rc = fail(GRMP_ECUDA, "upload failed");
   if (rc) { delete s; return rc; }
   *out = s;
+  return GRMP_OK;
+}
+int grmp_space_update_dofs(grmp_space* sp, const int32_t* celldofs) {
+  if (!sp || !celldofs) return fail(GRMP_EINVAL, "grmp_space_update_dofs: NULL argument");
+  cudaStream_t s = sp->grid->ctx->stream;
+  GRMP_TRY(sp->celldofs.upload(celldofs, (size_t)sp->grid->ncells * sp->nd, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
   return GRMP_OK;
 }
 int grmp_space_destroy(grmp_space* s) { delete s; return GRMP_OK; }
@@ -319,7 +353,7 @@ int grmp_blf_symbolic(grmp_blf* b, double factor, int64_t* nnz_out) {
   GRMP_TRY(b->nzval.alloc(b->pat.nnz));
   b->path = GRMP_PATH_GENERIC;
   if (want_fast) {
-    GRMP_TRY(fast_p2tet_build(ctx, p, b->pat, b->w_host, b->t1_derivs_host, &b->fast));
+    GRMP_TRY(fast_p2tet_build(ctx, p, b->pat, b->w_host, b->t1_derivs_host, b->ncols_owned, &b->fast));
     b->pat.slotmap.release();
     b->path = GRMP_PATH_FAST;
   }
@@ -353,17 +387,7 @@ int grmp_blf_numeric(grmp_blf* b, double factor, double* nzval_host) {
   BlfLocalParams p;
   GRMP_TRY(fill_blf_params(b, factor, &p));
   GRMP_CUDA(cudaEventRecord(ctx->ev0, s));
-  if (b->path == GRMP_PATH_FAST) {
-    GRMP_TRY(fast_p2tet_numeric(ctx, p, b->pat, b->fast, b->nzval.p));
-    b->st.kernel_launches = 1;
-  } else {
-    const size_t nl = (size_t)p.e1.nd * p.e2.nd * p.g.ncells;
-    if (b->lbuf.n != nl) GRMP_TRY(b->lbuf.alloc(nl));
-    p.lbuf = b->lbuf.p;
-    GRMP_TRY(launch_blf_local(p, s));
-    GRMP_TRY(launch_gather(s, b->pat, b->lbuf.p, b->nzval.p));
-    b->st.kernel_launches = 2;
-  }
+  GRMP_TRY(blf_numeric_launch(b, p, s));
   GRMP_CUDA(cudaEventRecord(ctx->ev1, s));
   if (nzval_host && b->pat.nnz) GRMP_CUDA(cudaMemcpyAsync(nzval_host, b->nzval.p, (size_t)b->pat.nnz * 8, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaStreamSynchronize(s));
@@ -371,6 +395,32 @@ int grmp_blf_numeric(grmp_blf* b, double factor, double* nzval_host) {
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   b->st.last_numeric_ms = ms;
   b->have_values = true;
+  return GRMP_OK;
+}
+
+int grmp_blf_numeric_steps(grmp_blf* b, double factor, int nsteps, double* total_ms) {
+  if (!b || nsteps < 0) return fail(GRMP_EINVAL, "grmp_blf_numeric_steps: bad argument");
+  if (!b->have_pattern) return fail(GRMP_ESTATE, "grmp_blf_symbolic has not been called");
+  grmp_ctx* ctx = b->s1->grid->ctx;
+  cudaStream_t s = ctx->stream;
+  GRMP_CUDA(cudaSetDevice(ctx->device));
+  BlfLocalParams p;
+  GRMP_TRY(fill_blf_params(b, factor, &p));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  GRMP_CUDA(cudaEventRecord(ctx->ev0, s));
+  for (int k = 0; k < nsteps; k++) GRMP_TRY(blf_numeric_launch(b, p, s));
+  GRMP_CUDA(cudaEventRecord(ctx->ev1, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  if (total_ms) *total_ms = ms;
+  if (nsteps > 0) { b->st.last_numeric_ms = ms / nsteps; b->have_values = true; }
+  return GRMP_OK;
+}
+
+int grmp_blf_set_owned_columns(grmp_blf* b, int64_t ncols_owned) {
+  if (!b) return fail(GRMP_EINVAL, "blf == NULL");
+  b->ncols_owned = ncols_owned;
   return GRMP_OK;
 }
 

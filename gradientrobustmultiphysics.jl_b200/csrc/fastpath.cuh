@@ -21,7 +21,7 @@ struct FastP2Tet {
 
 bool fast_p2tet_applicable(const BlfLocalParams& p);
 int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const std::vector<double>& w,
-                     const std::vector<double>& derivs, FastP2Tet* out);
+                     const std::vector<double>& derivs, i64 ncols_owned, FastP2Tet* out);
 int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const FastP2Tet& f, double* nzval);
 
 }  // namespace grmp

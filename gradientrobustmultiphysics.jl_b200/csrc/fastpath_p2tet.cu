@@ -29,7 +29,8 @@ namespace {
 
 constexpr int TPB = 128;             // threads per tile
 constexpr int MAX_TILE_COLS = 128;
-constexpr int SMEM_BUDGET = 56 * 1024;
+constexpr int SMEM_BUDGET = 56 * 1024;          // staged tiles: nzval slots + S of the distinct cells
+constexpr int SMEM_BUDGET_DIRECT = 64 * 1024;   // direct tiles (vertex columns): nzval slots only
 
 // local edge e -> (p,q), Tetrahedron3D edges [1 2],[1 3],[1 4],[2 3],[2 4],[3 4] (h1_p2.jl:231-236)
 __host__ __device__ inline void edge_nodes(int e, int& p, int& q) {
@@ -62,7 +63,7 @@ __host__ __device__ inline int canon_row(const int* pi, int r) {
 struct PackParams {
   const u32* gsrc;        // sorted pairs: lj*ncells + cell
   const u32* gcell;
-  const unsigned short* pair_local;
+  const u32* pair_x;      // tile-local cell index (staged tiles) or global cell index (direct tiles)
   const i32* slotmap;     // [ncells*100]
   const i64* colptr;      // 1-based
   const i32* celldofs;
@@ -85,9 +86,9 @@ __global__ void pack_pairs(PackParams p) {
     const i32 slot = p.slotmap[cell * 100 + li * 10 + lj];
     off[r] = (slot < 0) ? 255 : (unsigned char)(slot - base);
   }
-  off[10] = off[11] = 255;
+  off[10] = (unsigned char)lj; off[11] = 0;
   uint4 rec;
-  rec.x = (u32)p.pair_local[k] | ((u32)lj << 16);
+  rec.x = p.pair_x[k];
   rec.y = off[0] | (off[1] << 8) | (off[2] << 16) | ((u32)off[3] << 24);
   rec.z = off[4] | (off[5] << 8) | (off[6] << 16) | ((u32)off[7] << 24);
   rec.w = off[8] | (off[9] << 8) | (off[10] << 16) | ((u32)off[11] << 24);
@@ -135,8 +136,35 @@ __device__ __forceinline__ void cell_S(const GridView& g, i64 cell, double facto
   S[9] = sc * (n3x * n3x + n3y * n3y + n3z * n3z);
 }
 
-__device__ __forceinline__ void acc_add(double* acc, u32 off, double v) {
-  if (off != 255u) acc[off] += v;
+// the four values a vertex column a needs, straight from the coordinates (direct tiles):
+// S_aa and S_ab for the other three vertices in ascending order
+__device__ __forceinline__ void vertex_S(const GridView& g, i64 cell, int a, double factor, double& saa, double& s1, double& s2, double& s3) {
+  const i32* cn = g.cellnodes + cell * 4;
+  const int4 nd = *reinterpret_cast<const int4*>(cn);
+  const double* x0 = g.coords + (i64)(nd.x - 1) * 3;
+  const double* x1 = g.coords + (i64)(nd.y - 1) * 3;
+  const double* x2 = g.coords + (i64)(nd.z - 1) * 3;
+  const double* x3 = g.coords + (i64)(nd.w - 1) * 3;
+  const double p0x = x0[0], p0y = x0[1], p0z = x0[2];
+  const double ax = x1[0] - p0x, ay = x1[1] - p0y, az = x1[2] - p0z;
+  const double bx = x2[0] - p0x, by = x2[1] - p0y, bz = x2[2] - p0z;
+  const double cx = x3[0] - p0x, cy = x3[1] - p0y, cz = x3[2] - p0z;
+  const double n1x = by * cz - bz * cy, n1y = bz * cx - bx * cz, n1z = bx * cy - by * cx;
+  const double n2x = cy * az - cz * ay, n2y = cz * ax - cx * az, n2z = cx * ay - cy * ax;
+  const double n3x = ay * bz - az * by, n3y = az * bx - ax * bz, n3z = ax * by - ay * bx;
+  const double n0x = -(n1x + n2x + n3x), n0y = -(n1y + n2y + n3y), n0z = -(n1z + n2z + n3z);
+  const double nax = a == 0 ? n0x : a == 1 ? n1x : a == 2 ? n2x : n3x;
+  const double nay = a == 0 ? n0y : a == 1 ? n1y : a == 2 ? n2y : n3y;
+  const double naz = a == 0 ? n0z : a == 1 ? n1z : a == 2 ? n2z : n3z;
+  const double sc = factor / (36.0 * g.vol[cell]);
+  const double d0 = sc * (nax * n0x + nay * n0y + naz * n0z);
+  const double d1 = sc * (nax * n1x + nay * n1y + naz * n1z);
+  const double d2 = sc * (nax * n2x + nay * n2y + naz * n2z);
+  const double d3 = sc * (nax * n3x + nay * n3y + naz * n3z);
+  saa = a == 0 ? d0 : a == 1 ? d1 : a == 2 ? d2 : d3;
+  s1 = (a == 0) ? d1 : d0;
+  s2 = (a <= 1) ? d2 : d1;
+  s3 = (a <= 2) ? d3 : d2;
 }
 
 __global__ void __launch_bounds__(TPB) p2tet_tile_kernel(const TileParams p) {
@@ -147,6 +175,7 @@ __global__ void __launch_bounds__(TPB) p2tet_tile_kernel(const TileParams p) {
   const i64 g0 = p.colptr[c0] - 1, g1 = p.colptr[c1] - 1;
   const int nnz_t = (int)(g1 - g0);
   const int cb = p.tile_cellbeg[tile], nct = p.tile_cellbeg[tile + 1] - cb;
+  const bool staged = nct > 0;          // direct tiles (vertex columns) carry global cell ids and no S stage
   double* acc = sm;
   double* S = sm + nnz_t;
   if (tid < 10) {
@@ -176,38 +205,55 @@ __global__ void __launch_bounds__(TPB) p2tet_tile_kernel(const TileParams p) {
   __syncthreads();
   for (int col = c0 + tid; col < c1; col += TPB) {
     double* a = acc + (int)(p.colptr[col] - 1 - g0);
-    const i64 kb = p.col_pairbeg[col], ke = p.col_pairbeg[col + 1];
-    for (i64 k = kb; k < ke; k++) {
-      const uint4 rec = p.pairs[k];
-      const double* s = S + (rec.x & 0xffffu) * 10;
-      const int lj = (int)(rec.x >> 16);
-      const unsigned char* ix = s_sidx[lj];
+    i64 k = p.col_pairbeg[col];
+    const i64 ke = p.col_pairbeg[col + 1];
+    uint4 nxt = make_uint4(0, 0, 0, 0);
+    if (k < ke) nxt = p.pairs[k];
+    for (; k < ke; k++) {
+      const uint4 rec = nxt;
+      if (k + 1 < ke) nxt = p.pairs[k + 1];          // software prefetch of the next 16-byte record
+      const int lj = (int)((rec.w >> 16) & 255u);
+      double v[10];
       if (lj < 4) {
-        const double saa = s[ix[0]], s1 = s[ix[1]], s2 = s[ix[2]], s3 = s[ix[3]];
+        double saa, s1, s2, s3;
+        if (staged) {
+          const double* s = S + rec.x * 10;
+          const unsigned char* ix = s_sidx[lj];
+          saa = s[ix[0]]; s1 = s[ix[1]]; s2 = s[ix[2]]; s3 = s[ix[3]];
+        } else {
+          vertex_S(p.g, (i64)rec.x, lj, p.factor, saa, s1, s2, s3);
+        }
         const double m = -0.2 * saa;
-        acc_add(a, rec.y & 255u, 0.6 * saa);
-        acc_add(a, (rec.y >> 8) & 255u, -0.2 * s1);
-        acc_add(a, (rec.y >> 16) & 255u, -0.2 * s2);
-        acc_add(a, rec.y >> 24, -0.2 * s3);
-        acc_add(a, rec.z & 255u, 0.6 * s1 + m);
-        acc_add(a, (rec.z >> 8) & 255u, 0.6 * s2 + m);
-        acc_add(a, (rec.z >> 16) & 255u, 0.6 * s3 + m);
-        acc_add(a, rec.z >> 24, -0.2 * (s1 + s2));
-        acc_add(a, rec.w & 255u, -0.2 * (s1 + s3));
-        acc_add(a, (rec.w >> 8) & 255u, -0.2 * (s2 + s3));
+        v[0] = 0.6 * saa;
+        v[1] = -0.2 * s1; v[2] = -0.2 * s2; v[3] = -0.2 * s3;
+        v[4] = 0.6 * s1 + m; v[5] = 0.6 * s2 + m; v[6] = 0.6 * s3 + m;
+        v[7] = -0.2 * (s1 + s2); v[8] = -0.2 * (s1 + s3); v[9] = -0.2 * (s2 + s3);
       } else {
+        const double* s = S + rec.x * 10;
+        const unsigned char* ix = s_sidx[lj];
         const double spp = s[ix[0]], sqq = s[ix[1]], spq = s[ix[2]], spr = s[ix[3]], sps = s[ix[4]], sqr = s[ix[5]], sqs = s[ix[6]];
-        acc_add(a, rec.y & 255u, 0.6 * spq - 0.2 * spp);
-        acc_add(a, (rec.y >> 8) & 255u, 0.6 * spq - 0.2 * sqq);
-        acc_add(a, (rec.y >> 16) & 255u, -0.2 * (spr + sqr));
-        acc_add(a, rec.y >> 24, -0.2 * (sps + sqs));
-        acc_add(a, rec.z & 255u, 1.6 * (spp + sqq + spq));
-        acc_add(a, (rec.z >> 8) & 255u, 0.8 * (2.0 * sqr + spq + spr + spp));
-        acc_add(a, (rec.z >> 16) & 255u, 0.8 * (2.0 * sqs + spq + sps + spp));
-        acc_add(a, rec.z >> 24, 0.8 * (2.0 * spr + spq + sqr + sqq));
-        acc_add(a, rec.w & 255u, 0.8 * (2.0 * sps + spq + sqs + sqq));
-        acc_add(a, (rec.w >> 8) & 255u, 0.8 * (spr + sps + sqr + sqs));
+        v[0] = 0.6 * spq - 0.2 * spp;
+        v[1] = 0.6 * spq - 0.2 * sqq;
+        v[2] = -0.2 * (spr + sqr);
+        v[3] = -0.2 * (sps + sqs);
+        v[4] = 1.6 * (spp + sqq + spq);
+        v[5] = 0.8 * (2.0 * sqr + spq + spr + spp);
+        v[6] = 0.8 * (2.0 * sqs + spq + sps + spp);
+        v[7] = 0.8 * (2.0 * spr + spq + sqr + sqq);
+        v[8] = 0.8 * (2.0 * sps + spq + sqs + sqq);
+        v[9] = 0.8 * (spr + sps + sqr + sqs);
       }
+      // the 10 rows of one pair are distinct slots: read all, then write all (no dependent RMW chain)
+      u32 o[10];
+      o[0] = rec.y & 255u; o[1] = (rec.y >> 8) & 255u; o[2] = (rec.y >> 16) & 255u; o[3] = rec.y >> 24;
+      o[4] = rec.z & 255u; o[5] = (rec.z >> 8) & 255u; o[6] = (rec.z >> 16) & 255u; o[7] = rec.z >> 24;
+      o[8] = rec.w & 255u; o[9] = (rec.w >> 8) & 255u;
+      double c[10];
+#pragma unroll
+      for (int r = 0; r < 10; r++) c[r] = (o[r] != 255u) ? a[o[r]] : 0.0;
+#pragma unroll
+      for (int r = 0; r < 10; r++)
+        if (o[r] != 255u) a[o[r]] = c[r] + v[r];
     }
   }
   __syncthreads();
@@ -245,9 +291,10 @@ bool fast_p2tet_applicable(const BlfLocalParams& p) {
 }
 
 int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const std::vector<double>& w,
-                     const std::vector<double>& derivs, FastP2Tet* out) {
+                     const std::vector<double>& derivs, i64 ncols_owned, FastP2Tet* out) {
   cudaStream_t s = ctx->stream;
   const i64 ncells = p.g.ncells, ncols = pat.ncols;
+  const i64 ncols_tiled = (ncols_owned >= 0 && ncols_owned < ncols) ? ncols_owned : ncols;   // halo columns belong to another rank
   out->ntiles = 0;
   // (0) the caller's tables must be the standard P2 basis integrated exactly
   {
@@ -265,44 +312,52 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   DofGather dg;
   GRMP_TRY(build_dofgather(s, p.e1.celldofs, ncells, 10, ncols, &dg));
   const i64 npairs = dg.ncontrib;
-  std::vector<u32> h_cell(npairs);
+  std::vector<u32> h_cell(npairs), h_src(npairs);
   std::vector<i64> h_pairbeg(ncols + 1), h_colptr(ncols + 1);
   GRMP_CUDA(cudaMemcpyAsync(h_cell.data(), dg.gcell.p, npairs * 4, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaMemcpyAsync(h_src.data(), dg.gsrc.p, npairs * 4, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaMemcpyAsync(h_pairbeg.data(), dg.segptr.p, (ncols + 1) * 8, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaMemcpyAsync(h_colptr.data(), pat.colptr.p, (ncols + 1) * 8, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaStreamSynchronize(s));
   // (2) greedy tiles over the column range (host; one pass over the pairs)
   std::vector<i32> tile_colbeg{0}, tile_cellbeg{0}, tile_cells;
-  std::vector<unsigned short> pair_local(npairs);
+  std::vector<u32> pair_x(npairs);
+  int cur_direct = -1;   // mode of the open tile: 1 = direct (vertex columns, geometry per pair), 0 = staged
   std::vector<i32> mark(ncells, -1), local_of(ncells, 0);
   tile_cells.reserve((size_t)ncells * 4);
   int cur_tile = 0, cur_cols = 0, cur_cells = 0;
   i64 cur_nnz = 0;
   int max_smem = 0, max_cells = 0;
-  for (i64 j = 0; j < ncols; j++) {
+  for (i64 j = 0; j < ncols_tiled; j++) {
     const i64 len = h_colptr[j + 1] - h_colptr[j];
     if (len > 254) return fail(GRMP_EUNSUPPORTED, "fast path: a column has more than 254 entries");
+    const bool has_pairs = h_pairbeg[j + 1] > h_pairbeg[j];
+    const int direct = (has_pairs && (h_src[h_pairbeg[j]] / (u32)ncells) < 4) ? 1 : 0;   // vertex dof of the P2 element
     for (int attempt = 0; attempt < 2; attempt++) {
       int fresh = 0;
-      for (i64 k = h_pairbeg[j]; k < h_pairbeg[j + 1]; k++) if (mark[h_cell[k]] != cur_tile) fresh++;
+      if (!direct)
+        for (i64 k = h_pairbeg[j]; k < h_pairbeg[j + 1]; k++) if (mark[h_cell[k]] != cur_tile) fresh++;
       const i64 need = 8 * (cur_nnz + len) + 80 * (i64)(cur_cells + fresh);
-      if (cur_cols > 0 && (cur_cols + 1 > MAX_TILE_COLS || need > SMEM_BUDGET || cur_cells + fresh > 65535)) {
+      const i64 budget = direct ? SMEM_BUDGET_DIRECT : SMEM_BUDGET;
+      if (cur_cols > 0 && (cur_cols + 1 > MAX_TILE_COLS || need > budget || direct != cur_direct)) {
         tile_colbeg.push_back((i32)j); tile_cellbeg.push_back((i32)tile_cells.size());
         max_smem = std::max<i64>(max_smem, 8 * cur_nnz + 80 * (i64)cur_cells); max_cells = std::max(max_cells, cur_cells);
         cur_tile++; cur_cols = 0; cur_cells = 0; cur_nnz = 0;
         continue;   // re-evaluate the column in the fresh tile
       }
+      cur_direct = direct;
       for (i64 k = h_pairbeg[j]; k < h_pairbeg[j + 1]; k++) {
         const u32 c = h_cell[k];
+        if (direct) { pair_x[k] = c; continue; }
         if (mark[c] != cur_tile) { mark[c] = cur_tile; local_of[c] = cur_cells++; tile_cells.push_back((i32)c); }
-        pair_local[k] = (unsigned short)local_of[c];
+        pair_x[k] = (u32)local_of[c];
       }
       cur_cols++; cur_nnz += len;
       break;
     }
   }
-  if (cur_cols > 0 || ncols == 0) {
-    tile_colbeg.push_back((i32)ncols); tile_cellbeg.push_back((i32)tile_cells.size());
+  if (cur_cols > 0 || ncols_tiled == 0) {
+    tile_colbeg.push_back((i32)ncols_tiled); tile_cellbeg.push_back((i32)tile_cells.size());
     max_smem = std::max<i64>(max_smem, 8 * cur_nnz + 80 * (i64)cur_cells); max_cells = std::max(max_cells, cur_cells);
   }
   if (max_smem > 200 * 1024) return fail(GRMP_EUNSUPPORTED, "fast path: a single column exceeds the shared-memory tile");
@@ -311,8 +366,8 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   GRMP_TRY(out->tile_colbeg.upload(tile_colbeg.data(), tile_colbeg.size(), s));
   GRMP_TRY(out->tile_cellbeg.upload(tile_cellbeg.data(), tile_cellbeg.size(), s));
   GRMP_TRY(out->tile_cells.upload(tile_cells.data(), tile_cells.size(), s));
-  DevBuf<unsigned short> d_local;
-  GRMP_TRY(d_local.upload(pair_local.data(), npairs, s));
+  DevBuf<u32> d_local;
+  GRMP_TRY(d_local.upload(pair_x.data(), npairs, s));
   // (3) pack the 16-byte pair records on the device
   GRMP_TRY(out->pairs.alloc(npairs));
   GRMP_TRY(out->col_pairbeg.alloc(ncols + 1));

@@ -101,12 +101,16 @@ int grmp_grid_set_faces(grmp_grid* grid, int64_t nfaces, const int32_t* cellface
                         const int32_t* cellfaceorient, const double* facenormals, const double* facevolumes);
 /* re-upload coordinates / volumes of an existing grid (moving meshes, the e2e bench step) */
 int grmp_grid_update_geometry(grmp_grid* grid, const double* coords, const double* cellvolumes);
+/* re-upload CellNodes of an existing grid (same sizes; used by the end-to-end benchmark step) */
+int grmp_grid_update_cells(grmp_grid* grid, const int32_t* cellnodes);
 int grmp_grid_destroy(grmp_grid* grid);
 
 /* FESpace + CellDofs (src/finiteelements.jl:42-49, src/dofmaps.jl:201-363): the dof map is
  * produced by the host (Julia: FES[CellDofs].colentries) */
 int grmp_space_create(grmp_grid* grid, int fetype, int ncomp, int64_t ndofs, int nd_cell, const int32_t* celldofs,
                       grmp_space** out);
+/* re-upload CellDofs of an existing space (same sizes) */
+int grmp_space_update_dofs(grmp_space* space, const int32_t* celldofs);
 int grmp_space_destroy(grmp_space* space);
 
 /* AssemblyPattern{APT_BilinearForm...} + prepare_assembly! (bilinearform.jl:60-64,
@@ -136,6 +140,13 @@ int grmp_blf_get_pattern(grmp_blf* blf, int64_t* colptr, int64_t* rowval);
  * on the device; fetch later with grmp_blf_get_values). */
 int grmp_blf_numeric(grmp_blf* blf, double factor, double* nzval_host);
 int grmp_blf_get_values(grmp_blf* blf, double* nzval_host);
+/* nsteps back-to-back numeric assemblies bracketed by ONE pair of CUDA events on the launching
+ * stream (benchmarking / time loops that reassemble every step); total_ms receives the device time */
+int grmp_blf_numeric_steps(grmp_blf* blf, double factor, int nsteps, double* total_ms);
+/* Multi-GPU column ownership: only columns [0, ncols_owned) are assembled by the fast path (the
+ * host numbers the columns a rank owns first; halo columns belong to another rank, DESIGN.md
+ * "multi-GPU").  Call before grmp_blf_symbolic; ncols_owned < 0 restores "all columns". */
+int grmp_blf_set_owned_columns(grmp_blf* blf, int64_t ncols_owned);
 /* transpose_copy block (bilinearform.jl:358-364): CSC of the mirrored block with values
  * v * itemfactor / factor * factor_transpose * (-1), summed per entry in cell order.
  * Sizes: colptr_t[nrows+1], rowval_t[nnz], nzval_t[nnz]. Requires a prior numeric call. */
