@@ -112,38 +112,6 @@ def build_problem(level):
     return G, g, s, time.time() - t
 
 
-def partition(G, g, s, rank, world):
-    """cells [rank*nc/P, (rank+1)*nc/P) ; a dof is owned by the rank of its lowest-numbered cell;
-    local problem = own cells + halo cells touching owned dofs, owned dofs numbered first."""
-    nc = g.ncells
-    bounds = [(nc * r) // world for r in range(world + 1)]
-    dofs = s.celldofs.astype(np.int64) - 1
-    first_cell = np.full(s.ndofs, nc, dtype=np.int64)
-    np.minimum.at(first_cell, dofs.ravel(), np.repeat(np.arange(nc, dtype=np.int64), dofs.shape[1]))
-    owner = np.searchsorted(np.array(bounds[1:]), first_cell, side="right")
-    owned = owner == rank
-    cell_mask = owned[dofs].any(axis=1)
-    cells = np.nonzero(cell_mask)[0]
-    ldofs = dofs[cells]
-    used = np.zeros(s.ndofs, bool)
-    used[ldofs.ravel()] = True
-    order = np.concatenate([np.nonzero(used & owned)[0], np.nonzero(used & ~owned)[0]])
-    newid = np.full(s.ndofs, -1, dtype=np.int64)
-    newid[order] = np.arange(order.size)
-    n_owned = int((used & owned).sum())
-    # local grid (node renumbering keeps the library's inputs compact)
-    cn = g.cellnodes[cells].astype(np.int64) - 1
-    nodes = np.unique(cn)
-    nmap = np.full(g.nnodes, -1, dtype=np.int64)
-    nmap[nodes] = np.arange(nodes.size)
-    lg = G.ExtendableGrid(g.coords[nodes], nmap[cn] + 1, g.cellregions[cells])
-    lg._cache["vol"] = np.ascontiguousarray(g.cellvolumes[cells])
-    ls = G.FESpace(G.H1P2(1, 3), lg)
-    ls._celldofs = np.ascontiguousarray(newid[ldofs] + 1, dtype=np.int32)
-    ls.ndofs = int(order.size)
-    return lg, ls, n_owned, order
-
-
 def run_gpu(args):
     import ctypes as C
     import torch
@@ -159,7 +127,8 @@ def run_gpu(args):
     G, g, s, t_grid = build_problem(args.level)
     L = G._lib.lib()
     if world > 1:
-        lg, ls, n_owned, order = partition(G, g, s, rank, world)
+        lp = G.partition.partition(s, rank, world)
+        lg, ls, n_owned = lp.grid, lp.space, lp.n_owned
     else:
         lg, ls, n_owned = g, s, s.ndofs
     AP = G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [ls, ls])
@@ -168,6 +137,9 @@ def run_gpu(args):
     if args.path != "auto":
         G._lib.check(L.grmp_blf_set_path(h, {"generic": 1, "fast": 2}[args.path]))
     if world > 1:
+        G._lib.check(L.grmp_blf_set_owned_columns(h, n_owned))
+    elif args.owned_cols >= 0:      # experiment: time only the first columns (e.g. the vertex columns)
+        n_owned = args.owned_cols
         G._lib.check(L.grmp_blf_set_owned_columns(h, n_owned))
     nnz = C.c_int64(0)
     t0 = time.time()
@@ -345,6 +317,7 @@ def main():
     ap.add_argument("--level", type=int, default=6)
     ap.add_argument("--cpu-level", type=int, default=5)
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--owned-cols", type=int, default=-1)
     ap.add_argument("--path", default="auto", choices=["auto", "generic", "fast"])
     args = ap.parse_args()
     if args.impl == "reference":

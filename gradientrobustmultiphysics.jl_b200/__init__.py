@@ -21,4 +21,4 @@ from .assembly import (Identity, Gradient, SymmetricGradient, Divergence, Recons
                        blf_stats, quadrature_order, device_grid, device_space)
 from .operators import (PDEOperator, LaplaceOperator, ReactionOperator, LagrangeMultiplier, HookStiffnessOperator2D,
                         HookStiffnessOperator3D, BilinearForm, LinearForm, create_assembly_pattern, assemble_operator)
-from . import _lib
+from . import _lib, partition

@@ -30,7 +30,7 @@ namespace {
 constexpr int TPB = 128;             // threads per tile
 constexpr int MAX_TILE_COLS = 128;
 constexpr int SMEM_BUDGET = 56 * 1024;          // staged tiles: nzval slots + S of the distinct cells
-constexpr int SMEM_BUDGET_DIRECT = 64 * 1024;   // direct tiles (vertex columns): nzval slots only
+constexpr int SMEM_BUDGET_DIRECT = 56 * 1024;   // direct tiles (vertex columns): nzval slots + 32 B per pair
 
 // local edge e -> (p,q), Tetrahedron3D edges [1 2],[1 3],[1 4],[2 3],[2 4],[3 4] (h1_p2.jl:231-236)
 __host__ __device__ inline void edge_nodes(int e, int& p, int& q) {
@@ -167,15 +167,54 @@ __device__ __forceinline__ void vertex_S(const GridView& g, i64 cell, int a, dou
   s3 = (a <= 2) ? d3 : d2;
 }
 
+// add the 10 values of one pair into the column's slots; the 10 rows of a pair are distinct slots,
+// so all reads are issued before the writes (no dependent read-modify-write chain)
+__device__ __forceinline__ void pair_update(double* a, const uint4& rec, const double* v) {
+  u32 o[10];
+  o[0] = rec.y & 255u; o[1] = (rec.y >> 8) & 255u; o[2] = (rec.y >> 16) & 255u; o[3] = rec.y >> 24;
+  o[4] = rec.z & 255u; o[5] = (rec.z >> 8) & 255u; o[6] = (rec.z >> 16) & 255u; o[7] = rec.z >> 24;
+  o[8] = rec.w & 255u; o[9] = (rec.w >> 8) & 255u;
+  double c[10];
+#pragma unroll
+  for (int r = 0; r < 10; r++) c[r] = (o[r] != 255u) ? a[o[r]] : 0.0;
+#pragma unroll
+  for (int r = 0; r < 10; r++)
+    if (o[r] != 255u) a[o[r]] = c[r] + v[r];
+}
+
+__device__ __forceinline__ void vertex_values(double saa, double s1, double s2, double s3, double* v) {
+  const double m = -0.2 * saa;
+  v[0] = 0.6 * saa;
+  v[1] = -0.2 * s1; v[2] = -0.2 * s2; v[3] = -0.2 * s3;
+  v[4] = 0.6 * s1 + m; v[5] = 0.6 * s2 + m; v[6] = 0.6 * s3 + m;
+  v[7] = -0.2 * (s1 + s2); v[8] = -0.2 * (s1 + s3); v[9] = -0.2 * (s2 + s3);
+}
+
+__device__ __forceinline__ void edge_values(const double* s, const unsigned char* ix, double* v) {
+  const double spp = s[ix[0]], sqq = s[ix[1]], spq = s[ix[2]], spr = s[ix[3]], sps = s[ix[4]], sqr = s[ix[5]], sqs = s[ix[6]];
+  v[0] = 0.6 * spq - 0.2 * spp;
+  v[1] = 0.6 * spq - 0.2 * sqq;
+  v[2] = -0.2 * (spr + sqr);
+  v[3] = -0.2 * (sps + sqs);
+  v[4] = 1.6 * (spp + sqq + spq);
+  v[5] = 0.8 * (2.0 * sqr + spq + spr + spp);
+  v[6] = 0.8 * (2.0 * sqs + spq + sps + spp);
+  v[7] = 0.8 * (2.0 * spr + spq + sqr + sqq);
+  v[8] = 0.8 * (2.0 * sps + spq + sqs + sqq);
+  v[9] = 0.8 * (spr + sps + sqr + sqs);
+}
+
+constexpr int PF = 4;   // pair records fetched per batch (independent 16-byte loads in flight per thread)
+
 __global__ void __launch_bounds__(TPB) p2tet_tile_kernel(const TileParams p) {
   extern __shared__ double sm[];
   __shared__ unsigned char s_sidx[10][8];   // packed-S positions needed by a column of local dof lj
   const int tile = blockIdx.x, tid = threadIdx.x;
   const int c0 = p.tile_colbeg[tile], c1 = p.tile_colbeg[tile + 1];
+  const int cb = p.tile_cellbeg[tile], nct = p.tile_cellbeg[tile + 1] - cb;
   const i64 g0 = p.colptr[c0] - 1, g1 = p.colptr[c1] - 1;
   const int nnz_t = (int)(g1 - g0);
-  const int cb = p.tile_cellbeg[tile], nct = p.tile_cellbeg[tile + 1] - cb;
-  const bool staged = nct > 0;          // direct tiles (vertex columns) carry global cell ids and no S stage
+  const bool staged = nct > 0;          // staged: S of the distinct cells in smem; direct: per-pair values in smem
   double* acc = sm;
   double* S = sm + nnz_t;
   if (tid < 10) {
@@ -195,65 +234,102 @@ __global__ void __launch_bounds__(TPB) p2tet_tile_kernel(const TileParams p) {
       s_sidx[tid][7] = 0;
     }
   }
-  for (int i = tid; i < nnz_t; i += TPB) acc[i] = 0.0;
-  for (int i = tid; i < nct; i += TPB) {
-    double s[10];
-    cell_S(p.g, p.tile_cells[cb + i], p.factor, s);
-#pragma unroll
-    for (int k = 0; k < 10; k++) S[i * 10 + k] = s[k];
+  // this thread's column (tiles hold at most TPB columns) and its first batch of pair records:
+  // issued before the geometry phase so that the loads overlap it
+  const int col = c0 + tid;
+  const bool has_col = col < c1;
+  i64 kb = 0, ke = 0;
+  int abase = 0;
+  if (has_col) {
+    kb = p.col_pairbeg[col]; ke = p.col_pairbeg[col + 1];
+    abase = (int)(p.colptr[col] - 1 - g0);
   }
-  __syncthreads();
-  for (int col = c0 + tid; col < c1; col += TPB) {
-    double* a = acc + (int)(p.colptr[col] - 1 - g0);
-    i64 k = p.col_pairbeg[col];
-    const i64 ke = p.col_pairbeg[col + 1];
-    uint4 nxt = make_uint4(0, 0, 0, 0);
-    if (k < ke) nxt = p.pairs[k];
-    for (; k < ke; k++) {
-      const uint4 rec = nxt;
-      if (k + 1 < ke) nxt = p.pairs[k + 1];          // software prefetch of the next 16-byte record
-      const int lj = (int)((rec.w >> 16) & 255u);
-      double v[10];
-      if (lj < 4) {
-        double saa, s1, s2, s3;
-        if (staged) {
-          const double* s = S + rec.x * 10;
-          const unsigned char* ix = s_sidx[lj];
-          saa = s[ix[0]]; s1 = s[ix[1]]; s2 = s[ix[2]]; s3 = s[ix[3]];
-        } else {
-          vertex_S(p.g, (i64)rec.x, lj, p.factor, saa, s1, s2, s3);
-        }
-        const double m = -0.2 * saa;
-        v[0] = 0.6 * saa;
-        v[1] = -0.2 * s1; v[2] = -0.2 * s2; v[3] = -0.2 * s3;
-        v[4] = 0.6 * s1 + m; v[5] = 0.6 * s2 + m; v[6] = 0.6 * s3 + m;
-        v[7] = -0.2 * (s1 + s2); v[8] = -0.2 * (s1 + s3); v[9] = -0.2 * (s2 + s3);
-      } else {
-        const double* s = S + rec.x * 10;
-        const unsigned char* ix = s_sidx[lj];
-        const double spp = s[ix[0]], sqq = s[ix[1]], spq = s[ix[2]], spr = s[ix[3]], sps = s[ix[4]], sqr = s[ix[5]], sqs = s[ix[6]];
-        v[0] = 0.6 * spq - 0.2 * spp;
-        v[1] = 0.6 * spq - 0.2 * sqq;
-        v[2] = -0.2 * (spr + sqr);
-        v[3] = -0.2 * (sps + sqs);
-        v[4] = 1.6 * (spp + sqq + spq);
-        v[5] = 0.8 * (2.0 * sqr + spq + spr + spp);
-        v[6] = 0.8 * (2.0 * sqs + spq + sps + spp);
-        v[7] = 0.8 * (2.0 * spr + spq + sqr + sqq);
-        v[8] = 0.8 * (2.0 * sps + spq + sqs + sqq);
-        v[9] = 0.8 * (spr + sps + sqr + sqs);
+  uint4 rec[PF];
+#pragma unroll
+  for (int j = 0; j < PF; j++) rec[j] = (kb + j < ke) ? p.pairs[kb + j] : make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < nnz_t; i += TPB) acc[i] = 0.0;
+
+  if (staged) {
+    // ---- geometry of the tile's distinct cells, two cells per thread and round (independent loads) ----
+    for (int i = tid; i < nct; i += 2 * TPB) {
+      const int i2 = i + TPB;
+      const i64 cA = p.tile_cells[cb + i];
+      const i64 cB = (i2 < nct) ? p.tile_cells[cb + i2] : cA;
+      double sA[10], sB[10];
+      cell_S(p.g, cA, p.factor, sA);
+      cell_S(p.g, cB, p.factor, sB);
+#pragma unroll
+      for (int k = 0; k < 10; k++) S[i * 10 + k] = sA[k];
+      if (i2 < nct) {
+#pragma unroll
+        for (int k = 0; k < 10; k++) S[i2 * 10 + k] = sB[k];
       }
-      // the 10 rows of one pair are distinct slots: read all, then write all (no dependent RMW chain)
-      u32 o[10];
-      o[0] = rec.y & 255u; o[1] = (rec.y >> 8) & 255u; o[2] = (rec.y >> 16) & 255u; o[3] = rec.y >> 24;
-      o[4] = rec.z & 255u; o[5] = (rec.z >> 8) & 255u; o[6] = (rec.z >> 16) & 255u; o[7] = rec.z >> 24;
-      o[8] = rec.w & 255u; o[9] = (rec.w >> 8) & 255u;
-      double c[10];
+    }
+    __syncthreads();
+    if (has_col) {
+      double* a = acc + abase;
+      for (i64 k = kb; k < ke; k += PF) {
+        uint4 cur[PF];
 #pragma unroll
-      for (int r = 0; r < 10; r++) c[r] = (o[r] != 255u) ? a[o[r]] : 0.0;
+        for (int j = 0; j < PF; j++) cur[j] = rec[j];
 #pragma unroll
-      for (int r = 0; r < 10; r++)
-        if (o[r] != 255u) a[o[r]] = c[r] + v[r];
+        for (int j = 0; j < PF; j++) rec[j] = (k + PF + j < ke) ? p.pairs[k + PF + j] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < PF; j++) {
+          if (k + j < ke) {
+            const int lj = (int)((cur[j].w >> 16) & 255u);
+            const double* s = S + cur[j].x * 10;
+            const unsigned char* ix = s_sidx[lj];
+            double v[10];
+            if (lj < 4) vertex_values(s[ix[0]], s[ix[1]], s[ix[2]], s[ix[3]], v);
+            else edge_values(s, ix, v);
+            pair_update(a, cur[j], v);
+          }
+        }
+      }
+    }
+  } else {
+    // ---- direct tile (vertex columns): phase 1, one thread per PAIR computes its four S values from the
+    //      coordinates (PF pairs per thread in flight); phase 2, one thread per column accumulates ----
+    const i64 kt0 = p.col_pairbeg[c0], kt1 = p.col_pairbeg[c1];
+    const int npt = (int)(kt1 - kt0);
+    for (int q0 = 0; q0 < npt; q0 += PF * TPB) {
+      uint4 r4[PF];
+#pragma unroll
+      for (int j = 0; j < PF; j++) {
+        const int q = q0 + j * TPB + tid;
+        r4[j] = (q < npt) ? p.pairs[kt0 + q] : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int j = 0; j < PF; j++) {
+        const int q = q0 + j * TPB + tid;
+        if (q < npt) {
+          double saa, s1, s2, s3;
+          vertex_S(p.g, (i64)r4[j].x, (int)((r4[j].w >> 16) & 255u), p.factor, saa, s1, s2, s3);
+          double* st = S + (size_t)q * 4;
+          st[0] = saa; st[1] = s1; st[2] = s2; st[3] = s3;
+        }
+      }
+    }
+    __syncthreads();
+    if (has_col) {
+      double* a = acc + abase;
+      for (i64 k = kb; k < ke; k += PF) {
+        uint4 cur[PF];
+#pragma unroll
+        for (int j = 0; j < PF; j++) cur[j] = rec[j];
+#pragma unroll
+        for (int j = 0; j < PF; j++) rec[j] = (k + PF + j < ke) ? p.pairs[k + PF + j] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < PF; j++) {
+          if (k + j < ke) {
+            const double* st = S + (size_t)(k + j - kt0) * 4;
+            double v[10];
+            vertex_values(st[0], st[1], st[2], st[3], v);
+            pair_update(a, cur[j], v);
+          }
+        }
+      }
     }
   }
   __syncthreads();
@@ -326,7 +402,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   std::vector<i32> mark(ncells, -1), local_of(ncells, 0);
   tile_cells.reserve((size_t)ncells * 4);
   int cur_tile = 0, cur_cols = 0, cur_cells = 0;
-  i64 cur_nnz = 0;
+  i64 cur_nnz = 0, cur_pairs = 0;
   int max_smem = 0, max_cells = 0;
   for (i64 j = 0; j < ncols_tiled; j++) {
     const i64 len = h_colptr[j + 1] - h_colptr[j];
@@ -337,12 +413,13 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
       int fresh = 0;
       if (!direct)
         for (i64 k = h_pairbeg[j]; k < h_pairbeg[j + 1]; k++) if (mark[h_cell[k]] != cur_tile) fresh++;
-      const i64 need = 8 * (cur_nnz + len) + 80 * (i64)(cur_cells + fresh);
+      const i64 npj = h_pairbeg[j + 1] - h_pairbeg[j];
+      const i64 need = direct ? 8 * (cur_nnz + len) + 32 * (cur_pairs + npj) : 8 * (cur_nnz + len) + 80 * (i64)(cur_cells + fresh);
       const i64 budget = direct ? SMEM_BUDGET_DIRECT : SMEM_BUDGET;
       if (cur_cols > 0 && (cur_cols + 1 > MAX_TILE_COLS || need > budget || direct != cur_direct)) {
         tile_colbeg.push_back((i32)j); tile_cellbeg.push_back((i32)tile_cells.size());
-        max_smem = std::max<i64>(max_smem, 8 * cur_nnz + 80 * (i64)cur_cells); max_cells = std::max(max_cells, cur_cells);
-        cur_tile++; cur_cols = 0; cur_cells = 0; cur_nnz = 0;
+        max_smem = std::max<i64>(max_smem, 8 * cur_nnz + (cur_direct ? 32 * cur_pairs : 80 * (i64)cur_cells)); max_cells = std::max(max_cells, cur_cells);
+        cur_tile++; cur_cols = 0; cur_cells = 0; cur_nnz = 0; cur_pairs = 0;
         continue;   // re-evaluate the column in the fresh tile
       }
       cur_direct = direct;
@@ -352,13 +429,13 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
         if (mark[c] != cur_tile) { mark[c] = cur_tile; local_of[c] = cur_cells++; tile_cells.push_back((i32)c); }
         pair_x[k] = (u32)local_of[c];
       }
-      cur_cols++; cur_nnz += len;
+      cur_cols++; cur_nnz += len; cur_pairs += npj;
       break;
     }
   }
   if (cur_cols > 0 || ncols_tiled == 0) {
     tile_colbeg.push_back((i32)ncols_tiled); tile_cellbeg.push_back((i32)tile_cells.size());
-    max_smem = std::max<i64>(max_smem, 8 * cur_nnz + 80 * (i64)cur_cells); max_cells = std::max(max_cells, cur_cells);
+    max_smem = std::max<i64>(max_smem, 8 * cur_nnz + (cur_direct == 1 ? 32 * cur_pairs : 80 * (i64)cur_cells)); max_cells = std::max(max_cells, cur_cells);
   }
   if (max_smem > 200 * 1024) return fail(GRMP_EUNSUPPORTED, "fast path: a single column exceeds the shared-memory tile");
   out->ntiles = (int)tile_colbeg.size() - 1;

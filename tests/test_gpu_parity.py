@@ -324,3 +324,43 @@ def test_auto_path_prefers_fast_for_metric_form_only():
     with pytest.raises(G._lib.GrmpError):
         G.blf_set_path(AP2, G._lib.PATH_FAST)
         G.assemble_csc(AP2, 1.0)
+
+
+def test_partitioned_assembly_matches_global():
+    """multi-GPU path on one device: every 'rank' assembles its owned columns (fast path restricted by
+    grmp_blf_set_owned_columns), the merged column blocks equal the single-rank matrix"""
+    g = tet_grid(2, True)
+    s = G.FESpace(G.H1P2(1, 3), g)
+    AP = G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [s, s])
+    G.blf_set_path(AP, G._lib.PATH_GENERIC)
+    cp, rv, nz = G.assemble_csc(AP, 1.0)
+    world = 3
+    blocks = []
+    for r in range(world):
+        lp = G.partition.partition(s, r, world)
+        APr = G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [lp.space, lp.space])
+        G.prepare_assembly(APr)
+        G._lib.check(G._lib.lib().grmp_blf_set_owned_columns(APr.AM.h, lp.n_owned))
+        lcp, lrv, lnz = G.assemble_csc(APr, 1.0, skip_preps=True)
+        assert G.blf_stats(APr).path == G._lib.PATH_FAST
+        blocks.append(G.partition.owned_block_to_global(lp, lcp, lrv, lnz))
+    mcp, mrv, mnz = G.partition.merge_owned_columns(s.ndofs, blocks)
+    assert np.array_equal(mcp, cp) and np.array_equal(mrv, rv)
+    assert rel_err(mnz, nz) <= RTOL
+
+
+import glob
+import os
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_gpu_against_committed_golden_fixtures(path):
+    from golden.make_golden import CASES as GC, build_case
+    d = np.load(path)
+    name = os.path.basename(path)[:-4]
+    grid, space, AP, factor = build_case(G, GC[name])
+    G.blf_set_path(AP, G._lib.PATH_GENERIC)
+    cp, rv, nz = G.assemble_csc(AP, factor)
+    assert np.array_equal(cp, d["colptr"]) and np.array_equal(rv, d["rowval"]) and np.array_equal(nz, d["nzval"])

@@ -185,3 +185,23 @@ def test_oracle_pattern_is_subset_of_structural_pattern_and_perturbed_is_structu
     sp = G.FESpace(G.H1P2(1, 3), gp)
     assert n_axis <= structural
     assert nnz(gp, sp) <= structural
+
+
+def test_oracle_reproduces_committed_golden_fixtures():
+    import glob
+    from golden.make_golden import CASES, build_case, oracle_csc
+    files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
+    assert len(files) == len(CASES)
+    for f in files:
+        name = os.path.basename(f)[:-4]
+        g, s, AP, factor = build_case(G, CASES[name])
+        cp, rv, nz = oracle_csc(O, g, s, AP, factor)
+        d = np.load(f)
+        assert np.array_equal(cp, d["colptr"]) and np.array_equal(rv, d["rowval"]) and np.array_equal(nz, d["nzval"]), name
+    # the closed-form anchor of the reference tree (examples/ExampleA01_RationalMassMatrix.jl:17-35)
+    d = np.load(os.path.join(ROOT, "tests", "golden", "A01_P1_mass_reference_triangle.npz"))
+    M = np.zeros((3, 3))
+    for j in range(3):
+        for k in range(d["colptr"][j] - 1, d["colptr"][j + 1] - 1):
+            M[d["rowval"][k] - 1, j] = d["nzval"][k]
+    assert np.abs(M - 0.5 / 12 * np.array([[2, 1, 1], [1, 2, 1], [1, 1, 2]])).max() < 1e-16
