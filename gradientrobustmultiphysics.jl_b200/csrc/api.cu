@@ -165,7 +165,7 @@ static int blf_numeric_launch(grmp_blf* b, BlfLocalParams& p, cudaStream_t s) {
   grmp_ctx* ctx = b->s1->grid->ctx;
   if (b->path == GRMP_PATH_FAST) {
     GRMP_TRY(fast_p2tet_numeric(ctx, p, b->pat, b->fast, b->nzval.p));
-    b->st.kernel_launches = 1;
+    b->st.kernel_launches = 2;
   } else {
     const size_t nl = (size_t)p.e1.nd * p.e2.nd * p.g.ncells;
     if (b->lbuf.n != nl) GRMP_TRY(b->lbuf.alloc(nl));
@@ -349,13 +349,14 @@ int grmp_blf_symbolic(grmp_blf* b, double factor, int64_t* nnz_out) {
   p.keys = keys.p;
   GRMP_TRY(launch_blf_local(p, s));
   GRMP_TRY(build_pattern(s, keys, ncells * nloc, b->out_rows(), b->out_cols(), ncells, p.e1.nd, p.e2.nd, b->apt == GRMP_APT_SYMMETRIC,
-                         want_fast, &b->pat));
+                         false /* the fast path looks slots up by (row, col); no per-cell local->nnz map needed */, &b->pat));
   GRMP_TRY(b->nzval.alloc(b->pat.nnz));
   b->path = GRMP_PATH_GENERIC;
   if (want_fast) {
-    GRMP_TRY(fast_p2tet_build(ctx, p, b->pat, b->w_host, b->t1_derivs_host, b->ncols_owned, &b->fast));
+    const int rc = fast_p2tet_build(ctx, p, b->pat, b->w_host, b->t1_derivs_host, b->ncols_owned, &b->fast);
     b->pat.slotmap.release();
-    b->path = GRMP_PATH_FAST;
+    if (rc == GRMP_OK) b->path = GRMP_PATH_FAST;
+    else if (rc != GRMP_EUNSUPPORTED || b->path_req == GRMP_PATH_FAST) return rc;   // AUTO: grids the fast path cannot order use the generic path
   }
   GRMP_CUDA(cudaEventRecord(ctx->ev1, s));
   GRMP_CUDA(cudaStreamSynchronize(s));

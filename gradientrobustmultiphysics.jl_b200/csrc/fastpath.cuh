@@ -15,8 +15,10 @@ struct FastP2Tet {
   DevBuf<i32> tile_cellbeg;    // [ntiles+1] range into tile_cells
   DevBuf<i32> tile_cells;      // distinct cells of every tile
   DevBuf<i64> col_pairbeg;     // [ncols+1] pairs of a column
-  DevBuf<uint4> pairs;         // packed (local cell, permutation, 10 slot offsets)
-  DevBuf<double> ktab;         // reference integrals
+  DevBuf<uint4> pairs;         // ring-ordered pair records of the edge columns
+  DevBuf<uint4> cols;          // 2 per column: fixed-row offsets, closing offsets, mirrored slots
+  DevBuf<u32> vcols, vdiag;    // vertex columns and their diagonal slots
+  i64 nvcols = 0;
 };
 
 bool fast_p2tet_applicable(const BlfLocalParams& p);

@@ -1,23 +1,31 @@
-// fastpath_p2tet.cu -- owner-computes numeric kernel for the metric configuration:
+// fastpath_p2tet.cu -- owner-computes numeric kernels for the metric configuration:
 // 3D P2 Laplace stiffness (H1P2{1,3}, [Gradient, Gradient], NoAction) on a frozen pattern.
 //
 // Replaces, for this form, the whole cell loop of assemble! (bilinearform.jl:226-377:
-// update_trafo!/mapderiv!, update_basis! Gradient, quadrature contraction, _addnz scatter)
-// by ONE kernel in which every stored non-zero is computed and written exactly once:
+// update_trafo!/mapderiv!, update_basis! Gradient, quadrature contraction, _addnz scatter).
+// Every stored non-zero is computed once, in registers, and written once:
 //
-//   * a tile = a contiguous range of CSC columns (<= 128) whose nzval range is staged in
-//     shared memory and written back with fully coalesced stores;
-//   * the geometry S_ab = factor*|T| grad(lambda_a).grad(lambda_b) of the tile's distinct
-//     cells is computed once per tile into shared memory (the affine pullback of
-//     feevaluator_h1.jl:61-74 reduced to its 10 invariants);
-//   * one thread owns one column j and walks the cells K containing dof j ("pairs"); for
-//     each pair it evaluates the whole local column K_loc[:, lj] from S with the exact
-//     P2 integrals (the order-2 rule of quadrature.jl:274-284 integrates them exactly) and
-//     adds the 10 values into the column's slots through a 1-byte local->nnz map.
+//   edge kernel (p2tet_edge_kernel): one thread owns one EDGE column (pq) and walks the cells
+//     around the edge in ring order.  With the exact P2 integrals every local column
+//     K_loc[:, e_pq] is a short expression in S_ab = kappa |T| grad(lambda_a).grad(lambda_b)
+//     (the order-2 rule of quadrature.jl:274-284 integrates them exactly).  Rows v_p, v_q, e_pq
+//     receive a contribution from every ring cell and are summed in registers; the rows of a
+//     ring vertex c (v_c, e_pc, e_qc) receive exactly two contributions from consecutive ring
+//     cells and are completed through a 3-register carry; e_cc' has a single contribution.
+//     Nothing is read-modify-written in memory.  The column is staged in shared memory and
+//     written back with coalesced stores.  S of a tile's distinct cells is computed once per
+//     tile into shared memory (the affine pullback of feevaluator_h1.jl:61-74 reduced to its
+//     10 invariants).
+//   VERTEX columns need no work of their own: the matrix of this form is symmetric, so every
+//     off-diagonal entry (i, v_a) is the mirror image of an entry (v_a, i) that an edge thread
+//     has in a register anyway (i an edge dof), or the ring sum -0.2*sum S_pq of the edge (a b)
+//     (i = v_b).  Edge threads store those values straight to their mirrored slots.
+//   diagonal kernel (p2tet_vertex_diag_kernel): rows of a stiffness matrix sum to zero, so
+//     A[v,v] = -sum_{i != v} A[i,v]; one warp per vertex column, fixed reduction tree.
 //
-// No atomics, no inter-block dependencies -> deterministic.  Values agree with the
-// reference order of operations to rounding (<= 1e-12 relative, tests/test_gpu_parity.py);
-// the *pattern* always comes from the bit-exact symbolic pass.
+// No atomics, fixed summation orders -> deterministic.  Values agree with the reference's order of
+// operations to rounding (tests/test_gpu_parity.py states the tolerance); the PATTERN always
+// comes from the bit-exact symbolic pass, and slots are looked up in it by (row, column).
 #include <algorithm>
 #include <cmath>
 
@@ -27,96 +35,35 @@ namespace grmp {
 
 namespace {
 
-constexpr int TPB = 128;             // threads per tile
-constexpr int MAX_TILE_COLS = 128;
-constexpr int SMEM_BUDGET = 56 * 1024;          // staged tiles: nzval slots + S of the distinct cells
-constexpr int SMEM_BUDGET_DIRECT = 56 * 1024;   // direct tiles (vertex columns): nzval slots + 32 B per pair
+constexpr int TPB = 128;                 // threads (= edge columns) per tile
+constexpr int SMEM_BUDGET = 52 * 1024;   // nzval stage + S of the tile's distinct cells
+constexpr u32 NONE = 0xffffffffu;
 
 // local edge e -> (p,q), Tetrahedron3D edges [1 2],[1 3],[1 4],[2 3],[2 4],[3 4] (h1_p2.jl:231-236)
 __host__ __device__ inline void edge_nodes(int e, int& p, int& q) {
   const int P[6] = {0, 0, 0, 1, 1, 2}, Q[6] = {1, 2, 3, 2, 3, 3};
   p = P[e]; q = Q[e];
 }
-__host__ __device__ inline int edge_of(int a, int b) {  // a < b
-  return (a == 0) ? (b - 1) : (a == 1 ? b + 1 : 5);
+__host__ __device__ inline int edge_of(int a, int b) {   // local edge dof index 4.. of the vertex pair
+  if (a > b) { int t = a; a = b; b = t; }
+  return 4 + ((a == 0) ? (b - 1) : (a == 1 ? b + 1 : 5));
 }
 __host__ __device__ inline int sidx(int a, int b) {      // index of S_ab in the packed upper triangle
   if (a > b) { int t = a; a = b; b = t; }
   return a * 4 - a * (a - 1) / 2 + (b - a);
 }
-// canonical vertex permutation of a pair whose column is local dof lj:
-// vertex column a -> (a, others ascending); edge column (p,q) -> (p, q, others ascending)
-__host__ __device__ inline void canon_perm(int lj, int* pi) {
-  int used[4] = {0, 0, 0, 0}, n = 0;
-  if (lj < 4) { pi[n++] = lj; used[lj] = 1; }
-  else { int p, q; edge_nodes(lj - 4, p, q); pi[n++] = p; pi[n++] = q; used[p] = used[q] = 1; }
-  for (int v = 0; v < 4; v++) if (!used[v]) pi[n++] = v;
-}
-// canonical row r (v_pi0..v_pi3, e(pi0pi1), e(pi0pi2), e(pi0pi3), e(pi1pi2), e(pi1pi3), e(pi2pi3)) -> local dof
-__host__ __device__ inline int canon_row(const int* pi, int r) {
-  if (r < 4) return pi[r];
-  const int A[6] = {0, 0, 0, 1, 1, 2}, B[6] = {1, 2, 3, 2, 3, 3};
-  int a = pi[A[r - 4]], b = pi[B[r - 4]];
-  return 4 + (a < b ? edge_of(a, b) : edge_of(b, a));
-}
-
-struct PackParams {
-  const u32* gsrc;        // sorted pairs: lj*ncells + cell
-  const u32* gcell;
-  const u32* pair_x;      // tile-local cell index (staged tiles) or global cell index (direct tiles)
-  const i32* slotmap;     // [ncells*100]
-  const i64* colptr;      // 1-based
-  const i32* celldofs;
-  i64 npairs, ncells;
-  uint4* pairs;
-};
-
-__global__ void pack_pairs(PackParams p) {
-  i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  if (k >= p.npairs) return;
-  const i64 cell = p.gcell[k];
-  const int lj = (int)(p.gsrc[k] / (u32)p.ncells);
-  const i64 col = p.celldofs[cell * 10 + lj] - 1;
-  const i64 base = p.colptr[col] - 1;
-  int pi[4];
-  canon_perm(lj, pi);
-  unsigned char off[12];
-  for (int r = 0; r < 10; r++) {
-    const int li = canon_row(pi, r);
-    const i32 slot = p.slotmap[cell * 100 + li * 10 + lj];
-    off[r] = (slot < 0) ? 255 : (unsigned char)(slot - base);
-  }
-  off[10] = (unsigned char)lj; off[11] = 0;
-  uint4 rec;
-  rec.x = p.pair_x[k];
-  rec.y = off[0] | (off[1] << 8) | (off[2] << 16) | ((u32)off[3] << 24);
-  rec.z = off[4] | (off[5] << 8) | (off[6] << 16) | ((u32)off[7] << 24);
-  rec.w = off[8] | (off[9] << 8) | (off[10] << 16) | ((u32)off[11] << 24);
-  p.pairs[k] = rec;
-}
-
-struct TileParams {
-  GridView g;
-  const i64* colptr;        // 1-based [ncols+1]
-  const i64* col_pairbeg;   // [ncols+1]
-  const uint4* pairs;
-  const i32* tile_colbeg;
-  const i32* tile_cellbeg;
-  const i32* tile_cells;
-  double factor;
-  double* nzval;
-};
 
 // S_ab = factor * |T| * grad(lambda_a).grad(lambda_b), packed (00,01,02,03,11,12,13,22,23,33)
 __device__ __forceinline__ void cell_S(const GridView& g, i64 cell, double factor, double* S) {
-  const i32* cn = g.cellnodes + cell * 4;
-  const double* x0 = g.coords + (i64)(cn[0] - 1) * 3;
-  const double* x1 = g.coords + (i64)(cn[1] - 1) * 3;
-  const double* x2 = g.coords + (i64)(cn[2] - 1) * 3;
-  const double* x3 = g.coords + (i64)(cn[3] - 1) * 3;
-  const double ax = x1[0] - x0[0], ay = x1[1] - x0[1], az = x1[2] - x0[2];
-  const double bx = x2[0] - x0[0], by = x2[1] - x0[1], bz = x2[2] - x0[2];
-  const double cx = x3[0] - x0[0], cy = x3[1] - x0[1], cz = x3[2] - x0[2];
+  const int4 nd = *reinterpret_cast<const int4*>(g.cellnodes + cell * 4);
+  const double* x0 = g.coords + (i64)(nd.x - 1) * 3;
+  const double* x1 = g.coords + (i64)(nd.y - 1) * 3;
+  const double* x2 = g.coords + (i64)(nd.z - 1) * 3;
+  const double* x3 = g.coords + (i64)(nd.w - 1) * 3;
+  const double p0x = x0[0], p0y = x0[1], p0z = x0[2];
+  const double ax = x1[0] - p0x, ay = x1[1] - p0y, az = x1[2] - p0z;
+  const double bx = x2[0] - p0x, by = x2[1] - p0y, bz = x2[2] - p0z;
+  const double cx = x3[0] - p0x, cy = x3[1] - p0y, cz = x3[2] - p0z;
   // n1 = b x c, n2 = c x a, n3 = a x b : grad(lambda_k) = n_k / det
   const double n1x = by * cz - bz * cy, n1y = bz * cx - bx * cz, n1z = bx * cy - by * cx;
   const double n2x = cy * az - cz * ay, n2y = cz * ax - cx * az, n2z = cx * ay - cy * ax;
@@ -136,204 +83,273 @@ __device__ __forceinline__ void cell_S(const GridView& g, i64 cell, double facto
   S[9] = sc * (n3x * n3x + n3y * n3y + n3z * n3z);
 }
 
-// the four values a vertex column a needs, straight from the coordinates (direct tiles):
-// S_aa and S_ab for the other three vertices in ascending order
-__device__ __forceinline__ void vertex_S(const GridView& g, i64 cell, int a, double factor, double& saa, double& s1, double& s2, double& s3) {
-  const i32* cn = g.cellnodes + cell * 4;
-  const int4 nd = *reinterpret_cast<const int4*>(cn);
-  const double* x0 = g.coords + (i64)(nd.x - 1) * 3;
-  const double* x1 = g.coords + (i64)(nd.y - 1) * 3;
-  const double* x2 = g.coords + (i64)(nd.z - 1) * 3;
-  const double* x3 = g.coords + (i64)(nd.w - 1) * 3;
-  const double p0x = x0[0], p0y = x0[1], p0z = x0[2];
-  const double ax = x1[0] - p0x, ay = x1[1] - p0y, az = x1[2] - p0z;
-  const double bx = x2[0] - p0x, by = x2[1] - p0y, bz = x2[2] - p0z;
-  const double cx = x3[0] - p0x, cy = x3[1] - p0y, cz = x3[2] - p0z;
-  const double n1x = by * cz - bz * cy, n1y = bz * cx - bx * cz, n1z = bx * cy - by * cx;
-  const double n2x = cy * az - cz * ay, n2y = cz * ax - cx * az, n2z = cx * ay - cy * ax;
-  const double n3x = ay * bz - az * by, n3y = az * bx - ax * bz, n3z = ax * by - ay * bx;
-  const double n0x = -(n1x + n2x + n3x), n0y = -(n1y + n2y + n3y), n0z = -(n1z + n2z + n3z);
-  const double nax = a == 0 ? n0x : a == 1 ? n1x : a == 2 ? n2x : n3x;
-  const double nay = a == 0 ? n0y : a == 1 ? n1y : a == 2 ? n2y : n3y;
-  const double naz = a == 0 ? n0z : a == 1 ? n1z : a == 2 ? n2z : n3z;
-  const double sc = factor / (36.0 * g.vol[cell]);
-  const double d0 = sc * (nax * n0x + nay * n0y + naz * n0z);
-  const double d1 = sc * (nax * n1x + nay * n1y + naz * n1z);
-  const double d2 = sc * (nax * n2x + nay * n2y + naz * n2z);
-  const double d3 = sc * (nax * n3x + nay * n3y + naz * n3z);
-  saa = a == 0 ? d0 : a == 1 ? d1 : a == 2 ? d2 : d3;
-  s1 = (a == 0) ? d1 : d0;
-  s2 = (a <= 1) ? d2 : d1;
-  s3 = (a <= 2) ? d3 : d2;
+// ---- records ---------------------------------------------------------------------------------
+// pair record (16 B), pairs of a column stored in ring order:
+//   x : tile-local cell | perm << 16 | flags << 24   (perm = p | q<<2 | in<<4 | out<<6 local vertex ids)
+//   y : slot offsets inside the column of rows v_in, e_P,in, e_Q,in, e_in,out (255 = not in the pattern)
+//   z : mirrored slot (global nzval index) of row e_PQ in column v_in, or NONE
+//   w : chain-end pairs of multi-chain (halo) columns: mirrored slot of row e_PQ in column v_out, else unused
+// column record (32 B):
+//   a.x : offsets of rows v_P, v_Q, e_PQ | flags << 24 (bit 0: closed ring)
+//   a.y : closing offsets (closed: rows of the first pair's in-vertex; open: rows of the last pair's out-vertex)
+//   a.z, a.w : mirrored slots of row e_PQ in columns v_P, v_Q
+//   b.x : mirrored slot of row e_PQ in the column of the closing vertex
+//   b.y, b.z : slots of (row v_Q, col v_P) and (row v_P, col v_Q)
+constexpr u32 PF_FIRST = 1u;   // first pair of the column (closed ring: its in-rows are completed at the end)
+constexpr u32 PF_RESET = 2u;   // first pair of a further chain (halo columns of a partition): drop the carry
+constexpr u32 PF_END = 4u;     // last pair of a chain that is not the last chain: mirror its out-vertex row now (slot in w)
+
+struct PackParams {
+  const u32* pair_cell;     // global cell of the pair (ring order)
+  const u32* pair_local;    // tile-local cell
+  const u32* pair_code;     // perm | flags << 8
+  const i64* col_pairbeg;
+  const i64* colptr;        // 1-based
+  const i64* rowval;        // 1-based
+  const i32* celldofs;
+  const u32* col_of_pair;   // column of every pair
+  const unsigned char* col_closed;
+  i64 npairs, ncols;
+  uint4* pairs;
+  uint4* cols;              // 2 per column
+};
+
+// slot of (row, col) in the pattern as an offset inside the column, or -1
+__device__ __forceinline__ i64 find_slot(const PackParams& p, i64 row0, i64 col0) {
+  i64 lo = p.colptr[col0] - 1, hi = p.colptr[col0 + 1] - 1;
+  const i64 beg = lo, end = hi, target = row0 + 1;
+  while (lo < hi) {
+    i64 mid = (lo + hi) >> 1;
+    if (p.rowval[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  if (lo < end && p.rowval[lo] == target) return lo - beg;
+  return -1;
+}
+__device__ __forceinline__ u32 off8(i64 o) { return (o < 0 || o > 254) ? 255u : (u32)o; }
+__device__ __forceinline__ u32 gslot(const PackParams& p, i64 row0, i64 col0) {
+  i64 o = find_slot(p, row0, col0);
+  return o < 0 ? NONE : (u32)(p.colptr[col0] - 1 + o);
 }
 
-// add the 10 values of one pair into the column's slots; the 10 rows of a pair are distinct slots,
-// so all reads are issued before the writes (no dependent read-modify-write chain)
-__device__ __forceinline__ void pair_update(double* a, const uint4& rec, const double* v) {
-  u32 o[10];
-  o[0] = rec.y & 255u; o[1] = (rec.y >> 8) & 255u; o[2] = (rec.y >> 16) & 255u; o[3] = rec.y >> 24;
-  o[4] = rec.z & 255u; o[5] = (rec.z >> 8) & 255u; o[6] = (rec.z >> 16) & 255u; o[7] = rec.z >> 24;
-  o[8] = rec.w & 255u; o[9] = (rec.w >> 8) & 255u;
-  double c[10];
-#pragma unroll
-  for (int r = 0; r < 10; r++) c[r] = (o[r] != 255u) ? a[o[r]] : 0.0;
-#pragma unroll
-  for (int r = 0; r < 10; r++)
-    if (o[r] != 255u) a[o[r]] = c[r] + v[r];
+__global__ void pack_pairs(PackParams p) {
+  i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (k >= p.npairs) return;
+  const i64 col = p.col_of_pair[k];
+  if (p.col_closed[col] == 2) { p.pairs[k] = make_uint4(0, 0, 0, 0); return; }   // vertex column: no pair work
+  const i64 cell = p.pair_cell[k];
+  const u32 code = p.pair_code[k];
+  const int P = code & 3, Q = (code >> 2) & 3, I = (code >> 4) & 3, O = (code >> 6) & 3;
+  const i32* d = p.celldofs + cell * 10;
+  const i64 vin = d[I] - 1;
+  uint4 rec;
+  rec.x = p.pair_local[k] | ((code & 255u) << 16) | (((code >> 8) & 255u) << 24);
+  rec.y = off8(find_slot(p, vin, col)) | (off8(find_slot(p, d[edge_of(P, I)] - 1, col)) << 8) |
+          (off8(find_slot(p, d[edge_of(Q, I)] - 1, col)) << 16) | (off8(find_slot(p, d[edge_of(I, O)] - 1, col)) << 24);
+  rec.z = gslot(p, col, vin);
+  rec.w = (((code >> 8) & PF_END) != 0) ? gslot(p, col, d[O] - 1) : NONE;
+  p.pairs[k] = rec;
 }
 
-__device__ __forceinline__ void vertex_values(double saa, double s1, double s2, double s3, double* v) {
-  const double m = -0.2 * saa;
-  v[0] = 0.6 * saa;
-  v[1] = -0.2 * s1; v[2] = -0.2 * s2; v[3] = -0.2 * s3;
-  v[4] = 0.6 * s1 + m; v[5] = 0.6 * s2 + m; v[6] = 0.6 * s3 + m;
-  v[7] = -0.2 * (s1 + s2); v[8] = -0.2 * (s1 + s3); v[9] = -0.2 * (s2 + s3);
+__global__ void pack_cols(PackParams p) {
+  i64 j = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (j >= p.ncols) return;
+  const i64 kb = p.col_pairbeg[j], ke = p.col_pairbeg[j + 1];
+  uint4 a = make_uint4(0x00ffffffu, 0x00ffffffu, NONE, NONE), b = make_uint4(NONE, NONE, NONE, 0);
+  if (ke > kb && p.col_closed[j] != 2) {     // 2 = not an edge column
+    const bool closed = p.col_closed[j] == 1;
+    // reference orientation (P,Q) = first ring pair
+    const u32 c0 = p.pair_code[kb];
+    const i32* d0 = p.celldofs + (i64)p.pair_cell[kb] * 10;
+    const i64 vP = d0[c0 & 3] - 1, vQ = d0[(c0 >> 2) & 3] - 1;
+    a.x = off8(find_slot(p, vP, j)) | (off8(find_slot(p, vQ, j)) << 8) | (off8(find_slot(p, j, j)) << 16) | ((closed ? 1u : 0u) << 24);
+    // closing vertex: closed -> in-vertex of the first pair; open -> out-vertex of the last pair
+    const i64 kc = closed ? kb : ke - 1;
+    const u32 cc = p.pair_code[kc];
+    const i32* dc = p.celldofs + (i64)p.pair_cell[kc] * 10;
+    const int Pc = cc & 3, Qc = (cc >> 2) & 3, Vc = closed ? ((cc >> 4) & 3) : ((cc >> 6) & 3);
+    const i64 vC = dc[Vc] - 1;
+    a.y = off8(find_slot(p, vC, j)) | (off8(find_slot(p, dc[edge_of(Pc, Vc)] - 1, j)) << 8) | (off8(find_slot(p, dc[edge_of(Qc, Vc)] - 1, j)) << 16) | (255u << 24);
+    a.z = gslot(p, j, vP);
+    a.w = gslot(p, j, vQ);
+    b.x = gslot(p, j, vC);
+    b.y = gslot(p, vQ, vP);
+    b.z = gslot(p, vP, vQ);
+  }
+  p.cols[2 * j] = a;
+  p.cols[2 * j + 1] = b;
 }
 
-__device__ __forceinline__ void edge_values(const double* s, const unsigned char* ix, double* v) {
-  const double spp = s[ix[0]], sqq = s[ix[1]], spq = s[ix[2]], spr = s[ix[3]], sps = s[ix[4]], sqr = s[ix[5]], sqs = s[ix[6]];
-  v[0] = 0.6 * spq - 0.2 * spp;
-  v[1] = 0.6 * spq - 0.2 * sqq;
-  v[2] = -0.2 * (spr + sqr);
-  v[3] = -0.2 * (sps + sqs);
-  v[4] = 1.6 * (spp + sqq + spq);
-  v[5] = 0.8 * (2.0 * sqr + spq + spr + spp);
-  v[6] = 0.8 * (2.0 * sqs + spq + sps + spp);
-  v[7] = 0.8 * (2.0 * spr + spq + sqr + sqq);
-  v[8] = 0.8 * (2.0 * sps + spq + sqs + sqq);
-  v[9] = 0.8 * (spr + sps + sqr + sqs);
-}
+struct EdgeParams {
+  GridView g;
+  const i64* colptr;        // 1-based [ncols+1]
+  const i64* col_pairbeg;   // [ncols+1]
+  const uint4* pairs;
+  const uint4* cols;
+  const i32* tile_rng;      // [2*ntiles]: first column, end column (exclusive)
+  const i32* tile_crng;     // [2*ntiles]: range into tile_cells
+  const i32* tile_cells;
+  double factor;
+  double* nzval;
+};
 
 constexpr int PF = 4;   // pair records fetched per batch (independent 16-byte loads in flight per thread)
 
-__global__ void __launch_bounds__(TPB) p2tet_tile_kernel(const TileParams p) {
+__global__ void __launch_bounds__(TPB) p2tet_edge_kernel(const EdgeParams p) {
   extern __shared__ double sm[];
-  __shared__ unsigned char s_sidx[10][8];   // packed-S positions needed by a column of local dof lj
+  __shared__ unsigned long long s_tab[256];   // perm code -> 7 packed-S positions (one byte each)
   const int tile = blockIdx.x, tid = threadIdx.x;
-  const int c0 = p.tile_colbeg[tile], c1 = p.tile_colbeg[tile + 1];
-  const int cb = p.tile_cellbeg[tile], nct = p.tile_cellbeg[tile + 1] - cb;
+  const int c0 = p.tile_rng[2 * tile], c1 = p.tile_rng[2 * tile + 1];
+  const int cb = p.tile_crng[2 * tile], nct = p.tile_crng[2 * tile + 1] - cb;
   const i64 g0 = p.colptr[c0] - 1, g1 = p.colptr[c1] - 1;
   const int nnz_t = (int)(g1 - g0);
-  const bool staged = nct > 0;          // staged: S of the distinct cells in smem; direct: per-pair values in smem
-  double* acc = sm;
+  double* stage = sm;
   double* S = sm + nnz_t;
-  if (tid < 10) {
-    int pi[4];
-    canon_perm(tid, pi);
-    if (tid < 4) {   // vertex column a: S_aa, S_ab1, S_ab2, S_ab3
-      for (int k = 0; k < 4; k++) s_sidx[tid][k] = (unsigned char)sidx(pi[0], pi[k]);
-      for (int k = 4; k < 8; k++) s_sidx[tid][k] = 0;
-    } else {         // edge column (p,q | r,s): S_pp, S_qq, S_pq, S_pr, S_ps, S_qr, S_qs
-      s_sidx[tid][0] = (unsigned char)sidx(pi[0], pi[0]);
-      s_sidx[tid][1] = (unsigned char)sidx(pi[1], pi[1]);
-      s_sidx[tid][2] = (unsigned char)sidx(pi[0], pi[1]);
-      s_sidx[tid][3] = (unsigned char)sidx(pi[0], pi[2]);
-      s_sidx[tid][4] = (unsigned char)sidx(pi[0], pi[3]);
-      s_sidx[tid][5] = (unsigned char)sidx(pi[1], pi[2]);
-      s_sidx[tid][6] = (unsigned char)sidx(pi[1], pi[3]);
-      s_sidx[tid][7] = 0;
-    }
+  for (int c = tid; c < 256; c += TPB) {
+    const int P = c & 3, Q = (c >> 2) & 3, I = (c >> 4) & 3, O = (c >> 6) & 3;
+    unsigned long long t = 0;
+    t |= (unsigned long long)sidx(P, P);
+    t |= (unsigned long long)sidx(Q, Q) << 8;
+    t |= (unsigned long long)sidx(P, Q) << 16;
+    t |= (unsigned long long)sidx(P, I) << 24;
+    t |= (unsigned long long)sidx(P, O) << 32;
+    t |= (unsigned long long)sidx(Q, I) << 40;
+    t |= (unsigned long long)sidx(Q, O) << 48;
+    s_tab[c] = t;
   }
-  // this thread's column (tiles hold at most TPB columns) and its first batch of pair records:
-  // issued before the geometry phase so that the loads overlap it
+  // this thread's column and its first batch of pair records (issued before the geometry phase)
   const int col = c0 + tid;
   const bool has_col = col < c1;
   i64 kb = 0, ke = 0;
   int abase = 0;
+  uint4 ca = make_uint4(0, 0, 0, 0), cbx = make_uint4(0, 0, 0, 0);
   if (has_col) {
     kb = p.col_pairbeg[col]; ke = p.col_pairbeg[col + 1];
     abase = (int)(p.colptr[col] - 1 - g0);
+    ca = p.cols[2 * (i64)col]; cbx = p.cols[2 * (i64)col + 1];
   }
   uint4 rec[PF];
 #pragma unroll
   for (int j = 0; j < PF; j++) rec[j] = (kb + j < ke) ? p.pairs[kb + j] : make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < nnz_t; i += TPB) acc[i] = 0.0;
-
-  if (staged) {
-    // ---- geometry of the tile's distinct cells, two cells per thread and round (independent loads) ----
-    for (int i = tid; i < nct; i += 2 * TPB) {
-      const int i2 = i + TPB;
-      const i64 cA = p.tile_cells[cb + i];
-      const i64 cB = (i2 < nct) ? p.tile_cells[cb + i2] : cA;
-      double sA[10], sB[10];
-      cell_S(p.g, cA, p.factor, sA);
-      cell_S(p.g, cB, p.factor, sB);
+  for (int i = tid; i < nnz_t; i += TPB) stage[i] = 0.0;
+  // ---- geometry of the tile's distinct cells, two cells per thread and round ----
+  for (int i = tid; i < nct; i += 2 * TPB) {
+    const int i2 = i + TPB;
+    const i64 cA = p.tile_cells[cb + i];
+    const i64 cB = (i2 < nct) ? p.tile_cells[cb + i2] : cA;
+    double sA[10], sB[10];
+    cell_S(p.g, cA, p.factor, sA);
+    cell_S(p.g, cB, p.factor, sB);
 #pragma unroll
-      for (int k = 0; k < 10; k++) S[i * 10 + k] = sA[k];
-      if (i2 < nct) {
+    for (int k = 0; k < 10; k++) S[k * nct + i] = sA[k];        // k-major: conflict-free stores
+    if (i2 < nct) {
 #pragma unroll
-        for (int k = 0; k < 10; k++) S[i2 * 10 + k] = sB[k];
-      }
-    }
-    __syncthreads();
-    if (has_col) {
-      double* a = acc + abase;
-      for (i64 k = kb; k < ke; k += PF) {
-        uint4 cur[PF];
-#pragma unroll
-        for (int j = 0; j < PF; j++) cur[j] = rec[j];
-#pragma unroll
-        for (int j = 0; j < PF; j++) rec[j] = (k + PF + j < ke) ? p.pairs[k + PF + j] : make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int j = 0; j < PF; j++) {
-          if (k + j < ke) {
-            const int lj = (int)((cur[j].w >> 16) & 255u);
-            const double* s = S + cur[j].x * 10;
-            const unsigned char* ix = s_sidx[lj];
-            double v[10];
-            if (lj < 4) vertex_values(s[ix[0]], s[ix[1]], s[ix[2]], s[ix[3]], v);
-            else edge_values(s, ix, v);
-            pair_update(a, cur[j], v);
-          }
-        }
-      }
-    }
-  } else {
-    // ---- direct tile (vertex columns): phase 1, one thread per PAIR computes its four S values from the
-    //      coordinates (PF pairs per thread in flight); phase 2, one thread per column accumulates ----
-    const i64 kt0 = p.col_pairbeg[c0], kt1 = p.col_pairbeg[c1];
-    const int npt = (int)(kt1 - kt0);
-    for (int q0 = 0; q0 < npt; q0 += PF * TPB) {
-      uint4 r4[PF];
-#pragma unroll
-      for (int j = 0; j < PF; j++) {
-        const int q = q0 + j * TPB + tid;
-        r4[j] = (q < npt) ? p.pairs[kt0 + q] : make_uint4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int j = 0; j < PF; j++) {
-        const int q = q0 + j * TPB + tid;
-        if (q < npt) {
-          double saa, s1, s2, s3;
-          vertex_S(p.g, (i64)r4[j].x, (int)((r4[j].w >> 16) & 255u), p.factor, saa, s1, s2, s3);
-          double* st = S + (size_t)q * 4;
-          st[0] = saa; st[1] = s1; st[2] = s2; st[3] = s3;
-        }
-      }
-    }
-    __syncthreads();
-    if (has_col) {
-      double* a = acc + abase;
-      for (i64 k = kb; k < ke; k += PF) {
-        uint4 cur[PF];
-#pragma unroll
-        for (int j = 0; j < PF; j++) cur[j] = rec[j];
-#pragma unroll
-        for (int j = 0; j < PF; j++) rec[j] = (k + PF + j < ke) ? p.pairs[k + PF + j] : make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int j = 0; j < PF; j++) {
-          if (k + j < ke) {
-            const double* st = S + (size_t)(k + j - kt0) * 4;
-            double v[10];
-            vertex_values(st[0], st[1], st[2], st[3], v);
-            pair_update(a, cur[j], v);
-          }
-        }
-      }
+      for (int k = 0; k < 10; k++) S[k * nct + i2] = sB[k];
     }
   }
   __syncthreads();
-  for (int i = tid; i < nnz_t; i += TPB) p.nzval[g0 + i] = acc[i];
+  if (has_col && ke > kb) {
+    double* a = stage + abase;
+    double A = 0.0, B = 0.0, C = 0.0, W = 0.0;       // rows v_P, v_Q, e_PQ of the column; (v_P, v_Q) coupling
+    double c0r = 0.0, c1r = 0.0, c2r = 0.0;          // carry: partial rows of the shared ring vertex
+    double f0 = 0.0, f1 = 0.0, f2 = 0.0;             // closed ring: in-rows of the first pair, completed at the end
+    const bool closed = (ca.x >> 24) & 1u;
+    for (i64 k = kb; k < ke; k += PF) {
+      uint4 cur[PF];
+#pragma unroll
+      for (int j = 0; j < PF; j++) cur[j] = rec[j];
+#pragma unroll
+      for (int j = 0; j < PF; j++) rec[j] = (k + PF + j < ke) ? p.pairs[k + PF + j] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int j = 0; j < PF; j++) {
+        if (k + j < ke) {
+          const uint4 r = cur[j];
+          const u32 cl = r.x & 0xffffu;
+          const unsigned long long t = s_tab[(r.x >> 16) & 255u];
+          const double* s = S + cl;
+          const double spp = s[(int)(t & 255u) * nct], sqq = s[(int)((t >> 8) & 255u) * nct], spq = s[(int)((t >> 16) & 255u) * nct];
+          const double spi = s[(int)((t >> 24) & 255u) * nct], spo = s[(int)((t >> 32) & 255u) * nct];
+          const double sqi = s[(int)((t >> 40) & 255u) * nct], sqo = s[(int)((t >> 48) & 255u) * nct];
+          A += 0.6 * spq - 0.2 * spp;
+          B += 0.6 * spq - 0.2 * sqq;
+          C += 1.6 * (spp + sqq + spq);
+          W += -0.2 * spq;
+          const double base = spq + spp, baseq = spq + sqq;
+          const u32 fl = r.x >> 24;
+          if (fl & PF_RESET) { c0r = 0.0; c1r = 0.0; c2r = 0.0; }
+          const double in0 = c0r + -0.2 * (spi + sqi);                 // v_in
+          const double in1 = c1r + 0.8 * (2.0 * sqi + spi + base);      // e_P,in
+          const double in2 = c2r + 0.8 * (2.0 * spi + sqi + baseq);     // e_Q,in
+          c0r = -0.2 * (spo + sqo);                                     // v_out
+          c1r = 0.8 * (2.0 * sqo + spo + base);                         // e_P,out
+          c2r = 0.8 * (2.0 * spo + sqo + baseq);                        // e_Q,out
+          const double x = 0.8 * (spi + spo + sqi + sqo);               // e_in,out
+          const u32 o3 = r.y >> 24;
+          if (o3 != 255u) a[o3] = x;
+          if ((fl & PF_END) && r.w != NONE) p.nzval[r.w] = c0r;       // chain end inside a halo column: mirror (e_PQ, v_out)
+          if (closed && (fl & PF_FIRST)) {
+            f0 = in0; f1 = in1; f2 = in2;                               // partner is the last pair of the ring
+          } else {
+            const u32 o0 = r.y & 255u, o1 = (r.y >> 8) & 255u, o2 = (r.y >> 16) & 255u;
+            if (o0 != 255u) a[o0] = in0;
+            if (o1 != 255u) a[o1] = in1;
+            if (o2 != 255u) a[o2] = in2;
+            if (r.z != NONE) p.nzval[r.z] = in0;                        // mirror (e_PQ, v_in)
+          }
+        }
+      }
+    }
+    // closing rows: closed ring -> first pair's in-rows + last carry; open chain -> last pair's out-rows
+    {
+      const double q0 = closed ? f0 + c0r : c0r, q1 = closed ? f1 + c1r : c1r, q2 = closed ? f2 + c2r : c2r;
+      const u32 o0 = ca.y & 255u, o1 = (ca.y >> 8) & 255u, o2 = (ca.y >> 16) & 255u;
+      if (o0 != 255u) a[o0] = q0;
+      if (o1 != 255u) a[o1] = q1;
+      if (o2 != 255u) a[o2] = q2;
+      if (cbx.x != NONE) p.nzval[cbx.x] = q0;
+    }
+    {
+      const u32 oA = ca.x & 255u, oB = (ca.x >> 8) & 255u, oC = (ca.x >> 16) & 255u;
+      if (oA != 255u) a[oA] = A;
+      if (oB != 255u) a[oB] = B;
+      if (oC != 255u) a[oC] = C;
+      if (ca.z != NONE) p.nzval[ca.z] = A;       // (e_PQ, v_P)
+      if (ca.w != NONE) p.nzval[ca.w] = B;       // (e_PQ, v_Q)
+      if (cbx.y != NONE) p.nzval[cbx.y] = W;     // (v_Q, v_P)
+      if (cbx.z != NONE) p.nzval[cbx.z] = W;     // (v_P, v_Q)
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < nnz_t; i += TPB) p.nzval[g0 + i] = stage[i];
+}
+
+// A[v,v] = -sum_{i != v} A[i,v] : one warp per vertex column, fixed shuffle tree
+__global__ void p2tet_vertex_diag_kernel(const u32* vcols, const u32* vdiag, i64 nv, const i64* colptr, double* nzval) {
+  const i64 w = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= nv) return;
+  const i64 col = vcols[w];
+  const i64 b = colptr[col] - 1, e = colptr[col + 1] - 1;
+  const u32 d32 = vdiag[w];
+  const i64 dslot = (d32 == NONE) ? -1 : (i64)d32;
+  double s = 0.0;
+  for (i64 k = b + lane; k < e; k += 32)
+    if (k != dslot) s += nzval[k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0 && dslot >= 0) nzval[dslot] = -s;
+}
+
+__global__ void find_diag_slots(const u32* vcols, i64 nv, const i64* colptr, const i64* rowval, u32* vdiag) {
+  i64 w = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (w >= nv) return;
+  const i64 col = vcols[w];
+  i64 lo = colptr[col] - 1, hi = colptr[col + 1] - 1;
+  const i64 end = hi;
+  while (lo < hi) {
+    i64 mid = (lo + hi) >> 1;
+    if (rowval[mid] < col + 1) lo = mid + 1; else hi = mid;
+  }
+  vdiag[w] = (lo < end && rowval[lo] == col + 1) ? (u32)lo : NONE;
 }
 
 // closed-form local stiffness of the unit reference tetrahedron, used to verify that the
@@ -363,19 +379,23 @@ void reference_local_closed_form(double K[10][10]) {
 
 bool fast_p2tet_applicable(const BlfLocalParams& p) {
   return p.g.dim == 3 && p.same_eval && p.e1.fam == FAM_H1 && p.e1.op == GRMP_OP_GRAD && p.e1.ncomp == 1 && p.e1.nd == 10 &&
-         p.e1.tab_nd == 10 && p.action == GRMP_ACT_NONE && (p.apt == GRMP_APT_SYMMETRIC || (p.apt == GRMP_APT_BILINEARFORM && !p.transposed));
+         p.e1.tab_nd == 10 && p.action == GRMP_ACT_NONE && p.reg.n == 0 &&
+         (p.apt == GRMP_APT_SYMMETRIC || (p.apt == GRMP_APT_BILINEARFORM && !p.transposed));
 }
 
 int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const std::vector<double>& w,
                      const std::vector<double>& derivs, i64 ncols_owned, FastP2Tet* out) {
+  // halo columns (>= ncols_owned) are processed too: their mirrors complete the owned vertex columns;
+  // only they may consist of several chains (cells around a halo edge are present only where they touch an owned dof)
   cudaStream_t s = ctx->stream;
   const i64 ncells = p.g.ncells, ncols = pat.ncols;
-  const i64 ncols_tiled = (ncols_owned >= 0 && ncols_owned < ncols) ? ncols_owned : ncols;   // halo columns belong to another rank
-  out->ntiles = 0;
+  const i64 ncols_owned_eff = (ncols_owned >= 0 && ncols_owned < ncols) ? ncols_owned : ncols;
+  out->ntiles = 0; out->nvcols = 0;
+  if (pat.nnz >= (i64)NONE) return fail(GRMP_EUNSUPPORTED, "fast path: more than 2^32-1 non-zeros on one device");
   // (0) the caller's tables must be the standard P2 basis integrated exactly
   {
     const int nq = p.nq;
-    if ((int)w.size() != nq || derivs.size() != (size_t)nq * 3 * 10) return fail(GRMP_EINVAL, "fast path: table shape");
+    if ((int)w.size() != nq || derivs.size() != (size_t)nq * 3 * 10) return fail(GRMP_EUNSUPPORTED, "fast path: table shape");
     double K[10][10];
     reference_local_closed_form(K);
     for (int i = 0; i < 10; i++) for (int j = 0; j < 10; j++) {
@@ -390,80 +410,176 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   const i64 npairs = dg.ncontrib;
   std::vector<u32> h_cell(npairs), h_src(npairs);
   std::vector<i64> h_pairbeg(ncols + 1), h_colptr(ncols + 1);
+  std::vector<i32> h_cn((size_t)ncells * 4);
   GRMP_CUDA(cudaMemcpyAsync(h_cell.data(), dg.gcell.p, npairs * 4, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaMemcpyAsync(h_src.data(), dg.gsrc.p, npairs * 4, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaMemcpyAsync(h_pairbeg.data(), dg.segptr.p, (ncols + 1) * 8, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaMemcpyAsync(h_colptr.data(), pat.colptr.p, (ncols + 1) * 8, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaMemcpyAsync(h_cn.data(), p.g.cellnodes, (size_t)ncells * 16, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaStreamSynchronize(s));
-  // (2) greedy tiles over the column range (host; one pass over the pairs)
-  std::vector<i32> tile_colbeg{0}, tile_cellbeg{0}, tile_cells;
-  std::vector<u32> pair_x(npairs);
-  int cur_direct = -1;   // mode of the open tile: 1 = direct (vertex columns, geometry per pair), 0 = staged
+  // (2) host: ring order of every edge column, tiles over the edge columns, list of vertex columns
+  std::vector<u32> pair_cell(npairs), pair_local(npairs), pair_code(npairs), col_of_pair(npairs), vcols;
+  std::vector<unsigned char> col_closed(ncols, 2);
+  std::vector<i32> tile_rng, tile_crng, tile_cells;
   std::vector<i32> mark(ncells, -1), local_of(ncells, 0);
-  tile_cells.reserve((size_t)ncells * 4);
+  tile_cells.reserve((size_t)ncells * 3);
   int cur_tile = 0, cur_cols = 0, cur_cells = 0;
-  i64 cur_nnz = 0, cur_pairs = 0;
-  int max_smem = 0, max_cells = 0;
-  for (i64 j = 0; j < ncols_tiled; j++) {
+  i64 cur_nnz = 0, tile_first_col = 0;
+  i64 max_smem = 0;
+  auto close_tile = [&](i64 end_col) {
+    if (cur_cols == 0) return;
+    tile_rng.push_back((i32)tile_first_col); tile_rng.push_back((i32)end_col);
+    tile_crng.push_back((i32)(tile_cells.size() - cur_cells)); tile_crng.push_back((i32)tile_cells.size());
+    max_smem = std::max<i64>(max_smem, 8 * cur_nnz + 80 * (i64)cur_cells);
+    cur_tile++; cur_cols = 0; cur_cells = 0; cur_nnz = 0;
+  };
+  struct RP { u32 cell; int P, Q, R, S; i32 nR, nS; };
+  std::vector<RP> rp;
+  std::vector<char> used;
+  for (i64 j = 0; j < ncols; j++) {
+    const i64 kb = h_pairbeg[j], ke = h_pairbeg[j + 1];
     const i64 len = h_colptr[j + 1] - h_colptr[j];
-    if (len > 254) return fail(GRMP_EUNSUPPORTED, "fast path: a column has more than 254 entries");
-    const bool has_pairs = h_pairbeg[j + 1] > h_pairbeg[j];
-    const int direct = (has_pairs && (h_src[h_pairbeg[j]] / (u32)ncells) < 4) ? 1 : 0;   // vertex dof of the P2 element
+    if (ke == kb) { close_tile(j); continue; }
+    const int lj0 = (int)(h_src[kb] / (u32)ncells);
+    if (lj0 < 4) {   // vertex column: filled by mirrors + the diagonal kernel
+      close_tile(j);
+      vcols.push_back((u32)j);
+      for (i64 k = kb; k < ke; k++) { pair_cell[k] = h_cell[k]; pair_local[k] = 0; pair_code[k] = 0; col_of_pair[k] = (u32)j; }
+      continue;
+    }
+    if (len > 254) return fail(GRMP_EUNSUPPORTED, "fast path: an edge column has more than 254 entries");
+    // ---- ring order of the cells around the edge ----
+    const int n = (int)(ke - kb);
+    rp.resize(n);
+    i32 P0 = 0;
+    for (int t = 0; t < n; t++) {
+      const u32 c = h_cell[kb + t];
+      const int lj = (int)(h_src[kb + t] / (u32)ncells);
+      if (lj < 4) return fail(GRMP_EUNSUPPORTED, "fast path: mixed dof types in one column");
+      int pl, ql; edge_nodes(lj - 4, pl, ql);
+      int rl = -1, sl = -1;
+      for (int v = 0; v < 4; v++) if (v != pl && v != ql) { if (rl < 0) rl = v; else sl = v; }
+      const i32* cn = &h_cn[(size_t)c * 4];
+      if (t == 0) P0 = cn[pl];
+      if (cn[pl] != P0) { int tmp = pl; pl = ql; ql = tmp; }      // consistent global orientation (P,Q)
+      if (cn[pl] != P0) return fail(GRMP_EUNSUPPORTED, "fast path: inconsistent edge column");
+      rp[t] = RP{c, pl, ql, rl, sl, cn[rl], cn[sl]};
+    }
+    // degrees of the ring vertices; chains start at vertices of degree 1, a star without such a vertex is a closed ring
+    std::vector<int> degR(n), degS(n);
+    bool closed = true;
+    for (int t = 0; t < n; t++) {
+      int dR = 0, dS = 0;
+      for (int u = 0; u < n; u++) {
+        dR += (rp[u].nR == rp[t].nR) + (rp[u].nS == rp[t].nR);
+        dS += (rp[u].nR == rp[t].nS) + (rp[u].nS == rp[t].nS);
+      }
+      if (dR > 2 || dS > 2) return fail(GRMP_EUNSUPPORTED, "fast path: non-manifold edge star");
+      degR[t] = dR; degS[t] = dS;
+      if (dR == 1 || dS == 1) closed = false;
+    }
+    used.assign(n, 0);
+    int step = 0, nchains = 0;
+    while (step < n) {
+      int start = -1, start_in_is_R = 1;
+      if (closed) { if (step != 0) return fail(GRMP_EUNSUPPORTED, "fast path: edge star is not a single ring"); start = 0; }
+      else
+        for (int t = 0; t < n && start < 0; t++)
+          if (!used[t]) { if (degR[t] == 1) { start = t; start_in_is_R = 1; } else if (degS[t] == 1) { start = t; start_in_is_R = 0; } }
+      if (start < 0) return fail(GRMP_EUNSUPPORTED, "fast path: edge star mixes a ring and chains");
+      if (nchains > 0 && j < ncols_owned_eff) return fail(GRMP_EUNSUPPORTED, "fast path: an owned edge star is not a single chain");
+      int curp = start;
+      const i32 first_in = start_in_is_R ? rp[start].nR : rp[start].nS;
+      i32 vin = first_in;
+      bool chain_first = true;
+      while (true) {
+        used[curp] = 1;
+        const bool inR = (rp[curp].nR == vin);
+        const int I = inR ? rp[curp].R : rp[curp].S, O = inR ? rp[curp].S : rp[curp].R;
+        const i32 vout = inR ? rp[curp].nS : rp[curp].nR;
+        const i64 k = kb + step;
+        u32 fl = (step == 0) ? PF_FIRST : 0u;
+        if (chain_first && nchains > 0) fl |= PF_RESET;
+        pair_cell[k] = rp[curp].cell;
+        pair_code[k] = (u32)(rp[curp].P | (rp[curp].Q << 2) | (I << 4) | (O << 6)) | (fl << 8);
+        col_of_pair[k] = (u32)j;
+        step++; chain_first = false;
+        int nxt = -1;
+        for (int u = 0; u < n; u++) if (!used[u] && (rp[u].nR == vout || rp[u].nS == vout)) { nxt = u; break; }
+        if (nxt < 0) {
+          if (closed && (step != n || vout != first_in)) return fail(GRMP_EUNSUPPORTED, "fast path: edge ring does not close");
+          if (!closed && step < n) pair_code[k] |= (PF_END << 8);     // a further chain follows
+          break;
+        }
+        vin = vout; curp = nxt;
+      }
+      nchains++;
+    }
+    col_closed[j] = closed ? 1 : 0;
+    // ---- tile budget ----
     for (int attempt = 0; attempt < 2; attempt++) {
       int fresh = 0;
-      if (!direct)
-        for (i64 k = h_pairbeg[j]; k < h_pairbeg[j + 1]; k++) if (mark[h_cell[k]] != cur_tile) fresh++;
-      const i64 npj = h_pairbeg[j + 1] - h_pairbeg[j];
-      const i64 need = direct ? 8 * (cur_nnz + len) + 32 * (cur_pairs + npj) : 8 * (cur_nnz + len) + 80 * (i64)(cur_cells + fresh);
-      const i64 budget = direct ? SMEM_BUDGET_DIRECT : SMEM_BUDGET;
-      if (cur_cols > 0 && (cur_cols + 1 > MAX_TILE_COLS || need > budget || direct != cur_direct)) {
-        tile_colbeg.push_back((i32)j); tile_cellbeg.push_back((i32)tile_cells.size());
-        max_smem = std::max<i64>(max_smem, 8 * cur_nnz + (cur_direct ? 32 * cur_pairs : 80 * (i64)cur_cells)); max_cells = std::max(max_cells, cur_cells);
-        cur_tile++; cur_cols = 0; cur_cells = 0; cur_nnz = 0; cur_pairs = 0;
-        continue;   // re-evaluate the column in the fresh tile
-      }
-      cur_direct = direct;
-      for (i64 k = h_pairbeg[j]; k < h_pairbeg[j + 1]; k++) {
-        const u32 c = h_cell[k];
-        if (direct) { pair_x[k] = c; continue; }
+      for (i64 k = kb; k < ke; k++) if (mark[pair_cell[k]] != cur_tile) fresh++;
+      const i64 need = 8 * (cur_nnz + len) + 80 * (i64)(cur_cells + fresh);
+      if (cur_cols > 0 && (cur_cols + 1 > TPB || need > SMEM_BUDGET)) { close_tile(j); continue; }
+      if (cur_cols == 0) tile_first_col = j;
+      for (i64 k = kb; k < ke; k++) {
+        const u32 c = pair_cell[k];
         if (mark[c] != cur_tile) { mark[c] = cur_tile; local_of[c] = cur_cells++; tile_cells.push_back((i32)c); }
-        pair_x[k] = (u32)local_of[c];
+        pair_local[k] = (u32)local_of[c];
       }
-      cur_cols++; cur_nnz += len; cur_pairs += npj;
+      cur_cols++; cur_nnz += len;
       break;
     }
   }
-  if (cur_cols > 0 || ncols_tiled == 0) {
-    tile_colbeg.push_back((i32)ncols_tiled); tile_cellbeg.push_back((i32)tile_cells.size());
-    max_smem = std::max<i64>(max_smem, 8 * cur_nnz + (cur_direct == 1 ? 32 * cur_pairs : 80 * (i64)cur_cells)); max_cells = std::max(max_cells, cur_cells);
-  }
+  close_tile(ncols);
   if (max_smem > 200 * 1024) return fail(GRMP_EUNSUPPORTED, "fast path: a single column exceeds the shared-memory tile");
-  out->ntiles = (int)tile_colbeg.size() - 1;
-  out->npairs = npairs; out->smem_bytes = max_smem; out->max_tile_cells = max_cells;
-  GRMP_TRY(out->tile_colbeg.upload(tile_colbeg.data(), tile_colbeg.size(), s));
-  GRMP_TRY(out->tile_cellbeg.upload(tile_cellbeg.data(), tile_cellbeg.size(), s));
+  const int ntiles = (int)(tile_rng.size() / 2);
+  out->ntiles = ntiles; out->npairs = npairs; out->smem_bytes = (int)max_smem; out->nvcols = (i64)vcols.size();
+  if (tile_rng.empty()) { tile_rng.assign(2, 0); tile_crng.assign(2, 0); }
+  if (tile_cells.empty()) tile_cells.push_back(0);
+  if (vcols.empty()) vcols.push_back(0);
+  GRMP_TRY(out->tile_colbeg.upload(tile_rng.data(), tile_rng.size(), s));
+  GRMP_TRY(out->tile_cellbeg.upload(tile_crng.data(), tile_crng.size(), s));
   GRMP_TRY(out->tile_cells.upload(tile_cells.data(), tile_cells.size(), s));
-  DevBuf<u32> d_local;
-  GRMP_TRY(d_local.upload(pair_x.data(), npairs, s));
-  // (3) pack the 16-byte pair records on the device
-  GRMP_TRY(out->pairs.alloc(npairs));
+  // (3) pack pair / column records on the device (slots are looked up in the pattern by (row, col))
+  DevBuf<u32> d_cell, d_local, d_code, d_colof;
+  DevBuf<unsigned char> d_closed;
+  GRMP_TRY(d_cell.upload(pair_cell.data(), npairs, s)); GRMP_TRY(d_local.upload(pair_local.data(), npairs, s));
+  GRMP_TRY(d_code.upload(pair_code.data(), npairs, s)); GRMP_TRY(d_colof.upload(col_of_pair.data(), npairs, s));
+  GRMP_TRY(d_closed.upload(col_closed.data(), ncols, s));
+  GRMP_TRY(out->pairs.alloc(std::max<i64>(npairs, 1)));
+  GRMP_TRY(out->cols.alloc(2 * (size_t)std::max<i64>(ncols, 1)));
   GRMP_TRY(out->col_pairbeg.alloc(ncols + 1));
   GRMP_CUDA(cudaMemcpyAsync(out->col_pairbeg.p, dg.segptr.p, (ncols + 1) * 8, cudaMemcpyDeviceToDevice, s));
-  if (npairs) {
-    PackParams pp{dg.gsrc.p, dg.gcell.p, d_local.p, pat.slotmap.p, pat.colptr.p, p.e1.celldofs, npairs, ncells, out->pairs.p};
-    pack_pairs<<<(unsigned)((npairs + 255) / 256), 256, 0, s>>>(pp);
+  PackParams pp{d_cell.p, d_local.p, d_code.p, dg.segptr.p, pat.colptr.p, pat.rowval.p, p.e1.celldofs, d_colof.p, d_closed.p,
+                npairs, ncols, out->pairs.p, out->cols.p};
+  if (npairs) pack_pairs<<<(unsigned)((npairs + 255) / 256), 256, 0, s>>>(pp);
+  if (ncols) pack_cols<<<(unsigned)((ncols + 255) / 256), 256, 0, s>>>(pp);
+  GRMP_CUDA(cudaGetLastError());
+  // (4) vertex columns: list + diagonal slots
+  GRMP_TRY(out->vcols.upload(vcols.data(), vcols.size(), s));
+  GRMP_TRY(out->vdiag.alloc(vcols.size()));
+  if (out->nvcols > 0) {
+    find_diag_slots<<<(unsigned)((out->nvcols + 255) / 256), 256, 0, s>>>(out->vcols.p, out->nvcols, pat.colptr.p, pat.rowval.p, out->vdiag.p);
     GRMP_CUDA(cudaGetLastError());
   }
-  GRMP_CUDA(cudaFuncSetAttribute(p2tet_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(max_smem, 1024)));
+  GRMP_CUDA(cudaFuncSetAttribute(p2tet_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<i64>(max_smem, 1024)));
   GRMP_CUDA(cudaStreamSynchronize(s));
   return GRMP_OK;
 }
 
 int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const FastP2Tet& f, double* nzval) {
-  if (f.ntiles == 0) return GRMP_OK;
-  TileParams tp{p.g, pat.colptr.p, f.col_pairbeg.p, f.pairs.p, f.tile_colbeg.p, f.tile_cellbeg.p, f.tile_cells.p, p.factor, nzval};
-  p2tet_tile_kernel<<<f.ntiles, TPB, f.smem_bytes, ctx->stream>>>(tp);
-  GRMP_CUDA(cudaGetLastError());
+  if (f.ntiles > 0) {
+    EdgeParams ep{p.g, pat.colptr.p, f.col_pairbeg.p, f.pairs.p, f.cols.p, f.tile_colbeg.p, f.tile_cellbeg.p, f.tile_cells.p, p.factor, nzval};
+    p2tet_edge_kernel<<<f.ntiles, TPB, f.smem_bytes, ctx->stream>>>(ep);
+    GRMP_CUDA(cudaGetLastError());
+  }
+  if (f.nvcols > 0) {
+    const i64 threads = f.nvcols * 32;
+    p2tet_vertex_diag_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(f.vcols.p, f.vdiag.p, f.nvcols, pat.colptr.p, nzval);
+    GRMP_CUDA(cudaGetLastError());
+  }
   return GRMP_OK;
 }
 
