@@ -11,13 +11,13 @@ struct FastP2Tet {
   i64 npairs = 0;
   int smem_bytes = 0;
   int max_tile_cells = 0;
-  DevBuf<i32> tile_colbeg;     // [ntiles+1] first (permuted) column of a tile
-  DevBuf<i32> tile_cellbeg;    // [ntiles+1] range into tile_cells
-  DevBuf<i32> tile_cells;      // distinct cells of every tile
+  DevBuf<int4> tile_hdr;       // 2 per tile: column range, tile-cell range, nzval range
+  DevBuf<int4> tile_nodes;     // CellNodes of the distinct cells of every tile
   DevBuf<i64> col_pairbeg;     // [ncols+1] pairs of a column
   DevBuf<uint4> pairs;         // ring-ordered pair records of the edge columns
   DevBuf<uint4> cols;          // 2 per column: fixed-row offsets, closing offsets, mirrored slots
-  DevBuf<u32> vcols, vdiag;    // vertex columns and their diagonal slots
+  DevBuf<u32> vcols;           // vertex columns
+  DevBuf<uint4> vrec;          // per vertex column: first slot, #slots, diagonal slot
   i64 nvcols = 0;
 };
 

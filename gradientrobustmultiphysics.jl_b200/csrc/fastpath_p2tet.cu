@@ -36,7 +36,7 @@ namespace grmp {
 namespace {
 
 constexpr int TPB = 128;                 // threads (= edge columns) per tile
-constexpr int SMEM_BUDGET = 52 * 1024;   // nzval stage + S of the tile's distinct cells
+constexpr int SMEM_BUDGET = 44 * 1024;   // nzval stage + S of the tile's distinct cells
 constexpr u32 NONE = 0xffffffffu;
 
 // local edge e -> (p,q), Tetrahedron3D edges [1 2],[1 3],[1 4],[2 3],[2 4],[3 4] (h1_p2.jl:231-236)
@@ -54,8 +54,7 @@ __host__ __device__ inline int sidx(int a, int b) {      // index of S_ab in the
 }
 
 // S_ab = factor * |T| * grad(lambda_a).grad(lambda_b), packed (00,01,02,03,11,12,13,22,23,33)
-__device__ __forceinline__ void cell_S(const GridView& g, i64 cell, double factor, double* S) {
-  const int4 nd = *reinterpret_cast<const int4*>(g.cellnodes + cell * 4);
+__device__ __forceinline__ void cell_S(const GridView& g, const int4 nd, double factor, double* S) {
   const double* x0 = g.coords + (i64)(nd.x - 1) * 3;
   const double* x1 = g.coords + (i64)(nd.y - 1) * 3;
   const double* x2 = g.coords + (i64)(nd.z - 1) * 3;
@@ -69,8 +68,10 @@ __device__ __forceinline__ void cell_S(const GridView& g, i64 cell, double facto
   const double n2x = cy * az - cz * ay, n2y = cz * ax - cx * az, n2z = cx * ay - cy * ax;
   const double n3x = ay * bz - az * by, n3y = az * bx - ax * bz, n3z = ax * by - ay * bx;
   const double n0x = -(n1x + n2x + n3x), n0y = -(n1y + n2y + n3y), n0z = -(n1z + n2z + n3z);
-  // |T| / det^2 with det = 6|T| taken from CellVolumes like mapderiv! does: 1 / (36 |T|)
-  const double sc = factor / (36.0 * g.vol[cell]);
+  // |T| / det^2 = 1 / (6 |det|): the cell volume is recomputed from the coordinates (|det|/6), which agrees with
+  // CellVolumes to rounding and saves a dependent load
+  const double det = ax * n1x + ay * n1y + az * n1z;
+  const double sc = factor / (6.0 * fabs(det));
   S[0] = sc * (n0x * n0x + n0y * n0y + n0z * n0z);
   S[1] = sc * (n0x * n1x + n0y * n1y + n0z * n1z);
   S[2] = sc * (n0x * n2x + n0y * n2y + n0z * n2z);
@@ -94,7 +95,7 @@ __device__ __forceinline__ void cell_S(const GridView& g, i64 cell, double facto
 //   a.y : closing offsets (closed: rows of the first pair's in-vertex; open: rows of the last pair's out-vertex)
 //   a.z, a.w : mirrored slots of row e_PQ in columns v_P, v_Q
 //   b.x : mirrored slot of row e_PQ in the column of the closing vertex
-//   b.y, b.z : slots of (row v_Q, col v_P) and (row v_P, col v_Q)
+//   b.y, b.z : slots of (row v_Q, col v_P) and (row v_P, col v_Q);  b.w : first pair;  a.y >> 24 : number of pairs
 constexpr u32 PF_FIRST = 1u;   // first pair of the column (closed ring: its in-rows are completed at the end)
 constexpr u32 PF_RESET = 2u;   // first pair of a further chain (halo columns of a partition): drop the carry
 constexpr u32 PF_END = 4u;     // last pair of a chain that is not the last chain: mirror its out-vertex row now (slot in w)
@@ -168,12 +169,13 @@ __global__ void pack_cols(PackParams p) {
     const i32* dc = p.celldofs + (i64)p.pair_cell[kc] * 10;
     const int Pc = cc & 3, Qc = (cc >> 2) & 3, Vc = closed ? ((cc >> 4) & 3) : ((cc >> 6) & 3);
     const i64 vC = dc[Vc] - 1;
-    a.y = off8(find_slot(p, vC, j)) | (off8(find_slot(p, dc[edge_of(Pc, Vc)] - 1, j)) << 8) | (off8(find_slot(p, dc[edge_of(Qc, Vc)] - 1, j)) << 16) | (255u << 24);
+    a.y = off8(find_slot(p, vC, j)) | (off8(find_slot(p, dc[edge_of(Pc, Vc)] - 1, j)) << 8) | (off8(find_slot(p, dc[edge_of(Qc, Vc)] - 1, j)) << 16) | ((u32)(ke - kb) << 24);
     a.z = gslot(p, j, vP);
     a.w = gslot(p, j, vQ);
     b.x = gslot(p, j, vC);
     b.y = gslot(p, vQ, vP);
     b.z = gslot(p, vP, vQ);
+    b.w = (u32)kb;
   }
   p.cols[2 * j] = a;
   p.cols[2 * j + 1] = b;
@@ -185,25 +187,43 @@ struct EdgeParams {
   const i64* col_pairbeg;   // [ncols+1]
   const uint4* pairs;
   const uint4* cols;
-  const i32* tile_rng;      // [2*ntiles]: first column, end column (exclusive)
-  const i32* tile_crng;     // [2*ntiles]: range into tile_cells
-  const i32* tile_cells;
+  const int4* tile_hdr;     // 2 per tile: {first column, #columns, first tile cell, #tile cells}, {g0 lo, g0 hi, nnz, 0}
+  const int4* tile_nodes;   // CellNodes of the tiles' distinct cells
   double factor;
   double* nzval;
 };
 
 constexpr int PF = 4;   // pair records fetched per batch (independent 16-byte loads in flight per thread)
 
-__global__ void __launch_bounds__(TPB) p2tet_edge_kernel(const EdgeParams p) {
+__global__ void __launch_bounds__(TPB, 5) p2tet_edge_kernel(const EdgeParams p) {
   extern __shared__ double sm[];
   __shared__ unsigned long long s_tab[256];   // perm code -> 7 packed-S positions (one byte each)
   const int tile = blockIdx.x, tid = threadIdx.x;
-  const int c0 = p.tile_rng[2 * tile], c1 = p.tile_rng[2 * tile + 1];
-  const int cb = p.tile_crng[2 * tile], nct = p.tile_crng[2 * tile + 1] - cb;
-  const i64 g0 = p.colptr[c0] - 1, g1 = p.colptr[c1] - 1;
-  const int nnz_t = (int)(g1 - g0);
+  const int4 h0 = p.tile_hdr[2 * tile], h1 = p.tile_hdr[2 * tile + 1];
+  const int c0 = h0.x, ncol = h0.y, cb = h0.z, nct = h0.w;
+  const i64 g0 = (i64)(u32)h1.x | ((i64)h1.y << 32);
+  const int nnz_t = h1.z;
   double* stage = sm;
   double* S = sm + nnz_t;
+  // node ids of this thread's tile cells (up to GC per thread), issued first: the coordinate gathers depend on them
+  constexpr int GC = 4;
+  int4 nd[GC];
+#pragma unroll
+  for (int r = 0; r < GC; r++) {
+    const int i = tid + r * TPB;
+    nd[r] = (i < nct) ? p.tile_nodes[cb + i] : make_int4(1, 1, 1, 1);
+  }
+  // this thread's column record, pair range and first batch of pair records
+  const int col = c0 + tid;
+  const bool has_col = tid < ncol;
+  u32 kb = 0, ke = 0;
+  int abase = 0;
+  uint4 ca = make_uint4(0, 0, 0, 0), cbx = make_uint4(0, 0, 0, 0);
+  if (has_col) {
+    ca = p.cols[2 * (i64)col]; cbx = p.cols[2 * (i64)col + 1];
+    abase = (int)(p.colptr[col] - 1 - g0);
+    kb = cbx.w; ke = kb + (ca.y >> 24);
+  }
   for (int c = tid; c < 256; c += TPB) {
     const int P = c & 3, Q = (c >> 2) & 3, I = (c >> 4) & 3, O = (c >> 6) & 3;
     unsigned long long t = 0;
@@ -216,35 +236,26 @@ __global__ void __launch_bounds__(TPB) p2tet_edge_kernel(const EdgeParams p) {
     t |= (unsigned long long)sidx(Q, O) << 48;
     s_tab[c] = t;
   }
-  // this thread's column and its first batch of pair records (issued before the geometry phase)
-  const int col = c0 + tid;
-  const bool has_col = col < c1;
-  i64 kb = 0, ke = 0;
-  int abase = 0;
-  uint4 ca = make_uint4(0, 0, 0, 0), cbx = make_uint4(0, 0, 0, 0);
-  if (has_col) {
-    kb = p.col_pairbeg[col]; ke = p.col_pairbeg[col + 1];
-    abase = (int)(p.colptr[col] - 1 - g0);
-    ca = p.cols[2 * (i64)col]; cbx = p.cols[2 * (i64)col + 1];
-  }
   uint4 rec[PF];
 #pragma unroll
   for (int j = 0; j < PF; j++) rec[j] = (kb + j < ke) ? p.pairs[kb + j] : make_uint4(0, 0, 0, 0);
   for (int i = tid; i < nnz_t; i += TPB) stage[i] = 0.0;
-  // ---- geometry of the tile's distinct cells, two cells per thread and round ----
-  for (int i = tid; i < nct; i += 2 * TPB) {
-    const int i2 = i + TPB;
-    const i64 cA = p.tile_cells[cb + i];
-    const i64 cB = (i2 < nct) ? p.tile_cells[cb + i2] : cA;
-    double sA[10], sB[10];
-    cell_S(p.g, cA, p.factor, sA);
-    cell_S(p.g, cB, p.factor, sB);
+  // ---- geometry of the tile's distinct cells ----
 #pragma unroll
-    for (int k = 0; k < 10; k++) S[k * nct + i] = sA[k];        // k-major: conflict-free stores
-    if (i2 < nct) {
+  for (int r = 0; r < GC; r++) {
+    const int i = tid + r * TPB;
+    if (i < nct) {
+      double sA[10];
+      cell_S(p.g, nd[r], p.factor, sA);
 #pragma unroll
-      for (int k = 0; k < 10; k++) S[k * nct + i2] = sB[k];
+      for (int k = 0; k < 10; k++) S[k * nct + i] = sA[k];        // k-major: conflict-free stores
     }
+  }
+  for (int i = tid + GC * TPB; i < nct; i += TPB) {               // tiles with more than GC*TPB cells (rare)
+    double sA[10];
+    cell_S(p.g, p.tile_nodes[cb + i], p.factor, sA);
+#pragma unroll
+    for (int k = 0; k < 10; k++) S[k * nct + i] = sA[k];
   }
   __syncthreads();
   if (has_col && ke > kb) {
@@ -253,7 +264,7 @@ __global__ void __launch_bounds__(TPB) p2tet_edge_kernel(const EdgeParams p) {
     double c0r = 0.0, c1r = 0.0, c2r = 0.0;          // carry: partial rows of the shared ring vertex
     double f0 = 0.0, f1 = 0.0, f2 = 0.0;             // closed ring: in-rows of the first pair, completed at the end
     const bool closed = (ca.x >> 24) & 1u;
-    for (i64 k = kb; k < ke; k += PF) {
+    for (u32 k = kb; k < ke; k += PF) {
       uint4 cur[PF];
 #pragma unroll
       for (int j = 0; j < PF; j++) cur[j] = rec[j];
@@ -323,23 +334,27 @@ __global__ void __launch_bounds__(TPB) p2tet_edge_kernel(const EdgeParams p) {
 }
 
 // A[v,v] = -sum_{i != v} A[i,v] : one warp per vertex column, fixed shuffle tree
-__global__ void p2tet_vertex_diag_kernel(const u32* vcols, const u32* vdiag, i64 nv, const i64* colptr, double* nzval) {
+__global__ void p2tet_vertex_diag_kernel(const uint4* vrec, i64 nv, double* nzval) {
   const i64 w = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  const u32 lane = threadIdx.x & 31;
   if (w >= nv) return;
-  const i64 col = vcols[w];
-  const i64 b = colptr[col] - 1, e = colptr[col + 1] - 1;
-  const u32 d32 = vdiag[w];
+  const uint4 r = vrec[w];                 // {first slot, #slots, diagonal slot | NONE, 0}
+  const u32 b = r.x, e = r.x + r.y, d32 = r.z;
   const i64 dslot = (d32 == NONE) ? -1 : (i64)d32;
-  double s = 0.0;
-  for (i64 k = b + lane; k < e; k += 32)
-    if (k != dslot) s += nzval[k];
+  // three independent loads per lane cover columns of up to 96 entries in one round
+  const u32 k0 = b + lane, k1 = k0 + 32, k2 = k0 + 64;
+  const double v0 = (k0 < e && k0 != d32) ? nzval[k0] : 0.0;
+  const double v1 = (k1 < e && k1 != d32) ? nzval[k1] : 0.0;
+  const double v2 = (k2 < e && k2 != d32) ? nzval[k2] : 0.0;
+  double s = (v0 + v1) + v2;
+  for (u32 k = k0 + 96; k < e; k += 32)
+    if (k != d32) s += nzval[k];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0 && dslot >= 0) nzval[dslot] = -s;
 }
 
-__global__ void find_diag_slots(const u32* vcols, i64 nv, const i64* colptr, const i64* rowval, u32* vdiag) {
+__global__ void find_diag_slots(const u32* vcols, i64 nv, const i64* colptr, const i64* rowval, uint4* vrec) {
   i64 w = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (w >= nv) return;
   const i64 col = vcols[w];
@@ -349,7 +364,8 @@ __global__ void find_diag_slots(const u32* vcols, i64 nv, const i64* colptr, con
     i64 mid = (lo + hi) >> 1;
     if (rowval[mid] < col + 1) lo = mid + 1; else hi = mid;
   }
-  vdiag[w] = (lo < end && rowval[lo] == col + 1) ? (u32)lo : NONE;
+  const u32 d = (lo < end && rowval[lo] == col + 1) ? (u32)lo : NONE;
+  vrec[w] = make_uint4((u32)(colptr[col] - 1), (u32)(colptr[col + 1] - colptr[col]), d, 0);
 }
 
 // closed-form local stiffness of the unit reference tetrahedron, used to verify that the
@@ -420,16 +436,20 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   // (2) host: ring order of every edge column, tiles over the edge columns, list of vertex columns
   std::vector<u32> pair_cell(npairs), pair_local(npairs), pair_code(npairs), col_of_pair(npairs), vcols;
   std::vector<unsigned char> col_closed(ncols, 2);
-  std::vector<i32> tile_rng, tile_crng, tile_cells;
+  std::vector<int4> tile_hdr, tile_nodes;
+  std::vector<i32> tile_cells;   // distinct cells of the open tile (global ids), flushed into tile_nodes
   std::vector<i32> mark(ncells, -1), local_of(ncells, 0);
-  tile_cells.reserve((size_t)ncells * 3);
+  tile_nodes.reserve((size_t)ncells * 3);
   int cur_tile = 0, cur_cols = 0, cur_cells = 0;
   i64 cur_nnz = 0, tile_first_col = 0;
   i64 max_smem = 0;
   auto close_tile = [&](i64 end_col) {
     if (cur_cols == 0) return;
-    tile_rng.push_back((i32)tile_first_col); tile_rng.push_back((i32)end_col);
-    tile_crng.push_back((i32)(tile_cells.size() - cur_cells)); tile_crng.push_back((i32)tile_cells.size());
+    const i64 g0 = h_colptr[tile_first_col] - 1;
+    tile_hdr.push_back(make_int4((int)tile_first_col, (int)(end_col - tile_first_col), (int)tile_nodes.size(), cur_cells));
+    tile_hdr.push_back(make_int4((int)(u32)(g0 & 0xffffffffll), (int)(g0 >> 32), (int)cur_nnz, 0));
+    for (i32 c : tile_cells) tile_nodes.push_back(make_int4(h_cn[(size_t)c * 4], h_cn[(size_t)c * 4 + 1], h_cn[(size_t)c * 4 + 2], h_cn[(size_t)c * 4 + 3]));
+    tile_cells.clear();
     max_smem = std::max<i64>(max_smem, 8 * cur_nnz + 80 * (i64)cur_cells);
     cur_tile++; cur_cols = 0; cur_cells = 0; cur_nnz = 0;
   };
@@ -447,7 +467,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
       for (i64 k = kb; k < ke; k++) { pair_cell[k] = h_cell[k]; pair_local[k] = 0; pair_code[k] = 0; col_of_pair[k] = (u32)j; }
       continue;
     }
-    if (len > 254) return fail(GRMP_EUNSUPPORTED, "fast path: an edge column has more than 254 entries");
+    if (len > 254 || ke - kb > 255) return fail(GRMP_EUNSUPPORTED, "fast path: an edge column has more than 254 entries");
     // ---- ring order of the cells around the edge ----
     const int n = (int)(ke - kb);
     rp.resize(n);
@@ -534,14 +554,14 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   }
   close_tile(ncols);
   if (max_smem > 200 * 1024) return fail(GRMP_EUNSUPPORTED, "fast path: a single column exceeds the shared-memory tile");
-  const int ntiles = (int)(tile_rng.size() / 2);
+  const int ntiles = (int)(tile_hdr.size() / 2);
+  if (npairs >= (i64)NONE) return fail(GRMP_EUNSUPPORTED, "fast path: more than 2^32-1 pairs");
   out->ntiles = ntiles; out->npairs = npairs; out->smem_bytes = (int)max_smem; out->nvcols = (i64)vcols.size();
-  if (tile_rng.empty()) { tile_rng.assign(2, 0); tile_crng.assign(2, 0); }
-  if (tile_cells.empty()) tile_cells.push_back(0);
+  if (tile_hdr.empty()) tile_hdr.assign(2, make_int4(0, 0, 0, 0));
+  if (tile_nodes.empty()) tile_nodes.push_back(make_int4(1, 1, 1, 1));
   if (vcols.empty()) vcols.push_back(0);
-  GRMP_TRY(out->tile_colbeg.upload(tile_rng.data(), tile_rng.size(), s));
-  GRMP_TRY(out->tile_cellbeg.upload(tile_crng.data(), tile_crng.size(), s));
-  GRMP_TRY(out->tile_cells.upload(tile_cells.data(), tile_cells.size(), s));
+  GRMP_TRY(out->tile_hdr.upload(tile_hdr.data(), tile_hdr.size(), s));
+  GRMP_TRY(out->tile_nodes.upload(tile_nodes.data(), tile_nodes.size(), s));
   // (3) pack pair / column records on the device (slots are looked up in the pattern by (row, col))
   DevBuf<u32> d_cell, d_local, d_code, d_colof;
   DevBuf<unsigned char> d_closed;
@@ -559,9 +579,9 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   GRMP_CUDA(cudaGetLastError());
   // (4) vertex columns: list + diagonal slots
   GRMP_TRY(out->vcols.upload(vcols.data(), vcols.size(), s));
-  GRMP_TRY(out->vdiag.alloc(vcols.size()));
+  GRMP_TRY(out->vrec.alloc(vcols.size()));
   if (out->nvcols > 0) {
-    find_diag_slots<<<(unsigned)((out->nvcols + 255) / 256), 256, 0, s>>>(out->vcols.p, out->nvcols, pat.colptr.p, pat.rowval.p, out->vdiag.p);
+    find_diag_slots<<<(unsigned)((out->nvcols + 255) / 256), 256, 0, s>>>(out->vcols.p, out->nvcols, pat.colptr.p, pat.rowval.p, out->vrec.p);
     GRMP_CUDA(cudaGetLastError());
   }
   GRMP_CUDA(cudaFuncSetAttribute(p2tet_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<i64>(max_smem, 1024)));
@@ -571,13 +591,13 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
 
 int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const FastP2Tet& f, double* nzval) {
   if (f.ntiles > 0) {
-    EdgeParams ep{p.g, pat.colptr.p, f.col_pairbeg.p, f.pairs.p, f.cols.p, f.tile_colbeg.p, f.tile_cellbeg.p, f.tile_cells.p, p.factor, nzval};
+    EdgeParams ep{p.g, pat.colptr.p, f.col_pairbeg.p, f.pairs.p, f.cols.p, f.tile_hdr.p, f.tile_nodes.p, p.factor, nzval};
     p2tet_edge_kernel<<<f.ntiles, TPB, f.smem_bytes, ctx->stream>>>(ep);
     GRMP_CUDA(cudaGetLastError());
   }
   if (f.nvcols > 0) {
     const i64 threads = f.nvcols * 32;
-    p2tet_vertex_diag_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(f.vcols.p, f.vdiag.p, f.nvcols, pat.colptr.p, nzval);
+    p2tet_vertex_diag_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(f.vrec.p, f.nvcols, nzval);
     GRMP_CUDA(cudaGetLastError());
   }
   return GRMP_OK;
