@@ -17,7 +17,9 @@ struct FastP2Tet {
   DevBuf<uint4> pairs;         // ring-ordered pair records of the edge columns
   DevBuf<uint4> cols;          // 2 per column: fixed-row offsets, closing offsets, mirrored slots
   DevBuf<u32> vcols;           // vertex columns
-  DevBuf<uint4> vrec;          // per vertex column: first slot, #slots, diagonal slot
+  DevBuf<uint4> vrec;          // per vertex column: diagonal slot, first spoke slot, #spokes
+  DevBuf<uint2> spokes;        // per edge column: scratch slots in the spoke lists of its two end vertices
+  DevBuf<double> dscratch;     // per (vertex, spoke): 0.2 * ring sum of S_vv
   i64 nvcols = 0;
 };
 

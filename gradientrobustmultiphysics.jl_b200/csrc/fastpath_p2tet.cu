@@ -28,6 +28,7 @@
 // comes from the bit-exact symbolic pass, and slots are looked up in it by (row, column).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "fastpath.cuh"
 
@@ -187,24 +188,26 @@ struct EdgeParams {
   const i64* col_pairbeg;   // [ncols+1]
   const uint4* pairs;
   const uint4* cols;
+  const uint2* spokes;      // per column: scratch slots of the two end vertices' spoke lists
+  double* dscratch;         // [sum of spoke counts] 0.2 * ring sum of S_vv per (vertex, spoke)
   const int4* tile_hdr;     // 2 per tile: {first column, #columns, first tile cell, #tile cells}, {g0 lo, g0 hi, nnz, 0}
   const int4* tile_nodes;   // CellNodes of the tiles' distinct cells
   double factor;
   double* nzval;
+  int dbg;                  // GRMP_DEBUG_FLAGS: bit 0 = skip the mirrored stores (timing experiments only)
 };
 
-constexpr int PF = 4;   // pair records fetched per batch (independent 16-byte loads in flight per thread)
 
 __global__ void __launch_bounds__(TPB, 5) p2tet_edge_kernel(const EdgeParams p) {
   extern __shared__ double sm[];
-  __shared__ unsigned long long s_tab[256];   // perm code -> 7 packed-S positions (one byte each)
+  __shared__ uint4 s_tab[256];   // perm code -> byte offsets (k * nct * 8, 16 bit each) of S_pp,S_qq,S_pq,S_pi,S_po,S_qi,S_qo
   const int tile = blockIdx.x, tid = threadIdx.x;
   const int4 h0 = p.tile_hdr[2 * tile], h1 = p.tile_hdr[2 * tile + 1];
   const int c0 = h0.x, ncol = h0.y, cb = h0.z, nct = h0.w;
   const i64 g0 = (i64)(u32)h1.x | ((i64)h1.y << 32);
   const int nnz_t = h1.z;
-  double* stage = sm;
-  double* S = sm + nnz_t;
+  double* __restrict__ stage = sm;          // every slot of the tile is written exactly once -> no zero-init needed
+  double* __restrict__ S = sm + nnz_t;
   // node ids of this thread's tile cells (up to GC per thread), issued first: the coordinate gathers depend on them
   constexpr int GC = 4;
   int4 nd[GC];
@@ -219,27 +222,24 @@ __global__ void __launch_bounds__(TPB, 5) p2tet_edge_kernel(const EdgeParams p) 
   u32 kb = 0, ke = 0;
   int abase = 0;
   uint4 ca = make_uint4(0, 0, 0, 0), cbx = make_uint4(0, 0, 0, 0);
+  uint2 spk = make_uint2(NONE, NONE);
   if (has_col) {
     ca = p.cols[2 * (i64)col]; cbx = p.cols[2 * (i64)col + 1];
+    spk = p.spokes[col];
     abase = (int)(p.colptr[col] - 1 - g0);
     kb = cbx.w; ke = kb + (ca.y >> 24);
   }
   for (int c = tid; c < 256; c += TPB) {
-    const int P = c & 3, Q = (c >> 2) & 3, I = (c >> 4) & 3, O = (c >> 6) & 3;
-    unsigned long long t = 0;
-    t |= (unsigned long long)sidx(P, P);
-    t |= (unsigned long long)sidx(Q, Q) << 8;
-    t |= (unsigned long long)sidx(P, Q) << 16;
-    t |= (unsigned long long)sidx(P, I) << 24;
-    t |= (unsigned long long)sidx(P, O) << 32;
-    t |= (unsigned long long)sidx(Q, I) << 40;
-    t |= (unsigned long long)sidx(Q, O) << 48;
+    const u32 P = c & 3, Q = (c >> 2) & 3, I = (c >> 4) & 3, O = (c >> 6) & 3;
+    const u32 m = (u32)nct * 8u;
+    uint4 t;
+    t.x = (sidx(P, P) * m) | ((sidx(Q, Q) * m) << 16);
+    t.y = (sidx(P, Q) * m) | ((sidx(P, I) * m) << 16);
+    t.z = (sidx(P, O) * m) | ((sidx(Q, I) * m) << 16);
+    t.w = (sidx(Q, O) * m);
     s_tab[c] = t;
   }
-  uint4 rec[PF];
-#pragma unroll
-  for (int j = 0; j < PF; j++) rec[j] = (kb + j < ke) ? p.pairs[kb + j] : make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < nnz_t; i += TPB) stage[i] = 0.0;
+  uint4 rnext = (kb < ke) ? p.pairs[kb] : make_uint4(0, 0, 0, 0);   // a column's records share one or two cache lines
   // ---- geometry of the tile's distinct cells ----
 #pragma unroll
   for (int r = 0; r < GC; r++) {
@@ -259,54 +259,52 @@ __global__ void __launch_bounds__(TPB, 5) p2tet_edge_kernel(const EdgeParams p) 
   }
   __syncthreads();
   if (has_col && ke > kb) {
-    double* a = stage + abase;
+    double* __restrict__ a = stage + abase;
     double A = 0.0, B = 0.0, C = 0.0, W = 0.0;       // rows v_P, v_Q, e_PQ of the column; (v_P, v_Q) coupling
     double c0r = 0.0, c1r = 0.0, c2r = 0.0;          // carry: partial rows of the shared ring vertex
     double f0 = 0.0, f1 = 0.0, f2 = 0.0;             // closed ring: in-rows of the first pair, completed at the end
     const bool closed = (ca.x >> 24) & 1u;
-    for (u32 k = kb; k < ke; k += PF) {
-      uint4 cur[PF];
-#pragma unroll
-      for (int j = 0; j < PF; j++) cur[j] = rec[j];
-#pragma unroll
-      for (int j = 0; j < PF; j++) rec[j] = (k + PF + j < ke) ? p.pairs[k + PF + j] : make_uint4(0, 0, 0, 0);
-#pragma unroll
-      for (int j = 0; j < PF; j++) {
-        if (k + j < ke) {
-          const uint4 r = cur[j];
-          const u32 cl = r.x & 0xffffu;
-          const unsigned long long t = s_tab[(r.x >> 16) & 255u];
-          const double* s = S + cl;
-          const double spp = s[(int)(t & 255u) * nct], sqq = s[(int)((t >> 8) & 255u) * nct], spq = s[(int)((t >> 16) & 255u) * nct];
-          const double spi = s[(int)((t >> 24) & 255u) * nct], spo = s[(int)((t >> 32) & 255u) * nct];
-          const double sqi = s[(int)((t >> 40) & 255u) * nct], sqo = s[(int)((t >> 48) & 255u) * nct];
-          A += 0.6 * spq - 0.2 * spp;
-          B += 0.6 * spq - 0.2 * sqq;
-          C += 1.6 * (spp + sqq + spq);
-          W += -0.2 * spq;
-          const double base = spq + spp, baseq = spq + sqq;
-          const u32 fl = r.x >> 24;
-          if (fl & PF_RESET) { c0r = 0.0; c1r = 0.0; c2r = 0.0; }
-          const double in0 = c0r + -0.2 * (spi + sqi);                 // v_in
-          const double in1 = c1r + 0.8 * (2.0 * sqi + spi + base);      // e_P,in
-          const double in2 = c2r + 0.8 * (2.0 * spi + sqi + baseq);     // e_Q,in
-          c0r = -0.2 * (spo + sqo);                                     // v_out
-          c1r = 0.8 * (2.0 * sqo + spo + base);                         // e_P,out
-          c2r = 0.8 * (2.0 * spo + sqo + baseq);                        // e_Q,out
-          const double x = 0.8 * (spi + spo + sqi + sqo);               // e_in,out
-          const u32 o3 = r.y >> 24;
-          if (o3 != 255u) a[o3] = x;
-          if ((fl & PF_END) && r.w != NONE) p.nzval[r.w] = c0r;       // chain end inside a halo column: mirror (e_PQ, v_out)
-          if (closed && (fl & PF_FIRST)) {
-            f0 = in0; f1 = in1; f2 = in2;                               // partner is the last pair of the ring
-          } else {
-            const u32 o0 = r.y & 255u, o1 = (r.y >> 8) & 255u, o2 = (r.y >> 16) & 255u;
-            if (o0 != 255u) a[o0] = in0;
-            if (o1 != 255u) a[o1] = in1;
-            if (o2 != 255u) a[o2] = in2;
-            if (r.z != NONE) p.nzval[r.z] = in0;                        // mirror (e_PQ, v_in)
-          }
-        }
+    const char* __restrict__ Sb = reinterpret_cast<const char*>(S);
+    double Tp = 0.0, Tq = 0.0;                       // ring sums of S_PP, S_QQ: 0.2*sum over the spokes = diagonal of v_P, v_Q
+#pragma unroll 2
+    for (u32 k = kb; k < ke; k++) {
+      const uint4 r = rnext;
+      if (k + 1 < ke) rnext = p.pairs[k + 1];
+      const uint4 t = s_tab[(r.x >> 16) & 255u];
+      const char* sc = Sb + (r.x & 0xffffu) * 8u;
+      const double spp = *reinterpret_cast<const double*>(sc + (t.x & 0xffffu));
+      const double sqq = *reinterpret_cast<const double*>(sc + (t.x >> 16));
+      const double spq = *reinterpret_cast<const double*>(sc + (t.y & 0xffffu));
+      const double spi = *reinterpret_cast<const double*>(sc + (t.y >> 16));
+      const double spo = *reinterpret_cast<const double*>(sc + (t.z & 0xffffu));
+      const double sqi = *reinterpret_cast<const double*>(sc + (t.z >> 16));
+      const double sqo = *reinterpret_cast<const double*>(sc + (t.w & 0xffffu));
+      A += 0.6 * spq - 0.2 * spp;
+      B += 0.6 * spq - 0.2 * sqq;
+      C += 1.6 * (spp + sqq + spq);
+      W += -0.2 * spq;
+      Tp += spp; Tq += sqq;
+      const double base = spq + spp, baseq = spq + sqq;
+      const u32 fl = r.x >> 24;
+      if (fl & PF_RESET) { c0r = 0.0; c1r = 0.0; c2r = 0.0; }
+      const double in0 = c0r + -0.2 * (spi + sqi);                 // v_in
+      const double in1 = c1r + 0.8 * (2.0 * sqi + spi + base);      // e_P,in
+      const double in2 = c2r + 0.8 * (2.0 * spi + sqi + baseq);     // e_Q,in
+      c0r = -0.2 * (spo + sqo);                                     // v_out
+      c1r = 0.8 * (2.0 * sqo + spo + base);                         // e_P,out
+      c2r = 0.8 * (2.0 * spo + sqo + baseq);                        // e_Q,out
+      const double x = 0.8 * (spi + spo + sqi + sqo);               // e_in,out
+      const u32 o3 = r.y >> 24;
+      if (o3 != 255u) a[o3] = x;
+      if ((fl & PF_END) && r.w != NONE && !(p.dbg & 1)) p.nzval[r.w] = c0r;         // chain end inside a halo column: mirror (e_PQ, v_out)
+      if (closed && (fl & PF_FIRST)) {
+        f0 = in0; f1 = in1; f2 = in2;                               // partner is the last pair of the ring
+      } else {
+        const u32 o0 = r.y & 255u, o1 = (r.y >> 8) & 255u, o2 = (r.y >> 16) & 255u;
+        if (o0 != 255u) a[o0] = in0;
+        if (o1 != 255u) a[o1] = in1;
+        if (o2 != 255u) a[o2] = in2;
+        if (r.z != NONE && !(p.dbg & 1)) p.nzval[r.z] = in0;                        // mirror (e_PQ, v_in)
       }
     }
     // closing rows: closed ring -> first pair's in-rows + last carry; open chain -> last pair's out-rows
@@ -316,45 +314,48 @@ __global__ void __launch_bounds__(TPB, 5) p2tet_edge_kernel(const EdgeParams p) 
       if (o0 != 255u) a[o0] = q0;
       if (o1 != 255u) a[o1] = q1;
       if (o2 != 255u) a[o2] = q2;
-      if (cbx.x != NONE) p.nzval[cbx.x] = q0;
+      if (cbx.x != NONE && !(p.dbg & 1)) p.nzval[cbx.x] = q0;
     }
     {
       const u32 oA = ca.x & 255u, oB = (ca.x >> 8) & 255u, oC = (ca.x >> 16) & 255u;
       if (oA != 255u) a[oA] = A;
       if (oB != 255u) a[oB] = B;
       if (oC != 255u) a[oC] = C;
+      if (!(p.dbg & 1)) {
       if (ca.z != NONE) p.nzval[ca.z] = A;       // (e_PQ, v_P)
       if (ca.w != NONE) p.nzval[ca.w] = B;       // (e_PQ, v_Q)
       if (cbx.y != NONE) p.nzval[cbx.y] = W;     // (v_Q, v_P)
       if (cbx.z != NONE) p.nzval[cbx.z] = W;     // (v_P, v_Q)
+      }
+      if (spk.x != NONE) p.dscratch[spk.x] = 0.2 * Tp;
+      if (spk.y != NONE) p.dscratch[spk.y] = 0.2 * Tq;
     }
   }
   __syncthreads();
-  for (int i = tid; i < nnz_t; i += TPB) p.nzval[g0 + i] = stage[i];
+  {
+    double* __restrict__ dst = p.nzval + g0;
+    int i = tid;
+    for (; i + 3 * TPB < nnz_t; i += 4 * TPB) {
+      const double v0 = stage[i], v1 = stage[i + TPB], v2 = stage[i + 2 * TPB], v3 = stage[i + 3 * TPB];
+      dst[i] = v0; dst[i + TPB] = v1; dst[i + 2 * TPB] = v2; dst[i + 3 * TPB] = v3;
+    }
+    for (; i < nnz_t; i += TPB) dst[i] = stage[i];
+  }
 }
 
-// A[v,v] = -sum_{i != v} A[i,v] : one warp per vertex column, fixed shuffle tree
-__global__ void p2tet_vertex_diag_kernel(const uint4* vrec, i64 nv, double* nzval) {
-  const i64 w = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5;
-  const u32 lane = threadIdx.x & 31;
+// A[v,v] = 0.6 * sum_{K containing v} S_vv = 0.2 * sum over the spokes (v w) of the ring sums of S_vv (every cell at v
+// has three edges at v); the spoke values were left in dscratch by the edge threads.  Fixed order -> deterministic.
+__global__ void p2tet_vertex_diag_kernel(const uint4* vrec, i64 nv, const double* __restrict__ dscratch, double* nzval) {
+  const i64 w = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (w >= nv) return;
-  const uint4 r = vrec[w];                 // {first slot, #slots, diagonal slot | NONE, 0}
-  const u32 b = r.x, e = r.x + r.y, d32 = r.z;
-  const i64 dslot = (d32 == NONE) ? -1 : (i64)d32;
-  // three independent loads per lane cover columns of up to 96 entries in one round
-  const u32 k0 = b + lane, k1 = k0 + 32, k2 = k0 + 64;
-  const double v0 = (k0 < e && k0 != d32) ? nzval[k0] : 0.0;
-  const double v1 = (k1 < e && k1 != d32) ? nzval[k1] : 0.0;
-  const double v2 = (k2 < e && k2 != d32) ? nzval[k2] : 0.0;
-  double s = (v0 + v1) + v2;
-  for (u32 k = k0 + 96; k < e; k += 32)
-    if (k != d32) s += nzval[k];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0 && dslot >= 0) nzval[dslot] = -s;
+  const uint4 r = vrec[w];                 // {diagonal slot | NONE, first spoke slot, #spokes, 0}
+  if (r.x == NONE) return;
+  double s = 0.0;
+  for (u32 k = 0; k < r.z; k++) s += dscratch[r.y + k];
+  nzval[r.x] = s;
 }
 
-__global__ void find_diag_slots(const u32* vcols, i64 nv, const i64* colptr, const i64* rowval, uint4* vrec) {
+__global__ void find_diag_slots(const u32* vcols, const u32* vspoke, i64 nv, const i64* colptr, const i64* rowval, uint4* vrec) {
   i64 w = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (w >= nv) return;
   const i64 col = vcols[w];
@@ -365,7 +366,7 @@ __global__ void find_diag_slots(const u32* vcols, i64 nv, const i64* colptr, con
     if (rowval[mid] < col + 1) lo = mid + 1; else hi = mid;
   }
   const u32 d = (lo < end && rowval[lo] == col + 1) ? (u32)lo : NONE;
-  vrec[w] = make_uint4((u32)(colptr[col] - 1), (u32)(colptr[col + 1] - colptr[col]), d, 0);
+  vrec[w] = make_uint4(d, vspoke[2 * w], vspoke[2 * w + 1], 0);
 }
 
 // closed-form local stiffness of the unit reference tetrahedron, used to verify that the
@@ -426,16 +427,18 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   const i64 npairs = dg.ncontrib;
   std::vector<u32> h_cell(npairs), h_src(npairs);
   std::vector<i64> h_pairbeg(ncols + 1), h_colptr(ncols + 1);
-  std::vector<i32> h_cn((size_t)ncells * 4);
+  std::vector<i32> h_cn((size_t)ncells * 4), h_dofs((size_t)ncells * 10);
   GRMP_CUDA(cudaMemcpyAsync(h_cell.data(), dg.gcell.p, npairs * 4, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaMemcpyAsync(h_src.data(), dg.gsrc.p, npairs * 4, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaMemcpyAsync(h_pairbeg.data(), dg.segptr.p, (ncols + 1) * 8, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaMemcpyAsync(h_colptr.data(), pat.colptr.p, (ncols + 1) * 8, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaMemcpyAsync(h_cn.data(), p.g.cellnodes, (size_t)ncells * 16, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaMemcpyAsync(h_dofs.data(), p.e1.celldofs, (size_t)ncells * 40, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaStreamSynchronize(s));
   // (2) host: ring order of every edge column, tiles over the edge columns, list of vertex columns
   std::vector<u32> pair_cell(npairs), pair_local(npairs), pair_code(npairs), col_of_pair(npairs), vcols;
   std::vector<unsigned char> col_closed(ncols, 2);
+  std::vector<u32> endP(ncols, NONE), endQ(ncols, NONE);     // vertex dofs of the two ends of every edge column
   std::vector<int4> tile_hdr, tile_nodes;
   std::vector<i32> tile_cells;   // distinct cells of the open tile (global ids), flushed into tile_nodes
   std::vector<i32> mark(ncells, -1), local_of(ncells, 0);
@@ -484,6 +487,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
       if (cn[pl] != P0) { int tmp = pl; pl = ql; ql = tmp; }      // consistent global orientation (P,Q)
       if (cn[pl] != P0) return fail(GRMP_EUNSUPPORTED, "fast path: inconsistent edge column");
       rp[t] = RP{c, pl, ql, rl, sl, cn[rl], cn[sl]};
+      if (t == 0) { endP[j] = (u32)(h_dofs[(size_t)c * 10 + pl] - 1); endQ[j] = (u32)(h_dofs[(size_t)c * 10 + ql] - 1); }
     }
     // degrees of the ring vertices; chains start at vertices of degree 1, a star without such a vertex is a closed ring
     std::vector<int> degR(n), degS(n);
@@ -577,11 +581,27 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   if (npairs) pack_pairs<<<(unsigned)((npairs + 255) / 256), 256, 0, s>>>(pp);
   if (ncols) pack_cols<<<(unsigned)((ncols + 255) / 256), 256, 0, s>>>(pp);
   GRMP_CUDA(cudaGetLastError());
+  // (3b) spoke lists: the diagonal of a vertex column is 0.2 * sum over its spokes of the ring sums of S_vv
+  std::vector<u32> spoke_cnt(ncols, 0), spoke_ptr(ncols + 1, 0);
+  for (i64 j = 0; j < ncols; j++) if (endP[j] != NONE) { spoke_cnt[endP[j]]++; spoke_cnt[endQ[j]]++; }
+  for (i64 j = 0; j < ncols; j++) spoke_ptr[j + 1] = spoke_ptr[j] + spoke_cnt[j];
+  std::vector<uint2> spokes(std::max<i64>(ncols, 1), make_uint2(NONE, NONE));
+  std::fill(spoke_cnt.begin(), spoke_cnt.end(), 0);
+  for (i64 j = 0; j < ncols; j++) if (endP[j] != NONE) {
+    spokes[j].x = spoke_ptr[endP[j]] + spoke_cnt[endP[j]]++;
+    spokes[j].y = spoke_ptr[endQ[j]] + spoke_cnt[endQ[j]]++;
+  }
+  std::vector<u32> vspoke(2 * vcols.size());
+  for (size_t w2 = 0; w2 < vcols.size(); w2++) { vspoke[2 * w2] = spoke_ptr[vcols[w2]]; vspoke[2 * w2 + 1] = spoke_cnt[vcols[w2]]; }
+  DevBuf<u32> d_vspoke;
+  GRMP_TRY(d_vspoke.upload(vspoke.data(), vspoke.size(), s));
+  GRMP_TRY(out->spokes.upload(spokes.data(), spokes.size(), s));
+  GRMP_TRY(out->dscratch.alloc(std::max<size_t>(spoke_ptr[ncols], 1)));
   // (4) vertex columns: list + diagonal slots
   GRMP_TRY(out->vcols.upload(vcols.data(), vcols.size(), s));
   GRMP_TRY(out->vrec.alloc(vcols.size()));
   if (out->nvcols > 0) {
-    find_diag_slots<<<(unsigned)((out->nvcols + 255) / 256), 256, 0, s>>>(out->vcols.p, out->nvcols, pat.colptr.p, pat.rowval.p, out->vrec.p);
+    find_diag_slots<<<(unsigned)((out->nvcols + 255) / 256), 256, 0, s>>>(out->vcols.p, d_vspoke.p, out->nvcols, pat.colptr.p, pat.rowval.p, out->vrec.p);
     GRMP_CUDA(cudaGetLastError());
   }
   GRMP_CUDA(cudaFuncSetAttribute(p2tet_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<i64>(max_smem, 1024)));
@@ -591,13 +611,13 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
 
 int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const FastP2Tet& f, double* nzval) {
   if (f.ntiles > 0) {
-    EdgeParams ep{p.g, pat.colptr.p, f.col_pairbeg.p, f.pairs.p, f.cols.p, f.tile_hdr.p, f.tile_nodes.p, p.factor, nzval};
+    static const int dbg = getenv("GRMP_DEBUG_FLAGS") ? atoi(getenv("GRMP_DEBUG_FLAGS")) : 0;
+    EdgeParams ep{p.g, pat.colptr.p, f.col_pairbeg.p, f.pairs.p, f.cols.p, f.spokes.p, f.dscratch.p, f.tile_hdr.p, f.tile_nodes.p, p.factor, nzval, dbg};
     p2tet_edge_kernel<<<f.ntiles, TPB, f.smem_bytes, ctx->stream>>>(ep);
     GRMP_CUDA(cudaGetLastError());
   }
-  if (f.nvcols > 0) {
-    const i64 threads = f.nvcols * 32;
-    p2tet_vertex_diag_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(f.vrec.p, f.nvcols, nzval);
+  if (f.nvcols > 0 && !(getenv("GRMP_DEBUG_FLAGS") && (atoi(getenv("GRMP_DEBUG_FLAGS")) & 2))) {
+    p2tet_vertex_diag_kernel<<<(unsigned)((f.nvcols + 255) / 256), 256, 0, ctx->stream>>>(f.vrec.p, f.nvcols, f.dscratch.p, nzval);
     GRMP_CUDA(cudaGetLastError());
   }
   return GRMP_OK;
