@@ -8,6 +8,7 @@ namespace grmp {
 
 struct FastP2Tet {
   int ntiles = 0;
+  int tpb = 128;
   i64 npairs = 0;
   int smem_bytes = 0;
   int max_tile_cells = 0;

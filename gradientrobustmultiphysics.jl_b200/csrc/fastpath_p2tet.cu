@@ -36,8 +36,8 @@ namespace grmp {
 
 namespace {
 
-constexpr int TPB = 128;                 // threads (= edge columns) per tile
-constexpr int SMEM_BUDGET = 44 * 1024;   // nzval stage + S of the tile's distinct cells
+constexpr int TPB_DEFAULT = 128;         // threads (= edge columns) per tile
+constexpr int SMEM_BUDGET_DEFAULT = 44 * 1024;   // nzval stage + S of the tile's distinct cells
 constexpr u32 NONE = 0xffffffffu;
 
 // local edge e -> (p,q), Tetrahedron3D edges [1 2],[1 3],[1 4],[2 3],[2 4],[3 4] (h1_p2.jl:231-236)
@@ -55,15 +55,27 @@ __host__ __device__ inline int sidx(int a, int b) {      // index of S_ab in the
 }
 
 // S_ab = factor * |T| * grad(lambda_a).grad(lambda_b), packed (00,01,02,03,11,12,13,22,23,33)
-__device__ __forceinline__ void cell_S(const GridView& g, const int4 nd, double factor, double* S) {
-  const double* x0 = g.coords + (i64)(nd.x - 1) * 3;
-  const double* x1 = g.coords + (i64)(nd.y - 1) * 3;
-  const double* x2 = g.coords + (i64)(nd.z - 1) * 3;
-  const double* x3 = g.coords + (i64)(nd.w - 1) * 3;
-  const double p0x = x0[0], p0y = x0[1], p0z = x0[2];
-  const double ax = x1[0] - p0x, ay = x1[1] - p0y, az = x1[2] - p0z;
-  const double bx = x2[0] - p0x, by = x2[1] - p0y, bz = x2[2] - p0z;
-  const double cx = x3[0] - p0x, cy = x3[1] - p0y, cz = x3[2] - p0z;
+// one 256-bit gather per node from the padded coordinate copy (a node is 24 B inside one 32 B sector)
+__device__ __forceinline__ void load_node(const double* coords4, int node1, double& x, double& y, double& z) {
+  double w;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(coords4 + 4 * (i64)(node1 - 1)));
+}
+__device__ __forceinline__ void cell_S(const GridView& g, const int4 nd, double factor, double* S, int dbg = 0) {
+  double p0x, p0y, p0z, p1x, p1y, p1z, p2x, p2y, p2z, p3x, p3y, p3z;
+  if (!(dbg & 4)) {   // default: three 64-bit gathers per node (measured 8 % faster than one 256-bit gather from a padded copy)
+    const double* x0 = g.coords + (i64)(nd.x - 1) * 3; const double* x1 = g.coords + (i64)(nd.y - 1) * 3;
+    const double* x2 = g.coords + (i64)(nd.z - 1) * 3; const double* x3 = g.coords + (i64)(nd.w - 1) * 3;
+    p0x = x0[0]; p0y = x0[1]; p0z = x0[2]; p1x = x1[0]; p1y = x1[1]; p1z = x1[2];
+    p2x = x2[0]; p2y = x2[1]; p2z = x2[2]; p3x = x3[0]; p3y = x3[1]; p3z = x3[2];
+  } else {
+  load_node(g.coords4, nd.x, p0x, p0y, p0z);
+  load_node(g.coords4, nd.y, p1x, p1y, p1z);
+  load_node(g.coords4, nd.z, p2x, p2y, p2z);
+  load_node(g.coords4, nd.w, p3x, p3y, p3z);
+  }
+  const double ax = p1x - p0x, ay = p1y - p0y, az = p1z - p0z;
+  const double bx = p2x - p0x, by = p2y - p0y, bz = p2z - p0z;
+  const double cx = p3x - p0x, cy = p3y - p0y, cz = p3z - p0z;
   // n1 = b x c, n2 = c x a, n3 = a x b : grad(lambda_k) = n_k / det
   const double n1x = by * cz - bz * cy, n1y = bz * cx - bx * cz, n1z = bx * cy - by * cx;
   const double n2x = cy * az - cz * ay, n2y = cz * ax - cx * az, n2z = cx * ay - cy * ax;
@@ -198,7 +210,8 @@ struct EdgeParams {
 };
 
 
-__global__ void __launch_bounds__(TPB, 5) p2tet_edge_kernel(const EdgeParams p) {
+template <int TPB>
+__global__ void __launch_bounds__(TPB, (TPB <= 64 ? 10 : TPB <= 128 ? 5 : TPB <= 256 ? 2 : 1)) p2tet_edge_kernel(const EdgeParams p) {
   extern __shared__ double sm[];
   __shared__ uint4 s_tab[256];   // perm code -> byte offsets (k * nct * 8, 16 bit each) of S_pp,S_qq,S_pq,S_pi,S_po,S_qi,S_qo
   const int tile = blockIdx.x, tid = threadIdx.x;
@@ -246,14 +259,14 @@ __global__ void __launch_bounds__(TPB, 5) p2tet_edge_kernel(const EdgeParams p) 
     const int i = tid + r * TPB;
     if (i < nct) {
       double sA[10];
-      cell_S(p.g, nd[r], p.factor, sA);
+      cell_S(p.g, nd[r], p.factor, sA, p.dbg);
 #pragma unroll
       for (int k = 0; k < 10; k++) S[k * nct + i] = sA[k];        // k-major: conflict-free stores
     }
   }
   for (int i = tid + GC * TPB; i < nct; i += TPB) {               // tiles with more than GC*TPB cells (rare)
     double sA[10];
-    cell_S(p.g, p.tile_nodes[cb + i], p.factor, sA);
+    cell_S(p.g, p.tile_nodes[cb + i], p.factor, sA, p.dbg);
 #pragma unroll
     for (int k = 0; k < 10; k++) S[k * nct + i] = sA[k];
   }
@@ -435,6 +448,11 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   GRMP_CUDA(cudaMemcpyAsync(h_cn.data(), p.g.cellnodes, (size_t)ncells * 16, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaMemcpyAsync(h_dofs.data(), p.e1.celldofs, (size_t)ncells * 40, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaStreamSynchronize(s));
+  // tile shape (tunable for experiments: GRMP_FAST_TPB in {64,128,256}, GRMP_FAST_SMEM_KB)
+  int TPB = getenv("GRMP_FAST_TPB") ? atoi(getenv("GRMP_FAST_TPB")) : TPB_DEFAULT;
+  if (TPB != 64 && TPB != 128 && TPB != 256 && TPB != 512) TPB = TPB_DEFAULT;
+  const i64 SMEM_BUDGET = getenv("GRMP_FAST_SMEM_KB") ? 1024 * (i64)atoi(getenv("GRMP_FAST_SMEM_KB")) : SMEM_BUDGET_DEFAULT * (i64)TPB / TPB_DEFAULT;
+  out->tpb = TPB;
   // (2) host: ring order of every edge column, tiles over the edge columns, list of vertex columns
   std::vector<u32> pair_cell(npairs), pair_local(npairs), pair_code(npairs), col_of_pair(npairs), vcols;
   std::vector<unsigned char> col_closed(ncols, 2);
@@ -557,7 +575,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     }
   }
   close_tile(ncols);
-  if (max_smem > 200 * 1024) return fail(GRMP_EUNSUPPORTED, "fast path: a single column exceeds the shared-memory tile");
+  if (max_smem > 220 * 1024) return fail(GRMP_EUNSUPPORTED, "fast path: a single column exceeds the shared-memory tile");
   const int ntiles = (int)(tile_hdr.size() / 2);
   if (npairs >= (i64)NONE) return fail(GRMP_EUNSUPPORTED, "fast path: more than 2^32-1 pairs");
   out->ntiles = ntiles; out->npairs = npairs; out->smem_bytes = (int)max_smem; out->nvcols = (i64)vcols.size();
@@ -604,7 +622,11 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     find_diag_slots<<<(unsigned)((out->nvcols + 255) / 256), 256, 0, s>>>(out->vcols.p, d_vspoke.p, out->nvcols, pat.colptr.p, pat.rowval.p, out->vrec.p);
     GRMP_CUDA(cudaGetLastError());
   }
-  GRMP_CUDA(cudaFuncSetAttribute(p2tet_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<i64>(max_smem, 1024)));
+  const int smem_attr = (int)std::max<i64>(max_smem, 1024);
+  GRMP_CUDA(cudaFuncSetAttribute(p2tet_edge_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
+  GRMP_CUDA(cudaFuncSetAttribute(p2tet_edge_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
+  GRMP_CUDA(cudaFuncSetAttribute(p2tet_edge_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
+  GRMP_CUDA(cudaFuncSetAttribute(p2tet_edge_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
   GRMP_CUDA(cudaStreamSynchronize(s));
   return GRMP_OK;
 }
@@ -613,7 +635,10 @@ int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pa
   if (f.ntiles > 0) {
     static const int dbg = getenv("GRMP_DEBUG_FLAGS") ? atoi(getenv("GRMP_DEBUG_FLAGS")) : 0;
     EdgeParams ep{p.g, pat.colptr.p, f.col_pairbeg.p, f.pairs.p, f.cols.p, f.spokes.p, f.dscratch.p, f.tile_hdr.p, f.tile_nodes.p, p.factor, nzval, dbg};
-    p2tet_edge_kernel<<<f.ntiles, TPB, f.smem_bytes, ctx->stream>>>(ep);
+    if (f.tpb == 64) p2tet_edge_kernel<64><<<f.ntiles, 64, f.smem_bytes, ctx->stream>>>(ep);
+    else if (f.tpb == 256) p2tet_edge_kernel<256><<<f.ntiles, 256, f.smem_bytes, ctx->stream>>>(ep);
+    else if (f.tpb == 512) p2tet_edge_kernel<512><<<f.ntiles, 512, f.smem_bytes, ctx->stream>>>(ep);
+    else p2tet_edge_kernel<128><<<f.ntiles, 128, f.smem_bytes, ctx->stream>>>(ep);
     GRMP_CUDA(cudaGetLastError());
   }
   if (f.nvcols > 0 && !(getenv("GRMP_DEBUG_FLAGS") && (atoi(getenv("GRMP_DEBUG_FLAGS")) & 2))) {
