@@ -36,8 +36,8 @@ namespace grmp {
 
 namespace {
 
-constexpr int TPB_DEFAULT = 128;         // threads (= edge columns) per tile
-constexpr int SMEM_BUDGET_DEFAULT = 44 * 1024;   // nzval stage + S of the tile's distinct cells
+constexpr int TPB_DEFAULT = 256;         // threads (= edge columns) per tile
+constexpr int SMEM_BUDGET_DEFAULT = 88 * 1024;   // nzval stage + S of the tile's distinct cells
 constexpr u32 NONE = 0xffffffffu;
 
 // local edge e -> (p,q), Tetrahedron3D edges [1 2],[1 3],[1 4],[2 3],[2 4],[3 4] (h1_p2.jl:231-236)
@@ -219,8 +219,11 @@ __global__ void __launch_bounds__(TPB, (TPB <= 64 ? 10 : TPB <= 128 ? 5 : TPB <=
   const int c0 = h0.x, ncol = h0.y, cb = h0.z, nct = h0.w;
   const i64 g0 = (i64)(u32)h1.x | ((i64)h1.y << 32);
   const int nnz_t = h1.z;
-  double* __restrict__ stage = sm;          // every slot of the tile is written exactly once -> no zero-init needed
-  double* __restrict__ S = sm + nnz_t;
+  // stage[i] mirrors nzval[g0 + i]; it is shifted by one element when g0 is odd so that shared and global addresses
+  // of the same element are 16-byte aligned together (TMA bulk store).  Every slot is written exactly once -> no zero-init.
+  const int odd = (int)(g0 & 1);
+  double* __restrict__ stage = sm + odd;
+  double* __restrict__ S = sm + nnz_t + 2;
   // node ids of this thread's tile cells (up to GC per thread), issued first: the coordinate gathers depend on them
   constexpr int GC = 4;
   int4 nd[GC];
@@ -346,13 +349,20 @@ __global__ void __launch_bounds__(TPB, (TPB <= 64 ? 10 : TPB <= 128 ? 5 : TPB <=
   }
   __syncthreads();
   {
+    // the tile's nzval range is contiguous: one TMA bulk store (cp.async.bulk shared -> global) of the 16-byte aligned
+    // body, the (at most one) unaligned element at either end by ordinary stores
     double* __restrict__ dst = p.nzval + g0;
-    int i = tid;
-    for (; i + 3 * TPB < nnz_t; i += 4 * TPB) {
-      const double v0 = stage[i], v1 = stage[i + TPB], v2 = stage[i + 2 * TPB], v3 = stage[i + 3 * TPB];
-      dst[i] = v0; dst[i + TPB] = v1; dst[i + 2 * TPB] = v2; dst[i + 3 * TPB] = v3;
+    const int i0 = odd;                                   // first element whose address is 16-byte aligned
+    const int nb = (nnz_t > i0) ? ((nnz_t - i0) & ~1) : 0;  // elements in the bulk body
+    if (tid == 0 && nb > 0) {
+      const unsigned src = (unsigned)__cvta_generic_to_shared(stage + i0);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + i0), "r"(src), "r"(nb * 8) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    for (; i < nnz_t; i += TPB) dst[i] = stage[i];
+    if (tid == 1 && i0 == 1 && nnz_t > 0) dst[0] = stage[0];
+    if (tid == 2 && i0 + nb < nnz_t) dst[i0 + nb] = stage[i0 + nb];
+    if (tid == 0 && nb > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must stay alive until read
   }
 }
 
@@ -471,7 +481,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     tile_hdr.push_back(make_int4((int)(u32)(g0 & 0xffffffffll), (int)(g0 >> 32), (int)cur_nnz, 0));
     for (i32 c : tile_cells) tile_nodes.push_back(make_int4(h_cn[(size_t)c * 4], h_cn[(size_t)c * 4 + 1], h_cn[(size_t)c * 4 + 2], h_cn[(size_t)c * 4 + 3]));
     tile_cells.clear();
-    max_smem = std::max<i64>(max_smem, 8 * cur_nnz + 80 * (i64)cur_cells);
+    max_smem = std::max<i64>(max_smem, 8 * cur_nnz + 80 * (i64)cur_cells + 32);
     cur_tile++; cur_cols = 0; cur_cells = 0; cur_nnz = 0;
   };
   struct RP { u32 cell; int P, Q, R, S; i32 nR, nS; };
