@@ -129,8 +129,13 @@ def run_gpu(args):
     if world > 1:
         lp = G.partition.partition(s, rank, world)
         lg, ls, n_owned = lp.grid, lp.space, lp.n_owned
+        glob = {"ncells": int(g.ncells), "ndofs": int(s.ndofs)}
+        del g, s, lp            # every rank built the whole grid on the host; keep only its own part
+        import gc
+        gc.collect()
     else:
         lg, ls, n_owned = g, s, s.ndofs
+        glob = {"ncells": int(g.ncells), "ndofs": int(s.ndofs)}
     AP = G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [ls, ls])
     G.prepare_assembly(AP)
     h = AP.AM.h
@@ -234,7 +239,7 @@ def run_gpu(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic (uniform_refine(grid_unitcube(Tetrahedron3D), %d), H1P2{1,3}, LaplaceOperator(1.0))" % args.level,
         "config": {"workload": "Example301 Poisson 3D: H1P2 Laplace stiffness on uniform_refine(grid_unitcube(Tetrahedron3D),%d)" % args.level,
-                   "level": args.level, "ncells": int(g.ncells), "ndofs": int(s.ndofs), "nnz": int(nnz_total),
+                   "level": args.level, "ncells": glob["ncells"], "ndofs": glob["ndofs"], "nnz": int(nnz_total),
                    "cells_assembled_all_ranks": int(cells_total), "partition": "cell ranges, owner-computes columns" if world > 1 else "none",
                    "l2": "inputs+outputs (%.2f GB) >> 126 MB L2, no explicit flush" % ((b_alg + 16 * 10 * lg.ncells) / 1e9),
                    "path": {1: "generic", 2: "fast"}[int(st.path)], "tiles": int(st.ntiles)},

@@ -364,3 +364,69 @@ def test_gpu_against_committed_golden_fixtures(path):
     G.blf_set_path(AP, G._lib.PATH_GENERIC)
     cp, rv, nz = G.assemble_csc(AP, factor)
     assert np.array_equal(cp, d["colptr"]) and np.array_equal(rv, d["rowval"]) and np.array_equal(nz, d["nzval"])
+
+
+# ---- edge cases -------------------------------------------------------------------------------------
+def test_region_filter_selecting_nothing_gives_empty_pattern():
+    g = tri_grid(2)
+    s = G.FESpace(G.H1P1(1), g)
+    AP = G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [s, s], regions=[7])
+    cp, rv, nz = G.assemble_csc(AP, 1.0)
+    assert rv.size == 0 and nz.size == 0 and np.all(cp == 1)
+    ocp, orv, onz = oracle_blf(AP, 1.0)
+    assert np.array_equal(cp, ocp) and orv.size == 0
+    b = G.FEVector([s])
+    G.assemble_operator(b[1], G.LinearForm(G.Identity, G.DataFunction([1.0]), regions=[7]))
+    assert np.all(b.entries == 0)
+
+
+@pytest.mark.parametrize("geo", ["Triangle2D", "Tetrahedron3D"])
+def test_single_cell_grids_all_elements(geo):
+    g = G.reference_domain(geo)
+    dim = g.dim
+    fes = [G.H1P1(1), G.H1P2(1, dim), G.H1P2(dim, dim), G.H1BR(dim), G.HDIVRT0(dim), G.HDIVBDM1(dim), G.L2P0(1)]
+    for fe in fes:
+        s = G.FESpace(fe, g)
+        AP = G.DiscreteSymmetricBilinearForm([G.Identity, G.Identity], [s, s])
+        check_blf(AP, factor=1.0, exact=True)
+    s = G.FESpace(G.H1P2(1, dim), g)
+    check_blf(G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [s, s]), factor=3.0, exact=(dim == 2))
+
+
+def test_zero_factor_gives_empty_pattern_like_addnz():
+    # _addnz skips v == 0: with factor 0 nothing is ever inserted (fematrix.jl:54-58)
+    g = tri_grid(1)
+    s = G.FESpace(G.H1P1(1), g)
+    AP = G.DiscreteSymmetricBilinearForm([G.Identity, G.Identity], [s, s])
+    cp, rv, nz = G.assemble_csc(AP, 0.0)
+    assert rv.size == 0
+    ocp, orv, _ = oracle_blf(AP, 0.0)
+    assert orv.size == 0 and np.array_equal(cp, ocp)
+
+
+def test_c_abi_error_codes():
+    import ctypes as C
+    L = G._lib.lib()
+    g = tri_grid(1)
+    s = G.FESpace(G.H1P1(1), g)
+    AP = G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [s, s])
+    G.prepare_assembly(AP)
+    h = AP.AM.h
+    assert L.grmp_blf_numeric(h, 1.0, None) == -5                 # GRMP_ESTATE: numeric before symbolic
+    assert b"symbolic" in L.grmp_last_error()
+    assert L.grmp_blf_get_pattern(h, None, None) == -1            # GRMP_EINVAL
+    assert L.grmp_blf_set_path(h, 9) == -1
+    hg = C.c_void_p()
+    assert L.grmp_grid_create(G._lib.context(), 4, 0, None, 0, None, None, None, C.byref(hg)) == -1
+    assert L.grmp_init(99, C.byref(hg)) == -1                     # device index out of range
+    st = G._lib.Stats()
+    assert L.grmp_blf_stats(h, C.byref(st)) == 0
+
+
+def test_large_values_and_tiny_cells_scale_linearly():
+    g = tet_grid(1)
+    s = G.FESpace(G.H1P2(1, 3), g)
+    AP = G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [s, s])
+    cp, rv, nz1 = G.assemble_csc(AP, 1.0)
+    _, _, nz2 = G.assemble_csc(AP, 1e12, skip_preps=True)
+    assert rel_err(nz2, 1e12 * nz1) <= RTOL
