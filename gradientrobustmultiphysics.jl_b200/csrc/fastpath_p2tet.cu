@@ -211,7 +211,7 @@ struct EdgeParams {
 
 
 template <int TPB>
-__global__ void __launch_bounds__(TPB, (TPB <= 64 ? 10 : TPB <= 128 ? 5 : TPB <= 256 ? 2 : 1)) p2tet_edge_kernel(const EdgeParams p) {
+__global__ void __launch_bounds__(TPB, (TPB <= 64 ? 10 : TPB <= 128 ? 5 : TPB <= 192 ? 3 : TPB <= 256 ? 2 : 1)) p2tet_edge_kernel(const EdgeParams p) {
   extern __shared__ double sm[];
   __shared__ uint4 s_tab[256];   // perm code -> byte offsets (k * nct * 8, 16 bit each) of S_pp,S_qq,S_pq,S_pi,S_po,S_qi,S_qo
   const int tile = blockIdx.x, tid = threadIdx.x;
@@ -292,9 +292,16 @@ __global__ void __launch_bounds__(TPB, (TPB <= 64 ? 10 : TPB <= 128 ? 5 : TPB <=
       const double sqq = *reinterpret_cast<const double*>(sc + (t.x >> 16));
       const double spq = *reinterpret_cast<const double*>(sc + (t.y & 0xffffu));
       const double spi = *reinterpret_cast<const double*>(sc + (t.y >> 16));
-      const double spo = *reinterpret_cast<const double*>(sc + (t.z & 0xffffu));
       const double sqi = *reinterpret_cast<const double*>(sc + (t.z >> 16));
-      const double sqo = *reinterpret_cast<const double*>(sc + (t.w & 0xffffu));
+      // rows of S sum to zero (the barycentric gradients do): two of the seven values follow from the other five
+      double spo, sqo;
+      if (p.dbg & 8) {
+        spo = *reinterpret_cast<const double*>(sc + (t.z & 0xffffu));
+        sqo = *reinterpret_cast<const double*>(sc + (t.w & 0xffffu));
+      } else {
+        spo = -((spp + spq) + spi);
+        sqo = -((sqq + spq) + sqi);
+      }
       A += 0.6 * spq - 0.2 * spp;
       B += 0.6 * spq - 0.2 * sqq;
       C += 1.6 * (spp + sqq + spq);
@@ -460,7 +467,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   GRMP_CUDA(cudaStreamSynchronize(s));
   // tile shape (tunable for experiments: GRMP_FAST_TPB in {64,128,256}, GRMP_FAST_SMEM_KB)
   int TPB = getenv("GRMP_FAST_TPB") ? atoi(getenv("GRMP_FAST_TPB")) : TPB_DEFAULT;
-  if (TPB != 64 && TPB != 128 && TPB != 256 && TPB != 512) TPB = TPB_DEFAULT;
+  if (TPB != 64 && TPB != 128 && TPB != 192 && TPB != 256 && TPB != 512) TPB = TPB_DEFAULT;
   const i64 SMEM_BUDGET = getenv("GRMP_FAST_SMEM_KB") ? 1024 * (i64)atoi(getenv("GRMP_FAST_SMEM_KB")) : SMEM_BUDGET_DEFAULT * (i64)TPB / TPB_DEFAULT;
   out->tpb = TPB;
   // (2) host: ring order of every edge column, tiles over the edge columns, list of vertex columns
@@ -635,6 +642,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   const int smem_attr = (int)std::max<i64>(max_smem, 1024);
   GRMP_CUDA(cudaFuncSetAttribute(p2tet_edge_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
   GRMP_CUDA(cudaFuncSetAttribute(p2tet_edge_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
+  GRMP_CUDA(cudaFuncSetAttribute(p2tet_edge_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
   GRMP_CUDA(cudaFuncSetAttribute(p2tet_edge_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
   GRMP_CUDA(cudaFuncSetAttribute(p2tet_edge_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
   GRMP_CUDA(cudaStreamSynchronize(s));
@@ -647,6 +655,7 @@ int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pa
     EdgeParams ep{p.g, pat.colptr.p, f.col_pairbeg.p, f.pairs.p, f.cols.p, f.spokes.p, f.dscratch.p, f.tile_hdr.p, f.tile_nodes.p, p.factor, nzval, dbg};
     if (f.tpb == 64) p2tet_edge_kernel<64><<<f.ntiles, 64, f.smem_bytes, ctx->stream>>>(ep);
     else if (f.tpb == 256) p2tet_edge_kernel<256><<<f.ntiles, 256, f.smem_bytes, ctx->stream>>>(ep);
+    else if (f.tpb == 192) p2tet_edge_kernel<192><<<f.ntiles, 192, f.smem_bytes, ctx->stream>>>(ep);
     else if (f.tpb == 512) p2tet_edge_kernel<512><<<f.ntiles, 512, f.smem_bytes, ctx->stream>>>(ep);
     else p2tet_edge_kernel<128><<<f.ntiles, 128, f.smem_bytes, ctx->stream>>>(ep);
     GRMP_CUDA(cudaGetLastError());
