@@ -8,19 +8,16 @@ namespace grmp {
 
 struct FastP2Tet {
   int ntiles = 0;
-  int tpb = 128;
+  int tpb = 256;
   i64 npairs = 0;
   int smem_bytes = 0;
-  int max_tile_cells = 0;
-  DevBuf<int4> tile_hdr;       // 2 per tile: column range, tile-cell range, nzval range
-  DevBuf<int4> tile_nodes;     // CellNodes of the distinct cells of every tile
-  DevBuf<i64> col_pairbeg;     // [ncols+1] pairs of a column
-  DevBuf<uint4> pairs;         // ring-ordered pair records of the edge columns
-  DevBuf<uint4> cols;          // 2 per column: fixed-row offsets, closing offsets, mirrored slots
-  DevBuf<u32> vcols;           // vertex columns
-  DevBuf<uint4> vrec;          // per vertex column: diagonal slot, first spoke slot, #spokes
-  DevBuf<uint2> spokes;        // per edge column: scratch slots in the spoke lists of its two end vertices
-  DevBuf<double> dscratch;     // per (vertex, spoke): 0.2 * ring sum of S_vv
+  DevBuf<int4> tile_hdr;          // 3 per tile (TileHdr): column range, nzval range, blob / node-list / pair offsets
+  DevBuf<unsigned char> blob;     // per tile: column records, ring-ordered pair records, pair mirror slots (one TMA bulk load)
+  DevBuf<u32> tile_nodeids;       // distinct nodes of every tile (1-based)
+  DevBuf<u32> end_slots;          // per pair, only when a partition produced multi-chain halo columns
+  DevBuf<u32> vcols;              // vertex columns
+  DevBuf<uint4> vrec;             // per vertex column: diagonal slot, first spoke slot, #spokes
+  DevBuf<double> dscratch;        // per (vertex, spoke): 0.2 * ring sum of S_vv
   i64 nvcols = 0;
 };
 

@@ -12,16 +12,22 @@
 //     receive a contribution from every ring cell and are summed in registers; the rows of a
 //     ring vertex c (v_c, e_pc, e_qc) receive exactly two contributions from consecutive ring
 //     cells and are completed through a 3-register carry; e_cc' has a single contribution.
-//     Nothing is read-modify-written in memory.  The column is staged in shared memory and
-//     written back with coalesced stores.  S of a tile's distinct cells is computed once per
-//     tile into shared memory (the affine pullback of feevaluator_h1.jl:61-74 reduced to its
-//     10 invariants).
+//     Nothing is read-modify-written in memory.
+//     Geometry lives in registers: the ring cell (p, q, c_k, c_k+1) shares p, q with the whole
+//     ring and c_k with the previous cell, so ONE new vertex per cell is fetched (from the
+//     tile's node coordinates in shared memory) and one cross product a x (c - p) is carried
+//     (the affine pullback of feevaluator_h1.jl:61-74 reduced to the five off-diagonal
+//     invariants S_pq, S_pi, S_po, S_qi, S_qo; the diagonal ones follow from the zero row sums).
+//     A tile = TPB consecutive edge columns.  Its column and pair records form one contiguous
+//     blob that a single TMA bulk load (cp.async.bulk + mbarrier) brings into shared memory;
+//     the tile's contiguous nzval range is staged in shared memory and written with one TMA
+//     bulk store.
 //   VERTEX columns need no work of their own: the matrix of this form is symmetric, so every
 //     off-diagonal entry (i, v_a) is the mirror image of an entry (v_a, i) that an edge thread
 //     has in a register anyway (i an edge dof), or the ring sum -0.2*sum S_pq of the edge (a b)
 //     (i = v_b).  Edge threads store those values straight to their mirrored slots.
-//   diagonal kernel (p2tet_vertex_diag_kernel): rows of a stiffness matrix sum to zero, so
-//     A[v,v] = -sum_{i != v} A[i,v]; one warp per vertex column, fixed reduction tree.
+//   diagonal kernel (p2tet_vertex_diag_kernel): A[v,v] = 0.6 sum_K S_vv = 0.2 * sum over the
+//     spokes (v w) of the ring sums of S_vv, which the edge threads leave in a scratch list.
 //
 // No atomics, fixed summation orders -> deterministic.  Values agree with the reference's order of
 // operations to rounding (tests/test_gpu_parity.py states the tolerance); the PATTERN always
@@ -36,9 +42,10 @@ namespace grmp {
 
 namespace {
 
-constexpr int TPB_DEFAULT = 256;         // threads (= edge columns) per tile
-constexpr int SMEM_BUDGET_DEFAULT = 88 * 1024;   // nzval stage + S of the tile's distinct cells
+constexpr int TPB_DEFAULT = 256;                  // threads (= edge columns) per tile
+constexpr int SMEM_BUDGET_DEFAULT = 104 * 1024;   // records + node coordinates + nzval stage of a 256-column tile
 constexpr u32 NONE = 0xffffffffu;
+constexpr int MAX_TILE_NODES = 4095;              // 12-bit tile-local node ids
 
 // local edge e -> (p,q), Tetrahedron3D edges [1 2],[1 3],[1 4],[2 3],[2 4],[3 4] (h1_p2.jl:231-236)
 __host__ __device__ inline void edge_nodes(int e, int& p, int& q) {
@@ -49,83 +56,51 @@ __host__ __device__ inline int edge_of(int a, int b) {   // local edge dof index
   if (a > b) { int t = a; a = b; b = t; }
   return 4 + ((a == 0) ? (b - 1) : (a == 1 ? b + 1 : 5));
 }
-__host__ __device__ inline int sidx(int a, int b) {      // index of S_ab in the packed upper triangle
-  if (a > b) { int t = a; a = b; b = t; }
-  return a * 4 - a * (a - 1) / 2 + (b - a);
-}
-
-// S_ab = factor * |T| * grad(lambda_a).grad(lambda_b), packed (00,01,02,03,11,12,13,22,23,33)
-// one 256-bit gather per node from the padded coordinate copy (a node is 24 B inside one 32 B sector)
-__device__ __forceinline__ void load_node(const double* coords4, int node1, double& x, double& y, double& z) {
-  double w;
-  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(coords4 + 4 * (i64)(node1 - 1)));
-}
-__device__ __forceinline__ void cell_S(const GridView& g, const int4 nd, double factor, double* S, int dbg = 0) {
-  double p0x, p0y, p0z, p1x, p1y, p1z, p2x, p2y, p2z, p3x, p3y, p3z;
-  if (!(dbg & 4)) {   // default: three 64-bit gathers per node (measured 8 % faster than one 256-bit gather from a padded copy)
-    const double* x0 = g.coords + (i64)(nd.x - 1) * 3; const double* x1 = g.coords + (i64)(nd.y - 1) * 3;
-    const double* x2 = g.coords + (i64)(nd.z - 1) * 3; const double* x3 = g.coords + (i64)(nd.w - 1) * 3;
-    p0x = x0[0]; p0y = x0[1]; p0z = x0[2]; p1x = x1[0]; p1y = x1[1]; p1z = x1[2];
-    p2x = x2[0]; p2y = x2[1]; p2z = x2[2]; p3x = x3[0]; p3y = x3[1]; p3z = x3[2];
-  } else {
-  load_node(g.coords4, nd.x, p0x, p0y, p0z);
-  load_node(g.coords4, nd.y, p1x, p1y, p1z);
-  load_node(g.coords4, nd.z, p2x, p2y, p2z);
-  load_node(g.coords4, nd.w, p3x, p3y, p3z);
-  }
-  const double ax = p1x - p0x, ay = p1y - p0y, az = p1z - p0z;
-  const double bx = p2x - p0x, by = p2y - p0y, bz = p2z - p0z;
-  const double cx = p3x - p0x, cy = p3y - p0y, cz = p3z - p0z;
-  // n1 = b x c, n2 = c x a, n3 = a x b : grad(lambda_k) = n_k / det
-  const double n1x = by * cz - bz * cy, n1y = bz * cx - bx * cz, n1z = bx * cy - by * cx;
-  const double n2x = cy * az - cz * ay, n2y = cz * ax - cx * az, n2z = cx * ay - cy * ax;
-  const double n3x = ay * bz - az * by, n3y = az * bx - ax * bz, n3z = ax * by - ay * bx;
-  const double n0x = -(n1x + n2x + n3x), n0y = -(n1y + n2y + n3y), n0z = -(n1z + n2z + n3z);
-  // |T| / det^2 = 1 / (6 |det|): the cell volume is recomputed from the coordinates (|det|/6), which agrees with
-  // CellVolumes to rounding and saves a dependent load
-  const double det = ax * n1x + ay * n1y + az * n1z;
-  const double sc = factor / (6.0 * fabs(det));
-  S[0] = sc * (n0x * n0x + n0y * n0y + n0z * n0z);
-  S[1] = sc * (n0x * n1x + n0y * n1y + n0z * n1z);
-  S[2] = sc * (n0x * n2x + n0y * n2y + n0z * n2z);
-  S[3] = sc * (n0x * n3x + n0y * n3y + n0z * n3z);
-  S[4] = sc * (n1x * n1x + n1y * n1y + n1z * n1z);
-  S[5] = sc * (n1x * n2x + n1y * n2y + n1z * n2z);
-  S[6] = sc * (n1x * n3x + n1y * n3y + n1z * n3z);
-  S[7] = sc * (n2x * n2x + n2y * n2y + n2z * n2z);
-  S[8] = sc * (n2x * n3x + n2y * n3y + n2z * n3z);
-  S[9] = sc * (n3x * n3x + n3y * n3y + n3z * n3z);
-}
 
 // ---- records ---------------------------------------------------------------------------------
-// pair record (16 B), pairs of a column stored in ring order:
-//   x : tile-local cell | perm << 16 | flags << 24   (perm = p | q<<2 | in<<4 | out<<6 local vertex ids)
-//   y : slot offsets inside the column of rows v_in, e_P,in, e_Q,in, e_in,out (255 = not in the pattern)
-//   z : mirrored slot (global nzval index) of row e_PQ in column v_in, or NONE
-//   w : chain-end pairs of multi-chain (halo) columns: mirrored slot of row e_PQ in column v_out, else unused
-// column record (32 B):
-//   a.x : offsets of rows v_P, v_Q, e_PQ | flags << 24 (bit 0: closed ring)
-//   a.y : closing offsets (closed: rows of the first pair's in-vertex; open: rows of the last pair's out-vertex)
-//   a.z, a.w : mirrored slots of row e_PQ in columns v_P, v_Q
-//   b.x : mirrored slot of row e_PQ in the column of the closing vertex
-//   b.y, b.z : slots of (row v_Q, col v_P) and (row v_P, col v_Q);  b.w : first pair;  a.y >> 24 : number of pairs
-constexpr u32 PF_FIRST = 1u;   // first pair of the column (closed ring: its in-rows are completed at the end)
-constexpr u32 PF_RESET = 2u;   // first pair of a further chain (halo columns of a partition): drop the carry
-constexpr u32 PF_END = 4u;     // last pair of a chain that is not the last chain: mirror its out-vertex row now (slot in w)
+// tile header (48 B, global): see TileHdr.
+// tile blob (global, contiguous per tile, 16-byte aligned sections; one TMA bulk load):
+//   column records  48 B x ncol
+//     a.x : tile-local node of P | Q << 12 | #pairs << 24
+//     a.y : slot offsets inside the column of rows v_P, v_Q, e_PQ (255 = not in the pattern) | flags << 24 (bit 0: closed ring)
+//     a.z : closing offsets (closed: rows of the first pair's in-vertex; open: rows of the last pair's out-vertex)
+//     a.w : column start inside the tile's nzval range | first pair (tile-local) << 16
+//     b.x, b.y, b.z : mirrored slots (global nzval index or NONE) of row e_PQ in columns v_P, v_Q, v_closing
+//     b.w, c.x : slots of (row v_Q, col v_P) and (row v_P, col v_Q)
+//     c.y, c.z : scratch slots of this edge in the spoke lists of v_P, v_Q
+//   pair records 8 B x npairs, pairs of a column stored in ring order
+//     x : slot offsets inside the column of rows v_in, e_P,in, e_Q,in, e_in,out (255 = not in the pattern)
+//     y : tile-local node of the in-vertex | out-vertex << 12 | flags << 24
+//   pair mirrors 4 B x npairs : mirrored slot of row e_PQ in column v_in, or NONE
+constexpr u32 PF_RESET = 2u;   // first pair of a further chain (halo columns of a partition): drop the carry, reload the in-vertex
+constexpr u32 PF_END = 4u;     // last pair of a chain that is not the last chain: mirror its out-vertex row now (slot in end_slots)
+
+struct __align__(16) TileHdr {
+  int c0, ncol, nnodes, npairs;          // first column, #columns, #distinct nodes, #pairs
+  u32 g0lo, g0hi; int nnz; u32 blob16;   // first nzval slot, #slots, blob offset in 16-byte units
+  u32 pair_base, node_base, blob_bytes, pairs_off;   // global index of the first pair / node-list entry; blob size; byte offset of the pair records
+};
+static_assert(sizeof(TileHdr) == 48, "TileHdr layout");
+
+__host__ __device__ inline u32 pad16(u32 b) { return (b + 15u) & ~15u; }
 
 struct PackParams {
   const u32* pair_cell;     // global cell of the pair (ring order)
-  const u32* pair_local;    // tile-local cell
-  const u32* pair_code;     // perm | flags << 8
+  const u32* pair_io;       // tile-local in-node | out-node << 12
+  const u32* pair_code;     // perm (P | Q<<2 | I<<4 | O<<6) | flags << 8
   const i64* col_pairbeg;
   const i64* colptr;        // 1-based
   const i64* rowval;        // 1-based
   const i32* celldofs;
   const u32* col_of_pair;   // column of every pair
-  const unsigned char* col_closed;
+  const unsigned char* col_closed;   // 0 open chain(s), 1 closed ring, 2 not an edge column
+  const u32* col_tile;      // tile of every edge column
+  const u32* col_pq;        // tile-local node of P | Q << 12
+  const uint2* spokes;      // per column: scratch slots in the spoke lists of v_P, v_Q
+  const TileHdr* hdr;
   i64 npairs, ncols;
-  uint4* pairs;
-  uint4* cols;              // 2 per column
+  unsigned char* blob;
+  u32* end_slots;           // [npairs] or null
 };
 
 // slot of (row, col) in the pattern as an offset inside the column, or -1
@@ -149,209 +124,235 @@ __global__ void pack_pairs(PackParams p) {
   i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (k >= p.npairs) return;
   const i64 col = p.col_of_pair[k];
-  if (p.col_closed[col] == 2) { p.pairs[k] = make_uint4(0, 0, 0, 0); return; }   // vertex column: no pair work
+  if (p.col_closed[col] == 2) return;   // vertex column: no pair work
   const i64 cell = p.pair_cell[k];
   const u32 code = p.pair_code[k];
   const int P = code & 3, Q = (code >> 2) & 3, I = (code >> 4) & 3, O = (code >> 6) & 3;
+  const u32 fl = (code >> 8) & 255u;
   const i32* d = p.celldofs + cell * 10;
   const i64 vin = d[I] - 1;
-  uint4 rec;
-  rec.x = p.pair_local[k] | ((code & 255u) << 16) | (((code >> 8) & 255u) << 24);
-  rec.y = off8(find_slot(p, vin, col)) | (off8(find_slot(p, d[edge_of(P, I)] - 1, col)) << 8) |
+  const TileHdr h = p.hdr[p.col_tile[col]];
+  const u32 kl = (u32)(k - (i64)h.pair_base);
+  unsigned char* tb = p.blob + (size_t)h.blob16 * 16;
+  uint2 rec;
+  rec.x = off8(find_slot(p, vin, col)) | (off8(find_slot(p, d[edge_of(P, I)] - 1, col)) << 8) |
           (off8(find_slot(p, d[edge_of(Q, I)] - 1, col)) << 16) | (off8(find_slot(p, d[edge_of(I, O)] - 1, col)) << 24);
-  rec.z = gslot(p, col, vin);
-  rec.w = (((code >> 8) & PF_END) != 0) ? gslot(p, col, d[O] - 1) : NONE;
-  p.pairs[k] = rec;
+  rec.y = (p.pair_io[k] & 0xffffffu) | (fl << 24);
+  reinterpret_cast<uint2*>(tb + h.pairs_off)[kl] = rec;
+  reinterpret_cast<u32*>(tb + h.pairs_off + pad16(8u * (u32)h.npairs))[kl] = gslot(p, col, vin);
+  if (p.end_slots) p.end_slots[k] = (fl & PF_END) ? gslot(p, col, d[O] - 1) : NONE;
 }
 
 __global__ void pack_cols(PackParams p) {
   i64 j = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (j >= p.ncols) return;
+  if (p.col_closed[j] == 2) return;     // not an edge column
   const i64 kb = p.col_pairbeg[j], ke = p.col_pairbeg[j + 1];
-  uint4 a = make_uint4(0x00ffffffu, 0x00ffffffu, NONE, NONE), b = make_uint4(NONE, NONE, NONE, 0);
-  if (ke > kb && p.col_closed[j] != 2) {     // 2 = not an edge column
-    const bool closed = p.col_closed[j] == 1;
-    // reference orientation (P,Q) = first ring pair
-    const u32 c0 = p.pair_code[kb];
-    const i32* d0 = p.celldofs + (i64)p.pair_cell[kb] * 10;
-    const i64 vP = d0[c0 & 3] - 1, vQ = d0[(c0 >> 2) & 3] - 1;
-    a.x = off8(find_slot(p, vP, j)) | (off8(find_slot(p, vQ, j)) << 8) | (off8(find_slot(p, j, j)) << 16) | ((closed ? 1u : 0u) << 24);
-    // closing vertex: closed -> in-vertex of the first pair; open -> out-vertex of the last pair
-    const i64 kc = closed ? kb : ke - 1;
-    const u32 cc = p.pair_code[kc];
-    const i32* dc = p.celldofs + (i64)p.pair_cell[kc] * 10;
-    const int Pc = cc & 3, Qc = (cc >> 2) & 3, Vc = closed ? ((cc >> 4) & 3) : ((cc >> 6) & 3);
-    const i64 vC = dc[Vc] - 1;
-    a.y = off8(find_slot(p, vC, j)) | (off8(find_slot(p, dc[edge_of(Pc, Vc)] - 1, j)) << 8) | (off8(find_slot(p, dc[edge_of(Qc, Vc)] - 1, j)) << 16) | ((u32)(ke - kb) << 24);
-    a.z = gslot(p, j, vP);
-    a.w = gslot(p, j, vQ);
-    b.x = gslot(p, j, vC);
-    b.y = gslot(p, vQ, vP);
-    b.z = gslot(p, vP, vQ);
-    b.w = (u32)kb;
-  }
-  p.cols[2 * j] = a;
-  p.cols[2 * j + 1] = b;
+  const TileHdr h = p.hdr[p.col_tile[j]];
+  const i64 g0 = (i64)h.g0lo | ((i64)h.g0hi << 32);
+  const bool closed = p.col_closed[j] == 1;
+  // reference orientation (P,Q) = first ring pair
+  const u32 c0 = p.pair_code[kb];
+  const i32* d0 = p.celldofs + (i64)p.pair_cell[kb] * 10;
+  const i64 vP = d0[c0 & 3] - 1, vQ = d0[(c0 >> 2) & 3] - 1;
+  // closing vertex: closed -> in-vertex of the first pair; open -> out-vertex of the last pair
+  const i64 kc = closed ? kb : ke - 1;
+  const u32 cc = p.pair_code[kc];
+  const i32* dc = p.celldofs + (i64)p.pair_cell[kc] * 10;
+  const int Pc = cc & 3, Qc = (cc >> 2) & 3, Vc = closed ? ((cc >> 4) & 3) : ((cc >> 6) & 3);
+  const i64 vC = dc[Vc] - 1;
+  uint4 a, b, c;
+  a.x = (p.col_pq[j] & 0xffffffu) | ((u32)(ke - kb) << 24);
+  a.y = off8(find_slot(p, vP, j)) | (off8(find_slot(p, vQ, j)) << 8) | (off8(find_slot(p, j, j)) << 16) | ((closed ? 1u : 0u) << 24);
+  a.z = off8(find_slot(p, vC, j)) | (off8(find_slot(p, dc[edge_of(Pc, Vc)] - 1, j)) << 8) | (off8(find_slot(p, dc[edge_of(Qc, Vc)] - 1, j)) << 16);
+  a.w = (u32)(p.colptr[j] - 1 - g0) | ((u32)(kb - (i64)h.pair_base) << 16);
+  b.x = gslot(p, j, vP);
+  b.y = gslot(p, j, vQ);
+  b.z = gslot(p, j, vC);
+  b.w = gslot(p, vQ, vP);
+  c.x = gslot(p, vP, vQ);
+  c.y = p.spokes[j].x; c.z = p.spokes[j].y; c.w = 0;
+  uint4* dst = reinterpret_cast<uint4*>(p.blob + (size_t)h.blob16 * 16) + 3 * (j - h.c0);
+  dst[0] = a; dst[1] = b; dst[2] = c;
 }
 
 struct EdgeParams {
-  GridView g;
-  const i64* colptr;        // 1-based [ncols+1]
-  const i64* col_pairbeg;   // [ncols+1]
-  const uint4* pairs;
-  const uint4* cols;
-  const uint2* spokes;      // per column: scratch slots of the two end vertices' spoke lists
+  const double* coords;     // [nnodes][3]
+  const TileHdr* hdr;
+  const unsigned char* blob;
+  const u32* tile_nodeids;  // 1-based node ids of the tiles' distinct nodes
+  const u32* end_slots;     // [npairs] or null (only partitions have multi-chain columns)
   double* dscratch;         // [sum of spoke counts] 0.2 * ring sum of S_vv per (vertex, spoke)
-  const int4* tile_hdr;     // 2 per tile: {first column, #columns, first tile cell, #tile cells}, {g0 lo, g0 hi, nnz, 0}
-  const int4* tile_nodes;   // CellNodes of the tiles' distinct cells
   double factor;
   double* nzval;
   int dbg;                  // GRMP_DEBUG_FLAGS: bit 0 = skip the mirrored stores (timing experiments only)
 };
 
+__device__ __forceinline__ double fast_rcp(double d) {   // 1/d to ~1 ulp for normal d: MUFU.RCP64H + two Newton steps
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double t = fma(-d, r, 1.0);
+  r = fma(r, t, r);
+  t = fma(-d, r, 1.0);
+  r = fma(r, t, r);
+  return r;
+}
 
 template <int TPB>
 __global__ void __launch_bounds__(TPB, (TPB <= 64 ? 10 : TPB <= 128 ? 5 : TPB <= 192 ? 3 : TPB <= 256 ? 2 : 1)) p2tet_edge_kernel(const EdgeParams p) {
-  extern __shared__ double sm[];
-  __shared__ uint4 s_tab[256];   // perm code -> byte offsets (k * nct * 8, 16 bit each) of S_pp,S_qq,S_pq,S_pi,S_po,S_qi,S_qo
+  extern __shared__ __align__(128) unsigned char smraw[];
+  __shared__ __align__(8) unsigned long long mbar;
   const int tile = blockIdx.x, tid = threadIdx.x;
-  const int4 h0 = p.tile_hdr[2 * tile], h1 = p.tile_hdr[2 * tile + 1];
-  const int c0 = h0.x, ncol = h0.y, cb = h0.z, nct = h0.w;
+  const int4* hp = reinterpret_cast<const int4*>(p.hdr + tile);
+  const int4 h0 = __ldg(hp), h1 = __ldg(hp + 1), h2 = __ldg(hp + 2);
+  const int ncol = h0.y, nn = h0.z;
   const i64 g0 = (i64)(u32)h1.x | ((i64)h1.y << 32);
   const int nnz_t = h1.z;
-  // stage[i] mirrors nzval[g0 + i]; it is shifted by one element when g0 is odd so that shared and global addresses
-  // of the same element are 16-byte aligned together (TMA bulk store).  Every slot is written exactly once -> no zero-init.
+  const u32 blob_bytes = (u32)h2.z, pairs_off = (u32)h2.w, mir_off = pairs_off + pad16(8u * (u32)h0.w);
+  // shared memory: [blob | node coordinates | nzval stage].  stage[i] mirrors nzval[g0 + i]; it is shifted by one element
+  // when g0 is odd so that shared and global addresses of the same element are 16-byte aligned together (TMA bulk store).
+  // Every slot is written exactly once -> no zero-init.
+  double* __restrict__ X = reinterpret_cast<double*>(smraw + blob_bytes);
   const int odd = (int)(g0 & 1);
-  double* __restrict__ stage = sm + odd;
-  double* __restrict__ S = sm + nnz_t + 2;
-  // node ids of this thread's tile cells (up to GC per thread), issued first: the coordinate gathers depend on them
-  constexpr int GC = 4;
-  int4 nd[GC];
-#pragma unroll
-  for (int r = 0; r < GC; r++) {
-    const int i = tid + r * TPB;
-    nd[r] = (i < nct) ? p.tile_nodes[cb + i] : make_int4(1, 1, 1, 1);
+  double* __restrict__ stage = reinterpret_cast<double*>(smraw + blob_bytes + pad16(24u * (u32)nn)) + odd;
+  const unsigned mbar_a = (unsigned)__cvta_generic_to_shared(&mbar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(blob_bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smraw)),
+                 "l"(p.blob + (size_t)(u32)h1.w * 16), "r"(blob_bytes), "r"(mbar_a)
+                 : "memory");
   }
-  // this thread's column record, pair range and first batch of pair records
-  const int col = c0 + tid;
-  const bool has_col = tid < ncol;
-  u32 kb = 0, ke = 0;
-  int abase = 0;
-  uint4 ca = make_uint4(0, 0, 0, 0), cbx = make_uint4(0, 0, 0, 0);
-  uint2 spk = make_uint2(NONE, NONE);
-  if (has_col) {
-    ca = p.cols[2 * (i64)col]; cbx = p.cols[2 * (i64)col + 1];
-    spk = p.spokes[col];
-    abase = (int)(p.colptr[col] - 1 - g0);
-    kb = cbx.w; ke = kb + (ca.y >> 24);
+  // node coordinates of the tile -> shared memory (overlaps the bulk load of the records)
+  for (int i = tid; i < nn; i += TPB) {
+    const u32 id = __ldg(p.tile_nodeids + (size_t)(u32)h2.y + i);
+    const double* xg = p.coords + (size_t)(id - 1) * 3;
+    const double x = __ldg(xg), y = __ldg(xg + 1), z = __ldg(xg + 2);
+    X[3 * i] = x; X[3 * i + 1] = y; X[3 * i + 2] = z;
   }
-  for (int c = tid; c < 256; c += TPB) {
-    const u32 P = c & 3, Q = (c >> 2) & 3, I = (c >> 4) & 3, O = (c >> 6) & 3;
-    const u32 m = (u32)nct * 8u;
-    uint4 t;
-    t.x = (sidx(P, P) * m) | ((sidx(Q, Q) * m) << 16);
-    t.y = (sidx(P, Q) * m) | ((sidx(P, I) * m) << 16);
-    t.z = (sidx(P, O) * m) | ((sidx(Q, I) * m) << 16);
-    t.w = (sidx(Q, O) * m);
-    s_tab[c] = t;
-  }
-  uint4 rnext = (kb < ke) ? p.pairs[kb] : make_uint4(0, 0, 0, 0);   // a column's records share one or two cache lines
-  // ---- geometry of the tile's distinct cells ----
-#pragma unroll
-  for (int r = 0; r < GC; r++) {
-    const int i = tid + r * TPB;
-    if (i < nct) {
-      double sA[10];
-      cell_S(p.g, nd[r], p.factor, sA, p.dbg);
-#pragma unroll
-      for (int k = 0; k < 10; k++) S[k * nct + i] = sA[k];        // k-major: conflict-free stores
-    }
-  }
-  for (int i = tid + GC * TPB; i < nct; i += TPB) {               // tiles with more than GC*TPB cells (rare)
-    double sA[10];
-    cell_S(p.g, p.tile_nodes[cb + i], p.factor, sA, p.dbg);
-#pragma unroll
-    for (int k = 0; k < 10; k++) S[k * nct + i] = sA[k];
-  }
-  __syncthreads();
-  if (has_col && ke > kb) {
-    double* __restrict__ a = stage + abase;
-    double A = 0.0, B = 0.0, C = 0.0, W = 0.0;       // rows v_P, v_Q, e_PQ of the column; (v_P, v_Q) coupling
-    double c0r = 0.0, c1r = 0.0, c2r = 0.0;          // carry: partial rows of the shared ring vertex
-    double f0 = 0.0, f1 = 0.0, f2 = 0.0;             // closed ring: in-rows of the first pair, completed at the end
-    const bool closed = (ca.x >> 24) & 1u;
-    const char* __restrict__ Sb = reinterpret_cast<const char*>(S);
-    double Tp = 0.0, Tq = 0.0;                       // ring sums of S_PP, S_QQ: 0.2*sum over the spokes = diagonal of v_P, v_Q
-#pragma unroll 2
-    for (u32 k = kb; k < ke; k++) {
-      const uint4 r = rnext;
-      if (k + 1 < ke) rnext = p.pairs[k + 1];
-      const uint4 t = s_tab[(r.x >> 16) & 255u];
-      const char* sc = Sb + (r.x & 0xffffu) * 8u;
-      const double spp = *reinterpret_cast<const double*>(sc + (t.x & 0xffffu));
-      const double sqq = *reinterpret_cast<const double*>(sc + (t.x >> 16));
-      const double spq = *reinterpret_cast<const double*>(sc + (t.y & 0xffffu));
-      const double spi = *reinterpret_cast<const double*>(sc + (t.y >> 16));
-      const double sqi = *reinterpret_cast<const double*>(sc + (t.z >> 16));
-      // rows of S sum to zero (the barycentric gradients do): two of the seven values follow from the other five
-      double spo, sqo;
-      if (p.dbg & 8) {
-        spo = *reinterpret_cast<const double*>(sc + (t.z & 0xffffu));
-        sqo = *reinterpret_cast<const double*>(sc + (t.w & 0xffffu));
-      } else {
-        spo = -((spp + spq) + spi);
-        sqo = -((sqq + spq) + sqi);
+  __syncthreads();          // coordinates visible; also orders the mbarrier init before the waits of the other threads
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(mbar_a)
+      : "memory");
+  if (tid < ncol && !(p.dbg & 4)) {
+    const uint4* cr = reinterpret_cast<const uint4*>(smraw) + 3 * tid;
+    const uint4 ca = cr[0], cb = cr[1], cc = cr[2];
+    const u32 np = ca.x >> 24;
+    if (np > 0) {
+      const uint2* __restrict__ prec = reinterpret_cast<const uint2*>(smraw + pairs_off) + (ca.w >> 16);
+      const u32* __restrict__ pmir = reinterpret_cast<const u32*>(smraw + mir_off) + (ca.w >> 16);
+      double* __restrict__ a = stage + (ca.w & 0xffffu);
+      const bool closed = (ca.y >> 24) & 1u;
+      const u32 lp = ca.x & 0xfffu, lq = (ca.x >> 12) & 0xfffu;
+      const double px = X[3 * lp], py = X[3 * lp + 1], pz = X[3 * lp + 2];
+      const double ax = X[3 * lq] - px, ay = X[3 * lq + 1] - py, az = X[3 * lq + 2] - pz;
+      const double c8 = p.factor * (0.8 / 6.0);      // S' = 0.8 * S = c8 / |det| * n_a.n_b
+      uint2 r0 = prec[0];
+      uint2 r1 = prec[np > 1 ? 1 : 0];
+      double bx, by, bz, mcx, mcy, mcz;               // b = c_in - p, mc = a x b (carried around the ring)
+      {
+        const u32 li = r0.y & 0xfffu;
+        bx = X[3 * li] - px; by = X[3 * li + 1] - py; bz = X[3 * li + 2] - pz;
+        mcx = ay * bz - az * by; mcy = az * bx - ax * bz; mcz = ax * by - ay * bx;
       }
-      A += 0.6 * spq - 0.2 * spp;
-      B += 0.6 * spq - 0.2 * sqq;
-      C += 1.6 * (spp + sqq + spq);
-      W += -0.2 * spq;
-      Tp += spp; Tq += sqq;
-      const double base = spq + spp, baseq = spq + sqq;
-      const u32 fl = r.x >> 24;
-      if (fl & PF_RESET) { c0r = 0.0; c1r = 0.0; c2r = 0.0; }
-      const double in0 = c0r + -0.2 * (spi + sqi);                 // v_in
-      const double in1 = c1r + 0.8 * (2.0 * sqi + spi + base);      // e_P,in
-      const double in2 = c2r + 0.8 * (2.0 * spi + sqi + baseq);     // e_Q,in
-      c0r = -0.2 * (spo + sqo);                                     // v_out
-      c1r = 0.8 * (2.0 * sqo + spo + base);                         // e_P,out
-      c2r = 0.8 * (2.0 * spo + sqo + baseq);                        // e_Q,out
-      const double x = 0.8 * (spi + spo + sqi + sqo);               // e_in,out
-      const u32 o3 = r.y >> 24;
-      if (o3 != 255u) a[o3] = x;
-      if ((fl & PF_END) && r.w != NONE && !(p.dbg & 1)) p.nzval[r.w] = c0r;         // chain end inside a halo column: mirror (e_PQ, v_out)
-      if (closed && (fl & PF_FIRST)) {
-        f0 = in0; f1 = in1; f2 = in2;                               // partner is the last pair of the ring
-      } else {
-        const u32 o0 = r.y & 255u, o1 = (r.y >> 8) & 255u, o2 = (r.y >> 16) & 255u;
-        if (o0 != 255u) a[o0] = in0;
-        if (o1 != 255u) a[o1] = in1;
-        if (o2 != 255u) a[o2] = in2;
-        if (r.z != NONE && !(p.dbg & 1)) p.nzval[r.z] = in0;                        // mirror (e_PQ, v_in)
+      double ox, oy, oz;                              // coordinates of the out-vertex of the current pair
+      {
+        const u32 lo = (r0.y >> 12) & 0xfffu;
+        ox = X[3 * lo]; oy = X[3 * lo + 1]; oz = X[3 * lo + 2];
       }
-    }
-    // closing rows: closed ring -> first pair's in-rows + last carry; open chain -> last pair's out-rows
-    {
-      const double q0 = closed ? f0 + c0r : c0r, q1 = closed ? f1 + c1r : c1r, q2 = closed ? f2 + c2r : c2r;
-      const u32 o0 = ca.y & 255u, o1 = (ca.y >> 8) & 255u, o2 = (ca.y >> 16) & 255u;
-      if (o0 != 255u) a[o0] = q0;
-      if (o1 != 255u) a[o1] = q1;
-      if (o2 != 255u) a[o2] = q2;
-      if (cbx.x != NONE && !(p.dbg & 1)) p.nzval[cbx.x] = q0;
-    }
-    {
-      const u32 oA = ca.x & 255u, oB = (ca.x >> 8) & 255u, oC = (ca.x >> 16) & 255u;
-      if (oA != 255u) a[oA] = A;
-      if (oB != 255u) a[oB] = B;
-      if (oC != 255u) a[oC] = C;
-      if (!(p.dbg & 1)) {
-      if (ca.z != NONE) p.nzval[ca.z] = A;       // (e_PQ, v_P)
-      if (ca.w != NONE) p.nzval[ca.w] = B;       // (e_PQ, v_Q)
-      if (cbx.y != NONE) p.nzval[cbx.y] = W;     // (v_Q, v_P)
-      if (cbx.z != NONE) p.nzval[cbx.z] = W;     // (v_P, v_Q)
+      double R1 = 0.0, R2 = 0.0, R3 = 0.0;            // ring sums of S'_pq, S'_pi + S'_po, S'_qi + S'_qo
+      double c0r = 0.0, c1r = 0.0, c2r = 0.0;          // carry: partial rows of the shared ring vertex
+      double f0 = 0.0, f1 = 0.0, f2 = 0.0;             // closed ring: in-rows of the first pair, completed at the end
+      for (u32 k = 0; k < np; k++) {
+        // software pipeline: out-vertex of the next pair, record after next
+        const u32 ln = (r1.y >> 12) & 0xfffu;
+        const double nx = X[3 * ln], ny = X[3 * ln + 1], nz = X[3 * ln + 2];
+        const uint2 r2 = prec[k + 2 < np ? k + 2 : np - 1];
+        const u32 pm = pmir[k];
+        const u32 fl = r0.y >> 24;
+        if (fl & PF_RESET) {
+          const u32 li = r0.y & 0xfffu;
+          bx = X[3 * li] - px; by = X[3 * li + 1] - py; bz = X[3 * li + 2] - pz;
+          mcx = ay * bz - az * by; mcy = az * bx - ax * bz; mcz = ax * by - ay * bx;
+          c0r = 0.0; c1r = 0.0; c2r = 0.0;
+        }
+        // cell (p, q, in, out): a = q-p, b = in-p, e = out-p;  n_q = b x e, n_in = -(a x e), n_out = a x b, n_p = -(n_q+n_in+n_out)
+        const double ex = ox - px, ey = oy - py, ez = oz - pz;
+        const double mdx = ay * ez - az * ey, mdy = az * ex - ax * ez, mdz = ax * ey - ay * ex;
+        const double gx = by * ez - bz * ey, gy = bz * ex - bx * ez, gz = bx * ey - by * ex;
+        const double det = ax * gx + ay * gy + az * gz;
+        const double s = c8 * fast_rcp(fabs(det));
+        const double npx = mdx - gx - mcx, npy = mdy - gy - mcy, npz = mdz - gz - mcz;
+        const double spq = s * (npx * gx + npy * gy + npz * gz);
+        const double spi = -s * (npx * mdx + npy * mdy + npz * mdz);
+        const double spo = s * (npx * mcx + npy * mcy + npz * mcz);
+        const double sqi = -s * (gx * mdx + gy * mdy + gz * mdz);
+        const double sqo = s * (gx * mcx + gy * mcy + gz * mcz);
+        // with S' = 0.8 S and the zero row sums of S (S_pp = -(S_pq+S_pi+S_po), S_qq likewise):
+        //   v_in: -0.2(S_pi+S_qi)   e_P,in: 0.8(2 S_qi - S_po)   e_Q,in: 0.8(2 S_pi - S_qo)   e_in,out: 0.8(S_pi+S_po+S_qi+S_qo)
+        const double tp = spi + spo, tq = sqi + sqo;
+        R1 += spq; R2 += tp; R3 += tq;
+        const double in0 = c0r - 0.25 * (spi + sqi);
+        const double in1 = c1r + (2.0 * sqi - spo);
+        const double in2 = c2r + (2.0 * spi - sqo);
+        c0r = -0.25 * (spo + sqo);
+        c1r = 2.0 * sqo - spi;
+        c2r = 2.0 * spo - sqi;
+        const u32 o3 = r0.x >> 24;
+        if (o3 != 255u) a[o3] = tp + tq;
+        if ((fl & PF_END) && p.end_slots != nullptr && !(p.dbg & 1)) {     // chain end inside a halo column: mirror (e_PQ, v_out)
+          const u32 es = p.end_slots[(size_t)(u32)h2.x + (ca.w >> 16) + k];
+          if (es != NONE) p.nzval[es] = c0r;
+        }
+        if (closed && k == 0) {
+          f0 = in0; f1 = in1; f2 = in2;                                  // partner is the last pair of the ring
+        } else {
+          const u32 o0 = r0.x & 255u, o1 = (r0.x >> 8) & 255u, o2 = (r0.x >> 16) & 255u;
+          if (o0 != 255u) a[o0] = in0;
+          if (o1 != 255u) a[o1] = in1;
+          if (o2 != 255u) a[o2] = in2;
+          if (pm != NONE && !(p.dbg & 1)) p.nzval[pm] = in0;             // mirror (e_PQ, v_in)
+        }
+        bx = ex; by = ey; bz = ez; mcx = mdx; mcy = mdy; mcz = mdz;
+        ox = nx; oy = ny; oz = nz;
+        r0 = r1; r1 = r2;
       }
-      if (spk.x != NONE) p.dscratch[spk.x] = 0.2 * Tp;
-      if (spk.y != NONE) p.dscratch[spk.y] = 0.2 * Tq;
+      // closing rows: closed ring -> first pair's in-rows + last carry; open chain -> last pair's out-rows
+      {
+        const double q0 = closed ? f0 + c0r : c0r, q1 = closed ? f1 + c1r : c1r, q2 = closed ? f2 + c2r : c2r;
+        const u32 o0 = ca.z & 255u, o1 = (ca.z >> 8) & 255u, o2 = (ca.z >> 16) & 255u;
+        if (o0 != 255u) a[o0] = q0;
+        if (o1 != 255u) a[o1] = q1;
+        if (o2 != 255u) a[o2] = q2;
+        if (cb.z != NONE && !(p.dbg & 1)) p.nzval[cb.z] = q0;
+      }
+      {
+        // rows v_P, v_Q, e_PQ and the (v_P, v_Q) coupling from the ring sums (S'_pp = -(S'_pq + S'_pi + S'_po)):
+        //   A = sum 0.6 S_pq - 0.2 S_pp = R1 + R2/4,  C = 1.6 sum (S_pp+S_qq+S_pq) = -2 (R1+R2+R3),  W = -0.2 sum S_pq = -R1/4
+        const double A = R1 + 0.25 * R2, B = R1 + 0.25 * R3, C = -2.0 * (R1 + R2 + R3), W = -0.25 * R1;
+        const u32 oA = ca.y & 255u, oB = (ca.y >> 8) & 255u, oC = (ca.y >> 16) & 255u;
+        if (oA != 255u) a[oA] = A;
+        if (oB != 255u) a[oB] = B;
+        if (oC != 255u) a[oC] = C;
+        if (!(p.dbg & 1)) {
+          if (cb.x != NONE) p.nzval[cb.x] = A;       // (e_PQ, v_P)
+          if (cb.y != NONE) p.nzval[cb.y] = B;       // (e_PQ, v_Q)
+          if (cb.w != NONE) p.nzval[cb.w] = W;       // (v_Q, v_P)
+          if (cc.x != NONE) p.nzval[cc.x] = W;       // (v_P, v_Q)
+        }
+        if (cc.y != NONE) p.dscratch[cc.y] = -0.25 * (R1 + R2);   // 0.2 * ring sum of S_pp
+        if (cc.z != NONE) p.dscratch[cc.z] = -0.25 * (R1 + R3);   // 0.2 * ring sum of S_qq
+      }
     }
   }
   __syncthreads();
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(TPB, (TPB <= 64 ? 10 : TPB <= 128 ? 5 : TPB <=
     double* __restrict__ dst = p.nzval + g0;
     const int i0 = odd;                                   // first element whose address is 16-byte aligned
     const int nb = (nnz_t > i0) ? ((nnz_t - i0) & ~1) : 0;  // elements in the bulk body
-    if (tid == 0 && nb > 0) {
+    if (tid == 0 && nb > 0 && !(p.dbg & 8)) {
       const unsigned src = (unsigned)__cvta_generic_to_shared(stage + i0);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + i0), "r"(src), "r"(nb * 8) : "memory");
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(TPB, (TPB <= 64 ? 10 : TPB <= 128 ? 5 : TPB <=
     }
     if (tid == 1 && i0 == 1 && nnz_t > 0) dst[0] = stage[0];
     if (tid == 2 && i0 + nb < nnz_t) dst[i0 + nb] = stage[i0 + nb];
-    if (tid == 0 && nb > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must stay alive until read
+    if (tid == 0 && nb > 0 && !(p.dbg & 8)) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must stay alive until read
   }
 }
 
@@ -422,6 +423,11 @@ void reference_local_closed_form(double K[10][10]) {
   }
 }
 
+template <int TPB> int set_smem_attr(int bytes) {
+  GRMP_CUDA(cudaFuncSetAttribute(p2tet_edge_kernel<TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return GRMP_OK;
+}
+
 }  // namespace
 
 bool fast_p2tet_applicable(const BlfLocalParams& p) {
@@ -435,7 +441,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   // halo columns (>= ncols_owned) are processed too: their mirrors complete the owned vertex columns;
   // only they may consist of several chains (cells around a halo edge are present only where they touch an owned dof)
   cudaStream_t s = ctx->stream;
-  const i64 ncells = p.g.ncells, ncols = pat.ncols;
+  const i64 ncells = p.g.ncells, ncols = pat.ncols, nnodes = p.g.nnodes;
   const i64 ncols_owned_eff = (ncols_owned >= 0 && ncols_owned < ncols) ? ncols_owned : ncols;
   out->ntiles = 0; out->nvcols = 0;
   if (pat.nnz >= (i64)NONE) return fail(GRMP_EUNSUPPORTED, "fast path: more than 2^32-1 non-zeros on one device");
@@ -455,6 +461,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   DofGather dg;
   GRMP_TRY(build_dofgather(s, p.e1.celldofs, ncells, 10, ncols, &dg));
   const i64 npairs = dg.ncontrib;
+  if (npairs >= (i64)NONE) return fail(GRMP_EUNSUPPORTED, "fast path: more than 2^32-1 pairs");
   std::vector<u32> h_cell(npairs), h_src(npairs);
   std::vector<i64> h_pairbeg(ncols + 1), h_colptr(ncols + 1);
   std::vector<i32> h_cn((size_t)ncells * 4), h_dofs((size_t)ncells * 10);
@@ -465,35 +472,45 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   GRMP_CUDA(cudaMemcpyAsync(h_cn.data(), p.g.cellnodes, (size_t)ncells * 16, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaMemcpyAsync(h_dofs.data(), p.e1.celldofs, (size_t)ncells * 40, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaStreamSynchronize(s));
-  // tile shape (tunable for experiments: GRMP_FAST_TPB in {64,128,256}, GRMP_FAST_SMEM_KB)
+  // tile shape (tunable for experiments: GRMP_FAST_TPB in {64,128,192,256,512}, GRMP_FAST_SMEM_KB)
   int TPB = getenv("GRMP_FAST_TPB") ? atoi(getenv("GRMP_FAST_TPB")) : TPB_DEFAULT;
   if (TPB != 64 && TPB != 128 && TPB != 192 && TPB != 256 && TPB != 512) TPB = TPB_DEFAULT;
   const i64 SMEM_BUDGET = getenv("GRMP_FAST_SMEM_KB") ? 1024 * (i64)atoi(getenv("GRMP_FAST_SMEM_KB")) : SMEM_BUDGET_DEFAULT * (i64)TPB / TPB_DEFAULT;
   out->tpb = TPB;
   // (2) host: ring order of every edge column, tiles over the edge columns, list of vertex columns
-  std::vector<u32> pair_cell(npairs), pair_local(npairs), pair_code(npairs), col_of_pair(npairs), vcols;
+  std::vector<u32> pair_cell(npairs), pair_io(npairs), pair_code(npairs), col_of_pair(npairs), vcols;
   std::vector<unsigned char> col_closed(ncols, 2);
+  std::vector<u32> col_tile(ncols, NONE), col_pq(ncols, 0);
   std::vector<u32> endP(ncols, NONE), endQ(ncols, NONE);     // vertex dofs of the two ends of every edge column
-  std::vector<int4> tile_hdr, tile_nodes;
-  std::vector<i32> tile_cells;   // distinct cells of the open tile (global ids), flushed into tile_nodes
-  std::vector<i32> mark(ncells, -1), local_of(ncells, 0);
-  tile_nodes.reserve((size_t)ncells * 3);
-  int cur_tile = 0, cur_cols = 0, cur_cells = 0;
-  i64 cur_nnz = 0, tile_first_col = 0;
-  i64 max_smem = 0;
+  std::vector<TileHdr> hdr;
+  std::vector<u32> tile_nodeids;
+  std::vector<i32> nmark(nnodes + 1, -1), nlocal(nnodes + 1, 0);
+  int cur_tile = 0, cur_cols = 0, cur_nodes = 0;
+  i64 cur_nnz = 0, cur_pairs = 0, tile_first_col = 0, tile_node_base = 0, tile_pair_base = 0;
+  i64 max_smem = 0, blob_total16 = 0;
+  bool any_end = false;
+  auto tile_smem = [](i64 cols, i64 pairs, i64 nodes, i64 nnz) {
+    return 48 * cols + (i64)pad16((u32)(8 * pairs)) + (i64)pad16((u32)(4 * pairs)) + (i64)pad16((u32)(24 * nodes)) + 8 * (nnz + 2);
+  };
   auto close_tile = [&](i64 end_col) {
     if (cur_cols == 0) return;
     const i64 g0 = h_colptr[tile_first_col] - 1;
-    tile_hdr.push_back(make_int4((int)tile_first_col, (int)(end_col - tile_first_col), (int)tile_nodes.size(), cur_cells));
-    tile_hdr.push_back(make_int4((int)(u32)(g0 & 0xffffffffll), (int)(g0 >> 32), (int)cur_nnz, 0));
-    for (i32 c : tile_cells) tile_nodes.push_back(make_int4(h_cn[(size_t)c * 4], h_cn[(size_t)c * 4 + 1], h_cn[(size_t)c * 4 + 2], h_cn[(size_t)c * 4 + 3]));
-    tile_cells.clear();
-    max_smem = std::max<i64>(max_smem, 8 * cur_nnz + 80 * (i64)cur_cells + 32);
-    cur_tile++; cur_cols = 0; cur_cells = 0; cur_nnz = 0;
+    TileHdr h;
+    h.c0 = (int)tile_first_col; h.ncol = (int)(end_col - tile_first_col); h.nnodes = cur_nodes; h.npairs = (int)cur_pairs;
+    h.g0lo = (u32)(g0 & 0xffffffffll); h.g0hi = (u32)(g0 >> 32); h.nnz = (int)cur_nnz; h.blob16 = (u32)blob_total16;
+    h.pair_base = (u32)tile_pair_base; h.node_base = (u32)tile_node_base;
+    h.pairs_off = 48u * (u32)h.ncol;
+    h.blob_bytes = h.pairs_off + pad16(8u * (u32)cur_pairs) + pad16(4u * (u32)cur_pairs);
+    hdr.push_back(h);
+    blob_total16 += h.blob_bytes / 16;
+    max_smem = std::max<i64>(max_smem, tile_smem(h.ncol, cur_pairs, cur_nodes, cur_nnz));
+    tile_node_base = (i64)tile_nodeids.size();
+    cur_tile++; cur_cols = 0; cur_nodes = 0; cur_nnz = 0; cur_pairs = 0;
   };
   struct RP { u32 cell; int P, Q, R, S; i32 nR, nS; };
   std::vector<RP> rp;
   std::vector<char> used;
+  std::vector<i32> colnodes;
   for (i64 j = 0; j < ncols; j++) {
     const i64 kb = h_pairbeg[j], ke = h_pairbeg[j + 1];
     const i64 len = h_colptr[j + 1] - h_colptr[j];
@@ -502,14 +519,14 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     if (lj0 < 4) {   // vertex column: filled by mirrors + the diagonal kernel
       close_tile(j);
       vcols.push_back((u32)j);
-      for (i64 k = kb; k < ke; k++) { pair_cell[k] = h_cell[k]; pair_local[k] = 0; pair_code[k] = 0; col_of_pair[k] = (u32)j; }
+      for (i64 k = kb; k < ke; k++) { pair_cell[k] = h_cell[k]; pair_io[k] = 0; pair_code[k] = 0; col_of_pair[k] = (u32)j; }
       continue;
     }
     if (len > 254 || ke - kb > 255) return fail(GRMP_EUNSUPPORTED, "fast path: an edge column has more than 254 entries");
     // ---- ring order of the cells around the edge ----
     const int n = (int)(ke - kb);
     rp.resize(n);
-    i32 P0 = 0;
+    i32 P0 = 0, Q0 = 0;
     for (int t = 0; t < n; t++) {
       const u32 c = h_cell[kb + t];
       const int lj = (int)(h_src[kb + t] / (u32)ncells);
@@ -518,9 +535,9 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
       int rl = -1, sl = -1;
       for (int v = 0; v < 4; v++) if (v != pl && v != ql) { if (rl < 0) rl = v; else sl = v; }
       const i32* cn = &h_cn[(size_t)c * 4];
-      if (t == 0) P0 = cn[pl];
+      if (t == 0) { P0 = cn[pl]; Q0 = cn[ql]; }
       if (cn[pl] != P0) { int tmp = pl; pl = ql; ql = tmp; }      // consistent global orientation (P,Q)
-      if (cn[pl] != P0) return fail(GRMP_EUNSUPPORTED, "fast path: inconsistent edge column");
+      if (cn[pl] != P0 || cn[ql] != Q0) return fail(GRMP_EUNSUPPORTED, "fast path: inconsistent edge column");
       rp[t] = RP{c, pl, ql, rl, sl, cn[rl], cn[sl]};
       if (t == 0) { endP[j] = (u32)(h_dofs[(size_t)c * 10 + pl] - 1); endQ[j] = (u32)(h_dofs[(size_t)c * 10 + ql] - 1); }
     }
@@ -538,6 +555,9 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
       if (dR == 1 || dS == 1) closed = false;
     }
     used.assign(n, 0);
+    colnodes.clear();
+    colnodes.push_back(P0); colnodes.push_back(Q0);
+    std::vector<i32> ring_in(n), ring_out(n);
     int step = 0, nchains = 0;
     while (step < n) {
       int start = -1, start_in_is_R = 1;
@@ -557,17 +577,19 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
         const int I = inR ? rp[curp].R : rp[curp].S, O = inR ? rp[curp].S : rp[curp].R;
         const i32 vout = inR ? rp[curp].nS : rp[curp].nR;
         const i64 k = kb + step;
-        u32 fl = (step == 0) ? PF_FIRST : 0u;
+        u32 fl = 0u;
         if (chain_first && nchains > 0) fl |= PF_RESET;
         pair_cell[k] = rp[curp].cell;
         pair_code[k] = (u32)(rp[curp].P | (rp[curp].Q << 2) | (I << 4) | (O << 6)) | (fl << 8);
         col_of_pair[k] = (u32)j;
+        ring_in[step] = vin; ring_out[step] = vout;
+        colnodes.push_back(vin); colnodes.push_back(vout);
         step++; chain_first = false;
         int nxt = -1;
         for (int u = 0; u < n; u++) if (!used[u] && (rp[u].nR == vout || rp[u].nS == vout)) { nxt = u; break; }
         if (nxt < 0) {
           if (closed && (step != n || vout != first_in)) return fail(GRMP_EUNSUPPORTED, "fast path: edge ring does not close");
-          if (!closed && step < n) pair_code[k] |= (PF_END << 8);     // a further chain follows
+          if (!closed && step < n) { pair_code[k] |= (PF_END << 8); any_end = true; }     // a further chain follows
           break;
         }
         vin = vout; curp = nxt;
@@ -575,48 +597,34 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
       nchains++;
     }
     col_closed[j] = closed ? 1 : 0;
+    std::sort(colnodes.begin(), colnodes.end());
+    colnodes.erase(std::unique(colnodes.begin(), colnodes.end()), colnodes.end());
     // ---- tile budget ----
     for (int attempt = 0; attempt < 2; attempt++) {
       int fresh = 0;
-      for (i64 k = kb; k < ke; k++) if (mark[pair_cell[k]] != cur_tile) fresh++;
-      const i64 need = 8 * (cur_nnz + len) + 80 * (i64)(cur_cells + fresh);
-      if (cur_cols > 0 && (cur_cols + 1 > TPB || need > SMEM_BUDGET)) { close_tile(j); continue; }
-      if (cur_cols == 0) tile_first_col = j;
-      for (i64 k = kb; k < ke; k++) {
-        const u32 c = pair_cell[k];
-        if (mark[c] != cur_tile) { mark[c] = cur_tile; local_of[c] = cur_cells++; tile_cells.push_back((i32)c); }
-        pair_local[k] = (u32)local_of[c];
-      }
-      cur_cols++; cur_nnz += len;
+      for (i32 v : colnodes) if (nmark[v] != cur_tile) fresh++;
+      const i64 need = tile_smem(cur_cols + 1, cur_pairs + n, cur_nodes + fresh, cur_nnz + len);
+      if (cur_cols > 0 && (cur_cols + 1 > TPB || need > SMEM_BUDGET || cur_nodes + fresh > MAX_TILE_NODES || cur_pairs + n > 65535 || cur_nnz + len > 65535)) { close_tile(j); continue; }
+      if (cur_cols == 0) { tile_first_col = j; tile_pair_base = kb; }
+      for (i32 v : colnodes) if (nmark[v] != cur_tile) { nmark[v] = cur_tile; nlocal[v] = cur_nodes++; tile_nodeids.push_back((u32)v); }
+      for (int t = 0; t < n; t++) pair_io[kb + t] = (u32)nlocal[ring_in[t]] | ((u32)nlocal[ring_out[t]] << 12);
+      col_pq[j] = (u32)nlocal[P0] | ((u32)nlocal[Q0] << 12);
+      col_tile[j] = (u32)cur_tile;
+      cur_cols++; cur_nnz += len; cur_pairs += n;
       break;
     }
   }
   close_tile(ncols);
   if (max_smem > 220 * 1024) return fail(GRMP_EUNSUPPORTED, "fast path: a single column exceeds the shared-memory tile");
-  const int ntiles = (int)(tile_hdr.size() / 2);
-  if (npairs >= (i64)NONE) return fail(GRMP_EUNSUPPORTED, "fast path: more than 2^32-1 pairs");
+  const int ntiles = (int)hdr.size();
+  if (blob_total16 >= (i64)NONE) return fail(GRMP_EUNSUPPORTED, "fast path: record blob exceeds 64 GB");
   out->ntiles = ntiles; out->npairs = npairs; out->smem_bytes = (int)max_smem; out->nvcols = (i64)vcols.size();
-  if (tile_hdr.empty()) tile_hdr.assign(2, make_int4(0, 0, 0, 0));
-  if (tile_nodes.empty()) tile_nodes.push_back(make_int4(1, 1, 1, 1));
+  if (hdr.empty()) { TileHdr z{}; hdr.push_back(z); }
+  if (tile_nodeids.empty()) tile_nodeids.push_back(1);
   if (vcols.empty()) vcols.push_back(0);
-  GRMP_TRY(out->tile_hdr.upload(tile_hdr.data(), tile_hdr.size(), s));
-  GRMP_TRY(out->tile_nodes.upload(tile_nodes.data(), tile_nodes.size(), s));
-  // (3) pack pair / column records on the device (slots are looked up in the pattern by (row, col))
-  DevBuf<u32> d_cell, d_local, d_code, d_colof;
-  DevBuf<unsigned char> d_closed;
-  GRMP_TRY(d_cell.upload(pair_cell.data(), npairs, s)); GRMP_TRY(d_local.upload(pair_local.data(), npairs, s));
-  GRMP_TRY(d_code.upload(pair_code.data(), npairs, s)); GRMP_TRY(d_colof.upload(col_of_pair.data(), npairs, s));
-  GRMP_TRY(d_closed.upload(col_closed.data(), ncols, s));
-  GRMP_TRY(out->pairs.alloc(std::max<i64>(npairs, 1)));
-  GRMP_TRY(out->cols.alloc(2 * (size_t)std::max<i64>(ncols, 1)));
-  GRMP_TRY(out->col_pairbeg.alloc(ncols + 1));
-  GRMP_CUDA(cudaMemcpyAsync(out->col_pairbeg.p, dg.segptr.p, (ncols + 1) * 8, cudaMemcpyDeviceToDevice, s));
-  PackParams pp{d_cell.p, d_local.p, d_code.p, dg.segptr.p, pat.colptr.p, pat.rowval.p, p.e1.celldofs, d_colof.p, d_closed.p,
-                npairs, ncols, out->pairs.p, out->cols.p};
-  if (npairs) pack_pairs<<<(unsigned)((npairs + 255) / 256), 256, 0, s>>>(pp);
-  if (ncols) pack_cols<<<(unsigned)((ncols + 255) / 256), 256, 0, s>>>(pp);
-  GRMP_CUDA(cudaGetLastError());
-  // (3b) spoke lists: the diagonal of a vertex column is 0.2 * sum over its spokes of the ring sums of S_vv
+  GRMP_TRY(out->tile_hdr.upload(reinterpret_cast<const int4*>(hdr.data()), hdr.size() * 3, s));
+  GRMP_TRY(out->tile_nodeids.upload(tile_nodeids.data(), tile_nodeids.size(), s));
+  // (2b) spoke lists: the diagonal of a vertex column is 0.2 * sum over its spokes of the ring sums of S_vv
   std::vector<u32> spoke_cnt(ncols, 0), spoke_ptr(ncols + 1, 0);
   for (i64 j = 0; j < ncols; j++) if (endP[j] != NONE) { spoke_cnt[endP[j]]++; spoke_cnt[endQ[j]]++; }
   for (i64 j = 0; j < ncols; j++) spoke_ptr[j + 1] = spoke_ptr[j] + spoke_cnt[j];
@@ -629,9 +637,26 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   std::vector<u32> vspoke(2 * vcols.size());
   for (size_t w2 = 0; w2 < vcols.size(); w2++) { vspoke[2 * w2] = spoke_ptr[vcols[w2]]; vspoke[2 * w2 + 1] = spoke_cnt[vcols[w2]]; }
   DevBuf<u32> d_vspoke;
+  DevBuf<uint2> d_spokes;
   GRMP_TRY(d_vspoke.upload(vspoke.data(), vspoke.size(), s));
-  GRMP_TRY(out->spokes.upload(spokes.data(), spokes.size(), s));
+  GRMP_TRY(d_spokes.upload(spokes.data(), spokes.size(), s));
   GRMP_TRY(out->dscratch.alloc(std::max<size_t>(spoke_ptr[ncols], 1)));
+  // (3) pack column / pair records into the tile blobs on the device (slots are looked up in the pattern by (row, col))
+  DevBuf<u32> d_cell, d_io, d_code, d_colof, d_coltile, d_colpq;
+  DevBuf<unsigned char> d_closed;
+  GRMP_TRY(d_cell.upload(pair_cell.data(), npairs, s)); GRMP_TRY(d_io.upload(pair_io.data(), npairs, s));
+  GRMP_TRY(d_code.upload(pair_code.data(), npairs, s)); GRMP_TRY(d_colof.upload(col_of_pair.data(), npairs, s));
+  GRMP_TRY(d_closed.upload(col_closed.data(), ncols, s));
+  GRMP_TRY(d_coltile.upload(col_tile.data(), ncols, s)); GRMP_TRY(d_colpq.upload(col_pq.data(), ncols, s));
+  GRMP_TRY(out->blob.alloc(std::max<size_t>((size_t)blob_total16 * 16, 16)));
+  GRMP_CUDA(cudaMemsetAsync(out->blob.p, 0, out->blob.bytes(), s));
+  out->end_slots.release();
+  if (any_end) GRMP_TRY(out->end_slots.alloc(std::max<i64>(npairs, 1)));
+  PackParams pp{d_cell.p, d_io.p, d_code.p, dg.segptr.p, pat.colptr.p, pat.rowval.p, p.e1.celldofs, d_colof.p, d_closed.p,
+                d_coltile.p, d_colpq.p, d_spokes.p, reinterpret_cast<const TileHdr*>(out->tile_hdr.p), npairs, ncols, out->blob.p, out->end_slots.p};
+  if (npairs) pack_pairs<<<(unsigned)((npairs + 255) / 256), 256, 0, s>>>(pp);
+  if (ncols) pack_cols<<<(unsigned)((ncols + 255) / 256), 256, 0, s>>>(pp);
+  GRMP_CUDA(cudaGetLastError());
   // (4) vertex columns: list + diagonal slots
   GRMP_TRY(out->vcols.upload(vcols.data(), vcols.size(), s));
   GRMP_TRY(out->vrec.alloc(vcols.size()));
@@ -640,19 +665,16 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     GRMP_CUDA(cudaGetLastError());
   }
   const int smem_attr = (int)std::max<i64>(max_smem, 1024);
-  GRMP_CUDA(cudaFuncSetAttribute(p2tet_edge_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
-  GRMP_CUDA(cudaFuncSetAttribute(p2tet_edge_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
-  GRMP_CUDA(cudaFuncSetAttribute(p2tet_edge_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
-  GRMP_CUDA(cudaFuncSetAttribute(p2tet_edge_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
-  GRMP_CUDA(cudaFuncSetAttribute(p2tet_edge_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
+  GRMP_TRY(set_smem_attr<64>(smem_attr)); GRMP_TRY(set_smem_attr<128>(smem_attr)); GRMP_TRY(set_smem_attr<192>(smem_attr));
+  GRMP_TRY(set_smem_attr<256>(smem_attr)); GRMP_TRY(set_smem_attr<512>(smem_attr));
   GRMP_CUDA(cudaStreamSynchronize(s));
   return GRMP_OK;
 }
 
 int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const FastP2Tet& f, double* nzval) {
+  static const int dbg = getenv("GRMP_DEBUG_FLAGS") ? atoi(getenv("GRMP_DEBUG_FLAGS")) : 0;
   if (f.ntiles > 0) {
-    static const int dbg = getenv("GRMP_DEBUG_FLAGS") ? atoi(getenv("GRMP_DEBUG_FLAGS")) : 0;
-    EdgeParams ep{p.g, pat.colptr.p, f.col_pairbeg.p, f.pairs.p, f.cols.p, f.spokes.p, f.dscratch.p, f.tile_hdr.p, f.tile_nodes.p, p.factor, nzval, dbg};
+    EdgeParams ep{p.g.coords, reinterpret_cast<const TileHdr*>(f.tile_hdr.p), f.blob.p, f.tile_nodeids.p, f.end_slots.p, f.dscratch.p, p.factor, nzval, dbg};
     if (f.tpb == 64) p2tet_edge_kernel<64><<<f.ntiles, 64, f.smem_bytes, ctx->stream>>>(ep);
     else if (f.tpb == 256) p2tet_edge_kernel<256><<<f.ntiles, 256, f.smem_bytes, ctx->stream>>>(ep);
     else if (f.tpb == 192) p2tet_edge_kernel<192><<<f.ntiles, 192, f.smem_bytes, ctx->stream>>>(ep);
@@ -660,7 +682,7 @@ int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pa
     else p2tet_edge_kernel<128><<<f.ntiles, 128, f.smem_bytes, ctx->stream>>>(ep);
     GRMP_CUDA(cudaGetLastError());
   }
-  if (f.nvcols > 0 && !(getenv("GRMP_DEBUG_FLAGS") && (atoi(getenv("GRMP_DEBUG_FLAGS")) & 2))) {
+  if (f.nvcols > 0 && !(dbg & 2)) {
     p2tet_vertex_diag_kernel<<<(unsigned)((f.nvcols + 255) / 256), 256, 0, ctx->stream>>>(f.vrec.p, f.nvcols, f.dscratch.p, nzval);
     GRMP_CUDA(cudaGetLastError());
   }
