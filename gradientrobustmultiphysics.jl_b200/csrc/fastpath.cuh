@@ -11,9 +11,10 @@ struct FastP2Tet {
   int tpb = 256;
   i64 npairs = 0;
   int smem_bytes = 0;
-  DevBuf<int4> tile_hdr;          // 3 per tile (TileHdr): column range, nzval range, blob / node-list / pair offsets
-  DevBuf<unsigned char> blob;     // per tile: column records, ring-ordered pair records, pair mirror slots (one TMA bulk load)
-  DevBuf<u32> tile_nodeids;       // distinct nodes of every tile (1-based)
+  u32 in_stride = 0;              // bytes of one input buffer of the kernel's 2-deep ring (largest blob)
+  DevBuf<int4> tile_hdr;          // 3 per tile (TileHdr): column range, nzval range, blob / node-list / pair offsets (symbolic pass only)
+  DevBuf<uint2> tile_dir;         // per tile: blob offset (16-byte units), blob bytes
+  DevBuf<unsigned char> blob;     // per tile: header, column records, ring-ordered pair records, pair mirror slots, node coordinates (one TMA bulk load)
   DevBuf<u32> end_slots;          // per pair, only when a partition produced multi-chain halo columns
   DevBuf<u32> vcols;              // vertex columns
   DevBuf<uint4> vrec;             // per vertex column: diagonal slot, first spoke slot, #spokes

@@ -43,7 +43,8 @@ namespace grmp {
 namespace {
 
 constexpr int TPB_DEFAULT = 256;                  // threads (= edge columns) per tile
-constexpr int SMEM_BUDGET_DEFAULT = 104 * 1024;   // records + node coordinates + nzval stage of a 256-column tile
+// shared memory per CTA (2 input buffers + output stage) such that 2 / 3 / 5 CTAs of 256 / 192 / 128 threads fit on an SM
+__host__ inline i64 smem_budget_default(int tpb) { return 1024 * (i64)(tpb >= 512 ? 224 : tpb >= 256 ? 112 : tpb >= 192 ? 74 : tpb >= 128 ? 44 : 21); }
 constexpr u32 NONE = 0xffffffffu;
 constexpr int MAX_TILE_NODES = 4095;              // 12-bit tile-local node ids
 
@@ -58,8 +59,8 @@ __host__ __device__ inline int edge_of(int a, int b) {   // local edge dof index
 }
 
 // ---- records ---------------------------------------------------------------------------------
-// tile header (48 B, global): see TileHdr.
 // tile blob (global, contiguous per tile, 16-byte aligned sections; one TMA bulk load):
+//   tile header 48 B: see TileHdr
 //   column records  48 B x ncol
 //     a.x : tile-local node of P | Q << 12 | #pairs << 24
 //     a.y : slot offsets inside the column of rows v_P, v_Q, e_PQ (255 = not in the pattern) | flags << 24 (bit 0: closed ring)
@@ -72,6 +73,7 @@ __host__ __device__ inline int edge_of(int a, int b) {   // local edge dof index
 //     x : slot offsets inside the column of rows v_in, e_P,in, e_Q,in, e_in,out (255 = not in the pattern)
 //     y : tile-local node of the in-vertex | out-vertex << 12 | flags << 24
 //   pair mirrors 4 B x npairs : mirrored slot of row e_PQ in column v_in, or NONE
+//   node coordinates 24 B x nnodes : tile-blocked copy of Coordinates (the grid is immutable after grmp_grid_create)
 constexpr u32 PF_RESET = 2u;   // first pair of a further chain (halo columns of a partition): drop the carry, reload the in-vertex
 constexpr u32 PF_END = 4u;     // last pair of a chain that is not the last chain: mirror its out-vertex row now (slot in end_slots)
 
@@ -172,20 +174,32 @@ __global__ void pack_cols(PackParams p) {
   b.w = gslot(p, vQ, vP);
   c.x = gslot(p, vP, vQ);
   c.y = p.spokes[j].x; c.z = p.spokes[j].y; c.w = 0;
-  uint4* dst = reinterpret_cast<uint4*>(p.blob + (size_t)h.blob16 * 16) + 3 * (j - h.c0);
+  uint4* dst = reinterpret_cast<uint4*>(p.blob + (size_t)h.blob16 * 16 + 48) + 3 * (j - h.c0);
   dst[0] = a; dst[1] = b; dst[2] = c;
 }
 
+// one block per tile: header and node coordinates into the blob
+__global__ void pack_tile_nodes(const TileHdr* hdr, const u32* tile_nodeids, const double* coords, unsigned char* blob) {
+  const TileHdr h = hdr[blockIdx.x];
+  unsigned char* tb = blob + (size_t)h.blob16 * 16;
+  if (threadIdx.x < 3) reinterpret_cast<int4*>(tb)[threadIdx.x] = reinterpret_cast<const int4*>(hdr + blockIdx.x)[threadIdx.x];
+  double* X = reinterpret_cast<double*>(tb + h.pairs_off + pad16(8u * (u32)h.npairs) + pad16(4u * (u32)h.npairs));
+  for (int i = threadIdx.x; i < h.nnodes; i += blockDim.x) {
+    const double* xg = coords + (size_t)(tile_nodeids[(size_t)h.node_base + i] - 1) * 3;
+    X[3 * i] = xg[0]; X[3 * i + 1] = xg[1]; X[3 * i + 2] = xg[2];
+  }
+}
+
 struct EdgeParams {
-  const double* coords;     // [nnodes][3]
-  const TileHdr* hdr;
+  const uint2* tile_dir;    // per tile: blob offset (16-byte units), blob bytes
   const unsigned char* blob;
-  const u32* tile_nodeids;  // 1-based node ids of the tiles' distinct nodes
   const u32* end_slots;     // [npairs] or null (only partitions have multi-chain columns)
   double* dscratch;         // [sum of spoke counts] 0.2 * ring sum of S_vv per (vertex, spoke)
   double factor;
   double* nzval;
-  int dbg;                  // GRMP_DEBUG_FLAGS: bit 0 = skip the mirrored stores (timing experiments only)
+  int ntiles;
+  u32 in_stride;            // bytes of one input buffer (largest blob)
+  int dbg;                  // GRMP_DEBUG_FLAGS (timing experiments only): 1 skip mirrored stores, 4 skip the ring walk, 8 skip the bulk store
 };
 
 __device__ __forceinline__ double fast_rcp(double d) {   // 1/d to ~1 ulp for normal d: MUFU.RCP64H + two Newton steps
@@ -198,180 +212,202 @@ __device__ __forceinline__ double fast_rcp(double d) {   // 1/d to ~1 ulp for no
   return r;
 }
 
-template <int TPB>
-__global__ void __launch_bounds__(TPB, (TPB <= 64 ? 10 : TPB <= 128 ? 5 : TPB <= 192 ? 3 : TPB <= 256 ? 2 : 1)) p2tet_edge_kernel(const EdgeParams p) {
-  extern __shared__ __align__(128) unsigned char smraw[];
-  __shared__ __align__(8) unsigned long long mbar;
-  const int tile = blockIdx.x, tid = threadIdx.x;
-  const int4* hp = reinterpret_cast<const int4*>(p.hdr + tile);
-  const int4 h0 = __ldg(hp), h1 = __ldg(hp + 1), h2 = __ldg(hp + 2);
-  const int ncol = h0.y, nn = h0.z;
-  const i64 g0 = (i64)(u32)h1.x | ((i64)h1.y << 32);
-  const int nnz_t = h1.z;
-  const u32 blob_bytes = (u32)h2.z, pairs_off = (u32)h2.w, mir_off = pairs_off + pad16(8u * (u32)h0.w);
-  // shared memory: [blob | node coordinates | nzval stage].  stage[i] mirrors nzval[g0 + i]; it is shifted by one element
-  // when g0 is odd so that shared and global addresses of the same element are 16-byte aligned together (TMA bulk store).
-  // Every slot is written exactly once -> no zero-init.
-  double* __restrict__ X = reinterpret_cast<double*>(smraw + blob_bytes);
-  const int odd = (int)(g0 & 1);
-  double* __restrict__ stage = reinterpret_cast<double*>(smraw + blob_bytes + pad16(24u * (u32)nn)) + odd;
-  const unsigned mbar_a = (unsigned)__cvta_generic_to_shared(&mbar);
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(blob_bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(smraw)),
-                 "l"(p.blob + (size_t)(u32)h1.w * 16), "r"(blob_bytes), "r"(mbar_a)
-                 : "memory");
-  }
-  // node coordinates of the tile -> shared memory (overlaps the bulk load of the records)
-  for (int i = tid; i < nn; i += TPB) {
-    const u32 id = __ldg(p.tile_nodeids + (size_t)(u32)h2.y + i);
-    const double* xg = p.coords + (size_t)(id - 1) * 3;
-    const double x = __ldg(xg), y = __ldg(xg + 1), z = __ldg(xg + 2);
-    X[3 * i] = x; X[3 * i + 1] = y; X[3 * i + 2] = z;
-  }
-  __syncthreads();          // coordinates visible; also orders the mbarrier init before the waits of the other threads
+__device__ __forceinline__ void tile_load(const EdgeParams& p, uint2 dir, unsigned dst_smem, unsigned mbar_a) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(dir.y) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(p.blob + (size_t)dir.x * 16), "r"(dir.y), "r"(mbar_a)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar_a, unsigned parity) {
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
       "@P1 bra DONE;\n"
       "bra LAB_WAIT;\n"
       "DONE:\n"
-      "}" ::"r"(mbar_a)
+      "}" ::"r"(mbar_a), "r"(parity)
       : "memory");
-  if (tid < ncol && !(p.dbg & 4)) {
-    const uint4* cr = reinterpret_cast<const uint4*>(smraw) + 3 * tid;
-    const uint4 ca = cr[0], cb = cr[1], cc = cr[2];
-    const u32 np = ca.x >> 24;
-    if (np > 0) {
-      const uint2* __restrict__ prec = reinterpret_cast<const uint2*>(smraw + pairs_off) + (ca.w >> 16);
-      const u32* __restrict__ pmir = reinterpret_cast<const u32*>(smraw + mir_off) + (ca.w >> 16);
-      double* __restrict__ a = stage + (ca.w & 0xffffu);
-      const bool closed = (ca.y >> 24) & 1u;
-      const u32 lp = ca.x & 0xfffu, lq = (ca.x >> 12) & 0xfffu;
-      const double px = X[3 * lp], py = X[3 * lp + 1], pz = X[3 * lp + 2];
-      const double ax = X[3 * lq] - px, ay = X[3 * lq + 1] - py, az = X[3 * lq + 2] - pz;
-      const double c8 = p.factor * (0.8 / 6.0);      // S' = 0.8 * S = c8 / |det| * n_a.n_b
-      uint2 r0 = prec[0];
-      uint2 r1 = prec[np > 1 ? 1 : 0];
-      double bx, by, bz, mcx, mcy, mcz;               // b = c_in - p, mc = a x b (carried around the ring)
-      {
-        const u32 li = r0.y & 0xfffu;
-        bx = X[3 * li] - px; by = X[3 * li + 1] - py; bz = X[3 * li + 2] - pz;
-        mcx = ay * bz - az * by; mcy = az * bx - ax * bz; mcz = ax * by - ay * bx;
-      }
-      double ox, oy, oz;                              // coordinates of the out-vertex of the current pair
-      {
-        const u32 lo = (r0.y >> 12) & 0xfffu;
-        ox = X[3 * lo]; oy = X[3 * lo + 1]; oz = X[3 * lo + 2];
-      }
-      double R1 = 0.0, R2 = 0.0, R3 = 0.0;            // ring sums of S'_pq, S'_pi + S'_po, S'_qi + S'_qo
-      double c0r = 0.0, c1r = 0.0, c2r = 0.0;          // carry: partial rows of the shared ring vertex
-      double f0 = 0.0, f1 = 0.0, f2 = 0.0;             // closed ring: in-rows of the first pair, completed at the end
-      for (u32 k = 0; k < np; k++) {
-        // software pipeline: out-vertex of the next pair, record after next
-        const u32 ln = (r1.y >> 12) & 0xfffu;
-        const double nx = X[3 * ln], ny = X[3 * ln + 1], nz = X[3 * ln + 2];
-        const uint2 r2 = prec[k + 2 < np ? k + 2 : np - 1];
-        const u32 pm = pmir[k];
-        const u32 fl = r0.y >> 24;
-        if (fl & PF_RESET) {
+}
+
+// Persistent CTAs: CTA b walks tiles b, b + gridDim.x, ...  The inputs of a tile (header, records, node coordinates: one
+// contiguous blob) are prefetched two tiles ahead by TMA bulk loads into a 2-deep shared-memory ring, the output range is
+// staged in shared memory and leaves through a TMA bulk store that overlaps the next tile's ring walk.
+template <int TPB>
+__global__ void __launch_bounds__(TPB, (TPB <= 64 ? 10 : TPB <= 128 ? 5 : TPB <= 192 ? 3 : TPB <= 256 ? 2 : 1)) p2tet_edge_kernel(const EdgeParams p) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  __shared__ __align__(8) unsigned long long mbar[2];
+  const int tid = threadIdx.x;
+  const unsigned mbar_a = (unsigned)__cvta_generic_to_shared(&mbar[0]);
+  const unsigned in_a = (unsigned)__cvta_generic_to_shared(smraw);
+  double* const stage_base = reinterpret_cast<double*>(smraw + 2 * (size_t)p.in_stride);
+  const int G = gridDim.x;
+  int t = blockIdx.x;
+  uint2 dir_next = make_uint2(0, 0);       // thread 0: directory entry of the tile two steps ahead
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a + 8));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (t < p.ntiles) tile_load(p, __ldg(p.tile_dir + t), in_a, mbar_a);
+    if (t + G < p.ntiles) tile_load(p, __ldg(p.tile_dir + t + G), in_a + p.in_stride, mbar_a + 8);
+    if (t + 2 * G < p.ntiles) dir_next = __ldg(p.tile_dir + t + 2 * G);
+  }
+  __syncthreads();
+  for (int it = 0; t < p.ntiles; t += G, it++) {
+    const int cur = it & 1;
+    const unsigned char* __restrict__ in = smraw + (size_t)cur * p.in_stride;
+    mbar_wait(mbar_a + 8 * cur, (unsigned)(it >> 1) & 1u);
+    const int4 h0 = reinterpret_cast<const int4*>(in)[0], h1 = reinterpret_cast<const int4*>(in)[1], h2 = reinterpret_cast<const int4*>(in)[2];
+    const int ncol = h0.y;
+    const i64 g0 = (i64)(u32)h1.x | ((i64)h1.y << 32);
+    const int nnz_t = h1.z;
+    const u32 pairs_off = (u32)h2.w, mir_off = pairs_off + pad16(8u * (u32)h0.w), xyz_off = mir_off + pad16(4u * (u32)h0.w);
+    const double* __restrict__ X = reinterpret_cast<const double*>(in + xyz_off);
+    // stage[i] mirrors nzval[g0 + i]; it is shifted by one element when g0 is odd so that shared and global addresses of the
+    // same element are 16-byte aligned together (TMA bulk store).  Every slot is written exactly once -> no zero-init.
+    const int odd = (int)(g0 & 1);
+    double* __restrict__ stage = stage_base + odd;
+    // the previous tile's bulk store must have finished reading the stage before it is overwritten
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();
+    if (tid < ncol && !(p.dbg & 4)) {
+      const uint4* cr = reinterpret_cast<const uint4*>(in + 48) + 3 * tid;
+      const uint4 ca = cr[0], cb = cr[1], cc = cr[2];
+      const u32 np = ca.x >> 24;
+      if (np > 0) {
+        const uint2* __restrict__ prec = reinterpret_cast<const uint2*>(in + pairs_off) + (ca.w >> 16);
+        const u32* __restrict__ pmir = reinterpret_cast<const u32*>(in + mir_off) + (ca.w >> 16);
+        double* __restrict__ a = stage + (ca.w & 0xffffu);
+        const bool closed = (ca.y >> 24) & 1u;
+        const u32 lp = ca.x & 0xfffu, lq = (ca.x >> 12) & 0xfffu;
+        const double px = X[3 * lp], py = X[3 * lp + 1], pz = X[3 * lp + 2];
+        const double ax = X[3 * lq] - px, ay = X[3 * lq + 1] - py, az = X[3 * lq + 2] - pz;
+        const double c8 = p.factor * (0.8 / 6.0);      // S' = 0.8 * S = c8 / |det| * n_a.n_b
+        uint2 r0 = prec[0];
+        uint2 r1 = prec[np > 1 ? 1 : 0];
+        double bx, by, bz, mcx, mcy, mcz;               // b = c_in - p, mc = a x b (carried around the ring)
+        {
           const u32 li = r0.y & 0xfffu;
           bx = X[3 * li] - px; by = X[3 * li + 1] - py; bz = X[3 * li + 2] - pz;
           mcx = ay * bz - az * by; mcy = az * bx - ax * bz; mcz = ax * by - ay * bx;
-          c0r = 0.0; c1r = 0.0; c2r = 0.0;
         }
-        // cell (p, q, in, out): a = q-p, b = in-p, e = out-p;  n_q = b x e, n_in = -(a x e), n_out = a x b, n_p = -(n_q+n_in+n_out)
-        const double ex = ox - px, ey = oy - py, ez = oz - pz;
-        const double mdx = ay * ez - az * ey, mdy = az * ex - ax * ez, mdz = ax * ey - ay * ex;
-        const double gx = by * ez - bz * ey, gy = bz * ex - bx * ez, gz = bx * ey - by * ex;
-        const double det = ax * gx + ay * gy + az * gz;
-        const double s = c8 * fast_rcp(fabs(det));
-        const double npx = mdx - gx - mcx, npy = mdy - gy - mcy, npz = mdz - gz - mcz;
-        const double spq = s * (npx * gx + npy * gy + npz * gz);
-        const double spi = -s * (npx * mdx + npy * mdy + npz * mdz);
-        const double spo = s * (npx * mcx + npy * mcy + npz * mcz);
-        const double sqi = -s * (gx * mdx + gy * mdy + gz * mdz);
-        const double sqo = s * (gx * mcx + gy * mcy + gz * mcz);
-        // with S' = 0.8 S and the zero row sums of S (S_pp = -(S_pq+S_pi+S_po), S_qq likewise):
-        //   v_in: -0.2(S_pi+S_qi)   e_P,in: 0.8(2 S_qi - S_po)   e_Q,in: 0.8(2 S_pi - S_qo)   e_in,out: 0.8(S_pi+S_po+S_qi+S_qo)
-        const double tp = spi + spo, tq = sqi + sqo;
-        R1 += spq; R2 += tp; R3 += tq;
-        const double in0 = c0r - 0.25 * (spi + sqi);
-        const double in1 = c1r + (2.0 * sqi - spo);
-        const double in2 = c2r + (2.0 * spi - sqo);
-        c0r = -0.25 * (spo + sqo);
-        c1r = 2.0 * sqo - spi;
-        c2r = 2.0 * spo - sqi;
-        const u32 o3 = r0.x >> 24;
-        if (o3 != 255u) a[o3] = tp + tq;
-        if ((fl & PF_END) && p.end_slots != nullptr && !(p.dbg & 1)) {     // chain end inside a halo column: mirror (e_PQ, v_out)
-          const u32 es = p.end_slots[(size_t)(u32)h2.x + (ca.w >> 16) + k];
-          if (es != NONE) p.nzval[es] = c0r;
+        double ox, oy, oz;                              // coordinates of the out-vertex of the current pair
+        {
+          const u32 lo = (r0.y >> 12) & 0xfffu;
+          ox = X[3 * lo]; oy = X[3 * lo + 1]; oz = X[3 * lo + 2];
         }
-        if (closed && k == 0) {
-          f0 = in0; f1 = in1; f2 = in2;                                  // partner is the last pair of the ring
-        } else {
-          const u32 o0 = r0.x & 255u, o1 = (r0.x >> 8) & 255u, o2 = (r0.x >> 16) & 255u;
-          if (o0 != 255u) a[o0] = in0;
-          if (o1 != 255u) a[o1] = in1;
-          if (o2 != 255u) a[o2] = in2;
-          if (pm != NONE && !(p.dbg & 1)) p.nzval[pm] = in0;             // mirror (e_PQ, v_in)
+        double R1 = 0.0, R2 = 0.0, R3 = 0.0;            // ring sums of S'_pq, S'_pi + S'_po, S'_qi + S'_qo
+        double c0r = 0.0, c1r = 0.0, c2r = 0.0;          // carry: partial rows of the shared ring vertex
+        double f0 = 0.0, f1 = 0.0, f2 = 0.0;             // closed ring: in-rows of the first pair, completed at the end
+        for (u32 k = 0; k < np; k++) {
+          // software pipeline: out-vertex of the next pair, record after next
+          const u32 ln = (r1.y >> 12) & 0xfffu;
+          const double nx = X[3 * ln], ny = X[3 * ln + 1], nz = X[3 * ln + 2];
+          const uint2 r2 = prec[k + 2 < np ? k + 2 : np - 1];
+          const u32 pm = pmir[k];
+          const u32 fl = r0.y >> 24;
+          if (fl & PF_RESET) {
+            const u32 li = r0.y & 0xfffu;
+            bx = X[3 * li] - px; by = X[3 * li + 1] - py; bz = X[3 * li + 2] - pz;
+            mcx = ay * bz - az * by; mcy = az * bx - ax * bz; mcz = ax * by - ay * bx;
+            c0r = 0.0; c1r = 0.0; c2r = 0.0;
+          }
+          // cell (p, q, in, out): a = q-p, b = in-p, e = out-p;  n_q = b x e, n_in = -(a x e), n_out = a x b, n_p = -(n_q+n_in+n_out)
+          const double ex = ox - px, ey = oy - py, ez = oz - pz;
+          const double mdx = ay * ez - az * ey, mdy = az * ex - ax * ez, mdz = ax * ey - ay * ex;
+          const double gx = by * ez - bz * ey, gy = bz * ex - bx * ez, gz = bx * ey - by * ex;
+          const double det = ax * gx + ay * gy + az * gz;
+          const double s = c8 * fast_rcp(fabs(det));
+          const double npx = mdx - gx - mcx, npy = mdy - gy - mcy, npz = mdz - gz - mcz;
+          const double spq = s * (npx * gx + npy * gy + npz * gz);
+          const double spi = -s * (npx * mdx + npy * mdy + npz * mdz);
+          const double spo = s * (npx * mcx + npy * mcy + npz * mcz);
+          const double sqi = -s * (gx * mdx + gy * mdy + gz * mdz);
+          const double sqo = s * (gx * mcx + gy * mcy + gz * mcz);
+          // with S' = 0.8 S and the zero row sums of S (S_pp = -(S_pq+S_pi+S_po), S_qq likewise):
+          //   v_in: -0.2(S_pi+S_qi)   e_P,in: 0.8(2 S_qi - S_po)   e_Q,in: 0.8(2 S_pi - S_qo)   e_in,out: 0.8(S_pi+S_po+S_qi+S_qo)
+          const double tp = spi + spo, tq = sqi + sqo;
+          R1 += spq; R2 += tp; R3 += tq;
+          const double in0 = c0r - 0.25 * (spi + sqi);
+          const double in1 = c1r + (2.0 * sqi - spo);
+          const double in2 = c2r + (2.0 * spi - sqo);
+          c0r = -0.25 * (spo + sqo);
+          c1r = 2.0 * sqo - spi;
+          c2r = 2.0 * spo - sqi;
+          const u32 o3 = r0.x >> 24;
+          if (o3 != 255u) a[o3] = tp + tq;
+          if ((fl & PF_END) && p.end_slots != nullptr && !(p.dbg & 1)) {     // chain end inside a halo column: mirror (e_PQ, v_out)
+            const u32 es = p.end_slots[(size_t)(u32)h2.x + (ca.w >> 16) + k];
+            if (es != NONE) p.nzval[es] = c0r;
+          }
+          if (closed && k == 0) {
+            f0 = in0; f1 = in1; f2 = in2;                                  // partner is the last pair of the ring
+          } else {
+            const u32 o0 = r0.x & 255u, o1 = (r0.x >> 8) & 255u, o2 = (r0.x >> 16) & 255u;
+            if (o0 != 255u) a[o0] = in0;
+            if (o1 != 255u) a[o1] = in1;
+            if (o2 != 255u) a[o2] = in2;
+            if (pm != NONE && !(p.dbg & 1)) p.nzval[pm] = in0;             // mirror (e_PQ, v_in)
+          }
+          bx = ex; by = ey; bz = ez; mcx = mdx; mcy = mdy; mcz = mdz;
+          ox = nx; oy = ny; oz = nz;
+          r0 = r1; r1 = r2;
         }
-        bx = ex; by = ey; bz = ez; mcx = mdx; mcy = mdy; mcz = mdz;
-        ox = nx; oy = ny; oz = nz;
-        r0 = r1; r1 = r2;
-      }
-      // closing rows: closed ring -> first pair's in-rows + last carry; open chain -> last pair's out-rows
-      {
-        const double q0 = closed ? f0 + c0r : c0r, q1 = closed ? f1 + c1r : c1r, q2 = closed ? f2 + c2r : c2r;
-        const u32 o0 = ca.z & 255u, o1 = (ca.z >> 8) & 255u, o2 = (ca.z >> 16) & 255u;
-        if (o0 != 255u) a[o0] = q0;
-        if (o1 != 255u) a[o1] = q1;
-        if (o2 != 255u) a[o2] = q2;
-        if (cb.z != NONE && !(p.dbg & 1)) p.nzval[cb.z] = q0;
-      }
-      {
-        // rows v_P, v_Q, e_PQ and the (v_P, v_Q) coupling from the ring sums (S'_pp = -(S'_pq + S'_pi + S'_po)):
-        //   A = sum 0.6 S_pq - 0.2 S_pp = R1 + R2/4,  C = 1.6 sum (S_pp+S_qq+S_pq) = -2 (R1+R2+R3),  W = -0.2 sum S_pq = -R1/4
-        const double A = R1 + 0.25 * R2, B = R1 + 0.25 * R3, C = -2.0 * (R1 + R2 + R3), W = -0.25 * R1;
-        const u32 oA = ca.y & 255u, oB = (ca.y >> 8) & 255u, oC = (ca.y >> 16) & 255u;
-        if (oA != 255u) a[oA] = A;
-        if (oB != 255u) a[oB] = B;
-        if (oC != 255u) a[oC] = C;
-        if (!(p.dbg & 1)) {
-          if (cb.x != NONE) p.nzval[cb.x] = A;       // (e_PQ, v_P)
-          if (cb.y != NONE) p.nzval[cb.y] = B;       // (e_PQ, v_Q)
-          if (cb.w != NONE) p.nzval[cb.w] = W;       // (v_Q, v_P)
-          if (cc.x != NONE) p.nzval[cc.x] = W;       // (v_P, v_Q)
+        // closing rows: closed ring -> first pair's in-rows + last carry; open chain -> last pair's out-rows
+        {
+          const double q0 = closed ? f0 + c0r : c0r, q1 = closed ? f1 + c1r : c1r, q2 = closed ? f2 + c2r : c2r;
+          const u32 o0 = ca.z & 255u, o1 = (ca.z >> 8) & 255u, o2 = (ca.z >> 16) & 255u;
+          if (o0 != 255u) a[o0] = q0;
+          if (o1 != 255u) a[o1] = q1;
+          if (o2 != 255u) a[o2] = q2;
+          if (cb.z != NONE && !(p.dbg & 1)) p.nzval[cb.z] = q0;
         }
-        if (cc.y != NONE) p.dscratch[cc.y] = -0.25 * (R1 + R2);   // 0.2 * ring sum of S_pp
-        if (cc.z != NONE) p.dscratch[cc.z] = -0.25 * (R1 + R3);   // 0.2 * ring sum of S_qq
+        {
+          // rows v_P, v_Q, e_PQ and the (v_P, v_Q) coupling from the ring sums (S'_pp = -(S'_pq + S'_pi + S'_po)):
+          //   A = sum 0.6 S_pq - 0.2 S_pp = R1 + R2/4,  C = 1.6 sum (S_pp+S_qq+S_pq) = -2 (R1+R2+R3),  W = -0.2 sum S_pq = -R1/4
+          const double A = R1 + 0.25 * R2, B = R1 + 0.25 * R3, C = -2.0 * (R1 + R2 + R3), W = -0.25 * R1;
+          const u32 oA = ca.y & 255u, oB = (ca.y >> 8) & 255u, oC = (ca.y >> 16) & 255u;
+          if (oA != 255u) a[oA] = A;
+          if (oB != 255u) a[oB] = B;
+          if (oC != 255u) a[oC] = C;
+          if (!(p.dbg & 1)) {
+            if (cb.x != NONE) p.nzval[cb.x] = A;       // (e_PQ, v_P)
+            if (cb.y != NONE) p.nzval[cb.y] = B;       // (e_PQ, v_Q)
+            if (cb.w != NONE) p.nzval[cb.w] = W;       // (v_Q, v_P)
+            if (cc.x != NONE) p.nzval[cc.x] = W;       // (v_P, v_Q)
+          }
+          if (cc.y != NONE) p.dscratch[cc.y] = -0.25 * (R1 + R2);   // 0.2 * ring sum of S_pp
+          if (cc.z != NONE) p.dscratch[cc.z] = -0.25 * (R1 + R3);   // 0.2 * ring sum of S_qq
+        }
       }
     }
-  }
-  __syncthreads();
-  {
-    // the tile's nzval range is contiguous: one TMA bulk store (cp.async.bulk shared -> global) of the 16-byte aligned
-    // body, the (at most one) unaligned element at either end by ordinary stores
-    double* __restrict__ dst = p.nzval + g0;
-    const int i0 = odd;                                   // first element whose address is 16-byte aligned
-    const int nb = (nnz_t > i0) ? ((nnz_t - i0) & ~1) : 0;  // elements in the bulk body
-    if (tid == 0 && nb > 0 && !(p.dbg & 8)) {
-      const unsigned src = (unsigned)__cvta_generic_to_shared(stage + i0);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + i0), "r"(src), "r"(nb * 8) : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // stage writes -> visible to the bulk store
+    __syncthreads();
+    {
+      // the tile's nzval range is contiguous: one TMA bulk store (cp.async.bulk shared -> global) of the 16-byte aligned
+      // body, the (at most one) unaligned element at either end by ordinary stores
+      double* __restrict__ dst = p.nzval + g0;
+      const int i0 = odd;                                   // first element whose address is 16-byte aligned
+      const int nb = (nnz_t > i0) ? ((nnz_t - i0) & ~1) : 0;  // elements in the bulk body
+      if (tid == 0) {
+        if (nb > 0 && !(p.dbg & 8)) {
+          const unsigned src = (unsigned)__cvta_generic_to_shared(stage + i0);
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + i0), "r"(src), "r"(nb * 8) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        // this input buffer is free again (everybody passed the barrier): prefetch the tile two steps ahead into it
+        if (t + 2 * G < p.ntiles) {
+          tile_load(p, dir_next, in_a + cur * p.in_stride, mbar_a + 8 * cur);
+          if (t + 3 * G < p.ntiles) dir_next = __ldg(p.tile_dir + t + 3 * G);
+        }
+      }
+      if (tid == 1 && i0 == 1 && nnz_t > 0) dst[0] = stage[0];
+      if (tid == 2 && i0 + nb < nnz_t) dst[i0 + nb] = stage[i0 + nb];
     }
-    if (tid == 1 && i0 == 1 && nnz_t > 0) dst[0] = stage[0];
-    if (tid == 2 && i0 + nb < nnz_t) dst[i0 + nb] = stage[i0 + nb];
-    if (tid == 0 && nb > 0 && !(p.dbg & 8)) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must stay alive until read
   }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must stay alive until read
 }
 
 // A[v,v] = 0.6 * sum_{K containing v} S_vv = 0.2 * sum over the spokes (v w) of the ring sums of S_vv (every cell at v
@@ -475,7 +511,9 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   // tile shape (tunable for experiments: GRMP_FAST_TPB in {64,128,192,256,512}, GRMP_FAST_SMEM_KB)
   int TPB = getenv("GRMP_FAST_TPB") ? atoi(getenv("GRMP_FAST_TPB")) : TPB_DEFAULT;
   if (TPB != 64 && TPB != 128 && TPB != 192 && TPB != 256 && TPB != 512) TPB = TPB_DEFAULT;
-  const i64 SMEM_BUDGET = getenv("GRMP_FAST_SMEM_KB") ? 1024 * (i64)atoi(getenv("GRMP_FAST_SMEM_KB")) : SMEM_BUDGET_DEFAULT * (i64)TPB / TPB_DEFAULT;
+  const i64 SMEM_BUDGET = getenv("GRMP_FAST_SMEM_KB") ? 1024 * (i64)atoi(getenv("GRMP_FAST_SMEM_KB")) : smem_budget_default(TPB);
+  // separate caps for the input blob and the output stage (typical ratio 1 : 1.3), so that 2 * max blob + max stage stays inside the budget
+  const i64 BLOB_CAP = (SMEM_BUDGET * 3024 / 10000) & ~15ll, STAGE_CAP = SMEM_BUDGET - 2 * BLOB_CAP;
   out->tpb = TPB;
   // (2) host: ring order of every edge column, tiles over the edge columns, list of vertex columns
   std::vector<u32> pair_cell(npairs), pair_io(npairs), pair_code(npairs), col_of_pair(npairs), vcols;
@@ -487,11 +525,12 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   std::vector<i32> nmark(nnodes + 1, -1), nlocal(nnodes + 1, 0);
   int cur_tile = 0, cur_cols = 0, cur_nodes = 0;
   i64 cur_nnz = 0, cur_pairs = 0, tile_first_col = 0, tile_node_base = 0, tile_pair_base = 0;
-  i64 max_smem = 0, blob_total16 = 0;
+  i64 max_blob = 0, max_stage = 0, blob_total16 = 0;
   bool any_end = false;
-  auto tile_smem = [](i64 cols, i64 pairs, i64 nodes, i64 nnz) {
-    return 48 * cols + (i64)pad16((u32)(8 * pairs)) + (i64)pad16((u32)(4 * pairs)) + (i64)pad16((u32)(24 * nodes)) + 8 * (nnz + 2);
+  auto tile_blob = [](i64 cols, i64 pairs, i64 nodes) {
+    return 48 + 48 * cols + (i64)pad16((u32)(8 * pairs)) + (i64)pad16((u32)(4 * pairs)) + (i64)pad16((u32)(24 * nodes));
   };
+
   auto close_tile = [&](i64 end_col) {
     if (cur_cols == 0) return;
     const i64 g0 = h_colptr[tile_first_col] - 1;
@@ -499,11 +538,12 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     h.c0 = (int)tile_first_col; h.ncol = (int)(end_col - tile_first_col); h.nnodes = cur_nodes; h.npairs = (int)cur_pairs;
     h.g0lo = (u32)(g0 & 0xffffffffll); h.g0hi = (u32)(g0 >> 32); h.nnz = (int)cur_nnz; h.blob16 = (u32)blob_total16;
     h.pair_base = (u32)tile_pair_base; h.node_base = (u32)tile_node_base;
-    h.pairs_off = 48u * (u32)h.ncol;
-    h.blob_bytes = h.pairs_off + pad16(8u * (u32)cur_pairs) + pad16(4u * (u32)cur_pairs);
+    h.pairs_off = 48u + 48u * (u32)h.ncol;
+    h.blob_bytes = (u32)tile_blob(h.ncol, cur_pairs, cur_nodes);
     hdr.push_back(h);
     blob_total16 += h.blob_bytes / 16;
-    max_smem = std::max<i64>(max_smem, tile_smem(h.ncol, cur_pairs, cur_nodes, cur_nnz));
+    max_blob = std::max<i64>(max_blob, h.blob_bytes);
+    max_stage = std::max<i64>(max_stage, 8 * (cur_nnz + 2));
     tile_node_base = (i64)tile_nodeids.size();
     cur_tile++; cur_cols = 0; cur_nodes = 0; cur_nnz = 0; cur_pairs = 0;
   };
@@ -603,8 +643,8 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     for (int attempt = 0; attempt < 2; attempt++) {
       int fresh = 0;
       for (i32 v : colnodes) if (nmark[v] != cur_tile) fresh++;
-      const i64 need = tile_smem(cur_cols + 1, cur_pairs + n, cur_nodes + fresh, cur_nnz + len);
-      if (cur_cols > 0 && (cur_cols + 1 > TPB || need > SMEM_BUDGET || cur_nodes + fresh > MAX_TILE_NODES || cur_pairs + n > 65535 || cur_nnz + len > 65535)) { close_tile(j); continue; }
+      const bool over = tile_blob(cur_cols + 1, cur_pairs + n, cur_nodes + fresh) > BLOB_CAP || 8 * (cur_nnz + len + 2) > STAGE_CAP;
+      if (cur_cols > 0 && (cur_cols + 1 > TPB || over || cur_nodes + fresh > MAX_TILE_NODES || cur_pairs + n > 65535 || cur_nnz + len > 65535)) { close_tile(j); continue; }
       if (cur_cols == 0) { tile_first_col = j; tile_pair_base = kb; }
       for (i32 v : colnodes) if (nmark[v] != cur_tile) { nmark[v] = cur_tile; nlocal[v] = cur_nodes++; tile_nodeids.push_back((u32)v); }
       for (int t = 0; t < n; t++) pair_io[kb + t] = (u32)nlocal[ring_in[t]] | ((u32)nlocal[ring_out[t]] << 12);
@@ -615,15 +655,20 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     }
   }
   close_tile(ncols);
+  const i64 max_smem = 2 * max_blob + max_stage;
   if (max_smem > 220 * 1024) return fail(GRMP_EUNSUPPORTED, "fast path: a single column exceeds the shared-memory tile");
   const int ntiles = (int)hdr.size();
   if (blob_total16 >= (i64)NONE) return fail(GRMP_EUNSUPPORTED, "fast path: record blob exceeds 64 GB");
-  out->ntiles = ntiles; out->npairs = npairs; out->smem_bytes = (int)max_smem; out->nvcols = (i64)vcols.size();
+  out->ntiles = ntiles; out->npairs = npairs; out->smem_bytes = (int)std::max<i64>(max_smem, 1024); out->in_stride = (u32)max_blob; out->nvcols = (i64)vcols.size();
   if (hdr.empty()) { TileHdr z{}; hdr.push_back(z); }
   if (tile_nodeids.empty()) tile_nodeids.push_back(1);
   if (vcols.empty()) vcols.push_back(0);
+  std::vector<uint2> tile_dir(hdr.size());
+  for (size_t t2 = 0; t2 < hdr.size(); t2++) tile_dir[t2] = make_uint2(hdr[t2].blob16, hdr[t2].blob_bytes);
+  DevBuf<u32> d_nodeids;
   GRMP_TRY(out->tile_hdr.upload(reinterpret_cast<const int4*>(hdr.data()), hdr.size() * 3, s));
-  GRMP_TRY(out->tile_nodeids.upload(tile_nodeids.data(), tile_nodeids.size(), s));
+  GRMP_TRY(out->tile_dir.upload(tile_dir.data(), tile_dir.size(), s));
+  GRMP_TRY(d_nodeids.upload(tile_nodeids.data(), tile_nodeids.size(), s));
   // (2b) spoke lists: the diagonal of a vertex column is 0.2 * sum over its spokes of the ring sums of S_vv
   std::vector<u32> spoke_cnt(ncols, 0), spoke_ptr(ncols + 1, 0);
   for (i64 j = 0; j < ncols; j++) if (endP[j] != NONE) { spoke_cnt[endP[j]]++; spoke_cnt[endQ[j]]++; }
@@ -656,6 +701,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
                 d_coltile.p, d_colpq.p, d_spokes.p, reinterpret_cast<const TileHdr*>(out->tile_hdr.p), npairs, ncols, out->blob.p, out->end_slots.p};
   if (npairs) pack_pairs<<<(unsigned)((npairs + 255) / 256), 256, 0, s>>>(pp);
   if (ncols) pack_cols<<<(unsigned)((ncols + 255) / 256), 256, 0, s>>>(pp);
+  if (ntiles) pack_tile_nodes<<<ntiles, 128, 0, s>>>(reinterpret_cast<const TileHdr*>(out->tile_hdr.p), d_nodeids.p, p.g.coords, out->blob.p);
   GRMP_CUDA(cudaGetLastError());
   // (4) vertex columns: list + diagonal slots
   GRMP_TRY(out->vcols.upload(vcols.data(), vcols.size(), s));
@@ -671,15 +717,24 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   return GRMP_OK;
 }
 
+template <int TPB> int launch_edge(const EdgeParams& ep, const FastP2Tet& f, int sm_count, cudaStream_t s) {
+  int per_sm = 0;
+  GRMP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p2tet_edge_kernel<TPB>, TPB, (size_t)f.smem_bytes));
+  if (per_sm < 1) return fail(GRMP_ECUDA, "fast path: edge kernel does not fit on an SM");
+  const int grid = std::min(f.ntiles, per_sm * sm_count);
+  p2tet_edge_kernel<TPB><<<grid, TPB, f.smem_bytes, s>>>(ep);
+  return GRMP_OK;
+}
+
 int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const FastP2Tet& f, double* nzval) {
   static const int dbg = getenv("GRMP_DEBUG_FLAGS") ? atoi(getenv("GRMP_DEBUG_FLAGS")) : 0;
   if (f.ntiles > 0) {
-    EdgeParams ep{p.g.coords, reinterpret_cast<const TileHdr*>(f.tile_hdr.p), f.blob.p, f.tile_nodeids.p, f.end_slots.p, f.dscratch.p, p.factor, nzval, dbg};
-    if (f.tpb == 64) p2tet_edge_kernel<64><<<f.ntiles, 64, f.smem_bytes, ctx->stream>>>(ep);
-    else if (f.tpb == 256) p2tet_edge_kernel<256><<<f.ntiles, 256, f.smem_bytes, ctx->stream>>>(ep);
-    else if (f.tpb == 192) p2tet_edge_kernel<192><<<f.ntiles, 192, f.smem_bytes, ctx->stream>>>(ep);
-    else if (f.tpb == 512) p2tet_edge_kernel<512><<<f.ntiles, 512, f.smem_bytes, ctx->stream>>>(ep);
-    else p2tet_edge_kernel<128><<<f.ntiles, 128, f.smem_bytes, ctx->stream>>>(ep);
+    EdgeParams ep{f.tile_dir.p, f.blob.p, f.end_slots.p, f.dscratch.p, p.factor, nzval, f.ntiles, f.in_stride, dbg};
+    if (f.tpb == 64) GRMP_TRY(launch_edge<64>(ep, f, ctx->sm_count, ctx->stream));
+    else if (f.tpb == 256) GRMP_TRY(launch_edge<256>(ep, f, ctx->sm_count, ctx->stream));
+    else if (f.tpb == 192) GRMP_TRY(launch_edge<192>(ep, f, ctx->sm_count, ctx->stream));
+    else if (f.tpb == 512) GRMP_TRY(launch_edge<512>(ep, f, ctx->sm_count, ctx->stream));
+    else GRMP_TRY(launch_edge<128>(ep, f, ctx->sm_count, ctx->stream));
     GRMP_CUDA(cudaGetLastError());
   }
   if (f.nvcols > 0 && !(dbg & 2)) {
