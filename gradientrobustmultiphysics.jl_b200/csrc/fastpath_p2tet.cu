@@ -18,10 +18,13 @@
 //     tile's node coordinates in shared memory) and one cross product a x (c - p) is carried
 //     (the affine pullback of feevaluator_h1.jl:61-74 reduced to the five off-diagonal
 //     invariants S_pq, S_pi, S_po, S_qi, S_qo; the diagonal ones follow from the zero row sums).
-//     A tile = TPB consecutive edge columns.  Its column and pair records form one contiguous
-//     blob that a single TMA bulk load (cp.async.bulk + mbarrier) brings into shared memory;
-//     the tile's contiguous nzval range is staged in shared memory and written with one TMA
-//     bulk store.
+//     A tile = up to NW groups of up to 32 consecutive edge columns, one group per consumer warp.
+//     Its header, column / pair records and node coordinates form one contiguous blob that a
+//     single TMA bulk load (cp.async.bulk + mbarrier) brings into shared memory.  CTAs are
+//     persistent: a producer warp keeps a 2-deep ring of input blobs filled (full/empty
+//     mbarriers), the consumer warps never meet at a CTA-wide barrier.  Every warp stages the
+//     contiguous nzval range of its group in its own shared-memory slot and writes it with its
+//     own TMA bulk store, which overlaps the ring walk of its next group.
 //   VERTEX columns need no work of their own: the matrix of this form is symmetric, so every
 //     off-diagonal entry (i, v_a) is the mirror image of an entry (v_a, i) that an edge thread
 //     has in a register anyway (i an edge dof), or the ring sum -0.2*sum S_pq of the edge (a b)
@@ -34,6 +37,7 @@
 // comes from the bit-exact symbolic pass, and slots are looked up in it by (row, column).
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 
 #include "fastpath.cuh"
@@ -42,9 +46,10 @@ namespace grmp {
 
 namespace {
 
-constexpr int TPB_DEFAULT = 256;                  // threads (= edge columns) per tile
+constexpr int NW_DEFAULT = 7;                     // consumer warps per CTA (+ 1 producer warp)
+constexpr int SLOT_DEFAULT = 800;                 // nzval entries a warp may stage per group (32 columns x ~23 rows)
 // shared memory per CTA (2 input buffers + output stage) such that 2 / 3 / 5 CTAs of 256 / 192 / 128 threads fit on an SM
-__host__ inline i64 smem_budget_default(int tpb) { return 1024 * (i64)(tpb >= 512 ? 224 : tpb >= 256 ? 112 : tpb >= 192 ? 74 : tpb >= 128 ? 44 : 21); }
+__host__ inline i64 smem_budget_default(int nw) { return 1024 * (i64)(nw >= 5 ? 112 : nw == 4 ? 74 : 55); }   // 2 / 3 / 4 CTAs per SM
 constexpr u32 NONE = 0xffffffffu;
 constexpr int MAX_TILE_NODES = 4095;              // 12-bit tile-local node ids
 
@@ -60,12 +65,12 @@ __host__ __device__ inline int edge_of(int a, int b) {   // local edge dof index
 
 // ---- records ---------------------------------------------------------------------------------
 // tile blob (global, contiguous per tile, 16-byte aligned sections; one TMA bulk load):
-//   tile header 48 B: see TileHdr
+//   tile header 48 B: see TileHdr;  group table (NW+1) x {first column (tile-local), first nzval slot (relative to g0)}
 //   column records  48 B x ncol
 //     a.x : tile-local node of P | Q << 12 | #pairs << 24
 //     a.y : slot offsets inside the column of rows v_P, v_Q, e_PQ (255 = not in the pattern) | flags << 24 (bit 0: closed ring)
 //     a.z : closing offsets (closed: rows of the first pair's in-vertex; open: rows of the last pair's out-vertex)
-//     a.w : column start inside the tile's nzval range | first pair (tile-local) << 16
+//     a.w : column start inside the group's nzval range | first pair (tile-local) << 16
 //     b.x, b.y, b.z : mirrored slots (global nzval index or NONE) of row e_PQ in columns v_P, v_Q, v_closing
 //     b.w, c.x : slots of (row v_Q, col v_P) and (row v_P, col v_Q)
 //     c.y, c.z : scratch slots of this edge in the spoke lists of v_P, v_Q
@@ -81,6 +86,7 @@ struct __align__(16) TileHdr {
   int c0, ncol, nnodes, npairs;          // first column, #columns, #distinct nodes, #pairs
   u32 g0lo, g0hi; int nnz; u32 blob16;   // first nzval slot, #slots, blob offset in 16-byte units
   u32 pair_base, node_base, blob_bytes, pairs_off;   // global index of the first pair / node-list entry; blob size; byte offset of the pair records
+  // byte offset of the column records = pairs_off - 48 * ncol
 };
 static_assert(sizeof(TileHdr) == 48, "TileHdr layout");
 
@@ -98,6 +104,7 @@ struct PackParams {
   const unsigned char* col_closed;   // 0 open chain(s), 1 closed ring, 2 not an edge column
   const u32* col_tile;      // tile of every edge column
   const u32* col_pq;        // tile-local node of P | Q << 12
+  const u32* col_abase;     // first slot of the column relative to its group
   const uint2* spokes;      // per column: scratch slots in the spoke lists of v_P, v_Q
   const TileHdr* hdr;
   i64 npairs, ncols;
@@ -151,7 +158,6 @@ __global__ void pack_cols(PackParams p) {
   if (p.col_closed[j] == 2) return;     // not an edge column
   const i64 kb = p.col_pairbeg[j], ke = p.col_pairbeg[j + 1];
   const TileHdr h = p.hdr[p.col_tile[j]];
-  const i64 g0 = (i64)h.g0lo | ((i64)h.g0hi << 32);
   const bool closed = p.col_closed[j] == 1;
   // reference orientation (P,Q) = first ring pair
   const u32 c0 = p.pair_code[kb];
@@ -167,22 +173,23 @@ __global__ void pack_cols(PackParams p) {
   a.x = (p.col_pq[j] & 0xffffffu) | ((u32)(ke - kb) << 24);
   a.y = off8(find_slot(p, vP, j)) | (off8(find_slot(p, vQ, j)) << 8) | (off8(find_slot(p, j, j)) << 16) | ((closed ? 1u : 0u) << 24);
   a.z = off8(find_slot(p, vC, j)) | (off8(find_slot(p, dc[edge_of(Pc, Vc)] - 1, j)) << 8) | (off8(find_slot(p, dc[edge_of(Qc, Vc)] - 1, j)) << 16);
-  a.w = (u32)(p.colptr[j] - 1 - g0) | ((u32)(kb - (i64)h.pair_base) << 16);
+  a.w = (p.col_abase[j] & 0xffffu) | ((u32)(kb - (i64)h.pair_base) << 16);
   b.x = gslot(p, j, vP);
   b.y = gslot(p, j, vQ);
   b.z = gslot(p, j, vC);
   b.w = gslot(p, vQ, vP);
   c.x = gslot(p, vP, vQ);
   c.y = p.spokes[j].x; c.z = p.spokes[j].y; c.w = 0;
-  uint4* dst = reinterpret_cast<uint4*>(p.blob + (size_t)h.blob16 * 16 + 48) + 3 * (j - h.c0);
+  uint4* dst = reinterpret_cast<uint4*>(p.blob + (size_t)h.blob16 * 16 + (h.pairs_off - 48u * (u32)h.ncol)) + 3 * (j - h.c0);
   dst[0] = a; dst[1] = b; dst[2] = c;
 }
 
 // one block per tile: header and node coordinates into the blob
-__global__ void pack_tile_nodes(const TileHdr* hdr, const u32* tile_nodeids, const double* coords, unsigned char* blob) {
+__global__ void pack_tile_nodes(const TileHdr* hdr, const uint2* groups, int nw, const u32* tile_nodeids, const double* coords, unsigned char* blob) {
   const TileHdr h = hdr[blockIdx.x];
   unsigned char* tb = blob + (size_t)h.blob16 * 16;
   if (threadIdx.x < 3) reinterpret_cast<int4*>(tb)[threadIdx.x] = reinterpret_cast<const int4*>(hdr + blockIdx.x)[threadIdx.x];
+  if ((int)threadIdx.x <= nw) reinterpret_cast<uint2*>(tb + 48)[threadIdx.x] = groups[(size_t)blockIdx.x * (nw + 1) + threadIdx.x];
   double* X = reinterpret_cast<double*>(tb + h.pairs_off + pad16(8u * (u32)h.npairs) + pad16(4u * (u32)h.npairs));
   for (int i = threadIdx.x; i < h.nnodes; i += blockDim.x) {
     const double* xg = coords + (size_t)(tile_nodeids[(size_t)h.node_base + i] - 1) * 3;
@@ -197,8 +204,10 @@ struct EdgeParams {
   double* dscratch;         // [sum of spoke counts] 0.2 * ring sum of S_vv per (vertex, spoke)
   double factor;
   double* nzval;
+  int* tile_counter;        // dynamic tile scheduler: next unclaimed tile (zero at launch; reset by the diagonal kernel)
   int ntiles;
   u32 in_stride;            // bytes of one input buffer (largest blob)
+  u32 slot_elems;           // doubles per warp stage slot
   int dbg;                  // GRMP_DEBUG_FLAGS (timing experiments only): 1 skip mirrored stores, 4 skip the ring walk, 8 skip the bulk store
 };
 
@@ -212,11 +221,29 @@ __device__ __forceinline__ double fast_rcp(double d) {   // 1/d to ~1 ulp for no
   return r;
 }
 
-__device__ __forceinline__ void tile_load(const EdgeParams& p, uint2 dir, unsigned dst_smem, unsigned mbar_a) {
+__device__ __forceinline__ u64 l2_policy_evict_first() {
+  u64 pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ u64 l2_policy_evict_last() {
+  u64 pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_hint(double* ptr, double v, u64 pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(ptr), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tile_load(const EdgeParams& p, uint2 dir, unsigned dst_smem, unsigned mbar_a, u64 pol) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(dir.y) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
-               "l"(p.blob + (size_t)dir.x * 16), "r"(dir.y), "r"(mbar_a)
-               : "memory");
+  if (p.dbg & 32)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(p.blob + (size_t)dir.x * 16), "r"(dir.y), "r"(mbar_a)
+                 : "memory");
+  else
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+                 "l"(p.blob + (size_t)dir.x * 16), "r"(dir.y), "r"(mbar_a), "l"(pol)
+                 : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned mbar_a, unsigned parity) {
   asm volatile(
@@ -231,56 +258,90 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar_a, unsigned parity) {
       : "memory");
 }
 
-// Persistent CTAs: CTA b walks tiles b, b + gridDim.x, ...  The inputs of a tile (header, records, node coordinates: one
-// contiguous blob) are prefetched two tiles ahead by TMA bulk loads into a 2-deep shared-memory ring, the output range is
-// staged in shared memory and leaves through a TMA bulk store that overlaps the next tile's ring walk.
-template <int TPB>
-__global__ void __launch_bounds__(TPB, (TPB <= 64 ? 10 : TPB <= 128 ? 5 : TPB <= 192 ? 3 : TPB <= 256 ? 2 : 1)) p2tet_edge_kernel(const EdgeParams p) {
+// Persistent CTAs of NW consumer warps + 1 producer warp: CTA b walks tiles b, b + gridDim.x, ...  The producer keeps the
+// 2-deep input ring filled (TMA bulk loads, full[]/empty[] mbarriers); consumer warp w owns group w of every tile, stages the
+// group's nzval range in its own slot and stores it with its own TMA bulk store.  No CTA-wide barrier after the set-up.
+template <int NW>
+__global__ void __launch_bounds__((NW + 1) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 : 4)) p2tet_edge_kernel(const EdgeParams p) {
   extern __shared__ __align__(128) unsigned char smraw[];
-  __shared__ __align__(8) unsigned long long mbar[2];
-  const int tid = threadIdx.x;
-  const unsigned mbar_a = (unsigned)__cvta_generic_to_shared(&mbar[0]);
+  __shared__ __align__(8) unsigned long long mbar[4];      // full[0], full[1], empty[0], empty[1]
+  __shared__ int s_tile[2];                                // tile in each input buffer, -1 = no more tiles
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned full_a = (unsigned)__cvta_generic_to_shared(&mbar[0]), empty_a = full_a + 16;
   const unsigned in_a = (unsigned)__cvta_generic_to_shared(smraw);
-  double* const stage_base = reinterpret_cast<double*>(smraw + 2 * (size_t)p.in_stride);
   const int G = gridDim.x;
-  int t = blockIdx.x;
-  uint2 dir_next = make_uint2(0, 0);       // thread 0: directory entry of the tile two steps ahead
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a + 8));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_a));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_a + 8));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_a), "r"(NW));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_a + 8), "r"(NW));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if (t < p.ntiles) tile_load(p, __ldg(p.tile_dir + t), in_a, mbar_a);
-    if (t + G < p.ntiles) tile_load(p, __ldg(p.tile_dir + t + G), in_a + p.in_stride, mbar_a + 8);
-    if (t + 2 * G < p.ntiles) dir_next = __ldg(p.tile_dir + t + 2 * G);
   }
   __syncthreads();
-  for (int it = 0; t < p.ntiles; t += G, it++) {
+  if (warp == NW) {   // ---- producer ----
+    if (lane == 0) {
+      const u64 pol_stream = l2_policy_evict_first();
+      for (int it = 0;; it++) {
+        const int b = it & 1;
+        // tiles are claimed dynamically (SMs do not run at the same speed; a static split leaves the slowest SM as the tail)
+        const int t = (p.dbg & 1024) ? (int)blockIdx.x + it * G : atomicAdd(p.tile_counter, 1);
+        uint2 dir = make_uint2(0, 0);
+        if (t < p.ntiles) dir = __ldg(p.tile_dir + t);
+        if (it >= 2) mbar_wait(empty_a + 8 * b, (unsigned)((it >> 1) - 1) & 1u);   // all consumer warps released the buffer
+        if (t >= p.ntiles) {
+          if (p.dbg & 2048) { unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); printf("CTA %d sm %u tiles %d\n", (int)blockIdx.x, smid, it); }
+          s_tile[b] = -1;
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_a + 8 * b) : "memory");
+          break;
+        }
+        s_tile[b] = t;
+        tile_load(p, dir, in_a + b * p.in_stride, full_a + 8 * b, pol_stream);
+      }
+    }
+    return;
+  }
+  // ---- consumers ----
+  const u64 pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+  double* const slot = reinterpret_cast<double*>(smraw + 2 * (size_t)p.in_stride) + (size_t)warp * p.slot_elems;
+  for (int it = 0;; it++) {
     const int cur = it & 1;
-    const unsigned char* __restrict__ in = smraw + (size_t)cur * p.in_stride;
-    mbar_wait(mbar_a + 8 * cur, (unsigned)(it >> 1) & 1u);
+    const unsigned char* in = smraw + (size_t)cur * p.in_stride;
+    mbar_wait(full_a + 8 * cur, (unsigned)(it >> 1) & 1u);
+    if (*reinterpret_cast<volatile int*>(&s_tile[cur]) < 0) break;
     const int4 h0 = reinterpret_cast<const int4*>(in)[0], h1 = reinterpret_cast<const int4*>(in)[1], h2 = reinterpret_cast<const int4*>(in)[2];
-    const int ncol = h0.y;
-    const i64 g0 = (i64)(u32)h1.x | ((i64)h1.y << 32);
-    const int nnz_t = h1.z;
-    const u32 pairs_off = (u32)h2.w, mir_off = pairs_off + pad16(8u * (u32)h0.w), xyz_off = mir_off + pad16(4u * (u32)h0.w);
+    const uint2 gr0 = reinterpret_cast<const uint2*>(in + 48)[warp], gr1 = reinterpret_cast<const uint2*>(in + 48)[warp + 1];
+    const int col = (int)gr0.x + lane;                      // tile-local column of this lane
+    const bool has_col = col < (int)gr1.x;
+    const i64 g0 = ((i64)(u32)h1.x | ((i64)h1.y << 32)) + gr0.y;   // first nzval slot of the group
+    const int nnz_w = (int)(gr1.y - gr0.y);
+    const u32 pairs_off = (u32)h2.w, cols_off = pairs_off - 48u * (u32)h0.y;
+    const u32 mir_off = pairs_off + pad16(8u * (u32)h0.w), xyz_off = mir_off + pad16(4u * (u32)h0.w);
     const double* __restrict__ X = reinterpret_cast<const double*>(in + xyz_off);
     // stage[i] mirrors nzval[g0 + i]; it is shifted by one element when g0 is odd so that shared and global addresses of the
     // same element are 16-byte aligned together (TMA bulk store).  Every slot is written exactly once -> no zero-init.
     const int odd = (int)(g0 & 1);
-    double* __restrict__ stage = stage_base + odd;
-    // the previous tile's bulk store must have finished reading the stage before it is overwritten
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    __syncthreads();
-    if (tid < ncol && !(p.dbg & 4)) {
-      const uint4* cr = reinterpret_cast<const uint4*>(in + 48) + 3 * tid;
-      const uint4 ca = cr[0], cb = cr[1], cc = cr[2];
-      const u32 np = ca.x >> 24;
+    double* __restrict__ stage = slot + odd;
+    // this warp's previous bulk store must have finished reading the slot before it is overwritten
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+    // mirrored values leave through ordinary scattered stores.  They are issued AFTER the bulk store of the group: the
+    // proxy fence in front of the bulk store waits for the warp's outstanding global stores, so stores issued inside the
+    // ring walk would put a full store round trip into every tile.  Ring values (e_PQ, v_in) are parked in the shared-memory
+    // slot of their already consumed pair record, the column values stay in registers.
+    uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, cc = ca;
+    u32 np = 0;
+    bool closed = false;
+    double mA = 0.0, mB = 0.0, mW = 0.0, mq0 = 0.0, mTp = 0.0, mTq = 0.0;
+    if (has_col && !(p.dbg & 4)) {
+      const uint4* cr = reinterpret_cast<const uint4*>(in + cols_off) + 3 * col;
+      ca = cr[0]; cb = cr[1]; cc = cr[2];
+      np = ca.x >> 24;
       if (np > 0) {
-        const uint2* __restrict__ prec = reinterpret_cast<const uint2*>(in + pairs_off) + (ca.w >> 16);
-        const u32* __restrict__ pmir = reinterpret_cast<const u32*>(in + mir_off) + (ca.w >> 16);
+        const uint2* prec = reinterpret_cast<const uint2*>(in + pairs_off) + (ca.w >> 16);
+        double* park = reinterpret_cast<double*>(const_cast<unsigned char*>(in) + pairs_off) + (ca.w >> 16);
         double* __restrict__ a = stage + (ca.w & 0xffffu);
-        const bool closed = (ca.y >> 24) & 1u;
+        closed = (ca.y >> 24) & 1u;
         const u32 lp = ca.x & 0xfffu, lq = (ca.x >> 12) & 0xfffu;
         const double px = X[3 * lp], py = X[3 * lp + 1], pz = X[3 * lp + 2];
         const double ax = X[3 * lq] - px, ay = X[3 * lq + 1] - py, az = X[3 * lq + 2] - pz;
@@ -306,7 +367,6 @@ __global__ void __launch_bounds__(TPB, (TPB <= 64 ? 10 : TPB <= 128 ? 5 : TPB <=
           const u32 ln = (r1.y >> 12) & 0xfffu;
           const double nx = X[3 * ln], ny = X[3 * ln + 1], nz = X[3 * ln + 2];
           const uint2 r2 = prec[k + 2 < np ? k + 2 : np - 1];
-          const u32 pm = pmir[k];
           const u32 fl = r0.y >> 24;
           if (fl & PF_RESET) {
             const u32 li = r0.y & 0xfffu;
@@ -349,7 +409,7 @@ __global__ void __launch_bounds__(TPB, (TPB <= 64 ? 10 : TPB <= 128 ? 5 : TPB <=
             if (o0 != 255u) a[o0] = in0;
             if (o1 != 255u) a[o1] = in1;
             if (o2 != 255u) a[o2] = in2;
-            if (pm != NONE && !(p.dbg & 1)) p.nzval[pm] = in0;             // mirror (e_PQ, v_in)
+            park[k] = in0;                                                 // mirror (e_PQ, v_in), stored after the bulk store
           }
           bx = ex; by = ey; bz = ez; mcx = mdx; mcy = mdy; mcz = mdz;
           ox = nx; oy = ny; oz = nz;
@@ -362,7 +422,7 @@ __global__ void __launch_bounds__(TPB, (TPB <= 64 ? 10 : TPB <= 128 ? 5 : TPB <=
           if (o0 != 255u) a[o0] = q0;
           if (o1 != 255u) a[o1] = q1;
           if (o2 != 255u) a[o2] = q2;
-          if (cb.z != NONE && !(p.dbg & 1)) p.nzval[cb.z] = q0;
+          mq0 = q0;
         }
         {
           // rows v_P, v_Q, e_PQ and the (v_P, v_Q) coupling from the ring sums (S'_pp = -(S'_pq + S'_pi + S'_po)):
@@ -372,48 +432,68 @@ __global__ void __launch_bounds__(TPB, (TPB <= 64 ? 10 : TPB <= 128 ? 5 : TPB <=
           if (oA != 255u) a[oA] = A;
           if (oB != 255u) a[oB] = B;
           if (oC != 255u) a[oC] = C;
-          if (!(p.dbg & 1)) {
-            if (cb.x != NONE) p.nzval[cb.x] = A;       // (e_PQ, v_P)
-            if (cb.y != NONE) p.nzval[cb.y] = B;       // (e_PQ, v_Q)
-            if (cb.w != NONE) p.nzval[cb.w] = W;       // (v_Q, v_P)
-            if (cc.x != NONE) p.nzval[cc.x] = W;       // (v_P, v_Q)
-          }
-          if (cc.y != NONE) p.dscratch[cc.y] = -0.25 * (R1 + R2);   // 0.2 * ring sum of S_pp
-          if (cc.z != NONE) p.dscratch[cc.z] = -0.25 * (R1 + R3);   // 0.2 * ring sum of S_qq
+          mA = A; mB = B; mW = W;
+          mTp = -0.25 * (R1 + R2);                     // 0.2 * ring sum of S_pp
+          mTq = -0.25 * (R1 + R3);                     // 0.2 * ring sum of S_qq
         }
       }
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // stage writes -> visible to the bulk store
-    __syncthreads();
+    if (!(p.dbg & 256)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // stage writes -> visible to the bulk store
+    __syncwarp();
     {
-      // the tile's nzval range is contiguous: one TMA bulk store (cp.async.bulk shared -> global) of the 16-byte aligned
+      // the group's nzval range is contiguous: one TMA bulk store (cp.async.bulk shared -> global) of the 16-byte aligned
       // body, the (at most one) unaligned element at either end by ordinary stores
       double* __restrict__ dst = p.nzval + g0;
       const int i0 = odd;                                   // first element whose address is 16-byte aligned
-      const int nb = (nnz_t > i0) ? ((nnz_t - i0) & ~1) : 0;  // elements in the bulk body
-      if (tid == 0) {
-        if (nb > 0 && !(p.dbg & 8)) {
-          const unsigned src = (unsigned)__cvta_generic_to_shared(stage + i0);
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + i0), "r"(src), "r"(nb * 8) : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      const int nb = (nnz_w > i0) ? ((nnz_w - i0) & ~1) : 0;  // elements in the bulk body
+      if (lane == 0 && nb > 0 && !(p.dbg & 8)) {
+        const unsigned src = (unsigned)__cvta_generic_to_shared(stage + i0);
+        if (p.dbg & 64) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + i0), "r"(src), "r"(nb * 8) : "memory");
+        else asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst + i0), "r"(src), "r"(nb * 8), "l"(pol_stream) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (lane == 1 && i0 == 1 && nnz_w > 0) dst[0] = stage[0];
+      if (lane == 2 && i0 + nb < nnz_w) dst[i0 + nb] = stage[i0 + nb];
+    }
+    if (np > 0) {
+      if (!(p.dbg & 1)) {
+        const u32* __restrict__ pmir = reinterpret_cast<const u32*>(in + mir_off) + (ca.w >> 16);
+        const double* park = reinterpret_cast<const double*>(in + pairs_off) + (ca.w >> 16);
+        for (u32 k = closed ? 1u : 0u; k < np; k++) {
+          const u32 pm = pmir[k];
+          if (pm != NONE) { if (p.dbg & 128) p.nzval[pm] = park[k]; else st_hint(p.nzval + pm, park[k], pol_keep); }   // (e_PQ, v_in)
         }
-        // this input buffer is free again (everybody passed the barrier): prefetch the tile two steps ahead into it
-        if (t + 2 * G < p.ntiles) {
-          tile_load(p, dir_next, in_a + cur * p.in_stride, mbar_a + 8 * cur);
-          if (t + 3 * G < p.ntiles) dir_next = __ldg(p.tile_dir + t + 3 * G);
+        if (p.dbg & 128) {
+          if (cb.z != NONE) p.nzval[cb.z] = mq0;         // (e_PQ, v_closing)
+          if (cb.x != NONE) p.nzval[cb.x] = mA;          // (e_PQ, v_P)
+          if (cb.y != NONE) p.nzval[cb.y] = mB;          // (e_PQ, v_Q)
+          if (cb.w != NONE) p.nzval[cb.w] = mW;          // (v_Q, v_P)
+          if (cc.x != NONE) p.nzval[cc.x] = mW;          // (v_P, v_Q)
+        } else {
+          if (cb.z != NONE) st_hint(p.nzval + cb.z, mq0, pol_keep);
+          if (cb.x != NONE) st_hint(p.nzval + cb.x, mA, pol_keep);
+          if (cb.y != NONE) st_hint(p.nzval + cb.y, mB, pol_keep);
+          if (cb.w != NONE) st_hint(p.nzval + cb.w, mW, pol_keep);
+          if (cc.x != NONE) st_hint(p.nzval + cc.x, mW, pol_keep);
         }
       }
-      if (tid == 1 && i0 == 1 && nnz_t > 0) dst[0] = stage[0];
-      if (tid == 2 && i0 + nb < nnz_t) dst[i0 + nb] = stage[i0 + nb];
+      if (cc.y != NONE) p.dscratch[cc.y] = mTp;
+      if (cc.z != NONE) p.dscratch[cc.z] = mTq;
+    }
+    __syncwarp();                                            // every lane is done with this input buffer
+    if (lane == 0) {
+      if (p.dbg & 512) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_a + 8 * cur) : "memory");
+      else asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(empty_a + 8 * cur) : "memory");
     }
   }
-  if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must stay alive until read
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must stay alive until read
 }
 
 // A[v,v] = 0.6 * sum_{K containing v} S_vv = 0.2 * sum over the spokes (v w) of the ring sums of S_vv (every cell at v
 // has three edges at v); the spoke values were left in dscratch by the edge threads.  Fixed order -> deterministic.
-__global__ void p2tet_vertex_diag_kernel(const uint4* vrec, i64 nv, const double* __restrict__ dscratch, double* nzval) {
+__global__ void p2tet_vertex_diag_kernel(const uint4* vrec, i64 nv, const double* __restrict__ dscratch, double* nzval, int* tile_counter) {
   const i64 w = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (w == 0) *tile_counter = 0;           // re-arm the edge kernel's tile scheduler for the next assembly
   if (w >= nv) return;
   const uint4 r = vrec[w];                 // {diagonal slot | NONE, first spoke slot, #spokes, 0}
   if (r.x == NONE) return;
@@ -459,8 +539,8 @@ void reference_local_closed_form(double K[10][10]) {
   }
 }
 
-template <int TPB> int set_smem_attr(int bytes) {
-  GRMP_CUDA(cudaFuncSetAttribute(p2tet_edge_kernel<TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+template <int NW> int set_smem_attr(int bytes) {
+  GRMP_CUDA(cudaFuncSetAttribute(p2tet_edge_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   return GRMP_OK;
 }
 
@@ -508,13 +588,16 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   GRMP_CUDA(cudaMemcpyAsync(h_cn.data(), p.g.cellnodes, (size_t)ncells * 16, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaMemcpyAsync(h_dofs.data(), p.e1.celldofs, (size_t)ncells * 40, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaStreamSynchronize(s));
-  // tile shape (tunable for experiments: GRMP_FAST_TPB in {64,128,192,256,512}, GRMP_FAST_SMEM_KB)
-  int TPB = getenv("GRMP_FAST_TPB") ? atoi(getenv("GRMP_FAST_TPB")) : TPB_DEFAULT;
-  if (TPB != 64 && TPB != 128 && TPB != 192 && TPB != 256 && TPB != 512) TPB = TPB_DEFAULT;
-  const i64 SMEM_BUDGET = getenv("GRMP_FAST_SMEM_KB") ? 1024 * (i64)atoi(getenv("GRMP_FAST_SMEM_KB")) : smem_budget_default(TPB);
-  // separate caps for the input blob and the output stage (typical ratio 1 : 1.3), so that 2 * max blob + max stage stays inside the budget
-  const i64 BLOB_CAP = (SMEM_BUDGET * 3024 / 10000) & ~15ll, STAGE_CAP = SMEM_BUDGET - 2 * BLOB_CAP;
-  out->tpb = TPB;
+  // tile shape (tunable for experiments: GRMP_FAST_NW in 3..7, GRMP_FAST_SLOT, GRMP_FAST_SMEM_KB)
+  int NW = getenv("GRMP_FAST_NW") ? atoi(getenv("GRMP_FAST_NW")) : NW_DEFAULT;
+  if (NW < 3 || NW > 7) NW = NW_DEFAULT;
+  const i64 SLOT_CAP = getenv("GRMP_FAST_SLOT") ? std::max(256, atoi(getenv("GRMP_FAST_SLOT"))) : SLOT_DEFAULT;   // nzval entries per group
+  const i64 SMEM_BUDGET = getenv("GRMP_FAST_SMEM_KB") ? 1024 * (i64)atoi(getenv("GRMP_FAST_SMEM_KB")) : smem_budget_default(NW);
+  // shared memory of a CTA: 2 input buffers (largest blob) + NW stage slots
+  const i64 BLOB_CAP = ((SMEM_BUDGET - NW * 8 * (SLOT_CAP + 2)) / 2) & ~15ll;
+  if (BLOB_CAP < 4096) return fail(GRMP_EUNSUPPORTED, "fast path: shared-memory budget too small for the tile shape");
+  const u32 hdr_bytes = 48u + pad16(8u * (u32)(NW + 1));
+  out->nw = NW;
   // (2) host: ring order of every edge column, tiles over the edge columns, list of vertex columns
   std::vector<u32> pair_cell(npairs), pair_io(npairs), pair_code(npairs), col_of_pair(npairs), vcols;
   std::vector<unsigned char> col_closed(ncols, 2);
@@ -523,12 +606,17 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   std::vector<TileHdr> hdr;
   std::vector<u32> tile_nodeids;
   std::vector<i32> nmark(nnodes + 1, -1), nlocal(nnodes + 1, 0);
+  std::vector<u32> col_abase(ncols, 0);
+  std::vector<uint2> groups;                    // (NW+1) per tile: first column (tile-local), first slot (relative to g0)
   int cur_tile = 0, cur_cols = 0, cur_nodes = 0;
+  int cur_groups = 0, grp_cols = 0;             // closed groups of the open tile; columns / slots of the open group
+  i64 grp_nnz = 0;
+  uint2 cur_grp[9];
   i64 cur_nnz = 0, cur_pairs = 0, tile_first_col = 0, tile_node_base = 0, tile_pair_base = 0;
-  i64 max_blob = 0, max_stage = 0, blob_total16 = 0;
+  i64 max_blob = 0, max_slot = 0, blob_total16 = 0;
   bool any_end = false;
-  auto tile_blob = [](i64 cols, i64 pairs, i64 nodes) {
-    return 48 + 48 * cols + (i64)pad16((u32)(8 * pairs)) + (i64)pad16((u32)(4 * pairs)) + (i64)pad16((u32)(24 * nodes));
+  auto tile_blob = [&](i64 cols, i64 pairs, i64 nodes) {
+    return (i64)hdr_bytes + 48 * cols + (i64)pad16((u32)(8 * pairs)) + (i64)pad16((u32)(4 * pairs)) + (i64)pad16((u32)(24 * nodes));
   };
 
   auto close_tile = [&](i64 end_col) {
@@ -538,12 +626,15 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     h.c0 = (int)tile_first_col; h.ncol = (int)(end_col - tile_first_col); h.nnodes = cur_nodes; h.npairs = (int)cur_pairs;
     h.g0lo = (u32)(g0 & 0xffffffffll); h.g0hi = (u32)(g0 >> 32); h.nnz = (int)cur_nnz; h.blob16 = (u32)blob_total16;
     h.pair_base = (u32)tile_pair_base; h.node_base = (u32)tile_node_base;
-    h.pairs_off = 48u + 48u * (u32)h.ncol;
+    h.pairs_off = hdr_bytes + 48u * (u32)h.ncol;
     h.blob_bytes = (u32)tile_blob(h.ncol, cur_pairs, cur_nodes);
     hdr.push_back(h);
     blob_total16 += h.blob_bytes / 16;
     max_blob = std::max<i64>(max_blob, h.blob_bytes);
-    max_stage = std::max<i64>(max_stage, 8 * (cur_nnz + 2));
+    if (grp_cols > 0) { max_slot = std::max<i64>(max_slot, grp_nnz); cur_groups++; }
+    for (int w2 = cur_groups; w2 <= NW; w2++) cur_grp[w2] = make_uint2((u32)h.ncol, (u32)cur_nnz);   // empty trailing groups
+    for (int w2 = 0; w2 <= NW; w2++) groups.push_back(cur_grp[w2]);
+    cur_groups = 0; grp_cols = 0; grp_nnz = 0;
     tile_node_base = (i64)tile_nodeids.size();
     cur_tile++; cur_cols = 0; cur_nodes = 0; cur_nnz = 0; cur_pairs = 0;
   };
@@ -643,9 +734,15 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     for (int attempt = 0; attempt < 2; attempt++) {
       int fresh = 0;
       for (i32 v : colnodes) if (nmark[v] != cur_tile) fresh++;
-      const bool over = tile_blob(cur_cols + 1, cur_pairs + n, cur_nodes + fresh) > BLOB_CAP || 8 * (cur_nnz + len + 2) > STAGE_CAP;
-      if (cur_cols > 0 && (cur_cols + 1 > TPB || over || cur_nodes + fresh > MAX_TILE_NODES || cur_pairs + n > 65535 || cur_nnz + len > 65535)) { close_tile(j); continue; }
+      const bool over = tile_blob(cur_cols + 1, cur_pairs + n, cur_nodes + fresh) > BLOB_CAP;
+      const bool grp_full = grp_cols > 0 && (grp_cols == 32 || grp_nnz + len > SLOT_CAP);   // the column would open a new group
+      if (cur_cols > 0 && ((grp_full && cur_groups + 1 >= NW) || over || cur_nodes + fresh > MAX_TILE_NODES || cur_pairs + n > 65535)) { close_tile(j); continue; }
+      if (len > SLOT_CAP) return fail(GRMP_EUNSUPPORTED, "fast path: a single column exceeds the stage slot");
       if (cur_cols == 0) { tile_first_col = j; tile_pair_base = kb; }
+      if (grp_full) { max_slot = std::max<i64>(max_slot, grp_nnz); cur_groups++; grp_cols = 0; grp_nnz = 0; }
+      if (grp_cols == 0) cur_grp[cur_groups] = make_uint2((u32)cur_cols, (u32)cur_nnz);
+      col_abase[j] = (u32)grp_nnz;
+      grp_cols++; grp_nnz += len;
       for (i32 v : colnodes) if (nmark[v] != cur_tile) { nmark[v] = cur_tile; nlocal[v] = cur_nodes++; tile_nodeids.push_back((u32)v); }
       for (int t = 0; t < n; t++) pair_io[kb + t] = (u32)nlocal[ring_in[t]] | ((u32)nlocal[ring_out[t]] << 12);
       col_pq[j] = (u32)nlocal[P0] | ((u32)nlocal[Q0] << 12);
@@ -655,17 +752,20 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     }
   }
   close_tile(ncols);
-  const i64 max_smem = 2 * max_blob + max_stage;
+  const i64 slot_elems = (max_slot + 2 + 1) & ~1ll;     // even: keeps every slot 16-byte aligned
+  const i64 max_smem = 2 * max_blob + NW * 8 * slot_elems;
   if (max_smem > 220 * 1024) return fail(GRMP_EUNSUPPORTED, "fast path: a single column exceeds the shared-memory tile");
   const int ntiles = (int)hdr.size();
   if (blob_total16 >= (i64)NONE) return fail(GRMP_EUNSUPPORTED, "fast path: record blob exceeds 64 GB");
-  out->ntiles = ntiles; out->npairs = npairs; out->smem_bytes = (int)std::max<i64>(max_smem, 1024); out->in_stride = (u32)max_blob; out->nvcols = (i64)vcols.size();
-  if (hdr.empty()) { TileHdr z{}; hdr.push_back(z); }
+  out->ntiles = ntiles; out->npairs = npairs; out->smem_bytes = (int)std::max<i64>(max_smem, 1024); out->in_stride = (u32)max_blob; out->slot_elems = (u32)slot_elems; out->nvcols = (i64)vcols.size();
+  if (hdr.empty()) { TileHdr z{}; hdr.push_back(z); groups.assign(NW + 1, make_uint2(0, 0)); }
   if (tile_nodeids.empty()) tile_nodeids.push_back(1);
   if (vcols.empty()) vcols.push_back(0);
   std::vector<uint2> tile_dir(hdr.size());
   for (size_t t2 = 0; t2 < hdr.size(); t2++) tile_dir[t2] = make_uint2(hdr[t2].blob16, hdr[t2].blob_bytes);
   DevBuf<u32> d_nodeids;
+  DevBuf<uint2> d_groups;
+  GRMP_TRY(d_groups.upload(groups.data(), groups.size(), s));
   GRMP_TRY(out->tile_hdr.upload(reinterpret_cast<const int4*>(hdr.data()), hdr.size() * 3, s));
   GRMP_TRY(out->tile_dir.upload(tile_dir.data(), tile_dir.size(), s));
   GRMP_TRY(d_nodeids.upload(tile_nodeids.data(), tile_nodeids.size(), s));
@@ -686,22 +786,25 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   GRMP_TRY(d_vspoke.upload(vspoke.data(), vspoke.size(), s));
   GRMP_TRY(d_spokes.upload(spokes.data(), spokes.size(), s));
   GRMP_TRY(out->dscratch.alloc(std::max<size_t>(spoke_ptr[ncols], 1)));
+  GRMP_TRY(out->tile_counter.alloc(1));
+  GRMP_CUDA(cudaMemsetAsync(out->tile_counter.p, 0, sizeof(int), s));
   // (3) pack column / pair records into the tile blobs on the device (slots are looked up in the pattern by (row, col))
-  DevBuf<u32> d_cell, d_io, d_code, d_colof, d_coltile, d_colpq;
+  DevBuf<u32> d_cell, d_io, d_code, d_colof, d_coltile, d_colpq, d_abase;
   DevBuf<unsigned char> d_closed;
   GRMP_TRY(d_cell.upload(pair_cell.data(), npairs, s)); GRMP_TRY(d_io.upload(pair_io.data(), npairs, s));
   GRMP_TRY(d_code.upload(pair_code.data(), npairs, s)); GRMP_TRY(d_colof.upload(col_of_pair.data(), npairs, s));
   GRMP_TRY(d_closed.upload(col_closed.data(), ncols, s));
   GRMP_TRY(d_coltile.upload(col_tile.data(), ncols, s)); GRMP_TRY(d_colpq.upload(col_pq.data(), ncols, s));
+  GRMP_TRY(d_abase.upload(col_abase.data(), ncols, s));
   GRMP_TRY(out->blob.alloc(std::max<size_t>((size_t)blob_total16 * 16, 16)));
   GRMP_CUDA(cudaMemsetAsync(out->blob.p, 0, out->blob.bytes(), s));
   out->end_slots.release();
   if (any_end) GRMP_TRY(out->end_slots.alloc(std::max<i64>(npairs, 1)));
   PackParams pp{d_cell.p, d_io.p, d_code.p, dg.segptr.p, pat.colptr.p, pat.rowval.p, p.e1.celldofs, d_colof.p, d_closed.p,
-                d_coltile.p, d_colpq.p, d_spokes.p, reinterpret_cast<const TileHdr*>(out->tile_hdr.p), npairs, ncols, out->blob.p, out->end_slots.p};
+                d_coltile.p, d_colpq.p, d_abase.p, d_spokes.p, reinterpret_cast<const TileHdr*>(out->tile_hdr.p), npairs, ncols, out->blob.p, out->end_slots.p};
   if (npairs) pack_pairs<<<(unsigned)((npairs + 255) / 256), 256, 0, s>>>(pp);
   if (ncols) pack_cols<<<(unsigned)((ncols + 255) / 256), 256, 0, s>>>(pp);
-  if (ntiles) pack_tile_nodes<<<ntiles, 128, 0, s>>>(reinterpret_cast<const TileHdr*>(out->tile_hdr.p), d_nodeids.p, p.g.coords, out->blob.p);
+  if (ntiles) pack_tile_nodes<<<ntiles, 128, 0, s>>>(reinterpret_cast<const TileHdr*>(out->tile_hdr.p), d_groups.p, NW, d_nodeids.p, p.g.coords, out->blob.p);
   GRMP_CUDA(cudaGetLastError());
   // (4) vertex columns: list + diagonal slots
   GRMP_TRY(out->vcols.upload(vcols.data(), vcols.size(), s));
@@ -711,35 +814,39 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     GRMP_CUDA(cudaGetLastError());
   }
   const int smem_attr = (int)std::max<i64>(max_smem, 1024);
-  GRMP_TRY(set_smem_attr<64>(smem_attr)); GRMP_TRY(set_smem_attr<128>(smem_attr)); GRMP_TRY(set_smem_attr<192>(smem_attr));
-  GRMP_TRY(set_smem_attr<256>(smem_attr)); GRMP_TRY(set_smem_attr<512>(smem_attr));
+  GRMP_TRY(set_smem_attr<3>(smem_attr)); GRMP_TRY(set_smem_attr<4>(smem_attr)); GRMP_TRY(set_smem_attr<5>(smem_attr));
+  GRMP_TRY(set_smem_attr<6>(smem_attr)); GRMP_TRY(set_smem_attr<7>(smem_attr));
   GRMP_CUDA(cudaStreamSynchronize(s));
   return GRMP_OK;
 }
 
-template <int TPB> int launch_edge(const EdgeParams& ep, const FastP2Tet& f, int sm_count, cudaStream_t s) {
+template <int NW> int launch_edge(const EdgeParams& ep, const FastP2Tet& f, int sm_count, cudaStream_t s) {
   int per_sm = 0;
-  GRMP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p2tet_edge_kernel<TPB>, TPB, (size_t)f.smem_bytes));
+  GRMP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p2tet_edge_kernel<NW>, (NW + 1) * 32, (size_t)f.smem_bytes));
   if (per_sm < 1) return fail(GRMP_ECUDA, "fast path: edge kernel does not fit on an SM");
   const int grid = std::min(f.ntiles, per_sm * sm_count);
-  p2tet_edge_kernel<TPB><<<grid, TPB, f.smem_bytes, s>>>(ep);
+  p2tet_edge_kernel<NW><<<grid, (NW + 1) * 32, f.smem_bytes, s>>>(ep);
   return GRMP_OK;
 }
 
 int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const FastP2Tet& f, double* nzval) {
   static const int dbg = getenv("GRMP_DEBUG_FLAGS") ? atoi(getenv("GRMP_DEBUG_FLAGS")) : 0;
   if (f.ntiles > 0) {
-    EdgeParams ep{f.tile_dir.p, f.blob.p, f.end_slots.p, f.dscratch.p, p.factor, nzval, f.ntiles, f.in_stride, dbg};
-    if (f.tpb == 64) GRMP_TRY(launch_edge<64>(ep, f, ctx->sm_count, ctx->stream));
-    else if (f.tpb == 256) GRMP_TRY(launch_edge<256>(ep, f, ctx->sm_count, ctx->stream));
-    else if (f.tpb == 192) GRMP_TRY(launch_edge<192>(ep, f, ctx->sm_count, ctx->stream));
-    else if (f.tpb == 512) GRMP_TRY(launch_edge<512>(ep, f, ctx->sm_count, ctx->stream));
-    else GRMP_TRY(launch_edge<128>(ep, f, ctx->sm_count, ctx->stream));
+    EdgeParams ep{f.tile_dir.p, f.blob.p, f.end_slots.p, f.dscratch.p, p.factor, nzval, f.tile_counter.p, f.ntiles, f.in_stride, f.slot_elems, dbg};
+    switch (f.nw) {
+      case 3: GRMP_TRY(launch_edge<3>(ep, f, ctx->sm_count, ctx->stream)); break;
+      case 4: GRMP_TRY(launch_edge<4>(ep, f, ctx->sm_count, ctx->stream)); break;
+      case 5: GRMP_TRY(launch_edge<5>(ep, f, ctx->sm_count, ctx->stream)); break;
+      case 6: GRMP_TRY(launch_edge<6>(ep, f, ctx->sm_count, ctx->stream)); break;
+      default: GRMP_TRY(launch_edge<7>(ep, f, ctx->sm_count, ctx->stream)); break;
+    }
     GRMP_CUDA(cudaGetLastError());
   }
   if (f.nvcols > 0 && !(dbg & 2)) {
-    p2tet_vertex_diag_kernel<<<(unsigned)((f.nvcols + 255) / 256), 256, 0, ctx->stream>>>(f.vrec.p, f.nvcols, f.dscratch.p, nzval);
+    p2tet_vertex_diag_kernel<<<(unsigned)((f.nvcols + 255) / 256), 256, 0, ctx->stream>>>(f.vrec.p, f.nvcols, f.dscratch.p, nzval, f.tile_counter.p);
     GRMP_CUDA(cudaGetLastError());
+  } else {
+    GRMP_CUDA(cudaMemsetAsync(f.tile_counter.p, 0, sizeof(int), ctx->stream));
   }
   return GRMP_OK;
 }
