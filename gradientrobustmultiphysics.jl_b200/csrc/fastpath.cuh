@@ -13,14 +13,12 @@ struct FastP2Tet {
   int smem_bytes = 0;
   u32 slot_elems = 0;             // doubles per warp stage slot
   u32 in_stride = 0;              // bytes of one input buffer of the kernel's 2-deep ring (largest blob)
-  DevBuf<int4> tile_hdr;          // 3 per tile (TileHdr): column range, nzval range, blob / node-list / pair offsets (symbolic pass only)
   DevBuf<uint2> tile_dir;         // per tile: blob offset (16-byte units), blob bytes
-  DevBuf<unsigned char> blob;     // per tile: header, column records, ring-ordered pair records, pair mirror slots, node coordinates (one TMA bulk load)
+  DevBuf<unsigned char> blob;     // per tile: header, group table, column / pair records, node coordinates, sorted mirror list
   DevBuf<u32> end_slots;          // per pair, only when a partition produced multi-chain halo columns
   DevBuf<u32> vcols;              // vertex columns
-  DevBuf<uint4> vrec;             // per vertex column: diagonal slot, first spoke slot, #spokes
+  DevBuf<uint4> vrec;             // per vertex column: diagonal slot, first slot, #slots
   DevBuf<int> tile_counter;       // dynamic tile scheduler of the edge kernel
-  DevBuf<double> dscratch;        // per (vertex, spoke): 0.2 * ring sum of S_vv
   i64 nvcols = 0;
 };
 

@@ -19,26 +19,34 @@
 //     (the affine pullback of feevaluator_h1.jl:61-74 reduced to the five off-diagonal
 //     invariants S_pq, S_pi, S_po, S_qi, S_qo; the diagonal ones follow from the zero row sums).
 //     A tile = up to NW groups of up to 32 consecutive edge columns, one group per consumer warp.
-//     Its header, column / pair records and node coordinates form one contiguous blob that a
+//     Its header, records, node coordinates and mirror list form one contiguous blob that a
 //     single TMA bulk load (cp.async.bulk + mbarrier) brings into shared memory.  CTAs are
-//     persistent: a producer warp keeps a 2-deep ring of input blobs filled (full/empty
-//     mbarriers), the consumer warps never meet at a CTA-wide barrier.  Every warp stages the
-//     contiguous nzval range of its group in its own shared-memory slot and writes it with its
-//     own TMA bulk store, which overlaps the ring walk of its next group.
-//   VERTEX columns need no work of their own: the matrix of this form is symmetric, so every
+//     persistent and claim tiles from a global counter; one service warp keeps a 2-deep ring of
+//     input blobs filled, the consumer warps never meet at a CTA-wide barrier.  Every warp
+//     stages the contiguous nzval range of its group in its own shared-memory slot and writes
+//     it with its own TMA bulk store, which overlaps the ring walk of its next group.
+//   VERTEX columns need no ring walk of their own: the matrix of this form is symmetric, so every
 //     off-diagonal entry (i, v_a) is the mirror image of an entry (v_a, i) that an edge thread
 //     has in a register anyway (i an edge dof), or the ring sum -0.2*sum S_pq of the edge (a b)
-//     (i = v_b).  Edge threads store those values straight to their mirrored slots.
-//   diagonal kernel (p2tet_vertex_diag_kernel): A[v,v] = 0.6 sum_K S_vv = 0.2 * sum over the
-//     spokes (v w) of the ring sums of S_vv, which the edge threads leave in a scratch list.
+//     (i = v_b).  Edge threads park those values in shared memory (in the slots of their already
+//     consumed records); when all warps are done with a tile the service warp writes them to
+//     their mirrored slots in DESTINATION order (list sorted in the symbolic pass), so that the
+//     tile's values for one vertex column form one run of consecutive addresses.  Scattered
+//     8-byte stores are the scarce resource of this kernel: the device retires ~1e11 partial
+//     32-byte sector writes per second, half the rate of full sectors (tools/write_bw.cu).
+//   diagonal kernel (p2tet_vertex_diag_kernel): the columns of a stiffness matrix sum to zero
+//     (the basis is a partition of unity), so A[v,v] = -sum_{i != v} A[i,v]; one warp per vertex
+//     column, fixed reduction tree.
 //
-// No atomics, fixed summation orders -> deterministic.  Values agree with the reference's order of
-// operations to rounding (tests/test_gpu_parity.py states the tolerance); the PATTERN always
-// comes from the bit-exact symbolic pass, and slots are looked up in it by (row, column).
+// No atomics on values, fixed summation orders -> deterministic.  Values agree with the reference's
+// order of operations to rounding (tests/test_gpu_parity.py states the tolerance); the PATTERN
+// always comes from the bit-exact symbolic pass, and slots are looked up in it by (row, column).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+
+#include <cub/cub.cuh>
 
 #include "fastpath.cuh"
 
@@ -46,9 +54,8 @@ namespace grmp {
 
 namespace {
 
-constexpr int NW_DEFAULT = 7;                     // consumer warps per CTA (+ 1 producer warp)
+constexpr int NW_DEFAULT = 7;                     // consumer warps per CTA (+ 1 service warp)
 constexpr int SLOT_DEFAULT = 800;                 // nzval entries a warp may stage per group (32 columns x ~23 rows)
-// shared memory per CTA (2 input buffers + output stage) such that 2 / 3 / 5 CTAs of 256 / 192 / 128 threads fit on an SM
 __host__ inline i64 smem_budget_default(int nw) { return 1024 * (i64)(nw >= 5 ? 112 : nw == 4 ? 74 : 55); }   // 2 / 3 / 4 CTAs per SM
 constexpr u32 NONE = 0xffffffffu;
 constexpr int MAX_TILE_NODES = 4095;              // 12-bit tile-local node ids
@@ -66,31 +73,36 @@ __host__ __device__ inline int edge_of(int a, int b) {   // local edge dof index
 // ---- records ---------------------------------------------------------------------------------
 // tile blob (global, contiguous per tile, 16-byte aligned sections; one TMA bulk load):
 //   tile header 48 B: see TileHdr;  group table (NW+1) x {first column (tile-local), first nzval slot (relative to g0)}
-//   column records  48 B x ncol
-//     a.x : tile-local node of P | Q << 12 | #pairs << 24
-//     a.y : slot offsets inside the column of rows v_P, v_Q, e_PQ (255 = not in the pattern) | flags << 24 (bit 0: closed ring)
-//     a.z : closing offsets (closed: rows of the first pair's in-vertex; open: rows of the last pair's out-vertex)
-//     a.w : column start inside the group's nzval range | first pair (tile-local) << 16
-//     b.x, b.y, b.z : mirrored slots (global nzval index or NONE) of row e_PQ in columns v_P, v_Q, v_closing
-//     b.w, c.x : slots of (row v_Q, col v_P) and (row v_P, col v_Q)
-//     c.y, c.z : scratch slots of this edge in the spoke lists of v_P, v_Q
-//   pair records 8 B x npairs, pairs of a column stored in ring order
+//   column records  32 B x ncol   (16 B used; after the ring walk the owner parks 4 doubles A, B, q0, W in its record)
+//     x : tile-local node of P | Q << 12 | #pairs << 24
+//     y : slot offsets inside the column of rows v_P, v_Q, e_PQ (255 = not in the pattern) | flags << 24 (bit 0: closed ring)
+//     z : closing offsets (closed: rows of the first pair's in-vertex; open: rows of the last pair's out-vertex)
+//     w : column start inside the group's nzval range | first pair (tile-local) << 16
+//   pair records 8 B x npairs, pairs of a column stored in ring order (the owner parks the value of row v_in in it)
 //     x : slot offsets inside the column of rows v_in, e_P,in, e_Q,in, e_in,out (255 = not in the pattern)
 //     y : tile-local node of the in-vertex | out-vertex << 12 | flags << 24
-//   pair mirrors 4 B x npairs : mirrored slot of row e_PQ in column v_in, or NONE
 //   node coordinates 24 B x nnodes : tile-blocked copy of Coordinates (the grid is immutable after grmp_grid_create)
+//   mirror list, sorted by destination: u32 destination slot x nmax, then u16 source (8-byte word inside the blob) x nmax;
+//     nmax = 5 ncol + npairs candidates, the first nmir (header) are valid.  Candidates of column c: (e_PQ, v_P) <- A,
+//     (e_PQ, v_Q) <- B, (e_PQ, v_closing) <- q0, (v_Q, v_P) <- W, (v_P, v_Q) <- W; of pair k: (e_PQ, v_in) <- parked value.
 constexpr u32 PF_RESET = 2u;   // first pair of a further chain (halo columns of a partition): drop the carry, reload the in-vertex
 constexpr u32 PF_END = 4u;     // last pair of a chain that is not the last chain: mirror its out-vertex row now (slot in end_slots)
 
 struct __align__(16) TileHdr {
   int c0, ncol, nnodes, npairs;          // first column, #columns, #distinct nodes, #pairs
   u32 g0lo, g0hi; int nnz; u32 blob16;   // first nzval slot, #slots, blob offset in 16-byte units
-  u32 pair_base, node_base, blob_bytes, pairs_off;   // global index of the first pair / node-list entry; blob size; byte offset of the pair records
-  // byte offset of the column records = pairs_off - 48 * ncol
+  u32 pair_base, node_base;              // global index of the first pair / node-list entry (blob copy: node_base holds nmir)
+  u32 blob_bytes, cols_off;              // blob size; byte offset of the column records
 };
 static_assert(sizeof(TileHdr) == 48, "TileHdr layout");
 
 __host__ __device__ inline u32 pad16(u32 b) { return (b + 15u) & ~15u; }
+// section offsets inside a blob, all derived from the header
+__host__ __device__ inline u32 off_pairs(u32 cols_off, u32 ncol) { return cols_off + 32u * ncol; }
+__host__ __device__ inline u32 off_xyz(u32 cols_off, u32 ncol, u32 npairs) { return off_pairs(cols_off, ncol) + pad16(8u * npairs); }
+__host__ __device__ inline u32 off_mdst(u32 cols_off, u32 ncol, u32 npairs, u32 nnodes) { return off_xyz(cols_off, ncol, npairs) + pad16(24u * nnodes); }
+__host__ __device__ inline u32 off_msrc(u32 cols_off, u32 ncol, u32 npairs, u32 nnodes) { return off_mdst(cols_off, ncol, npairs, nnodes) + pad16(4u * (5u * ncol + npairs)); }
+__host__ __device__ inline u32 blob_size(u32 cols_off, u32 ncol, u32 npairs, u32 nnodes) { return off_msrc(cols_off, ncol, npairs, nnodes) + pad16(2u * (5u * ncol + npairs)); }
 
 struct PackParams {
   const u32* pair_cell;     // global cell of the pair (ring order)
@@ -105,11 +117,13 @@ struct PackParams {
   const u32* col_tile;      // tile of every edge column
   const u32* col_pq;        // tile-local node of P | Q << 12
   const u32* col_abase;     // first slot of the column relative to its group
-  const uint2* spokes;      // per column: scratch slots in the spoke lists of v_P, v_Q
   const TileHdr* hdr;
+  const int* mir_base;      // [ntiles+1] first mirror candidate of every tile
   i64 npairs, ncols;
   unsigned char* blob;
   u32* end_slots;           // [npairs] or null
+  u32* mkey;                // mirror candidates: destination slot (NONE = not in the pattern / no value)
+  u32* mval;                //                    source word inside the blob
 };
 
 // slot of (row, col) in the pattern as an offset inside the column, or -1
@@ -140,15 +154,21 @@ __global__ void pack_pairs(PackParams p) {
   const u32 fl = (code >> 8) & 255u;
   const i32* d = p.celldofs + cell * 10;
   const i64 vin = d[I] - 1;
-  const TileHdr h = p.hdr[p.col_tile[col]];
+  const u32 tile = p.col_tile[col];
+  const TileHdr h = p.hdr[tile];
   const u32 kl = (u32)(k - (i64)h.pair_base);
   unsigned char* tb = p.blob + (size_t)h.blob16 * 16;
+  const u32 po = off_pairs(h.cols_off, (u32)h.ncol);
   uint2 rec;
   rec.x = off8(find_slot(p, vin, col)) | (off8(find_slot(p, d[edge_of(P, I)] - 1, col)) << 8) |
           (off8(find_slot(p, d[edge_of(Q, I)] - 1, col)) << 16) | (off8(find_slot(p, d[edge_of(I, O)] - 1, col)) << 24);
   rec.y = (p.pair_io[k] & 0xffffffu) | (fl << 24);
-  reinterpret_cast<uint2*>(tb + h.pairs_off)[kl] = rec;
-  reinterpret_cast<u32*>(tb + h.pairs_off + pad16(8u * (u32)h.npairs))[kl] = gslot(p, col, vin);
+  reinterpret_cast<uint2*>(tb + po)[kl] = rec;
+  // mirror candidate (e_PQ, v_in); the first pair of a closed ring is completed by the last one and travels with the column
+  const bool first_of_closed = p.col_closed[col] == 1 && k == p.col_pairbeg[col];
+  const size_t m = (size_t)p.mir_base[tile] + 5u * (u32)h.ncol + kl;
+  p.mkey[m] = first_of_closed ? NONE : gslot(p, col, vin);
+  p.mval[m] = po / 8 + kl;
   if (p.end_slots) p.end_slots[k] = (fl & PF_END) ? gslot(p, col, d[O] - 1) : NONE;
 }
 
@@ -157,7 +177,8 @@ __global__ void pack_cols(PackParams p) {
   if (j >= p.ncols) return;
   if (p.col_closed[j] == 2) return;     // not an edge column
   const i64 kb = p.col_pairbeg[j], ke = p.col_pairbeg[j + 1];
-  const TileHdr h = p.hdr[p.col_tile[j]];
+  const u32 tile = p.col_tile[j];
+  const TileHdr h = p.hdr[tile];
   const bool closed = p.col_closed[j] == 1;
   // reference orientation (P,Q) = first ring pair
   const u32 c0 = p.pair_code[kb];
@@ -169,31 +190,53 @@ __global__ void pack_cols(PackParams p) {
   const i32* dc = p.celldofs + (i64)p.pair_cell[kc] * 10;
   const int Pc = cc & 3, Qc = (cc >> 2) & 3, Vc = closed ? ((cc >> 4) & 3) : ((cc >> 6) & 3);
   const i64 vC = dc[Vc] - 1;
-  uint4 a, b, c;
+  uint4 a;
   a.x = (p.col_pq[j] & 0xffffffu) | ((u32)(ke - kb) << 24);
   a.y = off8(find_slot(p, vP, j)) | (off8(find_slot(p, vQ, j)) << 8) | (off8(find_slot(p, j, j)) << 16) | ((closed ? 1u : 0u) << 24);
   a.z = off8(find_slot(p, vC, j)) | (off8(find_slot(p, dc[edge_of(Pc, Vc)] - 1, j)) << 8) | (off8(find_slot(p, dc[edge_of(Qc, Vc)] - 1, j)) << 16);
   a.w = (p.col_abase[j] & 0xffffu) | ((u32)(kb - (i64)h.pair_base) << 16);
-  b.x = gslot(p, j, vP);
-  b.y = gslot(p, j, vQ);
-  b.z = gslot(p, j, vC);
-  b.w = gslot(p, vQ, vP);
-  c.x = gslot(p, vP, vQ);
-  c.y = p.spokes[j].x; c.z = p.spokes[j].y; c.w = 0;
-  uint4* dst = reinterpret_cast<uint4*>(p.blob + (size_t)h.blob16 * 16 + (h.pairs_off - 48u * (u32)h.ncol)) + 3 * (j - h.c0);
-  dst[0] = a; dst[1] = b; dst[2] = c;
+  const u32 cl = (u32)(j - h.c0);
+  uint4* dst = reinterpret_cast<uint4*>(p.blob + (size_t)h.blob16 * 16 + h.cols_off) + 2 * cl;
+  dst[0] = a; dst[1] = make_uint4(0, 0, 0, 0);
+  // mirror candidates of the column: parked doubles A, B, q0, W at words 4 cl + {0,1,2,3} of the column section
+  const size_t m = (size_t)p.mir_base[tile] + 5u * cl;
+  const u32 w0 = h.cols_off / 8 + 4 * cl;
+  p.mkey[m + 0] = gslot(p, j, vP); p.mval[m + 0] = w0 + 0;    // (e_PQ, v_P) <- A
+  p.mkey[m + 1] = gslot(p, j, vQ); p.mval[m + 1] = w0 + 1;    // (e_PQ, v_Q) <- B
+  p.mkey[m + 2] = gslot(p, j, vC); p.mval[m + 2] = w0 + 2;    // (e_PQ, v_closing) <- q0
+  p.mkey[m + 3] = gslot(p, vQ, vP); p.mval[m + 3] = w0 + 3;   // (v_Q, v_P) <- W
+  p.mkey[m + 4] = gslot(p, vP, vQ); p.mval[m + 4] = w0 + 3;   // (v_P, v_Q) <- W
 }
 
-// one block per tile: header and node coordinates into the blob
-__global__ void pack_tile_nodes(const TileHdr* hdr, const uint2* groups, int nw, const u32* tile_nodeids, const double* coords, unsigned char* blob) {
+// one block per tile: header, group table, node coordinates and the destination-sorted mirror list into the blob
+__global__ void pack_tile_rest(const TileHdr* hdr, const uint2* groups, int nw, const u32* tile_nodeids, const double* coords,
+                               const int* mir_base, const u32* mkey_sorted, const u32* mval_sorted, unsigned char* blob) {
+  __shared__ int s_valid;
   const TileHdr h = hdr[blockIdx.x];
   unsigned char* tb = blob + (size_t)h.blob16 * 16;
-  if (threadIdx.x < 3) reinterpret_cast<int4*>(tb)[threadIdx.x] = reinterpret_cast<const int4*>(hdr + blockIdx.x)[threadIdx.x];
+  if (threadIdx.x == 0) s_valid = 0;
+  __syncthreads();
   if ((int)threadIdx.x <= nw) reinterpret_cast<uint2*>(tb + 48)[threadIdx.x] = groups[(size_t)blockIdx.x * (nw + 1) + threadIdx.x];
-  double* X = reinterpret_cast<double*>(tb + h.pairs_off + pad16(8u * (u32)h.npairs) + pad16(4u * (u32)h.npairs));
+  double* X = reinterpret_cast<double*>(tb + off_xyz(h.cols_off, (u32)h.ncol, (u32)h.npairs));
   for (int i = threadIdx.x; i < h.nnodes; i += blockDim.x) {
     const double* xg = coords + (size_t)(tile_nodeids[(size_t)h.node_base + i] - 1) * 3;
     X[3 * i] = xg[0]; X[3 * i + 1] = xg[1]; X[3 * i + 2] = xg[2];
+  }
+  const int m0 = mir_base[blockIdx.x], nm = mir_base[blockIdx.x + 1] - m0;
+  u32* md = reinterpret_cast<u32*>(tb + off_mdst(h.cols_off, (u32)h.ncol, (u32)h.npairs, (u32)h.nnodes));
+  unsigned short* ms = reinterpret_cast<unsigned short*>(tb + off_msrc(h.cols_off, (u32)h.ncol, (u32)h.npairs, (u32)h.nnodes));
+  int mine = 0;
+  for (int i = threadIdx.x; i < nm; i += blockDim.x) {
+    const u32 key = mkey_sorted[m0 + i];
+    md[i] = key; ms[i] = (unsigned short)mval_sorted[m0 + i];
+    mine += key != NONE;
+  }
+  atomicAdd(&s_valid, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    TileHdr hb = h;
+    hb.node_base = (u32)s_valid;      // nmir: the valid candidates sort in front of NONE
+    *reinterpret_cast<TileHdr*>(tb) = hb;
   }
 }
 
@@ -201,7 +244,6 @@ struct EdgeParams {
   const uint2* tile_dir;    // per tile: blob offset (16-byte units), blob bytes
   const unsigned char* blob;
   const u32* end_slots;     // [npairs] or null (only partitions have multi-chain columns)
-  double* dscratch;         // [sum of spoke counts] 0.2 * ring sum of S_vv per (vertex, spoke)
   double factor;
   double* nzval;
   int* tile_counter;        // dynamic tile scheduler: next unclaimed tile (zero at launch; reset by the diagonal kernel)
@@ -220,30 +262,16 @@ __device__ __forceinline__ double fast_rcp(double d) {   // 1/d to ~1 ulp for no
   r = fma(r, t, r);
   return r;
 }
-
 __device__ __forceinline__ u64 l2_policy_evict_first() {
   u64 pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
-__device__ __forceinline__ u64 l2_policy_evict_last() {
-  u64 pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ void st_hint(double* ptr, double v, u64 pol) {
-  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(ptr), "d"(v), "l"(pol) : "memory");
-}
 __device__ __forceinline__ void tile_load(const EdgeParams& p, uint2 dir, unsigned dst_smem, unsigned mbar_a, u64 pol) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(dir.y) : "memory");
-  if (p.dbg & 32)
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
-                 "l"(p.blob + (size_t)dir.x * 16), "r"(dir.y), "r"(mbar_a)
-                 : "memory");
-  else
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
-                 "l"(p.blob + (size_t)dir.x * 16), "r"(dir.y), "r"(mbar_a), "l"(pol)
-                 : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+               "l"(p.blob + (size_t)dir.x * 16), "r"(dir.y), "r"(mbar_a), "l"(pol)
+               : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned mbar_a, unsigned parity) {
   asm volatile(
@@ -258,55 +286,82 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar_a, unsigned parity) {
       : "memory");
 }
 
-// Persistent CTAs of NW consumer warps + 1 producer warp: CTA b walks tiles b, b + gridDim.x, ...  The producer keeps the
-// 2-deep input ring filled (TMA bulk loads, full[]/empty[] mbarriers); consumer warp w owns group w of every tile, stages the
-// group's nzval range in its own slot and stores it with its own TMA bulk store.  No CTA-wide barrier after the set-up.
+// service warp: the tile's parked mirror values -> their slots in the vertex columns, in destination order
+__device__ __forceinline__ void mirror_writeout(const EdgeParams& p, const unsigned char* in, int lane) {
+  const int4 h0 = reinterpret_cast<const int4*>(in)[0], h2 = reinterpret_cast<const int4*>(in)[2];
+  const u32 ncol = (u32)h0.y, nnodes = (u32)h0.z, npairs = (u32)h0.w, nmir = (u32)h2.y, cols_off = (u32)h2.w;
+  const u32* __restrict__ md = reinterpret_cast<const u32*>(in + off_mdst(cols_off, ncol, npairs, nnodes));
+  const unsigned short* __restrict__ ms = reinterpret_cast<const unsigned short*>(in + off_msrc(cols_off, ncol, npairs, nnodes));
+  const double* __restrict__ words = reinterpret_cast<const double*>(in);
+#pragma unroll 4
+  for (u32 i = lane; i < nmir; i += 32) p.nzval[md[i]] = words[ms[i]];
+}
+
+// Persistent CTAs of NW consumer warps + 1 service warp.  Tiles are claimed from a global counter.  The service warp keeps the
+// 2-deep input ring filled (TMA bulk loads, full[] mbarriers) and, once all consumer warps have left a tile (done[] mbarriers),
+// writes its mirror values out and reuses the buffer.  Consumer warp w owns group w of every tile, stages the group's nzval
+// range in its own slot and stores it with its own TMA bulk store.  No CTA-wide barrier after the set-up.
 template <int NW>
 __global__ void __launch_bounds__((NW + 1) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 : 4)) p2tet_edge_kernel(const EdgeParams p) {
   extern __shared__ __align__(128) unsigned char smraw[];
-  __shared__ __align__(8) unsigned long long mbar[4];      // full[0], full[1], empty[0], empty[1]
+  __shared__ __align__(8) unsigned long long mbar[4];      // full[0], full[1], done[0], done[1]
   __shared__ int s_tile[2];                                // tile in each input buffer, -1 = no more tiles
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const unsigned full_a = (unsigned)__cvta_generic_to_shared(&mbar[0]), empty_a = full_a + 16;
+  const unsigned full_a = (unsigned)__cvta_generic_to_shared(&mbar[0]), done_a = full_a + 16;
   const unsigned in_a = (unsigned)__cvta_generic_to_shared(smraw);
-  const int G = gridDim.x;
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_a));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_a + 8));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_a), "r"(NW));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_a + 8), "r"(NW));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(done_a), "r"(NW));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(done_a + 8), "r"(NW));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  if (warp == NW) {   // ---- producer ----
-    if (lane == 0) {
-      const u64 pol_stream = l2_policy_evict_first();
-      for (int it = 0;; it++) {
-        const int b = it & 1;
-        // tiles are claimed dynamically (SMs do not run at the same speed; a static split leaves the slowest SM as the tail)
-        const int t = (p.dbg & 1024) ? (int)blockIdx.x + it * G : atomicAdd(p.tile_counter, 1);
-        uint2 dir = make_uint2(0, 0);
+  if (warp == NW) {   // ---- service warp ----
+    const u64 pol_stream = l2_policy_evict_first();
+    int it = 0;
+    for (;; it++) {
+      const int b = it & 1;
+      int t = 0;
+      uint2 dir = make_uint2(0, 0);
+      if (lane == 0) {
+        // tiles are claimed dynamically: SMs do not run at the same speed, a static split leaves the slowest SM as the tail
+        t = atomicAdd(p.tile_counter, 1);
         if (t < p.ntiles) dir = __ldg(p.tile_dir + t);
-        if (it >= 2) mbar_wait(empty_a + 8 * b, (unsigned)((it >> 1) - 1) & 1u);   // all consumer warps released the buffer
-        if (t >= p.ntiles) {
-          if (p.dbg & 2048) { unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); printf("CTA %d sm %u tiles %d\n", (int)blockIdx.x, smid, it); }
+      }
+      if (it >= 2) {
+        mbar_wait(done_a + 8 * b, (unsigned)((it >> 1) - 1) & 1u);   // all consumer warps have left the tile in this buffer
+        if (!(p.dbg & 1)) mirror_writeout(p, smraw + (size_t)b * p.in_stride, lane);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // parked values (generic writes) before the next bulk load
+        __syncwarp();
+      }
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= p.ntiles) {
+        if (lane == 0) {
           s_tile[b] = -1;
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_a + 8 * b) : "memory");
-          break;
         }
+        break;
+      }
+      if (lane == 0) {
         s_tile[b] = t;
         tile_load(p, dir, in_a + b * p.in_stride, full_a + 8 * b, pol_stream);
       }
     }
+    if (it >= 1) {   // the other buffer still holds the last tile
+      const int b2 = (it - 1) & 1;
+      mbar_wait(done_a + 8 * b2, (unsigned)((it - 1) >> 1) & 1u);
+      if (!(p.dbg & 1)) mirror_writeout(p, smraw + (size_t)b2 * p.in_stride, lane);
+    }
     return;
   }
   // ---- consumers ----
-  const u64 pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+  const u64 pol_stream = l2_policy_evict_first();
   double* const slot = reinterpret_cast<double*>(smraw + 2 * (size_t)p.in_stride) + (size_t)warp * p.slot_elems;
   for (int it = 0;; it++) {
     const int cur = it & 1;
-    const unsigned char* in = smraw + (size_t)cur * p.in_stride;
+    unsigned char* in = smraw + (size_t)cur * p.in_stride;
     mbar_wait(full_a + 8 * cur, (unsigned)(it >> 1) & 1u);
     if (*reinterpret_cast<volatile int*>(&s_tile[cur]) < 0) break;
     const int4 h0 = reinterpret_cast<const int4*>(in)[0], h1 = reinterpret_cast<const int4*>(in)[1], h2 = reinterpret_cast<const int4*>(in)[2];
@@ -315,8 +370,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 : 4)
     const bool has_col = col < (int)gr1.x;
     const i64 g0 = ((i64)(u32)h1.x | ((i64)h1.y << 32)) + gr0.y;   // first nzval slot of the group
     const int nnz_w = (int)(gr1.y - gr0.y);
-    const u32 pairs_off = (u32)h2.w, cols_off = pairs_off - 48u * (u32)h0.y;
-    const u32 mir_off = pairs_off + pad16(8u * (u32)h0.w), xyz_off = mir_off + pad16(4u * (u32)h0.w);
+    const u32 cols_off = (u32)h2.w, pairs_off = off_pairs(cols_off, (u32)h0.y), xyz_off = off_xyz(cols_off, (u32)h0.y, (u32)h0.w);
     const double* __restrict__ X = reinterpret_cast<const double*>(in + xyz_off);
     // stage[i] mirrors nzval[g0 + i]; it is shifted by one element when g0 is odd so that shared and global addresses of the
     // same element are 16-byte aligned together (TMA bulk store).  Every slot is written exactly once -> no zero-init.
@@ -325,23 +379,15 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 : 4)
     // this warp's previous bulk store must have finished reading the slot before it is overwritten
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
-    // mirrored values leave through ordinary scattered stores.  They are issued AFTER the bulk store of the group: the
-    // proxy fence in front of the bulk store waits for the warp's outstanding global stores, so stores issued inside the
-    // ring walk would put a full store round trip into every tile.  Ring values (e_PQ, v_in) are parked in the shared-memory
-    // slot of their already consumed pair record, the column values stay in registers.
-    uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, cc = ca;
-    u32 np = 0;
-    bool closed = false;
-    double mA = 0.0, mB = 0.0, mW = 0.0, mq0 = 0.0, mTp = 0.0, mTq = 0.0;
     if (has_col && !(p.dbg & 4)) {
-      const uint4* cr = reinterpret_cast<const uint4*>(in + cols_off) + 3 * col;
-      ca = cr[0]; cb = cr[1]; cc = cr[2];
-      np = ca.x >> 24;
+      const uint4 ca = *reinterpret_cast<const uint4*>(in + cols_off + 32u * (u32)col);
+      const u32 np = ca.x >> 24;
+      double mA = 0.0, mB = 0.0, mW = 0.0, mq0 = 0.0;
       if (np > 0) {
         const uint2* prec = reinterpret_cast<const uint2*>(in + pairs_off) + (ca.w >> 16);
-        double* park = reinterpret_cast<double*>(const_cast<unsigned char*>(in) + pairs_off) + (ca.w >> 16);
+        double* park = reinterpret_cast<double*>(in + pairs_off) + (ca.w >> 16);   // consumed pair records take the mirror values
         double* __restrict__ a = stage + (ca.w & 0xffffu);
-        closed = (ca.y >> 24) & 1u;
+        const bool closed = (ca.y >> 24) & 1u;
         const u32 lp = ca.x & 0xfffu, lq = (ca.x >> 12) & 0xfffu;
         const double px = X[3 * lp], py = X[3 * lp + 1], pz = X[3 * lp + 2];
         const double ax = X[3 * lq] - px, ay = X[3 * lq + 1] - py, az = X[3 * lq + 2] - pz;
@@ -409,7 +455,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 : 4)
             if (o0 != 255u) a[o0] = in0;
             if (o1 != 255u) a[o1] = in1;
             if (o2 != 255u) a[o2] = in2;
-            park[k] = in0;                                                 // mirror (e_PQ, v_in), stored after the bulk store
+            park[k] = in0;                                                 // mirror (e_PQ, v_in)
           }
           bx = ex; by = ey; bz = ez; mcx = mdx; mcy = mdy; mcz = mdz;
           ox = nx; oy = ny; oz = nz;
@@ -433,12 +479,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 : 4)
           if (oB != 255u) a[oB] = B;
           if (oC != 255u) a[oC] = C;
           mA = A; mB = B; mW = W;
-          mTp = -0.25 * (R1 + R2);                     // 0.2 * ring sum of S_pp
-          mTq = -0.25 * (R1 + R3);                     // 0.2 * ring sum of S_qq
         }
       }
+      // park the column's mirror values in its own (consumed) record
+      double2* rec = reinterpret_cast<double2*>(in + cols_off + 32u * (u32)col);
+      rec[0] = make_double2(mA, mB); rec[1] = make_double2(mq0, mW);
     }
-    if (!(p.dbg & 256)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // stage writes -> visible to the bulk store
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // stage writes -> visible to the bulk store
     __syncwarp();
     {
       // the group's nzval range is contiguous: one TMA bulk store (cp.async.bulk shared -> global) of the 16-byte aligned
@@ -446,74 +493,63 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 : 4)
       double* __restrict__ dst = p.nzval + g0;
       const int i0 = odd;                                   // first element whose address is 16-byte aligned
       const int nb = (nnz_w > i0) ? ((nnz_w - i0) & ~1) : 0;  // elements in the bulk body
-      if (lane == 0 && nb > 0 && !(p.dbg & 8)) {
-        const unsigned src = (unsigned)__cvta_generic_to_shared(stage + i0);
-        if (p.dbg & 64) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + i0), "r"(src), "r"(nb * 8) : "memory");
-        else asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst + i0), "r"(src), "r"(nb * 8), "l"(pol_stream) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      if (lane == 0) {
+        if (nb > 0 && !(p.dbg & 8)) {
+          const unsigned src = (unsigned)__cvta_generic_to_shared(stage + i0);
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst + i0), "r"(src), "r"(nb * 8), "l"(pol_stream) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        // every lane is done with this input buffer (ordered by the __syncwarp above); release makes the parked values visible
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(done_a + 8 * cur) : "memory");
       }
       if (lane == 1 && i0 == 1 && nnz_w > 0) dst[0] = stage[0];
       if (lane == 2 && i0 + nb < nnz_w) dst[i0 + nb] = stage[i0 + nb];
-    }
-    if (np > 0) {
-      if (!(p.dbg & 1)) {
-        const u32* __restrict__ pmir = reinterpret_cast<const u32*>(in + mir_off) + (ca.w >> 16);
-        const double* park = reinterpret_cast<const double*>(in + pairs_off) + (ca.w >> 16);
-        for (u32 k = closed ? 1u : 0u; k < np; k++) {
-          const u32 pm = pmir[k];
-          if (pm != NONE) { if (p.dbg & 128) p.nzval[pm] = park[k]; else st_hint(p.nzval + pm, park[k], pol_keep); }   // (e_PQ, v_in)
-        }
-        if (p.dbg & 128) {
-          if (cb.z != NONE) p.nzval[cb.z] = mq0;         // (e_PQ, v_closing)
-          if (cb.x != NONE) p.nzval[cb.x] = mA;          // (e_PQ, v_P)
-          if (cb.y != NONE) p.nzval[cb.y] = mB;          // (e_PQ, v_Q)
-          if (cb.w != NONE) p.nzval[cb.w] = mW;          // (v_Q, v_P)
-          if (cc.x != NONE) p.nzval[cc.x] = mW;          // (v_P, v_Q)
-        } else {
-          if (cb.z != NONE) st_hint(p.nzval + cb.z, mq0, pol_keep);
-          if (cb.x != NONE) st_hint(p.nzval + cb.x, mA, pol_keep);
-          if (cb.y != NONE) st_hint(p.nzval + cb.y, mB, pol_keep);
-          if (cb.w != NONE) st_hint(p.nzval + cb.w, mW, pol_keep);
-          if (cc.x != NONE) st_hint(p.nzval + cc.x, mW, pol_keep);
-        }
-      }
-      if (cc.y != NONE) p.dscratch[cc.y] = mTp;
-      if (cc.z != NONE) p.dscratch[cc.z] = mTq;
-    }
-    __syncwarp();                                            // every lane is done with this input buffer
-    if (lane == 0) {
-      if (p.dbg & 512) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_a + 8 * cur) : "memory");
-      else asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(empty_a + 8 * cur) : "memory");
     }
   }
   if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must stay alive until read
 }
 
-// A[v,v] = 0.6 * sum_{K containing v} S_vv = 0.2 * sum over the spokes (v w) of the ring sums of S_vv (every cell at v
-// has three edges at v); the spoke values were left in dscratch by the edge threads.  Fixed order -> deterministic.
-__global__ void p2tet_vertex_diag_kernel(const uint4* vrec, i64 nv, const double* __restrict__ dscratch, double* nzval, int* tile_counter) {
-  const i64 w = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  if (w == 0) *tile_counter = 0;           // re-arm the edge kernel's tile scheduler for the next assembly
-  if (w >= nv) return;
-  const uint4 r = vrec[w];                 // {diagonal slot | NONE, first spoke slot, #spokes, 0}
-  if (r.x == NONE) return;
+// The columns of a stiffness matrix sum to zero (sum_i phi_i = 1): A[v,v] = -sum_{i != v} A[i,v].  Eight lanes per vertex
+// column (a column has ~65 entries), every lane keeps up to 8 independent loads in flight, fixed shuffle tree -> deterministic.
+// Also re-arms the edge kernel's tile scheduler.
+__global__ void __launch_bounds__(256) p2tet_vertex_diag_kernel(const uint4* __restrict__ vrec, i64 nv, double* nzval, int* tile_counter) {
+  const i64 w = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 3;
+  const int sub = threadIdx.x & 7;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *tile_counter = 0;
+  uint4 r = make_uint4(NONE, 0, 0, 0);     // {diagonal slot | NONE, first slot of the column, #slots, 0}
+  if (w < nv) r = __ldg(vrec + w);
   double s = 0.0;
-  for (u32 k = 0; k < r.z; k++) s += dscratch[r.y + k];
-  nzval[r.x] = s;
+  if (r.x != NONE) {
+    const double* __restrict__ c = nzval + r.y;
+    const u32 d = r.x - r.y;
+    u32 k = sub;
+    for (; k + 56 < r.z; k += 64) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = c[k + 8 * u];
+#pragma unroll
+      for (int u = 0; u < 8; u++) s += (k + 8 * u == d) ? 0.0 : v[u];
+    }
+    for (; k < r.z; k += 8) s += (k == d) ? 0.0 : c[k];
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  if (sub == 0 && r.x != NONE) nzval[r.x] = -s;
 }
 
-__global__ void find_diag_slots(const u32* vcols, const u32* vspoke, i64 nv, const i64* colptr, const i64* rowval, uint4* vrec) {
+__global__ void find_diag_slots(const u32* vcols, i64 nv, const i64* colptr, const i64* rowval, uint4* vrec) {
   i64 w = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (w >= nv) return;
   const i64 col = vcols[w];
-  i64 lo = colptr[col] - 1, hi = colptr[col + 1] - 1;
-  const i64 end = hi;
+  const i64 beg = colptr[col] - 1, end = colptr[col + 1] - 1;
+  i64 lo = beg, hi = end;
   while (lo < hi) {
     i64 mid = (lo + hi) >> 1;
     if (rowval[mid] < col + 1) lo = mid + 1; else hi = mid;
   }
   const u32 d = (lo < end && rowval[lo] == col + 1) ? (u32)lo : NONE;
-  vrec[w] = make_uint4(d, vspoke[2 * w], vspoke[2 * w + 1], 0);
+  vrec[w] = make_uint4(d, (u32)beg, (u32)(end - beg), 0);
 }
 
 // closed-form local stiffness of the unit reference tetrahedron, used to verify that the
@@ -580,13 +616,12 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   if (npairs >= (i64)NONE) return fail(GRMP_EUNSUPPORTED, "fast path: more than 2^32-1 pairs");
   std::vector<u32> h_cell(npairs), h_src(npairs);
   std::vector<i64> h_pairbeg(ncols + 1), h_colptr(ncols + 1);
-  std::vector<i32> h_cn((size_t)ncells * 4), h_dofs((size_t)ncells * 10);
+  std::vector<i32> h_cn((size_t)ncells * 4);
   GRMP_CUDA(cudaMemcpyAsync(h_cell.data(), dg.gcell.p, npairs * 4, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaMemcpyAsync(h_src.data(), dg.gsrc.p, npairs * 4, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaMemcpyAsync(h_pairbeg.data(), dg.segptr.p, (ncols + 1) * 8, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaMemcpyAsync(h_colptr.data(), pat.colptr.p, (ncols + 1) * 8, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaMemcpyAsync(h_cn.data(), p.g.cellnodes, (size_t)ncells * 16, cudaMemcpyDeviceToHost, s));
-  GRMP_CUDA(cudaMemcpyAsync(h_dofs.data(), p.e1.celldofs, (size_t)ncells * 40, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaStreamSynchronize(s));
   // tile shape (tunable for experiments: GRMP_FAST_NW in 3..7, GRMP_FAST_SLOT, GRMP_FAST_SMEM_KB)
   int NW = getenv("GRMP_FAST_NW") ? atoi(getenv("GRMP_FAST_NW")) : NW_DEFAULT;
@@ -596,18 +631,17 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   // shared memory of a CTA: 2 input buffers (largest blob) + NW stage slots
   const i64 BLOB_CAP = ((SMEM_BUDGET - NW * 8 * (SLOT_CAP + 2)) / 2) & ~15ll;
   if (BLOB_CAP < 4096) return fail(GRMP_EUNSUPPORTED, "fast path: shared-memory budget too small for the tile shape");
-  const u32 hdr_bytes = 48u + pad16(8u * (u32)(NW + 1));
+  const u32 cols_off = 48u + pad16(8u * (u32)(NW + 1));
   out->nw = NW;
   // (2) host: ring order of every edge column, tiles over the edge columns, list of vertex columns
   std::vector<u32> pair_cell(npairs), pair_io(npairs), pair_code(npairs), col_of_pair(npairs), vcols;
   std::vector<unsigned char> col_closed(ncols, 2);
-  std::vector<u32> col_tile(ncols, NONE), col_pq(ncols, 0);
-  std::vector<u32> endP(ncols, NONE), endQ(ncols, NONE);     // vertex dofs of the two ends of every edge column
+  std::vector<u32> col_tile(ncols, NONE), col_pq(ncols, 0), col_abase(ncols, 0);
   std::vector<TileHdr> hdr;
   std::vector<u32> tile_nodeids;
-  std::vector<i32> nmark(nnodes + 1, -1), nlocal(nnodes + 1, 0);
-  std::vector<u32> col_abase(ncols, 0);
   std::vector<uint2> groups;                    // (NW+1) per tile: first column (tile-local), first slot (relative to g0)
+  std::vector<int> mir_base(1, 0);              // first mirror candidate of every tile
+  std::vector<i32> nmark(nnodes + 1, -1), nlocal(nnodes + 1, 0);
   int cur_tile = 0, cur_cols = 0, cur_nodes = 0;
   int cur_groups = 0, grp_cols = 0;             // closed groups of the open tile; columns / slots of the open group
   i64 grp_nnz = 0;
@@ -615,10 +649,6 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   i64 cur_nnz = 0, cur_pairs = 0, tile_first_col = 0, tile_node_base = 0, tile_pair_base = 0;
   i64 max_blob = 0, max_slot = 0, blob_total16 = 0;
   bool any_end = false;
-  auto tile_blob = [&](i64 cols, i64 pairs, i64 nodes) {
-    return (i64)hdr_bytes + 48 * cols + (i64)pad16((u32)(8 * pairs)) + (i64)pad16((u32)(4 * pairs)) + (i64)pad16((u32)(24 * nodes));
-  };
-
   auto close_tile = [&](i64 end_col) {
     if (cur_cols == 0) return;
     const i64 g0 = h_colptr[tile_first_col] - 1;
@@ -626,11 +656,12 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     h.c0 = (int)tile_first_col; h.ncol = (int)(end_col - tile_first_col); h.nnodes = cur_nodes; h.npairs = (int)cur_pairs;
     h.g0lo = (u32)(g0 & 0xffffffffll); h.g0hi = (u32)(g0 >> 32); h.nnz = (int)cur_nnz; h.blob16 = (u32)blob_total16;
     h.pair_base = (u32)tile_pair_base; h.node_base = (u32)tile_node_base;
-    h.pairs_off = hdr_bytes + 48u * (u32)h.ncol;
-    h.blob_bytes = (u32)tile_blob(h.ncol, cur_pairs, cur_nodes);
+    h.cols_off = cols_off;
+    h.blob_bytes = blob_size(cols_off, (u32)h.ncol, (u32)cur_pairs, (u32)cur_nodes);
     hdr.push_back(h);
     blob_total16 += h.blob_bytes / 16;
     max_blob = std::max<i64>(max_blob, h.blob_bytes);
+    mir_base.push_back(mir_base.back() + 5 * h.ncol + (int)cur_pairs);
     if (grp_cols > 0) { max_slot = std::max<i64>(max_slot, grp_nnz); cur_groups++; }
     for (int w2 = cur_groups; w2 <= NW; w2++) cur_grp[w2] = make_uint2((u32)h.ncol, (u32)cur_nnz);   // empty trailing groups
     for (int w2 = 0; w2 <= NW; w2++) groups.push_back(cur_grp[w2]);
@@ -670,7 +701,6 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
       if (cn[pl] != P0) { int tmp = pl; pl = ql; ql = tmp; }      // consistent global orientation (P,Q)
       if (cn[pl] != P0 || cn[ql] != Q0) return fail(GRMP_EUNSUPPORTED, "fast path: inconsistent edge column");
       rp[t] = RP{c, pl, ql, rl, sl, cn[rl], cn[sl]};
-      if (t == 0) { endP[j] = (u32)(h_dofs[(size_t)c * 10 + pl] - 1); endQ[j] = (u32)(h_dofs[(size_t)c * 10 + ql] - 1); }
     }
     // degrees of the ring vertices; chains start at vertices of degree 1, a star without such a vertex is a closed ring
     std::vector<int> degR(n), degS(n);
@@ -734,7 +764,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     for (int attempt = 0; attempt < 2; attempt++) {
       int fresh = 0;
       for (i32 v : colnodes) if (nmark[v] != cur_tile) fresh++;
-      const bool over = tile_blob(cur_cols + 1, cur_pairs + n, cur_nodes + fresh) > BLOB_CAP;
+      const bool over = (i64)blob_size(cols_off, (u32)(cur_cols + 1), (u32)(cur_pairs + n), (u32)(cur_nodes + fresh)) > BLOB_CAP;
       const bool grp_full = grp_cols > 0 && (grp_cols == 32 || grp_nnz + len > SLOT_CAP);   // the column would open a new group
       if (cur_cols > 0 && ((grp_full && cur_groups + 1 >= NW) || over || cur_nodes + fresh > MAX_TILE_NODES || cur_pairs + n > 65535)) { close_tile(j); continue; }
       if (len > SLOT_CAP) return fail(GRMP_EUNSUPPORTED, "fast path: a single column exceeds the stage slot");
@@ -755,62 +785,68 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   const i64 slot_elems = (max_slot + 2 + 1) & ~1ll;     // even: keeps every slot 16-byte aligned
   const i64 max_smem = 2 * max_blob + NW * 8 * slot_elems;
   if (max_smem > 220 * 1024) return fail(GRMP_EUNSUPPORTED, "fast path: a single column exceeds the shared-memory tile");
+  if (max_blob > 8 * 65535) return fail(GRMP_EUNSUPPORTED, "fast path: tile blob exceeds the 16-bit word index of the mirror list");
   const int ntiles = (int)hdr.size();
   if (blob_total16 >= (i64)NONE) return fail(GRMP_EUNSUPPORTED, "fast path: record blob exceeds 64 GB");
-  out->ntiles = ntiles; out->npairs = npairs; out->smem_bytes = (int)std::max<i64>(max_smem, 1024); out->in_stride = (u32)max_blob; out->slot_elems = (u32)slot_elems; out->nvcols = (i64)vcols.size();
-  if (hdr.empty()) { TileHdr z{}; hdr.push_back(z); groups.assign(NW + 1, make_uint2(0, 0)); }
+  out->ntiles = ntiles; out->npairs = npairs; out->smem_bytes = (int)std::max<i64>(max_smem, 1024); out->in_stride = (u32)max_blob;
+  out->slot_elems = (u32)slot_elems; out->nvcols = (i64)vcols.size();
+  if (hdr.empty()) { TileHdr z{}; hdr.push_back(z); groups.assign(NW + 1, make_uint2(0, 0)); mir_base.push_back(0); }
   if (tile_nodeids.empty()) tile_nodeids.push_back(1);
   if (vcols.empty()) vcols.push_back(0);
   std::vector<uint2> tile_dir(hdr.size());
   for (size_t t2 = 0; t2 < hdr.size(); t2++) tile_dir[t2] = make_uint2(hdr[t2].blob16, hdr[t2].blob_bytes);
   DevBuf<u32> d_nodeids;
   DevBuf<uint2> d_groups;
+  DevBuf<int4> d_hdr;
+  DevBuf<int> d_mirbase;
   GRMP_TRY(d_groups.upload(groups.data(), groups.size(), s));
-  GRMP_TRY(out->tile_hdr.upload(reinterpret_cast<const int4*>(hdr.data()), hdr.size() * 3, s));
+  GRMP_TRY(d_hdr.upload(reinterpret_cast<const int4*>(hdr.data()), hdr.size() * 3, s));
+  GRMP_TRY(d_mirbase.upload(mir_base.data(), mir_base.size(), s));
   GRMP_TRY(out->tile_dir.upload(tile_dir.data(), tile_dir.size(), s));
   GRMP_TRY(d_nodeids.upload(tile_nodeids.data(), tile_nodeids.size(), s));
-  // (2b) spoke lists: the diagonal of a vertex column is 0.2 * sum over its spokes of the ring sums of S_vv
-  std::vector<u32> spoke_cnt(ncols, 0), spoke_ptr(ncols + 1, 0);
-  for (i64 j = 0; j < ncols; j++) if (endP[j] != NONE) { spoke_cnt[endP[j]]++; spoke_cnt[endQ[j]]++; }
-  for (i64 j = 0; j < ncols; j++) spoke_ptr[j + 1] = spoke_ptr[j] + spoke_cnt[j];
-  std::vector<uint2> spokes(std::max<i64>(ncols, 1), make_uint2(NONE, NONE));
-  std::fill(spoke_cnt.begin(), spoke_cnt.end(), 0);
-  for (i64 j = 0; j < ncols; j++) if (endP[j] != NONE) {
-    spokes[j].x = spoke_ptr[endP[j]] + spoke_cnt[endP[j]]++;
-    spokes[j].y = spoke_ptr[endQ[j]] + spoke_cnt[endQ[j]]++;
-  }
-  std::vector<u32> vspoke(2 * vcols.size());
-  for (size_t w2 = 0; w2 < vcols.size(); w2++) { vspoke[2 * w2] = spoke_ptr[vcols[w2]]; vspoke[2 * w2 + 1] = spoke_cnt[vcols[w2]]; }
-  DevBuf<u32> d_vspoke;
-  DevBuf<uint2> d_spokes;
-  GRMP_TRY(d_vspoke.upload(vspoke.data(), vspoke.size(), s));
-  GRMP_TRY(d_spokes.upload(spokes.data(), spokes.size(), s));
-  GRMP_TRY(out->dscratch.alloc(std::max<size_t>(spoke_ptr[ncols], 1)));
   GRMP_TRY(out->tile_counter.alloc(1));
   GRMP_CUDA(cudaMemsetAsync(out->tile_counter.p, 0, sizeof(int), s));
-  // (3) pack column / pair records into the tile blobs on the device (slots are looked up in the pattern by (row, col))
-  DevBuf<u32> d_cell, d_io, d_code, d_colof, d_coltile, d_colpq, d_abase;
+  // (3) pack column / pair records into the tile blobs on the device (slots are looked up in the pattern by (row, col)),
+  //     sort every tile's mirror candidates by destination slot
+  const i64 nmir_total = mir_base.back();
+  DevBuf<u32> d_cell, d_io, d_code, d_colof, d_coltile, d_colpq, d_abase, d_mkey, d_mval, d_mkey2, d_mval2;
   DevBuf<unsigned char> d_closed;
   GRMP_TRY(d_cell.upload(pair_cell.data(), npairs, s)); GRMP_TRY(d_io.upload(pair_io.data(), npairs, s));
   GRMP_TRY(d_code.upload(pair_code.data(), npairs, s)); GRMP_TRY(d_colof.upload(col_of_pair.data(), npairs, s));
   GRMP_TRY(d_closed.upload(col_closed.data(), ncols, s));
   GRMP_TRY(d_coltile.upload(col_tile.data(), ncols, s)); GRMP_TRY(d_colpq.upload(col_pq.data(), ncols, s));
   GRMP_TRY(d_abase.upload(col_abase.data(), ncols, s));
+  GRMP_TRY(d_mkey.alloc(std::max<i64>(nmir_total, 1))); GRMP_TRY(d_mval.alloc(std::max<i64>(nmir_total, 1)));
+  GRMP_TRY(d_mkey2.alloc(std::max<i64>(nmir_total, 1))); GRMP_TRY(d_mval2.alloc(std::max<i64>(nmir_total, 1)));
+  GRMP_CUDA(cudaMemsetAsync(d_mkey.p, 0xff, d_mkey.bytes(), s));
   GRMP_TRY(out->blob.alloc(std::max<size_t>((size_t)blob_total16 * 16, 16)));
   GRMP_CUDA(cudaMemsetAsync(out->blob.p, 0, out->blob.bytes(), s));
   out->end_slots.release();
   if (any_end) GRMP_TRY(out->end_slots.alloc(std::max<i64>(npairs, 1)));
   PackParams pp{d_cell.p, d_io.p, d_code.p, dg.segptr.p, pat.colptr.p, pat.rowval.p, p.e1.celldofs, d_colof.p, d_closed.p,
-                d_coltile.p, d_colpq.p, d_abase.p, d_spokes.p, reinterpret_cast<const TileHdr*>(out->tile_hdr.p), npairs, ncols, out->blob.p, out->end_slots.p};
+                d_coltile.p, d_colpq.p, d_abase.p, reinterpret_cast<const TileHdr*>(d_hdr.p), d_mirbase.p, npairs, ncols,
+                out->blob.p, out->end_slots.p, d_mkey.p, d_mval.p};
   if (npairs) pack_pairs<<<(unsigned)((npairs + 255) / 256), 256, 0, s>>>(pp);
   if (ncols) pack_cols<<<(unsigned)((ncols + 255) / 256), 256, 0, s>>>(pp);
-  if (ntiles) pack_tile_nodes<<<ntiles, 128, 0, s>>>(reinterpret_cast<const TileHdr*>(out->tile_hdr.p), d_groups.p, NW, d_nodeids.p, p.g.coords, out->blob.p);
   GRMP_CUDA(cudaGetLastError());
+  if (ntiles > 0) {
+    size_t tmp_bytes = 0;
+    GRMP_CUDA(cub::DeviceSegmentedSort::SortPairs(nullptr, tmp_bytes, d_mkey.p, d_mkey2.p, d_mval.p, d_mval2.p, (int)nmir_total, ntiles,
+                                                  d_mirbase.p, d_mirbase.p + 1, s));
+    DevBuf<unsigned char> d_tmp;
+    GRMP_TRY(d_tmp.alloc(std::max<size_t>(tmp_bytes, 16)));
+    GRMP_CUDA(cub::DeviceSegmentedSort::SortPairs(d_tmp.p, tmp_bytes, d_mkey.p, d_mkey2.p, d_mval.p, d_mval2.p, (int)nmir_total, ntiles,
+                                                  d_mirbase.p, d_mirbase.p + 1, s));
+    pack_tile_rest<<<ntiles, 128, 0, s>>>(reinterpret_cast<const TileHdr*>(d_hdr.p), d_groups.p, NW, d_nodeids.p, p.g.coords, d_mirbase.p,
+                                          d_mkey2.p, d_mval2.p, out->blob.p);
+    GRMP_CUDA(cudaGetLastError());
+    GRMP_CUDA(cudaStreamSynchronize(s));      // d_tmp and the sort buffers go out of scope below
+  }
   // (4) vertex columns: list + diagonal slots
   GRMP_TRY(out->vcols.upload(vcols.data(), vcols.size(), s));
   GRMP_TRY(out->vrec.alloc(vcols.size()));
   if (out->nvcols > 0) {
-    find_diag_slots<<<(unsigned)((out->nvcols + 255) / 256), 256, 0, s>>>(out->vcols.p, d_vspoke.p, out->nvcols, pat.colptr.p, pat.rowval.p, out->vrec.p);
+    find_diag_slots<<<(unsigned)((out->nvcols + 255) / 256), 256, 0, s>>>(out->vcols.p, out->nvcols, pat.colptr.p, pat.rowval.p, out->vrec.p);
     GRMP_CUDA(cudaGetLastError());
   }
   const int smem_attr = (int)std::max<i64>(max_smem, 1024);
@@ -832,7 +868,7 @@ template <int NW> int launch_edge(const EdgeParams& ep, const FastP2Tet& f, int 
 int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const FastP2Tet& f, double* nzval) {
   static const int dbg = getenv("GRMP_DEBUG_FLAGS") ? atoi(getenv("GRMP_DEBUG_FLAGS")) : 0;
   if (f.ntiles > 0) {
-    EdgeParams ep{f.tile_dir.p, f.blob.p, f.end_slots.p, f.dscratch.p, p.factor, nzval, f.tile_counter.p, f.ntiles, f.in_stride, f.slot_elems, dbg};
+    EdgeParams ep{f.tile_dir.p, f.blob.p, f.end_slots.p, p.factor, nzval, f.tile_counter.p, f.ntiles, f.in_stride, f.slot_elems, dbg};
     switch (f.nw) {
       case 3: GRMP_TRY(launch_edge<3>(ep, f, ctx->sm_count, ctx->stream)); break;
       case 4: GRMP_TRY(launch_edge<4>(ep, f, ctx->sm_count, ctx->stream)); break;
@@ -843,9 +879,9 @@ int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pa
     GRMP_CUDA(cudaGetLastError());
   }
   if (f.nvcols > 0 && !(dbg & 2)) {
-    p2tet_vertex_diag_kernel<<<(unsigned)((f.nvcols + 255) / 256), 256, 0, ctx->stream>>>(f.vrec.p, f.nvcols, f.dscratch.p, nzval, f.tile_counter.p);
+    p2tet_vertex_diag_kernel<<<(unsigned)((f.nvcols * 8 + 255) / 256), 256, 0, ctx->stream>>>(f.vrec.p, f.nvcols, nzval, f.tile_counter.p);
     GRMP_CUDA(cudaGetLastError());
-  } else {
+  } else if (f.ntiles > 0) {
     GRMP_CUDA(cudaMemsetAsync(f.tile_counter.p, 0, sizeof(int), ctx->stream));
   }
   return GRMP_OK;
