@@ -164,7 +164,7 @@ static int fill_blf_params(grmp_blf* b, double factor, BlfLocalParams* p) {
 static int blf_numeric_launch(grmp_blf* b, BlfLocalParams& p, cudaStream_t s) {
   grmp_ctx* ctx = b->s1->grid->ctx;
   if (b->path == GRMP_PATH_FAST) {
-    GRMP_TRY(fast_p2tet_numeric(ctx, p, b->pat, b->fast, b->nzval.p));
+    GRMP_TRY(fast_p2tet_numeric(ctx, p, b->pat, b->fast, b->s1->grid->geom_version, b->nzval.p));
     b->st.kernel_launches = 2;
   } else {
     const size_t nl = (size_t)p.e1.nd * p.e2.nd * p.g.ncells;
@@ -257,6 +257,7 @@ int grmp_grid_update_geometry(grmp_grid* g, const double* coords, const double* 
   if (g->dim == 3) GRMP_TRY(launch_pad_coords(g->coords.p, g->nnodes, g->coords4.p, s));
   GRMP_TRY(g->vol.upload(cellvolumes, (size_t)g->ncells, s));
   GRMP_CUDA(cudaStreamSynchronize(s));
+  g->geom_version++;
   return GRMP_OK;
 }
 
@@ -355,7 +356,7 @@ int grmp_blf_symbolic(grmp_blf* b, double factor, int64_t* nnz_out) {
   GRMP_TRY(b->nzval.alloc(b->pat.nnz));
   b->path = GRMP_PATH_GENERIC;
   if (want_fast) {
-    const int rc = fast_p2tet_build(ctx, p, b->pat, b->w_host, b->t1_derivs_host, b->ncols_owned, &b->fast);
+    const int rc = fast_p2tet_build(ctx, p, b->pat, b->w_host, b->t1_derivs_host, b->ncols_owned, b->s1->grid->geom_version, &b->fast);
     b->pat.slotmap.release();
     if (rc == GRMP_OK) b->path = GRMP_PATH_FAST;
     else if (rc != GRMP_EUNSUPPORTED || b->path_req == GRMP_PATH_FAST) return rc;   // AUTO: grids the fast path cannot order use the generic path

@@ -116,6 +116,7 @@ struct grmp_grid {
   grmp::DevBuf<double> coords, coords4, vol, fnormals, fvol;
   grmp::DevBuf<grmp::i32> cellnodes, regions, cellfaces, signs, orient;
   bool has_regions = false, has_faces = false;
+  grmp::i64 geom_version = 0;     // bumped by grmp_grid_update_geometry (the fast path keeps tile-blocked coordinate copies)
   grmp::GridView view() const;
 };
 

@@ -13,6 +13,9 @@ struct FastP2Tet {
   int smem_bytes = 0;
   u32 slot_elems = 0;             // doubles per warp stage slot
   u32 in_stride = 0;              // bytes of one input buffer of the kernel's 2-deep ring (largest blob)
+  i64 geom_version = 0;           // grmp_grid::geom_version the blobs' node coordinates were packed from
+  DevBuf<int4> tile_hdr;          // 3 per tile (TileHdr), kept for re-packing the coordinates
+  DevBuf<u32> tile_nodeids;       // distinct nodes of every tile (1-based), kept for re-packing the coordinates
   DevBuf<uint2> tile_dir;         // per tile: blob offset (16-byte units), blob bytes
   DevBuf<unsigned char> blob;     // per tile: header, group table, column / pair records, node coordinates, sorted mirror list
   DevBuf<u32> end_slots;          // per pair, only when a partition produced multi-chain halo columns
@@ -24,7 +27,7 @@ struct FastP2Tet {
 
 bool fast_p2tet_applicable(const BlfLocalParams& p);
 int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const std::vector<double>& w,
-                     const std::vector<double>& derivs, i64 ncols_owned, FastP2Tet* out);
-int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const FastP2Tet& f, double* nzval);
+                     const std::vector<double>& derivs, i64 ncols_owned, i64 geom_version, FastP2Tet* out);
+int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, FastP2Tet& f, i64 geom_version, double* nzval);
 
 }  // namespace grmp

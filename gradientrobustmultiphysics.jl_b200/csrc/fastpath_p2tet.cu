@@ -54,7 +54,8 @@ namespace grmp {
 
 namespace {
 
-constexpr int NW_DEFAULT = 7;                     // consumer warps per CTA (+ 1 service warp)
+constexpr int NW_DEFAULT = 7;                     // consumer warps per CTA
+constexpr int NSVC = 1;                           // service warps per CTA (tile loads, mirror write-out)
 constexpr int SLOT_DEFAULT = 800;                 // nzval entries a warp may stage per group (32 columns x ~23 rows)
 __host__ inline i64 smem_budget_default(int nw) { return 1024 * (i64)(nw >= 5 ? 112 : nw == 4 ? 74 : 55); }   // 2 / 3 / 4 CTAs per SM
 constexpr u32 NONE = 0xffffffffu;
@@ -240,6 +241,16 @@ __global__ void pack_tile_rest(const TileHdr* hdr, const uint2* groups, int nw, 
   }
 }
 
+// the grid's coordinates changed (grmp_grid_update_geometry): refresh the tile-blocked copies inside the blobs
+__global__ void repack_tile_coords(const TileHdr* hdr, const u32* tile_nodeids, const double* coords, unsigned char* blob) {
+  const TileHdr h = hdr[blockIdx.x];
+  double* X = reinterpret_cast<double*>(blob + (size_t)h.blob16 * 16 + off_xyz(h.cols_off, (u32)h.ncol, (u32)h.npairs));
+  for (int i = threadIdx.x; i < h.nnodes; i += blockDim.x) {
+    const double* xg = coords + (size_t)(tile_nodeids[(size_t)h.node_base + i] - 1) * 3;
+    X[3 * i] = xg[0]; X[3 * i + 1] = xg[1]; X[3 * i + 2] = xg[2];
+  }
+}
+
 struct EdgeParams {
   const uint2* tile_dir;    // per tile: blob offset (16-byte units), blob bytes
   const unsigned char* blob;
@@ -287,14 +298,24 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar_a, unsigned parity) {
 }
 
 // service warp: the tile's parked mirror values -> their slots in the vertex columns, in destination order
-__device__ __forceinline__ void mirror_writeout(const EdgeParams& p, const unsigned char* in, int lane) {
+__device__ __forceinline__ void mirror_writeout(const EdgeParams& p, const unsigned char* in, int lane, int nlanes) {
   const int4 h0 = reinterpret_cast<const int4*>(in)[0], h2 = reinterpret_cast<const int4*>(in)[2];
   const u32 ncol = (u32)h0.y, nnodes = (u32)h0.z, npairs = (u32)h0.w, nmir = (u32)h2.y, cols_off = (u32)h2.w;
   const u32* __restrict__ md = reinterpret_cast<const u32*>(in + off_mdst(cols_off, ncol, npairs, nnodes));
   const unsigned short* __restrict__ ms = reinterpret_cast<const unsigned short*>(in + off_msrc(cols_off, ncol, npairs, nnodes));
   const double* __restrict__ words = reinterpret_cast<const double*>(in);
-#pragma unroll 4
-  for (u32 i = lane; i < nmir; i += 32) p.nzval[md[i]] = words[ms[i]];
+  u32 i = lane;
+  for (; i + 7 * nlanes < nmir; i += 8 * nlanes) {    // 8 independent gather/store chains per lane
+    u32 d[8], w[8];
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) { d[u] = md[i + u * nlanes]; w[u] = ms[i + u * nlanes]; }
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = words[w[u]];
+#pragma unroll
+    for (int u = 0; u < 8; u++) p.nzval[d[u]] = v[u];
+  }
+  for (; i < nmir; i += nlanes) p.nzval[md[i]] = words[ms[i]];
 }
 
 // Persistent CTAs of NW consumer warps + 1 service warp.  Tiles are claimed from a global counter.  The service warp keeps the
@@ -302,10 +323,11 @@ __device__ __forceinline__ void mirror_writeout(const EdgeParams& p, const unsig
 // writes its mirror values out and reuses the buffer.  Consumer warp w owns group w of every tile, stages the group's nzval
 // range in its own slot and stores it with its own TMA bulk store.  No CTA-wide barrier after the set-up.
 template <int NW>
-__global__ void __launch_bounds__((NW + 1) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 : 4)) p2tet_edge_kernel(const EdgeParams p) {
+__global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 : 4)) p2tet_edge_kernel(const EdgeParams p) {
   extern __shared__ __align__(128) unsigned char smraw[];
   __shared__ __align__(8) unsigned long long mbar[4];      // full[0], full[1], done[0], done[1]
   __shared__ int s_tile[2];                                // tile in each input buffer, -1 = no more tiles
+  __shared__ int s_next;                                   // service warps: tile claimed for the next load
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned full_a = (unsigned)__cvta_generic_to_shared(&mbar[0]), done_a = full_a + 16;
   const unsigned in_a = (unsigned)__cvta_generic_to_shared(smraw);
@@ -318,33 +340,36 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 : 4)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  if (warp == NW) {   // ---- service warp ----
+  if (warp >= NW) {   // ---- service warps ----
     const u64 pol_stream = l2_policy_evict_first();
+    const int slane = tid - NW * 32;                        // 0 .. 32 NSVC - 1; thread 0 of the service warps loads tiles
     int it = 0;
     for (;; it++) {
       const int b = it & 1;
       int t = 0;
       uint2 dir = make_uint2(0, 0);
-      if (lane == 0) {
+      if (slane == 0) {
         // tiles are claimed dynamically: SMs do not run at the same speed, a static split leaves the slowest SM as the tail
         t = atomicAdd(p.tile_counter, 1);
         if (t < p.ntiles) dir = __ldg(p.tile_dir + t);
       }
       if (it >= 2) {
         mbar_wait(done_a + 8 * b, (unsigned)((it >> 1) - 1) & 1u);   // all consumer warps have left the tile in this buffer
-        if (!(p.dbg & 1)) mirror_writeout(p, smraw + (size_t)b * p.in_stride, lane);
+        if (!(p.dbg & 1)) mirror_writeout(p, smraw + (size_t)b * p.in_stride, slane, 32 * NSVC);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // parked values (generic writes) before the next bulk load
-        __syncwarp();
       }
-      t = __shfl_sync(0xffffffffu, t, 0);
+      if (slane == 0) s_next = t;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * NSVC) : "memory");     // write-out finished by all service warps; s_next visible
+      t = *reinterpret_cast<volatile int*>(&s_next);
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * NSVC) : "memory");     // everybody has read s_next
       if (t >= p.ntiles) {
-        if (lane == 0) {
+        if (slane == 0) {
           s_tile[b] = -1;
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_a + 8 * b) : "memory");
         }
         break;
       }
-      if (lane == 0) {
+      if (slane == 0) {
         s_tile[b] = t;
         tile_load(p, dir, in_a + b * p.in_stride, full_a + 8 * b, pol_stream);
       }
@@ -352,7 +377,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 : 4)
     if (it >= 1) {   // the other buffer still holds the last tile
       const int b2 = (it - 1) & 1;
       mbar_wait(done_a + 8 * b2, (unsigned)((it - 1) >> 1) & 1u);
-      if (!(p.dbg & 1)) mirror_writeout(p, smraw + (size_t)b2 * p.in_stride, lane);
+      if (!(p.dbg & 1)) mirror_writeout(p, smraw + (size_t)b2 * p.in_stride, slane, 32 * NSVC);
     }
     return;
   }
@@ -408,6 +433,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 : 4)
         double R1 = 0.0, R2 = 0.0, R3 = 0.0;            // ring sums of S'_pq, S'_pi + S'_po, S'_qi + S'_qo
         double c0r = 0.0, c1r = 0.0, c2r = 0.0;          // carry: partial rows of the shared ring vertex
         double f0 = 0.0, f1 = 0.0, f2 = 0.0;             // closed ring: in-rows of the first pair, completed at the end
+#pragma unroll 2
         for (u32 k = 0; k < np; k++) {
           // software pipeline: out-vertex of the next pair, record after next
           const u32 ln = (r1.y >> 12) & 0xfffu;
@@ -589,7 +615,7 @@ bool fast_p2tet_applicable(const BlfLocalParams& p) {
 }
 
 int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const std::vector<double>& w,
-                     const std::vector<double>& derivs, i64 ncols_owned, FastP2Tet* out) {
+                     const std::vector<double>& derivs, i64 ncols_owned, i64 geom_version, FastP2Tet* out) {
   // halo columns (>= ncols_owned) are processed too: their mirrors complete the owned vertex columns;
   // only they may consist of several chains (cells around a halo edge are present only where they touch an owned dof)
   cudaStream_t s = ctx->stream;
@@ -633,6 +659,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   if (BLOB_CAP < 4096) return fail(GRMP_EUNSUPPORTED, "fast path: shared-memory budget too small for the tile shape");
   const u32 cols_off = 48u + pad16(8u * (u32)(NW + 1));
   out->nw = NW;
+  out->geom_version = geom_version;
   // (2) host: ring order of every edge column, tiles over the edge columns, list of vertex columns
   std::vector<u32> pair_cell(npairs), pair_io(npairs), pair_code(npairs), col_of_pair(npairs), vcols;
   std::vector<unsigned char> col_closed(ncols, 2);
@@ -795,9 +822,9 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   if (vcols.empty()) vcols.push_back(0);
   std::vector<uint2> tile_dir(hdr.size());
   for (size_t t2 = 0; t2 < hdr.size(); t2++) tile_dir[t2] = make_uint2(hdr[t2].blob16, hdr[t2].blob_bytes);
-  DevBuf<u32> d_nodeids;
   DevBuf<uint2> d_groups;
-  DevBuf<int4> d_hdr;
+  DevBuf<u32>& d_nodeids = out->tile_nodeids;
+  DevBuf<int4>& d_hdr = out->tile_hdr;
   DevBuf<int> d_mirbase;
   GRMP_TRY(d_groups.upload(groups.data(), groups.size(), s));
   GRMP_TRY(d_hdr.upload(reinterpret_cast<const int4*>(hdr.data()), hdr.size() * 3, s));
@@ -858,15 +885,20 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
 
 template <int NW> int launch_edge(const EdgeParams& ep, const FastP2Tet& f, int sm_count, cudaStream_t s) {
   int per_sm = 0;
-  GRMP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p2tet_edge_kernel<NW>, (NW + 1) * 32, (size_t)f.smem_bytes));
+  GRMP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p2tet_edge_kernel<NW>, (NW + NSVC) * 32, (size_t)f.smem_bytes));
   if (per_sm < 1) return fail(GRMP_ECUDA, "fast path: edge kernel does not fit on an SM");
   const int grid = std::min(f.ntiles, per_sm * sm_count);
-  p2tet_edge_kernel<NW><<<grid, (NW + 1) * 32, f.smem_bytes, s>>>(ep);
+  p2tet_edge_kernel<NW><<<grid, (NW + NSVC) * 32, f.smem_bytes, s>>>(ep);
   return GRMP_OK;
 }
 
-int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const FastP2Tet& f, double* nzval) {
+int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, FastP2Tet& f, i64 geom_version, double* nzval) {
   static const int dbg = getenv("GRMP_DEBUG_FLAGS") ? atoi(getenv("GRMP_DEBUG_FLAGS")) : 0;
+  if (f.ntiles > 0 && f.geom_version != geom_version) {
+    repack_tile_coords<<<f.ntiles, 128, 0, ctx->stream>>>(reinterpret_cast<const TileHdr*>(f.tile_hdr.p), f.tile_nodeids.p, p.g.coords, f.blob.p);
+    GRMP_CUDA(cudaGetLastError());
+    f.geom_version = geom_version;
+  }
   if (f.ntiles > 0) {
     EdgeParams ep{f.tile_dir.p, f.blob.p, f.end_slots.p, p.factor, nzval, f.tile_counter.p, f.ntiles, f.in_stride, f.slot_elems, dbg};
     switch (f.nw) {

@@ -304,6 +304,41 @@ def test_fast_p2tet_matches_generic_and_is_deterministic():
     assert abs(A - A.T).max() < 1e-12 * np.abs(b[2]).max()
 
 
+def test_fast_p2tet_follows_geometry_updates():
+    """the fast path keeps tile-blocked copies of the node coordinates: grmp_grid_update_geometry must refresh them"""
+    g = tet_grid(2, True)
+    s = G.FESpace(G.H1P2(1, 3), g)
+    AP = G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [s, s])
+    G.blf_set_path(AP, G._lib.PATH_FAST)
+    G.assemble_csc(AP, 1.0)
+    # stretch the grid anisotropically (volumes scale by 6, the stiffness entries change non-uniformly)
+    g2 = tet_grid(2, True)
+    g2.coords[:, 0] *= 2.0
+    g2.coords[:, 2] *= 3.0
+    vol2 = np.ascontiguousarray(g.cellvolumes * 6.0)
+    L = G._lib.lib()
+    G._lib.check(L.grmp_grid_update_geometry(G.device_grid(g), G._lib.ptr(np.ascontiguousarray(g2.coords)), G._lib.ptr(vol2)))
+    _, _, nz = G.assemble_csc(AP, 1.0, skip_preps=True)
+    s2 = G.FESpace(G.H1P2(1, 3), g2)
+    AP2 = G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [s2, s2])
+    G.blf_set_path(AP2, G._lib.PATH_GENERIC)
+    _, _, ref = G.assemble_csc(AP2, 1.0)
+    assert rel_err(nz, ref) <= RTOL
+
+
+@pytest.mark.parametrize("nw,slot,kb", [(3, 256, 24), (4, 300, 40), (7, 800, 112), (5, 512, 64)])
+def test_fast_p2tet_tile_shapes(nw, slot, kb, monkeypatch):
+    """tiles / warp groups cut at different places (shared-memory budget, slot size, #consumer warps) give the same matrix"""
+    monkeypatch.setenv("GRMP_FAST_NW", str(nw))
+    monkeypatch.setenv("GRMP_FAST_SLOT", str(slot))
+    monkeypatch.setenv("GRMP_FAST_SMEM_KB", str(kb))
+    g = tet_grid(3, True)
+    s = G.FESpace(G.H1P2(1, 3), g)
+    AP = G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [s, s])
+    check_blf(AP, factor=1.25, exact=False, path=G._lib.PATH_FAST)
+    assert G.blf_stats(AP).ntiles > 8
+
+
 def test_fast_p2tet_region_filter_falls_back_correctly():
     g = tet_grid(1)
     g.cellregions[::2] = 2
