@@ -34,9 +34,9 @@
 //     tile's values for one vertex column form one run of consecutive addresses.  Scattered
 //     8-byte stores are the scarce resource of this kernel: the device retires ~1e11 partial
 //     32-byte sector writes per second, half the rate of full sectors (tools/write_bw.cu).
-//   diagonal kernel (p2tet_vertex_diag_kernel): the columns of a stiffness matrix sum to zero
-//     (the basis is a partition of unity), so A[v,v] = -sum_{i != v} A[i,v]; one warp per vertex
-//     column, fixed reduction tree.
+//   diagonal kernel (p2tet_vertex_diag_kernel): the vertex-vertex block is the P1 stiffness matrix
+//     scaled entrywise by 0.6 (diagonal) / -0.2 (off-diagonal) and P1 columns sum to zero, so
+//     A[v,v] = 3 * sum of the vertex rows w != v of column v; eight lanes per column, fixed tree.
 //
 // No atomics on values, fixed summation orders -> deterministic.  Values agree with the reference's
 // order of operations to rounding (tests/test_gpu_parity.py states the tolerance); the PATTERN
@@ -535,47 +535,55 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
   if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must stay alive until read
 }
 
-// The columns of a stiffness matrix sum to zero (sum_i phi_i = 1): A[v,v] = -sum_{i != v} A[i,v].  Eight lanes per vertex
-// column (a column has ~65 entries), every lane keeps up to 8 independent loads in flight, fixed shuffle tree -> deterministic.
+// Diagonal of the vertex columns.  The vertex-vertex block of the P2 stiffness matrix is the P1 stiffness matrix K1 scaled
+// entrywise (A[v,v] = 0.6 K1[v,v], A[w,v] = -0.2 K1[w,v]: the local vertex-vertex block is 0.6 / -0.2 S), and the columns of
+// K1 sum to zero (the P1 basis is a partition of unity), hence A[v,v] = 3 * sum_{w != v} A[w,v] over the VERTEX rows w of the
+// column only -- ~15 of its ~65 entries, every one of them mirrored into place by the edge kernel.  Eight lanes per column,
+// fixed shuffle tree -> deterministic.  vrec: {diagonal slot | NONE, first slot, #slots (<= 96), 0}, {row-is-vertex mask x3, 0}.
 // Also re-arms the edge kernel's tile scheduler.
 __global__ void __launch_bounds__(256) p2tet_vertex_diag_kernel(const uint4* __restrict__ vrec, i64 nv, double* nzval, int* tile_counter) {
   const i64 w = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 3;
   const int sub = threadIdx.x & 7;
   if (blockIdx.x == 0 && threadIdx.x == 0) *tile_counter = 0;
-  uint4 r = make_uint4(NONE, 0, 0, 0);     // {diagonal slot | NONE, first slot of the column, #slots, 0}
-  if (w < nv) r = __ldg(vrec + w);
+  uint4 r = make_uint4(NONE, 0, 0, 0), m = make_uint4(0, 0, 0, 0);
+  if (w < nv) { r = __ldg(vrec + 2 * w); m = __ldg(vrec + 2 * w + 1); }
   double s = 0.0;
   if (r.x != NONE) {
     const double* __restrict__ c = nzval + r.y;
     const u32 d = r.x - r.y;
-    u32 k = sub;
-    for (; k + 56 < r.z; k += 64) {
-      double v[8];
+    double v[12];
 #pragma unroll
-      for (int u = 0; u < 8; u++) v[u] = c[k + 8 * u];
-#pragma unroll
-      for (int u = 0; u < 8; u++) s += (k + 8 * u == d) ? 0.0 : v[u];
+    for (int u = 0; u < 12; u++) {          // slot k = sub + 8 u < 96: all loads are independent
+      const u32 k = sub + 8 * u;
+      const u32 word = u < 4 ? m.x : (u < 8 ? m.y : m.z);
+      const bool take = k < r.z && k != d && ((word >> (k & 31)) & 1u);
+      v[u] = take ? c[k] : 0.0;
     }
-    for (; k < r.z; k += 8) s += (k == d) ? 0.0 : c[k];
+#pragma unroll
+    for (int u = 0; u < 12; u++) s += v[u];
   }
   s += __shfl_xor_sync(0xffffffffu, s, 4);
   s += __shfl_xor_sync(0xffffffffu, s, 2);
   s += __shfl_xor_sync(0xffffffffu, s, 1);
-  if (sub == 0 && r.x != NONE) nzval[r.x] = -s;
+  if (sub == 0 && r.x != NONE) nzval[r.x] = 3.0 * s;
 }
 
-__global__ void find_diag_slots(const u32* vcols, i64 nv, const i64* colptr, const i64* rowval, uint4* vrec) {
+// is_vertex[row] != 0 marks vertex dofs.  Columns with more than 96 entries cannot use the mask: fails -> generic path.
+__global__ void find_diag_slots(const u32* vcols, i64 nv, const i64* colptr, const i64* rowval, const unsigned char* col_kind, uint4* vrec, int* too_long) {
   i64 w = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (w >= nv) return;
   const i64 col = vcols[w];
   const i64 beg = colptr[col] - 1, end = colptr[col + 1] - 1;
-  i64 lo = beg, hi = end;
-  while (lo < hi) {
-    i64 mid = (lo + hi) >> 1;
-    if (rowval[mid] < col + 1) lo = mid + 1; else hi = mid;
-  }
-  const u32 d = (lo < end && rowval[lo] == col + 1) ? (u32)lo : NONE;
-  vrec[w] = make_uint4(d, (u32)beg, (u32)(end - beg), 0);
+  u32 d = NONE, mask[3] = {0, 0, 0};
+  if (end - beg > 96) { atomicExch(too_long, 1); }
+  else
+    for (i64 k = beg; k < end; k++) {
+      const i64 row = rowval[k] - 1;
+      if (row == col) d = (u32)k;
+      else if (col_kind[row] == 2) mask[(k - beg) >> 5] |= 1u << ((k - beg) & 31);
+    }
+  vrec[2 * w] = make_uint4(d, (u32)beg, (u32)(end - beg), 0);
+  vrec[2 * w + 1] = make_uint4(mask[0], mask[1], mask[2], 0);
 }
 
 // closed-form local stiffness of the unit reference tetrahedron, used to verify that the
@@ -871,10 +879,17 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   }
   // (4) vertex columns: list + diagonal slots
   GRMP_TRY(out->vcols.upload(vcols.data(), vcols.size(), s));
-  GRMP_TRY(out->vrec.alloc(vcols.size()));
+  GRMP_TRY(out->vrec.alloc(2 * vcols.size()));
   if (out->nvcols > 0) {
-    find_diag_slots<<<(unsigned)((out->nvcols + 255) / 256), 256, 0, s>>>(out->vcols.p, out->nvcols, pat.colptr.p, pat.rowval.p, out->vrec.p);
+    // tile_counter doubles as the "a vertex column is too long" flag here (it is reset to zero below)
+    find_diag_slots<<<(unsigned)((out->nvcols + 255) / 256), 256, 0, s>>>(out->vcols.p, out->nvcols, pat.colptr.p, pat.rowval.p, d_closed.p, out->vrec.p,
+                                                                             out->tile_counter.p);
     GRMP_CUDA(cudaGetLastError());
+    int too_long = 0;
+    GRMP_CUDA(cudaMemcpyAsync(&too_long, out->tile_counter.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    GRMP_CUDA(cudaStreamSynchronize(s));
+    GRMP_CUDA(cudaMemsetAsync(out->tile_counter.p, 0, sizeof(int), s));
+    if (too_long) return fail(GRMP_EUNSUPPORTED, "fast path: a vertex column has more than 96 entries");
   }
   const int smem_attr = (int)std::max<i64>(max_smem, 1024);
   GRMP_TRY(set_smem_attr<3>(smem_attr)); GRMP_TRY(set_smem_attr<4>(smem_attr)); GRMP_TRY(set_smem_attr<5>(smem_attr));
