@@ -229,7 +229,7 @@ def run_gpu(args):
     tr = _traffic()
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": (tr or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
-                "kernel": "p2tet_edge_kernel (+ p2tet_vertex_diag_kernel, ~5 % of the step; duration = whole step)" if st.path == 2
+                "kernel": "p2tet_edge_kernel (+ p2tet_vertex_diag_kernel, ~10 % of the step; duration = whole step)" if st.path == 2
                 else "blf_local_kernel+gather_kernel",
                 "algorithmic_bytes_per_launch": int(b_alg), "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)}
     cpu = cpu_baseline(args.cpu_level) if world == 1 or True else None
