@@ -9,6 +9,7 @@ namespace grmp {
 struct FastP2Tet {
   int ntiles = 0;
   int nw = 7;                     // consumer warps per CTA
+  int nbuf = 2;                   // depth of the input ring
   i64 npairs = 0;
   int smem_bytes = 0;
   u32 slot_elems = 0;             // doubles per warp stage slot

@@ -261,6 +261,7 @@ struct EdgeParams {
   int ntiles;
   u32 in_stride;            // bytes of one input buffer (largest blob)
   u32 slot_elems;           // doubles per warp stage slot
+  int nbuf;                 // depth of the input ring (2 or 3)
   int dbg;                  // GRMP_DEBUG_FLAGS (timing experiments only): 1 skip mirrored stores, 4 skip the ring walk, 8 skip the bulk store
 };
 
@@ -325,17 +326,18 @@ __device__ __forceinline__ void mirror_writeout(const EdgeParams& p, const unsig
 template <int NW>
 __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 : 4)) p2tet_edge_kernel(const EdgeParams p) {
   extern __shared__ __align__(128) unsigned char smraw[];
-  __shared__ __align__(8) unsigned long long mbar[4];      // full[0], full[1], done[0], done[1]
-  __shared__ int s_tile[2];                                // tile in each input buffer, -1 = no more tiles
+  __shared__ __align__(8) unsigned long long mbar[6];      // full[0..2], done[0..2]
+  __shared__ int s_tile[3];                                // tile in each input buffer, -1 = no more tiles
   __shared__ int s_next;                                   // service warps: tile claimed for the next load
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const unsigned full_a = (unsigned)__cvta_generic_to_shared(&mbar[0]), done_a = full_a + 16;
+  const unsigned full_a = (unsigned)__cvta_generic_to_shared(&mbar[0]), done_a = full_a + 24;
+  const int NB = p.nbuf;
   const unsigned in_a = (unsigned)__cvta_generic_to_shared(smraw);
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_a));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_a + 8));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(done_a), "r"(NW));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(done_a + 8), "r"(NW));
+    for (int b = 0; b < 3; b++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_a + 8 * b));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(done_a + 8 * b), "r"(NW));
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -344,8 +346,8 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
     const u64 pol_stream = l2_policy_evict_first();
     const int slane = tid - NW * 32;                        // 0 .. 32 NSVC - 1; thread 0 of the service warps loads tiles
     int it = 0;
+    int b = 0, use = 0;                                       // buffer of iteration it, how often it has been filled before
     for (;; it++) {
-      const int b = it & 1;
       int t = 0;
       uint2 dir = make_uint2(0, 0);
       if (slane == 0) {
@@ -353,8 +355,8 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
         t = atomicAdd(p.tile_counter, 1);
         if (t < p.ntiles) dir = __ldg(p.tile_dir + t);
       }
-      if (it >= 2) {
-        mbar_wait(done_a + 8 * b, (unsigned)((it >> 1) - 1) & 1u);   // all consumer warps have left the tile in this buffer
+      if (use >= 1) {
+        mbar_wait(done_a + 8 * b, (unsigned)(use - 1) & 1u);   // all consumer warps have left the tile in this buffer
         if (!(p.dbg & 1)) mirror_writeout(p, smraw + (size_t)b * p.in_stride, slane, 32 * NSVC);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // parked values (generic writes) before the next bulk load
       }
@@ -373,21 +375,22 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
         s_tile[b] = t;
         tile_load(p, dir, in_a + b * p.in_stride, full_a + 8 * b, pol_stream);
       }
+      if (++b == NB) { b = 0; use++; }
     }
-    if (it >= 1) {   // the other buffer still holds the last tile
-      const int b2 = (it - 1) & 1;
-      mbar_wait(done_a + 8 * b2, (unsigned)((it - 1) >> 1) & 1u);
+    // the other buffers still hold the last NB - 1 tiles (iterations it - NB + 1 .. it - 1)
+    for (int j = (it >= NB - 1 ? it - (NB - 1) : 0); j < it; j++) {
+      const int b2 = j % NB;
+      mbar_wait(done_a + 8 * b2, (unsigned)(j / NB) & 1u);
       if (!(p.dbg & 1)) mirror_writeout(p, smraw + (size_t)b2 * p.in_stride, slane, 32 * NSVC);
     }
     return;
   }
   // ---- consumers ----
   const u64 pol_stream = l2_policy_evict_first();
-  double* const slot = reinterpret_cast<double*>(smraw + 2 * (size_t)p.in_stride) + (size_t)warp * p.slot_elems;
-  for (int it = 0;; it++) {
-    const int cur = it & 1;
+  double* const slot = reinterpret_cast<double*>(smraw + (size_t)NB * p.in_stride) + (size_t)warp * p.slot_elems;
+  for (int it = 0, cur = 0, use = 0;; it++) {
     unsigned char* in = smraw + (size_t)cur * p.in_stride;
-    mbar_wait(full_a + 8 * cur, (unsigned)(it >> 1) & 1u);
+    mbar_wait(full_a + 8 * cur, (unsigned)use & 1u);
     if (*reinterpret_cast<volatile int*>(&s_tile[cur]) < 0) break;
     const int4 h0 = reinterpret_cast<const int4*>(in)[0], h1 = reinterpret_cast<const int4*>(in)[1], h2 = reinterpret_cast<const int4*>(in)[2];
     const uint2 gr0 = reinterpret_cast<const uint2*>(in + 48)[warp], gr1 = reinterpret_cast<const uint2*>(in + 48)[warp + 1];
@@ -531,6 +534,7 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
       if (lane == 1 && i0 == 1 && nnz_w > 0) dst[0] = stage[0];
       if (lane == 2 && i0 + nb < nnz_w) dst[i0 + nb] = stage[i0 + nb];
     }
+    if (++cur == NB) { cur = 0; use++; }
   }
   if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must stay alive until read
 }
@@ -663,10 +667,13 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   const i64 SLOT_CAP = getenv("GRMP_FAST_SLOT") ? std::max(256, atoi(getenv("GRMP_FAST_SLOT"))) : SLOT_DEFAULT;   // nzval entries per group
   const i64 SMEM_BUDGET = getenv("GRMP_FAST_SMEM_KB") ? 1024 * (i64)atoi(getenv("GRMP_FAST_SMEM_KB")) : smem_budget_default(NW);
   // shared memory of a CTA: 2 input buffers (largest blob) + NW stage slots
-  const i64 BLOB_CAP = ((SMEM_BUDGET - NW * 8 * (SLOT_CAP + 2)) / 2) & ~15ll;
+  int NBUF = getenv("GRMP_FAST_NBUF") ? atoi(getenv("GRMP_FAST_NBUF")) : 2;
+  if (NBUF != 2 && NBUF != 3) NBUF = 2;
+  const i64 BLOB_CAP = ((SMEM_BUDGET - NW * 8 * (SLOT_CAP + 2)) / NBUF) & ~15ll;
   if (BLOB_CAP < 4096) return fail(GRMP_EUNSUPPORTED, "fast path: shared-memory budget too small for the tile shape");
   const u32 cols_off = 48u + pad16(8u * (u32)(NW + 1));
   out->nw = NW;
+  out->nbuf = NBUF;
   out->geom_version = geom_version;
   // (2) host: ring order of every edge column, tiles over the edge columns, list of vertex columns
   std::vector<u32> pair_cell(npairs), pair_io(npairs), pair_code(npairs), col_of_pair(npairs), vcols;
@@ -818,7 +825,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   }
   close_tile(ncols);
   const i64 slot_elems = (max_slot + 2 + 1) & ~1ll;     // even: keeps every slot 16-byte aligned
-  const i64 max_smem = 2 * max_blob + NW * 8 * slot_elems;
+  const i64 max_smem = NBUF * max_blob + NW * 8 * slot_elems;
   if (max_smem > 220 * 1024) return fail(GRMP_EUNSUPPORTED, "fast path: a single column exceeds the shared-memory tile");
   if (max_blob > 8 * 65535) return fail(GRMP_EUNSUPPORTED, "fast path: tile blob exceeds the 16-bit word index of the mirror list");
   const int ntiles = (int)hdr.size();
@@ -915,7 +922,7 @@ int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pa
     f.geom_version = geom_version;
   }
   if (f.ntiles > 0) {
-    EdgeParams ep{f.tile_dir.p, f.blob.p, f.end_slots.p, p.factor, nzval, f.tile_counter.p, f.ntiles, f.in_stride, f.slot_elems, dbg};
+    EdgeParams ep{f.tile_dir.p, f.blob.p, f.end_slots.p, p.factor, nzval, f.tile_counter.p, f.ntiles, f.in_stride, f.slot_elems, f.nbuf, dbg};
     switch (f.nw) {
       case 3: GRMP_TRY(launch_edge<3>(ep, f, ctx->sm_count, ctx->stream)); break;
       case 4: GRMP_TRY(launch_edge<4>(ep, f, ctx->sm_count, ctx->stream)); break;
