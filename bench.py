@@ -11,9 +11,10 @@ of fill!(A,0) + assemble!(A, AP; skip_preps = true).  L = 6 (6 2
   value   device-resident throughput: K steps bracketed by one pair of CUDA events on the library's
           launching stream (grmp_blf_numeric_steps), inputs resident in HBM; the working set
           (nzval 1.9 GB + maps) is far larger than the 126 MB L2, so no explicit flush is needed.
-  e2e     the same metric through the reference-facing call with HOST buffers: per step the grid
-          arrays (Coordinates, CellVolumes, CellNodes, CellDofs) are copied from pinned host memory,
-          the matrix is assembled and nzval is copied back to pinned host memory.
+  e2e     the same metric through the reference-facing call with HOST buffers (grmp_blf_assemble_host): per
+          step the grid arrays (Coordinates, CellVolumes, CellNodes, CellDofs) are copied from pinned host
+          memory, the matrix is assembled and nzval is copied back to pinned host memory; the uploads the
+          kernels do not read overlap the download.
   roofline  algorithmic bytes (8 nnz + 4 ncells (nn + nd) + 8 dim nnodes) / kernel time
           against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
   cpu_baseline  the oracle's restatement of the reference loop (1 thread: the reference cell loop is
@@ -178,14 +179,12 @@ def run_gpu(args):
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
     h_coords, h_vol, h_cn, h_dofs = pin(lg.coords), pin(lg.cellvolumes), pin(lg.cellnodes), pin(ls.celldofs)
     h_nz = torch.empty(nnz.value, dtype=torch.float64).pin_memory()
-    gh, sh = G.device_grid(lg), G.device_space(ls)
     e2e_steps = max(2, min(args.steps, 5))
 
     def e2e_step():
-        G._lib.check(L.grmp_grid_update_geometry(gh, h_coords.data_ptr(), h_vol.data_ptr()))
-        G._lib.check(L.grmp_grid_update_cells(gh, h_cn.data_ptr()))
-        G._lib.check(L.grmp_space_update_dofs(sh, h_dofs.data_ptr()))
-        G._lib.check(L.grmp_blf_numeric(h, 1.0, h_nz.data_ptr()))
+        # assemble!(A, AP) with the grid in host memory: one synchronous call, all copies inside (grmp.h: grmp_blf_assemble_host)
+        G._lib.check(L.grmp_blf_assemble_host(h, 1.0, h_coords.data_ptr(), h_vol.data_ptr(), h_cn.data_ptr(), h_dofs.data_ptr(), None,
+                                              h_nz.data_ptr()))
     e2e_step()
     if world > 1:
         dist.barrier()

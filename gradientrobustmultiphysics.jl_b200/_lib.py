@@ -22,7 +22,7 @@ EXPORTS = [
     "grmp_blf_numeric_steps", "grmp_blf_set_owned_columns", "grmp_space_create", "grmp_space_destroy", "grmp_blf_create",
     "grmp_blf_destroy", "grmp_blf_set_path", "grmp_blf_symbolic", "grmp_blf_get_pattern", "grmp_blf_numeric",
     "grmp_blf_get_values", "grmp_blf_transpose_copy", "grmp_blf_stats", "grmp_blf_device_values", "grmp_lf_create",
-    "grmp_lf_destroy", "grmp_lf_assemble", "grmp_lf_stats",
+    "grmp_lf_destroy", "grmp_lf_assemble", "grmp_lf_stats", "grmp_blf_assemble_host",
 ]
 
 
@@ -79,6 +79,7 @@ def lib():
         L.grmp_blf_symbolic.argtypes = [vp, dbl, C.POINTER(i64)]
         L.grmp_blf_get_pattern.argtypes = [vp, vp, vp]
         L.grmp_blf_numeric.argtypes = [vp, dbl, vp]
+        L.grmp_blf_assemble_host.argtypes = [vp, dbl, vp, vp, vp, vp, vp, vp]
         L.grmp_blf_get_values.argtypes = [vp, vp]
         L.grmp_blf_transpose_copy.argtypes = [vp, dbl, dbl, vp, vp, vp]
         L.grmp_blf_stats.argtypes = [vp, C.POINTER(Stats)]

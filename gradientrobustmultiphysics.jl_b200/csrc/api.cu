@@ -192,8 +192,10 @@ int grmp_init(int device, grmp_ctx** out) {
   grmp_ctx* c = new grmp_ctx();
   c->device = device;
   GRMP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  GRMP_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   GRMP_CUDA(cudaEventCreate(&c->ev0));
   GRMP_CUDA(cudaEventCreate(&c->ev1));
+  GRMP_CUDA(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
   cudaDeviceProp prop;
   GRMP_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
@@ -204,8 +206,9 @@ int grmp_init(int device, grmp_ctx** out) {
 int grmp_finalize(grmp_ctx* ctx) {
   if (!ctx) return GRMP_OK;
   cudaStreamSynchronize(ctx->stream);
-  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
-  cudaStreamDestroy(ctx->stream);
+  cudaStreamSynchronize(ctx->copy_stream);
+  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_copy);
+  cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
   return GRMP_OK;
 }
@@ -395,6 +398,41 @@ int grmp_blf_numeric(grmp_blf* b, double factor, double* nzval_host) {
   GRMP_CUDA(cudaEventRecord(ctx->ev1, s));
   if (nzval_host && b->pat.nnz) GRMP_CUDA(cudaMemcpyAsync(nzval_host, b->nzval.p, (size_t)b->pat.nnz * 8, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  b->st.last_numeric_ms = ms;
+  b->have_values = true;
+  return GRMP_OK;
+}
+
+int grmp_blf_assemble_host(grmp_blf* b, double factor, const double* coords, const double* cellvolumes, const int32_t* cellnodes,
+                           const int32_t* celldofs_row, const int32_t* celldofs_col, double* nzval_host) {
+  if (!b || !coords || !cellvolumes || !cellnodes || !celldofs_row) return fail(GRMP_EINVAL, "grmp_blf_assemble_host: NULL argument");
+  if (!b->have_pattern) return fail(GRMP_ESTATE, "grmp_blf_symbolic has not been called");
+  if (b->s2 != b->s1 && !celldofs_col) return fail(GRMP_EINVAL, "grmp_blf_assemble_host: CellDofs of the column space missing");
+  grmp_grid* g = b->s1->grid;
+  grmp_ctx* ctx = g->ctx;
+  cudaStream_t s = ctx->stream, sc = ctx->copy_stream;
+  GRMP_CUDA(cudaSetDevice(ctx->device));
+  // the coordinates are all the owner-computes kernels read: they go first on the compute stream; the other grid arrays
+  // travel on the copy stream, concurrently with the kernels and the download of nzval (PCIe is full duplex)
+  GRMP_TRY(g->coords.upload(coords, (size_t)g->nnodes * g->dim, s));
+  if (g->dim == 3) GRMP_TRY(launch_pad_coords(g->coords.p, g->nnodes, g->coords4.p, s));
+  g->geom_version++;
+  GRMP_TRY(g->vol.upload(cellvolumes, (size_t)g->ncells, sc));
+  GRMP_TRY(g->cellnodes.upload(cellnodes, (size_t)g->ncells * (g->dim + 1), sc));
+  GRMP_TRY(b->s1->celldofs.upload(celldofs_row, (size_t)g->ncells * b->s1->nd, sc));
+  if (b->s2 != b->s1) GRMP_TRY(b->s2->celldofs.upload(celldofs_col, (size_t)g->ncells * b->s2->nd, sc));
+  GRMP_CUDA(cudaEventRecord(ctx->ev_copy, sc));
+  if (b->path != GRMP_PATH_FAST) GRMP_CUDA(cudaStreamWaitEvent(s, ctx->ev_copy, 0));   // the generic kernels read all of them
+  BlfLocalParams p;
+  GRMP_TRY(fill_blf_params(b, factor, &p));
+  GRMP_CUDA(cudaEventRecord(ctx->ev0, s));
+  GRMP_TRY(blf_numeric_launch(b, p, s));
+  GRMP_CUDA(cudaEventRecord(ctx->ev1, s));
+  if (nzval_host && b->pat.nnz) GRMP_CUDA(cudaMemcpyAsync(nzval_host, b->nzval.p, (size_t)b->pat.nnz * 8, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  GRMP_CUDA(cudaStreamSynchronize(sc));
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   b->st.last_numeric_ms = ms;

@@ -104,8 +104,8 @@ struct RegionFilter {
 
 struct grmp_ctx {
   int device;
-  cudaStream_t stream;
-  cudaEvent_t ev0, ev1;
+  cudaStream_t stream, copy_stream;   // compute (+ result download) / uploads that may overlap it
+  cudaEvent_t ev0, ev1, ev_copy;
   int sm_count;
 };
 

@@ -140,6 +140,13 @@ int grmp_blf_get_pattern(grmp_blf* blf, int64_t* colptr, int64_t* rowval);
  * on the device; fetch later with grmp_blf_get_values). */
 int grmp_blf_numeric(grmp_blf* blf, double factor, double* nzval_host);
 int grmp_blf_get_values(grmp_blf* blf, double* nzval_host);
+/* assemble!(A, AP; factor, skip_preps = true) with the grid still in HOST memory, one synchronous call (the end-to-end form
+ * of bilinearform.jl:92-380 behind a Julia ccall): uploads Coordinates, CellVolumes, CellNodes (grid of the row space) and
+ * CellDofs (celldofs_col may be NULL when both arguments live in the same space), assembles on the frozen pattern and
+ * downloads nzval.  Uploads the kernels do not read overlap the assembly and the download. */
+int grmp_blf_assemble_host(grmp_blf* blf, double factor, const double* coords, const double* cellvolumes,
+                           const int32_t* cellnodes, const int32_t* celldofs_row, const int32_t* celldofs_col,
+                           double* nzval_host);
 /* nsteps back-to-back numeric assemblies bracketed by ONE pair of CUDA events on the launching
  * stream (benchmarking / time loops that reassemble every step); total_ms receives the device time */
 int grmp_blf_numeric_steps(grmp_blf* blf, double factor, int nsteps, double* total_ms);

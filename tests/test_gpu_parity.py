@@ -339,6 +339,27 @@ def test_fast_p2tet_tile_shapes(nw, slot, kb, monkeypatch):
     assert G.blf_stats(AP).ntiles > 8
 
 
+@pytest.mark.parametrize("path", ["fast", "generic"])
+def test_assemble_host_one_call_matches_split_calls(path):
+    """grmp_blf_assemble_host (uploads + assembly + download in one call, overlapped copies) == update_* + numeric"""
+    g = tet_grid(2, True)
+    s = G.FESpace(G.H1P2(1, 3), g)
+    AP = G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [s, s])
+    G.blf_set_path(AP, G._lib.PATH_FAST if path == "fast" else G._lib.PATH_GENERIC)
+    _, _, ref = G.assemble_csc(AP, 1.5)
+    L = G._lib.lib()
+    nz = np.zeros_like(ref)
+    cn, dofs, vol = np.ascontiguousarray(g.cellnodes), np.ascontiguousarray(s.celldofs), np.ascontiguousarray(g.cellvolumes)
+    x = np.ascontiguousarray(g.coords)
+    G._lib.check(L.grmp_blf_assemble_host(AP.AM.h, 1.5, G._lib.ptr(x), G._lib.ptr(vol), G._lib.ptr(cn), G._lib.ptr(dofs), None, G._lib.ptr(nz)))
+    assert np.array_equal(nz, ref)
+    # scaled geometry through the same call: entries of the 3D stiffness matrix scale with the length
+    x2, vol8 = np.ascontiguousarray(2.0 * x), np.ascontiguousarray(8.0 * vol)
+    G._lib.check(L.grmp_blf_assemble_host(AP.AM.h, 1.5, G._lib.ptr(x2), G._lib.ptr(vol8), G._lib.ptr(cn), G._lib.ptr(dofs), None, G._lib.ptr(nz)))
+    assert rel_err(nz, 2.0 * ref) <= RTOL
+    assert L.grmp_blf_assemble_host(AP.AM.h, 1.5, None, None, None, None, None, None) == -1
+
+
 def test_fast_p2tet_region_filter_falls_back_correctly():
     g = tet_grid(1)
     g.cellregions[::2] = 2
