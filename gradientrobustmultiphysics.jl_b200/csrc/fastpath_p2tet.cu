@@ -306,15 +306,19 @@ __device__ __forceinline__ void mirror_writeout(const EdgeParams& p, const unsig
   const unsigned short* __restrict__ ms = reinterpret_cast<const unsigned short*>(in + off_msrc(cols_off, ncol, npairs, nnodes));
   const double* __restrict__ words = reinterpret_cast<const double*>(in);
   u32 i = lane;
-  for (; i + 7 * nlanes < nmir; i += 8 * nlanes) {    // 8 independent gather/store chains per lane
-    u32 d[8], w[8];
-    double v[8];
+#ifndef GRMP_WRITEOUT_U
+#define GRMP_WRITEOUT_U 8
+#endif
+  constexpr int U = GRMP_WRITEOUT_U;                   // independent gather/store chains per lane
+  for (; i + (U - 1) * nlanes < nmir; i += U * nlanes) {
+    u32 d[U], w[U];
+    double v[U];
 #pragma unroll
-    for (int u = 0; u < 8; u++) { d[u] = md[i + u * nlanes]; w[u] = ms[i + u * nlanes]; }
+    for (int u = 0; u < U; u++) { d[u] = md[i + u * nlanes]; w[u] = ms[i + u * nlanes]; }
 #pragma unroll
-    for (int u = 0; u < 8; u++) v[u] = words[w[u]];
+    for (int u = 0; u < U; u++) v[u] = words[w[u]];
 #pragma unroll
-    for (int u = 0; u < 8; u++) p.nzval[d[u]] = v[u];
+    for (int u = 0; u < U; u++) p.nzval[d[u]] = v[u];
   }
   for (; i < nmir; i += nlanes) p.nzval[md[i]] = words[ms[i]];
 }

@@ -360,6 +360,32 @@ def test_assemble_host_one_call_matches_split_calls(path):
     assert L.grmp_blf_assemble_host(AP.AM.h, 1.5, None, None, None, None, None, None) == -1
 
 
+def test_fast_p2tet_level5_size_independent_properties():
+    """786 432 cells / 2.97e7 non-zeros (one level below the BASELINE configuration): properties that need no reference
+    matrix -- A 1 = 0, symmetry, the P1 relation of the vertex block -- plus agreement with the bit-exact generic path"""
+    import scipy.sparse as sp_
+    g = tet_grid(5)
+    s = G.FESpace(G.H1P2(1, 3), g)
+    AP = G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [s, s])
+    G.blf_set_path(AP, G._lib.PATH_FAST)
+    cp, rv, nz = G.assemble_csc(AP, 1.0)
+    _, _, nz2 = G.assemble_csc(AP, 1.0, skip_preps=True)
+    assert np.array_equal(nz, nz2)
+    assert G.blf_stats(AP).ntiles > 3000
+    A = sp_.csc_matrix((nz, rv - 1, cp - 1), shape=(s.ndofs, s.ndofs))
+    amax = np.abs(nz).max()
+    assert np.abs(A @ np.ones(s.ndofs)).max() < 1e-11 * amax
+    assert abs(A - A.T).max() < 1e-12 * amax
+    nn = g.nnodes
+    Avv = A[:nn, :nn].tocsc()
+    assert np.abs(Avv.diagonal() - 3.0 * (np.asarray(Avv.sum(axis=0)).ravel() - Avv.diagonal())).max() < 1e-11 * amax
+    APg = G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [s, s])
+    G.blf_set_path(APg, G._lib.PATH_GENERIC)
+    cpg, rvg, nzg = G.assemble_csc(APg, 1.0)
+    assert np.array_equal(cp, cpg) and np.array_equal(rv, rvg)
+    assert rel_err(nz, nzg) <= RTOL
+
+
 def test_fast_p2tet_region_filter_falls_back_correctly():
     g = tet_grid(1)
     g.cellregions[::2] = 2
