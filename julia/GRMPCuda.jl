@@ -166,6 +166,27 @@ function GRMP.assemble!(A::FEMatrixBlock{Float64,Int64,Float64,Int32}, AP::Assem
     return nothing
 end
 
+"""
+    assemble_from_host!(A, AP; factor)
+
+Reassembly after the grid moved (same topology): one `grmp_blf_assemble_host` call uploads `Coordinates`, `CellVolumes`,
+`CellNodes`, `CellDofs`, assembles on the frozen pattern and downloads `nzval` (uploads the kernels do not read overlap
+the download).  `AP` must have been assembled once through `assemble!` above.
+"""
+function assemble_from_host!(A::FEMatrixBlock{Float64,Int64,Float64,Int32}, AP::AssemblyPattern; factor = 1)
+    d = PATTERNS[AP]
+    xgrid = AP.FES[1].xgrid
+    coords = xgrid[Coordinates]; vol = xgrid[CellVolumes]; cn = xgrid[CellNodes]
+    dofs1 = AP.FES[1][CellDofs].colentries
+    dofs2 = AP.FES[2] === AP.FES[1] ? nothing : AP.FES[2][CellDofs].colentries
+    nzval = Vector{Float64}(undef, d.nnz)
+    GC.@preserve coords vol cn dofs1 dofs2 check(ccall((:grmp_blf_assemble_host, lib), Cint,
+        (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}),
+        d.h, factor, coords, vol, cn, dofs1, dofs2 === nothing ? C_NULL : pointer(dofs2), nzval))
+    install_block!(A, SparseMatrixCSC(size(A, 1), size(A, 2), d.colptr, d.rowval, nzval))
+    return nothing
+end
+
 # single-block FEMatrix with an empty target: adopt the CSC; otherwise merge (explicit zeros kept)
 function install_block!(A::FEMatrixBlock, B::SparseMatrixCSC{Float64,Int64})
     E = A.entries
