@@ -73,13 +73,17 @@ __host__ __device__ inline int edge_of(int a, int b) {   // local edge dof index
 
 // ---- records ---------------------------------------------------------------------------------
 // tile blob (global, contiguous per tile, 16-byte aligned sections; one TMA bulk load):
-//   tile header 48 B: see TileHdr;  group table (NW+1) x {first column (tile-local), first nzval slot (relative to g0)}
+//   tile header 48 B: see TileHdr;  group table (NW+1) x 16 B {first column (tile-local), first nzval slot (relative to g0),
+//     first pair record (tile-local), -}
 //   column records  32 B x ncol   (16 B used; after the ring walk the owner parks 4 doubles A, B, q0, W in its record)
 //     x : tile-local node of P | Q << 12 | #pairs << 24
 //     y : slot offsets inside the column of rows v_P, v_Q, e_PQ (255 = not in the pattern) | flags << 24 (bit 0: closed ring)
 //     z : closing offsets (closed: rows of the first pair's in-vertex; open: rows of the last pair's out-vertex)
 //     w : column start inside the group's nzval range | first pair (tile-local) << 16
-//   pair records 8 B x npairs, pairs of a column stored in ring order (the owner parks the value of row v_in in it)
+//   pair records 8 B x npairs (the owner parks the value of row v_in in it).  Inside a group they are stored ROUND-major and
+//     compact: first the records of ring position 0 of all columns of the group (lane order), then position 1 of the columns
+//     that have one, ...  A warp reads / parks consecutive addresses in every round (no bank conflicts); a lane finds its
+//     record with a ballot of "my ring is longer than k" and a running round base.
 //     x : slot offsets inside the column of rows v_in, e_P,in, e_Q,in, e_in,out (255 = not in the pattern)
 //     y : tile-local node of the in-vertex | out-vertex << 12 | flags << 24
 //   node coordinates 24 B x nnodes : tile-blocked copy of Coordinates (the grid is immutable after grmp_grid_create)
@@ -118,6 +122,8 @@ struct PackParams {
   const u32* col_tile;      // tile of every edge column
   const u32* col_pq;        // tile-local node of P | Q << 12
   const u32* col_abase;     // first slot of the column relative to its group
+  const u32* col_group;     // first column of the column's group | #columns of the group << 27... see pack_pairs
+  const u32* col_gcount;    // #columns of the column's group
   const TileHdr* hdr;
   const int* mir_base;      // [ntiles+1] first mirror candidate of every tile
   i64 npairs, ncols;
@@ -157,7 +163,19 @@ __global__ void pack_pairs(PackParams p) {
   const i64 vin = d[I] - 1;
   const u32 tile = p.col_tile[col];
   const TileHdr h = p.hdr[tile];
-  const u32 kl = (u32)(k - (i64)h.pair_base);
+  // round-major compact position inside the group: rounds before this one + columns of the group in front with a ring this long
+  u32 kl;
+  {
+    const i64 gf = p.col_group[col], gc = p.col_gcount[col];
+    const i64 kr = k - p.col_pairbeg[col];
+    u32 idx = 0;
+    for (i64 c = gf; c < gf + gc; c++) {
+      const i64 npc = p.col_pairbeg[c + 1] - p.col_pairbeg[c];
+      idx += (u32)(npc < kr ? npc : kr);          // rounds 0 .. kr-1 of column c
+      if (c < col && npc > kr) idx++;              // round kr of the columns in front
+    }
+    kl = (u32)(p.col_pairbeg[gf] - (i64)h.pair_base) + idx;
+  }
   unsigned char* tb = p.blob + (size_t)h.blob16 * 16;
   const u32 po = off_pairs(h.cols_off, (u32)h.ncol);
   uint2 rec;
@@ -210,14 +228,14 @@ __global__ void pack_cols(PackParams p) {
 }
 
 // one block per tile: header, group table, node coordinates and the destination-sorted mirror list into the blob
-__global__ void pack_tile_rest(const TileHdr* hdr, const uint2* groups, int nw, const u32* tile_nodeids, const double* coords,
+__global__ void pack_tile_rest(const TileHdr* hdr, const uint4* groups, int nw, const u32* tile_nodeids, const double* coords,
                                const int* mir_base, const u32* mkey_sorted, const u32* mval_sorted, unsigned char* blob) {
   __shared__ int s_valid;
   const TileHdr h = hdr[blockIdx.x];
   unsigned char* tb = blob + (size_t)h.blob16 * 16;
   if (threadIdx.x == 0) s_valid = 0;
   __syncthreads();
-  if ((int)threadIdx.x <= nw) reinterpret_cast<uint2*>(tb + 48)[threadIdx.x] = groups[(size_t)blockIdx.x * (nw + 1) + threadIdx.x];
+  if ((int)threadIdx.x <= nw) reinterpret_cast<uint4*>(tb + 48)[threadIdx.x] = groups[(size_t)blockIdx.x * (nw + 1) + threadIdx.x];
   double* X = reinterpret_cast<double*>(tb + off_xyz(h.cols_off, (u32)h.ncol, (u32)h.npairs));
   for (int i = threadIdx.x; i < h.nnodes; i += blockDim.x) {
     const double* xg = coords + (size_t)(tile_nodeids[(size_t)h.node_base + i] - 1) * 3;
@@ -397,9 +415,9 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
     mbar_wait(full_a + 8 * cur, (unsigned)use & 1u);
     if (*reinterpret_cast<volatile int*>(&s_tile[cur]) < 0) break;
     const int4 h0 = reinterpret_cast<const int4*>(in)[0], h1 = reinterpret_cast<const int4*>(in)[1], h2 = reinterpret_cast<const int4*>(in)[2];
-    const uint2 gr0 = reinterpret_cast<const uint2*>(in + 48)[warp], gr1 = reinterpret_cast<const uint2*>(in + 48)[warp + 1];
+    const uint4 gr0 = reinterpret_cast<const uint4*>(in + 48)[warp], gr1 = reinterpret_cast<const uint4*>(in + 48)[warp + 1];
     const int col = (int)gr0.x + lane;                      // tile-local column of this lane
-    const bool has_col = col < (int)gr1.x;
+    const bool has_col = col < (int)gr1.x && !(p.dbg & 4);
     const i64 g0 = ((i64)(u32)h1.x | ((i64)h1.y << 32)) + gr0.y;   // first nzval slot of the group
     const int nnz_w = (int)(gr1.y - gr0.y);
     const u32 cols_off = (u32)h2.w, pairs_off = off_pairs(cols_off, (u32)h0.y), xyz_off = off_xyz(cols_off, (u32)h0.y, (u32)h0.w);
@@ -411,41 +429,57 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
     // this warp's previous bulk store must have finished reading the slot before it is overwritten
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
-    if (has_col && !(p.dbg & 4)) {
-      const uint4 ca = *reinterpret_cast<const uint4*>(in + cols_off + 32u * (u32)col);
-      const u32 np = ca.x >> 24;
+    {
+      uint4 ca = make_uint4(0, 0, 0, 0);
+      if (has_col) ca = *reinterpret_cast<const uint4*>(in + cols_off + 32u * (u32)col);
+      const u32 np = ca.x >> 24;                            // 0 for lanes without a column
+      const u32 maxnp = __reduce_max_sync(0xffffffffu, np);
       double mA = 0.0, mB = 0.0, mW = 0.0, mq0 = 0.0;
-      if (np > 0) {
-        const uint2* prec = reinterpret_cast<const uint2*>(in + pairs_off) + (ca.w >> 16);
-        double* park = reinterpret_cast<double*>(in + pairs_off) + (ca.w >> 16);   // consumed pair records take the mirror values
-        double* __restrict__ a = stage + (ca.w & 0xffffu);
-        const bool closed = (ca.y >> 24) & 1u;
-        const u32 lp = ca.x & 0xfffu, lq = (ca.x >> 12) & 0xfffu;
-        const double px = X[3 * lp], py = X[3 * lp + 1], pz = X[3 * lp + 2];
-        const double ax = X[3 * lq] - px, ay = X[3 * lq + 1] - py, az = X[3 * lq + 2] - pz;
-        const double c8 = p.factor * (0.8 / 6.0);      // S' = 0.8 * S = c8 / |det| * n_a.n_b
-        uint2 r0 = prec[0];
-        uint2 r1 = prec[np > 1 ? 1 : 0];
-        double bx, by, bz, mcx, mcy, mcz;               // b = c_in - p, mc = a x b (carried around the ring)
-        {
-          const u32 li = r0.y & 0xfffu;
-          bx = X[3 * li] - px; by = X[3 * li + 1] - py; bz = X[3 * li + 2] - pz;
-          mcx = ay * bz - az * by; mcy = az * bx - ax * bz; mcz = ax * by - ay * bx;
-        }
-        double ox, oy, oz;                              // coordinates of the out-vertex of the current pair
-        {
-          const u32 lo = (r0.y >> 12) & 0xfffu;
-          ox = X[3 * lo]; oy = X[3 * lo + 1]; oz = X[3 * lo + 2];
-        }
-        double R1 = 0.0, R2 = 0.0, R3 = 0.0;            // ring sums of S'_pq, S'_pi + S'_po, S'_qi + S'_qo
-        double c0r = 0.0, c1r = 0.0, c2r = 0.0;          // carry: partial rows of the shared ring vertex
-        double f0 = 0.0, f1 = 0.0, f2 = 0.0;             // closed ring: in-rows of the first pair, completed at the end
+      // pair records of the group, round-major and compact: record of (lane, round j) = gp[base_j + rank of the lane among the
+      // lanes with np > j].  next_rec(j) must be called for j = 0, 1, 2, ... by the whole warp.
+      const uint2* gp = reinterpret_cast<const uint2*>(in + pairs_off) + gr0.z;
+      double* gpark = reinterpret_cast<double*>(in + pairs_off) + gr0.z;    // consumed pair records take the mirror values
+      const u32 lt = (1u << lane) - 1u;
+      u32 rbase = 0;
+      auto next_rec = [&](u32 j) -> u32 {
+        const u32 bal = __ballot_sync(0xffffffffu, j < np);
+        const u32 idx = rbase + __popc(bal & lt);
+        rbase += __popc(bal);
+        return idx;
+      };
+      u32 i0 = next_rec(0), i1 = next_rec(1);
+      double* __restrict__ a = stage + (ca.w & 0xffffu);
+      const bool closed = (ca.y >> 24) & 1u;
+      const u32 lp = ca.x & 0xfffu, lq = (ca.x >> 12) & 0xfffu;
+      const double px = X[3 * lp], py = X[3 * lp + 1], pz = X[3 * lp + 2];
+      const double ax = X[3 * lq] - px, ay = X[3 * lq + 1] - py, az = X[3 * lq + 2] - pz;
+      const double c8 = p.factor * (0.8 / 6.0);      // S' = 0.8 * S = c8 / |det| * n_a.n_b
+      uint2 r0 = make_uint2(0, 0), r1 = make_uint2(0, 0);
+      if (np > 0) r0 = gp[i0];
+      if (np > 1) r1 = gp[i1];
+      double bx, by, bz, mcx, mcy, mcz;               // b = c_in - p, mc = a x b (carried around the ring)
+      {
+        const u32 li = r0.y & 0xfffu;
+        bx = X[3 * li] - px; by = X[3 * li + 1] - py; bz = X[3 * li + 2] - pz;
+        mcx = ay * bz - az * by; mcy = az * bx - ax * bz; mcz = ax * by - ay * bx;
+      }
+      double ox, oy, oz;                              // coordinates of the out-vertex of the current pair
+      {
+        const u32 lo = (r0.y >> 12) & 0xfffu;
+        ox = X[3 * lo]; oy = X[3 * lo + 1]; oz = X[3 * lo + 2];
+      }
+      double R1 = 0.0, R2 = 0.0, R3 = 0.0;            // ring sums of S'_pq, S'_pi + S'_po, S'_qi + S'_qo
+      double c0r = 0.0, c1r = 0.0, c2r = 0.0;          // carry: partial rows of the shared ring vertex
+      double f0 = 0.0, f1 = 0.0, f2 = 0.0;             // closed ring: in-rows of the first pair, completed at the end
 #pragma unroll 2
-        for (u32 k = 0; k < np; k++) {
+      for (u32 k = 0; k < maxnp; k++) {
+        const u32 i2 = next_rec(k + 2);
+        if (k < np) {
           // software pipeline: out-vertex of the next pair, record after next
           const u32 ln = (r1.y >> 12) & 0xfffu;
           const double nx = X[3 * ln], ny = X[3 * ln + 1], nz = X[3 * ln + 2];
-          const uint2 r2 = prec[k + 2 < np ? k + 2 : np - 1];
+          uint2 r2 = r1;
+          if (k + 2 < np) r2 = gp[i2];
           const u32 fl = r0.y >> 24;
           if (fl & PF_RESET) {
             const u32 li = r0.y & 0xfffu;
@@ -488,12 +522,15 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
             if (o0 != 255u) a[o0] = in0;
             if (o1 != 255u) a[o1] = in1;
             if (o2 != 255u) a[o2] = in2;
-            park[k] = in0;                                                 // mirror (e_PQ, v_in)
+            gpark[i0] = in0;                                               // mirror (e_PQ, v_in)
           }
           bx = ex; by = ey; bz = ez; mcx = mdx; mcy = mdy; mcz = mdz;
           ox = nx; oy = ny; oz = nz;
           r0 = r1; r1 = r2;
         }
+        i0 = i1; i1 = i2;
+      }
+      if (np > 0) {
         // closing rows: closed ring -> first pair's in-rows + last carry; open chain -> last pair's out-rows
         {
           const double q0 = closed ? f0 + c0r : c0r, q1 = closed ? f1 + c1r : c1r, q2 = closed ? f2 + c2r : c2r;
@@ -514,9 +551,11 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
           mA = A; mB = B; mW = W;
         }
       }
-      // park the column's mirror values in its own (consumed) record
-      double2* rec = reinterpret_cast<double2*>(in + cols_off + 32u * (u32)col);
-      rec[0] = make_double2(mA, mB); rec[1] = make_double2(mq0, mW);
+      if (has_col) {
+        // park the column's mirror values in its own (consumed) record
+        double2* rec = reinterpret_cast<double2*>(in + cols_off + 32u * (u32)col);
+        rec[0] = make_double2(mA, mB); rec[1] = make_double2(mq0, mW);
+      }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // stage writes -> visible to the bulk store
     __syncwarp();
@@ -675,7 +714,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   if (NBUF != 2 && NBUF != 3) NBUF = 2;
   const i64 BLOB_CAP = ((SMEM_BUDGET - NW * 8 * (SLOT_CAP + 2)) / NBUF) & ~15ll;
   if (BLOB_CAP < 4096) return fail(GRMP_EUNSUPPORTED, "fast path: shared-memory budget too small for the tile shape");
-  const u32 cols_off = 48u + pad16(8u * (u32)(NW + 1));
+  const u32 cols_off = 48u + 16u * (u32)(NW + 1);
   out->nw = NW;
   out->nbuf = NBUF;
   out->geom_version = geom_version;
@@ -685,13 +724,18 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   std::vector<u32> col_tile(ncols, NONE), col_pq(ncols, 0), col_abase(ncols, 0);
   std::vector<TileHdr> hdr;
   std::vector<u32> tile_nodeids;
-  std::vector<uint2> groups;                    // (NW+1) per tile: first column (tile-local), first slot (relative to g0)
+  std::vector<uint4> groups;                    // (NW+1) per tile: first column (tile-local), first slot (relative to g0), first pair (tile-local)
+  std::vector<u32> col_group(ncols, 0), col_gcount(ncols, 0);   // first column / #columns of every edge column's group
+  i64 grp_first_col = 0;
   std::vector<int> mir_base(1, 0);              // first mirror candidate of every tile
   std::vector<i32> nmark(nnodes + 1, -1), nlocal(nnodes + 1, 0);
   int cur_tile = 0, cur_cols = 0, cur_nodes = 0;
   int cur_groups = 0, grp_cols = 0;             // closed groups of the open tile; columns / slots of the open group
   i64 grp_nnz = 0;
-  uint2 cur_grp[9];
+  uint4 cur_grp[9];
+  auto close_group = [&](i64 end_col) {       // columns [grp_first_col, end_col) form a group
+    for (i64 c = grp_first_col; c < end_col; c++) { col_group[c] = (u32)grp_first_col; col_gcount[c] = (u32)(end_col - grp_first_col); }
+  };
   i64 cur_nnz = 0, cur_pairs = 0, tile_first_col = 0, tile_node_base = 0, tile_pair_base = 0;
   i64 max_blob = 0, max_slot = 0, blob_total16 = 0;
   bool any_end = false;
@@ -708,8 +752,8 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     blob_total16 += h.blob_bytes / 16;
     max_blob = std::max<i64>(max_blob, h.blob_bytes);
     mir_base.push_back(mir_base.back() + 5 * h.ncol + (int)cur_pairs);
-    if (grp_cols > 0) { max_slot = std::max<i64>(max_slot, grp_nnz); cur_groups++; }
-    for (int w2 = cur_groups; w2 <= NW; w2++) cur_grp[w2] = make_uint2((u32)h.ncol, (u32)cur_nnz);   // empty trailing groups
+    if (grp_cols > 0) { max_slot = std::max<i64>(max_slot, grp_nnz); cur_groups++; close_group(end_col); }
+    for (int w2 = cur_groups; w2 <= NW; w2++) cur_grp[w2] = make_uint4((u32)h.ncol, (u32)cur_nnz, (u32)cur_pairs, 0);   // empty trailing groups
     for (int w2 = 0; w2 <= NW; w2++) groups.push_back(cur_grp[w2]);
     cur_groups = 0; grp_cols = 0; grp_nnz = 0;
     tile_node_base = (i64)tile_nodeids.size();
@@ -815,8 +859,8 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
       if (cur_cols > 0 && ((grp_full && cur_groups + 1 >= NW) || over || cur_nodes + fresh > MAX_TILE_NODES || cur_pairs + n > 65535)) { close_tile(j); continue; }
       if (len > SLOT_CAP) return fail(GRMP_EUNSUPPORTED, "fast path: a single column exceeds the stage slot");
       if (cur_cols == 0) { tile_first_col = j; tile_pair_base = kb; }
-      if (grp_full) { max_slot = std::max<i64>(max_slot, grp_nnz); cur_groups++; grp_cols = 0; grp_nnz = 0; }
-      if (grp_cols == 0) cur_grp[cur_groups] = make_uint2((u32)cur_cols, (u32)cur_nnz);
+      if (grp_full) { max_slot = std::max<i64>(max_slot, grp_nnz); cur_groups++; grp_cols = 0; grp_nnz = 0; close_group(j); }
+      if (grp_cols == 0) { cur_grp[cur_groups] = make_uint4((u32)cur_cols, (u32)cur_nnz, (u32)cur_pairs, 0); grp_first_col = j; }
       col_abase[j] = (u32)grp_nnz;
       grp_cols++; grp_nnz += len;
       for (i32 v : colnodes) if (nmark[v] != cur_tile) { nmark[v] = cur_tile; nlocal[v] = cur_nodes++; tile_nodeids.push_back((u32)v); }
@@ -836,12 +880,12 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   if (blob_total16 >= (i64)NONE) return fail(GRMP_EUNSUPPORTED, "fast path: record blob exceeds 64 GB");
   out->ntiles = ntiles; out->npairs = npairs; out->smem_bytes = (int)std::max<i64>(max_smem, 1024); out->in_stride = (u32)max_blob;
   out->slot_elems = (u32)slot_elems; out->nvcols = (i64)vcols.size();
-  if (hdr.empty()) { TileHdr z{}; hdr.push_back(z); groups.assign(NW + 1, make_uint2(0, 0)); mir_base.push_back(0); }
+  if (hdr.empty()) { TileHdr z{}; hdr.push_back(z); groups.assign(NW + 1, make_uint4(0, 0, 0, 0)); mir_base.push_back(0); }
   if (tile_nodeids.empty()) tile_nodeids.push_back(1);
   if (vcols.empty()) vcols.push_back(0);
   std::vector<uint2> tile_dir(hdr.size());
   for (size_t t2 = 0; t2 < hdr.size(); t2++) tile_dir[t2] = make_uint2(hdr[t2].blob16, hdr[t2].blob_bytes);
-  DevBuf<uint2> d_groups;
+  DevBuf<uint4> d_groups;
   DevBuf<u32>& d_nodeids = out->tile_nodeids;
   DevBuf<int4>& d_hdr = out->tile_hdr;
   DevBuf<int> d_mirbase;
@@ -855,13 +899,14 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   // (3) pack column / pair records into the tile blobs on the device (slots are looked up in the pattern by (row, col)),
   //     sort every tile's mirror candidates by destination slot
   const i64 nmir_total = mir_base.back();
-  DevBuf<u32> d_cell, d_io, d_code, d_colof, d_coltile, d_colpq, d_abase, d_mkey, d_mval, d_mkey2, d_mval2;
+  DevBuf<u32> d_cell, d_io, d_code, d_colof, d_coltile, d_colpq, d_abase, d_mkey, d_mval, d_mkey2, d_mval2, d_colgroup, d_colgcount;
   DevBuf<unsigned char> d_closed;
   GRMP_TRY(d_cell.upload(pair_cell.data(), npairs, s)); GRMP_TRY(d_io.upload(pair_io.data(), npairs, s));
   GRMP_TRY(d_code.upload(pair_code.data(), npairs, s)); GRMP_TRY(d_colof.upload(col_of_pair.data(), npairs, s));
   GRMP_TRY(d_closed.upload(col_closed.data(), ncols, s));
   GRMP_TRY(d_coltile.upload(col_tile.data(), ncols, s)); GRMP_TRY(d_colpq.upload(col_pq.data(), ncols, s));
   GRMP_TRY(d_abase.upload(col_abase.data(), ncols, s));
+  GRMP_TRY(d_colgroup.upload(col_group.data(), ncols, s)); GRMP_TRY(d_colgcount.upload(col_gcount.data(), ncols, s));
   GRMP_TRY(d_mkey.alloc(std::max<i64>(nmir_total, 1))); GRMP_TRY(d_mval.alloc(std::max<i64>(nmir_total, 1)));
   GRMP_TRY(d_mkey2.alloc(std::max<i64>(nmir_total, 1))); GRMP_TRY(d_mval2.alloc(std::max<i64>(nmir_total, 1)));
   GRMP_CUDA(cudaMemsetAsync(d_mkey.p, 0xff, d_mkey.bytes(), s));
@@ -870,7 +915,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   out->end_slots.release();
   if (any_end) GRMP_TRY(out->end_slots.alloc(std::max<i64>(npairs, 1)));
   PackParams pp{d_cell.p, d_io.p, d_code.p, dg.segptr.p, pat.colptr.p, pat.rowval.p, p.e1.celldofs, d_colof.p, d_closed.p,
-                d_coltile.p, d_colpq.p, d_abase.p, reinterpret_cast<const TileHdr*>(d_hdr.p), d_mirbase.p, npairs, ncols,
+                d_coltile.p, d_colpq.p, d_abase.p, d_colgroup.p, d_colgcount.p, reinterpret_cast<const TileHdr*>(d_hdr.p), d_mirbase.p, npairs, ncols,
                 out->blob.p, out->end_slots.p, d_mkey.p, d_mval.p};
   if (npairs) pack_pairs<<<(unsigned)((npairs + 255) / 256), 256, 0, s>>>(pp);
   if (ncols) pack_cols<<<(unsigned)((ncols + 255) / 256), 256, 0, s>>>(pp);
