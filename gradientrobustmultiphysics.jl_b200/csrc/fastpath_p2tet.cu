@@ -585,9 +585,10 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
 // Diagonal of the vertex columns.  The vertex-vertex block of the P2 stiffness matrix is the P1 stiffness matrix K1 scaled
 // entrywise (A[v,v] = 0.6 K1[v,v], A[w,v] = -0.2 K1[w,v]: the local vertex-vertex block is 0.6 / -0.2 S), and the columns of
 // K1 sum to zero (the P1 basis is a partition of unity), hence A[v,v] = 3 * sum_{w != v} A[w,v] over the VERTEX rows w of the
-// column only -- ~15 of its ~65 entries, every one of them mirrored into place by the edge kernel.  Eight lanes per column,
-// fixed shuffle tree -> deterministic.  vrec: {diagonal slot | NONE, first slot, #slots (<= 96), 0}, {row-is-vertex mask x3, 0}.
-// Also re-arms the edge kernel's tile scheduler.
+// column only -- ~15 of its ~65 entries, every one of them mirrored into place by the edge kernel.  Columns with more than 128
+// entries (vertices of very high valence) use the plain column sum instead: A[v,v] = -sum_{i != v} A[i,v] (P2 partition of
+// unity).  Eight lanes per column, fixed shuffle tree -> deterministic.
+// vrec: {diagonal slot | NONE, first slot, #slots, mode}, {row-is-vertex mask x4}.  Also re-arms the edge kernel's tile scheduler.
 __global__ void __launch_bounds__(256) p2tet_vertex_diag_kernel(const uint4* __restrict__ vrec, i64 nv, double* nzval, int* tile_counter) {
   const i64 w = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 3;
   const int sub = threadIdx.x & 7;
@@ -598,39 +599,43 @@ __global__ void __launch_bounds__(256) p2tet_vertex_diag_kernel(const uint4* __r
   if (r.x != NONE) {
     const double* __restrict__ c = nzval + r.y;
     const u32 d = r.x - r.y;
-    double v[12];
+    if (r.w == 0) {
+      double v[16];
 #pragma unroll
-    for (int u = 0; u < 12; u++) {          // slot k = sub + 8 u < 96: all loads are independent
-      const u32 k = sub + 8 * u;
-      const u32 word = u < 4 ? m.x : (u < 8 ? m.y : m.z);
-      const bool take = k < r.z && k != d && ((word >> (k & 31)) & 1u);
-      v[u] = take ? c[k] : 0.0;
+      for (int u = 0; u < 16; u++) {          // slot k = sub + 8 u < 128: all loads are independent
+        const u32 k = sub + 8 * u;
+        const u32 word = u < 4 ? m.x : (u < 8 ? m.y : (u < 12 ? m.z : m.w));
+        const bool take = k < r.z && k != d && ((word >> (k & 31)) & 1u);
+        v[u] = take ? c[k] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 16; u++) s += v[u];
+      s *= 3.0;
+    } else {
+      for (u32 k = sub; k < r.z; k += 8) s -= (k == d) ? 0.0 : c[k];
     }
-#pragma unroll
-    for (int u = 0; u < 12; u++) s += v[u];
   }
   s += __shfl_xor_sync(0xffffffffu, s, 4);
   s += __shfl_xor_sync(0xffffffffu, s, 2);
   s += __shfl_xor_sync(0xffffffffu, s, 1);
-  if (sub == 0 && r.x != NONE) nzval[r.x] = 3.0 * s;
+  if (sub == 0 && r.x != NONE) nzval[r.x] = s;
 }
 
-// is_vertex[row] != 0 marks vertex dofs.  Columns with more than 96 entries cannot use the mask: fails -> generic path.
-__global__ void find_diag_slots(const u32* vcols, i64 nv, const i64* colptr, const i64* rowval, const unsigned char* col_kind, uint4* vrec, int* too_long) {
+// col_kind[row] == 2 marks vertex dofs
+__global__ void find_diag_slots(const u32* vcols, i64 nv, const i64* colptr, const i64* rowval, const unsigned char* col_kind, uint4* vrec) {
   i64 w = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (w >= nv) return;
   const i64 col = vcols[w];
   const i64 beg = colptr[col] - 1, end = colptr[col + 1] - 1;
-  u32 d = NONE, mask[3] = {0, 0, 0};
-  if (end - beg > 96) { atomicExch(too_long, 1); }
-  else
-    for (i64 k = beg; k < end; k++) {
-      const i64 row = rowval[k] - 1;
-      if (row == col) d = (u32)k;
-      else if (col_kind[row] == 2) mask[(k - beg) >> 5] |= 1u << ((k - beg) & 31);
-    }
-  vrec[2 * w] = make_uint4(d, (u32)beg, (u32)(end - beg), 0);
-  vrec[2 * w + 1] = make_uint4(mask[0], mask[1], mask[2], 0);
+  const bool masked = end - beg <= 128;
+  u32 d = NONE, mask[4] = {0, 0, 0, 0};
+  for (i64 k = beg; k < end; k++) {
+    const i64 row = rowval[k] - 1;
+    if (row == col) d = (u32)k;
+    else if (masked && col_kind[row] == 2) mask[(k - beg) >> 5] |= 1u << ((k - beg) & 31);
+  }
+  vrec[2 * w] = make_uint4(d, (u32)beg, (u32)(end - beg), masked ? 0u : 1u);
+  vrec[2 * w + 1] = make_uint4(mask[0], mask[1], mask[2], mask[3]);
 }
 
 // closed-form local stiffness of the unit reference tetrahedron, used to verify that the
@@ -762,7 +767,8 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   struct RP { u32 cell; int P, Q, R, S; i32 nR, nS; };
   std::vector<RP> rp;
   std::vector<char> used;
-  std::vector<i32> colnodes;
+  std::vector<i32> colnodes, ring_in, ring_out;
+  std::vector<int> degR, degS;      // scratch of the column loop (no allocation per column)
   for (i64 j = 0; j < ncols; j++) {
     const i64 kb = h_pairbeg[j], ke = h_pairbeg[j + 1];
     const i64 len = h_colptr[j + 1] - h_colptr[j];
@@ -793,7 +799,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
       rp[t] = RP{c, pl, ql, rl, sl, cn[rl], cn[sl]};
     }
     // degrees of the ring vertices; chains start at vertices of degree 1, a star without such a vertex is a closed ring
-    std::vector<int> degR(n), degS(n);
+    degR.resize(n); degS.resize(n);
     bool closed = true;
     for (int t = 0; t < n; t++) {
       int dR = 0, dS = 0;
@@ -808,7 +814,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     used.assign(n, 0);
     colnodes.clear();
     colnodes.push_back(P0); colnodes.push_back(Q0);
-    std::vector<i32> ring_in(n), ring_out(n);
+    ring_in.resize(n); ring_out.resize(n);
     int step = 0, nchains = 0;
     while (step < n) {
       int start = -1, start_in_is_R = 1;
@@ -937,15 +943,8 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   GRMP_TRY(out->vcols.upload(vcols.data(), vcols.size(), s));
   GRMP_TRY(out->vrec.alloc(2 * vcols.size()));
   if (out->nvcols > 0) {
-    // tile_counter doubles as the "a vertex column is too long" flag here (it is reset to zero below)
-    find_diag_slots<<<(unsigned)((out->nvcols + 255) / 256), 256, 0, s>>>(out->vcols.p, out->nvcols, pat.colptr.p, pat.rowval.p, d_closed.p, out->vrec.p,
-                                                                             out->tile_counter.p);
+    find_diag_slots<<<(unsigned)((out->nvcols + 255) / 256), 256, 0, s>>>(out->vcols.p, out->nvcols, pat.colptr.p, pat.rowval.p, d_closed.p, out->vrec.p);
     GRMP_CUDA(cudaGetLastError());
-    int too_long = 0;
-    GRMP_CUDA(cudaMemcpyAsync(&too_long, out->tile_counter.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    GRMP_CUDA(cudaStreamSynchronize(s));
-    GRMP_CUDA(cudaMemsetAsync(out->tile_counter.p, 0, sizeof(int), s));
-    if (too_long) return fail(GRMP_EUNSUPPORTED, "fast path: a vertex column has more than 96 entries");
   }
   const int smem_attr = (int)std::max<i64>(max_smem, 1024);
   GRMP_TRY(set_smem_attr<3>(smem_attr)); GRMP_TRY(set_smem_attr<4>(smem_attr)); GRMP_TRY(set_smem_attr<5>(smem_attr));

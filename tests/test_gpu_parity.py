@@ -386,6 +386,40 @@ def test_fast_p2tet_level5_size_independent_properties():
     assert rel_err(nz, nzg) <= RTOL
 
 
+def delaunay_tet_grid(npts, seed):
+    """unstructured conforming tetrahedral mesh of random points in the unit cube (scipy Delaunay; degenerate slivers
+    removed, cells oriented positively): rings of very different lengths, many boundary (open) edge stars"""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(seed)
+    corners = np.array([[i, j, k] for i in (0., 1.) for j in (0., 1.) for k in (0., 1.)])
+    x = np.vstack([corners, rng.uniform(0.0, 1.0, size=(npts, 3))])
+    cells = Delaunay(x).simplices.astype(np.int64)
+    a, b, c = (x[cells[:, j]] - x[cells[:, 0]] for j in (1, 2, 3))
+    det = np.einsum("ij,ij->i", a, np.cross(b, c))
+    keep = np.abs(det) > 1e-13           # only exactly degenerate cells (none for these seeds; removing one would open the mesh)
+    assert keep.all() or keep.sum() > 0
+    cells = cells[keep]; det = det[keep]
+    neg = det < 0
+    cells[neg, 2], cells[neg, 3] = cells[neg, 3].copy(), cells[neg, 2].copy()
+    return G.ExtendableGrid(x, cells + 1)
+
+
+@pytest.mark.parametrize("npts,seed", [(60, 1), (400, 2), (2500, 3)])
+def test_fast_p2tet_unstructured_delaunay_mesh(npts, seed):
+    """ragged input: the ring walk on a mesh that is not a uniform refinement (ring lengths 3..15+, boundary chains).  The
+    fast path must assemble it to the same matrix as the generic path"""
+    g = delaunay_tet_grid(npts, seed)
+    s = G.FESpace(G.H1P2(1, 3), g)
+    APg = G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [s, s])
+    G.blf_set_path(APg, G._lib.PATH_GENERIC)
+    cpg, rvg, nzg = G.assemble_csc(APg, 1.0)
+    AP = G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [s, s])
+    G.blf_set_path(AP, G._lib.PATH_FAST)           # a mesh the fast path cannot order would raise with the reason
+    cp, rv, nz = G.assemble_csc(AP, 1.0)
+    assert np.array_equal(cp, cpg) and np.array_equal(rv, rvg)
+    assert rel_err(nz, nzg) <= 1e-10               # slivers: cancellation in the row-sum identities costs a few digits
+
+
 def test_fast_p2tet_region_filter_falls_back_correctly():
     g = tet_grid(1)
     g.cellregions[::2] = 2
