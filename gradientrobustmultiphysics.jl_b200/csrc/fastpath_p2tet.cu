@@ -600,16 +600,21 @@ __global__ void __launch_bounds__(256) p2tet_vertex_diag_kernel(const uint4* __r
     const double* __restrict__ c = nzval + r.y;
     const u32 d = r.x - r.y;
     if (r.w == 0) {
-      double v[16];
+      // the vertex rows are the lowest row indices of the column on an unpartitioned grid: usually only mask word 0 is set
 #pragma unroll
-      for (int u = 0; u < 16; u++) {          // slot k = sub + 8 u < 128: all loads are independent
-        const u32 k = sub + 8 * u;
-        const u32 word = u < 4 ? m.x : (u < 8 ? m.y : (u < 12 ? m.z : m.w));
-        const bool take = k < r.z && k != d && ((word >> (k & 31)) & 1u);
-        v[u] = take ? c[k] : 0.0;
+      for (int wd = 0; wd < 4; wd++) {
+        const u32 word = wd == 0 ? m.x : (wd == 1 ? m.y : (wd == 2 ? m.z : m.w));
+        if (word != 0u) {
+          double v[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {       // slots 32 wd + sub + 8 u: independent loads
+            const u32 k = 32 * wd + sub + 8 * u;
+            const bool take = k != d && ((word >> (sub + 8 * u)) & 1u);   // mask bits exist only for slots < #slots
+            v[u] = take ? c[k] : 0.0;
+          }
+          s += (v[0] + v[1]) + (v[2] + v[3]);
+        }
       }
-#pragma unroll
-      for (int u = 0; u < 16; u++) s += v[u];
       s *= 3.0;
     } else {
       for (u32 k = sub; k < r.z; k += 8) s -= (k == d) ? 0.0 : c[k];
