@@ -44,7 +44,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstdlib>
+#include <thread>
 
 #include <cub/cub.cuh>
 
@@ -684,6 +686,15 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   // halo columns (>= ncols_owned) are processed too: their mirrors complete the owned vertex columns;
   // only they may consist of several chains (cells around a halo edge are present only where they touch an owned dof)
   cudaStream_t s = ctx->stream;
+  const bool verbose = getenv("GRMP_VERBOSE") != nullptr;
+  auto t_start = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!verbose) return;
+    cudaStreamSynchronize(s);
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[grmp fast build] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - t_start).count());
+    t_start = t;
+  };
   const i64 ncells = p.g.ncells, ncols = pat.ncols, nnodes = p.g.nnodes;
   const i64 ncols_owned_eff = (ncols_owned >= 0 && ncols_owned < ncols) ? ncols_owned : ncols;
   out->ntiles = 0; out->nvcols = 0;
@@ -714,6 +725,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   GRMP_CUDA(cudaMemcpyAsync(h_colptr.data(), pat.colptr.p, (ncols + 1) * 8, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaMemcpyAsync(h_cn.data(), p.g.cellnodes, (size_t)ncells * 16, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaStreamSynchronize(s));
+  lap("dof gather + downloads");
   // tile shape (tunable for experiments: GRMP_FAST_NW in 3..7, GRMP_FAST_SLOT, GRMP_FAST_SMEM_KB)
   int NW = getenv("GRMP_FAST_NW") ? atoi(getenv("GRMP_FAST_NW")) : NW_DEFAULT;
   if (NW < 3 || NW > 7) NW = NW_DEFAULT;
@@ -769,96 +781,134 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     tile_node_base = (i64)tile_nodeids.size();
     cur_tile++; cur_cols = 0; cur_nodes = 0; cur_nnz = 0; cur_pairs = 0;
   };
-  struct RP { u32 cell; int P, Q, R, S; i32 nR, nS; };
-  std::vector<RP> rp;
-  std::vector<char> used;
-  std::vector<i32> colnodes, ring_in, ring_out;
-  std::vector<int> degR, degS;      // scratch of the column loop (no allocation per column)
+  // (2a) ring order of every edge column: independent per column -> host threads.  Stores the ring as global node ids
+  //      (pair_in / pair_out), the orientation (col_P, col_Q) and the flags; errors are reported after the join.
+  std::vector<i32> pair_in(npairs), pair_out(npairs), col_P(ncols, 0), col_Q(ncols, 0);
+  {
+    unsigned nthr = std::thread::hardware_concurrency();
+    nthr = std::max(1u, std::min(nthr ? nthr : 1u, 32u));
+    if (getenv("GRMP_HOST_THREADS")) nthr = (unsigned)std::max(1, atoi(getenv("GRMP_HOST_THREADS")));
+    if (ncols < 4096) nthr = 1;
+    std::vector<const char*> err(nthr, nullptr);
+    std::vector<char> end_seen(nthr, 0);
+    auto work = [&](unsigned tix) {
+      struct RP { u32 cell; int P, Q, R, S; i32 nR, nS; };
+      std::vector<RP> rp;
+      std::vector<char> used;
+      std::vector<int> degR, degS;
+      const i64 j0 = ncols * tix / nthr, j1 = ncols * (tix + 1) / nthr;
+      for (i64 j = j0; j < j1; j++) {
+        const i64 kb = h_pairbeg[j], ke = h_pairbeg[j + 1];
+        const i64 len = h_colptr[j + 1] - h_colptr[j];
+        if (ke == kb) continue;
+        const int lj0 = (int)(h_src[kb] / (u32)ncells);
+        if (lj0 < 4) {   // vertex column: filled by mirrors + the diagonal kernel
+          for (i64 k = kb; k < ke; k++) { pair_cell[k] = h_cell[k]; pair_io[k] = 0; pair_code[k] = 0; col_of_pair[k] = (u32)j; }
+          continue;
+        }
+        if (len > 254 || ke - kb > 255) { err[tix] = "fast path: an edge column has more than 254 entries"; return; }
+        // ---- ring order of the cells around the edge ----
+        const int n = (int)(ke - kb);
+        rp.resize(n);
+        i32 P0 = 0, Q0 = 0;
+        for (int t = 0; t < n; t++) {
+          const u32 c = h_cell[kb + t];
+          const int lj = (int)(h_src[kb + t] / (u32)ncells);
+          if (lj < 4) { err[tix] = "fast path: mixed dof types in one column"; return; }
+          int pl, ql; edge_nodes(lj - 4, pl, ql);
+          int rl = -1, sl = -1;
+          for (int v = 0; v < 4; v++) if (v != pl && v != ql) { if (rl < 0) rl = v; else sl = v; }
+          const i32* cn = &h_cn[(size_t)c * 4];
+          if (t == 0) { P0 = cn[pl]; Q0 = cn[ql]; }
+          if (cn[pl] != P0) { int tmp = pl; pl = ql; ql = tmp; }      // consistent global orientation (P,Q)
+          if (cn[pl] != P0 || cn[ql] != Q0) { err[tix] = "fast path: inconsistent edge column"; return; }
+          rp[t] = RP{c, pl, ql, rl, sl, cn[rl], cn[sl]};
+        }
+        col_P[j] = P0; col_Q[j] = Q0;
+        // degrees of the ring vertices; chains start at vertices of degree 1, a star without such a vertex is a closed ring
+        degR.resize(n); degS.resize(n);
+        bool closed = true;
+        for (int t = 0; t < n; t++) {
+          int dR = 0, dS = 0;
+          for (int u = 0; u < n; u++) {
+            dR += (rp[u].nR == rp[t].nR) + (rp[u].nS == rp[t].nR);
+            dS += (rp[u].nR == rp[t].nS) + (rp[u].nS == rp[t].nS);
+          }
+          if (dR > 2 || dS > 2) { err[tix] = "fast path: non-manifold edge star"; return; }
+          degR[t] = dR; degS[t] = dS;
+          if (dR == 1 || dS == 1) closed = false;
+        }
+        used.assign(n, 0);
+        int step = 0, nchains = 0;
+        while (step < n) {
+          int start = -1, start_in_is_R = 1;
+          if (closed) { if (step != 0) { err[tix] = "fast path: edge star is not a single ring"; return; } start = 0; }
+          else
+            for (int t = 0; t < n && start < 0; t++)
+              if (!used[t]) { if (degR[t] == 1) { start = t; start_in_is_R = 1; } else if (degS[t] == 1) { start = t; start_in_is_R = 0; } }
+          if (start < 0) { err[tix] = "fast path: edge star mixes a ring and chains"; return; }
+          if (nchains > 0 && j < ncols_owned_eff) { err[tix] = "fast path: an owned edge star is not a single chain"; return; }
+          int curp = start;
+          const i32 first_in = start_in_is_R ? rp[start].nR : rp[start].nS;
+          i32 vin = first_in;
+          bool chain_first = true;
+          while (true) {
+            used[curp] = 1;
+            const bool inR = (rp[curp].nR == vin);
+            const int I = inR ? rp[curp].R : rp[curp].S, O = inR ? rp[curp].S : rp[curp].R;
+            const i32 vout = inR ? rp[curp].nS : rp[curp].nR;
+            const i64 k = kb + step;
+            u32 fl = 0u;
+            if (chain_first && nchains > 0) fl |= PF_RESET;
+            pair_cell[k] = rp[curp].cell;
+            pair_code[k] = (u32)(rp[curp].P | (rp[curp].Q << 2) | (I << 4) | (O << 6)) | (fl << 8);
+            col_of_pair[k] = (u32)j;
+            pair_in[k] = vin; pair_out[k] = vout;
+            step++; chain_first = false;
+            int nxt = -1;
+            for (int u = 0; u < n; u++) if (!used[u] && (rp[u].nR == vout || rp[u].nS == vout)) { nxt = u; break; }
+            if (nxt < 0) {
+              if (closed && (step != n || vout != first_in)) { err[tix] = "fast path: edge ring does not close"; return; }
+              if (!closed && step < n) { pair_code[k] |= (PF_END << 8); end_seen[tix] = 1; }     // a further chain follows
+              break;
+            }
+            vin = vout; curp = nxt;
+          }
+          nchains++;
+        }
+        col_closed[j] = closed ? 1 : 0;
+      }
+    };
+    if (nthr == 1) work(0);
+    else {
+      std::vector<std::thread> pool;
+      for (unsigned t = 0; t < nthr; t++) pool.emplace_back(work, t);
+      for (auto& th : pool) th.join();
+    }
+    for (unsigned t = 0; t < nthr; t++) {
+      if (err[t]) return fail(GRMP_EUNSUPPORTED, err[t]);
+      any_end = any_end || end_seen[t];
+    }
+  }
+  lap("host ring order (threads)");
+  // (2b) tiles and warp groups over the edge columns, list of vertex columns: sequential
+  std::vector<i32> colnodes;
   for (i64 j = 0; j < ncols; j++) {
     const i64 kb = h_pairbeg[j], ke = h_pairbeg[j + 1];
     const i64 len = h_colptr[j + 1] - h_colptr[j];
     if (ke == kb) { close_tile(j); continue; }
-    const int lj0 = (int)(h_src[kb] / (u32)ncells);
-    if (lj0 < 4) {   // vertex column: filled by mirrors + the diagonal kernel
+    if (col_closed[j] == 2) {   // vertex column
       close_tile(j);
       vcols.push_back((u32)j);
-      for (i64 k = kb; k < ke; k++) { pair_cell[k] = h_cell[k]; pair_io[k] = 0; pair_code[k] = 0; col_of_pair[k] = (u32)j; }
       continue;
     }
-    if (len > 254 || ke - kb > 255) return fail(GRMP_EUNSUPPORTED, "fast path: an edge column has more than 254 entries");
-    // ---- ring order of the cells around the edge ----
     const int n = (int)(ke - kb);
-    rp.resize(n);
-    i32 P0 = 0, Q0 = 0;
-    for (int t = 0; t < n; t++) {
-      const u32 c = h_cell[kb + t];
-      const int lj = (int)(h_src[kb + t] / (u32)ncells);
-      if (lj < 4) return fail(GRMP_EUNSUPPORTED, "fast path: mixed dof types in one column");
-      int pl, ql; edge_nodes(lj - 4, pl, ql);
-      int rl = -1, sl = -1;
-      for (int v = 0; v < 4; v++) if (v != pl && v != ql) { if (rl < 0) rl = v; else sl = v; }
-      const i32* cn = &h_cn[(size_t)c * 4];
-      if (t == 0) { P0 = cn[pl]; Q0 = cn[ql]; }
-      if (cn[pl] != P0) { int tmp = pl; pl = ql; ql = tmp; }      // consistent global orientation (P,Q)
-      if (cn[pl] != P0 || cn[ql] != Q0) return fail(GRMP_EUNSUPPORTED, "fast path: inconsistent edge column");
-      rp[t] = RP{c, pl, ql, rl, sl, cn[rl], cn[sl]};
-    }
-    // degrees of the ring vertices; chains start at vertices of degree 1, a star without such a vertex is a closed ring
-    degR.resize(n); degS.resize(n);
-    bool closed = true;
-    for (int t = 0; t < n; t++) {
-      int dR = 0, dS = 0;
-      for (int u = 0; u < n; u++) {
-        dR += (rp[u].nR == rp[t].nR) + (rp[u].nS == rp[t].nR);
-        dS += (rp[u].nR == rp[t].nS) + (rp[u].nS == rp[t].nS);
-      }
-      if (dR > 2 || dS > 2) return fail(GRMP_EUNSUPPORTED, "fast path: non-manifold edge star");
-      degR[t] = dR; degS[t] = dS;
-      if (dR == 1 || dS == 1) closed = false;
-    }
-    used.assign(n, 0);
+    const i32 P0 = col_P[j], Q0 = col_Q[j];
+    const i32* ring_in = &pair_in[kb];
+    const i32* ring_out = &pair_out[kb];
     colnodes.clear();
     colnodes.push_back(P0); colnodes.push_back(Q0);
-    ring_in.resize(n); ring_out.resize(n);
-    int step = 0, nchains = 0;
-    while (step < n) {
-      int start = -1, start_in_is_R = 1;
-      if (closed) { if (step != 0) return fail(GRMP_EUNSUPPORTED, "fast path: edge star is not a single ring"); start = 0; }
-      else
-        for (int t = 0; t < n && start < 0; t++)
-          if (!used[t]) { if (degR[t] == 1) { start = t; start_in_is_R = 1; } else if (degS[t] == 1) { start = t; start_in_is_R = 0; } }
-      if (start < 0) return fail(GRMP_EUNSUPPORTED, "fast path: edge star mixes a ring and chains");
-      if (nchains > 0 && j < ncols_owned_eff) return fail(GRMP_EUNSUPPORTED, "fast path: an owned edge star is not a single chain");
-      int curp = start;
-      const i32 first_in = start_in_is_R ? rp[start].nR : rp[start].nS;
-      i32 vin = first_in;
-      bool chain_first = true;
-      while (true) {
-        used[curp] = 1;
-        const bool inR = (rp[curp].nR == vin);
-        const int I = inR ? rp[curp].R : rp[curp].S, O = inR ? rp[curp].S : rp[curp].R;
-        const i32 vout = inR ? rp[curp].nS : rp[curp].nR;
-        const i64 k = kb + step;
-        u32 fl = 0u;
-        if (chain_first && nchains > 0) fl |= PF_RESET;
-        pair_cell[k] = rp[curp].cell;
-        pair_code[k] = (u32)(rp[curp].P | (rp[curp].Q << 2) | (I << 4) | (O << 6)) | (fl << 8);
-        col_of_pair[k] = (u32)j;
-        ring_in[step] = vin; ring_out[step] = vout;
-        colnodes.push_back(vin); colnodes.push_back(vout);
-        step++; chain_first = false;
-        int nxt = -1;
-        for (int u = 0; u < n; u++) if (!used[u] && (rp[u].nR == vout || rp[u].nS == vout)) { nxt = u; break; }
-        if (nxt < 0) {
-          if (closed && (step != n || vout != first_in)) return fail(GRMP_EUNSUPPORTED, "fast path: edge ring does not close");
-          if (!closed && step < n) { pair_code[k] |= (PF_END << 8); any_end = true; }     // a further chain follows
-          break;
-        }
-        vin = vout; curp = nxt;
-      }
-      nchains++;
-    }
-    col_closed[j] = closed ? 1 : 0;
+    for (int t = 0; t < n; t++) { colnodes.push_back(ring_in[t]); colnodes.push_back(ring_out[t]); }
     std::sort(colnodes.begin(), colnodes.end());
     colnodes.erase(std::unique(colnodes.begin(), colnodes.end()), colnodes.end());
     // ---- tile budget ----
@@ -883,6 +933,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     }
   }
   close_tile(ncols);
+  lap("host tiles (sequential)");
   const i64 slot_elems = (max_slot + 2 + 1) & ~1ll;     // even: keeps every slot 16-byte aligned
   const i64 max_smem = NBUF * max_blob + NW * 8 * slot_elems;
   if (max_smem > 220 * 1024) return fail(GRMP_EUNSUPPORTED, "fast path: a single column exceeds the shared-memory tile");
@@ -907,6 +958,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   GRMP_TRY(d_nodeids.upload(tile_nodeids.data(), tile_nodeids.size(), s));
   GRMP_TRY(out->tile_counter.alloc(1));
   GRMP_CUDA(cudaMemsetAsync(out->tile_counter.p, 0, sizeof(int), s));
+  lap("tile tables upload");
   // (3) pack column / pair records into the tile blobs on the device (slots are looked up in the pattern by (row, col)),
   //     sort every tile's mirror candidates by destination slot
   const i64 nmir_total = mir_base.back();
@@ -928,6 +980,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   PackParams pp{d_cell.p, d_io.p, d_code.p, dg.segptr.p, pat.colptr.p, pat.rowval.p, p.e1.celldofs, d_colof.p, d_closed.p,
                 d_coltile.p, d_colpq.p, d_abase.p, d_colgroup.p, d_colgcount.p, reinterpret_cast<const TileHdr*>(d_hdr.p), d_mirbase.p, npairs, ncols,
                 out->blob.p, out->end_slots.p, d_mkey.p, d_mval.p};
+  lap("pair arrays upload");
   if (npairs) pack_pairs<<<(unsigned)((npairs + 255) / 256), 256, 0, s>>>(pp);
   if (ncols) pack_cols<<<(unsigned)((ncols + 255) / 256), 256, 0, s>>>(pp);
   GRMP_CUDA(cudaGetLastError());
@@ -944,6 +997,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     GRMP_CUDA(cudaGetLastError());
     GRMP_CUDA(cudaStreamSynchronize(s));      // d_tmp and the sort buffers go out of scope below
   }
+  lap("pack kernels + mirror sort");
   // (4) vertex columns: list + diagonal slots
   GRMP_TRY(out->vcols.upload(vcols.data(), vcols.size(), s));
   GRMP_TRY(out->vrec.alloc(2 * vcols.size()));
