@@ -299,11 +299,24 @@ __device__ __forceinline__ u64 l2_policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+__device__ __forceinline__ u64 l2_policy_evict_last() {
+  u64 pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_hint(double* ptr, double v, u64 pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(ptr), "d"(v), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void tile_load(const EdgeParams& p, uint2 dir, unsigned dst_smem, unsigned mbar_a, u64 pol) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(dir.y) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
-               "l"(p.blob + (size_t)dir.x * 16), "r"(dir.y), "r"(mbar_a), "l"(pol)
-               : "memory");
+  if (!(p.dbg & 64))
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(p.blob + (size_t)dir.x * 16), "r"(dir.y), "r"(mbar_a)
+                 : "memory");
+  else
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+                 "l"(p.blob + (size_t)dir.x * 16), "r"(dir.y), "r"(mbar_a), "l"(pol)
+                 : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned mbar_a, unsigned parity) {
   asm volatile(
@@ -325,6 +338,7 @@ __device__ __forceinline__ void mirror_writeout(const EdgeParams& p, const unsig
   const u32* __restrict__ md = reinterpret_cast<const u32*>(in + off_mdst(cols_off, ncol, npairs, nnodes));
   const unsigned short* __restrict__ ms = reinterpret_cast<const unsigned short*>(in + off_msrc(cols_off, ncol, npairs, nnodes));
   const double* __restrict__ words = reinterpret_cast<const double*>(in);
+  const u64 pol_keep = l2_policy_evict_last();
   u32 i = lane;
 #ifndef GRMP_WRITEOUT_U
 #define GRMP_WRITEOUT_U 8
@@ -337,10 +351,17 @@ __device__ __forceinline__ void mirror_writeout(const EdgeParams& p, const unsig
     for (int u = 0; u < U; u++) { d[u] = md[i + u * nlanes]; w[u] = ms[i + u * nlanes]; }
 #pragma unroll
     for (int u = 0; u < U; u++) v[u] = words[w[u]];
+    // evict-last: the sectors of a vertex column are completed by other tiles later; keeping the partially written lines in
+    // L2 until then (the streaming loads / bulk stores are evict-first) is worth 8 % of the kernel
+    if (p.dbg & 16) {
 #pragma unroll
-    for (int u = 0; u < U; u++) p.nzval[d[u]] = v[u];
+      for (int u = 0; u < U; u++) p.nzval[d[u]] = v[u];
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; u++) st_hint(p.nzval + d[u], v[u], pol_keep);
+    }
   }
-  for (; i < nmir; i += nlanes) p.nzval[md[i]] = words[ms[i]];
+  for (; i < nmir; i += nlanes) st_hint(p.nzval + md[i], words[ms[i]], pol_keep);
 }
 
 // Persistent CTAs of NW consumer warps + 1 service warp.  Tiles are claimed from a global counter.  The service warp keeps the
@@ -570,7 +591,8 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
       if (lane == 0) {
         if (nb > 0 && !(p.dbg & 8)) {
           const unsigned src = (unsigned)__cvta_generic_to_shared(stage + i0);
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst + i0), "r"(src), "r"(nb * 8), "l"(pol_stream) : "memory");
+          if (!(p.dbg & 32)) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + i0), "r"(src), "r"(nb * 8) : "memory");
+          else asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst + i0), "r"(src), "r"(nb * 8), "l"(pol_stream) : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         // every lane is done with this input buffer (ordered by the __syncwarp above); release makes the parked values visible
