@@ -231,7 +231,9 @@ def run_gpu(args):
                 "kernel": "p2tet_edge_kernel (+ p2tet_vertex_diag_kernel, ~10 % of the step; duration = whole step)" if st.path == 2
                 else "blf_local_kernel+gather_kernel",
                 "algorithmic_bytes_per_launch": int(b_alg), "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)}
-    cpu = cpu_baseline(args.cpu_level) if world == 1 or True else None
+    cpu = cpu_baseline(args.cpu_level)
+    if cpu is not None and world == 1:
+        cpu["all_cores"] = cpu_parallel_baseline(args.cpu_level)
     out = {
         "metric": "assembled nnz/s, 3D P2 Laplace stiffness (numeric assembly on a frozen pattern)",
         "value": value, "unit": "nnz/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -284,6 +286,50 @@ def cpu_baseline(level):
                 "host_cpus": os.cpu_count()}
     except Exception as e:  # the baseline must never take the bench line down
         return {"value": None, "unit": "nnz/s", "cores": 1, "kind": "port", "sample": "failed: %r" % (e,)}
+
+
+def cpu_parallel_baseline(level, nthreads=None):
+    """'best plausible CPU' line: the same oracle loop on all host cores.  The reference's cell loop is serial, so
+    this is NOT the reference arm: the cells are split into nthreads contiguous ranges exactly like the multi-GPU partition
+    (owner-computes with halo cells, partition.py), every thread reassembles its rank-local matrix on a frozen pattern (the
+    ctypes call releases the GIL), value = global nnz / slowest thread."""
+    import threading
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as O
+        T = int(nthreads or min(os.cpu_count() or 1, 16))
+        G, g, s, _ = build_problem(level)
+        lps = [G.partition.partition(s, r, T) for r in range(T)]
+        mats, nnz_owned = [], 0
+        for lp in lps:                                   # first assembly (pattern), untimed
+            A = O.OracleMatrix(lp.space.ndofs, lp.space.ndofs)
+            O.blf_assemble(A, lp.grid, lp.space, lp.space, O.OP_GRAD, O.OP_GRAD, apt=O.APT_SYMMETRIC, factor=1.0)
+            A.flush()
+            cp = A.csc()[0]
+            nnz_owned += int(cp[lp.n_owned] - 1)
+            A.fill_zero()
+            mats.append(A)
+        start = threading.Barrier(T + 1)
+        ends = [0.0] * T
+
+        def work(r):
+            lp = lps[r]
+            start.wait()
+            O.blf_assemble(mats[r], lp.grid, lp.space, lp.space, O.OP_GRAD, O.OP_GRAD, apt=O.APT_SYMMETRIC, factor=1.0)
+            ends[r] = time.time()
+        th = [threading.Thread(target=work, args=(r,)) for r in range(T)]
+        for t in th:
+            t.start()
+        start.wait()
+        t0 = time.time()
+        for t in th:
+            t.join()
+        dt = max(ends) - t0
+        return {"value": nnz_owned / dt, "unit": "nnz/s", "cores": T, "kind": "port, cell ranges on threads (owner-computes with halo)",
+                "sample": "level %d: %d threads, slowest %.2f s, cells assembled by all threads %d of %d" %
+                          (level, T, dt, sum(lp.grid.ncells for lp in lps), g.ncells)}
+    except Exception as e:
+        return {"value": None, "sample": "failed: %r" % (e,)}
 
 
 def run_reference(args):
