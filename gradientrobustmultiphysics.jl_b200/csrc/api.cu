@@ -450,7 +450,24 @@ int grmp_blf_numeric_steps(grmp_blf* b, double factor, int nsteps, double* total
   GRMP_TRY(fill_blf_params(b, factor, &p));
   GRMP_CUDA(cudaStreamSynchronize(s));
   GRMP_CUDA(cudaEventRecord(ctx->ev0, s));
-  for (int k = 0; k < nsteps; k++) GRMP_TRY(blf_numeric_launch(b, p, s));
+  int k = 0;
+  if (nsteps > 0) { GRMP_TRY(blf_numeric_launch(b, p, s)); k = 1; }
+  if (nsteps > 2 && !getenv("GRMP_NO_GRAPH")) {
+    // the remaining steps replay one captured step (two kernels) as a CUDA graph: smaller gaps between the launches
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    GRMP_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int rc = blf_numeric_launch(b, p, s);
+    const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (rc == GRMP_OK && ce == cudaSuccess && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+      for (; k < nsteps; k++) GRMP_CUDA(cudaGraphLaunch(exec, s));
+    } else {
+      (void)cudaGetLastError();     // capture not possible: plain launches below
+    }
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+  }
+  for (; k < nsteps; k++) GRMP_TRY(blf_numeric_launch(b, p, s));
   GRMP_CUDA(cudaEventRecord(ctx->ev1, s));
   GRMP_CUDA(cudaStreamSynchronize(s));
   float ms = 0;
