@@ -111,7 +111,7 @@ using namespace grmp;
 GridView grmp_grid::view() const {
   GridView v{};
   v.dim = dim; v.nnodes = nnodes; v.ncells = ncells; v.nfaces = nfaces;
-  v.coords = coords.p; v.coords4 = coords4.p; v.cellnodes = cellnodes.p; v.vol = vol.p; v.regions = has_regions ? regions.p : nullptr;
+  v.coords = coords.p; v.cellnodes = cellnodes.p; v.vol = vol.p; v.regions = has_regions ? regions.p : nullptr;
   v.cellfaces = cellfaces.p; v.signs = signs.p; v.orient = orient.p; v.fnormals = fnormals.p; v.fvol = fvol.p;
   return v;
 }
@@ -228,7 +228,6 @@ int grmp_grid_create(grmp_ctx* ctx, int dim, int64_t nnodes, const double* coord
   grmp_grid* g = new grmp_grid();
   g->ctx = ctx; g->dim = dim; g->nnodes = nnodes; g->ncells = ncells; g->nfaces = 0;
   int rc = g->coords.upload(coords, (size_t)nnodes * dim, ctx->stream);
-  if (!rc && dim == 3) { rc = g->coords4.alloc((size_t)nnodes * 4); if (!rc) rc = launch_pad_coords(g->coords.p, nnodes, g->coords4.p, ctx->stream); }
   if (!rc) rc = g->cellnodes.upload(cellnodes, (size_t)ncells * (dim + 1), ctx->stream);
   if (!rc) rc = g->vol.upload(cellvolumes, (size_t)ncells, ctx->stream);
   if (!rc && cellregions) { rc = g->regions.upload(cellregions, (size_t)ncells, ctx->stream); g->has_regions = true; }
@@ -257,7 +256,6 @@ int grmp_grid_update_geometry(grmp_grid* g, const double* coords, const double* 
   if (!g || !coords || !cellvolumes) return fail(GRMP_EINVAL, "grmp_grid_update_geometry: NULL argument");
   cudaStream_t s = g->ctx->stream;
   GRMP_TRY(g->coords.upload(coords, (size_t)g->nnodes * g->dim, s));
-  if (g->dim == 3) GRMP_TRY(launch_pad_coords(g->coords.p, g->nnodes, g->coords4.p, s));
   GRMP_TRY(g->vol.upload(cellvolumes, (size_t)g->ncells, s));
   GRMP_CUDA(cudaStreamSynchronize(s));
   g->geom_version++;
@@ -417,7 +415,6 @@ int grmp_blf_assemble_host(grmp_blf* b, double factor, const double* coords, con
   // the coordinates are all the owner-computes kernels read: they go first on the compute stream; the other grid arrays
   // travel on the copy stream, concurrently with the kernels and the download of nzval (PCIe is full duplex)
   GRMP_TRY(g->coords.upload(coords, (size_t)g->nnodes * g->dim, s));
-  if (g->dim == 3) GRMP_TRY(launch_pad_coords(g->coords.p, g->nnodes, g->coords4.p, s));
   g->geom_version++;
   GRMP_TRY(g->vol.upload(cellvolumes, (size_t)g->ncells, sc));
   GRMP_TRY(g->cellnodes.upload(cellnodes, (size_t)g->ncells * (g->dim + 1), sc));

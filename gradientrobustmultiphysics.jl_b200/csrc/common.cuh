@@ -64,7 +64,6 @@ struct GridView {
   int dim;
   i64 nnodes, ncells, nfaces;
   const double* coords;     // [nnodes][dim]
-  const double* coords4;    // dim == 3: [nnodes][4] (x,y,z,0), 32-byte aligned rows for single 256-bit gathers
   const i32* cellnodes;     // [ncells][dim+1], 1-based
   const double* vol;        // [ncells]
   const i32* regions;       // [ncells] or null
@@ -113,7 +112,7 @@ struct grmp_grid {
   grmp_ctx* ctx;
   int dim;
   grmp::i64 nnodes, ncells, nfaces;
-  grmp::DevBuf<double> coords, coords4, vol, fnormals, fvol;
+  grmp::DevBuf<double> coords, vol, fnormals, fvol;
   grmp::DevBuf<grmp::i32> cellnodes, regions, cellfaces, signs, orient;
   bool has_regions = false, has_faces = false;
   grmp::i64 geom_version = 0;     // bumped by grmp_grid_update_geometry (the fast path keeps tile-blocked coordinate copies)
@@ -171,6 +170,5 @@ struct LfLocalParams {
   unsigned char* active; // [ncells] 1 if the cell is assembled (region filter)
 };
 int launch_lf_local(const LfLocalParams& p, cudaStream_t s);
-int launch_pad_coords(const double* coords, i64 nnodes, double* coords4, cudaStream_t s);
 
 }  // namespace grmp

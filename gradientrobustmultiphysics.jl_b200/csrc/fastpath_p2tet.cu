@@ -915,6 +915,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   lap("host ring order (threads)");
   // (2b) tiles and warp groups over the edge columns, list of vertex columns: sequential
   std::vector<i32> colnodes;
+  std::vector<i64> cmark(nnodes + 1, -1);       // stamp: node already seen in this column (no sort / unique per column)
   for (i64 j = 0; j < ncols; j++) {
     const i64 kb = h_pairbeg[j], ke = h_pairbeg[j + 1];
     const i64 len = h_colptr[j + 1] - h_colptr[j];
@@ -931,8 +932,11 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     colnodes.clear();
     colnodes.push_back(P0); colnodes.push_back(Q0);
     for (int t = 0; t < n; t++) { colnodes.push_back(ring_in[t]); colnodes.push_back(ring_out[t]); }
-    std::sort(colnodes.begin(), colnodes.end());
-    colnodes.erase(std::unique(colnodes.begin(), colnodes.end()), colnodes.end());
+    {
+      size_t m = 0;
+      for (i32 v : colnodes) if (cmark[v] != j) { cmark[v] = j; colnodes[m++] = v; }
+      colnodes.resize(m);
+    }
     // ---- tile budget ----
     for (int attempt = 0; attempt < 2; attempt++) {
       int fresh = 0;

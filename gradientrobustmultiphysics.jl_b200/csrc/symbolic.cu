@@ -212,17 +212,6 @@ int build_pattern(cudaStream_t s, DevBuf<u64>& keys, i64 ntot, i64 nrows, i64 nc
   return GRMP_OK;
 }
 
-__global__ void pad_coords_kernel(const double* coords, i64 nnodes, double* coords4) {
-  i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  if (i >= nnodes) return;
-  coords4[4 * i] = coords[3 * i]; coords4[4 * i + 1] = coords[3 * i + 1]; coords4[4 * i + 2] = coords[3 * i + 2]; coords4[4 * i + 3] = 0.0;
-}
-int launch_pad_coords(const double* coords, i64 nnodes, double* coords4, cudaStream_t s) {
-  if (nnodes == 0) return GRMP_OK;
-  pad_coords_kernel<<<nblk(nnodes), 256, 0, s>>>(coords, nnodes, coords4);
-  GRMP_CUDA(cudaGetLastError());
-  return GRMP_OK;
-}
 
 int launch_gather(cudaStream_t s, const Pattern& pat, const double* lbuf, double* nzval) {
   if (pat.nnz == 0) return GRMP_OK;
