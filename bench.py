@@ -231,8 +231,9 @@ def run_gpu(args):
                 "kernel": "p2tet_edge_kernel (+ p2tet_vertex_diag_kernel, ~10 % of the step; duration = whole step)" if st.path == 2
                 else "blf_local_kernel+gather_kernel",
                 "algorithmic_bytes_per_launch": int(b_alg), "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)}
-    cpu = cpu_baseline(args.cpu_level)
-    if cpu is not None and world == 1:
+    cpu = None
+    if world == 1:      # the CPU arm is timed on rank 0 at N = 1 only
+        cpu = cpu_baseline(args.cpu_level)
         cpu["all_cores"] = cpu_parallel_baseline(args.cpu_level)
     out = {
         "metric": "assembled nnz/s, 3D P2 Laplace stiffness (numeric assembly on a frozen pattern)",
