@@ -362,7 +362,9 @@ def run_reference(args):
                                "(bounded sample of the level-%d workload)" % (level, args.level), "level": level,
                    "ncells": int(g.ncells), "nnz": int(nnz)},
         "cpu_baseline": {"value": value, "unit": "nnz/s", "cores": 1, "kind": "port", "sample": sample,
-                         "note": "Julia reference not runnable in this image; oracle port of bilinearform.jl:226-377, serial like the reference"},
+                         "note": "Julia reference not runnable in this image; oracle port of bilinearform.jl:226-377, serial like the reference "
+                                 "(its cell loop uses one thread whatever JULIA_NUM_THREADS is); all_cores = the same loop on cell-range partitions",
+                         "all_cores": cpu_parallel_baseline(level)},
         "e2e": {"value": value, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
