@@ -282,7 +282,9 @@ struct EdgeParams {
   u32 in_stride;            // bytes of one input buffer (largest blob)
   u32 slot_elems;           // doubles per warp stage slot
   int nbuf;                 // depth of the input ring (2 or 3)
-  int dbg;                  // GRMP_DEBUG_FLAGS (timing experiments only): 1 skip mirrored stores, 4 skip the ring walk, 8 skip the bulk store
+  int dbg;                  // GRMP_DEBUG_FLAGS (timing experiments only): 1 skip the mirror write-out, 2 skip the diagonal kernel, 4 skip the ring
+                            // walk, 8 skip the bulk stores, 16 mirror stores without the evict-last hint, 32 / 64 evict-first hint on the
+                            // bulk stores / blob loads
 };
 
 __device__ __forceinline__ double fast_rcp(double d) {   // 1/d to ~1 ulp for normal d: MUFU.RCP64H + two Newton steps
