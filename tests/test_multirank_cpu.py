@@ -79,3 +79,24 @@ def test_every_dof_has_exactly_one_owner_and_owned_columns_are_complete():
         touching = np.nonzero(np.isin(s.celldofs.astype(np.int64) - 1, owned_global).any(axis=1))[0]
         assert np.array_equal(np.sort(lp.cells), touching)
     assert total == s.ndofs
+
+
+import pytest
+
+
+@pytest.mark.parametrize("world,level", [(3, 1), (5, 2), (8, 2)])
+def test_partition_merge_for_the_bench_world_sizes(world, level):
+    """the 4- and 8-GPU runs of bench.py use the same host logic: every world size must reproduce the global matrix bit for bit
+    (in-process, the oracle as the per-rank assembler)"""
+    g = G.perturb_interior_nodes(G.uniform_refine(G.grid_unitcube("Tetrahedron3D"), level))
+    s = G.FESpace(G.H1P2(1, 3), g)
+    blocks, cells = [], 0
+    for r in range(world):
+        lp = G.partition.partition(s, r, world)
+        cells += lp.grid.ncells
+        cp, rv, nz = _assemble_oracle(lp.grid, lp.space)
+        blocks.append(G.partition.owned_block_to_global(lp, cp, rv, nz))
+    colptr, rowval, nzval = G.partition.merge_owned_columns(s.ndofs, blocks)
+    gcp, grv, gnz = _assemble_oracle(g, s)
+    assert np.array_equal(colptr, gcp) and np.array_equal(rowval, grv) and np.array_equal(nzval, gnz)
+    assert cells >= g.ncells          # halo cells are assembled more than once
