@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libgrmp_cuda.so")
 _lib = None
 
 OK = 0
-PATH_AUTO, PATH_GENERIC, PATH_FAST = 0, 1, 2
+PATH_AUTO, PATH_GENERIC, PATH_FAST, PATH_P2TET, PATH_COLUMNS, PATH_ATOMIC, PATH_COLOURED = 0, 1, 2, 2, 3, 4, 5
+PATH_NAMES = {1: "generic", 2: "p2tet", 3: "columns", 4: "atomic", 5: "coloured"}
 
 EXPORTS = [
     "grmp_last_error", "grmp_init", "grmp_finalize", "grmp_device_synchronize", "grmp_grid_create", "grmp_grid_set_faces",

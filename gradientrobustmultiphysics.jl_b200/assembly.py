@@ -15,6 +15,7 @@ runs in libgrmp_cuda (include/grmp.h) -- there is no CPU fallback:
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -147,6 +148,18 @@ def fdot_action(data):
     return _FDotAction(data)
 
 
+# numeric back end requested for newly prepared bilinear forms (include/grmp.h GRMP_PATH_*); tests pin the bit-exact path here
+DEFAULT_PATH = _lib.PATH_AUTO
+
+
+def _release(fn_name, handle):
+    """finalizer of a device object: the library owns the memory behind the handle (grmp.h 'Ownership')"""
+    try:
+        getattr(_lib.lib(), fn_name)(handle)
+    except Exception:
+        pass
+
+
 # ---- device mirrors of grid / space ---------------------------------------------------------------
 def device_grid(xgrid, need_faces=False):
     L = _lib.lib()
@@ -158,6 +171,7 @@ def device_grid(xgrid, need_faces=False):
                                       _lib.ptr(xgrid.cellnodes), _lib.ptr(vol), _lib.ptr(xgrid.cellregions), C.byref(h)))
         d = {"h": h, "faces": False}
         xgrid._dev = d
+        weakref.finalize(xgrid, _release, "grmp_grid_destroy", h)
     if need_faces and not d["faces"]:
         ori = np.ascontiguousarray(xgrid.cellfaceorientations) if xgrid.dim == 3 else None
         _lib.check(L.grmp_grid_set_faces(d["h"], xgrid.nfaces, _lib.ptr(xgrid.cellfaces), _lib.ptr(xgrid.cellfacesigns),
@@ -176,6 +190,8 @@ def device_space(FES: FESpace):
         _lib.check(_lib.lib().grmp_space_create(gh, FES.fetype.code, FES.fetype.ncomponents, FES.ndofs, dofs.shape[1], _lib.ptr(dofs),
                                                 C.byref(h)))
         FES._dev = d = h
+        # the space handle refers to the grid handle: keep the grid alive as long as the space, destroy the space first
+        weakref.finalize(FES, _release, "grmp_space_destroy", h)
     return d
 
 
@@ -236,7 +252,13 @@ def _tables(FES: FESpace, op, qf):
 
 
 class _Prepared:
-    pass
+    """prepared state of an AssemblyPattern; owns the device-side pattern object"""
+
+    def __del__(self):
+        h, kind = getattr(self, "h", None), getattr(self, "kind", None)
+        if h is not None and kind is not None:
+            _release("grmp_blf_destroy" if kind == "blf" else "grmp_lf_destroy", h)
+            self.h = None
 
 
 def quadrature_order(AP: AssemblyPattern):
@@ -277,6 +299,8 @@ def prepare_assembly(AP: AssemblyPattern, transposed_assembly=False):
         _lib.check(L.grmp_blf_create(s1, s2, AP.operators[0].code, AP.operators[1].code, act.code, _lib.ptr(act.params), AP.APT,
                                      int(bool(transposed_assembly)), _lib.ptr(regions), regions.size, len(P.qf), _lib.ptr(w), C.byref(t1), C.byref(t2), C.byref(h)))
         P.kind = "blf"
+        if DEFAULT_PATH != _lib.PATH_AUTO:
+            _lib.check(L.grmp_blf_set_path(h, DEFAULT_PATH))
         P.have_pattern = False
         P.transposed = bool(transposed_assembly) and AP.APT != APT_SymmetricBilinearForm
     P.h = h

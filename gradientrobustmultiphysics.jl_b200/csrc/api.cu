@@ -2,6 +2,7 @@
 #include <cstring>
 #include <mutex>
 
+#include "colpath.cuh"
 #include "common.cuh"
 #include "fastpath.cuh"
 #include "symbolic.cuh"
@@ -125,12 +126,14 @@ struct grmp_blf {
   DevBuf<double> w;
   EvalTables t1, t2;
   std::vector<double> w_host;
-  std::vector<double> t1_derivs_host;     // kept for the fast path's reference integrals
+  std::vector<double> t1_derivs_host, t1_vals_host, t2_derivs_host, t2_vals_host;   // host copies of the caller's evaluator tables
   Pattern pat;
+  ColPath colp;
   bool have_pattern = false, have_values = false;
   DevBuf<double> lbuf, nzval;
   FastP2Tet fast;
   i64 ncols_owned = -1;
+  double p2tet_kappa = 0.0;       // cancellation indicator of the grid (AUTO guard of the ring-walk kernel)
   grmp_stats st{};
   i64 out_rows() const { return (apt != GRMP_APT_SYMMETRIC && transposed) ? s2->ndofs : s1->ndofs; }
   i64 out_cols() const { return (apt != GRMP_APT_SYMMETRIC && transposed) ? s1->ndofs : s2->ndofs; }
@@ -166,6 +169,13 @@ static int blf_numeric_launch(grmp_blf* b, BlfLocalParams& p, cudaStream_t s) {
   if (b->path == GRMP_PATH_FAST) {
     GRMP_TRY(fast_p2tet_numeric(ctx, p, b->pat, b->fast, b->s1->grid->geom_version, b->nzval.p));
     b->st.kernel_launches = 2;
+  } else if (b->path == GRMP_PATH_COLUMNS) {
+    GRMP_TRY(colpath_numeric(ctx, p, b->pat, b->colp, b->nzval.p));
+    b->st.kernel_launches = (i64)b->colp.classes.size();
+  } else if (b->path == GRMP_PATH_ATOMIC || b->path == GRMP_PATH_COLOURED) {
+    i64 nl = 0;
+    GRMP_TRY(cellpath_numeric(ctx, p, b->pat, b->colp, b->path == GRMP_PATH_ATOMIC ? 0 : 1, b->nzval.p, &nl));
+    b->st.kernel_launches = nl;
   } else {
     const size_t nl = (size_t)p.e1.nd * p.e2.nd * p.g.ncells;
     if (b->lbuf.n != nl) GRMP_TRY(b->lbuf.alloc(nl));
@@ -312,7 +322,13 @@ int grmp_blf_create(grmp_space* s1, grmp_space* s2, int op1, int op2, int action
   b->w_host.assign(qweights, qweights + nq);
   if (!rc) rc = upload_tables(tab1, nq, s1->grid->dim, st, &b->t1);
   if (!rc && tab1->refderivs) b->t1_derivs_host.assign(tab1->refderivs, tab1->refderivs + (size_t)nq * s1->grid->dim * tab1->nd_all * tab1->ncomp);
-  if (!rc && !b->same_eval) rc = upload_tables(tab2 ? tab2 : tab1, nq, s1->grid->dim, st, &b->t2);
+  if (!rc && tab1->refvals) b->t1_vals_host.assign(tab1->refvals, tab1->refvals + (size_t)nq * tab1->nd_all * tab1->ncomp);
+  if (!rc && !b->same_eval) {
+    const grmp_evaltab* t2 = tab2 ? tab2 : tab1;
+    rc = upload_tables(t2, nq, s1->grid->dim, st, &b->t2);
+    if (!rc && t2->refderivs) b->t2_derivs_host.assign(t2->refderivs, t2->refderivs + (size_t)nq * s1->grid->dim * t2->nd_all * t2->ncomp);
+    if (!rc && t2->refvals) b->t2_vals_host.assign(t2->refvals, t2->refvals + (size_t)nq * t2->nd_all * t2->ncomp);
+  }
   BlfLocalParams p;
   if (!rc) rc = fill_blf_params(b, 1.0, &p);   // validates the combination
   if (!rc) {
@@ -330,7 +346,7 @@ int grmp_blf_create(grmp_space* s1, grmp_space* s2, int op1, int op2, int action
 int grmp_blf_destroy(grmp_blf* b) { delete b; return GRMP_OK; }
 
 int grmp_blf_set_path(grmp_blf* b, int path) {
-  if (!b || path < 0 || path > 2) return fail(GRMP_EINVAL, "grmp_blf_set_path: bad argument");
+  if (!b || path < 0 || path > GRMP_PATH_COLOURED) return fail(GRMP_EINVAL, "grmp_blf_set_path: bad argument");
   b->path_req = path;
   return GRMP_OK;
 }
@@ -344,30 +360,53 @@ int grmp_blf_symbolic(grmp_blf* b, double factor, int64_t* nnz_out) {
   GRMP_TRY(fill_blf_params(b, factor, &p));
   const i64 ncells = p.g.ncells;
   const int nloc = p.e1.nd * p.e2.nd;
-  const bool fast_ok = fast_p2tet_applicable(p);
-  if (b->path_req == GRMP_PATH_FAST && !fast_ok) return fail(GRMP_EUNSUPPORTED, "no fast path for this form");
-  const bool want_fast = fast_ok && b->path_req != GRMP_PATH_GENERIC;
+  const int req = b->path_req;
+  const bool p2_ok = fast_p2tet_applicable(p);
+  const bool col_ok = colpath_applicable(p, b->nq, &b->colp);
+  const bool cell_req = (req == GRMP_PATH_ATOMIC || req == GRMP_PATH_COLOURED);
+  if (req == GRMP_PATH_FAST && !p2_ok && !col_ok) return fail(GRMP_EUNSUPPORTED, "no fast path for this form");
+  if ((req == GRMP_PATH_COLUMNS || cell_req) && !col_ok) return fail(GRMP_EUNSUPPORTED, "no column / cell kernel for this form");
   GRMP_CUDA(cudaEventRecord(ctx->ev0, s));
   DevBuf<u64> keys;
   GRMP_TRY(keys.alloc((size_t)ncells * nloc));
   p.keys = keys.p;
   GRMP_TRY(launch_blf_local(p, s));
   GRMP_TRY(build_pattern(s, keys, ncells * nloc, b->out_rows(), b->out_cols(), ncells, p.e1.nd, p.e2.nd, b->apt == GRMP_APT_SYMMETRIC,
-                         false /* the fast path looks slots up by (row, col); no per-cell local->nnz map needed */, &b->pat));
+                         cell_req /* per-cell local->nnz map: only the cell-parallel kernels scatter through it */, &b->pat));
   GRMP_TRY(b->nzval.alloc(b->pat.nnz));
   b->path = GRMP_PATH_GENERIC;
-  if (want_fast) {
-    const int rc = fast_p2tet_build(ctx, p, b->pat, b->w_host, b->t1_derivs_host, b->ncols_owned, b->s1->grid->geom_version, &b->fast);
-    b->pat.slotmap.release();
-    if (rc == GRMP_OK) b->path = GRMP_PATH_FAST;
-    else if (rc != GRMP_EUNSUPPORTED || b->path_req == GRMP_PATH_FAST) return rc;   // AUTO: grids the fast path cannot order use the generic path
+  b->p2tet_kappa = 0.0;
+  bool want_p2 = p2_ok && (req == GRMP_PATH_AUTO || req == GRMP_PATH_FAST);
+  if (want_p2 && req == GRMP_PATH_AUTO) {
+    // cancellation guard: the ring-walk kernel derives diagonal entries from zero row sums, which loses digits on cells with
+    // large sum_b |S_ab| / S_aa (slivers, strongly obtuse cells).  AUTO only takes it where 1e-12 is safe.
+    GRMP_TRY(fast_p2tet_quality(ctx, p, &b->p2tet_kappa));
+    const double kmax = getenv("GRMP_P2TET_KAPPA") ? atof(getenv("GRMP_P2TET_KAPPA")) : 16.0;
+    if (!(b->p2tet_kappa <= kmax)) want_p2 = false;
   }
+  if (want_p2) {
+    const int rc = fast_p2tet_build(ctx, p, b->pat, b->w_host, b->t1_derivs_host, b->ncols_owned, b->s1->grid->geom_version, &b->fast);
+    if (rc == GRMP_OK) b->path = GRMP_PATH_FAST;
+    else if (rc != GRMP_EUNSUPPORTED || (req == GRMP_PATH_FAST && !col_ok)) return rc;   // grids the ring walk cannot order fall through
+  }
+  if (b->path == GRMP_PATH_GENERIC && col_ok && req != GRMP_PATH_GENERIC) {
+    const int rc = colpath_build(ctx, p, b->pat, b->w_host, b->t1_vals_host, b->t1_derivs_host, b->t2_vals_host, b->t2_derivs_host,
+                                 cell_req ? -1 : b->ncols_owned, &b->colp);
+    if (rc == GRMP_OK) {
+      b->path = GRMP_PATH_COLUMNS;
+      if (cell_req) {
+        GRMP_TRY(cellpath_build(ctx, p, b->pat, req == GRMP_PATH_COLOURED, &b->colp));
+        b->path = req;
+      }
+    } else if (rc != GRMP_EUNSUPPORTED || req != GRMP_PATH_AUTO) return rc;
+  }
+  b->pat.slotmap.release();
   GRMP_CUDA(cudaEventRecord(ctx->ev1, s));
   GRMP_CUDA(cudaStreamSynchronize(s));
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   b->st.last_symbolic_ms = ms; b->st.nnz = b->pat.nnz; b->st.ncontrib = b->pat.ncontrib; b->st.path = b->path;
-  b->st.ntiles = b->fast.ntiles;
+  b->st.ntiles = b->path == GRMP_PATH_FAST ? b->fast.ntiles : (int)b->colp.ntiles;
   b->have_pattern = true; b->have_values = false;
   if (nnz_out) *nnz_out = b->pat.nnz;
   return GRMP_OK;

@@ -1,0 +1,551 @@
+// colpath.cu -- owner-computes column kernels: the numeric kernel family for every (element, operator) pair on the path.
+//
+// Replaces the cell loop of assemble! (bilinearform.jl:226-377) on a frozen pattern.  One THREAD owns one matrix column
+// (a dof of the column space); it walks the cells that contain the dof, evaluates its own local column of every such cell
+// (colpath_ev.cuh) and accumulates the entries in the shared-memory image of its column; a warp owns 32 consecutive
+// columns = one contiguous range of nzval, which it finally stores with fully coalesced writes.  Every stored non-zero is
+// written exactly once, nothing is read-modify-written in global memory, there are no atomics and the summation order is
+// fixed (cells ascending, like the reference) -> deterministic.
+//
+// Data a CTA (tile = NW groups of 32 columns) touches:
+//   * the distinct cells of the tile: geometry is evaluated ONCE per tile cell (update_trafo!/mapderiv!,
+//     feevaluator.jl:371-390, plus face signs / normals) into a shared-memory cache by all threads of the CTA;
+//   * pair records (16/32/48 B): tile-local cell, local function of the column, and for every local row its slot inside
+//     the column (255: the entry is not in the pattern -- _addnz skipped it, fematrix.jl:54-58).  Records of a group are
+//     stored ROUND-major (pair k of all 32 columns, then pair k+1, ...) so every round is one coalesced load;
+//   * the column function's reference table in shared memory (lane-varying index), the row table in constant memory
+//     (uniform index), quadrature weights in constant memory.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+#include "colpath.cuh"
+#include "colpath_ev.cuh"
+
+namespace grmp {
+
+namespace {
+
+__constant__ double c_tabR[TABR_MAX];   // row table [q][s][a]
+__constant__ double c_wq[WQ_MAX];
+
+struct ColParams {
+  GridView g;
+  const uint4* recs;
+  const unsigned short* col_np;
+  const unsigned char* col_len;
+  const i64* pairbeg;
+  const i64* colptr;        // 1-based
+  const u32* tile_cellptr;
+  const u32* tile_cells;
+  const u32* tile_list;     // tiles of this launch (one class)
+  const double* tabC;
+  double factor;
+  double act_p[2];
+  double* nzval;
+  i64 ncols_used, ngroups;
+  int nw, nq;
+};
+
+template <int NV> __device__ __forceinline__ u32 rec_byte(const u32 (&w)[NV * 4], int i) { return (w[i >> 2] >> (8 * (i & 3))) & 255u; }
+
+template <class RowEv, class ColEv, int ACT, int NV>
+__global__ void __launch_bounds__(256) col_kernel(const ColParams p) {
+  using L = CacheLayout<RowEv, ColEv>;
+  static_assert(RowEv::RD == ColEv::RD, "operator result dimensions must match");
+  static_assert(RowEv::ED == ColEv::ED, "one grid");
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthr = blockDim.x;
+  const int nq = p.nq;
+  const int ntab = ColEv::NAS * nq * CT_PAD;
+  __shared__ u32 s_nnz[8];
+  double* const sCt = sm;
+  double* const cache = sm + ((ntab + 1) & ~1);
+  const i64 tile = p.tile_list[blockIdx.x];
+  const u32 c0 = p.tile_cellptr[tile], nct = p.tile_cellptr[tile + 1] - c0;
+  const i64 grp = tile * p.nw + warp;
+  const i64 j = grp * 32 + lane;
+  const bool has = grp < p.ngroups && j < p.ncols_used;
+  const u32 np = has ? p.col_np[j] : 0u;
+  const u32 len = has ? p.col_len[j] : 0u;
+  u32 start = len;     // exclusive prefix sum of len over the warp
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u32 t = __shfl_up_sync(0xffffffffu, start, d);
+    if (lane >= d) start += t;
+  }
+  const u32 nnz_w = __shfl_sync(0xffffffffu, start, 31);
+  start -= len;
+  if (lane == 0) s_nnz[warp] = nnz_w;
+  for (int i = tid; i < ntab; i += nthr) sCt[i] = p.tabC[i];
+  for (u32 t = tid; t < nct; t += nthr) build_cell_cache<RowEv, ColEv>(p.g, (i64)p.tile_cells[c0 + t], p.factor, cache + (size_t)t * L::STRIDE);
+  __syncthreads();
+  if (grp >= p.ngroups) return;
+  u32 acc_off = 0;
+  for (int w2 = 0; w2 < warp; w2++) acc_off += (s_nnz[w2] + 1u) & ~1u;
+  double* const acc = cache + (size_t)nct * L::STRIDE + acc_off;
+  const i64 g0 = p.colptr[grp * 32] - 1;
+  const i64 recbase = p.pairbeg[grp * 32];
+  for (u32 e = lane; e < nnz_w; e += 32) acc[e] = 0.0;
+  __syncwarp();
+  const u32 maxnp = __reduce_max_sync(0xffffffffu, np);
+  const u32 lt = (1u << lane) - 1u;
+  u32 rbase = 0;
+  double* const a = acc + start;
+  for (u32 k = 0; k < maxnp; k++) {
+    const u32 bal = __ballot_sync(0xffffffffu, k < np);
+    const u32 idx = rbase + __popc(bal & lt);
+    rbase += __popc(bal);
+    if (k < np) {
+      u32 w[NV * 4];
+#pragma unroll
+      for (int v = 0; v < NV; v++) {
+        const uint4 r = __ldg(p.recs + (size_t)(recbase + idx) * NV + v);
+        w[4 * v] = r.x; w[4 * v + 1] = r.y; w[4 * v + 2] = r.z; w[4 * v + 3] = r.w;
+      }
+      const u32 lc = (w[0] >> 16) & 255u;
+      if (lc != 255u) {
+        const double* cr = cache + (size_t)(w[0] & 0xffffu) * L::STRIDE;
+        const double s = cr[0];
+        typename RowEv::Regs RR;
+        typename ColEv::Regs RC;
+        RowEv::load(cr + L::OFF_R, RR);
+        ColEv::load(cr + L::OFF_C, RC);
+        typename RowEv::Acc A;
+        RowEv::acc_zero(A);
+#pragma unroll 1
+        for (int q = 0; q < nq; q++) {
+          double Y[ColEv::RD];
+          ColEv::col_eval(RC, sCt, nq, q, (int)lc, Y);
+          const double ws = c_wq[q] * s;
+#pragma unroll
+          for (int i = 0; i < ColEv::RD; i++) Y[i] *= ws;
+          apply_action_col<ACT, ColEv::RD>(p.act_p, Y);
+          double U[RowEv::NCU][RowEv::NAS];
+          RowEv::pullback(RR, Y, U);
+          RowEv::acc_rows(A, U, c_tabR + q * (RowEv::NSF * RowEv::NAS));
+        }
+        RowEv::emit_rows(RR, A, [&](int r, double v) {
+          const u32 o = rec_byte<NV>(w, 4 + r);
+          if (o != 255u) a[o] += v;
+        });
+      }
+    }
+  }
+  __syncwarp();
+  double* __restrict__ dst = p.nzval + g0;
+  for (u32 e = lane; e < nnz_w; e += 32) dst[e] = acc[e];
+}
+
+// ---- one-time record build ------------------------------------------------------------------------------------------------
+struct PackParams {
+  const i64* colptr; const i64* rowval;        // pattern, 1-based
+  const i64* pairbeg; const u32* gcell; const u32* gsrc;   // column -> (cell, local dof) pairs, cells ascending
+  const i32* dofsR; int ndR;                   // CellDofs of the row space
+  const i32* orient; const i32* regions; RegionFilter reg;
+  const u32* tile_cellptr; const u32* tile_cells;
+  i64 ncells, ncols_used;
+  int nrow;            // rows of the kernel's row loop (reference functions for BDM1 3D)
+  int row_bdm3, col_bdm3;   // BDM1 3D: local dof <-> reference function through CellFaceOrientations (hdiv_bdm1.jl:313-328)
+  int nw, nv;
+  uint4* recs;
+  int* err;
+};
+
+__device__ __forceinline__ int bdm3_ref_of_local(const i32* o, int l) {   // subset[l], 0-based
+  const int j = l / 3, m = l - 3 * j, oj = o[j] - 1;
+  const int s1 = oj == 0 ? 1 : (oj == 1 ? 0 : (oj == 2 ? 1 : 2)), s2 = oj == 0 ? 2 : (oj == 1 ? 2 : (oj == 2 ? 0 : 1));
+  return m == 0 ? 4 * j : (m == 1 ? 4 * j + 3 - s1 : 4 * j + 3 - s2);
+}
+__device__ __forceinline__ int bdm3_local_of_ref(const i32* o, int r) {   // -1: not selected on this cell
+  const int j = r >> 2;
+  for (int m = 0; m < 3; m++)
+    if (bdm3_ref_of_local(o, 3 * j + m) == r) return 3 * j + m;
+  return -1;
+}
+
+__global__ void col_stats(const i64* colptr, const i64* pairbeg, i64 ncols_used, unsigned short* col_np, unsigned char* col_len, int* err,
+                          int* max_grp_nnz) {
+  const i64 j = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  int len = 0;
+  if (j < ncols_used) {
+    const i64 l = colptr[j + 1] - colptr[j], n = pairbeg[j + 1] - pairbeg[j];
+    if (l > 254 || n > 65535) atomicExch(err, 1);
+    col_np[j] = (unsigned short)n; col_len[j] = (unsigned char)l;
+    len = (int)l;
+  }
+  for (int d = 16; d > 0; d >>= 1) len += __shfl_xor_sync(0xffffffffu, len, d);   // blockDim is a multiple of 32 and groups are warp aligned
+  if ((threadIdx.x & 31) == 0) atomicMax(max_grp_nnz, len);
+}
+
+__global__ void tile_keys(const i64* pairbeg, const u32* gcell, i64 ncols_used, int cpt, u64* keys) {
+  const i64 j = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (j >= ncols_used) return;
+  const u64 t = (u64)(j / cpt) << 32;
+  for (i64 k = pairbeg[j]; k < pairbeg[j + 1]; k++) keys[k] = t | gcell[k];
+}
+__global__ void tile_ptr(const u64* uniq, i64 n, i64 ntiles, u32* tile_cellptr, int* max_cells) {
+  const i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (t > ntiles) return;
+  auto lb = [&](u64 key) {
+    i64 lo = 0, hi = n;
+    while (lo < hi) { const i64 mid = (lo + hi) >> 1; if (uniq[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+  };
+  const i64 b = lb((u64)t << 32);
+  tile_cellptr[t] = (u32)b;
+  if (t < ntiles) atomicMax(max_cells, (int)(lb((u64)(t + 1) << 32) - b));
+}
+// shared-memory doubles a tile needs: column table + cell cache + the nzval image of its groups
+__global__ void tile_need(const u32* tile_cellptr, const i64* colptr, i64 ntiles, i64 ncols_used, int nw, int ntab_even, int stride, int* need) {
+  const i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  i64 n = ntab_even + (i64)(tile_cellptr[t + 1] - tile_cellptr[t]) * stride;
+  for (int w = 0; w < nw; w++) {
+    const i64 c0 = min((t * nw + w) * 32, ncols_used), c1 = min(c0 + 32, ncols_used);
+    n += ((colptr[c1] - colptr[c0]) + 1) & ~1ll;
+  }
+  need[t] = (int)min(n, (i64)0x7fffffff);
+}
+__global__ void low32(const u64* a, i64 n, u32* out) {
+  const i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (u32)(a[i] & 0xffffffffull);
+}
+
+__global__ void pack_records(PackParams p) {
+  const i64 grp = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (grp * 32 >= p.ncols_used) return;
+  const i64 j = grp * 32 + lane;
+  const bool has = j < p.ncols_used;
+  const i64 kb = has ? p.pairbeg[j] : 0;
+  const u32 np = has ? (u32)(p.pairbeg[j + 1] - kb) : 0u;
+  const i64 recbase = p.pairbeg[grp * 32];
+  const i64 tile = grp / p.nw;
+  const u32 tc0 = p.tile_cellptr[tile], tc1 = p.tile_cellptr[tile + 1];
+  const i64 cb = has ? p.colptr[j] - 1 : 0, ce = has ? p.colptr[j + 1] - 1 : 0;
+  const u32 maxnp = __reduce_max_sync(0xffffffffu, np);
+  const u32 lt = (1u << lane) - 1u;
+  u32 rbase = 0;
+  for (u32 k = 0; k < maxnp; k++) {
+    const u32 bal = __ballot_sync(0xffffffffu, k < np);
+    const u32 idx = rbase + __popc(bal & lt);
+    rbase += __popc(bal);
+    if (k >= np) continue;
+    const i64 cell = p.gcell[kb + k];
+    int lc = (int)(p.gsrc[kb + k] / (u32)p.ncells);
+    bool active = true;
+    if (p.reg.n > 0) {
+      active = false;
+      if (p.regions) for (int r = 0; r < p.reg.n; r++) active = active || p.regions[cell] == p.reg.r[r];
+    }
+    if (p.col_bdm3) lc = bdm3_ref_of_local(p.orient + cell * 4, lc);
+    u32 lo = tc0, hi = tc1;
+    while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (p.tile_cells[mid] < (u32)cell) lo = mid + 1; else hi = mid; }
+    if (lo >= tc1 || p.tile_cells[lo] != (u32)cell || lo - tc0 > 65535u) atomicExch(p.err, 2);
+    u32 w[12];
+    for (int i = 0; i < 12; i++) w[i] = 0xffffffffu;
+    w[0] = (lo - tc0) | ((active ? (u32)lc : 255u) << 16) | 0xff000000u;
+    for (int r = 0; r < p.nrow; r++) {
+      int l = r;
+      if (p.row_bdm3) l = bdm3_local_of_ref(p.orient + cell * 4, r);
+      u32 off = 255u;
+      if (l >= 0) {
+        const i64 target = p.dofsR[cell * p.ndR + l];     // 1-based row
+        i64 a = cb, b = ce;
+        while (a < b) { const i64 mid = (a + b) >> 1; if (p.rowval[mid] < target) a = mid + 1; else b = mid; }
+        if (a < ce && p.rowval[a] == target) off = (u32)(a - cb);
+      }
+      const int byte = 4 + r;
+      w[byte >> 2] = (w[byte >> 2] & ~(255u << (8 * (byte & 3)))) | (off << (8 * (byte & 3)));
+    }
+    uint4* dst = p.recs + (size_t)(recbase + idx) * p.nv;
+    for (int v = 0; v < p.nv; v++) dst[v] = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
+  }
+}
+
+inline unsigned nblk(i64 n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+// ---- kernel table ----------------------------------------------------------------------------------------------------------
+typedef int (*LaunchFn)(const ColParams&, int nblocks, int nthreads, int smem, cudaStream_t);
+struct Variant {
+  bool (*match)(const ColEvalDesc& row, const ColEvalDesc& col, int act);
+  LaunchFn launch;
+  int (*cache_stride)();
+  int nrow, nv, tabR_per_q, nas_c;
+};
+
+template <class RowEv, class ColEv, int ACT> struct VariantImpl {
+  static constexpr int NV = (4 + RowEv::NROW + 15) / 16;
+  static bool match(const ColEvalDesc& row, const ColEvalDesc& col, int act) { return act == ACT && ev_matches<RowEv>(row) && ev_matches<ColEv>(col); }
+  static int launch(const ColParams& p, int nblocks, int nthreads, int smem, cudaStream_t s) {
+    static int attr_set = 0;
+    if (smem > attr_set) {
+      GRMP_CUDA(cudaFuncSetAttribute(col_kernel<RowEv, ColEv, ACT, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_set = smem;
+    }
+    col_kernel<RowEv, ColEv, ACT, NV><<<nblocks, nthreads, smem, s>>>(p);
+    GRMP_CUDA(cudaGetLastError());
+    return GRMP_OK;
+  }
+  static int cache_stride() { return CacheLayout<RowEv, ColEv>::STRIDE; }
+};
+#define GRMP_UNPAREN(...) __VA_ARGS__
+#define GRMP_VARIANT(R, C, A)                                                                                          \
+  {&VariantImpl<GRMP_UNPAREN R, GRMP_UNPAREN C, A>::match, &VariantImpl<GRMP_UNPAREN R, GRMP_UNPAREN C, A>::launch,     \
+   &VariantImpl<GRMP_UNPAREN R, GRMP_UNPAREN C, A>::cache_stride, GRMP_UNPAREN R::NROW, VariantImpl<GRMP_UNPAREN R, GRMP_UNPAREN C, A>::NV, \
+   GRMP_UNPAREN R::NSF * GRMP_UNPAREN R::NAS, GRMP_UNPAREN C::NAS},
+const Variant VARIANTS[] = {GRMP_SQUARE_FORMS(GRMP_VARIANT) GRMP_RECT_FORMS(GRMP_VARIANT)};
+constexpr int NVARIANTS = sizeof(VARIANTS) / sizeof(VARIANTS[0]);
+
+int describe(const EvalView& e, int ed, ColEvalDesc* d) {
+  d->op = e.op; d->ed = ed; d->nd = e.nd; d->fam = e.fam; d->nbub = 0;
+  if (e.op == GRMP_OP_RECON_ID_RT0 || e.op == GRMP_OP_RECON_ID_BDM1) return -1;
+  if (e.fam == FAM_H1) {
+    if (e.nd % e.ncomp) return -1;
+    d->kind = 0; d->nc = e.ncomp; d->nds = e.nd / e.ncomp;
+  } else if (e.fam == FAM_H1BR) {
+    d->kind = 0; d->nc = ed; d->nds = ed + 1; d->nbub = ed + 1;
+  } else if (e.fam == FAM_RT0 || e.fam == FAM_BDM1) {
+    d->kind = 1; d->nc = 1; d->nds = e.nd_all;
+  } else return -1;
+  return 0;
+}
+
+// host: scalar row / column tables from the caller's evaluator tables; verifies the componentwise structure
+int make_tables(const ColEvalDesc& d, int nq, const std::vector<double>& vals, const std::vector<double>& derivs, int nd_all, int ncomp,
+                std::vector<double>* T /* [s][a][q] */, int* nas) {
+  const int ed = d.ed;
+  const bool der = (d.op != GRMP_OP_ID);
+  *nas = (d.kind == 0) ? (der ? ed : 1) : (d.op == GRMP_OP_ID ? ed : 1);
+  const int nsf = d.nds + d.nbub;
+  T->assign((size_t)nsf * (*nas) * nq, 0.0);
+  auto V = [&](int q, int l, int c) { return vals[((size_t)q * nd_all + l) * ncomp + c]; };
+  auto D = [&](int q, int a, int l, int c) { return derivs[((size_t)q * ed + a) * ((size_t)nd_all * ncomp) + l + (size_t)c * nd_all]; };
+  if (der && derivs.size() != (size_t)nq * ed * nd_all * ncomp) return fail(GRMP_EUNSUPPORTED, "column kernels: derivative table missing");
+  if (!der && vals.size() != (size_t)nq * nd_all * ncomp) return fail(GRMP_EUNSUPPORTED, "column kernels: value table missing");
+  if (d.kind == 1) {
+    for (int r = 0; r < nsf; r++) for (int q = 0; q < nq; q++) {
+      if (d.op == GRMP_OP_ID) for (int a = 0; a < ed; a++) (*T)[((size_t)r * ed + a) * nq + q] = V(q, r, a);
+      else { double s = 0.0; for (int jj = 0; jj < ed; jj++) s += D(q, jj, r, jj); (*T)[(size_t)r * nq + q] = s; }
+    }
+    return GRMP_OK;
+  }
+  const int ndof = d.nc * d.nds + d.nbub;
+  if (ndof != nd_all || ncomp != d.nc) return fail(GRMP_EUNSUPPORTED, "column kernels: table shape");
+  for (int s = 0; s < nsf; s++) {
+    const int l0 = s < d.nds ? s : d.nc * d.nds + (s - d.nds);
+    for (int q = 0; q < nq; q++) {
+      if (der) for (int a = 0; a < ed; a++) (*T)[((size_t)s * ed + a) * nq + q] = D(q, a, l0, 0);
+      else (*T)[(size_t)s * nq + q] = V(q, l0, 0);
+    }
+  }
+  // structure check: dof (c, s) lives in component c only, bubbles carry the same scalar in every component
+  for (int l = 0; l < ndof; l++) for (int c = 0; c < d.nc; c++) for (int q = 0; q < nq; q++) for (int a = 0; a < *nas; a++) {
+    const bool bub = l >= d.nc * d.nds;
+    const int s = bub ? d.nds + (l - d.nc * d.nds) : l % d.nds;
+    const double expect = (bub || l / d.nds == c) ? (*T)[((size_t)s * (*nas) + a) * nq + q] : 0.0;
+    const double got = der ? D(q, a, l, c) : V(q, l, c);
+    if (got != expect) return fail(GRMP_EUNSUPPORTED, "column kernels: evaluator table is not componentwise");
+  }
+  return GRMP_OK;
+}
+
+}  // namespace
+
+static u64 g_const_owner = 0;    // uid of the ColPath whose tables are in constant memory
+static u64 g_next_uid = 1;
+
+bool colpath_applicable(const BlfLocalParams& p, int nq, ColPath* cp) {
+  if (p.apt == GRMP_APT_LUMPED) return false;
+  const bool tr = (p.apt != GRMP_APT_SYMMETRIC && p.transposed);
+  const EvalView& er = tr ? p.e2 : p.e1;
+  const EvalView& ec = tr ? p.e1 : p.e2;
+  if (describe(er, p.g.dim, &cp->row) || describe(ec, p.g.dim, &cp->col)) return false;
+  if (nq > WQ_MAX) return false;
+  cp->row_is_arg1 = !tr;
+  cp->variant = -1;
+  for (int v = 0; v < NVARIANTS; v++)
+    if (VARIANTS[v].match(cp->row, cp->col, p.action)) { cp->variant = v; break; }
+  if (cp->variant < 0) return false;
+  if ((size_t)VARIANTS[cp->variant].tabR_per_q * nq > TABR_MAX) return false;
+  cp->nq = nq;
+  return true;
+}
+
+int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const std::vector<double>& w, const std::vector<double>& vals1,
+                  const std::vector<double>& derivs1, const std::vector<double>& vals2, const std::vector<double>& derivs2, i64 ncols_owned,
+                  ColPath* cp) {
+  cudaStream_t s = ctx->stream;
+  cp->built = false;
+  cp->uid = g_next_uid++;
+  const Variant& V = VARIANTS[cp->variant];
+  const bool tr = !cp->row_is_arg1;
+  const EvalView& er = tr ? p.e2 : p.e1;
+  const EvalView& ec = tr ? p.e1 : p.e2;
+  const int nq = p.nq;
+  const i64 ncols = pat.ncols, ncells = p.g.ncells;
+  // tables
+  {
+    const std::vector<double>& v2 = p.same_eval ? vals1 : vals2;
+    const std::vector<double>& d2 = p.same_eval ? derivs1 : derivs2;
+    std::vector<double> TR, TC;
+    int nasR = 0, nasC = 0;
+    GRMP_TRY(make_tables(cp->row, nq, tr ? v2 : vals1, tr ? d2 : derivs1, er.tab_nd, er.tab_nc, &TR, &nasR));
+    GRMP_TRY(make_tables(cp->col, nq, tr ? vals1 : v2, tr ? derivs1 : d2, ec.tab_nd, ec.tab_nc, &TC, &nasC));
+    const int nsfR = cp->row.nds + cp->row.nbub, nsfC = cp->col.nds + cp->col.nbub;
+    cp->tabR.assign((size_t)nq * nsfR * nasR, 0.0);        // [q][s][a]
+    for (int q = 0; q < nq; q++) for (int sI = 0; sI < nsfR; sI++) for (int a = 0; a < nasR; a++)
+      cp->tabR[((size_t)q * nsfR + sI) * nasR + a] = TR[((size_t)sI * nasR + a) * nq + q];
+    std::vector<double> tc((size_t)nasC * nq * CT_PAD, 0.0);   // [a][q][CT_PAD]
+    for (int a = 0; a < nasC; a++) for (int q = 0; q < nq; q++) for (int sI = 0; sI < nsfC; sI++)
+      tc[((size_t)a * nq + q) * CT_PAD + sI] = TC[((size_t)sI * nasC + a) * nq + q];
+    GRMP_TRY(cp->tabC.upload(tc.data(), tc.size(), s));
+    cp->wq = w;
+  }
+  const i64 ncols_used = (ncols_owned >= 0 && ncols_owned < ncols) ? ncols_owned : ncols;
+  cp->ncols_used = ncols_used;
+  cp->ngroups = (ncols_used + 31) / 32;
+  cp->nv = V.nv;
+  if (ncols_used == 0 || pat.nnz == 0) { cp->ntiles = 0; cp->built = true; return GRMP_OK; }
+  // (1) column -> (cell, local dof) pairs, cells ascending
+  DofGather dg;
+  GRMP_TRY(build_dofgather(s, ec.celldofs, ncells, ec.nd, ncols, &dg));
+  i64 npairs_used = 0;
+  GRMP_CUDA(cudaMemcpyAsync(&npairs_used, dg.segptr.p + ncols_used, 8, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  cp->npairs = npairs_used;
+  // (2) per-column counts
+  DevBuf<int> flags;                          // [0] error, [1] max group nnz, [2] max tile cells
+  GRMP_TRY(flags.alloc(4));
+  GRMP_CUDA(cudaMemsetAsync(flags.p, 0, 16, s));
+  GRMP_TRY(cp->col_np.alloc(ncols_used)); GRMP_TRY(cp->col_len.alloc(ncols_used));
+  col_stats<<<nblk(ncols_used), 256, 0, s>>>(pat.colptr.p, dg.segptr.p, ncols_used, cp->col_np.p, cp->col_len.p, flags.p, flags.p + 1);
+  GRMP_CUDA(cudaGetLastError());
+  // (3) tiles: NW groups per CTA, distinct cells per tile; shrink the tile until the shared-memory image fits
+  int nw = getenv("GRMP_COL_NW") ? atoi(getenv("GRMP_COL_NW")) : 4;
+  nw = std::max(1, std::min(nw, 8));
+  const int stride = V.cache_stride();
+  DevBuf<u64> keys, keys2, uniq;
+  DevBuf<unsigned char> temp;
+  DevBuf<i64> nuniq_d;
+  GRMP_TRY(nuniq_d.alloc(1));
+  GRMP_TRY(keys.alloc(std::max<i64>(npairs_used, 1))); GRMP_TRY(keys2.alloc(std::max<i64>(npairs_used, 1))); GRMP_TRY(uniq.alloc(std::max<i64>(npairs_used, 1)));
+  int hflags[4] = {0, 0, 0, 0};
+  for (;; nw >>= 1) {
+    const int cpt = 32 * nw;
+    const i64 ntiles = (ncols_used + cpt - 1) / cpt;
+    tile_keys<<<nblk(ncols_used), 256, 0, s>>>(dg.segptr.p, dg.gcell.p, ncols_used, cpt, keys.p);
+    GRMP_CUDA(cudaGetLastError());
+    int end_bit = 33;
+    while (end_bit < 64 && ((u64)ntiles >> (end_bit - 32)) != 0) end_bit++;
+    size_t tb = 0, tb2 = 0;
+    GRMP_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, keys.p, keys2.p, npairs_used, 0, end_bit, s));
+    GRMP_CUDA(cub::DeviceSelect::Unique(nullptr, tb2, keys2.p, uniq.p, nuniq_d.p, npairs_used, s));
+    if (std::max(tb, tb2) > temp.n) GRMP_TRY(temp.alloc(std::max(tb, tb2)));
+    GRMP_CUDA(cub::DeviceRadixSort::SortKeys(temp.p, tb, keys.p, keys2.p, npairs_used, 0, end_bit, s));
+    GRMP_CUDA(cub::DeviceSelect::Unique(temp.p, tb2, keys2.p, uniq.p, nuniq_d.p, npairs_used, s));
+    i64 nuniq = 0;
+    GRMP_CUDA(cudaMemcpyAsync(&nuniq, nuniq_d.p, 8, cudaMemcpyDeviceToHost, s));
+    GRMP_CUDA(cudaStreamSynchronize(s));
+    if (nuniq >= (i64)0xffffffffll) return fail(GRMP_EUNSUPPORTED, "column kernels: more than 2^32 tile cells");
+    GRMP_TRY(cp->tile_cellptr.alloc(ntiles + 1));
+    GRMP_TRY(cp->tile_cells.alloc(std::max<i64>(nuniq, 1)));
+    GRMP_CUDA(cudaMemsetAsync(flags.p + 2, 0, 4, s));
+    tile_ptr<<<nblk(ntiles + 1), 256, 0, s>>>(uniq.p, nuniq, ntiles, cp->tile_cellptr.p, flags.p + 2);
+    low32<<<nblk(nuniq), 256, 0, s>>>(uniq.p, nuniq, cp->tile_cells.p);
+    GRMP_CUDA(cudaGetLastError());
+    GRMP_CUDA(cudaMemcpyAsync(hflags, flags.p, 16, cudaMemcpyDeviceToHost, s));
+    GRMP_CUDA(cudaStreamSynchronize(s));
+    if (hflags[0]) return fail(GRMP_EUNSUPPORTED, "column kernels: a column has more than 254 entries or 65535 cells");
+    // shared-memory need of every tile; tiles are launched in classes of similar need
+    const int ntab_even = (V.nas_c * nq * CT_PAD + 1) & ~1;
+    DevBuf<int> need_d;
+    GRMP_TRY(need_d.alloc(ntiles));
+    tile_need<<<nblk(ntiles), 256, 0, s>>>(cp->tile_cellptr.p, pat.colptr.p, ntiles, ncols_used, nw, ntab_even, stride, need_d.p);
+    GRMP_CUDA(cudaGetLastError());
+    std::vector<int> need(ntiles);
+    GRMP_CUDA(cudaMemcpyAsync(need.data(), need_d.p, (size_t)ntiles * 4, cudaMemcpyDeviceToHost, s));
+    GRMP_CUDA(cudaStreamSynchronize(s));
+    int need_max = 0;
+    for (int n : need) need_max = std::max(need_max, n);
+    if (hflags[2] <= 65535 && (i64)need_max * 8 <= 200 * 1024) {
+      cp->nw = nw; cp->ntiles = ntiles; cp->max_tile_cells = hflags[2]; cp->max_grp_nnz = hflags[1]; cp->smem_bytes = need_max * 8;
+      // classes: capacities that let 16 / 8 / 4 / 2 / 1 CTAs share an SM (227 KB usable, 1 KB reserved per CTA)
+      const int caps[6] = {6 * 1024, 13 * 1024, 27 * 1024, 55 * 1024, 112 * 1024, 200 * 1024};
+      std::vector<std::vector<u32>> lists(6);
+      for (i64 t = 0; t < ntiles; t++) {
+        int c = 0;
+        while (c < 5 && (i64)need[t] * 8 > caps[c]) c++;
+        lists[c].push_back((u32)t);
+      }
+      std::vector<u32> all;
+      cp->classes.clear();
+      for (int c = 0; c < 6; c++) {
+        if (lists[c].empty()) continue;
+        int mx = 0;
+        for (u32 t : lists[c]) mx = std::max(mx, need[t]);
+        cp->classes.push_back(ColPath::TileClass{mx * 8, (i64)all.size(), (i64)lists[c].size()});
+        all.insert(all.end(), lists[c].begin(), lists[c].end());
+      }
+      GRMP_TRY(cp->class_tiles.upload(all.data(), all.size(), s));
+      GRMP_CUDA(cudaStreamSynchronize(s));
+      break;
+    }
+    if (nw == 1) return fail(GRMP_EUNSUPPORTED, "column kernels: one group of 32 columns does not fit into shared memory");
+  }
+  keys.release(); keys2.release(); uniq.release(); temp.release();
+  // (4) records
+  GRMP_TRY(cp->recs.alloc((size_t)std::max<i64>(npairs_used, 1) * cp->nv));
+  PackParams pp{};
+  pp.colptr = pat.colptr.p; pp.rowval = pat.rowval.p; pp.pairbeg = dg.segptr.p; pp.gcell = dg.gcell.p; pp.gsrc = dg.gsrc.p;
+  pp.dofsR = er.celldofs; pp.ndR = er.nd; pp.orient = p.g.orient; pp.regions = p.g.regions; pp.reg = p.reg;
+  pp.tile_cellptr = cp->tile_cellptr.p; pp.tile_cells = cp->tile_cells.p; pp.ncells = ncells; pp.ncols_used = ncols_used;
+  pp.nrow = V.nrow; pp.row_bdm3 = (cp->row.kind == 1 && cp->row.nds == 16); pp.col_bdm3 = (cp->col.kind == 1 && cp->col.nds == 16);
+  pp.nw = cp->nw; pp.nv = cp->nv; pp.recs = cp->recs.p; pp.err = flags.p;
+  pack_records<<<nblk(cp->ngroups * 32, 128), 128, 0, s>>>(pp);
+  GRMP_CUDA(cudaGetLastError());
+  GRMP_CUDA(cudaMemcpyAsync(hflags, flags.p, 4, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  if (hflags[0]) return fail(GRMP_EUNSUPPORTED, "column kernels: record build failed");
+  // keep the pair offsets of the groups
+  GRMP_TRY(cp->pairbeg.alloc(ncols + 1));
+  GRMP_CUDA(cudaMemcpyAsync(cp->pairbeg.p, dg.segptr.p, (size_t)(ncols + 1) * 8, cudaMemcpyDeviceToDevice, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  if (getenv("GRMP_VERBOSE"))
+  {
+    fprintf(stderr, "[grmp columns] variant %d nw %d tiles %lld pairs %lld max tile cells %d max group nnz %d record %d B; classes:", cp->variant,
+            cp->nw, (long long)cp->ntiles, (long long)cp->npairs, cp->max_tile_cells, cp->max_grp_nnz, 16 * cp->nv);
+    for (auto& c : cp->classes) fprintf(stderr, " %lld tiles <= %d B;", (long long)c.count, c.smem_bytes);
+    fprintf(stderr, "\n");
+  }
+  cp->built = true;
+  return GRMP_OK;
+}
+
+
+int colpath_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, ColPath& cp, double* nzval) {
+  if (!cp.built) return fail(GRMP_ESTATE, "column kernels: records not built");
+  if (cp.ntiles == 0) return GRMP_OK;
+  cudaStream_t s = ctx->stream;
+  const Variant& V = VARIANTS[cp.variant];
+  if (g_const_owner != cp.uid) {
+    GRMP_CUDA(cudaMemcpyToSymbolAsync(c_tabR, cp.tabR.data(), cp.tabR.size() * 8, 0, cudaMemcpyHostToDevice, s));
+    GRMP_CUDA(cudaMemcpyToSymbolAsync(c_wq, cp.wq.data(), cp.wq.size() * 8, 0, cudaMemcpyHostToDevice, s));
+    g_const_owner = cp.uid;
+  }
+  ColParams cpar{};
+  cpar.g = p.g; cpar.recs = cp.recs.p; cpar.col_np = cp.col_np.p; cpar.col_len = cp.col_len.p; cpar.pairbeg = cp.pairbeg.p;
+  cpar.colptr = pat.colptr.p; cpar.tile_cellptr = cp.tile_cellptr.p; cpar.tile_cells = cp.tile_cells.p; cpar.tabC = cp.tabC.p;
+  cpar.factor = p.factor; cpar.act_p[0] = p.act_p[0]; cpar.act_p[1] = p.act_p[1]; cpar.nzval = nzval;
+  cpar.ncols_used = cp.ncols_used; cpar.ngroups = cp.ngroups; cpar.nw = cp.nw; cpar.nq = cp.nq;
+  for (const auto& c : cp.classes) {     // big tiles first: they have the fewest CTAs per SM and would otherwise be the tail
+    cpar.tile_list = cp.class_tiles.p + c.first;
+    GRMP_TRY(V.launch(cpar, (int)c.count, 32 * cp.nw, c.smem_bytes, s));
+  }
+  return GRMP_OK;
+}
+
+}  // namespace grmp

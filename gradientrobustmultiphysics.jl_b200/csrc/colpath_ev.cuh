@@ -1,0 +1,403 @@
+// colpath_ev.cuh -- per-cell affine pullbacks of the evaluators, written for the owner-computes column kernels
+// (colpath.cu) and the cell-parallel scatter kernels (cellpath.cu).
+//
+// A local matrix entry of assemble! (bilinearform.jl:294-317) is
+//     local[r, c] = sum_q w_q  cvR[:, r, q] . C . cvC[:, c, q]          (C: identity or the Hooke tensor)
+// and every evaluator on the path is an affine image of a reference table,
+//     cv[k, l, q] = sum_a J[k][a](cell) * coef[l](cell) * T[l][a][q]
+// (feevaluator_h1.jl:61-145: J = L2GAinv; feevaluator_hdiv.jl:2-19, 54-71: J = A / det, coef = +-1).
+// A thread that owns a matrix column evaluates ITS function once per quadrature point (table index lane-varying, from shared
+// memory), applies weight, item factor and action, pulls the result back through the row evaluator's J,
+//     U[a] = sum_k J[k][a] Y[k],
+// and then every row is a short dot product of U with the ROW table, whose index is uniform over the warp (constant memory):
+//     local[r, c] = sum_q sum_a U_q[a] * T_R[r][a][q].
+// Vector-valued H1 spaces are componentwise copies of a scalar space (h1_p1.jl:64-75, h1_p2.jl:208-239) plus, for
+// Bernardi-Raugel, one bubble per face multiplied by the face normal (h1v_br.jl:117-162, 218-273): tables hold the scalar
+// functions only, beta[c] carries the component structure.
+#pragma once
+#include "common.cuh"
+
+namespace grmp {
+
+constexpr int CT_PAD = 16;          // column tables: 16 functions per (a, q) row = 128 B -> conflict-free for any lane pattern
+constexpr int TABR_MAX = 4096;      // doubles of the row table in constant memory
+constexpr int WQ_MAX = 64;
+
+template <int ED> struct CellGeo {
+  double A[ED][ED], Ainv[ED][ED], det, idet;
+};
+
+// update_trafo! / mapderiv! (feevaluator.jl:371-390): A[:,j] = x_{j+1} - x_1, Ainv = A^{-T}
+template <int ED> __device__ __forceinline__ void cell_geo(const GridView& g, i64 cell, CellGeo<ED>& T) {
+  const i32* cn = g.cellnodes + cell * (ED + 1);
+  const double* x0 = g.coords + (i64)(cn[0] - 1) * ED;
+  double b[ED];
+#pragma unroll
+  for (int k = 0; k < ED; k++) b[k] = x0[k];
+#pragma unroll
+  for (int j = 0; j < ED; j++) {
+    const double* xj = g.coords + (i64)(cn[j + 1] - 1) * ED;
+#pragma unroll
+    for (int k = 0; k < ED; k++) T.A[k][j] = xj[k] - b[k];
+  }
+  const double(*A)[ED] = T.A;
+  if constexpr (ED == 2) {
+    T.det = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+    T.idet = 1.0 / T.det;
+    T.Ainv[1][1] = A[0][0] * T.idet;
+    T.Ainv[1][0] = -A[0][1] * T.idet;
+    T.Ainv[0][1] = -A[1][0] * T.idet;
+    T.Ainv[0][0] = A[1][1] * T.idet;
+  } else {
+    const double c00 = A[1][1] * A[2][2] - A[1][2] * A[2][1], c01 = A[1][0] * A[2][2] - A[1][2] * A[2][0], c02 = A[1][0] * A[2][1] - A[1][1] * A[2][0];
+    T.det = A[0][0] * c00 - A[0][1] * c01 + A[0][2] * c02;
+    T.idet = 1.0 / T.det;
+    T.Ainv[0][0] = c00 * T.idet;
+    T.Ainv[0][1] = -c01 * T.idet;
+    T.Ainv[0][2] = c02 * T.idet;
+    T.Ainv[1][0] = -(A[0][1] * A[2][2] - A[0][2] * A[2][1]) * T.idet;
+    T.Ainv[1][1] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) * T.idet;
+    T.Ainv[1][2] = -(A[0][0] * A[2][1] - A[0][1] * A[2][0]) * T.idet;
+    T.Ainv[2][0] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) * T.idet;
+    T.Ainv[2][1] = -(A[0][0] * A[1][2] - A[0][2] * A[1][0]) * T.idet;
+    T.Ainv[2][2] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) * T.idet;
+  }
+}
+
+__host__ __device__ constexpr int voigt_slot(int ed, int kc) {   // feevaluator.jl:231: [1,3,3,2] / [1,6,5,6,2,4,5,4,3], 0-based here
+  return ed == 2 ? (kc == 0 ? 0 : (kc == 3 ? 1 : 2))
+                 : (kc == 0 ? 0 : kc == 1 ? 5 : kc == 2 ? 4 : kc == 3 ? 5 : kc == 4 ? 1 : kc == 5 ? 3 : kc == 6 ? 4 : kc == 7 ? 3 : 2);
+}
+
+// ---- componentwise H1 spaces: P1 / P2 / P0 with NC components, Bernardi-Raugel (NC = ED, NBUB = ED + 1) -------------------
+template <int ED_, int NC_, int NDS_, int NBUB_, int OP_> struct H1Ev {
+  static constexpr int ED = ED_, NC = NC_, NDS = NDS_, NBUB = NBUB_, OP = OP_, KIND = 0;
+  static constexpr int ND = NC * NDS + NBUB, NROW = ND, NSF = NDS + NBUB;
+  static constexpr bool DER = (OP != GRMP_OP_ID);
+  static constexpr int NAS = DER ? ED : 1, NCU = NC;
+  static constexpr int RD = OP == GRMP_OP_ID ? NC : OP == GRMP_OP_GRAD ? NC * ED : OP == GRMP_OP_SYMGRAD ? (ED == 2 ? 3 : 6) : 1;
+  static constexpr int NM = DER ? ED * ED : 0;
+  static constexpr int CACHE_N = NM + NBUB * ED;
+  static_assert(NSF <= CT_PAD, "column table row too short");
+  struct Regs {
+    double M[NM > 0 ? NM : 1];
+    double nb[NBUB > 0 ? NBUB * ED : 1];
+  };
+  __device__ __forceinline__ static void build_cache(const GridView& g, i64 cell, const CellGeo<ED>& T, double* out) {
+    if constexpr (DER) {
+#pragma unroll
+      for (int k = 0; k < ED; k++)
+#pragma unroll
+        for (int a = 0; a < ED; a++) out[k * ED + a] = T.Ainv[k][a];
+    }
+    if constexpr (NBUB > 0) {   // h1v_br.jl:150-162, 253-273: bubble coefficients = face normal
+      const i32* cf = g.cellfaces + cell * (ED + 1);
+#pragma unroll
+      for (int b = 0; b < NBUB; b++)
+#pragma unroll
+        for (int c = 0; c < ED; c++) out[NM + b * ED + c] = g.fnormals[(i64)(cf[b] - 1) * ED + c];
+    }
+  }
+  __device__ __forceinline__ static void load(const double* cr, Regs& R) {
+#pragma unroll
+    for (int i = 0; i < NM; i++) R.M[i] = cr[i];
+#pragma unroll
+    for (int i = 0; i < NBUB * ED; i++) R.nb[i] = cr[NM + i];
+  }
+  // operator values of local function l at quadrature point q (Ct: [a][q][CT_PAD] scalar table)
+  __device__ __forceinline__ static void col_eval(const Regs& R, const double* __restrict__ Ct, int nq, int q, int l, double (&Y)[RD]) {
+    int s, cl;
+    double beta[NC];
+    if (NBUB > 0 && l >= NC * NDS) {
+      const int b = l - NC * NDS;
+      s = NDS + b; cl = -1;
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        double v = 0.0;
+#pragma unroll
+        for (int bb = 0; bb < NBUB; bb++) v = (bb == b) ? R.nb[bb * ED + c] : v;
+        beta[c] = v;
+      }
+    } else {
+      cl = l / NDS; s = l - cl * NDS;
+#pragma unroll
+      for (int c = 0; c < NC; c++) beta[c] = (c == cl) ? 1.0 : 0.0;
+    }
+    if constexpr (OP == GRMP_OP_ID) {
+      const double v = Ct[(size_t)q * CT_PAD + s];
+#pragma unroll
+      for (int c = 0; c < NC; c++) Y[c] = beta[c] * v;
+    } else {
+      double d[ED], gr[ED];
+#pragma unroll
+      for (int a = 0; a < ED; a++) d[a] = Ct[((size_t)a * nq + q) * CT_PAD + s];
+#pragma unroll
+      for (int k = 0; k < ED; k++) {
+        double t = 0.0;
+#pragma unroll
+        for (int a = 0; a < ED; a++) t = fma(R.M[k * ED + a], d[a], t);
+        gr[k] = t;
+      }
+      if constexpr (OP == GRMP_OP_GRAD) {
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+#pragma unroll
+          for (int k = 0; k < ED; k++) Y[c * ED + k] = beta[c] * gr[k];
+      } else if constexpr (OP == GRMP_OP_SYMGRAD) {   // feevaluator_h1.jl:97-116, offdiagval = 1
+#pragma unroll
+        for (int v = 0; v < RD; v++) Y[v] = 0.0;
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+#pragma unroll
+          for (int k = 0; k < ED; k++) Y[voigt_slot(ED, k + c * ED)] += beta[c] * gr[k];
+      } else {   // Divergence, feevaluator_h1.jl:119-145
+        double t = 0.0;
+#pragma unroll
+        for (int c = 0; c < NC; c++) t = fma(beta[c], gr[c], t);
+        Y[0] = t;
+      }
+    }
+  }
+  // U[c][a] = sum_k J[k][a] Y[...]: the column value pulled back to the reference directions of component c
+  __device__ __forceinline__ static void pullback(const Regs& R, const double (&Y)[RD], double (&U)[NCU][NAS]) {
+    if constexpr (OP == GRMP_OP_ID) {
+#pragma unroll
+      for (int c = 0; c < NC; c++) U[c][0] = Y[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < NC; c++)
+#pragma unroll
+        for (int a = 0; a < ED; a++) {
+          double t = 0.0;
+          if constexpr (OP == GRMP_OP_GRAD) {
+#pragma unroll
+            for (int k = 0; k < ED; k++) t = fma(R.M[k * ED + a], Y[c * ED + k], t);
+          } else if constexpr (OP == GRMP_OP_SYMGRAD) {
+#pragma unroll
+            for (int k = 0; k < ED; k++) t = fma(R.M[k * ED + a], Y[voigt_slot(ED, k + c * ED)], t);
+          } else {
+            t = R.M[c * ED + a] * Y[0];
+          }
+          U[c][a] = t;
+        }
+    }
+  }
+  // accumulators of one column: E[c][s] for the componentwise rows, Eb[b][c] for the bubble rows
+  struct Acc {
+    double E[NC][NDS];
+    double Eb[NBUB > 0 ? NBUB : 1][NC];
+  };
+  __device__ __forceinline__ static void acc_zero(Acc& A) {
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+#pragma unroll
+      for (int s = 0; s < NDS; s++) A.E[c][s] = 0.0;
+#pragma unroll
+    for (int b = 0; b < NBUB; b++)
+#pragma unroll
+      for (int c = 0; c < NC; c++) A.Eb[b][c] = 0.0;
+  }
+  // Rt: row table of quadrature point q, [s][a] (uniform address -> constant memory operand)
+  __device__ __forceinline__ static void acc_rows(Acc& A, const double (&U)[NCU][NAS], const double* __restrict__ Rt) {
+#pragma unroll
+    for (int s = 0; s < NDS; s++)
+#pragma unroll
+      for (int a = 0; a < NAS; a++) {
+        const double t = Rt[s * NAS + a];
+#pragma unroll
+        for (int c = 0; c < NC; c++) A.E[c][s] = fma(U[c][a], t, A.E[c][s]);
+      }
+#pragma unroll
+    for (int b = 0; b < NBUB; b++)
+#pragma unroll
+      for (int a = 0; a < NAS; a++) {
+        const double t = Rt[(NDS + b) * NAS + a];
+#pragma unroll
+        for (int c = 0; c < NC; c++) A.Eb[b][c] = fma(U[c][a], t, A.Eb[b][c]);
+      }
+  }
+  template <class F> __device__ __forceinline__ static void emit_rows(const Regs& R, const Acc& A, F&& f) {
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+#pragma unroll
+      for (int s = 0; s < NDS; s++) f(c * NDS + s, A.E[c][s]);
+#pragma unroll
+    for (int b = 0; b < NBUB; b++) {
+      double t = 0.0;
+#pragma unroll
+      for (int c = 0; c < NC; c++) t = fma(R.nb[b * ED + c], A.Eb[b][c], t);
+      f(NC * NDS + b, t);
+    }
+  }
+};
+
+// ---- Hdiv spaces (contravariant Piola): RT0 (NDALL = ED + 1), BDM1 (2D: 6, 3D: 16 reference functions of which 12 are selected) ----
+template <int ED_, int NDALL_, int OP_> struct HdivEv {
+  static constexpr int ED = ED_, NC = 1, NDS = NDALL_, NBUB = 0, OP = OP_, KIND = 1;
+  static constexpr int NROW = NDALL_, NSF = NDALL_;
+  static constexpr int NAS = OP == GRMP_OP_ID ? ED : 1, NCU = 1;
+  static constexpr int RD = OP == GRMP_OP_ID ? ED : 1;
+  static constexpr int NM = ED * ED;
+  static constexpr int CACHE_N = NM + 2;
+  static_assert(NSF <= CT_PAD, "column table row too short");
+  struct Regs {
+    double M[NM];
+    double idet;
+    u32 neg;
+  };
+  // bit r of the mask: coefficient of reference function r is negative (hdiv_rt0.jl:106-116, hdiv_bdm1.jl:278-307)
+  __device__ __forceinline__ static u32 negmask(const GridView& g, i64 cell) {
+    const i32* sg = g.signs + cell * (ED + 1);
+    u32 m = 0;
+    if constexpr (NDALL_ == ED + 1) {
+#pragma unroll
+      for (int j = 0; j < ED + 1; j++) m |= (sg[j] < 0 ? 1u : 0u) << j;
+    } else if constexpr (ED == 2) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) m |= (sg[j] < 0 ? 1u : 0u) << (2 * j);
+    } else {   // 3D: local dof 3j -> ref 4j (sign), 3j+1 -> ref 4j+3-s1[o] (-1), 3j+2 -> ref 4j+3-s2[o] (+1)
+      const i32* o = g.orient + cell * 4;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int oj = o[j] - 1;
+        const int s1 = oj == 0 ? 1 : (oj == 1 ? 0 : (oj == 2 ? 1 : 2));
+        m |= (sg[j] < 0 ? 1u : 0u) << (4 * j);
+        m |= 1u << (4 * j + 3 - s1);
+      }
+    }
+    return m;
+  }
+  __device__ __forceinline__ static void build_cache(const GridView& g, i64 cell, const CellGeo<ED>& T, double* out) {
+#pragma unroll
+    for (int k = 0; k < ED; k++)
+#pragma unroll
+      for (int a = 0; a < ED; a++) out[k * ED + a] = T.A[k][a];
+    out[NM] = T.idet;
+    out[NM + 1] = __longlong_as_double((long long)negmask(g, cell));
+  }
+  __device__ __forceinline__ static void load(const double* cr, Regs& R) {
+#pragma unroll
+    for (int i = 0; i < NM; i++) R.M[i] = cr[i];
+    R.idet = cr[NM];
+    R.neg = (u32)__double_as_longlong(cr[NM + 1]);
+  }
+  __device__ __forceinline__ static void col_eval(const Regs& R, const double* __restrict__ Ct, int nq, int q, int l, double (&Y)[RD]) {
+    const double sg = ((R.neg >> l) & 1u) ? -R.idet : R.idet;
+    if constexpr (OP == GRMP_OP_ID) {
+      double d[ED];
+#pragma unroll
+      for (int a = 0; a < ED; a++) d[a] = Ct[((size_t)a * nq + q) * CT_PAD + l];
+#pragma unroll
+      for (int k = 0; k < ED; k++) {
+        double t = 0.0;
+#pragma unroll
+        for (int a = 0; a < ED; a++) t = fma(R.M[k * ED + a], d[a], t);
+        Y[k] = sg * t;
+      }
+    } else {
+      Y[0] = sg * Ct[(size_t)q * CT_PAD + l];
+    }
+  }
+  __device__ __forceinline__ static void pullback(const Regs& R, const double (&Y)[RD], double (&U)[NCU][NAS]) {
+    if constexpr (OP == GRMP_OP_ID) {
+#pragma unroll
+      for (int a = 0; a < ED; a++) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < ED; k++) t = fma(R.M[k * ED + a], Y[k], t);
+        U[0][a] = R.idet * t;
+      }
+    } else {
+      U[0][0] = R.idet * Y[0];
+    }
+  }
+  struct Acc {
+    double E[NDALL_];
+  };
+  __device__ __forceinline__ static void acc_zero(Acc& A) {
+#pragma unroll
+    for (int r = 0; r < NDALL_; r++) A.E[r] = 0.0;
+  }
+  __device__ __forceinline__ static void acc_rows(Acc& A, const double (&U)[NCU][NAS], const double* __restrict__ Rt) {
+#pragma unroll
+    for (int r = 0; r < NDALL_; r++)
+#pragma unroll
+      for (int a = 0; a < NAS; a++) A.E[r] = fma(U[0][a], Rt[r * NAS + a], A.E[r]);
+  }
+  template <class F> __device__ __forceinline__ static void emit_rows(const Regs& R, const Acc& A, F&& f) {
+#pragma unroll
+    for (int r = 0; r < NDALL_; r++) f(r, ((R.neg >> r) & 1u) ? -A.E[r] : A.E[r]);
+  }
+};
+
+// Hooke tensors (pdeoperators.jl:265-270, 304-312) applied to the column value
+template <int ACT, int RD> __device__ __forceinline__ void apply_action_col(const double* p, double (&Y)[RD]) {
+  if constexpr (ACT == GRMP_ACT_HOOKE2D) {
+    static_assert(RD == 3, "Hooke 2D acts on Voigt vectors of length 3");
+    const double mu = p[0], la = p[1];
+    const double a = (la + 2 * mu) * Y[0] + la * Y[1], b = (la + 2 * mu) * Y[1] + la * Y[0];
+    Y[0] = a; Y[1] = b; Y[2] = mu * Y[2];
+  } else if constexpr (ACT == GRMP_ACT_HOOKE3D) {
+    static_assert(RD == 6, "Hooke 3D acts on Voigt vectors of length 6");
+    const double mu = p[0], la = p[1];
+    const double a = (la + 2 * mu) * Y[0] + la * (Y[1] + Y[2]), b = (la + 2 * mu) * Y[1] + la * (Y[0] + Y[2]),
+                 c = (la + 2 * mu) * Y[2] + la * (Y[0] + Y[1]);
+    Y[0] = a; Y[1] = b; Y[2] = c; Y[3] = mu * Y[3]; Y[4] = mu * Y[4]; Y[5] = mu * Y[5];
+  }
+}
+
+// cache record of one cell: [0] item factor (CellVolumes * factor, bilinearform.jl:320), then the row evaluator's part, then
+// the column evaluator's part unless both need the same data
+template <class RowEv, class ColEv> struct CacheLayout {
+  static constexpr bool SAME = (RowEv::KIND == ColEv::KIND && RowEv::NC == ColEv::NC && RowEv::NDS == ColEv::NDS && RowEv::NBUB == ColEv::NBUB &&
+                                RowEv::CACHE_N == ColEv::CACHE_N);
+  static constexpr int OFF_R = 1, OFF_C = SAME ? 1 : 1 + RowEv::CACHE_N;
+  static constexpr int N = 1 + RowEv::CACHE_N + (SAME ? 0 : ColEv::CACHE_N);
+  static constexpr int STRIDE = (N + 1) & ~1;     // even: records stay 16-byte aligned
+};
+
+template <class RowEv, class ColEv>
+__device__ __forceinline__ void build_cell_cache(const GridView& g, i64 cell, double factor, double* cr) {
+  using L = CacheLayout<RowEv, ColEv>;
+  CellGeo<RowEv::ED> T;
+  cell_geo<RowEv::ED>(g, cell, T);
+  cr[0] = g.vol[cell] * factor;
+  RowEv::build_cache(g, cell, T, cr + L::OFF_R);
+  if constexpr (!L::SAME) ColEv::build_cache(g, cell, T, cr + L::OFF_C);
+}
+
+// forms with a kernel: X(row evaluator, column evaluator, action)
+#define GRMP_H1_SQUARE(X, ED, NC, NDS, NB)                                                                       \
+  X((H1Ev<ED, NC, NDS, NB, GRMP_OP_GRAD>), (H1Ev<ED, NC, NDS, NB, GRMP_OP_GRAD>), GRMP_ACT_NONE)                 \
+  X((H1Ev<ED, NC, NDS, NB, GRMP_OP_ID>), (H1Ev<ED, NC, NDS, NB, GRMP_OP_ID>), GRMP_ACT_NONE)
+#define GRMP_HDIV_SQUARE(X, ED, NDALL)                                                                           \
+  X((HdivEv<ED, NDALL, GRMP_OP_ID>), (HdivEv<ED, NDALL, GRMP_OP_ID>), GRMP_ACT_NONE)                             \
+  X((HdivEv<ED, NDALL, GRMP_OP_DIV>), (HdivEv<ED, NDALL, GRMP_OP_DIV>), GRMP_ACT_NONE)
+#define GRMP_RECT(X, A, B) X(A, B, GRMP_ACT_NONE) X(B, A, GRMP_ACT_NONE)
+
+#define GRMP_SQUARE_FORMS(X)                                                                                     \
+  GRMP_H1_SQUARE(X, 2, 1, 3, 0) GRMP_H1_SQUARE(X, 2, 2, 3, 0) GRMP_H1_SQUARE(X, 2, 1, 6, 0) GRMP_H1_SQUARE(X, 2, 2, 6, 0) \
+  GRMP_H1_SQUARE(X, 2, 2, 3, 3) GRMP_H1_SQUARE(X, 2, 1, 1, 0)                                                    \
+  GRMP_H1_SQUARE(X, 3, 1, 4, 0) GRMP_H1_SQUARE(X, 3, 3, 4, 0) GRMP_H1_SQUARE(X, 3, 1, 10, 0) GRMP_H1_SQUARE(X, 3, 3, 10, 0) \
+  GRMP_H1_SQUARE(X, 3, 3, 4, 4) GRMP_H1_SQUARE(X, 3, 1, 1, 0)                                                    \
+  X((H1Ev<2, 2, 3, 0, GRMP_OP_SYMGRAD>), (H1Ev<2, 2, 3, 0, GRMP_OP_SYMGRAD>), GRMP_ACT_HOOKE2D)                  \
+  X((H1Ev<2, 2, 6, 0, GRMP_OP_SYMGRAD>), (H1Ev<2, 2, 6, 0, GRMP_OP_SYMGRAD>), GRMP_ACT_HOOKE2D)                  \
+  X((H1Ev<3, 3, 4, 0, GRMP_OP_SYMGRAD>), (H1Ev<3, 3, 4, 0, GRMP_OP_SYMGRAD>), GRMP_ACT_HOOKE3D)                  \
+  X((H1Ev<3, 3, 10, 0, GRMP_OP_SYMGRAD>), (H1Ev<3, 3, 10, 0, GRMP_OP_SYMGRAD>), GRMP_ACT_HOOKE3D)                \
+  GRMP_HDIV_SQUARE(X, 2, 3) GRMP_HDIV_SQUARE(X, 2, 6) GRMP_HDIV_SQUARE(X, 3, 4) GRMP_HDIV_SQUARE(X, 3, 16)
+
+#define GRMP_RECT_FORMS(X)                                                                                       \
+  GRMP_RECT(X, (H1Ev<2, 2, 3, 3, GRMP_OP_DIV>), (H1Ev<2, 1, 1, 0, GRMP_OP_ID>))                                  \
+  GRMP_RECT(X, (H1Ev<3, 3, 4, 4, GRMP_OP_DIV>), (H1Ev<3, 1, 1, 0, GRMP_OP_ID>))                                  \
+  GRMP_RECT(X, (H1Ev<2, 2, 6, 0, GRMP_OP_DIV>), (H1Ev<2, 1, 3, 0, GRMP_OP_ID>))                                  \
+  GRMP_RECT(X, (H1Ev<3, 3, 10, 0, GRMP_OP_DIV>), (H1Ev<3, 1, 4, 0, GRMP_OP_ID>))                                 \
+  GRMP_RECT(X, (HdivEv<2, 3, GRMP_OP_DIV>), (H1Ev<2, 1, 1, 0, GRMP_OP_ID>))                                      \
+  GRMP_RECT(X, (HdivEv<2, 6, GRMP_OP_DIV>), (H1Ev<2, 1, 1, 0, GRMP_OP_ID>))                                      \
+  GRMP_RECT(X, (HdivEv<3, 4, GRMP_OP_DIV>), (H1Ev<3, 1, 1, 0, GRMP_OP_ID>))                                      \
+  GRMP_RECT(X, (HdivEv<3, 16, GRMP_OP_DIV>), (H1Ev<3, 1, 1, 0, GRMP_OP_ID>))
+
+template <class Ev> __host__ inline bool ev_matches(const ColEvalDesc& d) {
+  return Ev::KIND == d.kind && Ev::ED == d.ed && Ev::NC == d.nc && Ev::NDS == d.nds && Ev::NBUB == d.nbub && Ev::OP == d.op;
+}
+
+}  // namespace grmp

@@ -27,6 +27,9 @@ struct FastP2Tet {
 };
 
 bool fast_p2tet_applicable(const BlfLocalParams& p);
+// max over cells T and vertices a of sum_{b != a} |S_ab| / S_aa, S = grad(lambda_a).grad(lambda_b): the factor by which the
+// row-sum identities of the ring-walk kernel amplify rounding errors (1 on non-obtuse cells)
+int fast_p2tet_quality(grmp_ctx* ctx, const BlfLocalParams& p, double* kappa);
 int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const std::vector<double>& w,
                      const std::vector<double>& derivs, i64 ncols_owned, i64 geom_version, FastP2Tet* out);
 int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, FastP2Tet& f, i64 geom_version, double* nzval);

@@ -46,6 +46,7 @@
 #include <cstdio>
 #include <chrono>
 #include <cstdlib>
+#include <cstring>
 #include <thread>
 
 #include <cub/cub.cuh>
@@ -697,6 +698,54 @@ template <int NW> int set_smem_attr(int bytes) {
   return GRMP_OK;
 }
 
+__global__ void p2tet_quality_kernel(const double* __restrict__ coords, const i32* __restrict__ cellnodes, i64 ncells, unsigned long long* out) {
+  const i64 cell = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  double kap = 0.0;
+  if (cell < ncells) {
+    const i32* cn = cellnodes + cell * 4;
+    double x[4][3];
+    for (int a = 0; a < 4; a++) for (int k = 0; k < 3; k++) x[a][k] = coords[(i64)(cn[a] - 1) * 3 + k];
+    // inward face normals (unnormalised): n_a is orthogonal to the face opposite to vertex a; S_ab ~ n_a . n_b
+    double n[4][3];
+    for (int a = 0; a < 4; a++) {
+      const int i = (a + 1) & 3, j = (a + 2) & 3, k = (a + 3) & 3;
+      const double u[3] = {x[j][0] - x[i][0], x[j][1] - x[i][1], x[j][2] - x[i][2]}, v[3] = {x[k][0] - x[i][0], x[k][1] - x[i][1], x[k][2] - x[i][2]};
+      double c[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+      const double w[3] = {x[a][0] - x[i][0], x[a][1] - x[i][1], x[a][2] - x[i][2]};
+      const double sgn = (c[0] * w[0] + c[1] * w[1] + c[2] * w[2]) < 0 ? -1.0 : 1.0;
+      for (int d = 0; d < 3; d++) n[a][d] = sgn * c[d];
+    }
+    for (int a = 0; a < 4; a++) {
+      double off = 0.0;
+      for (int b = 0; b < 4; b++) if (b != a) off += fabs(n[a][0] * n[b][0] + n[a][1] * n[b][1] + n[a][2] * n[b][2]);
+      const double dg = n[a][0] * n[a][0] + n[a][1] * n[a][1] + n[a][2] * n[a][2];
+      kap = fmax(kap, dg > 0.0 ? off / dg : 1e300);
+    }
+  }
+  for (int d = 16; d > 0; d >>= 1) kap = fmax(kap, __shfl_xor_sync(0xffffffffu, kap, d));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(kap));   // non-negative doubles order like integers
+}
+
+}  // namespace
+
+int fast_p2tet_quality(grmp_ctx* ctx, const BlfLocalParams& p, double* kappa) {
+  DevBuf<unsigned long long> d;
+  GRMP_TRY(d.alloc(1));
+  GRMP_CUDA(cudaMemsetAsync(d.p, 0, 8, ctx->stream));
+  if (p.g.ncells > 0) {
+    p2tet_quality_kernel<<<(unsigned)((p.g.ncells + 255) / 256), 256, 0, ctx->stream>>>(p.g.coords, p.g.cellnodes, p.g.ncells, d.p);
+    GRMP_CUDA(cudaGetLastError());
+  }
+  unsigned long long bits = 0;
+  GRMP_CUDA(cudaMemcpyAsync(&bits, d.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  GRMP_CUDA(cudaStreamSynchronize(ctx->stream));
+  double k;
+  memcpy(&k, &bits, 8);
+  *kappa = k;
+  return GRMP_OK;
+}
+
+namespace {
 }  // namespace
 
 bool fast_p2tet_applicable(const BlfLocalParams& p) {

@@ -46,8 +46,17 @@ enum { GRMP_ACT_NONE = 0, GRMP_ACT_HOOKE2D = 1, GRMP_ACT_HOOKE3D = 2 };
 enum { GRMP_APT_BILINEARFORM = 0, GRMP_APT_SYMMETRIC = 1, GRMP_APT_LUMPED = 2 };
 /* right-hand side data of a LinearForm (fdot_action, src/actions.jl:119-128) */
 enum { GRMP_F_NONE = 0, GRMP_F_CONST = 1, GRMP_F_QP_TABLE = 2 };
-/* numeric back ends of a bilinear form */
-enum { GRMP_PATH_AUTO = 0, GRMP_PATH_GENERIC = 1, GRMP_PATH_FAST = 2 };
+/* numeric back ends of a bilinear form
+ *   GENERIC   bit-exact two-phase path (reference operation and summation order, no FMA): the correctness path
+ *   FAST      request the fastest owner-computes kernel that exists for the form (P2TET where applicable, else COLUMNS)
+ *   P2TET     = what FAST resolves to for the metric form: ring-walk kernel of the 3D P2 Laplace stiffness matrix
+ *   COLUMNS   owner-computes column kernels (one thread per matrix column, every non-zero written once, deterministic):
+ *             H1 P1/P2/P0 (1..dim components), Bernardi-Raugel, RT0, BDM1; Identity/Gradient/SymmetricGradient+Hooke/Divergence
+ *   ATOMIC    cell-parallel kernel, FP64 atomics through the per-cell local->nnz map (measured alternative, order not fixed)
+ *   COLOURED  cell-parallel kernel under element colouring (deterministic; one launch per colour)
+ *   AUTO      P2TET if applicable and the mesh passes the cancellation guard, else COLUMNS if a kernel exists, else GENERIC */
+enum { GRMP_PATH_AUTO = 0, GRMP_PATH_GENERIC = 1, GRMP_PATH_FAST = 2, GRMP_PATH_P2TET = 2, GRMP_PATH_COLUMNS = 3, GRMP_PATH_ATOMIC = 4,
+       GRMP_PATH_COLOURED = 5 };
 
 typedef struct grmp_ctx grmp_ctx;
 typedef struct grmp_grid grmp_grid;

@@ -708,6 +708,15 @@ struct ExtSparse {
 inline void addnz(ExtSparse* A, i64 i, i64 j, double v, double fac) {
   if (v != 0.0) A->add(v * fac, i - 1, j - 1);
 }
+// Magnitude mode (test infrastructure, not part of the reference): the assembly loop accumulates sum |w_q * a_k * b_k| per
+// local entry and adds |.| into the matrix, with the zero test of _addnz still made on the true value, so the pattern is
+// unchanged.  The result S_ij bounds the rounding error of ANY evaluation order of entry ij by (#ops) * eps * S_ij; the parity
+// tests use it to tell entries that are small by cancellation (no order but the reference's own reproduces their digits)
+// from entries that are simply small.
+static bool g_magnitude_mode = false;
+inline void addnz2(ExtSparse* A, i64 i, i64 j, double vtest, double vadd) {
+  if (vtest != 0.0) A->add(vadd, i - 1, j - 1);
+}
 
 inline bool in_regions(const Grid& g, i64 cell, const i32* regions, int nregions) {
   if (nregions == 1 && regions[0] == 0) return true;        // regions == [0]
@@ -740,6 +749,7 @@ int polyorder_of(const Space& s, int edim) { return fe_info(s.fe, s.ncomp, edim)
 extern "C" {
 
 const char* orc_last_error() { return g_err.c_str(); }
+void orc_set_magnitude_mode(int on) { g_magnitude_mode = on != 0; }
 
 struct orc_grid {
   int dim; i64 nnodes, ncells, nfaces;
@@ -824,6 +834,10 @@ int orc_blf_assemble(void* Aptr, const orc_grid* og, const orc_space* os1, const
   else { rdim_action = (action == ACT_HOOKE2D) ? 3 : 6; if (in_dim != rdim_action) { g_err = "action/operator size mismatch"; return -1; } }
   if (rdim_action != e2->resultdim) { g_err = "operator result dimensions do not match"; return -1; }
   std::vector<double> local((size_t)nd1 * nd2, 0.0), action_result(rdim_action), action_input(in_dim);
+  const bool mag = g_magnitude_mode;
+  std::vector<double> localabs(mag ? (size_t)nd1 * nd2 : 0, 0.0), action_abs(rdim_action), input_abs(in_dim), params_abs(2, 0.0);
+  if (mag && act_params) { params_abs[0] = std::fabs(act_params[0]); params_abs[1] = std::fabs(act_params[1]); }
+  if (mag && transpose_copy) { g_err = "magnitude mode: no transpose copy"; return -1; }
   const bool is_symmetric = (apt == APT_SYMMETRIC);
   for (i64 item = 0; item < g.ncells; item++) {
     if (!in_regions(g, item, regions, nregions)) continue;
@@ -836,6 +850,14 @@ int orc_blf_assemble(void* Aptr, const orc_grid* og, const orc_space* os1, const
         } else {                                            // 310-313
           for (int k = 0; k < in_dim; k++) action_input[k] = e1.cv(k, di, i) * 1.0 * 1.0;
           apply_action(action, act_params, action_input.data(), action_result.data());
+        }
+        if (mag) {
+          if (action == ACT_NONE) for (int k = 0; k < rdim_action; k++) action_abs[k] = std::fabs(action_result[k]);
+          else { for (int k = 0; k < in_dim; k++) input_abs[k] = std::fabs(action_input[k]); apply_action(action, params_abs.data(), input_abs.data(), action_abs.data()); }
+          for (int dj = (apt == APT_LUMPED ? di : (locsym ? di : 0)); dj < (apt == APT_LUMPED ? di + 1 : nd2); dj++) {
+            double t = 0; for (int k = 0; k < rdim_action; k++) t += action_abs[k] * std::fabs(e2->cv(k, dj, i));
+            localabs[(size_t)di * nd2 + dj] += std::fabs(q.w[i]) * t;
+          }
         }
         // basismul! (180-220)
         if (apt == APT_LUMPED) {
@@ -851,6 +873,21 @@ int orc_blf_assemble(void* Aptr, const orc_grid* og, const orc_space* os1, const
     }
     double itemfactor = g.vol[item] * factor * 1.0;          // 320
     const i32* d1 = s1.celldofs + item * nd1; const i32* d2 = s2.celldofs + item * nd2;
+    if (mag) {
+      const double af = std::fabs(itemfactor);
+      for (int di = 0; di < nd1; di++) for (int dj = 0; dj < nd2; dj++) {
+        if (locsym && dj < di) continue;
+        if (apt == APT_LUMPED && dj != di) continue;
+        const double v = local[(size_t)di * nd2 + dj] * itemfactor, va = localabs[(size_t)di * nd2 + dj] * af;
+        i64 arow = d1[di] + offsetX, acol = d2[dj] + offsetY;
+        if (!locsym && transposed_assembly) std::swap(arow, acol);
+        addnz2(A, arow, acol, v, va);
+        if (locsym && dj != di) addnz2(A, d1[dj] + offsetX, d2[di] + offsetY, v, va);
+      }
+      std::fill(local.begin(), local.end(), 0.0);
+      std::fill(localabs.begin(), localabs.end(), 0.0);
+      continue;
+    }
     if (locsym) {                                           // 329-346
       for (int di = 0; di < nd1; di++) for (int dj = di + 1; dj < nd2; dj++) {
         double v = local[(size_t)di * nd2 + dj] * itemfactor;

@@ -160,6 +160,11 @@ def blf_assemble(A: OracleMatrix, grid, space1, space2, op1, op2, *, action=ACT_
                                   float(ft), offsetX, offsetY, bonus_quadorder))
 
 
+def set_magnitude_mode(on: bool):
+    """test infrastructure: subsequent blf_assemble calls accumulate sum |w a b| per entry (same pattern); see grmp_oracle.cpp"""
+    lib().orc_set_magnitude_mode(C.c_int(1 if on else 0))
+
+
 def lf_nq(grid, space, op, bonus_quadorder=0):
     g = _grid_struct(grid, False)
     s = _space_struct(space)
