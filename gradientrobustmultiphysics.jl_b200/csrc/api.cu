@@ -171,7 +171,7 @@ static int blf_numeric_launch(grmp_blf* b, BlfLocalParams& p, cudaStream_t s) {
     b->st.kernel_launches = 2;
   } else if (b->path == GRMP_PATH_COLUMNS) {
     GRMP_TRY(colpath_numeric(ctx, p, b->pat, b->colp, b->nzval.p));
-    b->st.kernel_launches = (i64)b->colp.classes.size();
+    b->st.kernel_launches = (i64)b->colp.classes.size();        // one launch per tile class
   } else if (b->path == GRMP_PATH_ATOMIC || b->path == GRMP_PATH_COLOURED) {
     i64 nl = 0;
     GRMP_TRY(cellpath_numeric(ctx, p, b->pat, b->colp, b->path == GRMP_PATH_ATOMIC ? 0 : 1, b->nzval.p, &nl));

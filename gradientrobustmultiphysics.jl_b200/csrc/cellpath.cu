@@ -107,7 +107,7 @@ template <class RowEv, class ColEv, int ACT> struct CellVariantImpl {
   }
 };
 #define GRMP_UNPAREN(...) __VA_ARGS__
-#define GRMP_CELLVARIANT(R, C, A) \
+#define GRMP_CELLVARIANT(R, C, A, Q) \
   {&CellVariantImpl<GRMP_UNPAREN R, GRMP_UNPAREN C, A>::match, &CellVariantImpl<GRMP_UNPAREN R, GRMP_UNPAREN C, A>::launch},
 const CellVariant CELLVARIANTS[] = {GRMP_SQUARE_FORMS(GRMP_CELLVARIANT)};
 constexpr int NCELLVARIANTS = sizeof(CELLVARIANTS) / sizeof(CELLVARIANTS[0]);

@@ -2,10 +2,13 @@
 //
 // Replaces the cell loop of assemble! (bilinearform.jl:226-377) on a frozen pattern.  One THREAD owns one matrix column
 // (a dof of the column space); it walks the cells that contain the dof, evaluates its own local column of every such cell
-// (colpath_ev.cuh) and accumulates the entries in the shared-memory image of its column; a warp owns 32 consecutive
-// columns = one contiguous range of nzval, which it finally stores with fully coalesced writes.  Every stored non-zero is
-// written exactly once, nothing is read-modify-written in global memory, there are no atomics and the summation order is
-// fixed (cells ascending, like the reference) -> deterministic.
+// (colpath_ev.cuh) and accumulates the entries in the shared-memory image of its column.  The images of the 32 columns of a
+// warp are interleaved ([slot][lane]), so the read-modify-write of a warp never has a bank conflict whatever the slots are;
+// finally every lane streams its column to nzval with 32-byte stores (full sectors).  Every stored non-zero is written
+// exactly once, nothing is read-modify-written in global memory, there are no atomics and the summation order is fixed
+// (cells ascending, like the reference) -> deterministic.
+// Columns are processed in a locality order (sorted by their first cell, then by length inside a tile), not in dof order:
+// dofs that are numbered far apart but live on the same cells (vertices of a refined grid) share the geometry cache.
 //
 // Data a CTA (tile = NW groups of 32 columns) touches:
 //   * the distinct cells of the tile: geometry is evaluated ONCE per tile cell (update_trafo!/mapderiv!,
@@ -34,10 +37,10 @@ __constant__ double c_wq[WQ_MAX];
 struct ColParams {
   GridView g;
   const uint4* recs;
-  const unsigned short* col_np;
-  const unsigned char* col_len;
-  const i64* pairbeg;
-  const i64* colptr;        // 1-based
+  const unsigned short* pos_np;    // per position (column in locality order): pairs (cells)
+  const unsigned char* pos_len;    //   stored entries
+  const i64* pos_start;            //   first nzval slot of the column (0-based)
+  const i64* pos_recbeg;           //   first record (exclusive scan of pos_np); groups start at multiples of 32
   const u32* tile_cellptr;
   const u32* tile_cells;
   const u32* tile_list;     // tiles of this launch (one class)
@@ -51,98 +54,128 @@ struct ColParams {
 
 template <int NV> __device__ __forceinline__ u32 rec_byte(const u32 (&w)[NV * 4], int i) { return (w[i >> 2] >> (8 * (i & 3))) & 255u; }
 
-template <class RowEv, class ColEv, int ACT, int NV>
+template <class RowEv, class ColEv, int ACT, int NV, int NQ>
 __global__ void __launch_bounds__(256) col_kernel(const ColParams p) {
   using L = CacheLayout<RowEv, ColEv>;
   static_assert(RowEv::RD == ColEv::RD, "operator result dimensions must match");
   static_assert(RowEv::ED == ColEv::ED, "one grid");
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthr = blockDim.x;
-  const int nq = p.nq;
-  const int ntab = ColEv::NAS * nq * CT_PAD;
-  __shared__ u32 s_nnz[8];
+  constexpr int nq = NQ;
+  constexpr int ntab = ColEv::NAS * nq * CT_PAD;
+  __shared__ u32 s_maxlen[8];
   double* const sCt = sm;
   double* const cache = sm + ((ntab + 1) & ~1);
   const i64 tile = p.tile_list[blockIdx.x];
   const u32 c0 = p.tile_cellptr[tile], nct = p.tile_cellptr[tile + 1] - c0;
   const i64 grp = tile * p.nw + warp;
-  const i64 j = grp * 32 + lane;
-  const bool has = grp < p.ngroups && j < p.ncols_used;
-  const u32 np = has ? p.col_np[j] : 0u;
-  const u32 len = has ? p.col_len[j] : 0u;
-  u32 start = len;     // exclusive prefix sum of len over the warp
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const u32 t = __shfl_up_sync(0xffffffffu, start, d);
-    if (lane >= d) start += t;
-  }
-  const u32 nnz_w = __shfl_sync(0xffffffffu, start, 31);
-  start -= len;
-  if (lane == 0) s_nnz[warp] = nnz_w;
+  const i64 pos = grp * 32 + lane;
+  const bool has = grp < p.ngroups && pos < p.ncols_used;
+  const u32 np = has ? p.pos_np[pos] : 0u;
+  const u32 len = has ? p.pos_len[pos] : 0u;
+  const u32 maxlen = __reduce_max_sync(0xffffffffu, len);
+  if (lane == 0) s_maxlen[warp] = maxlen;
   for (int i = tid; i < ntab; i += nthr) sCt[i] = p.tabC[i];
-  for (u32 t = tid; t < nct; t += nthr) build_cell_cache<RowEv, ColEv>(p.g, (i64)p.tile_cells[c0 + t], p.factor, cache + (size_t)t * L::STRIDE);
+  // geometry cache of the tile: update_trafo! / mapderiv! / coefficient data once per tile cell.  (A separate per-cell pre-pass
+  // whose records are copied here was measured: the extra round trip through memory costs more than the ~2x redundant
+  // evaluation saves -- BR x P0 0.45 -> 0.24, RT0 0.18 -> 0.14, BDM1 0.23 -> 0.24 of the roofline.)
+  for (u32 t = tid; t < nct; t += nthr) build_cell_cache<RowEv, ColEv>(p.g, (i64)p.tile_cells[c0 + t], 1.0, cache + (size_t)t * L::STRIDE);
   __syncthreads();
   if (grp >= p.ngroups) return;
   u32 acc_off = 0;
-  for (int w2 = 0; w2 < warp; w2++) acc_off += (s_nnz[w2] + 1u) & ~1u;
-  double* const acc = cache + (size_t)nct * L::STRIDE + acc_off;
-  const i64 g0 = p.colptr[grp * 32] - 1;
-  const i64 recbase = p.pairbeg[grp * 32];
-  for (u32 e = lane; e < nnz_w; e += 32) acc[e] = 0.0;
-  __syncwarp();
+  for (int w2 = 0; w2 < warp; w2++) acc_off += s_maxlen[w2] + 1u;     // + 1: trash row of every warp (entries that are not in the pattern)
+  // image of the warp's 32 columns: slot k of lane l at [k][l] -> every warp access touches 32 consecutive doubles
+  double* const a = cache + (size_t)nct * L::STRIDE + (size_t)acc_off * 32 + lane;
+  const i64 recbase = p.pos_recbeg[grp * 32];
+  for (u32 k = 0; k < maxlen; k++) a[k * 32] = 0.0;
   const u32 maxnp = __reduce_max_sync(0xffffffffu, np);
   const u32 lt = (1u << lane) - 1u;
   u32 rbase = 0;
-  double* const a = acc + start;
-  for (u32 k = 0; k < maxnp; k++) {
+  auto next_idx = [&](u32 k) -> u32 {      // record of (lane, round k); must be called for k = 0, 1, 2, ... by the whole warp
     const u32 bal = __ballot_sync(0xffffffffu, k < np);
     const u32 idx = rbase + __popc(bal & lt);
     rbase += __popc(bal);
-    if (k < np) {
-      u32 w[NV * 4];
+    return idx;
+  };
+  uint4 rn[NV];                            // record of the next round (prefetched one round ahead)
+  {
+    const u32 i0 = next_idx(0);
 #pragma unroll
-      for (int v = 0; v < NV; v++) {
-        const uint4 r = __ldg(p.recs + (size_t)(recbase + idx) * NV + v);
-        w[4 * v] = r.x; w[4 * v + 1] = r.y; w[4 * v + 2] = r.z; w[4 * v + 3] = r.w;
-      }
-      const u32 lc = (w[0] >> 16) & 255u;
-      if (lc != 255u) {
-        const double* cr = cache + (size_t)(w[0] & 0xffffu) * L::STRIDE;
-        const double s = cr[0];
-        typename RowEv::Regs RR;
-        typename ColEv::Regs RC;
-        RowEv::load(cr + L::OFF_R, RR);
-        ColEv::load(cr + L::OFF_C, RC);
-        typename RowEv::Acc A;
-        RowEv::acc_zero(A);
-#pragma unroll 1
-        for (int q = 0; q < nq; q++) {
-          double Y[ColEv::RD];
-          ColEv::col_eval(RC, sCt, nq, q, (int)lc, Y);
-          const double ws = c_wq[q] * s;
+    for (int v = 0; v < NV; v++) rn[v] = make_uint4(0x00ff0000u, 0, 0, 0);
+    if (0 < np) {
 #pragma unroll
-          for (int i = 0; i < ColEv::RD; i++) Y[i] *= ws;
-          apply_action_col<ACT, ColEv::RD>(p.act_p, Y);
-          double U[RowEv::NCU][RowEv::NAS];
-          RowEv::pullback(RR, Y, U);
-          RowEv::acc_rows(A, U, c_tabR + q * (RowEv::NSF * RowEv::NAS));
-        }
-        RowEv::emit_rows(RR, A, [&](int r, double v) {
-          const u32 o = rec_byte<NV>(w, 4 + r);
-          if (o != 255u) a[o] += v;
-        });
-      }
+      for (int v = 0; v < NV; v++) rn[v] = __ldg(p.recs + (size_t)(recbase + i0) * NV + v);
     }
   }
-  __syncwarp();
-  double* __restrict__ dst = p.nzval + g0;
-  for (u32 e = lane; e < nnz_w; e += 32) dst[e] = acc[e];
+  for (u32 k = 0; k < maxnp; k++) {
+    u32 w[NV * 4];
+#pragma unroll
+    for (int v = 0; v < NV; v++) { w[4 * v] = rn[v].x; w[4 * v + 1] = rn[v].y; w[4 * v + 2] = rn[v].z; w[4 * v + 3] = rn[v].w; }
+    {
+      const u32 i1 = next_idx(k + 1);
+      if (k + 1 < np) {
+#pragma unroll
+        for (int v = 0; v < NV; v++) rn[v] = __ldg(p.recs + (size_t)(recbase + i1) * NV + v);
+      }
+    }
+    const u32 lc = (w[0] >> 16) & 255u;
+    if (k < np && lc != 255u) {
+      const double* cr = cache + (size_t)(w[0] & 0xffffu) * L::STRIDE;
+      const double s = cr[0] * p.factor;
+      typename RowEv::Regs RR;
+      typename ColEv::Regs RC;
+      RowEv::load(cr + L::OFF_R, RR);
+      ColEv::load(cr + L::OFF_C, RC);
+      typename RowEv::Acc A;
+      RowEv::acc_zero(A);
+#pragma unroll 1
+      for (int q = 0; q < nq; q++) {
+        double Y[ColEv::RD];
+        ColEv::col_eval(RC, sCt, nq, q, (int)lc, Y);
+        const double ws = c_wq[q] * s;
+#pragma unroll
+        for (int i = 0; i < ColEv::RD; i++) Y[i] *= ws;
+        apply_action_col<ACT, ColEv::RD>(p.act_p, Y);
+        double U[RowEv::NCU][RowEv::NAS];
+        RowEv::pullback(RR, Y, U);
+        RowEv::acc_rows(A, U, c_tabR + q * (RowEv::NSF * RowEv::NAS));
+      }
+      // rows that are not in the pattern (slot 255) go to the warp's trash row: no branch per row
+      RowEv::emit_rows(RR, A, [&](int r, double v) {
+        const u32 o = min(rec_byte<NV>(w, 4 + r), maxlen);
+        a[o * 32] += v;
+      });
+    }
+  }
+  // write-out: every lane streams its own column; 32-byte stores cover whole sectors, the unaligned ends go element-wise
+  if (maxlen == 0) return;
+  double* const dst = p.nzval + (has ? p.pos_start[pos] : 0);
+  u32 head = (4u - (u32)(((size_t)dst >> 3) & 3u)) & 3u;
+  if (head > len) head = len;
+#pragma unroll
+  for (u32 i = 0; i < 3; i++)
+    if (i < head) dst[i] = a[i * 32];
+  const u32 nbody = (len - head) >> 2;
+  const u32 maxbody = __reduce_max_sync(0xffffffffu, nbody);
+  for (u32 b = 0; b < maxbody; b++) {
+    if (b < nbody) {
+      const u32 k = head + 4 * b;
+      const double v0 = a[k * 32], v1 = a[(k + 1) * 32], v2 = a[(k + 2) * 32], v3 = a[(k + 3) * 32];
+      asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + k), "d"(v0), "d"(v1), "d"(v2), "d"(v3) : "memory");
+    }
+  }
+  const u32 kt = head + 4 * nbody;
+#pragma unroll
+  for (u32 i = 0; i < 3; i++)
+    if (kt + i < len) dst[kt + i] = a[(kt + i) * 32];
 }
 
 // ---- one-time record build ------------------------------------------------------------------------------------------------
 struct PackParams {
   const i64* colptr; const i64* rowval;        // pattern, 1-based
   const i64* pairbeg; const u32* gcell; const u32* gsrc;   // column -> (cell, local dof) pairs, cells ascending
+  const u32* colperm;                          // position -> column
+  const i64* pos_recbeg;                       // position -> first record
   const i32* dofsR; int ndR;                   // CellDofs of the row space
   const i32* orient; const i32* regions; RegionFilter reg;
   const u32* tile_cellptr; const u32* tile_cells;
@@ -166,25 +199,39 @@ __device__ __forceinline__ int bdm3_local_of_ref(const i32* o, int r) {   // -1:
   return -1;
 }
 
-__global__ void col_stats(const i64* colptr, const i64* pairbeg, i64 ncols_used, unsigned short* col_np, unsigned char* col_len, int* err,
-                          int* max_grp_nnz) {
-  const i64 j = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  int len = 0;
-  if (j < ncols_used) {
-    const i64 l = colptr[j + 1] - colptr[j], n = pairbeg[j + 1] - pairbeg[j];
-    if (l > 254 || n > 65535) atomicExch(err, 1);
-    col_np[j] = (unsigned short)n; col_len[j] = (unsigned char)l;
-    len = (int)l;
-  }
-  for (int d = 16; d > 0; d >>= 1) len += __shfl_xor_sync(0xffffffffu, len, d);   // blockDim is a multiple of 32 and groups are warp aligned
-  if ((threadIdx.x & 31) == 0) atomicMax(max_grp_nnz, len);
-}
-
-__global__ void tile_keys(const i64* pairbeg, const u32* gcell, i64 ncols_used, int cpt, u64* keys) {
+// sort key of the locality order: first (lowest) cell of the column, then the column itself
+__global__ void order_keys(const i64* colptr, const i64* pairbeg, const u32* gcell, i64 ncols_used, u64* keys, u32* ids, int* err) {
   const i64 j = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (j >= ncols_used) return;
-  const u64 t = (u64)(j / cpt) << 32;
-  for (i64 k = pairbeg[j]; k < pairbeg[j + 1]; k++) keys[k] = t | gcell[k];
+  const i64 l = colptr[j + 1] - colptr[j], n = pairbeg[j + 1] - pairbeg[j];
+  if (l > 254 || n > 65535) atomicExch(err, 1);
+  const u64 first = n > 0 ? (u64)gcell[pairbeg[j]] : 0xffffffffull;
+  keys[j] = (first << 32) | (u64)j;
+  ids[j] = (u32)j;
+}
+// second key: (tile, length) -> columns of similar length share a warp (the interleaved image is sized by the longest)
+__global__ void tile_len_keys(const u32* order1, const i64* colptr, i64 ncols_used, int cpt, u64* keys) {
+  const i64 pos = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (pos >= ncols_used) return;
+  const i64 j = order1[pos];
+  keys[pos] = ((u64)(pos / cpt) << 8) | (u64)(colptr[j + 1] - colptr[j]);
+}
+__global__ void pos_arrays(const u32* colperm, const i64* colptr, const i64* pairbeg, i64 ncols_used, unsigned short* pos_np, unsigned char* pos_len,
+                           i64* pos_start, i64* np64) {
+  const i64 pos = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (pos >= ncols_used) return;
+  const i64 j = colperm[pos];
+  const i64 n = pairbeg[j + 1] - pairbeg[j];
+  pos_np[pos] = (unsigned short)n; pos_len[pos] = (unsigned char)(colptr[j + 1] - colptr[j]); pos_start[pos] = colptr[j] - 1;
+  np64[pos] = n;
+}
+__global__ void tile_keys(const u32* colperm, const i64* pairbeg, const i64* pos_recbeg, const u32* gcell, i64 ncols_used, int cpt, u64* keys) {
+  const i64 pos = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (pos >= ncols_used) return;
+  const i64 j = colperm[pos];
+  const u64 t = (u64)(pos / cpt) << 32;
+  const i64 kb = pairbeg[j], n = pairbeg[j + 1] - kb, ob = pos_recbeg[pos];
+  for (i64 k = 0; k < n; k++) keys[ob + k] = t | gcell[kb + k];
 }
 __global__ void tile_ptr(const u64* uniq, i64 n, i64 ntiles, u32* tile_cellptr, int* max_cells) {
   const i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
@@ -198,14 +245,17 @@ __global__ void tile_ptr(const u64* uniq, i64 n, i64 ntiles, u32* tile_cellptr, 
   tile_cellptr[t] = (u32)b;
   if (t < ntiles) atomicMax(max_cells, (int)(lb((u64)(t + 1) << 32) - b));
 }
-// shared-memory doubles a tile needs: column table + cell cache + the nzval image of its groups
-__global__ void tile_need(const u32* tile_cellptr, const i64* colptr, i64 ntiles, i64 ncols_used, int nw, int ntab_even, int stride, int* need) {
+// shared-memory doubles a tile needs: column table + cell cache + the interleaved images of its groups
+__global__ void tile_need(const u32* tile_cellptr, const unsigned char* pos_len, i64 ntiles, i64 ncols_used, int nw, int ntab_even, int stride,
+                          int* need) {
   const i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (t >= ntiles) return;
   i64 n = ntab_even + (i64)(tile_cellptr[t + 1] - tile_cellptr[t]) * stride;
   for (int w = 0; w < nw; w++) {
-    const i64 c0 = min((t * nw + w) * 32, ncols_used), c1 = min(c0 + 32, ncols_used);
-    n += ((colptr[c1] - colptr[c0]) + 1) & ~1ll;
+    const i64 p0 = min((t * nw + w) * 32, ncols_used), p1 = min(p0 + 32, ncols_used);
+    int mx = 0;
+    for (i64 q = p0; q < p1; q++) mx = max(mx, (int)pos_len[q]);
+    n += 32 * (i64)(mx + 1);
   }
   need[t] = (int)min(n, (i64)0x7fffffff);
 }
@@ -218,11 +268,12 @@ __global__ void pack_records(PackParams p) {
   const i64 grp = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (grp * 32 >= p.ncols_used) return;
-  const i64 j = grp * 32 + lane;
-  const bool has = j < p.ncols_used;
+  const i64 pos = grp * 32 + lane;
+  const bool has = pos < p.ncols_used;
+  const i64 j = has ? (i64)p.colperm[pos] : 0;
   const i64 kb = has ? p.pairbeg[j] : 0;
   const u32 np = has ? (u32)(p.pairbeg[j + 1] - kb) : 0u;
-  const i64 recbase = p.pairbeg[grp * 32];
+  const i64 recbase = p.pos_recbeg[grp * 32];
   const i64 tile = grp / p.nw;
   const u32 tc0 = p.tile_cellptr[tile], tc1 = p.tile_cellptr[tile + 1];
   const i64 cb = has ? p.colptr[j] - 1 : 0, ce = has ? p.colptr[j + 1] - 1 : 0;
@@ -271,31 +322,31 @@ inline unsigned nblk(i64 n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 // ---- kernel table ----------------------------------------------------------------------------------------------------------
 typedef int (*LaunchFn)(const ColParams&, int nblocks, int nthreads, int smem, cudaStream_t);
 struct Variant {
-  bool (*match)(const ColEvalDesc& row, const ColEvalDesc& col, int act);
+  bool (*match)(const ColEvalDesc& row, const ColEvalDesc& col, int act, int nq);
   LaunchFn launch;
   int (*cache_stride)();
   int nrow, nv, tabR_per_q, nas_c;
 };
 
-template <class RowEv, class ColEv, int ACT> struct VariantImpl {
+template <class RowEv, class ColEv, int ACT, int NQ> struct VariantImpl {
   static constexpr int NV = (4 + RowEv::NROW + 15) / 16;
-  static bool match(const ColEvalDesc& row, const ColEvalDesc& col, int act) { return act == ACT && ev_matches<RowEv>(row) && ev_matches<ColEv>(col); }
+  static bool match(const ColEvalDesc& row, const ColEvalDesc& col, int act, int nq) { return act == ACT && nq == NQ && ev_matches<RowEv>(row) && ev_matches<ColEv>(col); }
   static int launch(const ColParams& p, int nblocks, int nthreads, int smem, cudaStream_t s) {
     static int attr_set = 0;
     if (smem > attr_set) {
-      GRMP_CUDA(cudaFuncSetAttribute(col_kernel<RowEv, ColEv, ACT, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      GRMP_CUDA(cudaFuncSetAttribute(col_kernel<RowEv, ColEv, ACT, NV, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       attr_set = smem;
     }
-    col_kernel<RowEv, ColEv, ACT, NV><<<nblocks, nthreads, smem, s>>>(p);
+    col_kernel<RowEv, ColEv, ACT, NV, NQ><<<nblocks, nthreads, smem, s>>>(p);
     GRMP_CUDA(cudaGetLastError());
     return GRMP_OK;
   }
   static int cache_stride() { return CacheLayout<RowEv, ColEv>::STRIDE; }
 };
 #define GRMP_UNPAREN(...) __VA_ARGS__
-#define GRMP_VARIANT(R, C, A)                                                                                          \
-  {&VariantImpl<GRMP_UNPAREN R, GRMP_UNPAREN C, A>::match, &VariantImpl<GRMP_UNPAREN R, GRMP_UNPAREN C, A>::launch,     \
-   &VariantImpl<GRMP_UNPAREN R, GRMP_UNPAREN C, A>::cache_stride, GRMP_UNPAREN R::NROW, VariantImpl<GRMP_UNPAREN R, GRMP_UNPAREN C, A>::NV, \
+#define GRMP_VARIANT(R, C, A, Q)                                                                                       \
+  {&VariantImpl<GRMP_UNPAREN R, GRMP_UNPAREN C, A, Q>::match, &VariantImpl<GRMP_UNPAREN R, GRMP_UNPAREN C, A, Q>::launch, \
+   &VariantImpl<GRMP_UNPAREN R, GRMP_UNPAREN C, A, Q>::cache_stride, GRMP_UNPAREN R::NROW, VariantImpl<GRMP_UNPAREN R, GRMP_UNPAREN C, A, Q>::NV, \
    GRMP_UNPAREN R::NSF * GRMP_UNPAREN R::NAS, GRMP_UNPAREN C::NAS},
 const Variant VARIANTS[] = {GRMP_SQUARE_FORMS(GRMP_VARIANT) GRMP_RECT_FORMS(GRMP_VARIANT)};
 constexpr int NVARIANTS = sizeof(VARIANTS) / sizeof(VARIANTS[0]);
@@ -368,7 +419,7 @@ bool colpath_applicable(const BlfLocalParams& p, int nq, ColPath* cp) {
   cp->row_is_arg1 = !tr;
   cp->variant = -1;
   for (int v = 0; v < NVARIANTS; v++)
-    if (VARIANTS[v].match(cp->row, cp->col, p.action)) { cp->variant = v; break; }
+    if (VARIANTS[v].match(cp->row, cp->col, p.action, nq)) { cp->variant = v; break; }
   if (cp->variant < 0) return false;
   if ((size_t)VARIANTS[cp->variant].tabR_per_q * nq > TABR_MAX) return false;
   cp->nq = nq;
@@ -417,27 +468,63 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
   GRMP_CUDA(cudaMemcpyAsync(&npairs_used, dg.segptr.p + ncols_used, 8, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaStreamSynchronize(s));
   cp->npairs = npairs_used;
-  // (2) per-column counts
-  DevBuf<int> flags;                          // [0] error, [1] max group nnz, [2] max tile cells
+  // (2) locality order of the columns: by first cell (radix sort, stable)
+  DevBuf<int> flags;                          // [0] error, [2] max tile cells
   GRMP_TRY(flags.alloc(4));
   GRMP_CUDA(cudaMemsetAsync(flags.p, 0, 16, s));
-  GRMP_TRY(cp->col_np.alloc(ncols_used)); GRMP_TRY(cp->col_len.alloc(ncols_used));
-  col_stats<<<nblk(ncols_used), 256, 0, s>>>(pat.colptr.p, dg.segptr.p, ncols_used, cp->col_np.p, cp->col_len.p, flags.p, flags.p + 1);
+  DevBuf<u64> ck1, ck2; DevBuf<u32> ci1, ci2; DevBuf<unsigned char> temp;
+  GRMP_TRY(ck1.alloc(ncols_used)); GRMP_TRY(ck2.alloc(ncols_used)); GRMP_TRY(ci1.alloc(ncols_used)); GRMP_TRY(ci2.alloc(ncols_used));
+  order_keys<<<nblk(ncols_used), 256, 0, s>>>(pat.colptr.p, dg.segptr.p, dg.gcell.p, ncols_used, ck1.p, ci1.p, flags.p);
   GRMP_CUDA(cudaGetLastError());
-  // (3) tiles: NW groups per CTA, distinct cells per tile; shrink the tile until the shared-memory image fits
+  const bool natural = getenv("GRMP_COL_NATURAL_ORDER") != nullptr;    // experiment: keep the dof order
+  {
+    cub::DoubleBuffer<u64> dk(ck1.p, ck2.p);
+    cub::DoubleBuffer<u32> dv(ci1.p, ci2.p);
+    if (!natural) {
+      size_t tb = 0;
+      GRMP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, ncols_used, 0, 64, s));
+      if (tb > temp.n) GRMP_TRY(temp.alloc(tb));
+      GRMP_CUDA(cub::DeviceRadixSort::SortPairs(temp.p, tb, dk, dv, ncols_used, 0, 64, s));
+    }
+    if (dv.Current() != ci1.p) GRMP_CUDA(cudaMemcpyAsync(ci1.p, dv.Current(), (size_t)ncols_used * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  // (3) tiles: NW groups per CTA; inside a tile columns are ordered by length; distinct cells per tile; shrink the tile until
+  //     the shared-memory image fits
   int nw = getenv("GRMP_COL_NW") ? atoi(getenv("GRMP_COL_NW")) : 4;
   nw = std::max(1, std::min(nw, 8));
   const int stride = V.cache_stride();
   DevBuf<u64> keys, keys2, uniq;
-  DevBuf<unsigned char> temp;
-  DevBuf<i64> nuniq_d;
+  DevBuf<i64> nuniq_d, np64;
   GRMP_TRY(nuniq_d.alloc(1));
   GRMP_TRY(keys.alloc(std::max<i64>(npairs_used, 1))); GRMP_TRY(keys2.alloc(std::max<i64>(npairs_used, 1))); GRMP_TRY(uniq.alloc(std::max<i64>(npairs_used, 1)));
+  GRMP_TRY(cp->colperm.alloc(ncols_used)); GRMP_TRY(cp->pos_np.alloc(ncols_used)); GRMP_TRY(cp->pos_len.alloc(ncols_used));
+  GRMP_TRY(cp->pos_start.alloc(ncols_used)); GRMP_TRY(cp->pos_recbeg.alloc(ncols_used + 1)); GRMP_TRY(np64.alloc(ncols_used + 1));
   int hflags[4] = {0, 0, 0, 0};
   for (;; nw >>= 1) {
     const int cpt = 32 * nw;
     const i64 ntiles = (ncols_used + cpt - 1) / cpt;
-    tile_keys<<<nblk(ncols_used), 256, 0, s>>>(dg.segptr.p, dg.gcell.p, ncols_used, cpt, keys.p);
+    {
+      tile_len_keys<<<nblk(ncols_used), 256, 0, s>>>(ci1.p, pat.colptr.p, ncols_used, cpt, ck1.p);
+      GRMP_CUDA(cudaGetLastError());
+      GRMP_CUDA(cudaMemcpyAsync(ci2.p, ci1.p, (size_t)ncols_used * 4, cudaMemcpyDeviceToDevice, s));
+      cub::DoubleBuffer<u64> dk(ck1.p, ck2.p);
+      cub::DoubleBuffer<u32> dv(ci2.p, cp->colperm.p);
+      size_t tb = 0;
+      GRMP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, ncols_used, 0, 64, s));
+      if (tb > temp.n) GRMP_TRY(temp.alloc(tb));
+      GRMP_CUDA(cub::DeviceRadixSort::SortPairs(temp.p, tb, dk, dv, ncols_used, 0, 64, s));
+      if (dv.Current() != cp->colperm.p) GRMP_CUDA(cudaMemcpyAsync(cp->colperm.p, dv.Current(), (size_t)ncols_used * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    pos_arrays<<<nblk(ncols_used), 256, 0, s>>>(cp->colperm.p, pat.colptr.p, dg.segptr.p, ncols_used, cp->pos_np.p, cp->pos_len.p, cp->pos_start.p, np64.p);
+    GRMP_CUDA(cudaGetLastError());
+    GRMP_CUDA(cudaMemsetAsync(np64.p + ncols_used, 0, 8, s));
+    {
+      size_t tb = 0;
+      GRMP_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, np64.p, cp->pos_recbeg.p, ncols_used + 1, s));
+      if (tb > temp.n) GRMP_TRY(temp.alloc(tb));
+      GRMP_CUDA(cub::DeviceScan::ExclusiveSum(temp.p, tb, np64.p, cp->pos_recbeg.p, ncols_used + 1, s));
+    }
+    tile_keys<<<nblk(ncols_used), 256, 0, s>>>(cp->colperm.p, dg.segptr.p, cp->pos_recbeg.p, dg.gcell.p, ncols_used, cpt, keys.p);
     GRMP_CUDA(cudaGetLastError());
     int end_bit = 33;
     while (end_bit < 64 && ((u64)ntiles >> (end_bit - 32)) != 0) end_bit++;
@@ -464,7 +551,7 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
     const int ntab_even = (V.nas_c * nq * CT_PAD + 1) & ~1;
     DevBuf<int> need_d;
     GRMP_TRY(need_d.alloc(ntiles));
-    tile_need<<<nblk(ntiles), 256, 0, s>>>(cp->tile_cellptr.p, pat.colptr.p, ntiles, ncols_used, nw, ntab_even, stride, need_d.p);
+    tile_need<<<nblk(ntiles), 256, 0, s>>>(cp->tile_cellptr.p, cp->pos_len.p, ntiles, ncols_used, nw, ntab_even, stride, need_d.p);
     GRMP_CUDA(cudaGetLastError());
     std::vector<int> need(ntiles);
     GRMP_CUDA(cudaMemcpyAsync(need.data(), need_d.p, (size_t)ntiles * 4, cudaMemcpyDeviceToHost, s));
@@ -472,7 +559,7 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
     int need_max = 0;
     for (int n : need) need_max = std::max(need_max, n);
     if (hflags[2] <= 65535 && (i64)need_max * 8 <= 200 * 1024) {
-      cp->nw = nw; cp->ntiles = ntiles; cp->max_tile_cells = hflags[2]; cp->max_grp_nnz = hflags[1]; cp->smem_bytes = need_max * 8;
+      cp->nw = nw; cp->ntiles = ntiles; cp->max_tile_cells = hflags[2]; cp->smem_bytes = need_max * 8;
       // classes: capacities that let 16 / 8 / 4 / 2 / 1 CTAs share an SM (227 KB usable, 1 KB reserved per CTA)
       const int caps[6] = {6 * 1024, 13 * 1024, 27 * 1024, 55 * 1024, 112 * 1024, 200 * 1024};
       std::vector<std::vector<u32>> lists(6);
@@ -483,7 +570,7 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
       }
       std::vector<u32> all;
       cp->classes.clear();
-      for (int c = 0; c < 6; c++) {
+      for (int c = 5; c >= 0; c--) {       // crowded tiles first
         if (lists[c].empty()) continue;
         int mx = 0;
         for (u32 t : lists[c]) mx = std::max(mx, need[t]);
@@ -496,11 +583,12 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
     }
     if (nw == 1) return fail(GRMP_EUNSUPPORTED, "column kernels: one group of 32 columns does not fit into shared memory");
   }
-  keys.release(); keys2.release(); uniq.release(); temp.release();
+  keys.release(); keys2.release(); uniq.release(); temp.release(); ck1.release(); ck2.release(); ci1.release(); ci2.release(); np64.release();
   // (4) records
   GRMP_TRY(cp->recs.alloc((size_t)std::max<i64>(npairs_used, 1) * cp->nv));
   PackParams pp{};
   pp.colptr = pat.colptr.p; pp.rowval = pat.rowval.p; pp.pairbeg = dg.segptr.p; pp.gcell = dg.gcell.p; pp.gsrc = dg.gsrc.p;
+  pp.colperm = cp->colperm.p; pp.pos_recbeg = cp->pos_recbeg.p;
   pp.dofsR = er.celldofs; pp.ndR = er.nd; pp.orient = p.g.orient; pp.regions = p.g.regions; pp.reg = p.reg;
   pp.tile_cellptr = cp->tile_cellptr.p; pp.tile_cells = cp->tile_cells.p; pp.ncells = ncells; pp.ncols_used = ncols_used;
   pp.nrow = V.nrow; pp.row_bdm3 = (cp->row.kind == 1 && cp->row.nds == 16); pp.col_bdm3 = (cp->col.kind == 1 && cp->col.nds == 16);
@@ -510,14 +598,10 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
   GRMP_CUDA(cudaMemcpyAsync(hflags, flags.p, 4, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaStreamSynchronize(s));
   if (hflags[0]) return fail(GRMP_EUNSUPPORTED, "column kernels: record build failed");
-  // keep the pair offsets of the groups
-  GRMP_TRY(cp->pairbeg.alloc(ncols + 1));
-  GRMP_CUDA(cudaMemcpyAsync(cp->pairbeg.p, dg.segptr.p, (size_t)(ncols + 1) * 8, cudaMemcpyDeviceToDevice, s));
-  GRMP_CUDA(cudaStreamSynchronize(s));
   if (getenv("GRMP_VERBOSE"))
   {
-    fprintf(stderr, "[grmp columns] variant %d nw %d tiles %lld pairs %lld max tile cells %d max group nnz %d record %d B; classes:", cp->variant,
-            cp->nw, (long long)cp->ntiles, (long long)cp->npairs, cp->max_tile_cells, cp->max_grp_nnz, 16 * cp->nv);
+    fprintf(stderr, "[grmp columns] variant %d nw %d tiles %lld pairs %lld tile cells %lld (max %d per tile) record %d B; classes:", cp->variant,
+            cp->nw, (long long)cp->ntiles, (long long)cp->npairs, (long long)cp->tile_cells.n, cp->max_tile_cells, 16 * cp->nv);
     for (auto& c : cp->classes) fprintf(stderr, " %lld tiles <= %d B;", (long long)c.count, c.smem_bytes);
     fprintf(stderr, "\n");
   }
@@ -537,8 +621,8 @@ int colpath_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, 
     g_const_owner = cp.uid;
   }
   ColParams cpar{};
-  cpar.g = p.g; cpar.recs = cp.recs.p; cpar.col_np = cp.col_np.p; cpar.col_len = cp.col_len.p; cpar.pairbeg = cp.pairbeg.p;
-  cpar.colptr = pat.colptr.p; cpar.tile_cellptr = cp.tile_cellptr.p; cpar.tile_cells = cp.tile_cells.p; cpar.tabC = cp.tabC.p;
+  cpar.g = p.g; cpar.recs = cp.recs.p; cpar.pos_np = cp.pos_np.p; cpar.pos_len = cp.pos_len.p; cpar.pos_start = cp.pos_start.p;
+  cpar.pos_recbeg = cp.pos_recbeg.p; cpar.tile_cellptr = cp.tile_cellptr.p; cpar.tile_cells = cp.tile_cells.p; cpar.tabC = cp.tabC.p;
   cpar.factor = p.factor; cpar.act_p[0] = p.act_p[0]; cpar.act_p[1] = p.act_p[1]; cpar.nzval = nzval;
   cpar.ncols_used = cp.ncols_used; cpar.ngroups = cp.ngroups; cpar.nw = cp.nw; cpar.nq = cp.nq;
   for (const auto& c : cp.classes) {     // big tiles first: they have the fewest CTAs per SM and would otherwise be the tail

@@ -38,9 +38,11 @@ struct ColPath {
   ColEvalDesc row{}, col{};
   bool row_is_arg1 = true;         // rows of the output = first argument (no transposed_assembly)
   DevBuf<uint4> recs;              // pair records, round-major inside every group of 32 columns
-  DevBuf<unsigned short> col_np;   // pairs (cells) per column
-  DevBuf<unsigned char> col_len;   // stored entries per column
-  DevBuf<i64> pairbeg;             // [ncols+1] first pair of every column (= first record of every group at multiples of 32)
+  DevBuf<u32> colperm;             // position in the locality order -> column
+  DevBuf<unsigned short> pos_np;   // per position: pairs (cells) of the column
+  DevBuf<unsigned char> pos_len;   //   stored entries of the column
+  DevBuf<i64> pos_start;           //   first nzval slot of the column (0-based)
+  DevBuf<i64> pos_recbeg;          // [ncols_used+1] first record of every position (groups start at multiples of 32)
   DevBuf<u32> tile_cellptr;        // [ntiles+1]
   DevBuf<u32> tile_cells;          // distinct cells of every tile (0-based)
   DevBuf<double> tabC;             // column-function table [a][q][16]

@@ -29,7 +29,14 @@ template <int ED> struct CellGeo {
 
 // update_trafo! / mapderiv! (feevaluator.jl:371-390): A[:,j] = x_{j+1} - x_1, Ainv = A^{-T}
 template <int ED> __device__ __forceinline__ void cell_geo(const GridView& g, i64 cell, CellGeo<ED>& T) {
-  const i32* cn = g.cellnodes + cell * (ED + 1);
+  i32 cn[ED + 1];
+  if constexpr (ED == 3) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(g.cellnodes) + cell);
+    cn[0] = v.x; cn[1] = v.y; cn[2] = v.z; cn[3] = v.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < ED + 1; j++) cn[j] = __ldg(g.cellnodes + cell * (ED + 1) + j);
+  }
   const double* x0 = g.coords + (i64)(cn[0] - 1) * ED;
   double b[ED];
 #pragma unroll
@@ -356,6 +363,7 @@ template <class RowEv, class ColEv> struct CacheLayout {
   static constexpr int STRIDE = (N + 1) & ~1;     // even: records stay 16-byte aligned
 };
 
+// (the column kernels store CellVolumes here and apply `factor` when they read the record)
 template <class RowEv, class ColEv>
 __device__ __forceinline__ void build_cell_cache(const GridView& g, i64 cell, double factor, double* cr) {
   using L = CacheLayout<RowEv, ColEv>;
@@ -366,35 +374,41 @@ __device__ __forceinline__ void build_cell_cache(const GridView& g, i64 cell, do
   if constexpr (!L::SAME) ColEv::build_cache(g, cell, T, cr + L::OFF_C);
 }
 
-// forms with a kernel: X(row evaluator, column evaluator, action)
-#define GRMP_H1_SQUARE(X, ED, NC, NDS, NB)                                                                       \
-  X((H1Ev<ED, NC, NDS, NB, GRMP_OP_GRAD>), (H1Ev<ED, NC, NDS, NB, GRMP_OP_GRAD>), GRMP_ACT_NONE)                 \
-  X((H1Ev<ED, NC, NDS, NB, GRMP_OP_ID>), (H1Ev<ED, NC, NDS, NB, GRMP_OP_ID>), GRMP_ACT_NONE)
-#define GRMP_HDIV_SQUARE(X, ED, NDALL)                                                                           \
-  X((HdivEv<ED, NDALL, GRMP_OP_ID>), (HdivEv<ED, NDALL, GRMP_OP_ID>), GRMP_ACT_NONE)                             \
-  X((HdivEv<ED, NDALL, GRMP_OP_DIV>), (HdivEv<ED, NDALL, GRMP_OP_DIV>), GRMP_ACT_NONE)
-#define GRMP_RECT(X, A, B) X(A, B, GRMP_ACT_NONE) X(B, A, GRMP_ACT_NONE)
+// forms with a kernel: X(row evaluator, column evaluator, action, NQ).  NQ is the number of quadrature points of the rule that
+// prepare_assembly! picks for the form (assemblypatterns.jl:559-565: order = sum(polynomial order + operator shift); midpoint
+// rules 1 point, order-2 rules 3 / 4 points, order 4: 9-point Stroud rule / 11-point tetrahedron rule).  A compile-time NQ lets
+// the row table sit in the FMA's constant operand; forms assembled with another rule (bonus_quadorder) use the generic path.
+#define GRMP_H1_SQUARE(X, ED, NC, NDS, NB, NQG, NQI)                                                             \
+  X((H1Ev<ED, NC, NDS, NB, GRMP_OP_GRAD>), (H1Ev<ED, NC, NDS, NB, GRMP_OP_GRAD>), GRMP_ACT_NONE, NQG)            \
+  X((H1Ev<ED, NC, NDS, NB, GRMP_OP_ID>), (H1Ev<ED, NC, NDS, NB, GRMP_OP_ID>), GRMP_ACT_NONE, NQI)
+#define GRMP_HDIV_SQUARE(X, ED, NDALL, NQI)                                                                      \
+  X((HdivEv<ED, NDALL, GRMP_OP_ID>), (HdivEv<ED, NDALL, GRMP_OP_ID>), GRMP_ACT_NONE, NQI)                        \
+  X((HdivEv<ED, NDALL, GRMP_OP_DIV>), (HdivEv<ED, NDALL, GRMP_OP_DIV>), GRMP_ACT_NONE, 1)
+#define GRMP_RECT(X, A, B, NQ) X(A, B, GRMP_ACT_NONE, NQ) X(B, A, GRMP_ACT_NONE, NQ)
 
 #define GRMP_SQUARE_FORMS(X)                                                                                     \
-  GRMP_H1_SQUARE(X, 2, 1, 3, 0) GRMP_H1_SQUARE(X, 2, 2, 3, 0) GRMP_H1_SQUARE(X, 2, 1, 6, 0) GRMP_H1_SQUARE(X, 2, 2, 6, 0) \
-  GRMP_H1_SQUARE(X, 2, 2, 3, 3) GRMP_H1_SQUARE(X, 2, 1, 1, 0)                                                    \
-  GRMP_H1_SQUARE(X, 3, 1, 4, 0) GRMP_H1_SQUARE(X, 3, 3, 4, 0) GRMP_H1_SQUARE(X, 3, 1, 10, 0) GRMP_H1_SQUARE(X, 3, 3, 10, 0) \
-  GRMP_H1_SQUARE(X, 3, 3, 4, 4) GRMP_H1_SQUARE(X, 3, 1, 1, 0)                                                    \
-  X((H1Ev<2, 2, 3, 0, GRMP_OP_SYMGRAD>), (H1Ev<2, 2, 3, 0, GRMP_OP_SYMGRAD>), GRMP_ACT_HOOKE2D)                  \
-  X((H1Ev<2, 2, 6, 0, GRMP_OP_SYMGRAD>), (H1Ev<2, 2, 6, 0, GRMP_OP_SYMGRAD>), GRMP_ACT_HOOKE2D)                  \
-  X((H1Ev<3, 3, 4, 0, GRMP_OP_SYMGRAD>), (H1Ev<3, 3, 4, 0, GRMP_OP_SYMGRAD>), GRMP_ACT_HOOKE3D)                  \
-  X((H1Ev<3, 3, 10, 0, GRMP_OP_SYMGRAD>), (H1Ev<3, 3, 10, 0, GRMP_OP_SYMGRAD>), GRMP_ACT_HOOKE3D)                \
-  GRMP_HDIV_SQUARE(X, 2, 3) GRMP_HDIV_SQUARE(X, 2, 6) GRMP_HDIV_SQUARE(X, 3, 4) GRMP_HDIV_SQUARE(X, 3, 16)
+  GRMP_H1_SQUARE(X, 2, 1, 3, 0, 1, 3) GRMP_H1_SQUARE(X, 2, 2, 3, 0, 1, 3) GRMP_H1_SQUARE(X, 2, 1, 6, 0, 3, 9)    \
+  GRMP_H1_SQUARE(X, 2, 2, 6, 0, 3, 9) GRMP_H1_SQUARE(X, 2, 2, 3, 3, 3, 9)                                        \
+  X((H1Ev<2, 1, 1, 0, GRMP_OP_ID>), (H1Ev<2, 1, 1, 0, GRMP_OP_ID>), GRMP_ACT_NONE, 1)                            \
+  GRMP_H1_SQUARE(X, 3, 1, 4, 0, 1, 4) GRMP_H1_SQUARE(X, 3, 3, 4, 0, 1, 4) GRMP_H1_SQUARE(X, 3, 1, 10, 0, 4, 11)  \
+  GRMP_H1_SQUARE(X, 3, 3, 10, 0, 4, 11)                                                                          \
+  X((H1Ev<3, 3, 4, 4, GRMP_OP_GRAD>), (H1Ev<3, 3, 4, 4, GRMP_OP_GRAD>), GRMP_ACT_NONE, 11)                       \
+  X((H1Ev<3, 1, 1, 0, GRMP_OP_ID>), (H1Ev<3, 1, 1, 0, GRMP_OP_ID>), GRMP_ACT_NONE, 1)                            \
+  X((H1Ev<2, 2, 3, 0, GRMP_OP_SYMGRAD>), (H1Ev<2, 2, 3, 0, GRMP_OP_SYMGRAD>), GRMP_ACT_HOOKE2D, 1)               \
+  X((H1Ev<2, 2, 6, 0, GRMP_OP_SYMGRAD>), (H1Ev<2, 2, 6, 0, GRMP_OP_SYMGRAD>), GRMP_ACT_HOOKE2D, 3)               \
+  X((H1Ev<3, 3, 4, 0, GRMP_OP_SYMGRAD>), (H1Ev<3, 3, 4, 0, GRMP_OP_SYMGRAD>), GRMP_ACT_HOOKE3D, 1)               \
+  X((H1Ev<3, 3, 10, 0, GRMP_OP_SYMGRAD>), (H1Ev<3, 3, 10, 0, GRMP_OP_SYMGRAD>), GRMP_ACT_HOOKE3D, 4)             \
+  GRMP_HDIV_SQUARE(X, 2, 3, 3) GRMP_HDIV_SQUARE(X, 2, 6, 3) GRMP_HDIV_SQUARE(X, 3, 4, 4) GRMP_HDIV_SQUARE(X, 3, 16, 4)
 
 #define GRMP_RECT_FORMS(X)                                                                                       \
-  GRMP_RECT(X, (H1Ev<2, 2, 3, 3, GRMP_OP_DIV>), (H1Ev<2, 1, 1, 0, GRMP_OP_ID>))                                  \
-  GRMP_RECT(X, (H1Ev<3, 3, 4, 4, GRMP_OP_DIV>), (H1Ev<3, 1, 1, 0, GRMP_OP_ID>))                                  \
-  GRMP_RECT(X, (H1Ev<2, 2, 6, 0, GRMP_OP_DIV>), (H1Ev<2, 1, 3, 0, GRMP_OP_ID>))                                  \
-  GRMP_RECT(X, (H1Ev<3, 3, 10, 0, GRMP_OP_DIV>), (H1Ev<3, 1, 4, 0, GRMP_OP_ID>))                                 \
-  GRMP_RECT(X, (HdivEv<2, 3, GRMP_OP_DIV>), (H1Ev<2, 1, 1, 0, GRMP_OP_ID>))                                      \
-  GRMP_RECT(X, (HdivEv<2, 6, GRMP_OP_DIV>), (H1Ev<2, 1, 1, 0, GRMP_OP_ID>))                                      \
-  GRMP_RECT(X, (HdivEv<3, 4, GRMP_OP_DIV>), (H1Ev<3, 1, 1, 0, GRMP_OP_ID>))                                      \
-  GRMP_RECT(X, (HdivEv<3, 16, GRMP_OP_DIV>), (H1Ev<3, 1, 1, 0, GRMP_OP_ID>))
+  GRMP_RECT(X, (H1Ev<2, 2, 3, 3, GRMP_OP_DIV>), (H1Ev<2, 1, 1, 0, GRMP_OP_ID>), 1)                               \
+  GRMP_RECT(X, (H1Ev<3, 3, 4, 4, GRMP_OP_DIV>), (H1Ev<3, 1, 1, 0, GRMP_OP_ID>), 4)                               \
+  GRMP_RECT(X, (H1Ev<2, 2, 6, 0, GRMP_OP_DIV>), (H1Ev<2, 1, 3, 0, GRMP_OP_ID>), 3)                               \
+  GRMP_RECT(X, (H1Ev<3, 3, 10, 0, GRMP_OP_DIV>), (H1Ev<3, 1, 4, 0, GRMP_OP_ID>), 4)                              \
+  GRMP_RECT(X, (HdivEv<2, 3, GRMP_OP_DIV>), (H1Ev<2, 1, 1, 0, GRMP_OP_ID>), 1)                                   \
+  GRMP_RECT(X, (HdivEv<2, 6, GRMP_OP_DIV>), (H1Ev<2, 1, 1, 0, GRMP_OP_ID>), 1)                                   \
+  GRMP_RECT(X, (HdivEv<3, 4, GRMP_OP_DIV>), (H1Ev<3, 1, 1, 0, GRMP_OP_ID>), 1)                                   \
+  GRMP_RECT(X, (HdivEv<3, 16, GRMP_OP_DIV>), (H1Ev<3, 1, 1, 0, GRMP_OP_ID>), 1)
 
 template <class Ev> __host__ inline bool ev_matches(const ColEvalDesc& d) {
   return Ev::KIND == d.kind && Ev::ED == d.ed && Ev::NC == d.nc && Ev::NDS == d.nds && Ev::NBUB == d.nbub && Ev::OP == d.op;
