@@ -18,7 +18,8 @@ from .fespace import FESpace, FEVector, FEMatrix, FEMatrixBlock, FEVectorBlock
 from .assembly import (Identity, Gradient, SymmetricGradient, Divergence, ReconstructionIdentity, NoAction, HookeAction, Action,
                        DataFunction, fdot_action, AssemblyPattern, DiscreteBilinearForm, DiscreteSymmetricBilinearForm,
                        DiscreteLumpedBilinearForm, DiscreteLinearForm, prepare_assembly, assemble, assemble_csc, blf_set_path,
-                       blf_stats, quadrature_order, device_grid, device_space)
+                       blf_stats, quadrature_order, device_grid, device_space, addblock_matmul, residual, apply_penalties,
+                       device_csc, fetch_values)
 from .operators import (PDEOperator, LaplaceOperator, ReactionOperator, LagrangeMultiplier, HookStiffnessOperator2D,
                         HookStiffnessOperator3D, BilinearForm, LinearForm, create_assembly_pattern, assemble_operator)
-from . import _lib, partition
+from . import _lib, assembly, partition

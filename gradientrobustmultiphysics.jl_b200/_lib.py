@@ -23,7 +23,8 @@ EXPORTS = [
     "grmp_blf_numeric_steps", "grmp_blf_set_owned_columns", "grmp_space_create", "grmp_space_destroy", "grmp_blf_create",
     "grmp_blf_destroy", "grmp_blf_set_path", "grmp_blf_symbolic", "grmp_blf_get_pattern", "grmp_blf_numeric",
     "grmp_blf_get_values", "grmp_blf_transpose_copy", "grmp_blf_stats", "grmp_blf_device_values", "grmp_lf_create",
-    "grmp_lf_destroy", "grmp_lf_assemble", "grmp_lf_stats", "grmp_blf_assemble_host",
+    "grmp_lf_destroy", "grmp_lf_assemble", "grmp_lf_stats", "grmp_blf_assemble_host", "grmp_blf_device_csc", "grmp_blf_matmul",
+    "grmp_blf_matmul_device", "grmp_blf_residual", "grmp_blf_apply_penalties",
 ]
 
 
@@ -38,6 +39,11 @@ class EvalTab(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("last_numeric_ms", C.c_double), ("last_symbolic_ms", C.c_double), ("nnz", C.c_int64), ("ncontrib", C.c_int64),
                 ("kernel_launches", C.c_int64), ("path", C.c_int32), ("ntiles", C.c_int32)]
+
+
+class DeviceCSC(C.Structure):
+    _fields_ = [("nrows", C.c_int64), ("ncols", C.c_int64), ("nnz", C.c_int64), ("colptr", C.c_void_p), ("rowval", C.c_void_p),
+                ("nzval", C.c_void_p), ("device", C.c_int32), ("reserved", C.c_int32)]
 
 
 def build(force: bool = False) -> str:
@@ -89,6 +95,11 @@ def lib():
         L.grmp_lf_destroy.argtypes = [vp]
         L.grmp_lf_assemble.argtypes = [vp, dbl, i32, vp, vp, i64]
         L.grmp_lf_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.grmp_blf_device_csc.argtypes = [vp, C.POINTER(DeviceCSC)]
+        L.grmp_blf_matmul.argtypes = [vp, vp, vp, dbl, i32]
+        L.grmp_blf_matmul_device.argtypes = [vp, vp, vp, dbl, i32]
+        L.grmp_blf_residual.argtypes = [vp, vp, vp, vp, i64, vp, C.POINTER(dbl)]
+        L.grmp_blf_apply_penalties.argtypes = [vp, vp, i64, dbl, C.POINTER(i64)]
         _lib = L
     return _lib
 

@@ -343,6 +343,46 @@ def assemble_csc(AP: AssemblyPattern, factor=1.0, skip_preps=False, transposed_a
     return P.colptr, P.rowval, nzval
 
 
+# ---- the matrix stays on the device: products, residuals, penalties --------------------------------
+def addblock_matmul(a: np.ndarray, AP: AssemblyPattern, b: np.ndarray, factor=1, transposed=False):
+    """addblock_matmul!(a, B, b; factor, transposed) (fematrix.jl:402-473) with B = the device-resident matrix of the last
+    assemble_csc(AP, ...): a += B*b*factor (or B'*b*factor), bit-identical to the reference loop"""
+    assert a.dtype == np.float64 and b.dtype == np.float64 and a.flags.c_contiguous and b.flags.c_contiguous
+    _lib.check(_lib.lib().grmp_blf_matmul(AP.AM.h, _lib.ptr(b), _lib.ptr(a), float(factor), int(bool(transposed))))
+    return a
+
+
+def residual(AP: AssemblyPattern, x: np.ndarray, b: np.ndarray | None = None, fixed_dofs=None, want_vector=True):
+    """residual check of solve_direct! (solvers.jl:661-668): r = A*x - b, r[fixed_dofs] = 0; returns (r, sum r_i^2)"""
+    nrows = AP.FES[1].ndofs if AP.AM.transposed else AP.FES[0].ndofs
+    r = np.zeros(nrows) if want_vector else None
+    fd = None if fixed_dofs is None else np.ascontiguousarray(fixed_dofs, dtype=np.int64)
+    nrm = C.c_double(0)
+    _lib.check(_lib.lib().grmp_blf_residual(AP.AM.h, _lib.ptr(np.ascontiguousarray(x)), _lib.ptr(b), _lib.ptr(fd), 0 if fd is None else fd.size,
+                                            _lib.ptr(r), C.byref(nrm)))
+    return r, nrm.value
+
+
+def apply_penalties(AP: AssemblyPattern, fixed_dofs, penalty):
+    """apply_penalties!(A, fixed_dofs, penalty) (fematrix.jl:349-355) on the device-resident values"""
+    fd = np.ascontiguousarray(fixed_dofs, dtype=np.int64)
+    miss = C.c_int64(0)
+    _lib.check(_lib.lib().grmp_blf_apply_penalties(AP.AM.h, _lib.ptr(fd), fd.size, float(penalty), C.byref(miss)))
+
+
+def device_csc(AP: AssemblyPattern):
+    """device pointers of the assembled SparseMatrixCSC (hand-off to a GPU solver, solvers.jl:655)"""
+    d = _lib.DeviceCSC()
+    _lib.check(_lib.lib().grmp_blf_device_csc(AP.AM.h, C.byref(d)))
+    return d
+
+
+def fetch_values(AP: AssemblyPattern):
+    nz = np.zeros(AP.AM.nnz)
+    _lib.check(_lib.lib().grmp_blf_get_values(AP.AM.h, _lib.ptr(nz)))
+    return nz
+
+
 def _embed(block: FEMatrixBlock, colptr, rowval, nzval):
     """place a block CSC at (offsetX, offsetY) of the parent matrix"""
     par = block.parent

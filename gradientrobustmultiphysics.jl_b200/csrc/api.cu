@@ -5,6 +5,7 @@
 #include "colpath.cuh"
 #include "common.cuh"
 #include "fastpath.cuh"
+#include "sparseops.cuh"
 #include "symbolic.cuh"
 
 namespace grmp {
@@ -129,6 +130,14 @@ struct grmp_blf {
   std::vector<double> t1_derivs_host, t1_vals_host, t2_derivs_host, t2_vals_host;   // host copies of the caller's evaluator tables
   Pattern pat;
   ColPath colp;
+  CsrView csr;
+  i64 topo_grid = 0, topo_s1 = 0, topo_s2 = 0;     // versions of CellNodes / CellDofs the pattern was built from
+  i64 halo_first_slot = -1;                        // first nzval slot of the columns another rank owns (-1: none)
+  DevBuf<i32> cmp_nodes, cmp_dofs1, cmp_dofs2;      // scratch of grmp_blf_assemble_host's topology check
+  DevBuf<int> cmp_flag;
+  DevBuf<double> vec_in, vec_out, vec_rhs, scalar;    // vectors of the matrix-vector entry points
+  DevBuf<i64> fixed;
+  double last_matmul_ms = 0.0;
   bool have_pattern = false, have_values = false;
   DevBuf<double> lbuf, nzval;
   FastP2Tet fast;
@@ -164,11 +173,26 @@ static int fill_blf_params(grmp_blf* b, double factor, BlfLocalParams* p) {
   return GRMP_OK;
 }
 
+static int blf_check_fresh(grmp_blf* b) {
+  if (!b->have_pattern) return fail(GRMP_ESTATE, "grmp_blf_symbolic has not been called");
+  if (b->topo_grid != b->s1->grid->topo_version || b->topo_s1 != b->s1->topo_version || b->topo_s2 != b->s2->topo_version)
+    return fail(GRMP_ESTATE, "CellNodes / CellDofs changed after grmp_blf_symbolic: the pattern is stale, run the symbolic pass again");
+  return GRMP_OK;
+}
+
+__global__ void compare_i32(const i32* a, const i32* b, i64 n, int* differs) {
+  const i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (i < n && a[i] != b[i]) *differs = 1;
+}
+
 static int blf_numeric_launch(grmp_blf* b, BlfLocalParams& p, cudaStream_t s) {
   grmp_ctx* ctx = b->s1->grid->ctx;
   if (b->path == GRMP_PATH_FAST) {
     GRMP_TRY(fast_p2tet_numeric(ctx, p, b->pat, b->fast, b->s1->grid->geom_version, b->nzval.p));
     b->st.kernel_launches = 2;
+    // halo columns (owned by another rank) are walked for their mirrors only; what they staged is not a matrix column
+    if (b->halo_first_slot >= 0 && b->halo_first_slot < b->pat.nnz)
+      GRMP_CUDA(cudaMemsetAsync(b->nzval.p + b->halo_first_slot, 0, (size_t)(b->pat.nnz - b->halo_first_slot) * 8, s));
   } else if (b->path == GRMP_PATH_COLUMNS) {
     GRMP_TRY(colpath_numeric(ctx, p, b->pat, b->colp, b->nzval.p));
     b->st.kernel_launches = (i64)b->colp.classes.size();        // one launch per tile class
@@ -277,6 +301,8 @@ int grmp_grid_update_cells(grmp_grid* g, const int32_t* cellnodes) {
   cudaStream_t s = g->ctx->stream;
   GRMP_TRY(g->cellnodes.upload(cellnodes, (size_t)g->ncells * (g->dim + 1), s));
   GRMP_CUDA(cudaStreamSynchronize(s));
+  g->topo_version++;
+  g->geom_version++;
   return GRMP_OK;
 }
 
@@ -300,6 +326,7 @@ int grmp_space_update_dofs(grmp_space* sp, const int32_t* celldofs) {
   cudaStream_t s = sp->grid->ctx->stream;
   GRMP_TRY(sp->celldofs.upload(celldofs, (size_t)sp->grid->ncells * sp->nd, s));
   GRMP_CUDA(cudaStreamSynchronize(s));
+  sp->topo_version++;
   return GRMP_OK;
 }
 int grmp_space_destroy(grmp_space* s) { delete s; return GRMP_OK; }
@@ -408,6 +435,14 @@ int grmp_blf_symbolic(grmp_blf* b, double factor, int64_t* nnz_out) {
   b->st.last_symbolic_ms = ms; b->st.nnz = b->pat.nnz; b->st.ncontrib = b->pat.ncontrib; b->st.path = b->path;
   b->st.ntiles = b->path == GRMP_PATH_FAST ? b->fast.ntiles : (int)b->colp.ntiles;
   b->have_pattern = true; b->have_values = false;
+  b->csr.built = false;
+  b->topo_grid = b->s1->grid->topo_version; b->topo_s1 = b->s1->topo_version; b->topo_s2 = b->s2->topo_version;
+  b->halo_first_slot = -1;
+  if (b->path == GRMP_PATH_FAST && b->ncols_owned >= 0 && b->ncols_owned < b->pat.ncols) {
+    i64 cpv = 0;
+    GRMP_CUDA(cudaMemcpy(&cpv, b->pat.colptr.p + b->ncols_owned, 8, cudaMemcpyDeviceToHost));
+    b->halo_first_slot = cpv - 1;
+  }
   if (nnz_out) *nnz_out = b->pat.nnz;
   return GRMP_OK;
 }
@@ -424,7 +459,7 @@ int grmp_blf_get_pattern(grmp_blf* b, int64_t* colptr, int64_t* rowval) {
 
 int grmp_blf_numeric(grmp_blf* b, double factor, double* nzval_host) {
   if (!b) return fail(GRMP_EINVAL, "blf == NULL");
-  if (!b->have_pattern) return fail(GRMP_ESTATE, "grmp_blf_symbolic has not been called");
+  GRMP_TRY(blf_check_fresh(b));
   grmp_ctx* ctx = b->s1->grid->ctx;
   cudaStream_t s = ctx->stream;
   GRMP_CUDA(cudaSetDevice(ctx->device));
@@ -444,41 +479,57 @@ int grmp_blf_numeric(grmp_blf* b, double factor, double* nzval_host) {
 
 int grmp_blf_assemble_host(grmp_blf* b, double factor, const double* coords, const double* cellvolumes, const int32_t* cellnodes,
                            const int32_t* celldofs_row, const int32_t* celldofs_col, double* nzval_host) {
-  if (!b || !coords || !cellvolumes || !cellnodes || !celldofs_row) return fail(GRMP_EINVAL, "grmp_blf_assemble_host: NULL argument");
-  if (!b->have_pattern) return fail(GRMP_ESTATE, "grmp_blf_symbolic has not been called");
-  if (b->s2 != b->s1 && !celldofs_col) return fail(GRMP_EINVAL, "grmp_blf_assemble_host: CellDofs of the column space missing");
+  if (!b || !coords || !cellvolumes) return fail(GRMP_EINVAL, "grmp_blf_assemble_host: NULL argument");
+  GRMP_TRY(blf_check_fresh(b));
   grmp_grid* g = b->s1->grid;
   grmp_ctx* ctx = g->ctx;
   cudaStream_t s = ctx->stream, sc = ctx->copy_stream;
   GRMP_CUDA(cudaSetDevice(ctx->device));
-  // the coordinates are all the owner-computes kernels read: they go first on the compute stream; the other grid arrays
-  // travel on the copy stream, concurrently with the kernels and the download of nzval (PCIe is full duplex)
+  // geometry is what may change on a frozen pattern: it goes first on the compute stream.  The topology arrays, when the
+  // caller hands them over, travel on the copy stream concurrently with the kernels and the download (PCIe is full duplex)
+  // and are compared with the arrays of the symbolic pass.
   GRMP_TRY(g->coords.upload(coords, (size_t)g->nnodes * g->dim, s));
+  GRMP_TRY(g->vol.upload(cellvolumes, (size_t)g->ncells, s));
   g->geom_version++;
-  GRMP_TRY(g->vol.upload(cellvolumes, (size_t)g->ncells, sc));
-  GRMP_TRY(g->cellnodes.upload(cellnodes, (size_t)g->ncells * (g->dim + 1), sc));
-  GRMP_TRY(b->s1->celldofs.upload(celldofs_row, (size_t)g->ncells * b->s1->nd, sc));
-  if (b->s2 != b->s1) GRMP_TRY(b->s2->celldofs.upload(celldofs_col, (size_t)g->ncells * b->s2->nd, sc));
-  GRMP_CUDA(cudaEventRecord(ctx->ev_copy, sc));
-  if (b->path != GRMP_PATH_FAST) GRMP_CUDA(cudaStreamWaitEvent(s, ctx->ev_copy, 0));   // the generic kernels read all of them
+  const bool check = cellnodes || celldofs_row || celldofs_col;
+  if (check) {
+    if (b->cmp_flag.n == 0) GRMP_TRY(b->cmp_flag.alloc(1));
+    GRMP_CUDA(cudaMemsetAsync(b->cmp_flag.p, 0, sizeof(int), sc));
+    auto cmp = [&](const int32_t* host, DevBuf<i32>& scratch, const DevBuf<i32>& ref) -> int {
+      if (!host || ref.n == 0) return GRMP_OK;
+      GRMP_TRY(scratch.upload(host, ref.n, sc));
+      compare_i32<<<(unsigned)((ref.n + 255) / 256), 256, 0, sc>>>(scratch.p, ref.p, (i64)ref.n, b->cmp_flag.p);
+      GRMP_CUDA(cudaGetLastError());
+      return GRMP_OK;
+    };
+    GRMP_TRY(cmp(cellnodes, b->cmp_nodes, g->cellnodes));
+    GRMP_TRY(cmp(celldofs_row, b->cmp_dofs1, b->s1->celldofs));
+    if (b->s2 != b->s1) GRMP_TRY(cmp(celldofs_col, b->cmp_dofs2, b->s2->celldofs));
+  }
   BlfLocalParams p;
   GRMP_TRY(fill_blf_params(b, factor, &p));
   GRMP_CUDA(cudaEventRecord(ctx->ev0, s));
   GRMP_TRY(blf_numeric_launch(b, p, s));
   GRMP_CUDA(cudaEventRecord(ctx->ev1, s));
   if (nzval_host && b->pat.nnz) GRMP_CUDA(cudaMemcpyAsync(nzval_host, b->nzval.p, (size_t)b->pat.nnz * 8, cudaMemcpyDeviceToHost, s));
+  int differs = 0;
+  if (check) GRMP_CUDA(cudaMemcpyAsync(&differs, b->cmp_flag.p, sizeof(int), cudaMemcpyDeviceToHost, sc));
   GRMP_CUDA(cudaStreamSynchronize(s));
   GRMP_CUDA(cudaStreamSynchronize(sc));
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   b->st.last_numeric_ms = ms;
   b->have_values = true;
+  if (differs) {
+    b->have_values = false;
+    return fail(GRMP_ESTATE, "grmp_blf_assemble_host: CellNodes / CellDofs differ from the arrays of the symbolic pass (stale pattern)");
+  }
   return GRMP_OK;
 }
 
 int grmp_blf_numeric_steps(grmp_blf* b, double factor, int nsteps, double* total_ms) {
   if (!b || nsteps < 0) return fail(GRMP_EINVAL, "grmp_blf_numeric_steps: bad argument");
-  if (!b->have_pattern) return fail(GRMP_ESTATE, "grmp_blf_symbolic has not been called");
+  GRMP_TRY(blf_check_fresh(b));
   grmp_ctx* ctx = b->s1->grid->ctx;
   cudaStream_t s = ctx->stream;
   GRMP_CUDA(cudaSetDevice(ctx->device));
@@ -530,14 +581,18 @@ int grmp_blf_get_values(grmp_blf* b, double* nzval_host) {
 
 int grmp_blf_transpose_copy(grmp_blf* b, double factor, double factor_transpose, int64_t* colptr_t, int64_t* rowval_t, double* nzval_t) {
   if (!b || !colptr_t) return fail(GRMP_EINVAL, "grmp_blf_transpose_copy: NULL argument");
-  if (!b->have_values || b->path != GRMP_PATH_GENERIC || b->lbuf.n == 0)
-    return fail(GRMP_ESTATE, "transpose copy needs a prior generic-path grmp_blf_numeric with the same factor");
+  if (!b->have_values) return fail(GRMP_ESTATE, "transpose copy needs a prior grmp_blf_numeric with the same factor");
   if (b->apt == GRMP_APT_SYMMETRIC) return fail(GRMP_EUNSUPPORTED, "transpose_copy is only assembled by the general branch (bilinearform.jl:347-367)");
   cudaStream_t s = b->s1->grid->ctx->stream;
   DevBuf<i64> cpt, rvt; DevBuf<i32> perm; DevBuf<double> tv, tvp;
   GRMP_TRY(build_transposed(s, b->pat, cpt, rvt, perm));
   GRMP_TRY(tv.alloc(b->pat.nnz)); GRMP_TRY(tvp.alloc(b->pat.nnz));
-  GRMP_TRY(launch_gather_transposed(s, b->pat, b->lbuf.p, factor, factor_transpose, tv.p));
+  if (b->path == GRMP_PATH_GENERIC && b->lbuf.n != 0) {
+    GRMP_TRY(launch_gather_transposed(s, b->pat, b->lbuf.p, factor, factor_transpose, tv.p));     // term by term, bit-exact
+  } else {
+    // the fast kernels keep no per-cell values: scale the assembled entries (equal to the term-by-term sum up to rounding)
+    GRMP_TRY(launch_scale(s, b->nzval.p, b->pat.nnz, -(factor_transpose / factor), tv.p));
+  }
   GRMP_TRY(launch_permute(s, tv.p, perm.p, b->pat.nnz, tvp.p));
   GRMP_CUDA(cudaMemcpyAsync(colptr_t, cpt.p, (size_t)(b->pat.nrows + 1) * 8, cudaMemcpyDeviceToHost, s));
   if (b->pat.nnz) {
@@ -557,6 +612,88 @@ int grmp_blf_stats(grmp_blf* b, grmp_stats* out) {
 int grmp_blf_device_values(grmp_blf* b, void** dptr) {
   if (!b || !dptr) return fail(GRMP_EINVAL, "NULL argument");
   *dptr = b->nzval.p;
+  return GRMP_OK;
+}
+
+int grmp_blf_device_csc(grmp_blf* b, grmp_device_csc* out) {
+  if (!b || !out) return fail(GRMP_EINVAL, "NULL argument");
+  if (!b->have_values) return fail(GRMP_ESTATE, "grmp_blf_numeric has not been called");
+  out->nrows = b->pat.nrows; out->ncols = b->pat.ncols; out->nnz = b->pat.nnz;
+  out->colptr = b->pat.colptr.p; out->rowval = b->pat.rowval.p; out->nzval = b->nzval.p;
+  out->device = b->s1->grid->ctx->device; out->reserved = 0;
+  return GRMP_OK;
+}
+
+int grmp_blf_matmul_device(grmp_blf* b, const double* b_dev, double* a_dev, double factor, int transposed) {
+  if (!b || !b_dev || !a_dev) return fail(GRMP_EINVAL, "grmp_blf_matmul_device: NULL argument");
+  if (!b->have_values) return fail(GRMP_ESTATE, "grmp_blf_numeric has not been called");
+  grmp_ctx* ctx = b->s1->grid->ctx;
+  GRMP_CUDA(cudaSetDevice(ctx->device));
+  if (!transposed && !b->csr.built) GRMP_TRY(build_csr_view(ctx->stream, b->pat, &b->csr));
+  GRMP_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  GRMP_TRY(launch_matmul(ctx->stream, b->pat, b->csr, b->nzval.p, b_dev, a_dev, factor, transposed));
+  GRMP_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  GRMP_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  b->last_matmul_ms = ms;
+  return GRMP_OK;
+}
+
+int grmp_blf_matmul(grmp_blf* b, const double* b_host, double* a_host, double factor, int transposed) {
+  if (!b || !b_host || !a_host) return fail(GRMP_EINVAL, "grmp_blf_matmul: NULL argument");
+  if (!b->have_values) return fail(GRMP_ESTATE, "grmp_blf_numeric has not been called");
+  cudaStream_t s = b->s1->grid->ctx->stream;
+  const i64 nin = transposed ? b->pat.nrows : b->pat.ncols, nout = transposed ? b->pat.ncols : b->pat.nrows;
+  GRMP_TRY(b->vec_in.upload(b_host, (size_t)nin, s));
+  GRMP_TRY(b->vec_out.upload(a_host, (size_t)nout, s));
+  GRMP_TRY(grmp_blf_matmul_device(b, b->vec_in.p, b->vec_out.p, factor, transposed));
+  if (nout) GRMP_CUDA(cudaMemcpyAsync(a_host, b->vec_out.p, (size_t)nout * 8, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  return GRMP_OK;
+}
+
+int grmp_blf_residual(grmp_blf* b, const double* x_host, const double* b_host, const int64_t* fixed_dofs, int64_t nfixed, double* r_host,
+                      double* norm2) {
+  if (!b || !x_host || nfixed < 0 || (nfixed > 0 && !fixed_dofs)) return fail(GRMP_EINVAL, "grmp_blf_residual: bad argument");
+  if (!b->have_values) return fail(GRMP_ESTATE, "grmp_blf_numeric has not been called");
+  grmp_ctx* ctx = b->s1->grid->ctx;
+  cudaStream_t s = ctx->stream;
+  GRMP_CUDA(cudaSetDevice(ctx->device));
+  const i64 n = b->pat.nrows;
+  GRMP_TRY(b->vec_in.upload(x_host, (size_t)b->pat.ncols, s));
+  if (b->vec_out.n != (size_t)n) GRMP_TRY(b->vec_out.alloc(n));
+  if (n) GRMP_CUDA(cudaMemsetAsync(b->vec_out.p, 0, (size_t)n * 8, s));
+  if (!b->csr.built) GRMP_TRY(build_csr_view(s, b->pat, &b->csr));
+  GRMP_TRY(launch_matmul(s, b->pat, b->csr, b->nzval.p, b->vec_in.p, b->vec_out.p, 1.0, 0));
+  if (b_host) GRMP_TRY(b->vec_rhs.upload(b_host, (size_t)n, s));
+  if (nfixed > 0) GRMP_TRY(b->fixed.upload(fixed_dofs, (size_t)nfixed, s));
+  if (b->scalar.n == 0) GRMP_TRY(b->scalar.alloc(2));
+  GRMP_TRY(launch_residual_finish(s, b->vec_out.p, b_host ? b->vec_rhs.p : nullptr, n, nfixed > 0 ? b->fixed.p : nullptr, nfixed,
+                                  norm2 ? b->scalar.p : nullptr));
+  if (norm2) GRMP_CUDA(cudaMemcpyAsync(norm2, b->scalar.p, 8, cudaMemcpyDeviceToHost, s));
+  if (r_host && n) GRMP_CUDA(cudaMemcpyAsync(r_host, b->vec_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  return GRMP_OK;
+}
+
+int grmp_blf_apply_penalties(grmp_blf* b, const int64_t* fixed_dofs, int64_t nfixed, double penalty, int64_t* nmissing) {
+  if (!b || nfixed < 0 || (nfixed > 0 && !fixed_dofs)) return fail(GRMP_EINVAL, "grmp_blf_apply_penalties: bad argument");
+  if (!b->have_values) return fail(GRMP_ESTATE, "grmp_blf_numeric has not been called");
+  grmp_ctx* ctx = b->s1->grid->ctx;
+  cudaStream_t s = ctx->stream;
+  GRMP_CUDA(cudaSetDevice(ctx->device));
+  if (nmissing) *nmissing = 0;
+  if (nfixed == 0) return GRMP_OK;
+  GRMP_TRY(b->fixed.upload(fixed_dofs, (size_t)nfixed, s));
+  DevBuf<i64> missing;
+  GRMP_TRY(missing.alloc(1));
+  GRMP_TRY(launch_penalties(s, b->pat, b->nzval.p, b->fixed.p, nfixed, penalty, missing.p));
+  i64 m = 0;
+  GRMP_CUDA(cudaMemcpyAsync(&m, missing.p, 8, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  if (nmissing) *nmissing = m;
+  if (m > 0) return fail(GRMP_EUNSUPPORTED, "apply_penalties: a fixed dof has no stored diagonal entry (the frozen pattern cannot grow)");
   return GRMP_OK;
 }
 

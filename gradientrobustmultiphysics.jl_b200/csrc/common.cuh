@@ -116,6 +116,7 @@ struct grmp_grid {
   grmp::DevBuf<grmp::i32> cellnodes, regions, cellfaces, signs, orient;
   bool has_regions = false, has_faces = false;
   grmp::i64 geom_version = 0;     // bumped by grmp_grid_update_geometry (the fast path keeps tile-blocked coordinate copies)
+  grmp::i64 topo_version = 0;     // bumped by grmp_grid_update_cells: patterns built before are stale
   grmp::GridView view() const;
 };
 
@@ -124,6 +125,7 @@ struct grmp_space {
   int fetype, ncomp, nd;
   grmp::i64 ndofs;
   grmp::DevBuf<grmp::i32> celldofs;
+  grmp::i64 topo_version = 0;     // bumped by grmp_space_update_dofs
 };
 
 namespace grmp {

@@ -253,6 +253,17 @@ int build_transposed(cudaStream_t s, const Pattern& pat, DevBuf<i64>& colptr_t, 
   return GRMP_OK;
 }
 
+__global__ void scale_kernel(const double* src, i64 n, double alpha, double* dst) {
+  i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (k < n) dst[k] = src[k] * alpha;
+}
+int launch_scale(cudaStream_t s, const double* src, i64 n, double alpha, double* dst) {
+  if (n == 0) return GRMP_OK;
+  scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, n, alpha, dst);
+  GRMP_CUDA(cudaGetLastError());
+  return GRMP_OK;
+}
+
 int launch_permute(cudaStream_t s, const double* src, const i32* perm, i64 n, double* dst) {
   if (n == 0) return GRMP_OK;
   permute_kernel<<<nblk(n), 256, 0, s>>>(src, perm, n, dst);

@@ -30,6 +30,7 @@ int launch_gather_transposed(cudaStream_t s, const Pattern& pat, const double* l
 // CSC of the transposed pattern: colptr_t [nrows+1], rowval_t [nnz] (1-based) and perm[pos] = source slot
 int build_transposed(cudaStream_t s, const Pattern& pat, DevBuf<i64>& colptr_t, DevBuf<i64>& rowval_t, DevBuf<i32>& perm);
 int launch_permute(cudaStream_t s, const double* src, const i32* perm, i64 n, double* dst);
+int launch_scale(cudaStream_t s, const double* src, i64 n, double alpha, double* dst);
 
 // LinearForm: dof -> (cell, local dof) lists in cell order
 struct DofGather {

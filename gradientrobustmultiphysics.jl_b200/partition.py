@@ -5,7 +5,9 @@ bilinearform.jl:226); the path shards naturally because cells are independent un
 work coupled only through shared dofs.  Scheme (owner-computes, variant B):
 
   * the cells are split into `world` contiguous ranges -- `uniform_refine` numbers the
-    children of a coarse cell contiguously, so ranges are spatially compact;
+    children of a coarse cell contiguously, so ranges are spatially compact.  The ranges are
+    balanced by owner-computes WORK, not by cell count: a dof costs its owner one visit of
+    every cell that contains it, and the lower ranks own the dofs on the range interfaces;
   * a dof (matrix column/row) is owned by the rank that holds its lowest-numbered cell;
   * a rank assembles its cells plus the halo cells touching an owned dof, with the owned
     dofs numbered first (`grmp_blf_set_owned_columns`), so every owned column is complete
@@ -32,20 +34,44 @@ def cell_ranges(ncells: int, world: int):
     return [(ncells * r) // world for r in range(world + 1)]
 
 
-def dof_owner(space: FESpace, world: int):
+def _first_cells(space: FESpace):
     nc = space.xgrid.ncells
     dofs = space.celldofs.astype(np.int64) - 1
     first_cell = np.full(space.ndofs, nc, dtype=np.int64)
     np.minimum.at(first_cell, dofs.ravel(), np.repeat(np.arange(nc, dtype=np.int64), dofs.shape[1]))
-    bounds = np.array(cell_ranges(nc, world)[1:])
-    return np.searchsorted(bounds, first_cell, side="right")
+    return first_cell
 
 
-def partition(space: FESpace, rank: int, world: int) -> LocalProblem:
+def balanced_cell_ranges(space: FESpace, world: int):
+    """cell range boundaries such that every rank owns about the same number of (dof, cell) visits: a dof belongs to its
+    lowest-numbered cell and costs one visit per cell that contains it"""
+    nc = space.xgrid.ncells
+    if world <= 1 or nc == 0:
+        return cell_ranges(nc, world)
+    dofs = space.celldofs.astype(np.int64) - 1
+    visits = np.bincount(dofs.ravel(), minlength=space.ndofs)            # cells per dof
+    w = np.bincount(_first_cells(space), weights=visits, minlength=nc + 1)[:nc]
+    cum = np.cumsum(w)
+    bounds = [0]
+    for r in range(1, world):
+        bounds.append(int(np.searchsorted(cum, cum[-1] * r / world, side="left")) + 1)
+    bounds.append(nc)
+    for r in range(1, world + 1):                                          # keep the ranges non-empty and ordered
+        bounds[r] = min(max(bounds[r], bounds[r - 1]), nc)
+    return bounds
+
+
+def dof_owner(space: FESpace, world: int, bounds=None):
+    bounds = np.array((bounds if bounds is not None else balanced_cell_ranges(space, world))[1:])
+    return np.searchsorted(bounds, _first_cells(space), side="right")
+
+
+def partition(space: FESpace, rank: int, world: int, balance: str = "work") -> LocalProblem:
     """rank-local grid/space: own + halo cells, owned dofs first (local numbering, 1-based CellDofs)"""
     g = space.xgrid
     dofs = space.celldofs.astype(np.int64) - 1
-    owned = dof_owner(space, world) == rank
+    bounds = balanced_cell_ranges(space, world) if balance == "work" else cell_ranges(g.ncells, world)
+    owned = dof_owner(space, world, bounds) == rank
     cells = np.nonzero(owned[dofs].any(axis=1))[0]
     ldofs = dofs[cells]
     used = np.zeros(space.ndofs, bool)

@@ -110,7 +110,8 @@ int grmp_grid_set_faces(grmp_grid* grid, int64_t nfaces, const int32_t* cellface
                         const int32_t* cellfaceorient, const double* facenormals, const double* facevolumes);
 /* re-upload coordinates / volumes of an existing grid (moving meshes, the e2e bench step) */
 int grmp_grid_update_geometry(grmp_grid* grid, const double* coords, const double* cellvolumes);
-/* re-upload CellNodes of an existing grid (same sizes; used by the end-to-end benchmark step) */
+/* re-upload CellNodes of an existing grid (same sizes).  Invalidates the pattern of every form on the grid: numeric calls
+ * return GRMP_ESTATE until grmp_blf_symbolic has run again. */
 int grmp_grid_update_cells(grmp_grid* grid, const int32_t* cellnodes);
 int grmp_grid_destroy(grmp_grid* grid);
 
@@ -118,7 +119,7 @@ int grmp_grid_destroy(grmp_grid* grid);
  * produced by the host (Julia: FES[CellDofs].colentries) */
 int grmp_space_create(grmp_grid* grid, int fetype, int ncomp, int64_t ndofs, int nd_cell, const int32_t* celldofs,
                       grmp_space** out);
-/* re-upload CellDofs of an existing space (same sizes) */
+/* re-upload CellDofs of an existing space (same sizes); invalidates the pattern of every form on the space like grmp_grid_update_cells */
 int grmp_space_update_dofs(grmp_space* space, const int32_t* celldofs);
 int grmp_space_destroy(grmp_space* space);
 
@@ -150,12 +151,15 @@ int grmp_blf_get_pattern(grmp_blf* blf, int64_t* colptr, int64_t* rowval);
 int grmp_blf_numeric(grmp_blf* blf, double factor, double* nzval_host);
 int grmp_blf_get_values(grmp_blf* blf, double* nzval_host);
 /* assemble!(A, AP; factor, skip_preps = true) with the grid still in HOST memory, one synchronous call (the end-to-end form
- * of bilinearform.jl:92-380 behind a Julia ccall): uploads Coordinates, CellVolumes, CellNodes (grid of the row space) and
- * CellDofs (celldofs_col may be NULL when both arguments live in the same space), assembles on the frozen pattern and
- * downloads nzval.  Uploads the kernels do not read overlap the assembly and the download. */
+ * of bilinearform.jl:92-380 behind a Julia ccall): uploads Coordinates and CellVolumes, assembles on the frozen pattern and
+ * downloads nzval. */
 int grmp_blf_assemble_host(grmp_blf* blf, double factor, const double* coords, const double* cellvolumes,
                            const int32_t* cellnodes, const int32_t* celldofs_row, const int32_t* celldofs_col,
                            double* nzval_host);
+/* Geometry (Coordinates, CellVolumes) is what may change on a frozen pattern.  cellnodes / celldofs_* may be NULL (trust the
+ * frozen pattern, like skip_preps = true does); when given they are uploaded on the copy stream and COMPARED with the arrays of
+ * the symbolic pass -- a difference returns GRMP_ESTATE (the pattern, the gather lists and the records are stale: call
+ * grmp_grid_update_cells / grmp_space_update_dofs and grmp_blf_symbolic again).  nzval_host may be NULL (values stay resident). */
 /* nsteps back-to-back numeric assemblies bracketed by ONE pair of CUDA events on the launching
  * stream (benchmarking / time loops that reassemble every step); total_ms receives the device time */
 int grmp_blf_numeric_steps(grmp_blf* blf, double factor, int nsteps, double* total_ms);
@@ -171,6 +175,34 @@ int grmp_blf_transpose_copy(grmp_blf* blf, double factor, double factor_transpos
 int grmp_blf_stats(grmp_blf* blf, grmp_stats* out);
 /* raw device pointer of nzval (for device-side consumers / benchmarks; owned by the library) */
 int grmp_blf_device_values(grmp_blf* blf, void** dptr);
+
+/* ---- what the reference does with the matrix right after assembly, without bringing it back to the host ------------------
+ * Device-resident SparseMatrixCSC{Float64,Int64} of the last numeric call: the hand-off to a GPU solver in place of
+ * `_LinearProblem(A.entries.cscmatrix, b.entries, SC)` (src/solvers.jl:655).  Pointers are device pointers owned by the
+ * library, valid until the next symbolic call / destroy; colptr and rowval are 1-based Int64 like Julia's. */
+typedef struct grmp_device_csc {
+  int64_t nrows, ncols, nnz;
+  const int64_t* colptr;   /* [ncols+1] */
+  const int64_t* rowval;   /* [nnz] */
+  const double* nzval;     /* [nnz] */
+  int32_t device;
+  int32_t reserved;
+} grmp_device_csc;
+int grmp_blf_device_csc(grmp_blf* blf, grmp_device_csc* out);
+/* addblock_matmul!(a, B, b; factor, transposed) (src/fematrix.jl:402-473): a += B*b*factor, or a += B'*b*factor.  Host vectors
+ * (a: nrows / ncols entries, updated in place).  Every a[i] receives its terms one at a time in the reference's order (columns
+ * ascending, separate multiply and add), so the result is bit-identical to the reference's loop. */
+int grmp_blf_matmul(grmp_blf* blf, const double* b_host, double* a_host, double factor, int transposed);
+/* the same with device vectors (no copies; for device-resident solvers / time loops) */
+int grmp_blf_matmul_device(grmp_blf* blf, const double* b_dev, double* a_dev, double factor, int transposed);
+/* residual check of solve_direct! (src/solvers.jl:661-668): r = A*x - b, r[fixed_dofs] = 0; returns sum r_i^2 in *norm2.
+ * fixed_dofs are 1-based and may be NULL; b_host may be NULL (r = A*x); r_host may be NULL (only the norm is wanted). */
+int grmp_blf_residual(grmp_blf* blf, const double* x_host, const double* b_host, const int64_t* fixed_dofs, int64_t nfixed,
+                      double* r_host, double* norm2);
+/* apply_penalties!(A, fixed_dofs, penalty) (src/fematrix.jl:349-355): A[dof,dof] = penalty on the device-resident values.
+ * The reference would INSERT a missing diagonal entry; a frozen pattern cannot grow, so the call fails with GRMP_EUNSUPPORTED
+ * (and changes nothing else) if a fixed dof has no stored diagonal -- *nmissing (may be NULL) tells how many. */
+int grmp_blf_apply_penalties(grmp_blf* blf, const int64_t* fixed_dofs, int64_t nfixed, double penalty, int64_t* nmissing);
 
 /* AssemblyPattern{APT_LinearForm} (linearform.jl:29-33) with a single test-function argument */
 int grmp_lf_create(grmp_space* space, int op, const int32_t* regions, int nregions, int nq, const double* qweights,
