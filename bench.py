@@ -129,8 +129,9 @@ def local_problem(G, args, rank, world, dist):
     if rank == 0:
         _, g, s, _ = build_problem(args.level)
         glob = {"ncells": int(g.ncells), "ndofs": int(s.ndofs)}
+        bounds = G.partition.halo_balanced_cell_ranges(s, world)
         for r in range(world - 1, -1, -1):
-            lp = G.partition.partition(s, r, world)
+            lp = G.partition.partition(s, r, world, bounds=bounds)
             np.savez(_shm_path(r), coords=lp.grid.coords, cellnodes=lp.grid.cellnodes, vol=lp.grid.cellvolumes, celldofs=lp.space.celldofs,
                      n_owned=lp.n_owned, ndofs=lp.space.ndofs, l2g=lp.local2global, gcells=glob["ncells"], gdofs=glob["ndofs"])
         del g, s, lp
@@ -350,7 +351,7 @@ def run_gpu(args):
         "config": {"workload": "Example301 Poisson 3D: H1P2 Laplace stiffness on uniform_refine(grid_unitcube(Tetrahedron3D),%d)" % args.level,
                    "level": args.level, "ncells": glob["ncells"], "ndofs": glob["ndofs"], "nnz": int(nnz_total),
                    "cells_assembled_all_ranks": int(cells_total),
-                   "partition": "contiguous cell ranges balanced by owner-computes work, owned columns per rank, no numeric-phase exchange" if world > 1 else "none",
+                   "partition": "contiguous cell ranges balanced by walked cells (own + halo), owned columns per rank, no numeric-phase exchange" if world > 1 else "none",
                    "l2": "inputs+outputs (%.2f GB) >> 126 MB L2, no explicit flush" % ((b_alg + 16 * 10 * lg.ncells) / 1e9),
                    "path": G._lib.PATH_NAMES[int(st.path)], "tiles": int(st.ntiles)},
         "e2e": {"value": nnz_total / e2e_s, "unit": "nnz/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -6,8 +6,8 @@ work coupled only through shared dofs.  Scheme (owner-computes, v
 
   * the cells are split into `world` contiguous ranges -- `uniform_refine` numbers the
     children of a coarse cell contiguously, so ranges are spatially compact.  The ranges are
-    balanced by owner-computes WORK, not by cell count: a dof costs its owner one visit of
-    every cell that contains it, and the lower ranks own the dofs on the range interfaces;
+    balanced by the cells a rank WALKS (own + halo), which is what its time is proportional to;
+    the lower ranks own the dofs on the range interfaces and carry the larger halos;
   * a dof (matrix column/row) is owned by the rank that holds its lowest-numbered cell;
   * a rank assembles its cells plus the halo cells touching an owned dof, with the owned
     dofs numbered first (`grmp_blf_set_owned_columns`), so every owned column is complete
@@ -61,16 +61,51 @@ def balanced_cell_ranges(space: FESpace, world: int):
     return bounds
 
 
+def halo_balanced_cell_ranges(space: FESpace, world: int, iterations: int = 3):
+    """cell range boundaries such that every rank ASSEMBLES about the same number of cells, halo included.  Measured on the
+    metric kernel (tools/emulate_ranks.py): a rank's time is proportional to the cells it walks -- halo cells cost as much as
+    own cells, and the low ranks (which own the interface dofs) carry the larger halos."""
+    nc = space.xgrid.ncells
+    bounds = cell_ranges(nc, world)
+    if world <= 1 or nc < world:
+        return bounds
+    dofs = space.celldofs.astype(np.int64) - 1
+    first = _first_cells(space)
+    for _ in range(iterations):
+        owner = np.searchsorted(np.array(bounds[1:]), first, side="right")
+        cell_owner_min = owner[dofs].min(axis=1)          # a cell is walked by every rank that owns one of its dofs
+        cell_owner_max = owner[dofs].max(axis=1)
+        own = np.diff(bounds).astype(np.float64)
+        walked = np.zeros(world)
+        for r in range(world):
+            walked[r] = np.count_nonzero((cell_owner_min <= r) & (cell_owner_max >= r) & (owner[dofs] == r).any(axis=1))
+        halo = walked - own
+        target = (nc + halo.sum()) / world
+        sizes = np.maximum(target - halo, 1.0)
+        sizes *= nc / sizes.sum()
+        nb = np.concatenate([[0], np.round(np.cumsum(sizes)).astype(np.int64)])
+        nb[-1] = nc
+        bounds = [int(min(max(b, 0), nc)) for b in nb]
+        for r in range(1, world + 1):
+            bounds[r] = max(bounds[r], bounds[r - 1])
+    return bounds
+
+
+_BALANCERS = {"work": balanced_cell_ranges, "halo": halo_balanced_cell_ranges, "cells": lambda space, world: cell_ranges(space.xgrid.ncells, world)}
+DEFAULT_BALANCE = "halo"
+
+
 def dof_owner(space: FESpace, world: int, bounds=None):
-    bounds = np.array((bounds if bounds is not None else balanced_cell_ranges(space, world))[1:])
+    bounds = np.array((bounds if bounds is not None else _BALANCERS[DEFAULT_BALANCE](space, world))[1:])
     return np.searchsorted(bounds, _first_cells(space), side="right")
 
 
-def partition(space: FESpace, rank: int, world: int, balance: str = "work") -> LocalProblem:
+def partition(space: FESpace, rank: int, world: int, balance: str | None = None, bounds=None) -> LocalProblem:
     """rank-local grid/space: own + halo cells, owned dofs first (local numbering, 1-based CellDofs)"""
     g = space.xgrid
     dofs = space.celldofs.astype(np.int64) - 1
-    bounds = balanced_cell_ranges(space, world) if balance == "work" else cell_ranges(g.ncells, world)
+    if bounds is None:
+        bounds = _BALANCERS[balance or DEFAULT_BALANCE](space, world)
     owned = dof_owner(space, world, bounds) == rank
     cells = np.nonzero(owned[dofs].any(axis=1))[0]
     ldofs = dofs[cells]
