@@ -24,7 +24,7 @@ EXPORTS = [
     "grmp_blf_destroy", "grmp_blf_set_path", "grmp_blf_symbolic", "grmp_blf_get_pattern", "grmp_blf_numeric",
     "grmp_blf_get_values", "grmp_blf_transpose_copy", "grmp_blf_stats", "grmp_blf_device_values", "grmp_lf_create",
     "grmp_lf_destroy", "grmp_lf_assemble", "grmp_lf_stats", "grmp_blf_assemble_host", "grmp_blf_device_csc", "grmp_blf_matmul",
-    "grmp_blf_matmul_device", "grmp_blf_residual", "grmp_blf_apply_penalties",
+    "grmp_blf_matmul_device", "grmp_blf_residual", "grmp_blf_apply_penalties", "grmp_lf_set_path",
 ]
 
 
@@ -93,6 +93,7 @@ def lib():
         L.grmp_blf_device_values.argtypes = [vp, C.POINTER(vp)]
         L.grmp_lf_create.argtypes = [vp, i32, vp, i32, i32, vp, C.POINTER(EvalTab), C.POINTER(vp)]
         L.grmp_lf_destroy.argtypes = [vp]
+        L.grmp_lf_set_path.argtypes = [vp, i32]
         L.grmp_lf_assemble.argtypes = [vp, dbl, i32, vp, vp, i64]
         L.grmp_lf_stats.argtypes = [vp, C.POINTER(Stats)]
         L.grmp_blf_device_csc.argtypes = [vp, C.POINTER(DeviceCSC)]

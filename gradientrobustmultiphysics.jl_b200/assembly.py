@@ -288,6 +288,8 @@ def prepare_assembly(AP: AssemblyPattern, transposed_assembly=False):
         _lib.check(L.grmp_lf_create(sp, AP.operators[0].code, _lib.ptr(regions), regions.size, len(P.qf), _lib.ptr(w), C.byref(tab),
                                     C.byref(h)))
         P.kind = "lf"
+        if DEFAULT_PATH != _lib.PATH_AUTO:
+            _lib.check(L.grmp_lf_set_path(h, _lib.PATH_GENERIC if DEFAULT_PATH == _lib.PATH_GENERIC else _lib.PATH_COLUMNS))
     else:
         s1, s2 = device_space(AP.FES[0]), device_space(AP.FES[1])
         t1, k1 = _tables(AP.FES[0], AP.operators[0], P.qf)

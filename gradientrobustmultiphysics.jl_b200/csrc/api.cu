@@ -150,7 +150,11 @@ struct grmp_blf {
 
 struct grmp_lf {
   grmp_space* sp;
-  int op, nq;
+  int op, nq, path_req = GRMP_PATH_AUTO, path = GRMP_PATH_GENERIC;
+  bool fast_tried = false;
+  LfPath lfp;
+  std::vector<double> w_host, vals_host, derivs_host;
+  i64 topo_grid = 0, topo_sp = 0;
   RegionFilter reg;
   DevBuf<double> w, lbuf, b, fdata;
   DevBuf<unsigned char> active;
@@ -706,6 +710,10 @@ int grmp_lf_create(grmp_space* sp, int op, const int32_t* regions, int nregions,
   int rc = make_regions(regions, nregions, &l->reg);
   if (!rc) rc = l->w.upload(qweights, nq, s);
   if (!rc) rc = upload_tables(tab, nq, sp->grid->dim, s, &l->tab);
+  l->w_host.assign(qweights, qweights + nq);
+  if (!rc && tab->refvals) l->vals_host.assign(tab->refvals, tab->refvals + (size_t)nq * tab->nd_all * tab->ncomp);
+  if (!rc && tab->refderivs) l->derivs_host.assign(tab->refderivs, tab->refderivs + (size_t)nq * sp->grid->dim * tab->nd_all * tab->ncomp);
+  l->topo_grid = sp->grid->topo_version; l->topo_sp = sp->topo_version;
   EvalView e;
   if (!rc) rc = make_evalview(sp, op, l->tab, &e);
   if (!rc) rc = build_dofgather(s, sp->celldofs.p, sp->grid->ncells, sp->nd, sp->ndofs, &l->dg);
@@ -719,6 +727,14 @@ int grmp_lf_create(grmp_space* sp, int op, const int32_t* regions, int nregions,
 }
 int grmp_lf_destroy(grmp_lf* l) { delete l; return GRMP_OK; }
 
+int grmp_lf_set_path(grmp_lf* l, int path) {
+  if (!l || (path != GRMP_PATH_AUTO && path != GRMP_PATH_GENERIC && path != GRMP_PATH_FAST && path != GRMP_PATH_COLUMNS))
+    return fail(GRMP_EINVAL, "grmp_lf_set_path: bad argument");
+  l->path_req = path;
+  l->fast_tried = false;
+  return GRMP_OK;
+}
+
 int grmp_lf_assemble(grmp_lf* l, double factor, int fsrc, const double* fdata, double* b_host, int64_t offset) {
   if (!l || !b_host) return fail(GRMP_EINVAL, "grmp_lf_assemble: NULL argument");
   if (fsrc != GRMP_F_NONE && !fdata) return fail(GRMP_EINVAL, "fdata missing");
@@ -726,23 +742,41 @@ int grmp_lf_assemble(grmp_lf* l, double factor, int fsrc, const double* fdata, d
   grmp_ctx* ctx = sp->grid->ctx;
   cudaStream_t s = ctx->stream;
   GRMP_CUDA(cudaSetDevice(ctx->device));
+  if (l->topo_grid != sp->grid->topo_version || l->topo_sp != sp->topo_version)
+    return fail(GRMP_ESTATE, "CellNodes / CellDofs changed after grmp_lf_create: the gather lists are stale, create the linear form again");
   LfLocalParams p{};
   p.g = sp->grid->view();
   GRMP_TRY(make_evalview(sp, l->op, l->tab, &p.e));
   p.reg = l->reg; p.nq = l->nq; p.w = l->w.p; p.factor = factor; p.fsrc = fsrc;
+  if (!l->fast_tried) {      // owner-computes gather kernels where one exists for the evaluator (AUTO), else the bit-exact two-phase path
+    l->fast_tried = true;
+    l->path = GRMP_PATH_GENERIC;
+    if (l->path_req != GRMP_PATH_GENERIC) {
+      int rc = GRMP_EUNSUPPORTED;
+      if (lfpath_applicable(p.e, sp->grid->dim, l->nq, &l->lfp))
+        rc = lfpath_build(ctx, p.g, p.e, l->reg, l->w_host, l->vals_host, l->derivs_host, sp->ndofs, &l->lfp);
+      else set_error("no linear form kernel for this evaluator");
+      if (rc == GRMP_OK) l->path = GRMP_PATH_COLUMNS;
+      else if (rc != GRMP_EUNSUPPORTED || l->path_req != GRMP_PATH_AUTO) { l->fast_tried = false; return rc; }
+    }
+  }
   if (fsrc == GRMP_F_CONST) GRMP_TRY(l->fdata.upload(fdata, (size_t)p.e.rd, s));
   else if (fsrc == GRMP_F_QP_TABLE) GRMP_TRY(l->fdata.upload(fdata, (size_t)sp->grid->ncells * l->nq * p.e.rd, s));
   p.fdata = l->fdata.p; p.lbuf = l->lbuf.p; p.active = l->active.p;
   GRMP_CUDA(cudaMemcpyAsync(l->b.p, b_host + offset, (size_t)sp->ndofs * 8, cudaMemcpyHostToDevice, s));
   GRMP_CUDA(cudaEventRecord(ctx->ev0, s));
-  GRMP_TRY(launch_lf_local(p, s));
-  GRMP_TRY(launch_lf_gather(s, l->dg, l->lbuf.p, l->active.p, l->b.p));
+  if (l->path == GRMP_PATH_COLUMNS) {
+    GRMP_TRY(lfpath_numeric(ctx, p.g, l->lfp, factor, fsrc, l->fdata.p, l->b.p));
+  } else {
+    GRMP_TRY(launch_lf_local(p, s));
+    GRMP_TRY(launch_lf_gather(s, l->dg, l->lbuf.p, l->active.p, l->b.p));
+  }
   GRMP_CUDA(cudaEventRecord(ctx->ev1, s));
   GRMP_CUDA(cudaMemcpyAsync(b_host + offset, l->b.p, (size_t)sp->ndofs * 8, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaStreamSynchronize(s));
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-  l->st.last_numeric_ms = ms; l->st.kernel_launches = 2; l->st.path = GRMP_PATH_GENERIC;
+  l->st.last_numeric_ms = ms; l->st.kernel_launches = l->path == GRMP_PATH_COLUMNS ? (i64)l->lfp.classes.size() : 2; l->st.path = l->path;
   return GRMP_OK;
 }
 

@@ -203,7 +203,7 @@ __device__ __forceinline__ int bdm3_local_of_ref(const i32* o, int r) {   // -1:
 __global__ void order_keys(const i64* colptr, const i64* pairbeg, const u32* gcell, i64 ncols_used, u64* keys, u32* ids, int* err) {
   const i64 j = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (j >= ncols_used) return;
-  const i64 l = colptr[j + 1] - colptr[j], n = pairbeg[j + 1] - pairbeg[j];
+  const i64 l = colptr ? colptr[j + 1] - colptr[j] : 0, n = pairbeg[j + 1] - pairbeg[j];
   if (l > 254 || n > 65535) atomicExch(err, 1);
   const u64 first = n > 0 ? (u64)gcell[pairbeg[j]] : 0xffffffffull;
   keys[j] = (first << 32) | (u64)j;
@@ -353,7 +353,11 @@ constexpr int NVARIANTS = sizeof(VARIANTS) / sizeof(VARIANTS[0]);
 
 int describe(const EvalView& e, int ed, ColEvalDesc* d) {
   d->op = e.op; d->ed = ed; d->nd = e.nd; d->fam = e.fam; d->nbub = 0;
-  if (e.op == GRMP_OP_RECON_ID_RT0 || e.op == GRMP_OP_RECON_ID_BDM1) return -1;
+  if (e.op == GRMP_OP_RECON_ID_RT0 || e.op == GRMP_OP_RECON_ID_BDM1) {
+    if (ed != 2 || e.fam != FAM_H1BR) return -1;       // tetrahedra: quadrature order 6 (46 points) stays on the generic path
+    d->kind = 2; d->nc = 1; d->nds = e.tab_nd;
+    return 0;
+  }
   if (e.fam == FAM_H1) {
     if (e.nd % e.ncomp) return -1;
     d->kind = 0; d->nc = e.ncomp; d->nds = e.nd / e.ncomp;
@@ -369,17 +373,18 @@ int describe(const EvalView& e, int ed, ColEvalDesc* d) {
 int make_tables(const ColEvalDesc& d, int nq, const std::vector<double>& vals, const std::vector<double>& derivs, int nd_all, int ncomp,
                 std::vector<double>* T /* [s][a][q] */, int* nas) {
   const int ed = d.ed;
-  const bool der = (d.op != GRMP_OP_ID);
-  *nas = (d.kind == 0) ? (der ? ed : 1) : (d.op == GRMP_OP_ID ? ed : 1);
+  const bool der = (d.op != GRMP_OP_ID && d.kind != 2);
+  const bool values_table = (d.op == GRMP_OP_ID || d.kind == 2);          // Hdiv Identity / reconstruction: value table of the Hdiv space
+  *nas = (d.kind == 0) ? (der ? ed : 1) : (values_table ? ed : 1);
   const int nsf = d.nds + d.nbub;
   T->assign((size_t)nsf * (*nas) * nq, 0.0);
   auto V = [&](int q, int l, int c) { return vals[((size_t)q * nd_all + l) * ncomp + c]; };
   auto D = [&](int q, int a, int l, int c) { return derivs[((size_t)q * ed + a) * ((size_t)nd_all * ncomp) + l + (size_t)c * nd_all]; };
   if (der && derivs.size() != (size_t)nq * ed * nd_all * ncomp) return fail(GRMP_EUNSUPPORTED, "column kernels: derivative table missing");
   if (!der && vals.size() != (size_t)nq * nd_all * ncomp) return fail(GRMP_EUNSUPPORTED, "column kernels: value table missing");
-  if (d.kind == 1) {
+  if (d.kind != 0) {
     for (int r = 0; r < nsf; r++) for (int q = 0; q < nq; q++) {
-      if (d.op == GRMP_OP_ID) for (int a = 0; a < ed; a++) (*T)[((size_t)r * ed + a) * nq + q] = V(q, r, a);
+      if (values_table) for (int a = 0; a < ed; a++) (*T)[((size_t)r * ed + a) * nq + q] = V(q, r, a);
       else { double s = 0.0; for (int jj = 0; jj < ed; jj++) s += D(q, jj, r, jj); (*T)[(size_t)r * nq + q] = s; }
     }
     return GRMP_OK;
@@ -628,6 +633,321 @@ int colpath_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, 
   for (const auto& c : cp.classes) {     // big tiles first: they have the fewest CTAs per SM and would otherwise be the tail
     cpar.tile_list = cp.class_tiles.p + c.first;
     GRMP_TRY(V.launch(cpar, (int)c.count, 32 * cp.nw, c.smem_bytes, s));
+  }
+  return GRMP_OK;
+}
+
+
+// ==== LinearForm gather kernels ===============================================================================================
+namespace {
+
+struct LfParams {
+  GridView g;
+  const u32* recs;
+  const u32* dofperm;
+  const unsigned short* pos_np;
+  const i64* pos_recbeg;
+  const u32* tile_cellptr;
+  const u32* tile_cells;
+  const u32* tile_list;
+  const double* tabC;
+  const double* wq;
+  const double* fdata;
+  double* b;
+  double factor;
+  i64 ndofs, ngroups;
+  int nw, nq, fsrc;
+};
+
+// b[dof] += (sum_q (sum_k f_k(x_q) cv[k, l, q]) w_q) * (factor * |T|), cells ascending (linearform.jl:181-220).  One thread owns one
+// dof: its value is accumulated in a register and written once; no atomics, order fixed.
+template <class Ev>
+__global__ void __launch_bounds__(256) lf_kernel(const LfParams p) {
+  constexpr int STRIDE = (2 + Ev::CACHE_N + 1) & ~1;       // [0] |T|, [1] cell id, then the evaluator's data
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthr = blockDim.x;
+  const int nq = p.nq;
+  const int ntab = Ev::NAS * nq * CT_PAD;
+  double* const sCt = sm;
+  double* const sW = sm + ((ntab + 1) & ~1);
+  double* const cache = sW + ((nq + 1) & ~1);
+  const i64 tile = p.tile_list[blockIdx.x];
+  const u32 c0 = p.tile_cellptr[tile], nct = p.tile_cellptr[tile + 1] - c0;
+  for (int i = tid; i < ntab; i += nthr) sCt[i] = p.tabC[i];
+  for (int i = tid; i < nq; i += nthr) sW[i] = p.wq[i];
+  for (u32 t = tid; t < nct; t += nthr) {
+    const i64 cell = p.tile_cells[c0 + t];
+    double* cr = cache + (size_t)t * STRIDE;
+    CellGeo<Ev::ED> T;
+    cell_geo<Ev::ED>(p.g, cell, T);
+    cr[0] = p.g.vol[cell];
+    cr[1] = __longlong_as_double((long long)cell);
+    Ev::build_cache(p.g, cell, T, cr + 2);
+  }
+  __syncthreads();
+  const i64 grp = tile * p.nw + warp;
+  if (grp >= p.ngroups) return;
+  const i64 pos = grp * 32 + lane;
+  const bool has = pos < p.ndofs;
+  const u32 np = has ? p.pos_np[pos] : 0u;
+  const i64 recbase = p.pos_recbeg[grp * 32];
+  const u32 maxnp = __reduce_max_sync(0xffffffffu, np);
+  const u32 lt = (1u << lane) - 1u;
+  u32 rbase = 0;
+  const i64 dof = has ? (i64)p.dofperm[pos] : 0;
+  double acc = has ? p.b[dof] : 0.0;
+  for (u32 k = 0; k < maxnp; k++) {
+    const u32 bal = __ballot_sync(0xffffffffu, k < np);
+    const u32 idx = rbase + __popc(bal & lt);
+    rbase += __popc(bal);
+    if (k >= np) continue;
+    const u32 rec = __ldg(p.recs + recbase + idx);
+    const u32 lc = (rec >> 16) & 255u;
+    if (lc == 255u) continue;
+    const double* cr = cache + (size_t)(rec & 0xffffu) * STRIDE;
+    typename Ev::Regs R;
+    Ev::load(cr + 2, R);
+    const i64 cell = __double_as_longlong(cr[1]);
+    double lb = 0.0;
+#pragma unroll 1
+    for (int q = 0; q < nq; q++) {
+      double Y[Ev::RD];
+      Ev::col_eval(R, sCt, nq, q, (int)lc, Y);
+      double t = 0.0;
+      if (p.fsrc == GRMP_F_NONE) {
+#pragma unroll
+        for (int i = 0; i < Ev::RD; i++) t += Y[i];
+      } else if (p.fsrc == GRMP_F_CONST) {
+#pragma unroll
+        for (int i = 0; i < Ev::RD; i++) t = fma(__ldg(p.fdata + i), Y[i], t);
+      } else {
+        const double* f = p.fdata + ((size_t)cell * nq + q) * Ev::RD;
+#pragma unroll
+        for (int i = 0; i < Ev::RD; i++) t = fma(__ldg(f + i), Y[i], t);
+      }
+      lb = fma(t, sW[q], lb);
+    }
+    acc += lb * (p.factor * cr[0]);
+  }
+  if (has) p.b[dof] = acc;
+}
+
+__global__ void lf_pack_records(const u32* dofperm, const i64* pairbeg, const i64* pos_recbeg, const u32* gcell, const u32* gsrc,
+                                const i32* orient, const i32* regions, RegionFilter reg, const u32* tile_cellptr, const u32* tile_cells,
+                                i64 ncells, i64 ndofs, int nw, int col_bdm3, u32* recs, int* err) {
+  const i64 grp = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (grp * 32 >= ndofs) return;
+  const i64 pos = grp * 32 + lane;
+  const bool has = pos < ndofs;
+  const i64 j = has ? (i64)dofperm[pos] : 0;
+  const i64 kb = has ? pairbeg[j] : 0;
+  const u32 np = has ? (u32)(pairbeg[j + 1] - kb) : 0u;
+  const i64 recbase = pos_recbeg[grp * 32];
+  const i64 tile = grp / nw;
+  const u32 tc0 = tile_cellptr[tile], tc1 = tile_cellptr[tile + 1];
+  const u32 maxnp = __reduce_max_sync(0xffffffffu, np);
+  const u32 lt = (1u << lane) - 1u;
+  u32 rbase = 0;
+  for (u32 k = 0; k < maxnp; k++) {
+    const u32 bal = __ballot_sync(0xffffffffu, k < np);
+    const u32 idx = rbase + __popc(bal & lt);
+    rbase += __popc(bal);
+    if (k >= np) continue;
+    const i64 cell = gcell[kb + k];
+    int lc = (int)(gsrc[kb + k] / (u32)ncells);
+    bool active = true;
+    if (reg.n > 0) {
+      active = false;
+      if (regions) for (int r = 0; r < reg.n; r++) active = active || regions[cell] == reg.r[r];
+    }
+    if (col_bdm3) lc = bdm3_ref_of_local(orient + cell * 4, lc);
+    u32 lo = tc0, hi = tc1;
+    while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (tile_cells[mid] < (u32)cell) lo = mid + 1; else hi = mid; }
+    if (lo >= tc1 || tile_cells[lo] != (u32)cell || lo - tc0 > 65535u) atomicExch(err, 2);
+    recs[recbase + idx] = (lo - tc0) | ((active ? (u32)lc : 255u) << 16);
+  }
+}
+
+typedef int (*LfLaunchFn)(const LfParams&, int nblocks, int nthreads, int smem, cudaStream_t);
+struct LfVariant {
+  bool (*match)(const ColEvalDesc&);
+  LfLaunchFn launch;
+  int stride, nas;
+};
+template <class Ev> struct LfVariantImpl {
+  static bool match(const ColEvalDesc& d) { return ev_matches<Ev>(d); }
+  static int launch(const LfParams& p, int nblocks, int nthreads, int smem, cudaStream_t s) {
+    static int attr_set = 0;
+    if (smem > attr_set) {
+      GRMP_CUDA(cudaFuncSetAttribute(lf_kernel<Ev>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_set = smem;
+    }
+    lf_kernel<Ev><<<nblocks, nthreads, smem, s>>>(p);
+    GRMP_CUDA(cudaGetLastError());
+    return GRMP_OK;
+  }
+};
+#define GRMP_LFV(...) {&LfVariantImpl<__VA_ARGS__>::match, &LfVariantImpl<__VA_ARGS__>::launch, (2 + __VA_ARGS__::CACHE_N + 1) & ~1, __VA_ARGS__::NAS},
+#define GRMP_LF_H1(ED, NC, NDS, NB) GRMP_LFV(H1Ev<ED, NC, NDS, NB, GRMP_OP_ID>) GRMP_LFV(H1Ev<ED, NC, NDS, NB, GRMP_OP_GRAD>)
+const LfVariant LFVARIANTS[] = {
+    GRMP_LF_H1(2, 1, 3, 0) GRMP_LF_H1(2, 2, 3, 0) GRMP_LF_H1(2, 1, 6, 0) GRMP_LF_H1(2, 2, 6, 0) GRMP_LF_H1(2, 2, 3, 3) GRMP_LFV(H1Ev<2, 1, 1, 0, GRMP_OP_ID>)
+    GRMP_LF_H1(3, 1, 4, 0) GRMP_LF_H1(3, 3, 4, 0) GRMP_LF_H1(3, 1, 10, 0) GRMP_LF_H1(3, 3, 10, 0) GRMP_LF_H1(3, 3, 4, 4) GRMP_LFV(H1Ev<3, 1, 1, 0, GRMP_OP_ID>)
+    GRMP_LFV(H1Ev<2, 2, 3, 0, GRMP_OP_DIV>) GRMP_LFV(H1Ev<2, 2, 6, 0, GRMP_OP_DIV>) GRMP_LFV(H1Ev<2, 2, 3, 3, GRMP_OP_DIV>)
+    GRMP_LFV(H1Ev<3, 3, 4, 0, GRMP_OP_DIV>) GRMP_LFV(H1Ev<3, 3, 10, 0, GRMP_OP_DIV>) GRMP_LFV(H1Ev<3, 3, 4, 4, GRMP_OP_DIV>)
+    GRMP_LFV(HdivEv<2, 3, GRMP_OP_ID>) GRMP_LFV(HdivEv<2, 6, GRMP_OP_ID>) GRMP_LFV(HdivEv<3, 4, GRMP_OP_ID>) GRMP_LFV(HdivEv<3, 16, GRMP_OP_ID>)
+    GRMP_LFV(HdivEv<2, 3, GRMP_OP_DIV>) GRMP_LFV(HdivEv<2, 6, GRMP_OP_DIV>) GRMP_LFV(HdivEv<3, 4, GRMP_OP_DIV>) GRMP_LFV(HdivEv<3, 16, GRMP_OP_DIV>)
+    GRMP_LFV(ReconEv2D<3>) GRMP_LFV(ReconEv2D<6>)};
+constexpr int NLFVARIANTS = sizeof(LFVARIANTS) / sizeof(LFVARIANTS[0]);
+
+}  // namespace
+
+bool lfpath_applicable(const EvalView& e, int edim, int nq, LfPath* lp) {
+  if (describe(e, edim, &lp->ev)) return false;
+  if (nq > 256) return false;
+  lp->variant = -1;
+  for (int v = 0; v < NLFVARIANTS; v++)
+    if (LFVARIANTS[v].match(lp->ev)) { lp->variant = v; break; }
+  lp->nq = nq;
+  return lp->variant >= 0;
+}
+
+int lfpath_build(grmp_ctx* ctx, const GridView& g, const EvalView& e, const RegionFilter& reg, const std::vector<double>& w,
+                 const std::vector<double>& vals, const std::vector<double>& derivs, i64 ndofs, LfPath* lp) {
+  cudaStream_t s = ctx->stream;
+  lp->built = false;
+  const LfVariant& V = LFVARIANTS[lp->variant];
+  const int nq = lp->nq;
+  const i64 ncells = g.ncells;
+  {
+    std::vector<double> T;
+    int nas = 0;
+    GRMP_TRY(make_tables(lp->ev, nq, vals, derivs, e.tab_nd, e.tab_nc, &T, &nas));
+    const int nsf = lp->ev.nds + lp->ev.nbub;
+    std::vector<double> tc((size_t)nas * nq * CT_PAD, 0.0);
+    for (int a = 0; a < nas; a++) for (int q = 0; q < nq; q++) for (int sI = 0; sI < nsf; sI++)
+      tc[((size_t)a * nq + q) * CT_PAD + sI] = T[((size_t)sI * nas + a) * nq + q];
+    GRMP_TRY(lp->tabC.upload(tc.data(), tc.size(), s));
+    GRMP_TRY(lp->wq.upload(w.data(), w.size(), s));
+  }
+  lp->ndofs = ndofs;
+  lp->ngroups = (ndofs + 31) / 32;
+  lp->ntiles = 0;
+  if (ndofs == 0 || ncells == 0) { lp->built = true; return GRMP_OK; }
+  DofGather dg;
+  GRMP_TRY(build_dofgather(s, e.celldofs, ncells, e.nd, ndofs, &dg));
+  lp->npairs = dg.ncontrib;
+  const i64 npairs = dg.ncontrib;
+  DevBuf<int> flags;
+  GRMP_TRY(flags.alloc(4));
+  GRMP_CUDA(cudaMemsetAsync(flags.p, 0, 16, s));
+  DevBuf<u64> ck1, ck2, keys, keys2, uniq; DevBuf<u32> ci1; DevBuf<unsigned char> temp; DevBuf<i64> np64, nuniq_d, dummy_start;
+  DevBuf<unsigned char> dummy_len;
+  GRMP_TRY(ck1.alloc(ndofs)); GRMP_TRY(ck2.alloc(ndofs)); GRMP_TRY(ci1.alloc(ndofs)); GRMP_TRY(lp->dofperm.alloc(ndofs));
+  order_keys<<<nblk(ndofs), 256, 0, s>>>(nullptr, dg.segptr.p, dg.gcell.p, ndofs, ck1.p, ci1.p, flags.p);
+  GRMP_CUDA(cudaGetLastError());
+  {
+    cub::DoubleBuffer<u64> dk(ck1.p, ck2.p);
+    cub::DoubleBuffer<u32> dv(ci1.p, lp->dofperm.p);
+    size_t tb = 0;
+    GRMP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, ndofs, 0, 64, s));
+    GRMP_TRY(temp.alloc(tb));
+    GRMP_CUDA(cub::DeviceRadixSort::SortPairs(temp.p, tb, dk, dv, ndofs, 0, 64, s));
+    if (dv.Current() != lp->dofperm.p) GRMP_CUDA(cudaMemcpyAsync(lp->dofperm.p, dv.Current(), (size_t)ndofs * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  GRMP_TRY(lp->pos_np.alloc(ndofs)); GRMP_TRY(lp->pos_recbeg.alloc(ndofs + 1)); GRMP_TRY(np64.alloc(ndofs + 1));
+  GRMP_TRY(dummy_len.alloc(ndofs)); GRMP_TRY(dummy_start.alloc(ndofs));
+  // colptr of a pseudo pattern with one entry per dof: reuse pos_arrays with the pair offsets as "colptr"
+  pos_arrays<<<nblk(ndofs), 256, 0, s>>>(lp->dofperm.p, dg.segptr.p, dg.segptr.p, ndofs, lp->pos_np.p, dummy_len.p, dummy_start.p, np64.p);
+  GRMP_CUDA(cudaGetLastError());
+  GRMP_CUDA(cudaMemsetAsync(np64.p + ndofs, 0, 8, s));
+  {
+    size_t tb = 0;
+    GRMP_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, np64.p, lp->pos_recbeg.p, ndofs + 1, s));
+    if (tb > temp.n) GRMP_TRY(temp.alloc(tb));
+    GRMP_CUDA(cub::DeviceScan::ExclusiveSum(temp.p, tb, np64.p, lp->pos_recbeg.p, ndofs + 1, s));
+  }
+  GRMP_TRY(keys.alloc(std::max<i64>(npairs, 1))); GRMP_TRY(keys2.alloc(std::max<i64>(npairs, 1))); GRMP_TRY(uniq.alloc(std::max<i64>(npairs, 1)));
+  GRMP_TRY(nuniq_d.alloc(1));
+  int nw = 4;
+  int hflags[4] = {0, 0, 0, 0};
+  for (;; nw >>= 1) {
+    const int cpt = 32 * nw;
+    const i64 ntiles = (ndofs + cpt - 1) / cpt;
+    tile_keys<<<nblk(ndofs), 256, 0, s>>>(lp->dofperm.p, dg.segptr.p, lp->pos_recbeg.p, dg.gcell.p, ndofs, cpt, keys.p);
+    GRMP_CUDA(cudaGetLastError());
+    int end_bit = 33;
+    while (end_bit < 64 && ((u64)ntiles >> (end_bit - 32)) != 0) end_bit++;
+    size_t tb = 0, tb2 = 0;
+    GRMP_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, keys.p, keys2.p, npairs, 0, end_bit, s));
+    GRMP_CUDA(cub::DeviceSelect::Unique(nullptr, tb2, keys2.p, uniq.p, nuniq_d.p, npairs, s));
+    if (std::max(tb, tb2) > temp.n) GRMP_TRY(temp.alloc(std::max(tb, tb2)));
+    GRMP_CUDA(cub::DeviceRadixSort::SortKeys(temp.p, tb, keys.p, keys2.p, npairs, 0, end_bit, s));
+    GRMP_CUDA(cub::DeviceSelect::Unique(temp.p, tb2, keys2.p, uniq.p, nuniq_d.p, npairs, s));
+    i64 nuniq = 0;
+    GRMP_CUDA(cudaMemcpyAsync(&nuniq, nuniq_d.p, 8, cudaMemcpyDeviceToHost, s));
+    GRMP_CUDA(cudaStreamSynchronize(s));
+    GRMP_TRY(lp->tile_cellptr.alloc(ntiles + 1));
+    GRMP_TRY(lp->tile_cells.alloc(std::max<i64>(nuniq, 1)));
+    GRMP_CUDA(cudaMemsetAsync(flags.p + 2, 0, 4, s));
+    tile_ptr<<<nblk(ntiles + 1), 256, 0, s>>>(uniq.p, nuniq, ntiles, lp->tile_cellptr.p, flags.p + 2);
+    low32<<<nblk(nuniq), 256, 0, s>>>(uniq.p, nuniq, lp->tile_cells.p);
+    GRMP_CUDA(cudaGetLastError());
+    std::vector<u32> tcp(ntiles + 1);
+    GRMP_CUDA(cudaMemcpyAsync(tcp.data(), lp->tile_cellptr.p, (size_t)(ntiles + 1) * 4, cudaMemcpyDeviceToHost, s));
+    GRMP_CUDA(cudaMemcpyAsync(hflags, flags.p, 16, cudaMemcpyDeviceToHost, s));
+    GRMP_CUDA(cudaStreamSynchronize(s));
+    if (hflags[0]) return fail(GRMP_EUNSUPPORTED, "linear form kernels: a dof lies in more than 65535 cells");
+    const i64 fixed = 8 * ((((i64)V.nas * nq * CT_PAD + 1) & ~1) + ((nq + 1) & ~1));
+    const i64 need_max = fixed + (i64)hflags[2] * V.stride * 8;
+    if (hflags[2] <= 65535 && need_max <= 200 * 1024) {
+      lp->nw = nw; lp->ntiles = ntiles;
+      const int caps[6] = {6 * 1024, 13 * 1024, 27 * 1024, 55 * 1024, 112 * 1024, 200 * 1024};
+      std::vector<std::vector<u32>> lists(6);
+      std::vector<int> mx(6, 0);
+      for (i64 t = 0; t < ntiles; t++) {
+        const int need = (int)(fixed + (i64)(tcp[t + 1] - tcp[t]) * V.stride * 8);
+        int c = 0;
+        while (c < 5 && need > caps[c]) c++;
+        lists[c].push_back((u32)t);
+        mx[c] = std::max(mx[c], need);
+      }
+      std::vector<u32> all;
+      lp->classes.clear();
+      for (int c = 5; c >= 0; c--) {
+        if (lists[c].empty()) continue;
+        lp->classes.push_back(ColPath::TileClass{mx[c], (i64)all.size(), (i64)lists[c].size()});
+        all.insert(all.end(), lists[c].begin(), lists[c].end());
+      }
+      GRMP_TRY(lp->class_tiles.upload(all.data(), all.size(), s));
+      GRMP_CUDA(cudaStreamSynchronize(s));
+      break;
+    }
+    if (nw == 1) return fail(GRMP_EUNSUPPORTED, "linear form kernels: one group of 32 dofs does not fit into shared memory");
+  }
+  GRMP_TRY(lp->recs.alloc(std::max<i64>(npairs, 1)));
+  lf_pack_records<<<nblk(lp->ngroups * 32, 128), 128, 0, s>>>(lp->dofperm.p, dg.segptr.p, lp->pos_recbeg.p, dg.gcell.p, dg.gsrc.p, g.orient, g.regions,
+                                                             reg, lp->tile_cellptr.p, lp->tile_cells.p, ncells, ndofs, lp->nw,
+                                                             (lp->ev.kind == 1 && lp->ev.nds == 16) ? 1 : 0, lp->recs.p, flags.p);
+  GRMP_CUDA(cudaGetLastError());
+  GRMP_CUDA(cudaMemcpyAsync(hflags, flags.p, 4, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  if (hflags[0]) return fail(GRMP_EUNSUPPORTED, "linear form kernels: record build failed");
+  lp->built = true;
+  return GRMP_OK;
+}
+
+int lfpath_numeric(grmp_ctx* ctx, const GridView& g, LfPath& lp, double factor, int fsrc, const double* fdata, double* b) {
+  if (!lp.built) return fail(GRMP_ESTATE, "linear form kernels: records not built");
+  if (lp.ntiles == 0) return GRMP_OK;
+  const LfVariant& V = LFVARIANTS[lp.variant];
+  LfParams p{};
+  p.g = g; p.recs = lp.recs.p; p.dofperm = lp.dofperm.p; p.pos_np = lp.pos_np.p; p.pos_recbeg = lp.pos_recbeg.p;
+  p.tile_cellptr = lp.tile_cellptr.p; p.tile_cells = lp.tile_cells.p; p.tabC = lp.tabC.p; p.wq = lp.wq.p; p.fdata = fdata; p.b = b;
+  p.factor = factor; p.ndofs = lp.ndofs; p.ngroups = lp.ngroups; p.nw = lp.nw; p.nq = lp.nq; p.fsrc = fsrc;
+  for (const auto& c : lp.classes) {
+    p.tile_list = lp.class_tiles.p + c.first;
+    GRMP_TRY(V.launch(p, (int)c.count, 32 * lp.nw, c.smem_bytes, ctx->stream));
   }
   return GRMP_OK;
 }

@@ -54,6 +54,27 @@ struct ColPath {
   std::vector<i64> colour_ptr;     // [ncolours+1]
 };
 
+// LinearForm: one thread per dof gathers the contributions of the cells around it (register accumulation, cells ascending)
+struct LfPath {
+  bool built = false;
+  int variant = -1, nw = 4, nq = 0;
+  i64 ndofs = 0, ngroups = 0, ntiles = 0, npairs = 0;
+  ColEvalDesc ev{};
+  DevBuf<u32> recs;                // per pair: tile-local cell | local function << 16 (255: cell filtered out by the regions)
+  DevBuf<u32> dofperm;             // position -> dof
+  DevBuf<unsigned short> pos_np;
+  DevBuf<i64> pos_recbeg;
+  DevBuf<u32> tile_cellptr, tile_cells, class_tiles;
+  std::vector<ColPath::TileClass> classes;
+  DevBuf<double> tabC, wq;
+};
+bool lfpath_applicable(const EvalView& e, int edim, int nq, LfPath* lp);
+int lfpath_build(grmp_ctx* ctx, const GridView& g, const EvalView& e, const RegionFilter& reg, const std::vector<double>& w,
+                 const std::vector<double>& vals, const std::vector<double>& derivs, i64 ndofs, LfPath* lp);
+// b[dof] += sum over the cells of the dof, cells ascending (linearform.jl:181-220); fdata: device pointer (GRMP_F_CONST: rd values,
+// GRMP_F_QP_TABLE: [ncells][nq][rd])
+int lfpath_numeric(grmp_ctx* ctx, const GridView& g, LfPath& lp, double factor, int fsrc, const double* fdata, double* b);
+
 // does a column kernel exist for this form?  (fills the descriptors)
 bool colpath_applicable(const BlfLocalParams& p, int nq, ColPath* cp);
 // one-time build of the records (device), tables (host copies of the caller's tables) ...

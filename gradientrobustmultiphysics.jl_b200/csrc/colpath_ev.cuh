@@ -337,6 +337,116 @@ template <int ED_, int NDALL_, int OP_> struct HdivEv {
   }
 };
 
+// ---- ReconstructionIdentity{HDIVRT0{2} | HDIVBDM1{2}} on Bernardi-Raugel, triangles (feevaluator_h1.jl:342-381) ----------------
+// R phi_l = sum_r rc[l][r] psi_r with psi_r the Piola-mapped Hdiv basis and rc from boundary_coefficients!
+// (reconstructions.jl:353-403): for a nodal dof (component k, node n) and every face F containing n
+//     rc[(k,n)][F, RT0 function] = 1/2 |F| n_k(F),      rc[(k,n)][F, BDM1 function] = -+1/12 |F| n_k(F) sign_F  (n first / second node of F)
+// and rc[bubble F][F, RT0 function] = |F|.  The reconstruction is FUSED into the contraction: a column thread combines the
+// reference functions with its weights before the Piola map, the row side accumulates against the Hdiv reference table
+// (uniform index, constant memory) and applies rc when the rows are emitted -- the coefficient matrix is never formed.
+template <int NDALL2_> struct ReconEv2D {
+  static constexpr int ED = 2, NC = 1, NDS = NDALL2_, NBUB = 0, KIND = 2;
+  static constexpr bool BDM = (NDALL2_ == 6);
+  static constexpr int OP = BDM ? GRMP_OP_RECON_ID_BDM1 : GRMP_OP_RECON_ID_RT0;
+  static constexpr int NF = 3, NN = 3, NM2 = BDM ? 2 : 1;
+  static constexpr int NROW = ED * NN + NF, NSF = NDALL2_;
+  static constexpr int NAS = ED, NCU = 1, RD = ED, NM = ED * ED;
+  static constexpr int CACHE_N = NM + 2 + NF * ED + NF;
+  struct Regs {
+    double M[NM], idet, fw[NF * ED], fv[NF];
+    u32 bits;     // bit f: CellFaceSigns[f] < 0
+  };
+  __device__ __forceinline__ static void build_cache(const GridView& g, i64 cell, const CellGeo<ED>& T, double* out) {
+#pragma unroll
+    for (int k = 0; k < ED; k++)
+#pragma unroll
+      for (int a = 0; a < ED; a++) out[k * ED + a] = T.A[k][a];
+    out[NM] = T.idet;
+    const i32* sg = g.signs + cell * NF;
+    const i32* cf = g.cellfaces + cell * NF;
+    u32 bits = 0;
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+      bits |= (sg[f] < 0 ? 1u : 0u) << f;
+      const i64 face = cf[f] - 1;
+      const double fv = g.fvol[face];
+#pragma unroll
+      for (int k = 0; k < ED; k++) out[NM + 2 + f * ED + k] = fv * g.fnormals[face * ED + k];
+      out[NM + 2 + NF * ED + f] = fv;
+    }
+    out[NM + 1] = __longlong_as_double((long long)bits);
+  }
+  __device__ __forceinline__ static void load(const double* cr, Regs& R) {
+#pragma unroll
+    for (int i = 0; i < NM; i++) R.M[i] = cr[i];
+    R.idet = cr[NM];
+    R.bits = (u32)__double_as_longlong(cr[NM + 1]);
+#pragma unroll
+    for (int i = 0; i < NF * ED; i++) R.fw[i] = cr[NM + 2 + i];
+#pragma unroll
+    for (int i = 0; i < NF; i++) R.fv[i] = cr[NM + 2 + NF * ED + i];
+  }
+  // local face -> nodes of Triangle2D: [1 2], [2 3], [3 1]
+  __host__ __device__ static constexpr int face_node(int f, int pos) { return pos == 0 ? f : (f + 1) % 3; }
+  // weight of Hdiv local dof (f, m) in R phi_l, including the Hdiv coefficient sign of that dof (hdiv_rt0.jl:106-116,
+  // hdiv_bdm1.jl:278-290: CellFaceSigns on the RT0-type functions only)
+  __device__ __forceinline__ static double weight(const Regs& R, int l, int f, int m) {
+    const double sgn = ((R.bits >> f) & 1u) ? -1.0 : 1.0;
+    double w = 0.0;
+    if (l >= ED * NN) {
+      if (l - ED * NN == f && m == 0) w = R.fv[f] * sgn;
+    } else {
+      const int k = l / NN, node = l - k * NN;
+      const double fwk = k == 0 ? R.fw[f * ED] : R.fw[f * ED + 1];
+      if (node == face_node(f, 0)) w = (m == 0) ? 0.5 * fwk * sgn : (-1.0 / 12.0) * fwk * sgn;    // BDM1 part: rc carries sign_F, the function none
+      else if (node == face_node(f, 1)) w = (m == 0) ? 0.5 * fwk * sgn : (1.0 / 12.0) * fwk * sgn;
+    }
+    return w;
+  }
+  __device__ __forceinline__ static void col_eval(const Regs& R, const double* __restrict__ Ct, int nq, int q, int l, double (&Y)[RD]) {
+    double h[ED] = {0.0, 0.0};
+#pragma unroll
+    for (int f = 0; f < NF; f++)
+#pragma unroll
+      for (int m = 0; m < NM2; m++) {
+        const double w = weight(R, l, f, m);
+        const int r = BDM ? 2 * f + m : f;
+#pragma unroll
+        for (int a = 0; a < ED; a++) h[a] = fma(w, Ct[((size_t)a * nq + q) * CT_PAD + r], h[a]);
+      }
+#pragma unroll
+    for (int k = 0; k < ED; k++) Y[k] = R.idet * (R.M[k * ED] * h[0] + R.M[k * ED + 1] * h[1]);
+  }
+  __device__ __forceinline__ static void pullback(const Regs& R, const double (&Y)[RD], double (&U)[NCU][NAS]) {
+#pragma unroll
+    for (int a = 0; a < ED; a++) U[0][a] = R.idet * (R.M[a] * Y[0] + R.M[ED + a] * Y[1]);
+  }
+  struct Acc {
+    double E[NDALL2_];
+  };
+  __device__ __forceinline__ static void acc_zero(Acc& A) {
+#pragma unroll
+    for (int r = 0; r < NDALL2_; r++) A.E[r] = 0.0;
+  }
+  __device__ __forceinline__ static void acc_rows(Acc& A, const double (&U)[NCU][NAS], const double* __restrict__ Rt) {
+#pragma unroll
+    for (int r = 0; r < NDALL2_; r++)
+#pragma unroll
+      for (int a = 0; a < NAS; a++) A.E[r] = fma(U[0][a], Rt[r * NAS + a], A.E[r]);
+  }
+  template <class F> __device__ __forceinline__ static void emit_rows(const Regs& R, const Acc& A, F&& f) {
+#pragma unroll
+    for (int l = 0; l < NROW; l++) {
+      double v = 0.0;
+#pragma unroll
+      for (int fc = 0; fc < NF; fc++)
+#pragma unroll
+        for (int m = 0; m < NM2; m++) v = fma(weight(R, l, fc, m), A.E[BDM ? 2 * fc + m : fc], v);
+      f(l, v);
+    }
+  }
+};
+
 // Hooke tensors (pdeoperators.jl:265-270, 304-312) applied to the column value
 template <int ACT, int RD> __device__ __forceinline__ void apply_action_col(const double* p, double (&Y)[RD]) {
   if constexpr (ACT == GRMP_ACT_HOOKE2D) {
@@ -398,7 +508,8 @@ __device__ __forceinline__ void build_cell_cache(const GridView& g, i64 cell, do
   X((H1Ev<2, 2, 6, 0, GRMP_OP_SYMGRAD>), (H1Ev<2, 2, 6, 0, GRMP_OP_SYMGRAD>), GRMP_ACT_HOOKE2D, 3)               \
   X((H1Ev<3, 3, 4, 0, GRMP_OP_SYMGRAD>), (H1Ev<3, 3, 4, 0, GRMP_OP_SYMGRAD>), GRMP_ACT_HOOKE3D, 1)               \
   X((H1Ev<3, 3, 10, 0, GRMP_OP_SYMGRAD>), (H1Ev<3, 3, 10, 0, GRMP_OP_SYMGRAD>), GRMP_ACT_HOOKE3D, 4)             \
-  GRMP_HDIV_SQUARE(X, 2, 3, 3) GRMP_HDIV_SQUARE(X, 2, 6, 3) GRMP_HDIV_SQUARE(X, 3, 4, 4) GRMP_HDIV_SQUARE(X, 3, 16, 4)
+  GRMP_HDIV_SQUARE(X, 2, 3, 3) GRMP_HDIV_SQUARE(X, 2, 6, 3) GRMP_HDIV_SQUARE(X, 3, 4, 4) GRMP_HDIV_SQUARE(X, 3, 16, 4)  \
+  X((ReconEv2D<3>), (ReconEv2D<3>), GRMP_ACT_NONE, 9) X((ReconEv2D<6>), (ReconEv2D<6>), GRMP_ACT_NONE, 9)
 
 #define GRMP_RECT_FORMS(X)                                                                                       \
   GRMP_RECT(X, (H1Ev<2, 2, 3, 3, GRMP_OP_DIV>), (H1Ev<2, 1, 1, 0, GRMP_OP_ID>), 1)                               \

@@ -208,6 +208,9 @@ int grmp_blf_apply_penalties(grmp_blf* blf, const int64_t* fixed_dofs, int64_t n
 int grmp_lf_create(grmp_space* space, int op, const int32_t* regions, int nregions, int nq, const double* qweights,
                    const grmp_evaltab* tab, grmp_lf** out);
 int grmp_lf_destroy(grmp_lf* lf);
+/* numeric back end of the linear form: GRMP_PATH_GENERIC (bit-exact two-phase path) or GRMP_PATH_COLUMNS (one thread per dof
+ * gathers its cells' contributions in registers, cells ascending); GRMP_PATH_AUTO (default) takes COLUMNS where a kernel exists */
+int grmp_lf_set_path(grmp_lf* lf, int path);
 /* assemble!(b, AP; factor, offset) (linearform.jl:47-237): b[dof+offset] += contributions in
  * cell order.  fsrc = GRMP_F_NONE (no action: input = ones, 74-75), GRMP_F_CONST
  * (fdata[resultdim]) or GRMP_F_QP_TABLE (fdata[ncells][nq][resultdim], the host-evaluated

@@ -57,6 +57,14 @@ SQUARE = [
     ("BR tri Laplace perturbed", lambda: tri_grid(3, True), lambda: G.H1BR(2), (G.Gradient, G.Gradient)),
     ("BR tet Laplace", lambda: tet_grid(1, True), lambda: G.H1BR(3), (G.Gradient, G.Gradient)),
     ("BR tri mass", lambda: tri_grid(2), lambda: G.H1BR(2), (G.Identity, G.Identity)),
+    ("BR tri recon RT0 mass (C4)", lambda: tri_grid(2), lambda: G.H1BR(2),
+     (G.ReconstructionIdentity(G.HDIVRT0(2)), G.ReconstructionIdentity(G.HDIVRT0(2)))),
+    ("BR tri recon RT0 mass perturbed", lambda: tri_grid(3, True), lambda: G.H1BR(2),
+     (G.ReconstructionIdentity(G.HDIVRT0(2)), G.ReconstructionIdentity(G.HDIVRT0(2)))),
+    ("BR tri recon BDM1 mass (C4)", lambda: tri_grid(2, True), lambda: G.H1BR(2),
+     (G.ReconstructionIdentity(G.HDIVBDM1(2)), G.ReconstructionIdentity(G.HDIVBDM1(2)))),
+    ("BR tri recon BDM1 mass axis aligned", lambda: tri_grid(3), lambda: G.H1BR(2),
+     (G.ReconstructionIdentity(G.HDIVBDM1(2)), G.ReconstructionIdentity(G.HDIVBDM1(2)))),
 ]
 
 
@@ -201,3 +209,67 @@ def test_cell_parallel_hooke():
     s = G.FESpace(G.H1P2(2, 2), g)
     for path in (ATOM, COLR):
         check(G.DiscreteBilinearForm([G.SymmetricGradient(1), G.SymmetricGradient(1)], [s, s], G.HookeAction(2, 2.0, 3.0)), path=path)
+
+
+# ---- linear forms: owner-computes gather kernels (one thread per dof) vs the oracle ----------------------------------------------
+from test_gpu_parity import LF_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("case", LF_CASES, ids=[c[0] for c in LF_CASES])
+def test_lf_gather_kernels(case):
+    _, gridf, fef, op, kind, regions = case
+    g = gridf()
+    s = G.FESpace(fef(), g)
+    dim = g.dim
+    nc = s.fetype.ncomponents
+    bonus = 0
+    if kind == "const":
+        data = G.DataFunction([1.0])
+    elif kind == "none":
+        data = None
+    elif kind == "fun":
+        data = G.DataFunction(lambda x: np.sin(x[0]) * x[1] + (x[2] if len(x) > 2 else 0.0), [1, dim], bonus_quadorder=2)
+        bonus = 2
+    elif kind == "vfun":
+        data = G.DataFunction(lambda x: np.stack([x[k] ** 2 + x[(k + 1) % len(x)] for k in range(len(x))]), [nc, dim], bonus_quadorder=1)
+        bonus = 1
+    else:
+        data = G.DataFunction(lambda x: np.stack([3 * x[k] ** 2 for k in range(len(x))]), [nc, dim], bonus_quadorder=2)
+        bonus = 2
+    expect_fast = not (isinstance(op, G.ReconstructionIdentity) and dim == 3)     # tetrahedral reconstruction stays generic
+    old = G.assembly.DEFAULT_PATH
+    G.assembly.DEFAULT_PATH = G._lib.PATH_AUTO
+    try:
+        Op = G.LinearForm(op, data, regions=regions, factor=2.0)
+        b = G.FEVector([s])
+        b.entries[:] = 0.25
+        AP = G.assemble_operator(b[1], Op)
+        assert G.blf_stats(AP).path == (COLS if expect_fast else GEN)
+        first = b.entries.copy()
+        b.entries[:] = 0.25
+        G.assemble_operator(b[1], Op, Pattern=AP, skip_preps=True)
+        assert np.array_equal(first, b.entries), "two runs differ"
+    finally:
+        G.assembly.DEFAULT_PATH = old
+    qo = G.quadrature_order(AP)
+    P = AP.AM
+    O.qrule_override(dim, qo, P.qf.xref, P.qf.w)
+    try:
+        ob = np.full(s.ndofs, 0.25)
+        mag = np.zeros(s.ndofs)
+        if kind == "const":
+            O.lf_assemble(ob, g, s, op.code, fsrc=O.F_CONST, fdata=[1.0], regions=regions, factor=2.0, bonus_quadorder=bonus)
+        elif kind == "none":
+            O.lf_assemble(ob, g, s, op.code, fsrc=O.F_NONE, regions=regions, factor=2.0)
+        else:
+            xq = O.quadpoints(g, qo)
+            flat = xq.reshape(-1, dim)
+            vals = np.asarray(data.kernel(flat.T), dtype=np.float64).reshape(-1, flat.shape[0]).T
+            table = vals.reshape(g.ncells, len(P.qf), -1)
+            O.lf_assemble(ob, g, s, op.code, fsrc=O.F_QP_TABLE, fdata=table, regions=regions, factor=2.0, bonus_quadorder=bonus)
+    finally:
+        O.qrule_override(dim, qo)
+    # entries of b are sums over cells and quadrature points with mixed signs: tolerance relative to the largest entry of the
+    # contribution (b - 0.25), i.e. 1e-12 * max|b| absolute plus 1e-12 relative
+    scale = np.abs(ob - 0.25).max()
+    assert np.abs(b.entries - ob).max() <= 1e-12 * max(scale, 1e-300), np.abs(b.entries - ob).max() / scale
