@@ -63,10 +63,12 @@ __global__ void __launch_bounds__(128) cell_kernel(const CellParams p) {
   for (int lc = 0; lc < ColEv::NROW; lc++) {
     typename RowEv::Acc A;
     RowEv::acc_zero(A);
+    typename ColEv::Prep PC;
+    ColEv::prep(RC, lc, PC);
 #pragma unroll 1
     for (int q = 0; q < nq; q++) {
       double Y[ColEv::RD];
-      ColEv::col_eval(RC, sCt, nq, q, lc, Y);
+      ColEv::col_eval(RC, PC, sCt, nq, q, Y);
       const double ws = sW[q] * s;
 #pragma unroll
       for (int k = 0; k < ColEv::RD; k++) Y[k] *= ws;

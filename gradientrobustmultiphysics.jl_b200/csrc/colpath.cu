@@ -128,10 +128,12 @@ __global__ void __launch_bounds__(256) col_kernel(const ColParams p) {
       ColEv::load(cr + L::OFF_C, RC);
       typename RowEv::Acc A;
       RowEv::acc_zero(A);
+      typename ColEv::Prep PC;
+      ColEv::prep(RC, (int)lc, PC);
 #pragma unroll 1
       for (int q = 0; q < nq; q++) {
         double Y[ColEv::RD];
-        ColEv::col_eval(RC, sCt, nq, q, (int)lc, Y);
+        ColEv::col_eval(RC, PC, sCt, nq, q, Y);
         const double ws = c_wq[q] * s;
 #pragma unroll
         for (int i = 0; i < ColEv::RD; i++) Y[i] *= ws;
@@ -709,10 +711,12 @@ __global__ void __launch_bounds__(256) lf_kernel(const LfParams p) {
     Ev::load(cr + 2, R);
     const i64 cell = __double_as_longlong(cr[1]);
     double lb = 0.0;
+    typename Ev::Prep PC;
+    Ev::prep(R, (int)lc, PC);
 #pragma unroll 1
     for (int q = 0; q < nq; q++) {
       double Y[Ev::RD];
-      Ev::col_eval(R, sCt, nq, q, (int)lc, Y);
+      Ev::col_eval(R, PC, sCt, nq, q, Y);
       double t = 0.0;
       if (p.fsrc == GRMP_F_NONE) {
 #pragma unroll

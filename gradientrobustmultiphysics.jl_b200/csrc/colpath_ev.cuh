@@ -111,25 +111,33 @@ template <int ED_, int NC_, int NDS_, int NBUB_, int OP_> struct H1Ev {
 #pragma unroll
     for (int i = 0; i < NBUB * ED; i++) R.nb[i] = cr[NM + i];
   }
-  // operator values of local function l at quadrature point q (Ct: [a][q][CT_PAD] scalar table)
-  __device__ __forceinline__ static void col_eval(const Regs& R, const double* __restrict__ Ct, int nq, int q, int l, double (&Y)[RD]) {
-    int s, cl;
+  // what does not depend on the quadrature point: scalar function and component weights of local function l
+  struct Prep {
+    int s;
     double beta[NC];
+  };
+  __device__ __forceinline__ static void prep(const Regs& R, int l, Prep& P) {
     if (NBUB > 0 && l >= NC * NDS) {
       const int b = l - NC * NDS;
-      s = NDS + b; cl = -1;
+      P.s = NDS + b;
 #pragma unroll
       for (int c = 0; c < NC; c++) {
         double v = 0.0;
 #pragma unroll
         for (int bb = 0; bb < NBUB; bb++) v = (bb == b) ? R.nb[bb * ED + c] : v;
-        beta[c] = v;
+        P.beta[c] = v;
       }
     } else {
-      cl = l / NDS; s = l - cl * NDS;
+      const int cl = l / NDS;
+      P.s = l - cl * NDS;
 #pragma unroll
-      for (int c = 0; c < NC; c++) beta[c] = (c == cl) ? 1.0 : 0.0;
+      for (int c = 0; c < NC; c++) P.beta[c] = (c == cl) ? 1.0 : 0.0;
     }
+  }
+  // operator values of local function l at quadrature point q (Ct: [a][q][CT_PAD] scalar table)
+  __device__ __forceinline__ static void col_eval(const Regs& R, const Prep& P, const double* __restrict__ Ct, int nq, int q, double (&Y)[RD]) {
+    const int s = P.s;
+    const double(&beta)[NC] = P.beta;
     if constexpr (OP == GRMP_OP_ID) {
       const double v = Ct[(size_t)q * CT_PAD + s];
 #pragma unroll
@@ -288,8 +296,17 @@ template <int ED_, int NDALL_, int OP_> struct HdivEv {
     R.idet = cr[NM];
     R.neg = (u32)__double_as_longlong(cr[NM + 1]);
   }
-  __device__ __forceinline__ static void col_eval(const Regs& R, const double* __restrict__ Ct, int nq, int q, int l, double (&Y)[RD]) {
-    const double sg = ((R.neg >> l) & 1u) ? -R.idet : R.idet;
+  struct Prep {
+    int l;
+    double sg;
+  };
+  __device__ __forceinline__ static void prep(const Regs& R, int l, Prep& P) {
+    P.l = l;
+    P.sg = ((R.neg >> l) & 1u) ? -R.idet : R.idet;
+  }
+  __device__ __forceinline__ static void col_eval(const Regs& R, const Prep& P, const double* __restrict__ Ct, int nq, int q, double (&Y)[RD]) {
+    const double sg = P.sg;
+    const int l = P.l;
     if constexpr (OP == GRMP_OP_ID) {
       double d[ED];
 #pragma unroll
@@ -403,13 +420,22 @@ template <int NDALL2_> struct ReconEv2D {
     }
     return w;
   }
-  __device__ __forceinline__ static void col_eval(const Regs& R, const double* __restrict__ Ct, int nq, int q, int l, double (&Y)[RD]) {
+  struct Prep {
+    double w[NF][NM2];
+  };
+  __device__ __forceinline__ static void prep(const Regs& R, int l, Prep& P) {
+#pragma unroll
+    for (int f = 0; f < NF; f++)
+#pragma unroll
+      for (int m = 0; m < NM2; m++) P.w[f][m] = weight(R, l, f, m);
+  }
+  __device__ __forceinline__ static void col_eval(const Regs& R, const Prep& P, const double* __restrict__ Ct, int nq, int q, double (&Y)[RD]) {
     double h[ED] = {0.0, 0.0};
 #pragma unroll
     for (int f = 0; f < NF; f++)
 #pragma unroll
       for (int m = 0; m < NM2; m++) {
-        const double w = weight(R, l, f, m);
+        const double w = P.w[f][m];
         const int r = BDM ? 2 * f + m : f;
 #pragma unroll
         for (int a = 0; a < ED; a++) h[a] = fma(w, Ct[((size_t)a * nq + q) * CT_PAD + r], h[a]);
