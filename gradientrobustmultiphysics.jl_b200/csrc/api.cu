@@ -565,6 +565,7 @@ int grmp_blf_numeric_steps(grmp_blf* b, double factor, int nsteps, double* total
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   if (total_ms) *total_ms = ms;
   if (nsteps > 0) { b->st.last_numeric_ms = ms / nsteps; b->have_values = true; }
+  if (b->path == GRMP_PATH_FAST) GRMP_TRY(fast_p2tet_print_prof(ctx, b->fast));
   return GRMP_OK;
 }
 

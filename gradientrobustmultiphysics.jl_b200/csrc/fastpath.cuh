@@ -24,6 +24,8 @@ struct FastP2Tet {
   DevBuf<uint4> vrec;             // per vertex column: diagonal slot, first slot, #slots
   DevBuf<int> tile_counter;       // dynamic tile scheduler of the edge kernel
   i64 nvcols = 0;
+  DevBuf<unsigned long long> prof; // GRMP_FAST_PROF: cycle counters of the last launch (8 per CTA)
+  int grid = 0;                   // CTAs of the last edge-kernel launch
 };
 
 bool fast_p2tet_applicable(const BlfLocalParams& p);
@@ -32,6 +34,8 @@ bool fast_p2tet_applicable(const BlfLocalParams& p);
 int fast_p2tet_quality(grmp_ctx* ctx, const BlfLocalParams& p, double* kappa);
 int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const std::vector<double>& w,
                      const std::vector<double>& derivs, i64 ncols_owned, i64 geom_version, FastP2Tet* out);
+// GRMP_FAST_PROF: mean cycle counters of the last launch on stderr
+int fast_p2tet_print_prof(grmp_ctx* ctx, const FastP2Tet& f);
 int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, FastP2Tet& f, i64 geom_version, double* nzval);
 
 }  // namespace grmp

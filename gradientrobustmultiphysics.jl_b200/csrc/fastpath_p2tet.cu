@@ -283,6 +283,7 @@ struct EdgeParams {
   u32 in_stride;            // bytes of one input buffer (largest blob)
   u32 slot_elems;           // doubles per warp stage slot
   int nbuf;                 // depth of the input ring (2 or 3)
+  unsigned long long* prof; // GRMP_FAST_PROF: 8 cycle counters per CTA (service warp: wait done, mirror write-out, total; consumer warp 0: wait full, total)
   int dbg;                  // GRMP_DEBUG_FLAGS (timing experiments only): 1 skip the mirror write-out, 2 skip the diagonal kernel, 4 skip the ring
                             // walk, 8 skip the bulk stores, 16 mirror stores without the evict-last hint, 32 / 64 evict-first hint on the
                             // bulk stores / blob loads
@@ -395,6 +396,8 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
     const int slane = tid - NW * 32;                        // 0 .. 32 NSVC - 1; thread 0 of the service warps loads tiles
     int it = 0;
     int b = 0, use = 0;                                       // buffer of iteration it, how often it has been filled before
+    long long c_wait = 0, c_wo = 0;
+    const long long c_start = clock64();
     for (;; it++) {
       int t = 0;
       uint2 dir = make_uint2(0, 0);
@@ -404,9 +407,12 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
         if (t < p.ntiles) dir = __ldg(p.tile_dir + t);
       }
       if (use >= 1) {
+        const long long c0 = clock64();
         mbar_wait(done_a + 8 * b, (unsigned)(use - 1) & 1u);   // all consumer warps have left the tile in this buffer
+        const long long c1 = clock64();
         if (!(p.dbg & 1)) mirror_writeout(p, smraw + (size_t)b * p.in_stride, slane, 32 * NSVC);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // parked values (generic writes) before the next bulk load
+        c_wait += c1 - c0; c_wo += clock64() - c1;
       }
       if (slane == 0) s_next = t;
       asm volatile("bar.sync 1, %0;" ::"n"(32 * NSVC) : "memory");     // write-out finished by all service warps; s_next visible
@@ -431,14 +437,24 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
       mbar_wait(done_a + 8 * b2, (unsigned)(j / NB) & 1u);
       if (!(p.dbg & 1)) mirror_writeout(p, smraw + (size_t)b2 * p.in_stride, slane, 32 * NSVC);
     }
+    if (p.prof != nullptr && slane == 0) {
+      unsigned long long* q = p.prof + 8 * (size_t)blockIdx.x;
+      q[0] = (unsigned long long)c_wait; q[1] = (unsigned long long)c_wo; q[2] = (unsigned long long)(clock64() - c_start); q[7] = (unsigned long long)it;
+    }
     return;
   }
   // ---- consumers ----
   const u64 pol_stream = l2_policy_evict_first();
   double* const slot = reinterpret_cast<double*>(smraw + (size_t)NB * p.in_stride) + (size_t)warp * p.slot_elems;
+  long long cc_wait = 0;
+  const long long cc_start = clock64();
   for (int it = 0, cur = 0, use = 0;; it++) {
     unsigned char* in = smraw + (size_t)cur * p.in_stride;
-    mbar_wait(full_a + 8 * cur, (unsigned)use & 1u);
+    {
+      const long long c0 = clock64();
+      mbar_wait(full_a + 8 * cur, (unsigned)use & 1u);
+      cc_wait += clock64() - c0;
+    }
     if (*reinterpret_cast<volatile int*>(&s_tile[cur]) < 0) break;
     const int4 h0 = reinterpret_cast<const int4*>(in)[0], h1 = reinterpret_cast<const int4*>(in)[1], h2 = reinterpret_cast<const int4*>(in)[2];
     const uint4 gr0 = reinterpret_cast<const uint4*>(in + 48)[warp], gr1 = reinterpret_cast<const uint4*>(in + 48)[warp + 1];
@@ -607,6 +623,10 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
     if (++cur == NB) { cur = 0; use++; }
   }
   if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must stay alive until read
+  if (p.prof != nullptr && tid == 0) {
+    unsigned long long* q = p.prof + 8 * (size_t)blockIdx.x;
+    q[3] = (unsigned long long)cc_wait; q[4] = (unsigned long long)(clock64() - cc_start);
+  }
 }
 
 // Diagonal of the vertex columns.  The vertex-vertex block of the P2 stiffness matrix is the P1 stiffness matrix K1 scaled
@@ -1033,6 +1053,11 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   GRMP_TRY(d_mirbase.upload(mir_base.data(), mir_base.size(), s));
   GRMP_TRY(out->tile_dir.upload(tile_dir.data(), tile_dir.size(), s));
   GRMP_TRY(d_nodeids.upload(tile_nodeids.data(), tile_nodeids.size(), s));
+  out->prof.release();
+  if (getenv("GRMP_FAST_PROF")) {
+    GRMP_TRY(out->prof.alloc(8 * 1024));
+    GRMP_CUDA(cudaMemsetAsync(out->prof.p, 0, out->prof.bytes(), s));
+  }
   GRMP_TRY(out->tile_counter.alloc(1));
   GRMP_CUDA(cudaMemsetAsync(out->tile_counter.p, 0, sizeof(int), s));
   lap("tile tables upload");
@@ -1089,11 +1114,12 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   return GRMP_OK;
 }
 
-template <int NW> int launch_edge(const EdgeParams& ep, const FastP2Tet& f, int sm_count, cudaStream_t s) {
+template <int NW> int launch_edge(const EdgeParams& ep, FastP2Tet& f, int sm_count, cudaStream_t s) {
   int per_sm = 0;
   GRMP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p2tet_edge_kernel<NW>, (NW + NSVC) * 32, (size_t)f.smem_bytes));
   if (per_sm < 1) return fail(GRMP_ECUDA, "fast path: edge kernel does not fit on an SM");
-  const int grid = std::min(f.ntiles, per_sm * sm_count);
+  const int grid = std::min(std::min(f.ntiles, per_sm * sm_count), 1024);
+  f.grid = grid;
   p2tet_edge_kernel<NW><<<grid, (NW + NSVC) * 32, f.smem_bytes, s>>>(ep);
   return GRMP_OK;
 }
@@ -1106,7 +1132,7 @@ int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pa
     f.geom_version = geom_version;
   }
   if (f.ntiles > 0) {
-    EdgeParams ep{f.tile_dir.p, f.blob.p, f.end_slots.p, p.factor, nzval, f.tile_counter.p, f.ntiles, f.in_stride, f.slot_elems, f.nbuf, dbg};
+    EdgeParams ep{f.tile_dir.p, f.blob.p, f.end_slots.p, p.factor, nzval, f.tile_counter.p, f.ntiles, f.in_stride, f.slot_elems, f.nbuf, f.prof.p, dbg};
     switch (f.nw) {
       case 3: GRMP_TRY(launch_edge<3>(ep, f, ctx->sm_count, ctx->stream)); break;
       case 4: GRMP_TRY(launch_edge<4>(ep, f, ctx->sm_count, ctx->stream)); break;
@@ -1122,6 +1148,18 @@ int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pa
   } else if (f.ntiles > 0) {
     GRMP_CUDA(cudaMemsetAsync(f.tile_counter.p, 0, sizeof(int), ctx->stream));
   }
+  return GRMP_OK;
+}
+
+int fast_p2tet_print_prof(grmp_ctx* ctx, const FastP2Tet& f) {
+  if (!f.prof.p || f.grid < 1) return GRMP_OK;
+  std::vector<unsigned long long> h(f.prof.n);
+  GRMP_CUDA(cudaStreamSynchronize(ctx->stream));
+  GRMP_CUDA(cudaMemcpy(h.data(), f.prof.p, f.prof.bytes(), cudaMemcpyDeviceToHost));
+  double m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int c = 0; c < f.grid; c++) for (int k = 0; k < 8; k++) m[k] += (double)h[8 * (size_t)c + k] / f.grid;
+  fprintf(stderr, "[grmp fast prof] per CTA (mean cycles): service warp wait-done %.0f  mirror write-out %.0f  total %.0f | consumer warp 0 "
+                  "wait-full %.0f  total %.0f | tiles %.1f\n", m[0], m[1], m[2], m[3], m[4], m[7]);
   return GRMP_OK;
 }
 
