@@ -199,7 +199,7 @@ static int blf_numeric_launch(grmp_blf* b, BlfLocalParams& p, cudaStream_t s) {
       GRMP_CUDA(cudaMemsetAsync(b->nzval.p + b->halo_first_slot, 0, (size_t)(b->pat.nnz - b->halo_first_slot) * 8, s));
   } else if (b->path == GRMP_PATH_COLUMNS) {
     GRMP_TRY(colpath_numeric(ctx, p, b->pat, b->colp, b->nzval.p));
-    b->st.kernel_launches = (i64)b->colp.classes.size();        // one launch per tile class
+    b->st.kernel_launches = 1 + (i64)b->colp.classes.size();    // geometry records + one launch per tile class
   } else if (b->path == GRMP_PATH_ATOMIC || b->path == GRMP_PATH_COLOURED) {
     i64 nl = 0;
     GRMP_TRY(cellpath_numeric(ctx, p, b->pat, b->colp, b->path == GRMP_PATH_ATOMIC ? 0 : 1, b->nzval.p, &nl));

@@ -11,9 +11,12 @@
 // dofs that are numbered far apart but live on the same cells (vertices of a refined grid) share the geometry cache.
 //
 // Data a CTA (tile = NW groups of 32 columns) touches:
-//   * the distinct cells of the tile: geometry is evaluated ONCE per tile cell (update_trafo!/mapderiv!,
-//     feevaluator.jl:371-390, plus face signs / normals) into a shared-memory cache by all threads of the CTA;
-//   * pair records (16/32/48 B): tile-local cell, local function of the column, and for every local row its slot inside
+//   * per-cell geometry records (update_trafo!/mapderiv!, feevaluator.jl:371-390, plus face signs / normals), evaluated ONCE
+//     per cell and assembly by cell_geo_kernel into a global array that the column threads read through L1/L2 (every cell is
+//     read by its nd columns; the locality order keeps those reads close in time).  Up to round 2 the geometry was rebuilt per
+//     tile into a shared-memory cache: a five-deep chain of dependent global loads and a CTA barrier in front of ~3 rounds of
+//     work per thread -- a third of the kernel's time (profiles/r2_col_kernels_ncu.md);
+//   * pair records (16/32/48 B): cell (24 bit), local function of the column, and for every local row its slot inside
 //     the column (255: the entry is not in the pattern -- _addnz skipped it, fematrix.jl:54-58).  Records of a group are
 //     stored ROUND-major (pair k of all 32 columns, then pair k+1, ...) so every round is one coalesced load;
 //   * the column function's reference table in shared memory (lane-varying index), the row table in constant memory
@@ -41,8 +44,7 @@ struct ColParams {
   const unsigned char* pos_len;    //   stored entries
   const i64* pos_start;            //   first nzval slot of the column (0-based)
   const i64* pos_recbeg;           //   first record (exclusive scan of pos_np); groups start at multiples of 32
-  const u32* tile_cellptr;
-  const u32* tile_cells;
+  const double* geo;        // [ncells][STRIDE] geometry records of this assembly (cell_geo_kernel)
   const u32* tile_list;     // tiles of this launch (one class)
   const double* tabC;
   double factor;
@@ -53,6 +55,21 @@ struct ColParams {
 };
 
 template <int NV> __device__ __forceinline__ u32 rec_byte(const u32 (&w)[NV * 4], int i) { return (w[i >> 2] >> (8 * (i & 3))) & 255u; }
+
+// geometry record of every cell: [0] CellVolumes, then the row / column evaluator's data (CacheLayout)
+template <class RowEv, class ColEv>
+__global__ void __launch_bounds__(256) cell_geo_kernel(const GridView g, double* __restrict__ geo) {
+  using L = CacheLayout<RowEv, ColEv>;
+  const i64 cell = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (cell >= g.ncells) return;
+  double cr[L::STRIDE];
+#pragma unroll
+  for (int i = 0; i < L::STRIDE; i++) cr[i] = 0.0;
+  build_cell_cache<RowEv, ColEv>(g, cell, 1.0, cr);
+  double2* dst = reinterpret_cast<double2*>(geo + cell * L::STRIDE);
+#pragma unroll
+  for (int i = 0; i < L::STRIDE / 2; i++) dst[i] = make_double2(cr[2 * i], cr[2 * i + 1]);
+}
 
 template <class RowEv, class ColEv, int ACT, int NV, int NQ>
 __global__ void __launch_bounds__(256) col_kernel(const ColParams p) {
@@ -65,29 +82,18 @@ __global__ void __launch_bounds__(256) col_kernel(const ColParams p) {
   constexpr int ntab = ColEv::NAS * nq * CT_PAD;
   __shared__ u32 s_maxlen[8];
   double* const sCt = sm;
-  double* const cache = sm + ((ntab + 1) & ~1);
+  double* const img = sm + ((ntab + 1) & ~1);
   const i64 tile = p.tile_list[blockIdx.x];
-  const u32 c0 = p.tile_cellptr[tile], nct = p.tile_cellptr[tile + 1] - c0;
   const i64 grp = tile * p.nw + warp;
   const i64 pos = grp * 32 + lane;
   const bool has = grp < p.ngroups && pos < p.ncols_used;
   const u32 np = has ? p.pos_np[pos] : 0u;
   const u32 len = has ? p.pos_len[pos] : 0u;
+  const i64 recbase = grp < p.ngroups ? p.pos_recbeg[grp * 32] : 0;
+  double* const dst = p.nzval + (has ? p.pos_start[pos] : 0);
   const u32 maxlen = __reduce_max_sync(0xffffffffu, len);
   if (lane == 0) s_maxlen[warp] = maxlen;
   for (int i = tid; i < ntab; i += nthr) sCt[i] = p.tabC[i];
-  // geometry cache of the tile: update_trafo! / mapderiv! / coefficient data once per tile cell.  (A separate per-cell pre-pass
-  // whose records are copied here was measured: the extra round trip through memory costs more than the ~2x redundant
-  // evaluation saves -- BR x P0 0.45 -> 0.24, RT0 0.18 -> 0.14, BDM1 0.23 -> 0.24 of the roofline.)
-  for (u32 t = tid; t < nct; t += nthr) build_cell_cache<RowEv, ColEv>(p.g, (i64)p.tile_cells[c0 + t], 1.0, cache + (size_t)t * L::STRIDE);
-  __syncthreads();
-  if (grp >= p.ngroups) return;
-  u32 acc_off = 0;
-  for (int w2 = 0; w2 < warp; w2++) acc_off += s_maxlen[w2] + 1u;     // + 1: trash row of every warp (entries that are not in the pattern)
-  // image of the warp's 32 columns: slot k of lane l at [k][l] -> every warp access touches 32 consecutive doubles
-  double* const a = cache + (size_t)nct * L::STRIDE + (size_t)acc_off * 32 + lane;
-  const i64 recbase = p.pos_recbeg[grp * 32];
-  for (u32 k = 0; k < maxlen; k++) a[k * 32] = 0.0;
   const u32 maxnp = __reduce_max_sync(0xffffffffu, np);
   const u32 lt = (1u << lane) - 1u;
   u32 rbase = 0;
@@ -97,20 +103,37 @@ __global__ void __launch_bounds__(256) col_kernel(const ColParams p) {
     rbase += __popc(bal);
     return idx;
   };
+  // record and geometry of round 0 are in flight while the table is staged
   uint4 rn[NV];                            // record of the next round (prefetched one round ahead)
   {
     const u32 i0 = next_idx(0);
 #pragma unroll
-    for (int v = 0; v < NV; v++) rn[v] = make_uint4(0x00ff0000u, 0, 0, 0);
+    for (int v = 0; v < NV; v++) rn[v] = make_uint4(0xff000000u, 0, 0, 0);
     if (0 < np) {
 #pragma unroll
       for (int v = 0; v < NV; v++) rn[v] = __ldg(p.recs + (size_t)(recbase + i0) * NV + v);
     }
   }
+  __syncthreads();
+  if (grp >= p.ngroups) return;
+  u32 acc_off = 0;
+  for (int w2 = 0; w2 < warp; w2++) acc_off += s_maxlen[w2] + 1u;     // + 1: trash row of every warp (entries that are not in the pattern)
+  // image of the warp's 32 columns: slot k of lane l at [k][l] -> every warp access touches 32 consecutive doubles
+  double* const a = img + (size_t)acc_off * 32 + lane;
+  for (u32 k = 0; k < maxlen; k++) a[k * 32] = 0.0;
   for (u32 k = 0; k < maxnp; k++) {
     u32 w[NV * 4];
 #pragma unroll
     for (int v = 0; v < NV; v++) { w[4 * v] = rn[v].x; w[4 * v + 1] = rn[v].y; w[4 * v + 2] = rn[v].z; w[4 * v + 3] = rn[v].w; }
+    const u32 lc = w[0] >> 24;
+    const bool work = k < np && lc != 255u;
+    // geometry record of this round's cell: 16-byte loads, issued before the next record is requested
+    double cr[L::STRIDE];
+    if (work) {
+      const double2* src = reinterpret_cast<const double2*>(p.geo + (size_t)(w[0] & 0xffffffu) * L::STRIDE);
+#pragma unroll
+      for (int i = 0; i < L::STRIDE / 2; i++) { const double2 t = __ldg(src + i); cr[2 * i] = t.x; cr[2 * i + 1] = t.y; }
+    }
     {
       const u32 i1 = next_idx(k + 1);
       if (k + 1 < np) {
@@ -118,9 +141,7 @@ __global__ void __launch_bounds__(256) col_kernel(const ColParams p) {
         for (int v = 0; v < NV; v++) rn[v] = __ldg(p.recs + (size_t)(recbase + i1) * NV + v);
       }
     }
-    const u32 lc = (w[0] >> 16) & 255u;
-    if (k < np && lc != 255u) {
-      const double* cr = cache + (size_t)(w[0] & 0xffffu) * L::STRIDE;
+    if (work) {
       const double s = cr[0] * p.factor;
       typename RowEv::Regs RR;
       typename ColEv::Regs RC;
@@ -151,7 +172,6 @@ __global__ void __launch_bounds__(256) col_kernel(const ColParams p) {
   }
   // write-out: every lane streams its own column; 32-byte stores cover whole sectors, the unaligned ends go element-wise
   if (maxlen == 0) return;
-  double* const dst = p.nzval + (has ? p.pos_start[pos] : 0);
   u32 head = (4u - (u32)(((size_t)dst >> 3) & 3u)) & 3u;
   if (head > len) head = len;
 #pragma unroll
@@ -180,7 +200,6 @@ struct PackParams {
   const i64* pos_recbeg;                       // position -> first record
   const i32* dofsR; int ndR;                   // CellDofs of the row space
   const i32* orient; const i32* regions; RegionFilter reg;
-  const u32* tile_cellptr; const u32* tile_cells;
   i64 ncells, ncols_used;
   int nrow;            // rows of the kernel's row loop (reference functions for BDM1 3D)
   int row_bdm3, col_bdm3;   // BDM1 3D: local dof <-> reference function through CellFaceOrientations (hdiv_bdm1.jl:313-328)
@@ -247,12 +266,11 @@ __global__ void tile_ptr(const u64* uniq, i64 n, i64 ntiles, u32* tile_cellptr, 
   tile_cellptr[t] = (u32)b;
   if (t < ntiles) atomicMax(max_cells, (int)(lb((u64)(t + 1) << 32) - b));
 }
-// shared-memory doubles a tile needs: column table + cell cache + the interleaved images of its groups
-__global__ void tile_need(const u32* tile_cellptr, const unsigned char* pos_len, i64 ntiles, i64 ncols_used, int nw, int ntab_even, int stride,
-                          int* need) {
+// shared-memory doubles a tile needs: column table + the interleaved images of its groups
+__global__ void tile_need(const unsigned char* pos_len, i64 ntiles, i64 ncols_used, int nw, int ntab_even, int* need) {
   const i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (t >= ntiles) return;
-  i64 n = ntab_even + (i64)(tile_cellptr[t + 1] - tile_cellptr[t]) * stride;
+  i64 n = ntab_even;
   for (int w = 0; w < nw; w++) {
     const i64 p0 = min((t * nw + w) * 32, ncols_used), p1 = min(p0 + 32, ncols_used);
     int mx = 0;
@@ -276,8 +294,6 @@ __global__ void pack_records(PackParams p) {
   const i64 kb = has ? p.pairbeg[j] : 0;
   const u32 np = has ? (u32)(p.pairbeg[j + 1] - kb) : 0u;
   const i64 recbase = p.pos_recbeg[grp * 32];
-  const i64 tile = grp / p.nw;
-  const u32 tc0 = p.tile_cellptr[tile], tc1 = p.tile_cellptr[tile + 1];
   const i64 cb = has ? p.colptr[j] - 1 : 0, ce = has ? p.colptr[j + 1] - 1 : 0;
   const u32 maxnp = __reduce_max_sync(0xffffffffu, np);
   const u32 lt = (1u << lane) - 1u;
@@ -295,12 +311,9 @@ __global__ void pack_records(PackParams p) {
       if (p.regions) for (int r = 0; r < p.reg.n; r++) active = active || p.regions[cell] == p.reg.r[r];
     }
     if (p.col_bdm3) lc = bdm3_ref_of_local(p.orient + cell * 4, lc);
-    u32 lo = tc0, hi = tc1;
-    while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (p.tile_cells[mid] < (u32)cell) lo = mid + 1; else hi = mid; }
-    if (lo >= tc1 || p.tile_cells[lo] != (u32)cell || lo - tc0 > 65535u) atomicExch(p.err, 2);
     u32 w[12];
     for (int i = 0; i < 12; i++) w[i] = 0xffffffffu;
-    w[0] = (lo - tc0) | ((active ? (u32)lc : 255u) << 16) | 0xff000000u;
+    w[0] = (u32)cell | ((active ? (u32)lc : 255u) << 24);
     for (int r = 0; r < p.nrow; r++) {
       int l = r;
       if (p.row_bdm3) l = bdm3_local_of_ref(p.orient + cell * 4, r);
@@ -323,9 +336,11 @@ inline unsigned nblk(i64 n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 
 // ---- kernel table ----------------------------------------------------------------------------------------------------------
 typedef int (*LaunchFn)(const ColParams&, int nblocks, int nthreads, int smem, cudaStream_t);
+typedef int (*GeoFn)(const GridView&, double* geo, cudaStream_t);
 struct Variant {
   bool (*match)(const ColEvalDesc& row, const ColEvalDesc& col, int act, int nq);
   LaunchFn launch;
+  GeoFn geo;
   int (*cache_stride)();
   int nrow, nv, tabR_per_q, nas_c;
 };
@@ -343,12 +358,17 @@ template <class RowEv, class ColEv, int ACT, int NQ> struct VariantImpl {
     GRMP_CUDA(cudaGetLastError());
     return GRMP_OK;
   }
+  static int geo(const GridView& g, double* out, cudaStream_t s) {
+    cell_geo_kernel<RowEv, ColEv><<<(unsigned)((g.ncells + 255) / 256), 256, 0, s>>>(g, out);
+    GRMP_CUDA(cudaGetLastError());
+    return GRMP_OK;
+  }
   static int cache_stride() { return CacheLayout<RowEv, ColEv>::STRIDE; }
 };
 #define GRMP_UNPAREN(...) __VA_ARGS__
 #define GRMP_VARIANT(R, C, A, Q)                                                                                       \
   {&VariantImpl<GRMP_UNPAREN R, GRMP_UNPAREN C, A, Q>::match, &VariantImpl<GRMP_UNPAREN R, GRMP_UNPAREN C, A, Q>::launch, \
-   &VariantImpl<GRMP_UNPAREN R, GRMP_UNPAREN C, A, Q>::cache_stride, GRMP_UNPAREN R::NROW, VariantImpl<GRMP_UNPAREN R, GRMP_UNPAREN C, A, Q>::NV, \
+   &VariantImpl<GRMP_UNPAREN R, GRMP_UNPAREN C, A, Q>::geo, &VariantImpl<GRMP_UNPAREN R, GRMP_UNPAREN C, A, Q>::cache_stride, GRMP_UNPAREN R::NROW, VariantImpl<GRMP_UNPAREN R, GRMP_UNPAREN C, A, Q>::NV, \
    GRMP_UNPAREN R::NSF * GRMP_UNPAREN R::NAS, GRMP_UNPAREN C::NAS},
 const Variant VARIANTS[] = {GRMP_SQUARE_FORMS(GRMP_VARIANT) GRMP_RECT_FORMS(GRMP_VARIANT)};
 constexpr int NVARIANTS = sizeof(VARIANTS) / sizeof(VARIANTS[0]);
@@ -495,15 +515,11 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
     }
     if (dv.Current() != ci1.p) GRMP_CUDA(cudaMemcpyAsync(ci1.p, dv.Current(), (size_t)ncols_used * 4, cudaMemcpyDeviceToDevice, s));
   }
-  // (3) tiles: NW groups per CTA; inside a tile columns are ordered by length; distinct cells per tile; shrink the tile until
-  //     the shared-memory image fits
-  int nw = getenv("GRMP_COL_NW") ? atoi(getenv("GRMP_COL_NW")) : 4;
+  // (3) tiles: NW groups per CTA; inside a tile columns are ordered by length; shrink the tile until the shared-memory image fits
+  if (ncells > (i64)0x1000000) return fail(GRMP_EUNSUPPORTED, "column kernels: more than 2^24 cells on one device (24-bit cell ids in the records)");
+  int nw = getenv("GRMP_COL_NW") ? atoi(getenv("GRMP_COL_NW")) : 8;
   nw = std::max(1, std::min(nw, 8));
-  const int stride = V.cache_stride();
-  DevBuf<u64> keys, keys2, uniq;
-  DevBuf<i64> nuniq_d, np64;
-  GRMP_TRY(nuniq_d.alloc(1));
-  GRMP_TRY(keys.alloc(std::max<i64>(npairs_used, 1))); GRMP_TRY(keys2.alloc(std::max<i64>(npairs_used, 1))); GRMP_TRY(uniq.alloc(std::max<i64>(npairs_used, 1)));
+  DevBuf<i64> np64;
   GRMP_TRY(cp->colperm.alloc(ncols_used)); GRMP_TRY(cp->pos_np.alloc(ncols_used)); GRMP_TRY(cp->pos_len.alloc(ncols_used));
   GRMP_TRY(cp->pos_start.alloc(ncols_used)); GRMP_TRY(cp->pos_recbeg.alloc(ncols_used + 1)); GRMP_TRY(np64.alloc(ncols_used + 1));
   int hflags[4] = {0, 0, 0, 0};
@@ -531,26 +547,6 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
       if (tb > temp.n) GRMP_TRY(temp.alloc(tb));
       GRMP_CUDA(cub::DeviceScan::ExclusiveSum(temp.p, tb, np64.p, cp->pos_recbeg.p, ncols_used + 1, s));
     }
-    tile_keys<<<nblk(ncols_used), 256, 0, s>>>(cp->colperm.p, dg.segptr.p, cp->pos_recbeg.p, dg.gcell.p, ncols_used, cpt, keys.p);
-    GRMP_CUDA(cudaGetLastError());
-    int end_bit = 33;
-    while (end_bit < 64 && ((u64)ntiles >> (end_bit - 32)) != 0) end_bit++;
-    size_t tb = 0, tb2 = 0;
-    GRMP_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, keys.p, keys2.p, npairs_used, 0, end_bit, s));
-    GRMP_CUDA(cub::DeviceSelect::Unique(nullptr, tb2, keys2.p, uniq.p, nuniq_d.p, npairs_used, s));
-    if (std::max(tb, tb2) > temp.n) GRMP_TRY(temp.alloc(std::max(tb, tb2)));
-    GRMP_CUDA(cub::DeviceRadixSort::SortKeys(temp.p, tb, keys.p, keys2.p, npairs_used, 0, end_bit, s));
-    GRMP_CUDA(cub::DeviceSelect::Unique(temp.p, tb2, keys2.p, uniq.p, nuniq_d.p, npairs_used, s));
-    i64 nuniq = 0;
-    GRMP_CUDA(cudaMemcpyAsync(&nuniq, nuniq_d.p, 8, cudaMemcpyDeviceToHost, s));
-    GRMP_CUDA(cudaStreamSynchronize(s));
-    if (nuniq >= (i64)0xffffffffll) return fail(GRMP_EUNSUPPORTED, "column kernels: more than 2^32 tile cells");
-    GRMP_TRY(cp->tile_cellptr.alloc(ntiles + 1));
-    GRMP_TRY(cp->tile_cells.alloc(std::max<i64>(nuniq, 1)));
-    GRMP_CUDA(cudaMemsetAsync(flags.p + 2, 0, 4, s));
-    tile_ptr<<<nblk(ntiles + 1), 256, 0, s>>>(uniq.p, nuniq, ntiles, cp->tile_cellptr.p, flags.p + 2);
-    low32<<<nblk(nuniq), 256, 0, s>>>(uniq.p, nuniq, cp->tile_cells.p);
-    GRMP_CUDA(cudaGetLastError());
     GRMP_CUDA(cudaMemcpyAsync(hflags, flags.p, 16, cudaMemcpyDeviceToHost, s));
     GRMP_CUDA(cudaStreamSynchronize(s));
     if (hflags[0]) return fail(GRMP_EUNSUPPORTED, "column kernels: a column has more than 254 entries or 65535 cells");
@@ -558,15 +554,15 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
     const int ntab_even = (V.nas_c * nq * CT_PAD + 1) & ~1;
     DevBuf<int> need_d;
     GRMP_TRY(need_d.alloc(ntiles));
-    tile_need<<<nblk(ntiles), 256, 0, s>>>(cp->tile_cellptr.p, cp->pos_len.p, ntiles, ncols_used, nw, ntab_even, stride, need_d.p);
+    tile_need<<<nblk(ntiles), 256, 0, s>>>(cp->pos_len.p, ntiles, ncols_used, nw, ntab_even, need_d.p);
     GRMP_CUDA(cudaGetLastError());
     std::vector<int> need(ntiles);
     GRMP_CUDA(cudaMemcpyAsync(need.data(), need_d.p, (size_t)ntiles * 4, cudaMemcpyDeviceToHost, s));
     GRMP_CUDA(cudaStreamSynchronize(s));
     int need_max = 0;
     for (int n : need) need_max = std::max(need_max, n);
-    if (hflags[2] <= 65535 && (i64)need_max * 8 <= 200 * 1024) {
-      cp->nw = nw; cp->ntiles = ntiles; cp->max_tile_cells = hflags[2]; cp->smem_bytes = need_max * 8;
+    if ((i64)need_max * 8 <= 200 * 1024) {
+      cp->nw = nw; cp->ntiles = ntiles; cp->smem_bytes = need_max * 8;
       // classes: capacities that let 16 / 8 / 4 / 2 / 1 CTAs share an SM (227 KB usable, 1 KB reserved per CTA)
       const int caps[6] = {6 * 1024, 13 * 1024, 27 * 1024, 55 * 1024, 112 * 1024, 200 * 1024};
       std::vector<std::vector<u32>> lists(6);
@@ -590,14 +586,15 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
     }
     if (nw == 1) return fail(GRMP_EUNSUPPORTED, "column kernels: one group of 32 columns does not fit into shared memory");
   }
-  keys.release(); keys2.release(); uniq.release(); temp.release(); ck1.release(); ck2.release(); ci1.release(); ci2.release(); np64.release();
+  temp.release(); ck1.release(); ck2.release(); ci1.release(); ci2.release(); np64.release();
+  GRMP_TRY(cp->geo.alloc((size_t)ncells * V.cache_stride()));
   // (4) records
   GRMP_TRY(cp->recs.alloc((size_t)std::max<i64>(npairs_used, 1) * cp->nv));
   PackParams pp{};
   pp.colptr = pat.colptr.p; pp.rowval = pat.rowval.p; pp.pairbeg = dg.segptr.p; pp.gcell = dg.gcell.p; pp.gsrc = dg.gsrc.p;
   pp.colperm = cp->colperm.p; pp.pos_recbeg = cp->pos_recbeg.p;
   pp.dofsR = er.celldofs; pp.ndR = er.nd; pp.orient = p.g.orient; pp.regions = p.g.regions; pp.reg = p.reg;
-  pp.tile_cellptr = cp->tile_cellptr.p; pp.tile_cells = cp->tile_cells.p; pp.ncells = ncells; pp.ncols_used = ncols_used;
+  pp.ncells = ncells; pp.ncols_used = ncols_used;
   pp.nrow = V.nrow; pp.row_bdm3 = (cp->row.kind == 1 && cp->row.nds == 16); pp.col_bdm3 = (cp->col.kind == 1 && cp->col.nds == 16);
   pp.nw = cp->nw; pp.nv = cp->nv; pp.recs = cp->recs.p; pp.err = flags.p;
   pack_records<<<nblk(cp->ngroups * 32, 128), 128, 0, s>>>(pp);
@@ -607,8 +604,8 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
   if (hflags[0]) return fail(GRMP_EUNSUPPORTED, "column kernels: record build failed");
   if (getenv("GRMP_VERBOSE"))
   {
-    fprintf(stderr, "[grmp columns] variant %d nw %d tiles %lld pairs %lld tile cells %lld (max %d per tile) record %d B; classes:", cp->variant,
-            cp->nw, (long long)cp->ntiles, (long long)cp->npairs, (long long)cp->tile_cells.n, cp->max_tile_cells, 16 * cp->nv);
+    fprintf(stderr, "[grmp columns] variant %d nw %d tiles %lld pairs %lld geometry record %d B pair record %d B; classes:", cp->variant,
+            cp->nw, (long long)cp->ntiles, (long long)cp->npairs, 8 * V.cache_stride(), 16 * cp->nv);
     for (auto& c : cp->classes) fprintf(stderr, " %lld tiles <= %d B;", (long long)c.count, c.smem_bytes);
     fprintf(stderr, "\n");
   }
@@ -629,9 +626,10 @@ int colpath_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, 
   }
   ColParams cpar{};
   cpar.g = p.g; cpar.recs = cp.recs.p; cpar.pos_np = cp.pos_np.p; cpar.pos_len = cp.pos_len.p; cpar.pos_start = cp.pos_start.p;
-  cpar.pos_recbeg = cp.pos_recbeg.p; cpar.tile_cellptr = cp.tile_cellptr.p; cpar.tile_cells = cp.tile_cells.p; cpar.tabC = cp.tabC.p;
+  cpar.pos_recbeg = cp.pos_recbeg.p; cpar.geo = cp.geo.p; cpar.tabC = cp.tabC.p;
   cpar.factor = p.factor; cpar.act_p[0] = p.act_p[0]; cpar.act_p[1] = p.act_p[1]; cpar.nzval = nzval;
   cpar.ncols_used = cp.ncols_used; cpar.ngroups = cp.ngroups; cpar.nw = cp.nw; cpar.nq = cp.nq;
+  GRMP_TRY(V.geo(p.g, cp.geo.p, s));     // update_trafo! / mapderiv! / coefficient data of every cell, once per assembly
   for (const auto& c : cp.classes) {     // big tiles first: they have the fewest CTAs per SM and would otherwise be the tail
     cpar.tile_list = cp.class_tiles.p + c.first;
     GRMP_TRY(V.launch(cpar, (int)c.count, 32 * cp.nw, c.smem_bytes, s));

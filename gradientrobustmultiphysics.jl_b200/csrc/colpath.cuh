@@ -24,7 +24,7 @@ struct ColPath {
   bool built = false;
   u64 uid = 0;                     // identifies whose tables sit in constant memory
   int variant = 0;                 // index into the kernel table (colpath.cu)
-  int nw = 4;                      // warps (= groups of 32 columns) per CTA / tile
+  int nw = 8;                      // warps (= groups of 32 columns) per CTA / tile
   int nv = 1;                      // 16-byte vectors per pair record
   int nq = 0;
   i64 ncols_used = 0, ngroups = 0, ntiles = 0, npairs = 0;
@@ -43,8 +43,7 @@ struct ColPath {
   DevBuf<unsigned char> pos_len;   //   stored entries of the column
   DevBuf<i64> pos_start;           //   first nzval slot of the column (0-based)
   DevBuf<i64> pos_recbeg;          // [ncols_used+1] first record of every position (groups start at multiples of 32)
-  DevBuf<u32> tile_cellptr;        // [ntiles+1]
-  DevBuf<u32> tile_cells;          // distinct cells of every tile (0-based)
+  DevBuf<double> geo;              // [ncells][stride] per-cell geometry records, rewritten by every numeric call
   DevBuf<double> tabC;             // column-function table [a][q][16]
   std::vector<double> tabR;        // row table [s][a][q] -> constant memory at launch
   std::vector<double> wq;

@@ -398,14 +398,19 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
     int b = 0, use = 0;                                       // buffer of iteration it, how often it has been filled before
     long long c_wait = 0, c_wo = 0;
     const long long c_start = clock64();
+    // tiles are claimed dynamically (SMs do not run at the same speed, a static split leaves the slowest SM as the tail) and ONE
+    // ITERATION AHEAD: under a saturated memory system the atomic and the directory lookup behind it take ~3000 cycles, which
+    // used to sit between the write-out and the next bulk load (GRMP_FAST_PROF: 38 % of the service warp's time, consumers
+    // waiting 23 % of theirs).  Now both are in flight while the warp waits for the consumers and writes the mirrors out.
+    int t_cur = 0;
+    uint2 dir_cur = make_uint2(0, 0);
+    if (slane == 0) {
+      t_cur = atomicAdd(p.tile_counter, 1);
+      if (t_cur < p.ntiles) dir_cur = __ldg(p.tile_dir + t_cur);
+    }
     for (;; it++) {
-      int t = 0;
-      uint2 dir = make_uint2(0, 0);
-      if (slane == 0) {
-        // tiles are claimed dynamically: SMs do not run at the same speed, a static split leaves the slowest SM as the tail
-        t = atomicAdd(p.tile_counter, 1);
-        if (t < p.ntiles) dir = __ldg(p.tile_dir + t);
-      }
+      int t_nxt = 0;
+      if (slane == 0) t_nxt = atomicAdd(p.tile_counter, 1);    // not consumed before the end of the iteration
       if (use >= 1) {
         const long long c0 = clock64();
         mbar_wait(done_a + 8 * b, (unsigned)(use - 1) & 1u);   // all consumer warps have left the tile in this buffer
@@ -414,10 +419,16 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // parked values (generic writes) before the next bulk load
         c_wait += c1 - c0; c_wo += clock64() - c1;
       }
-      if (slane == 0) s_next = t;
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * NSVC) : "memory");     // write-out finished by all service warps; s_next visible
-      t = *reinterpret_cast<volatile int*>(&s_next);
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * NSVC) : "memory");     // everybody has read s_next
+      int t;
+      if (NSVC == 1) {
+        __syncwarp();                                                   // the write-out of all lanes is ordered before the bulk load
+        t = __shfl_sync(0xffffffffu, t_cur, 0);
+      } else {
+        if (slane == 0) s_next = t_cur;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * NSVC) : "memory");     // write-out finished by all service warps; s_next visible
+        t = *reinterpret_cast<volatile int*>(&s_next);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * NSVC) : "memory");     // everybody has read s_next
+      }
       if (t >= p.ntiles) {
         if (slane == 0) {
           s_tile[b] = -1;
@@ -427,7 +438,10 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
       }
       if (slane == 0) {
         s_tile[b] = t;
-        tile_load(p, dir, in_a + b * p.in_stride, full_a + 8 * b, pol_stream);
+        tile_load(p, dir_cur, in_a + b * p.in_stride, full_a + 8 * b, pol_stream);
+        t_cur = t_nxt;
+        dir_cur = make_uint2(0, 0);
+        if (t_cur < p.ntiles) dir_cur = __ldg(p.tile_dir + t_cur);     // consumed at the next bulk load
       }
       if (++b == NB) { b = 0; use++; }
     }

@@ -1,16 +1,21 @@
 # GRMPCuda.jl -- Julia glue that puts libgrmp_cuda behind the unchanged
 # GradientRobustMultiPhysics.jl API (PDEDescription / add_operator! / assemble! / solve!).
 #
-# NOT RUNNABLE IN THE BUILD CONTAINER (no julia binary, no network).  It is kept tiny and
-# mechanical: every `ccall` below has a line-for-line ctypes twin in
-# gradientrobustmultiphysics.jl_b200/_lib.py + assembly.py, which is what the test-suite runs.
+# NOT RUNNABLE IN THE BUILD CONTAINER (no julia binary, no network).  It is kept mechanical: every `ccall`
+# below has a line-for-line ctypes twin in gradientrobustmultiphysics.jl_b200/_lib.py + assembly.py, which is
+# what the test-suite runs.
 #
-# How it hooks in: it adds *more specific* methods of
-#     assemble!(A::FEMatrixBlock, AP::AssemblyPattern{<:APT_BilinearForm,Float64,ON_CELLS}, FEB; ...)
-#     assemble!(b::FEVectorBlock, AP::AssemblyPattern{APT_LinearForm,Float64,ON_CELLS}, FEB; ...)
-# (reference: src/assemblypatterns/bilinearform.jl:384-400, src/assemblypatterns/linearform.jl:239-251)
-# for the (FEType, operator, action) triples the library supports, and throws for anything else
-# it is asked to handle explicitly -- not loading this file leaves the reference untouched.
+# How it hooks in.  The reference assembles through
+#     assemble!(A::AbstractArray{T,2}, AP::AssemblyPattern{<:APT_BilinearForm,T,AT,Tv,Ti}, FEB = []; ...)   bilinearform.jl:92-103
+#     assemble!(b::Union{AbstractArray{T,1},AbstractArray{T,2}}, AP::AssemblyPattern{<:APT_LinearForm,...}, FEB = []; ...)   linearform.jl:47-54
+# and `assemble_operator!` (pdeoperators.jl:978-1006) calls them WITHOUT the FEB argument for every operator that has no
+# fixed arguments.  This file adds the two-argument methods
+#     assemble!(A::FEMatrixBlock{Float64,Int64,Float64,Int32}, AP::AssemblyPattern{<:APT_BilinearForm,Float64,ON_CELLS,Float64,Int32}; ...)
+#     assemble!(b::FEVectorBlock{Float64,Float64,Int32},       AP::AssemblyPattern{<:APT_LinearForm,Float64,ON_CELLS,Float64,Int32}; ...)
+# which are more specific than the reference's, so PDEDescription / add_operator! / solve! reach them unchanged.  Calls WITH
+# coefficient arguments (FEB, row N4 of SURVEY.md 8f) never dispatch here.  Inside, `blf_plan` / `lf_plan` decide whether the
+# (FEType, operator, action) triple is on the device path; everything else is handed back to the reference method with
+# `invoke` and ALL keyword arguments -- the library itself has no CPU fallback, the reference loop simply stays reachable.
 module GRMPCuda
 
 using GradientRobustMultiPhysics
@@ -27,14 +32,17 @@ struct GrmpError <: Exception
 end
 check(rc::Cint) = rc == 0 ? nothing : throw(GrmpError(rc, unsafe_string(ccall((:grmp_last_error, lib), Cstring, ()))))
 
-# ---- codes of include/grmp.h ---------------------------------------------------------------
+# ---- codes of include/grmp.h (nothing = not on the device path) -----------------------------------------------------
+fecode(::Type) = nothing
 fecode(::Type{<:H1P1}) = 1
 fecode(::Type{<:H1P2}) = 2
-fecode(::Type{<:H1Pk{n,2,2}}) where {n} = 2     # same tables as H1P2 (DESIGN.md)
+fecode(::Type{<:H1Pk{n,2,2}}) where {n} = 2     # same tables as H1P2 (DESIGN.md 3.2)
+fecode(::Type{<:H1Pk{n,3,2}}) where {n} = 2
 fecode(::Type{<:H1BR}) = 3
 fecode(::Type{<:HDIVRT0}) = 4
 fecode(::Type{<:HDIVBDM1}) = 5
 fecode(::Type{<:L2P0}) = 6
+opcode(::Type) = nothing
 opcode(::Type{Identity}) = 1
 opcode(::Type{Gradient}) = 2
 opcode(::Type{SymmetricGradient{1}}) = 3
@@ -44,6 +52,7 @@ opcode(::Type{ReconstructionIdentity{FER}}) where {FER<:HDIVBDM1} = 6
 aptcode(::Type{GRMP.APT_BilinearForm}) = 0
 aptcode(::Type{GRMP.APT_SymmetricBilinearForm}) = 1
 aptcode(::Type{GRMP.APT_LumpedBilinearForm}) = 2
+const F_NONE, F_CONST, F_QP_TABLE = 0, 1, 2
 
 struct EvalTab
     nd_all::Int32
@@ -52,39 +61,54 @@ struct EvalTab
     refderivs::Ptr{Float64}
 end
 
-# ---- handles (finalizers call the *_destroy entry points) ------------------------------------
-mutable struct Ctx;   h::Ptr{Cvoid}; end
-mutable struct DGrid; h::Ptr{Cvoid}; hasfaces::Bool; end
-mutable struct DSpace; h::Ptr{Cvoid}; end
-mutable struct DBlf;  h::Ptr{Cvoid}; nnz::Int64; colptr::Vector{Int64}; rowval::Vector{Int64}; end
+# ---- handles: the library owns the memory, finalizers call the *_destroy entry points (grmp.h "Ownership") ------------------
+mutable struct Ctx;    h::Ptr{Cvoid}; device::Int; end
+mutable struct DGrid;  h::Ptr{Cvoid}; hasfaces::Bool; ctx::Ctx; end
+mutable struct DSpace; h::Ptr{Cvoid}; grid::DGrid; end
+mutable struct DBlf
+    h::Ptr{Cvoid}; nnz::Int64; colptr::Vector{Int64}; rowval::Vector{Int64}
+    factor::Float64; transposed::Bool; spaces::Tuple{DSpace,DSpace}
+end
+mutable struct DLf; h::Ptr{Cvoid}; space::DSpace; end
+destroy(sym::Symbol, x) = (x.h == C_NULL || ccall((sym, lib), Cint, (Ptr{Cvoid},), x.h); x.h = C_NULL; nothing)
 
-const CTX = Ref{Union{Nothing,Ctx}}(nothing)
-function context(device = 0)
-    if CTX[] === nothing
+# One context per device of THIS process (grmp_init(device, &ctx)).  A single Julia process reaches several GPUs by making
+# one of them current -- `GRMPCuda.device!(k)` -- before the grid of a subdomain is first assembled: every handle remembers
+# its context, so forms on different grids may live on different devices and be assembled from different tasks
+# (handles are independent, grmp.h "Threading"; ccall blocks only the calling task's thread).  Multi-GPU assembly of ONE grid
+# is one process per GPU (DESIGN.md 4): the partition is made on the host, every process runs this same glue on its part.
+const CONTEXTS = Dict{Int,Ctx}()
+const CURRENT_DEVICE = Ref(0)
+device!(k::Integer) = (CURRENT_DEVICE[] = Int(k); context(); nothing)
+function context(device::Int = CURRENT_DEVICE[])
+    get!(CONTEXTS, device) do
         h = Ref{Ptr{Cvoid}}()
         check(ccall((:grmp_init, lib), Cint, (Cint, Ref{Ptr{Cvoid}}), device, h))
-        CTX[] = Ctx(h[])
+        c = Ctx(h[], device)
+        finalizer(x -> destroy(:grmp_finalize, x), c)
+        c
     end
-    return CTX[]
 end
 
-const GRIDS = IdDict{Any,DGrid}()
+# caches are weak in the Julia object: a grid / space / pattern that is garbage-collected releases its device memory
+const GRIDS = WeakKeyDict{Any,DGrid}()
 function device_grid(xgrid::ExtendableGrid{Float64,Int32}; faces = false)
     g = get!(GRIDS, xgrid) do
-        coords = xgrid[Coordinates]; cn = xgrid[CellNodes]::Matrix{Int32}
-        vol = xgrid[CellVolumes]; reg = Vector{Int32}(xgrid[CellRegions])
+        coords = xgrid[Coordinates]; cn = Matrix{Int32}(xgrid[CellNodes])
+        vol = Vector{Float64}(xgrid[CellVolumes]); reg = Vector{Int32}(xgrid[CellRegions])
         h = Ref{Ptr{Cvoid}}()
+        ctx = context()
         GC.@preserve coords cn vol reg check(ccall((:grmp_grid_create, lib), Cint,
             (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Ref{Ptr{Cvoid}}),
-            context().h, size(coords, 1), size(coords, 2), coords, size(cn, 2), cn, vol, reg, h))
-        d = DGrid(h[], false)
-        finalizer(x -> ccall((:grmp_grid_destroy, lib), Cint, (Ptr{Cvoid},), x.h), d)
+            ctx.h, size(coords, 1), size(coords, 2), coords, size(cn, 2), cn, vol, reg, h))
+        d = DGrid(h[], false, ctx)
+        finalizer(x -> destroy(:grmp_grid_destroy, x), d)
         d
     end
     if faces && !g.hasfaces
         cf = Matrix{Int32}(xgrid[CellFaces]); sg = Matrix{Int32}(xgrid[CellFaceSigns])
         ori = size(xgrid[Coordinates], 1) == 3 ? Matrix{Int32}(xgrid[CellFaceOrientations]) : Matrix{Int32}(undef, 0, 0)
-        fn = xgrid[FaceNormals]; fv = xgrid[FaceVolumes]
+        fn = Matrix{Float64}(xgrid[FaceNormals]); fv = Vector{Float64}(xgrid[FaceVolumes])
         GC.@preserve cf sg ori fn fv check(ccall((:grmp_grid_set_faces, lib), Cint,
             (Ptr{Cvoid}, Int64, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
             g.h, length(fv), cf, sg, isempty(ori) ? C_NULL : pointer(ori), fn, fv))
@@ -93,74 +117,152 @@ function device_grid(xgrid::ExtendableGrid{Float64,Int32}; faces = false)
     return g
 end
 
-const SPACES = IdDict{Any,DSpace}()
+"`update_geometry!(xgrid)`: the coordinates of a grid moved in place (same topology) -- re-upload Coordinates / CellVolumes"
+function update_geometry!(xgrid::ExtendableGrid{Float64,Int32})
+    haskey(GRIDS, xgrid) || return nothing
+    coords = xgrid[Coordinates]; vol = Vector{Float64}(xgrid[CellVolumes])
+    GC.@preserve coords vol check(ccall((:grmp_grid_update_geometry, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), GRIDS[xgrid].h, coords, vol))
+end
+
+const SPACES = WeakKeyDict{Any,DSpace}()
 function device_space(FES::FESpace{Float64,Int32,FEType}) where {FEType}
     get!(SPACES, FES) do
         g = device_grid(FES.xgrid; faces = FEType <: Union{H1BR,HDIVRT0,HDIVBDM1})
         dofs = FES[CellDofs]
-        colentries = dofs isa GRMP.SerialVariableTargetAdjacency ?
-            Int32.(reshape(1:FES.ndofs, :, num_sources(FES.xgrid[CellNodes]))) : Matrix{Int32}(reshape(dofs.colentries, :, num_sources(dofs)))
+        ncells = num_sources(FES.xgrid[CellNodes])
+        # broken spaces (always L2P0, finiteelements.jl:78-80) carry a SerialVariableTargetAdjacency: dofs of cell c are (c-1) nd + 1 : c nd
+        colentries = dofs isa GRMP.SerialVariableTargetAdjacency ? Matrix{Int32}(reshape(Int32(1):Int32(FES.ndofs), :, ncells)) :
+                     Matrix{Int32}(reshape(dofs.colentries, :, ncells))
         h = Ref{Ptr{Cvoid}}()
         GC.@preserve colentries check(ccall((:grmp_space_create, lib), Cint,
             (Ptr{Cvoid}, Cint, Cint, Int64, Cint, Ptr{Int32}, Ref{Ptr{Cvoid}}),
             g.h, fecode(FEType), get_ncomponents(FEType), FES.ndofs, size(colentries, 1), colentries, h))
-        d = DSpace(h[])
-        finalizer(x -> ccall((:grmp_space_destroy, lib), Cint, (Ptr{Cvoid},), x.h), d)
+        d = DSpace(h[], g)
+        finalizer(x -> destroy(:grmp_space_destroy, x), d)
         d
     end
 end
 
-# tables straight out of the reference's FEEvaluator (ForwardDiff bits travel unchanged)
+# tables straight out of the reference's FEEvaluator (feevaluator.jl:34-138): ForwardDiff's bits travel unchanged
 function evaltab(ev)   # ev::GRMP.SingleFEEvaluator
-    nq = length(ev.xref)
-    vals = isempty(ev.refbasisvals) ? Float64[] : permutedims(cat(ev.refbasisvals...; dims = 3), (2, 1, 3))[:]  # [comp, dof, i] -> memory [i][dof][comp]
-    ders = ev.derivorder > 0 ? ev.refbasisderivvals[:] : Float64[]                                              # [row, j, i] column-major == [i][j][row]
+    vals = permutedims(cat(ev.refbasisvals...; dims = 3), (2, 1, 3))[:]     # refbasisvals[i][dof, comp] -> memory [i][dof][comp]
+    ders = ev.derivorder > 0 ? ev.refbasisderivvals[:] : Float64[]         # [dof + comp nd_all, j, i], column-major == [i][j][row]
     return vals, ders, EvalTab(size(ev.refbasisvals[1], 1), size(ev.refbasisvals[1], 2), pointer(vals), isempty(ders) ? C_NULL : pointer(ders))
 end
 
-const PATTERNS = IdDict{Any,DBlf}()
+# ---- what is on the device path -----------------------------------------------------------------------------------------
+"""
+    hooke_parameters(action) -> (actcode, [μ, λ]) or nothing
+
+The library evaluates `NoAction` and the constant isotropic Hooke tensors of HookStiffnessOperator2D/3D
+(pdeoperators.jl:256-273, 296-315).  Their kernels are closures over (μ, λ); instead of reaching into the closure the
+tensor is PROBED: C e_i for the unit vectors, and accepted only if it has exactly the Hooke structure
+(c11 = λ + 2μ, c12 = λ, c33/c44 = μ, zeros elsewhere) -- any other user Action returns `nothing` and stays on the reference path.
+"""
+function hooke_parameters(action)
+    action isa NoAction && return (0, Float64[])
+    action isa GRMP.DefaultUserAction || return nothing
+    (GRMP.is_xdependent(action) || GRMP.is_timedependent(action) || GRMP.is_itemdependent(action) || GRMP.is_xrefdependent(action)) && return nothing
+    n = action.argsizes[1]
+    (n == action.argsizes[2] && (n == 3 || n == 6)) || return nothing
+    C = zeros(n, n); r = zeros(n)
+    for i = 1:n
+        e = zeros(n); e[i] = 1
+        fill!(r, 0); action.kernel(r, e); C[:, i] = r
+    end
+    nd = n == 3 ? 2 : 3
+    μ, λ = C[n, n], C[1, 2]
+    for i = 1:n, j = 1:n
+        expect = i == j ? (i <= nd ? λ + 2μ : μ) : (i <= nd && j <= nd ? λ : 0.0)
+        C[i, j] == expect || return nothing
+    end
+    # linearity spot check (a kernel that is not a constant tensor must not pass)
+    x = collect(1.0:n); action.kernel(r, x)
+    maximum(abs.(r .- C * x)) <= 1e-12 * maximum(abs.(C)) * n || return nothing
+    return (n == 3 ? 1 : 2, Float64[μ, λ])
+end
+
+struct BlfPlan; act::Int; par::Vector{Float64}; ops::Tuple{Int,Int}; end
+function blf_plan(AP::AssemblyPattern{APT}) where {APT}
+    length(AP.FES) == 2 && length(AP.operators) == 2 || return nothing
+    AP.FES[1].xgrid === AP.FES[2].xgrid || return nothing
+    AP.FES[1].xgrid[UniqueCellGeometries] in ([Triangle2D], [Tetrahedron3D]) || return nothing
+    all(F -> fecode(eltype(F)) !== nothing && !F.broken || eltype(F) <: L2P0, AP.FES) || return nothing
+    o1, o2 = opcode(AP.operators[1]), opcode(AP.operators[2])
+    (o1 === nothing || o2 === nothing) && return nothing
+    hp = hooke_parameters(AP.action)
+    hp === nothing && return nothing
+    hp[1] != 0 && AP.apply_action_to != [1] && return nothing
+    return BlfPlan(hp[1], hp[2], (o1, o2))
+end
+
+# ---- BilinearForm -----------------------------------------------------------------------------------------------------
+# keyed by the pattern AND the output orientation; the factor of the symbolic pass is remembered: the reference's pattern is
+# value dependent (_addnz skips exact zeros, fematrix.jl:54-65), so a frozen pattern is reused only with skip_preps = true
+# (the reference's own contract for reassembly, solvers.jl:556) or when nothing that defines it changed.
+const PATTERNS = WeakKeyDict{Any,Dict{Bool,DBlf}}()
+
+function build_blf(A, AP::AssemblyPattern{APT}, plan::BlfPlan, factor, transposed_assembly) where {APT}
+    e1 = GRMP.get_basisevaler(AP.AM, 1, 1); e2 = GRMP.get_basisevaler(AP.AM, 2, 1)
+    v1, d1, t1 = evaltab(e1); v2, d2, t2 = evaltab(e2)
+    w = Vector{Float64}(GRMP.get_qweights(AP.AM))
+    par = plan.par
+    regions = AP.regions == [0] ? Int32[] : Vector{Int32}(AP.regions)
+    s1, s2 = device_space(AP.FES[1]), device_space(AP.FES[2])
+    h = Ref{Ptr{Cvoid}}()
+    GC.@preserve v1 d1 v2 d2 w par regions check(ccall((:grmp_blf_create, lib), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float64}, Cint, Cint, Ptr{Int32}, Cint, Cint, Ptr{Float64}, Ref{EvalTab}, Ref{EvalTab}, Ref{Ptr{Cvoid}}),
+        s1.h, s2.h, plan.ops[1], plan.ops[2], plan.act, isempty(par) ? C_NULL : pointer(par), aptcode(APT), transposed_assembly,
+        isempty(regions) ? C_NULL : pointer(regions), length(regions), length(w), w, t1, t2, h))
+    b = DBlf(h[], 0, Int64[], Int64[], Float64(factor), transposed_assembly, (s1, s2))
+    finalizer(x -> destroy(:grmp_blf_destroy, x), b)
+    symbolic!(b, A, factor)
+    return b
+end
+function symbolic!(b::DBlf, A, factor)
+    nnz = Ref{Int64}(0)
+    check(ccall((:grmp_blf_symbolic, lib), Cint, (Ptr{Cvoid}, Float64, Ref{Int64}), b.h, factor, nnz))
+    b.nnz = nnz[]; b.factor = factor
+    b.colptr = Vector{Int64}(undef, size(A, 2) + 1); b.rowval = Vector{Int64}(undef, nnz[])
+    check(ccall((:grmp_blf_get_pattern, lib), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), b.h, b.colptr, b.rowval))
+end
 
 """
-    assemble!(A::FEMatrixBlock, AP; factor, skip_preps, ...)   (device version)
+    assemble!(A::FEMatrixBlock, AP; factor, factor_transpose, skip_preps, transposed_assembly, transpose_copy)   (device version)
 
-First call: prepare_assembly! (host, unchanged), grmp_blf_create + grmp_blf_symbolic + pattern download.
-Every call: grmp_blf_numeric into a nzval buffer, then the block is installed / merged into
-`A.entries` (single-block matrices: `A.entries.cscmatrix = SparseMatrixCSC(m, n, colptr, rowval, nzval)`;
-otherwise `addblock!`-style merge through a temporary SparseMatrixCSC).
+skip_preps = false (first assembly, bilinearform.jl:104-107): prepare_assembly! on the host (unchanged), then the symbolic
+pass runs (again) with this `factor` -- grmp_blf_create once per (pattern, orientation), grmp_blf_symbolic + pattern download.
+skip_preps = true: numeric assembly on the frozen pattern (grmp_blf_numeric).  The block is then installed into `A.entries`
+(single-block matrix with an empty target: `A.entries.cscmatrix = SparseMatrixCSC(m, n, colptr, rowval, nzval)`; otherwise
+an addblock!-style merge), the transposed copy likewise.
 """
-function GRMP.assemble!(A::FEMatrixBlock{Float64,Int64,Float64,Int32}, AP::AssemblyPattern{APT,Float64,ON_CELLS}, FEB = [];
+function GRMP.assemble!(A::FEMatrixBlock{Float64,Int64,Float64,Int32}, AP::AssemblyPattern{APT,Float64,ON_CELLS,Float64,Int32};
         factor = 1, factor_transpose = factor, skip_preps::Bool = false, fixed_arguments = nothing,
         transposed_assembly::Bool = false, transpose_copy = nothing) where {APT<:GRMP.APT_BilinearForm}
-    length(FEB) == 0 || return invoke(GRMP.assemble!, Tuple{FEMatrixBlock,AssemblyPattern,Any}, A, AP, FEB; factor, skip_preps)  # 'next' row N4
+    plan = blf_plan(AP)
+    if plan === nothing || !(transpose_copy === nothing || transpose_copy isa FEMatrixBlock{Float64,Int64,Float64,Int32})
+        # not on the device path: the reference's own loop, all keywords forwarded
+        return invoke(GRMP.assemble!, Tuple{AbstractArray{Float64,2},AssemblyPattern{APT,Float64,ON_CELLS,Float64,Int32}}, A, AP;
+                      factor, factor_transpose, skip_preps, fixed_arguments, transposed_assembly, transpose_copy)
+    end
     skip_preps || GRMP.prepare_assembly!(AP)
-    d = get!(PATTERNS, AP) do
-        e1 = GRMP.get_basisevaler(AP.AM, 1, 1); e2 = GRMP.get_basisevaler(AP.AM, 2, 1)
-        v1, d1, t1 = evaltab(e1); v2, d2, t2 = evaltab(e2)
-        w = GRMP.get_qweights(AP.AM)
-        act, par = AP.action isa NoAction ? (0, Float64[]) : hooke_parameters(AP.action)   # Hooke tensors only; anything else throws
-        regions = Vector{Int32}(AP.regions)
-        h = Ref{Ptr{Cvoid}}()
-        GC.@preserve v1 d1 v2 d2 w par regions check(ccall((:grmp_blf_create, lib), Cint,
-            (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float64}, Cint, Cint, Ptr{Int32}, Cint, Cint, Ptr{Float64}, Ref{EvalTab}, Ref{EvalTab}, Ref{Ptr{Cvoid}}),
-            device_space(AP.FES[1]).h, device_space(AP.FES[2]).h, opcode(AP.operators[1]), opcode(AP.operators[2]), act,
-            isempty(par) ? C_NULL : pointer(par), aptcode(APT), transposed_assembly, regions, length(regions), length(w), w, t1, t2, h))
-        nnz = Ref{Int64}(0)
-        check(ccall((:grmp_blf_symbolic, lib), Cint, (Ptr{Cvoid}, Float64, Ref{Int64}), h[], factor, nnz))
-        colptr = Vector{Int64}(undef, size(A, 2) + 1); rowval = Vector{Int64}(undef, nnz[])
-        check(ccall((:grmp_blf_get_pattern, lib), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), h[], colptr, rowval))
-        b = DBlf(h[], nnz[], colptr, rowval)
-        finalizer(x -> ccall((:grmp_blf_destroy, lib), Cint, (Ptr{Cvoid},), x.h), b)
-        b
+    tr = transposed_assembly && !(APT <: GRMP.APT_SymmetricBilinearForm)
+    byor = get!(() -> Dict{Bool,DBlf}(), PATTERNS, AP)
+    d = get(byor, tr, nothing)
+    if d === nothing
+        d = byor[tr] = build_blf(A, AP, plan, Float64(factor), tr)
+    elseif !skip_preps
+        symbolic!(d, A, Float64(factor))           # prepare_assembly! ran again: quadrature / tables / factor may define a new pattern
     end
     nzval = Vector{Float64}(undef, d.nnz)
-    check(ccall((:grmp_blf_numeric, lib), Cint, (Ptr{Cvoid}, Float64, Ptr{Float64}), d.h, factor, nzval))
-    B = SparseMatrixCSC(size(A, 1), size(A, 2), d.colptr, d.rowval, nzval)
-    install_block!(A, B)
+    check(ccall((:grmp_blf_numeric, lib), Cint, (Ptr{Cvoid}, Float64, Ptr{Float64}), d.h, Float64(factor), nzval))
+    install_block!(A, SparseMatrixCSC(size(A, 1), size(A, 2), d.colptr, d.rowval, nzval))
     if transpose_copy !== nothing
-        cpt = Vector{Int64}(undef, size(A, 1) + 1); rvt = Vector{Int64}(undef, d.nnz); nzt = Vector{Float64}(undef, d.nnz)
+        m = size(transpose_copy, 2)       # = rows of A
+        cpt = Vector{Int64}(undef, m + 1); rvt = Vector{Int64}(undef, d.nnz); nzt = Vector{Float64}(undef, d.nnz)
         check(ccall((:grmp_blf_transpose_copy, lib), Cint, (Ptr{Cvoid}, Float64, Float64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
-            d.h, factor, factor_transpose, cpt, rvt, nzt))
-        install_block!(transpose_copy, SparseMatrixCSC(size(A, 2), size(A, 1), cpt, rvt, nzt))
+            d.h, Float64(factor), Float64(factor_transpose), cpt, rvt, nzt))
+        install_block!(transpose_copy, SparseMatrixCSC(size(transpose_copy, 1), m, cpt, rvt, nzt))
     end
     AP.last_allocations = 0
     return nothing
@@ -169,25 +271,23 @@ end
 """
     assemble_from_host!(A, AP; factor)
 
-Reassembly after the grid moved (same topology): one `grmp_blf_assemble_host` call uploads `Coordinates`, `CellVolumes`,
-`CellNodes`, `CellDofs`, assembles on the frozen pattern and downloads `nzval` (uploads the kernels do not read overlap
-the download).  `AP` must have been assembled once through `assemble!` above.
+Reassembly after the grid moved (same topology): one `grmp_blf_assemble_host` call uploads `Coordinates` and `CellVolumes`,
+assembles on the frozen pattern and downloads `nzval`.  `AP` must have been assembled once through `assemble!` above.
 """
-function assemble_from_host!(A::FEMatrixBlock{Float64,Int64,Float64,Int32}, AP::AssemblyPattern; factor = 1)
-    d = PATTERNS[AP]
+function assemble_from_host!(A::FEMatrixBlock{Float64,Int64,Float64,Int32}, AP::AssemblyPattern; factor = 1, transposed_assembly::Bool = false)
+    d = PATTERNS[AP][transposed_assembly]
     xgrid = AP.FES[1].xgrid
-    coords = xgrid[Coordinates]; vol = xgrid[CellVolumes]; cn = xgrid[CellNodes]
-    dofs1 = AP.FES[1][CellDofs].colentries
-    dofs2 = AP.FES[2] === AP.FES[1] ? nothing : AP.FES[2][CellDofs].colentries
+    coords = xgrid[Coordinates]; vol = Vector{Float64}(xgrid[CellVolumes])
     nzval = Vector{Float64}(undef, d.nnz)
-    GC.@preserve coords vol cn dofs1 dofs2 check(ccall((:grmp_blf_assemble_host, lib), Cint,
+    GC.@preserve coords vol check(ccall((:grmp_blf_assemble_host, lib), Cint,
         (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}),
-        d.h, factor, coords, vol, cn, dofs1, dofs2 === nothing ? C_NULL : pointer(dofs2), nzval))
+        d.h, Float64(factor), coords, vol, C_NULL, C_NULL, C_NULL, nzval))
     install_block!(A, SparseMatrixCSC(size(A, 1), size(A, 2), d.colptr, d.rowval, nzval))
     return nothing
 end
 
-# single-block FEMatrix with an empty target: adopt the CSC; otherwise merge (explicit zeros kept)
+# single-block FEMatrix with an empty target: adopt the CSC; otherwise merge entry by entry like _addnz (explicit zeros of
+# the block are kept: they are entries of the reference's pattern, fematrix.jl:54-65 only skips zero CONTRIBUTIONS)
 function install_block!(A::FEMatrixBlock, B::SparseMatrixCSC{Float64,Int64})
     E = A.entries
     flush!(E)
@@ -202,7 +302,114 @@ function install_block!(A::FEMatrixBlock, B::SparseMatrixCSC{Float64,Int64})
     end
 end
 
-hooke_parameters(action) = error("only NoAction and the Hooke tensor actions of HookStiffnessOperator2D/3D are evaluated on the device; " *
-                                 "construct the operator through GRMPCuda.HookStiffnessOperator2D to record (μ, λ)")
+# ---- device-resident follow-ups (SURVEY.md 8f N1 / N3): the matrix of the last assemble! stays on the GPU ---------------------
+"`matmul!(a, AP, b; factor, transposed)`: a += A b factor on the device matrix of `AP` (addblock_matmul!, fematrix.jl:402-473)"
+function matmul!(a::Vector{Float64}, AP::AssemblyPattern, b::Vector{Float64}; factor = 1, transposed::Bool = false, transposed_assembly::Bool = false)
+    d = PATTERNS[AP][transposed_assembly]
+    check(ccall((:grmp_blf_matmul, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Cint), d.h, b, a, Float64(factor), transposed))
+    return a
+end
+"`residual!(r, AP, x, b, fixed_dofs)`: r = A x - b, r[fixed_dofs] = 0, returns sum r_i^2 (solve_direct!'s check, solvers.jl:661-668)"
+function residual!(r::Vector{Float64}, AP::AssemblyPattern, x::Vector{Float64}, b::Vector{Float64}, fixed_dofs::Vector{Int64}; transposed_assembly::Bool = false)
+    d = PATTERNS[AP][transposed_assembly]
+    n2 = Ref{Float64}(0)
+    check(ccall((:grmp_blf_residual, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Int64, Ptr{Float64}, Ref{Float64}),
+        d.h, x, b, fixed_dofs, length(fixed_dofs), r, n2))
+    return n2[]
+end
+"`apply_penalties!(AP, fixed_dofs, penalty)` on the device values (fematrix.jl:349-355); throws if a fixed dof has no stored diagonal"
+function apply_penalties!(AP::AssemblyPattern, fixed_dofs::Vector{Int64}, penalty; transposed_assembly::Bool = false)
+    d = PATTERNS[AP][transposed_assembly]
+    missing_diag = Ref{Int64}(0)
+    check(ccall((:grmp_blf_apply_penalties, lib), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64, Float64, Ref{Int64}), d.h, fixed_dofs, length(fixed_dofs), Float64(penalty), missing_diag))
+end
+
+# ---- LinearForm ------------------------------------------------------------------------------------------------------
+struct LfPlan; op::Int; fsrc::Int; end
+function lf_plan(AP::AssemblyPattern)
+    length(AP.FES) == 1 && length(AP.operators) == 1 || return nothing
+    F = AP.FES[1]
+    F.xgrid[UniqueCellGeometries] in ([Triangle2D], [Tetrahedron3D]) || return nothing
+    (fecode(eltype(F)) !== nothing && (!F.broken || eltype(F) <: L2P0)) || return nothing
+    o = opcode(AP.operators[1])
+    o === nothing && return nothing
+    a = AP.action
+    a isa NoAction && return LfPlan(o, F_NONE)
+    a isa GRMP.DefaultUserAction || return nothing
+    a.argsizes[2] == 0 || return nothing                                  # fdot_action(f): the result does not depend on an input (actions.jl:119-128)
+    (GRMP.is_itemdependent(a) || GRMP.is_xrefdependent(a)) && return nothing  # "I" / "L" dependencies stay on the reference path
+    return LfPlan(o, GRMP.is_xdependent(a) ? F_QP_TABLE : F_CONST)
+end
+
+const LFS = WeakKeyDict{Any,DLf}()
+
+# f at the quadrature points of every cell, evaluated exactly as the reference loop does it (linearform.jl:197-201:
+# update_trafo! / eval_trafo!(action.x, L2G, xref[i]); eval_action!(action, input)) -> table [ncells][nq][resultdim]
+function tabulate_action(AP::AssemblyPattern, ev, nq::Int)
+    action = AP.action
+    rd = action.argsizes[1]
+    xgrid = AP.FES[1].xgrid
+    ncells = num_sources(xgrid[CellNodes])
+    regions = AP.regions; allitems = regions == [0]
+    xreg = xgrid[CellRegions]
+    input = zeros(Float64, 0)
+    if !GRMP.is_xdependent(action)
+        GRMP.eval_action!(action, input)
+        return Vector{Float64}(action.val[1:rd])
+    end
+    tab = zeros(Float64, rd, nq, ncells)
+    for cell = 1:ncells
+        (allitems || xreg[cell] in regions) || continue
+        update_trafo!(ev.L2G, cell)
+        for i = 1:nq
+            eval_trafo!(action.x, ev.L2G, ev.xref[i])
+            GRMP.eval_action!(action, input)
+            @views tab[:, i, cell] .= action.val[1:rd]
+        end
+    end
+    return vec(tab)
+end
+
+"""
+    assemble!(b::FEVectorBlock, AP; skip_preps, factor)   (device version; reference: linearform.jl:47-237, 239-251)
+
+b[dof + b.offset] += contributions in cell order.  A DataFunction cannot cross the C ABI: it is tabulated on the host at the
+quadrature points (GRMP_F_QP_TABLE) or passed as a constant (GRMP_F_CONST); the basis evaluation, contraction and scatter
+run on the device.
+"""
+function GRMP.assemble!(b::FEVectorBlock{Float64,Float64,Int32}, AP::AssemblyPattern{APT,Float64,ON_CELLS,Float64,Int32};
+        skip_preps::Bool = false, factor = 1, fixed_arguments = nothing) where {APT<:GRMP.APT_LinearForm}
+    plan = lf_plan(AP)
+    if plan === nothing
+        return invoke(GRMP.assemble!, Tuple{Union{AbstractArray{Float64,1},AbstractArray{Float64,2}},AssemblyPattern{APT,Float64,ON_CELLS,Float64,Int32}},
+                      b, AP; skip_preps, factor, fixed_arguments)
+    end
+    @assert b.FES == AP.FES[1]
+    skip_preps || GRMP.prepare_assembly!(AP)
+    ev = GRMP.get_basisevaler(AP.AM, 1, 1)
+    w = Vector{Float64}(GRMP.get_qweights(AP.AM))
+    if !skip_preps && haskey(LFS, AP)      # prepare_assembly! ran again: the tables may have changed
+        destroy(:grmp_lf_destroy, LFS[AP]); delete!(LFS, AP)
+    end
+    d = get!(LFS, AP) do
+        v, dv, t = evaltab(ev)
+        regions = AP.regions == [0] ? Int32[] : Vector{Int32}(AP.regions)
+        s = device_space(AP.FES[1])
+        h = Ref{Ptr{Cvoid}}()
+        GC.@preserve v dv w regions check(ccall((:grmp_lf_create, lib), Cint,
+            (Ptr{Cvoid}, Cint, Ptr{Int32}, Cint, Cint, Ptr{Float64}, Ref{EvalTab}, Ref{Ptr{Cvoid}}),
+            s.h, plan.op, isempty(regions) ? C_NULL : pointer(regions), length(regions), length(w), w, t, h))
+        l = DLf(h[], s)
+        finalizer(x -> destroy(:grmp_lf_destroy, x), l)
+        l
+    end
+    fdata = plan.fsrc == F_NONE ? Float64[] : tabulate_action(AP, ev, length(w))
+    entries = b.entries
+    GC.@preserve fdata entries check(ccall((:grmp_lf_assemble, lib), Cint,
+        (Ptr{Cvoid}, Float64, Cint, Ptr{Float64}, Ptr{Float64}, Int64),
+        d.h, Float64(factor), plan.fsrc, isempty(fdata) ? C_NULL : pointer(fdata), entries, b.offset))
+    AP.last_allocations = 0
+    return nothing
+end
 
 end # module

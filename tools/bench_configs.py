@@ -81,21 +81,22 @@ def main():
     ap.add_argument("--paths", default="columns")
     ap.add_argument("--only", default="")
     ap.add_argument("--lf", action="store_true")
+    ap.add_argument("--l2d", type=int, default=10, help="refinement level of the unit square (10: 4.2 M triangles)")
+    ap.add_argument("--l3d", type=int, default=5, help="refinement level of the unit cube (5: 0.8 M tetrahedra; P1 / RT0 run one level finer)")
     a = ap.parse_args()
     paths = a.paths.split(",")
-    Lt, Lq = (6, 4) if a.small else (9, 6)
+    # sizes: SURVEY.md 8(d) -- triangles level 9-10 (1-4.2 M cells), tetrahedra level 5-6 (0.8-6.3 M cells).  The low-order forms run on
+    # the larger grid (their matrices are small: level-5 P1 is 2 M non-zeros = 5 us at the roofline, i.e. pure launch latency).
+    Lt, Lq = (6, 4) if a.small else (a.l2d, a.l3d)
+    Lq_big = Lq if a.small else Lq + 1
     sym, gen = G.DiscreteSymmetricBilinearForm, G.DiscreteBilinearForm
     mu = 1000 / 1.4
     lam = 0.4 * mu / 0.2
     cfgs = []
-    g3 = lambda: G.uniform_refine(G.grid_unitcube("Tetrahedron3D"), Lq - 1)   # noqa: E731
+    g3 = lambda: G.uniform_refine(G.grid_unitcube("Tetrahedron3D"), Lq)       # noqa: E731
+    g3b = lambda: G.uniform_refine(G.grid_unitcube("Tetrahedron3D"), Lq_big)  # noqa: E731
     g2 = lambda: G.uniform_refine(G.grid_unitsquare("Triangle2D"), Lt)        # noqa: E731
     cfgs.append(("C1 P2 tri Laplace L%d" % Lt, g2, lambda g: (lambda s: sym([G.Gradient, G.Gradient], [s, s]))(G.FESpace(G.H1P2(1, 2), g)), 1.0))
-    cfgs.append(("C2 P1 tet Laplace L%d" % (Lq - 1), g3, lambda g: (lambda s: sym([G.Gradient, G.Gradient], [s, s]))(G.FESpace(G.H1P1(1), g)), 1.0))
-    cfgs.append(("C2 P2 tet Laplace L%d" % (Lq - 1), g3, lambda g: (lambda s: sym([G.Gradient, G.Gradient], [s, s]))(G.FESpace(G.H1P2(1, 3), g)), 1.0))
-    cfgs.append(("P2 tet mass L%d" % (Lq - 1), g3, lambda g: (lambda s: sym([G.Identity, G.Identity], [s, s]))(G.FESpace(G.H1P2(1, 3), g)), 1.0))
-    cfgs.append(("C5 RT0 tet mass L%d" % (Lq - 1), g3, lambda g: (lambda s: sym([G.Identity, G.Identity], [s, s]))(G.FESpace(G.HDIVRT0(3), g)), 1.0))
-    cfgs.append(("C5 BDM1 tet mass L%d" % (Lq - 1), g3, lambda g: (lambda s: sym([G.Identity, G.Identity], [s, s]))(G.FESpace(G.HDIVBDM1(3), g)), 1.0))
     cfgs.append(("C3 Hooke H1P2{2,2} tri L%d" % Lt, g2,
                  lambda g: (lambda s: gen([G.SymmetricGradient(1), G.SymmetricGradient(1)], [s, s], G.HookeAction(2, mu, lam)))(G.FESpace(G.H1P2(2, 2), g)), 1.0))
     cfgs.append(("C4 BR tri Laplace L%d" % Lt, g2, lambda g: (lambda s: sym([G.Gradient, G.Gradient], [s, s]))(G.FESpace(G.H1BR(2), g)), 1.0))
@@ -103,6 +104,11 @@ def main():
                  lambda g: gen([G.Divergence, G.Identity], [G.FESpace(G.H1BR(2), g), G.FESpace(G.L2P0(1), g)]), -1.0))
     R = G.ReconstructionIdentity(G.HDIVBDM1(2))
     cfgs.append(("C4 BR recon-BDM1 mass L%d" % Lt, g2, lambda g: (lambda s: sym([R, R], [s, s]))(G.FESpace(G.H1BR(2), g)), 1.0))
+    cfgs.append(("C2 P2 tet Laplace L%d" % Lq, g3, lambda g: (lambda s: sym([G.Gradient, G.Gradient], [s, s]))(G.FESpace(G.H1P2(1, 3), g)), 1.0))
+    cfgs.append(("P2 tet mass L%d" % Lq, g3, lambda g: (lambda s: sym([G.Identity, G.Identity], [s, s]))(G.FESpace(G.H1P2(1, 3), g)), 1.0))
+    cfgs.append(("C5 BDM1 tet mass L%d" % Lq, g3, lambda g: (lambda s: sym([G.Identity, G.Identity], [s, s]))(G.FESpace(G.HDIVBDM1(3), g)), 1.0))
+    cfgs.append(("C2 P1 tet Laplace L%d" % Lq_big, g3b, lambda g: (lambda s: sym([G.Gradient, G.Gradient], [s, s]))(G.FESpace(G.H1P1(1), g)), 1.0))
+    cfgs.append(("C5 RT0 tet mass L%d" % Lq_big, g3b, lambda g: (lambda s: sym([G.Identity, G.Identity], [s, s]))(G.FESpace(G.HDIVRT0(3), g)), 1.0))
     cache = {}
     for name, gf, mk, factor in cfgs:
         if a.only and a.only not in name:
@@ -117,6 +123,7 @@ def main():
         run(name, lambda: mk(g), factor=factor, paths=ps)
     if not a.lf:
         return
+    cache.clear()
     g = g2()
     sv = G.FESpace(G.H1BR(2), g)
     for nm, op, bonus in (("C4 LF recon-BDM1 (tabulated f, 9-pt Stroud)", R, 2), ("LF identity BR", G.Identity, 0)):
