@@ -19,7 +19,7 @@ from .assembly import (Identity, Gradient, SymmetricGradient, Divergence, Recons
                        DataFunction, fdot_action, AssemblyPattern, DiscreteBilinearForm, DiscreteSymmetricBilinearForm,
                        DiscreteLumpedBilinearForm, DiscreteLinearForm, prepare_assembly, assemble, assemble_csc, blf_set_path,
                        blf_stats, quadrature_order, device_grid, device_space, addblock_matmul, residual, apply_penalties,
-                       device_csc, fetch_values)
+                       device_csc, fetch_values, ItemIntegrator, L2NormIntegrator, L2ErrorIntegrator, evaluate, evaluate_itemwise)
 from .operators import (PDEOperator, LaplaceOperator, ReactionOperator, LagrangeMultiplier, HookStiffnessOperator2D,
                         HookStiffnessOperator3D, BilinearForm, LinearForm, create_assembly_pattern, assemble_operator)
 from . import _lib, assembly, partition

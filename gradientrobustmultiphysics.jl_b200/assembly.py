@@ -196,7 +196,7 @@ def device_space(FES: FESpace):
 
 
 # ---- assembly patterns ---------------------------------------------------------------------------
-APT_BilinearForm, APT_SymmetricBilinearForm, APT_LumpedBilinearForm, APT_LinearForm = 0, 1, 2, 10
+APT_BilinearForm, APT_SymmetricBilinearForm, APT_LumpedBilinearForm, APT_LinearForm, APT_ItemIntegrator = 0, 1, 2, 10, 20
 
 
 class AssemblyPattern:
@@ -257,7 +257,7 @@ class _Prepared:
     def __del__(self):
         h, kind = getattr(self, "h", None), getattr(self, "kind", None)
         if h is not None and kind is not None:
-            _release("grmp_blf_destroy" if kind == "blf" else "grmp_lf_destroy", h)
+            _release({"blf": "grmp_blf_destroy", "lf": "grmp_lf_destroy", "ii": "grmp_ii_destroy"}[kind], h)
             self.h = None
 
 
@@ -281,7 +281,14 @@ def prepare_assembly(AP: AssemblyPattern, transposed_assembly=False):
     regions = np.ascontiguousarray(AP.regions, dtype=np.int32)
     w = np.ascontiguousarray(P.qf.w)
     h = C.c_void_p()
-    if AP.APT == APT_LinearForm:
+    if AP.APT == APT_ItemIntegrator:
+        sp = device_space(AP.FES[0])
+        tab, keep = _tables(AP.FES[0], AP.operators[0], P.qf)
+        P.keep.append(keep)
+        _lib.check(L.grmp_ii_create(sp, AP.operators[0].code, AP.action.code, _lib.ptr(regions), regions.size, len(P.qf), _lib.ptr(w),
+                                    C.byref(tab), C.byref(h)))
+        P.kind = "ii"
+    elif AP.APT == APT_LinearForm:
         sp = device_space(AP.FES[0])
         tab, keep = _tables(AP.FES[0], AP.operators[0], P.qf)
         P.keep.append(keep)
@@ -470,6 +477,78 @@ def _assemble_lf(b, AP, factor=1, skip_preps=False, offset=0):
     _lib.check(L.grmp_lf_assemble(P.h, float(factor), fsrc, _lib.ptr(fd), _lib.ptr(entries), int(offset)))
     AP.last_allocations = 0
     return None
+
+
+# ---- ItemIntegrator (itemintegrator.jl) ----------------------------------------------------------------------------------------
+class _IIAction:
+    """the closed set of ItemIntegrator kernels evaluated on the device (grmp.h GRMP_II_*)"""
+
+    def __init__(self, code, bonus_quadorder=0, data=None, factor=1.0, name="ItemIntegrator"):
+        self.code, self.bonus_quadorder, self.data, self.factor, self.name = code, bonus_quadorder, data, float(factor), name
+
+
+def ItemIntegrator(operators, action=None, regions=(0,), name="ItemIntegrator"):
+    """ItemIntegrator(operators, action; AT = ON_CELLS, regions) (itemintegrator.jl:18-21); one argument, NoAction or one of the
+    integrators below"""
+    if len(operators) != 1:
+        raise NotImplementedError("ItemIntegrators with several arguments are a 'next' row (SURVEY.md 8f N4)")
+    act = action if isinstance(action, _IIAction) else _IIAction(0)
+    if action is not None and not isinstance(action, (_IIAction, NoAction)):
+        raise NotImplementedError("user Actions cannot cross the C ABI: NoAction, L2NormIntegrator and L2ErrorIntegrator run on the device")
+    return AssemblyPattern(APT_ItemIntegrator, name, [], operators, act, [1], regions)
+
+
+def L2NormIntegrator(ncomponents, operator, quadorder=2, regions=(0,), name="L2 norm"):
+    """L2NormIntegrator(ncomponents, operator; quadorder = 2) (itemintegrator.jl:91-110)"""
+    return ItemIntegrator([operator], _IIAction(1, bonus_quadorder=quadorder, name=name), regions=regions, name=name)
+
+
+def L2ErrorIntegrator(compare_data: DataFunction, operator=None, quadorder="auto", factor=1, regions=(0,), name="auto"):
+    """L2ErrorIntegrator(compare_data, operator; quadorder = "auto", factor) (itemintegrator.jl:33-78): || compare_data - factor u_h ||^2
+    per item; "auto" = twice the bonus quadrature order of the data"""
+    q = 2 * compare_data.bonus_quadorder if quadorder == "auto" else int(quadorder)
+    nm = f"L2 error ({compare_data.name})" if name == "auto" else name
+    return ItemIntegrator([Identity if operator is None else operator], _IIAction(2, bonus_quadorder=q, data=compare_data, factor=factor, name=nm),
+                          regions=regions, name=nm)
+
+
+def _ii_prepare(AP, FEB, skip_preps):
+    if isinstance(FEB, (list, tuple)):
+        assert len(FEB) == 1
+        FEB = FEB[0]
+    assert isinstance(FEB, FEVectorBlock), "evaluate an ItemIntegrator on an FEVectorBlock"
+    if AP.AM is None or not skip_preps or AP.FES != [FEB.FES]:
+        AP.FES = [FEB.FES]                       # prepare_assembly!(AP, FE) (itemintegrator.jl:186-192)
+        prepare_assembly(AP)
+    P = AP.AM
+    data = None
+    if AP.action.code == 2:
+        fsrc, fd = _qp_table(AP, P)                 # compare_data at the quadrature points (L2error_function, itemintegrator.jl:52-69)
+        if fsrc == 1:
+            fd = np.broadcast_to(fd, (FEB.FES.xgrid.ncells, len(P.qf), fd.size))
+        data = np.ascontiguousarray(fd, dtype=np.float64)
+        if data.shape[-1] != _resultdim(AP):
+            raise ValueError(f"compare data has {data.shape[-1]} components, operator result has {_resultdim(AP)}")
+    coeffs = np.ascontiguousarray(FEB.entries[FEB.offset:FEB.offset + FEB.FES.ndofs])
+    rd = C.c_int(0)
+    _lib.check(_lib.lib().grmp_ii_resultdim(P.h, C.byref(rd)))
+    return P, coeffs, data, rd.value
+
+
+def evaluate_itemwise(b, AP: AssemblyPattern, FEB, skip_preps=False):
+    """evaluate!(b, AP, FEB) (itemintegrator.jl:160-300): b[item, j] += ... (Julia: b[j, item]); returns b"""
+    P, coeffs, data, rd = _ii_prepare(AP, FEB, skip_preps)
+    assert b.dtype == np.float64 and b.flags.c_contiguous and b.shape == (AP.FES[0].xgrid.ncells, rd)
+    _lib.check(_lib.lib().grmp_ii_evaluate(P.h, _lib.ptr(coeffs), AP.action.factor, _lib.ptr(data), _lib.ptr(b), None))
+    return b
+
+
+def evaluate(AP: AssemblyPattern, FEB, skip_preps=False):
+    """evaluate(AP, FEB) (itemintegrator.jl:316-360): accumulation over all items; a scalar if the result has one component"""
+    P, coeffs, data, rd = _ii_prepare(AP, FEB, skip_preps)
+    tot = np.zeros(rd)
+    _lib.check(_lib.lib().grmp_ii_evaluate(P.h, _lib.ptr(coeffs), AP.action.factor, _lib.ptr(data), None, _lib.ptr(tot)))
+    return float(tot[0]) if rd == 1 else tot
 
 
 def _resultdim(AP):

@@ -163,6 +163,16 @@ struct grmp_lf {
   grmp_stats st{};
 };
 
+struct grmp_ii {
+  grmp_space* sp;
+  int op, kind, nq;
+  i64 topo_grid = 0, topo_sp = 0;
+  RegionFilter reg;
+  DevBuf<double> w, coeffs, data, b, itemval, total;
+  DevBuf<unsigned char> tmp;
+  EvalTables tab;
+};
+
 static int blf_numeric_launch(grmp_blf* b, BlfLocalParams& p, cudaStream_t s);
 
 static int fill_blf_params(grmp_blf* b, double factor, BlfLocalParams* p) {
@@ -778,6 +788,64 @@ int grmp_lf_assemble(grmp_lf* l, double factor, int fsrc, const double* fdata, d
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   l->st.last_numeric_ms = ms; l->st.kernel_launches = l->path == GRMP_PATH_COLUMNS ? (i64)l->lfp.classes.size() : 2; l->st.path = l->path;
+  return GRMP_OK;
+}
+
+int grmp_ii_create(grmp_space* sp, int op, int kind, const int32_t* regions, int nregions, int nq, const double* qweights,
+                   const grmp_evaltab* tab, grmp_ii** out) {
+  if (!sp || !qweights || !tab || !out || nq <= 0 || kind < GRMP_II_NONE || kind > GRMP_II_L2ERROR) return fail(GRMP_EINVAL, "grmp_ii_create: bad argument");
+  grmp_ii* ii = new grmp_ii();
+  cudaStream_t s = sp->grid->ctx->stream;
+  ii->sp = sp; ii->op = op; ii->kind = kind; ii->nq = nq;
+  int rc = make_regions(regions, nregions, &ii->reg);
+  if (!rc) rc = ii->w.upload(qweights, nq, s);
+  if (!rc) rc = upload_tables(tab, nq, sp->grid->dim, s, &ii->tab);
+  ii->topo_grid = sp->grid->topo_version; ii->topo_sp = sp->topo_version;
+  EvalView e;
+  if (!rc) rc = make_evalview(sp, op, ii->tab, &e);
+  if (!rc && cudaStreamSynchronize(s) != cudaSuccess) rc = fail(GRMP_ECUDA, "upload failed");
+  if (rc) { delete ii; return rc; }
+  *out = ii;
+  return GRMP_OK;
+}
+int grmp_ii_destroy(grmp_ii* ii) { delete ii; return GRMP_OK; }
+
+int grmp_ii_resultdim(grmp_ii* ii, int* resultdim) {
+  if (!ii || !resultdim) return fail(GRMP_EINVAL, "NULL argument");
+  EvalView e;
+  GRMP_TRY(make_evalview(ii->sp, ii->op, ii->tab, &e));
+  *resultdim = ii->kind == GRMP_II_NONE ? e.rd : 1;
+  return GRMP_OK;
+}
+
+int grmp_ii_evaluate(grmp_ii* ii, const double* coeffs_host, double factor, const double* data_host, double* b_host, double* total_host) {
+  if (!ii || !coeffs_host) return fail(GRMP_EINVAL, "grmp_ii_evaluate: NULL argument");
+  if (ii->kind == GRMP_II_L2ERROR && !data_host) return fail(GRMP_EINVAL, "grmp_ii_evaluate: compare data missing");
+  grmp_space* sp = ii->sp;
+  grmp_ctx* ctx = sp->grid->ctx;
+  cudaStream_t s = ctx->stream;
+  GRMP_CUDA(cudaSetDevice(ctx->device));
+  if (ii->topo_grid != sp->grid->topo_version || ii->topo_sp != sp->topo_version)
+    return fail(GRMP_ESTATE, "CellNodes / CellDofs changed after grmp_ii_create: create the integrator again");
+  IiLocalParams p{};
+  p.g = sp->grid->view();
+  GRMP_TRY(make_evalview(sp, ii->op, ii->tab, &p.e));
+  const i64 ncells = sp->grid->ncells;
+  const int ardim = ii->kind == GRMP_II_NONE ? p.e.rd : 1;
+  p.reg = ii->reg; p.nq = ii->nq; p.w = ii->w.p; p.kind = ii->kind; p.ardim = ardim; p.factor = factor;
+  GRMP_TRY(ii->coeffs.upload(coeffs_host, (size_t)sp->ndofs, s));
+  if (ii->kind == GRMP_II_L2ERROR) GRMP_TRY(ii->data.upload(data_host, (size_t)ncells * ii->nq * p.e.rd, s));
+  if (b_host) GRMP_TRY(ii->b.upload(b_host, (size_t)ncells * ardim, s));
+  if (ii->itemval.n < (size_t)ncells * ardim) GRMP_TRY(ii->itemval.alloc((size_t)std::max<i64>(ncells * ardim, 1)));
+  if (ii->total.n < (size_t)ardim) GRMP_TRY(ii->total.alloc((size_t)ardim));
+  p.coeffs = ii->coeffs.p; p.data = ii->data.p; p.b = b_host ? ii->b.p : nullptr; p.itemval = ii->itemval.p;
+  GRMP_TRY(launch_ii_local(p, s));
+  if (total_host) {
+    for (int j = 0; j < ardim; j++) GRMP_TRY(device_sum(s, ii->itemval.p + (size_t)j * ncells, ncells, ii->total.p + j, &ii->tmp));
+    GRMP_CUDA(cudaMemcpyAsync(total_host, ii->total.p, (size_t)ardim * 8, cudaMemcpyDeviceToHost, s));
+  }
+  if (b_host) GRMP_CUDA(cudaMemcpyAsync(b_host, ii->b.p, (size_t)ncells * ardim * 8, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
   return GRMP_OK;
 }
 

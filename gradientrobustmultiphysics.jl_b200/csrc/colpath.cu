@@ -192,6 +192,114 @@ __global__ void __launch_bounds__(256) col_kernel(const ColParams p) {
     if (kt + i < len) dst[kt + i] = a[(kt + i) * 32];
 }
 
+// ---- closed-form kernels (colpath_ev.cuh, "reference tensor" evaluators): same tiles, records, image and write-out as
+//      col_kernel; the quadrature loop is replaced by NT multiply-adds per local row against K_t[s][s_col] in shared memory --------
+template <class F>
+__global__ void __launch_bounds__(256) cf_geo_kernel(const GridView g, double act0, double act1, double* __restrict__ geo) {
+  const i64 cell = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (cell >= g.ncells) return;
+  double cr[F::STRIDE];
+#pragma unroll
+  for (int i = 0; i < F::STRIDE; i++) cr[i] = 0.0;
+  const double act_p[2] = {act0, act1};
+  F::geo(g, cell, act_p, cr);
+  double2* dst = reinterpret_cast<double2*>(geo + cell * F::STRIDE);
+#pragma unroll
+  for (int i = 0; i < F::STRIDE / 2; i++) dst[i] = make_double2(cr[2 * i], cr[2 * i + 1]);
+}
+
+template <class F, int NV>
+__global__ void __launch_bounds__(256) cf_kernel(const ColParams p) {
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthr = blockDim.x;
+  constexpr int ntab = F::NT * F::NSF * CT_PAD;
+  __shared__ u32 s_maxlen[8];
+  double* const sK = sm;
+  double* const img = sm + ntab;
+  const i64 tile = p.tile_list[blockIdx.x];
+  const i64 grp = tile * p.nw + warp;
+  const i64 pos = grp * 32 + lane;
+  const bool has = grp < p.ngroups && pos < p.ncols_used;
+  const u32 np = has ? p.pos_np[pos] : 0u;
+  const u32 len = has ? p.pos_len[pos] : 0u;
+  const i64 recbase = grp < p.ngroups ? p.pos_recbeg[grp * 32] : 0;
+  double* const dst = p.nzval + (has ? p.pos_start[pos] : 0);
+  const u32 maxlen = __reduce_max_sync(0xffffffffu, len);
+  if (lane == 0) s_maxlen[warp] = maxlen;
+  for (int i = tid; i < ntab; i += nthr) sK[i] = p.tabC[i];
+  const u32 maxnp = __reduce_max_sync(0xffffffffu, np);
+  const u32 lt = (1u << lane) - 1u;
+  u32 rbase = 0;
+  auto next_idx = [&](u32 k) -> u32 {
+    const u32 bal = __ballot_sync(0xffffffffu, k < np);
+    const u32 idx = rbase + __popc(bal & lt);
+    rbase += __popc(bal);
+    return idx;
+  };
+  uint4 rn[NV];
+  {
+    const u32 i0 = next_idx(0);
+#pragma unroll
+    for (int v = 0; v < NV; v++) rn[v] = make_uint4(0xff000000u, 0, 0, 0);
+    if (0 < np) {
+#pragma unroll
+      for (int v = 0; v < NV; v++) rn[v] = __ldg(p.recs + (size_t)(recbase + i0) * NV + v);
+    }
+  }
+  __syncthreads();
+  if (grp >= p.ngroups) return;
+  u32 acc_off = 0;
+  for (int w2 = 0; w2 < warp; w2++) acc_off += s_maxlen[w2] + 1u;
+  double* const a = img + (size_t)acc_off * 32 + lane;
+  for (u32 k = 0; k < maxlen; k++) a[k * 32] = 0.0;
+  const double factor = p.factor;
+  for (u32 k = 0; k < maxnp; k++) {
+    u32 w[NV * 4];
+#pragma unroll
+    for (int v = 0; v < NV; v++) { w[4 * v] = rn[v].x; w[4 * v + 1] = rn[v].y; w[4 * v + 2] = rn[v].z; w[4 * v + 3] = rn[v].w; }
+    const u32 lc = w[0] >> 24;
+    const bool work = k < np && lc != 255u;
+    double cr[F::STRIDE];
+    if (work) {
+      const double2* src = reinterpret_cast<const double2*>(p.geo + (size_t)(w[0] & 0xffffffu) * F::STRIDE);
+#pragma unroll
+      for (int i = 0; i < F::STRIDE / 2; i++) { const double2 t = __ldg(src + i); cr[2 * i] = t.x; cr[2 * i + 1] = t.y; }
+    }
+    {
+      const u32 i1 = next_idx(k + 1);
+      if (k + 1 < np) {
+#pragma unroll
+        for (int v = 0; v < NV; v++) rn[v] = __ldg(p.recs + (size_t)(recbase + i1) * NV + v);
+      }
+    }
+    if (work) {
+      F::column(cr, (int)lc, sK, [&](int r, double v) {
+        const u32 o = min(rec_byte<NV>(w, 4 + r), maxlen);     // rows that are not in the pattern go to the warp's trash row
+        a[o * 32] = fma(v, factor, a[o * 32]);
+      });
+    }
+  }
+  if (maxlen == 0) return;
+  u32 head = (4u - (u32)(((size_t)dst >> 3) & 3u)) & 3u;
+  if (head > len) head = len;
+#pragma unroll
+  for (u32 i = 0; i < 3; i++)
+    if (i < head) dst[i] = a[i * 32];
+  const u32 nbody = (len - head) >> 2;
+  const u32 maxbody = __reduce_max_sync(0xffffffffu, nbody);
+  for (u32 b = 0; b < maxbody; b++) {
+    if (b < nbody) {
+      const u32 k = head + 4 * b;
+      const double v0 = a[k * 32], v1 = a[(k + 1) * 32], v2 = a[(k + 2) * 32], v3 = a[(k + 3) * 32];
+      asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + k), "d"(v0), "d"(v1), "d"(v2), "d"(v3) : "memory");
+    }
+  }
+  const u32 kt = head + 4 * nbody;
+#pragma unroll
+  for (u32 i = 0; i < 3; i++)
+    if (kt + i < len) dst[kt + i] = a[(kt + i) * 32];
+}
+
 // ---- one-time record build ------------------------------------------------------------------------------------------------
 struct PackParams {
   const i64* colptr; const i64* rowval;        // pattern, 1-based
@@ -373,6 +481,40 @@ template <class RowEv, class ColEv, int ACT, int NQ> struct VariantImpl {
 const Variant VARIANTS[] = {GRMP_SQUARE_FORMS(GRMP_VARIANT) GRMP_RECT_FORMS(GRMP_VARIANT)};
 constexpr int NVARIANTS = sizeof(VARIANTS) / sizeof(VARIANTS[0]);
 
+typedef int (*CfGeoFn)(const GridView&, const double* act_p, double* geo, cudaStream_t);
+struct CfVariant {
+  bool (*match)(const ColEvalDesc& row, const ColEvalDesc& col, int act);
+  LaunchFn launch;
+  CfGeoFn geo;
+  int stride, nrow, nv, nt, nsf, ed, symk;
+};
+template <class F> struct CfVariantImpl {
+  static constexpr int NV = (4 + F::NROW + 15) / 16;
+  static bool match(const ColEvalDesc& row, const ColEvalDesc& col, int act) {
+    return act == F::ACT && ev_matches<typename F::Quad>(row) && ev_matches<typename F::Quad>(col);
+  }
+  static int launch(const ColParams& p, int nblocks, int nthreads, int smem, cudaStream_t s) {
+    static int attr_set = 0;
+    if (smem > attr_set) {
+      GRMP_CUDA(cudaFuncSetAttribute(cf_kernel<F, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_set = smem;
+    }
+    cf_kernel<F, NV><<<nblocks, nthreads, smem, s>>>(p);
+    GRMP_CUDA(cudaGetLastError());
+    return GRMP_OK;
+  }
+  static int geo(const GridView& g, const double* act_p, double* out, cudaStream_t s) {
+    cf_geo_kernel<F><<<(unsigned)((g.ncells + 255) / 256), 256, 0, s>>>(g, act_p[0], act_p[1], out);
+    GRMP_CUDA(cudaGetLastError());
+    return GRMP_OK;
+  }
+};
+#define GRMP_CFV(F) {&CfVariantImpl<GRMP_UNPAREN F>::match, &CfVariantImpl<GRMP_UNPAREN F>::launch, &CfVariantImpl<GRMP_UNPAREN F>::geo, \
+                     GRMP_UNPAREN F::STRIDE, GRMP_UNPAREN F::NROW, CfVariantImpl<GRMP_UNPAREN F>::NV, GRMP_UNPAREN F::NT, GRMP_UNPAREN F::NSF, \
+                     GRMP_UNPAREN F::ED, GRMP_UNPAREN F::SYMK ? 1 : 0},
+const CfVariant CFVARIANTS[] = {GRMP_CF_FORMS(GRMP_CFV)};
+constexpr int NCFVARIANTS = sizeof(CFVARIANTS) / sizeof(CFVARIANTS[0]);
+
 int describe(const EvalView& e, int ed, ColEvalDesc* d) {
   d->op = e.op; d->ed = ed; d->nd = e.nd; d->fam = e.fam; d->nbub = 0;
   if (e.op == GRMP_OP_RECON_ID_RT0 || e.op == GRMP_OP_RECON_ID_BDM1) {
@@ -445,11 +587,16 @@ bool colpath_applicable(const BlfLocalParams& p, int nq, ColPath* cp) {
   if (nq > WQ_MAX) return false;
   cp->row_is_arg1 = !tr;
   cp->variant = -1;
+  cp->cf_variant = -1;
+  cp->nq = nq;
+  // closed-form kernel first (any quadrature rule: K is the rule's own sum), GRMP_COL_QUADRATURE=1 keeps the quadrature kernels
+  if (!getenv("GRMP_COL_QUADRATURE") && p.same_eval)
+    for (int v = 0; v < NCFVARIANTS; v++)
+      if (CFVARIANTS[v].match(cp->row, cp->col, p.action)) { cp->cf_variant = v; return true; }
   for (int v = 0; v < NVARIANTS; v++)
     if (VARIANTS[v].match(cp->row, cp->col, p.action, nq)) { cp->variant = v; break; }
   if (cp->variant < 0) return false;
   if ((size_t)VARIANTS[cp->variant].tabR_per_q * nq > TABR_MAX) return false;
-  cp->nq = nq;
   return true;
 }
 
@@ -459,14 +606,44 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
   cudaStream_t s = ctx->stream;
   cp->built = false;
   cp->uid = g_next_uid++;
-  const Variant& V = VARIANTS[cp->variant];
+  const bool cf = cp->cf_variant >= 0;
+  const Variant& V = VARIANTS[cf ? 0 : cp->variant];
   const bool tr = !cp->row_is_arg1;
   const EvalView& er = tr ? p.e2 : p.e1;
   const EvalView& ec = tr ? p.e1 : p.e2;
   const int nq = p.nq;
   const i64 ncols = pat.ncols, ncells = p.g.ncells;
+  const int v_nrow = cf ? CFVARIANTS[cp->cf_variant].nrow : V.nrow, v_nv = cf ? CFVARIANTS[cp->cf_variant].nv : V.nv;
+  const int v_stride = cf ? CFVARIANTS[cp->cf_variant].stride : V.cache_stride();
   // tables
-  {
+  if (cf) {
+    // K_t[s][s_col] = sum_q w_q T[s][a][q] T[s_col][b][q] from the caller's own tables and weights (t = (a, b); symmetric G: a <= b and
+    // K_ab + K_ba merged), layout [t][s][CT_PAD]
+    const CfVariant& F = CFVARIANTS[cp->cf_variant];
+    std::vector<double> T;
+    int nas = 0;
+    GRMP_TRY(make_tables(cp->row, nq, vals1, derivs1, er.tab_nd, er.tab_nc, &T, &nas));
+    const int nsf = F.nsf, ed = F.ed;
+    if (nsf != cp->row.nds + cp->row.nbub) return fail(GRMP_EUNSUPPORTED, "column kernels: closed-form table shape");
+    auto Kab = [&](int a, int b, int sI, int sJ) {
+      double v = 0.0;
+      for (int q = 0; q < nq; q++) v += w[q] * T[((size_t)sI * nas + a) * nq + q] * T[((size_t)sJ * nas + b) * nq + q];
+      return v;
+    };
+    std::vector<double> K((size_t)F.nt * nsf * CT_PAD, 0.0);
+    for (int t = 0; t < F.nt; t++) {
+      int a = 0, b = 0;
+      if (nas > 1) {
+        if (F.symk) { a = sym_a(ed, t); b = sym_b(ed, t); } else { a = t / ed; b = t % ed; }
+      }
+      for (int sI = 0; sI < nsf; sI++) for (int sJ = 0; sJ < nsf; sJ++)
+        K[((size_t)t * nsf + sI) * CT_PAD + sJ] = Kab(a, b, sI, sJ) + ((F.symk && a != b) ? Kab(b, a, sI, sJ) : 0.0);
+    }
+    if ((nas > 1) != (F.nt > 1)) return fail(GRMP_EUNSUPPORTED, "column kernels: closed-form table shape");
+    GRMP_TRY(cp->tabC.upload(K.data(), K.size(), s));
+    cp->tabR.clear();
+    cp->wq = w;
+  } else {
     const std::vector<double>& v2 = p.same_eval ? vals1 : vals2;
     const std::vector<double>& d2 = p.same_eval ? derivs1 : derivs2;
     std::vector<double> TR, TC;
@@ -486,7 +663,7 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
   const i64 ncols_used = (ncols_owned >= 0 && ncols_owned < ncols) ? ncols_owned : ncols;
   cp->ncols_used = ncols_used;
   cp->ngroups = (ncols_used + 31) / 32;
-  cp->nv = V.nv;
+  cp->nv = v_nv;
   if (ncols_used == 0 || pat.nnz == 0) { cp->ntiles = 0; cp->built = true; return GRMP_OK; }
   // (1) column -> (cell, local dof) pairs, cells ascending
   DofGather dg;
@@ -517,7 +694,7 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
   }
   // (3) tiles: NW groups per CTA; inside a tile columns are ordered by length; shrink the tile until the shared-memory image fits
   if (ncells > (i64)0x1000000) return fail(GRMP_EUNSUPPORTED, "column kernels: more than 2^24 cells on one device (24-bit cell ids in the records)");
-  int nw = getenv("GRMP_COL_NW") ? atoi(getenv("GRMP_COL_NW")) : 8;
+  int nw = getenv("GRMP_COL_NW") ? atoi(getenv("GRMP_COL_NW")) : 4;
   nw = std::max(1, std::min(nw, 8));
   DevBuf<i64> np64;
   GRMP_TRY(cp->colperm.alloc(ncols_used)); GRMP_TRY(cp->pos_np.alloc(ncols_used)); GRMP_TRY(cp->pos_len.alloc(ncols_used));
@@ -551,7 +728,7 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
     GRMP_CUDA(cudaStreamSynchronize(s));
     if (hflags[0]) return fail(GRMP_EUNSUPPORTED, "column kernels: a column has more than 254 entries or 65535 cells");
     // shared-memory need of every tile; tiles are launched in classes of similar need
-    const int ntab_even = (V.nas_c * nq * CT_PAD + 1) & ~1;
+    const int ntab_even = cf ? CFVARIANTS[cp->cf_variant].nt * CFVARIANTS[cp->cf_variant].nsf * CT_PAD : (V.nas_c * nq * CT_PAD + 1) & ~1;
     DevBuf<int> need_d;
     GRMP_TRY(need_d.alloc(ntiles));
     tile_need<<<nblk(ntiles), 256, 0, s>>>(cp->pos_len.p, ntiles, ncols_used, nw, ntab_even, need_d.p);
@@ -587,7 +764,7 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
     if (nw == 1) return fail(GRMP_EUNSUPPORTED, "column kernels: one group of 32 columns does not fit into shared memory");
   }
   temp.release(); ck1.release(); ck2.release(); ci1.release(); ci2.release(); np64.release();
-  GRMP_TRY(cp->geo.alloc((size_t)ncells * V.cache_stride()));
+  GRMP_TRY(cp->geo.alloc((size_t)ncells * v_stride));
   // (4) records
   GRMP_TRY(cp->recs.alloc((size_t)std::max<i64>(npairs_used, 1) * cp->nv));
   PackParams pp{};
@@ -595,7 +772,7 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
   pp.colperm = cp->colperm.p; pp.pos_recbeg = cp->pos_recbeg.p;
   pp.dofsR = er.celldofs; pp.ndR = er.nd; pp.orient = p.g.orient; pp.regions = p.g.regions; pp.reg = p.reg;
   pp.ncells = ncells; pp.ncols_used = ncols_used;
-  pp.nrow = V.nrow; pp.row_bdm3 = (cp->row.kind == 1 && cp->row.nds == 16); pp.col_bdm3 = (cp->col.kind == 1 && cp->col.nds == 16);
+  pp.nrow = v_nrow; pp.row_bdm3 = (cp->row.kind == 1 && cp->row.nds == 16); pp.col_bdm3 = (cp->col.kind == 1 && cp->col.nds == 16);
   pp.nw = cp->nw; pp.nv = cp->nv; pp.recs = cp->recs.p; pp.err = flags.p;
   pack_records<<<nblk(cp->ngroups * 32, 128), 128, 0, s>>>(pp);
   GRMP_CUDA(cudaGetLastError());
@@ -604,8 +781,8 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
   if (hflags[0]) return fail(GRMP_EUNSUPPORTED, "column kernels: record build failed");
   if (getenv("GRMP_VERBOSE"))
   {
-    fprintf(stderr, "[grmp columns] variant %d nw %d tiles %lld pairs %lld geometry record %d B pair record %d B; classes:", cp->variant,
-            cp->nw, (long long)cp->ntiles, (long long)cp->npairs, 8 * V.cache_stride(), 16 * cp->nv);
+    fprintf(stderr, "[grmp columns] nw %d variant %d (1000+: closed form) tiles %lld pairs %lld geometry record %d B pair record %d B; classes:", cp->nw,
+            cf ? 1000 + cp->cf_variant : cp->variant, (long long)cp->ntiles, (long long)cp->npairs, 8 * v_stride, 16 * cp->nv);
     for (auto& c : cp->classes) fprintf(stderr, " %lld tiles <= %d B;", (long long)c.count, c.smem_bytes);
     fprintf(stderr, "\n");
   }
@@ -618,8 +795,9 @@ int colpath_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, 
   if (!cp.built) return fail(GRMP_ESTATE, "column kernels: records not built");
   if (cp.ntiles == 0) return GRMP_OK;
   cudaStream_t s = ctx->stream;
-  const Variant& V = VARIANTS[cp.variant];
-  if (g_const_owner != cp.uid) {
+  const bool cf = cp.cf_variant >= 0;
+  const Variant& V = VARIANTS[cf ? 0 : cp.variant];
+  if (!cf && g_const_owner != cp.uid) {
     GRMP_CUDA(cudaMemcpyToSymbolAsync(c_tabR, cp.tabR.data(), cp.tabR.size() * 8, 0, cudaMemcpyHostToDevice, s));
     GRMP_CUDA(cudaMemcpyToSymbolAsync(c_wq, cp.wq.data(), cp.wq.size() * 8, 0, cudaMemcpyHostToDevice, s));
     g_const_owner = cp.uid;
@@ -629,10 +807,12 @@ int colpath_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, 
   cpar.pos_recbeg = cp.pos_recbeg.p; cpar.geo = cp.geo.p; cpar.tabC = cp.tabC.p;
   cpar.factor = p.factor; cpar.act_p[0] = p.act_p[0]; cpar.act_p[1] = p.act_p[1]; cpar.nzval = nzval;
   cpar.ncols_used = cp.ncols_used; cpar.ngroups = cp.ngroups; cpar.nw = cp.nw; cpar.nq = cp.nq;
-  GRMP_TRY(V.geo(p.g, cp.geo.p, s));     // update_trafo! / mapderiv! / coefficient data of every cell, once per assembly
+  // update_trafo! / mapderiv! / coefficient data of every cell, once per assembly
+  if (cf) GRMP_TRY(CFVARIANTS[cp.cf_variant].geo(p.g, p.act_p, cp.geo.p, s)); else GRMP_TRY(V.geo(p.g, cp.geo.p, s));
   for (const auto& c : cp.classes) {     // big tiles first: they have the fewest CTAs per SM and would otherwise be the tail
     cpar.tile_list = cp.class_tiles.p + c.first;
-    GRMP_TRY(V.launch(cpar, (int)c.count, 32 * cp.nw, c.smem_bytes, s));
+    if (cf) GRMP_TRY(CFVARIANTS[cp.cf_variant].launch(cpar, (int)c.count, 32 * cp.nw, c.smem_bytes, s));
+    else GRMP_TRY(V.launch(cpar, (int)c.count, 32 * cp.nw, c.smem_bytes, s));
   }
   return GRMP_OK;
 }

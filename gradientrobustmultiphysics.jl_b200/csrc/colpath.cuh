@@ -24,7 +24,8 @@ struct ColPath {
   bool built = false;
   u64 uid = 0;                     // identifies whose tables sit in constant memory
   int variant = 0;                 // index into the kernel table (colpath.cu)
-  int nw = 8;                      // warps (= groups of 32 columns) per CTA / tile
+  int cf_variant = -1;             // >= 0: closed-form kernel (reference tensors instead of a quadrature loop)
+  int nw = 4;                      // warps (= groups of 32 columns) per CTA / tile
   int nv = 1;                      // 16-byte vectors per pair record
   int nq = 0;
   i64 ncols_used = 0, ngroups = 0, ntiles = 0, npairs = 0;

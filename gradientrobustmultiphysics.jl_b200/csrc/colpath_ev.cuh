@@ -552,3 +552,217 @@ template <class Ev> __host__ inline bool ev_matches(const ColEvalDesc& d) {
 }
 
 }  // namespace grmp
+
+// ==== closed-form ("reference tensor") evaluators ==============================================================================
+// On affine cells every local entry of the forms below is
+//     local[r, c] = sum_t G_t(cell) * K_t[r][c],     K_t[r][c] = sum_q w_q T_R[r][a][q] T_C[c][b][q],  t = (a, b)
+// (the quadrature sum commutes with the cell's constant Jacobian; bilinearform.jl:294-317 with feevaluator_h1.jl:61-74,
+// feevaluator_hdiv.jl:2-19).  K is formed ONCE from the caller's tables and weights (host, colpath_build), G once per cell
+// (cell_geo_kernel), and a column thread needs NT fused multiply-adds per local row instead of a quadrature loop.
+// The classes share the pair records of the quadrature evaluators above (same NROW, same row numbering).
+namespace grmp {
+
+__host__ __device__ constexpr int nsym(int ed) { return ed * (ed + 1) / 2; }
+__host__ __device__ constexpr int sym_a(int ed, int t) { return ed == 2 ? (t == 0 ? 0 : (t == 1 ? 0 : 1)) : (t < 3 ? 0 : (t < 5 ? 1 : 2)); }
+__host__ __device__ constexpr int sym_b(int ed, int t) { return ed == 2 ? (t == 0 ? 0 : (t == 1 ? 1 : 1)) : (t == 0 ? 0 : t == 1 ? 1 : t == 2 ? 2 : t == 3 ? 1 : t == 4 ? 2 : 2); }
+
+// ---- H1 (componentwise, + Bernardi-Raugel bubbles): [Gradient, Gradient] (OPK = GRMP_OP_GRAD) or [Identity, Identity] (GRMP_OP_ID),
+//      NoAction.  Scalar matrix column Sc[s] = sum_t G_t K_t[s][s_col]; entries = component weights x Sc (h1v_br.jl:150-162).
+template <int ED_, int NC_, int NDS_, int NBUB_, int OPK_> struct CfH1 {
+  static constexpr int ED = ED_, NC = NC_, NDS = NDS_, NBUB = NBUB_, OPK = OPK_;
+  static constexpr int NSF = NDS + NBUB, NROW = NC * NDS + NBUB;
+  static constexpr int NT = OPK == GRMP_OP_GRAD ? nsym(ED) : 1;      // symmetric G: K_t = K_ab + K_ba for a != b
+  static constexpr bool SYMK = true;
+  static constexpr int GEO_N = NT + NBUB * ED;
+  static constexpr int STRIDE = (GEO_N + 1) & ~1;
+  using Quad = H1Ev<ED, NC, NDS, NBUB, OPK>;                           // the quadrature evaluator with the same records / tables
+  static constexpr int ACT = GRMP_ACT_NONE;
+  __device__ __forceinline__ static void geo(const GridView& g, i64 cell, const double* act_p, double* out) {
+    CellGeo<ED> T;
+    cell_geo<ED>(g, cell, T);
+    const double vol = g.vol[cell];
+    if constexpr (OPK == GRMP_OP_GRAD) {
+#pragma unroll
+      for (int t = 0; t < NT; t++) {
+        const int a = sym_a(ED, t), b = sym_b(ED, t);
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < ED; k++) s = fma(T.Ainv[k][a], T.Ainv[k][b], s);
+        out[t] = vol * s;
+      }
+    } else out[0] = vol;
+    if constexpr (NBUB > 0) {
+      const i32* cf = g.cellfaces + cell * (ED + 1);
+#pragma unroll
+      for (int b = 0; b < NBUB; b++)
+#pragma unroll
+        for (int c = 0; c < ED; c++) out[NT + b * ED + c] = g.fnormals[(i64)(cf[b] - 1) * ED + c];
+    }
+  }
+  // one (cell, column) pair: emit(row, value / factor)
+  template <class F> __device__ __forceinline__ static void column(const double* __restrict__ cr, int l, const double* __restrict__ sK, F&& emit) {
+    int scol;
+    double beta[NC];
+    if (NBUB > 0 && l >= NC * NDS) {
+      const int b = l - NC * NDS;
+      scol = NDS + b;
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        double v = 0.0;
+#pragma unroll
+        for (int bb = 0; bb < NBUB; bb++) v = (bb == b) ? cr[NT + bb * ED + c] : v;
+        beta[c] = v;
+      }
+    } else {
+      const int cl = l / NDS;
+      scol = l - cl * NDS;
+#pragma unroll
+      for (int c = 0; c < NC; c++) beta[c] = (c == cl) ? 1.0 : 0.0;
+    }
+    double G[NT];
+#pragma unroll
+    for (int t = 0; t < NT; t++) G[t] = cr[t];
+    double Sc[NSF];
+#pragma unroll
+    for (int s = 0; s < NSF; s++) {
+      double v = 0.0;
+#pragma unroll
+      for (int t = 0; t < NT; t++) v = fma(G[t], sK[(t * NSF + s) * CT_PAD + scol], v);
+      Sc[s] = v;
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+#pragma unroll
+      for (int s = 0; s < NDS; s++) emit(c * NDS + s, beta[c] * Sc[s]);
+#pragma unroll
+    for (int b = 0; b < NBUB; b++) {
+      double t = 0.0;
+#pragma unroll
+      for (int c = 0; c < NC; c++) t = fma(cr[NT + b * ED + c], beta[c], t);
+      emit(NC * NDS + b, t * Sc[NDS + b]);
+    }
+  }
+};
+
+// ---- vector H1 [SymmetricGradient, SymmetricGradient] with the isotropic Hooke tensor (pdeoperators.jl:256-315): for
+//      u = phi e_c (row), v = psi e_c' (column):  C eps(u) : eps(v) = sum_kl E[c][k][c'][l] d_k phi d_l psi with
+//      c == c': (lambda + 2 mu) d_c d_c + mu sum_{k != c} d_k d_k;   c != c': lambda d_c phi d_c' psi + mu d_c' phi d_c psi
+//      (Voigt form with summed off-diagonals, feevaluator_h1.jl:97-116, offdiagval = 1).
+//      G[c'][c][a][b] = |T| sum_kl Ainv[k][a] E[c][k][c'][l] Ainv[l][b]: the column's block of NC ED^2 numbers is contiguous.
+template <int ED_, int NDS_> struct CfHooke {
+  static constexpr int ED = ED_, NC = ED_, NDS = NDS_, NBUB = 0, OPK = GRMP_OP_SYMGRAD;
+  static constexpr int NSF = NDS, NROW = NC * NDS;
+  static constexpr int NT = ED * ED;                 // K_ab not symmetrised
+  static constexpr bool SYMK = false;
+  static constexpr int GEO_N = NC * NC * ED * ED;
+  static constexpr int STRIDE = (GEO_N + 1) & ~1;
+  using Quad = H1Ev<ED, ED, NDS, 0, GRMP_OP_SYMGRAD>;
+  static constexpr int ACT = ED == 2 ? GRMP_ACT_HOOKE2D : GRMP_ACT_HOOKE3D;
+  __device__ __forceinline__ static void geo(const GridView& g, i64 cell, const double* act_p, double* out) {
+    CellGeo<ED> T;
+    cell_geo<ED>(g, cell, T);
+    const double vol = g.vol[cell], mu = act_p[0], la = act_p[1];
+#pragma unroll
+    for (int cc = 0; cc < NC; cc++)        // column component c'
+#pragma unroll
+      for (int c = 0; c < NC; c++)         // row component c
+#pragma unroll
+        for (int a = 0; a < ED; a++)
+#pragma unroll
+          for (int b = 0; b < ED; b++) {
+            double s;
+            if (c == cc) {
+              s = (la + 2.0 * mu) * T.Ainv[c][a] * T.Ainv[c][b];
+#pragma unroll
+              for (int k = 0; k < ED; k++)
+                if (k != c) s = fma(mu * T.Ainv[k][a], T.Ainv[k][b], s);
+            } else {
+              s = la * T.Ainv[c][a] * T.Ainv[cc][b] + mu * T.Ainv[cc][a] * T.Ainv[c][b];
+            }
+            out[((cc * NC + c) * ED + a) * ED + b] = vol * s;
+          }
+  }
+  template <class F> __device__ __forceinline__ static void column(const double* __restrict__ cr, int l, const double* __restrict__ sK, F&& emit) {
+    const int cl = l / NDS, scol = l - cl * NDS;
+    double G[NC][NT];
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+#pragma unroll
+      for (int t = 0; t < NT; t++) {
+        double v = 0.0;
+#pragma unroll
+        for (int cc = 0; cc < NC; cc++) v = (cc == cl) ? cr[(cc * NC + c) * NT + t] : v;
+        G[c][t] = v;
+      }
+#pragma unroll
+    for (int s = 0; s < NDS; s++) {
+      double k[NT];
+#pragma unroll
+      for (int t = 0; t < NT; t++) k[t] = sK[(t * NSF + s) * CT_PAD + scol];
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        double v = 0.0;
+#pragma unroll
+        for (int t = 0; t < NT; t++) v = fma(G[c][t], k[t], v);
+        emit(c * NDS + s, v);
+      }
+    }
+  }
+};
+
+// ---- Hdiv [Identity, Identity] (mass, contravariant Piola, feevaluator_hdiv.jl:2-19): G_t = |T| / det^2 (A^T A)_ab, signs of the
+//      reference functions from CellFaceSigns / orientations (HdivEv::negmask); rows are REFERENCE functions (records map them)
+template <int ED_, int NDALL_> struct CfHdivMass {
+  static constexpr int ED = ED_, NC = 1, NDS = NDALL_, NBUB = 0, OPK = GRMP_OP_ID;
+  static constexpr int NSF = NDALL_, NROW = NDALL_;
+  static constexpr int NT = nsym(ED);
+  static constexpr bool SYMK = true;
+  static constexpr int GEO_N = NT + 1;
+  static constexpr int STRIDE = (GEO_N + 1) & ~1;
+  using Quad = HdivEv<ED, NDALL_, GRMP_OP_ID>;
+  static constexpr int ACT = GRMP_ACT_NONE;
+  __device__ __forceinline__ static void geo(const GridView& g, i64 cell, const double* act_p, double* out) {
+    CellGeo<ED> T;
+    cell_geo<ED>(g, cell, T);
+    const double f = g.vol[cell] * T.idet * T.idet;
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+      const int a = sym_a(ED, t), b = sym_b(ED, t);
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < ED; k++) s = fma(T.A[k][a], T.A[k][b], s);
+      out[t] = f * s;
+    }
+    out[NT] = __longlong_as_double((long long)Quad::negmask(g, cell));
+  }
+  template <class F> __device__ __forceinline__ static void column(const double* __restrict__ cr, int l, const double* __restrict__ sK, F&& emit) {
+    const u32 neg = (u32)__double_as_longlong(cr[NT]);
+    const u32 flip = ((neg >> l) & 1u) ? ~neg : neg;      // bit r: sign_r * sign_l < 0
+    double G[NT];
+#pragma unroll
+    for (int t = 0; t < NT; t++) G[t] = cr[t];
+#pragma unroll
+    for (int r = 0; r < NDALL_; r++) {
+      double v = 0.0;
+#pragma unroll
+      for (int t = 0; t < NT; t++) v = fma(G[t], sK[(t * NSF + r) * CT_PAD + l], v);
+      emit(r, ((flip >> r) & 1u) ? -v : v);
+    }
+  }
+};
+
+// forms with a closed-form kernel: Y(class, NQ of the rule prepare_assembly! picks -- only used to match the quadrature variant
+// whose records are shared)
+#define GRMP_CF_FORMS(Y)                                                                                                   \
+  Y((CfH1<2, 1, 3, 0, GRMP_OP_GRAD>)) Y((CfH1<2, 2, 3, 0, GRMP_OP_GRAD>)) Y((CfH1<2, 1, 6, 0, GRMP_OP_GRAD>))            \
+  Y((CfH1<2, 2, 6, 0, GRMP_OP_GRAD>)) Y((CfH1<2, 2, 3, 3, GRMP_OP_GRAD>))                                                 \
+  Y((CfH1<3, 1, 4, 0, GRMP_OP_GRAD>)) Y((CfH1<3, 3, 4, 0, GRMP_OP_GRAD>)) Y((CfH1<3, 1, 10, 0, GRMP_OP_GRAD>))           \
+  Y((CfH1<3, 3, 10, 0, GRMP_OP_GRAD>)) Y((CfH1<3, 3, 4, 4, GRMP_OP_GRAD>))                                                \
+  Y((CfH1<2, 1, 3, 0, GRMP_OP_ID>)) Y((CfH1<2, 2, 3, 0, GRMP_OP_ID>)) Y((CfH1<2, 1, 6, 0, GRMP_OP_ID>))                  \
+  Y((CfH1<2, 2, 6, 0, GRMP_OP_ID>)) Y((CfH1<2, 2, 3, 3, GRMP_OP_ID>))                                                     \
+  Y((CfH1<3, 1, 4, 0, GRMP_OP_ID>)) Y((CfH1<3, 3, 4, 0, GRMP_OP_ID>)) Y((CfH1<3, 1, 10, 0, GRMP_OP_ID>))                 \
+  Y((CfH1<3, 3, 10, 0, GRMP_OP_ID>))                                                                                      \
+  Y((CfHooke<2, 3>)) Y((CfHooke<2, 6>)) Y((CfHooke<3, 4>)) Y((CfHooke<3, 10>))                                            \
+  Y((CfHdivMass<2, 3>)) Y((CfHdivMass<2, 6>)) Y((CfHdivMass<3, 4>)) Y((CfHdivMass<3, 16>))
+
+}  // namespace grmp

@@ -173,4 +173,21 @@ struct LfLocalParams {
 };
 int launch_lf_local(const LfLocalParams& p, cudaStream_t s);
 
+// ItemIntegrator with one argument (itemintegrator.jl:160-300)
+struct IiLocalParams {
+  GridView g;
+  EvalView e;
+  RegionFilter reg;
+  int nq;
+  const double* w;
+  int kind;              // GRMP_II_*
+  int ardim;             // result length: rd (NONE) or 1
+  double factor;         // L2ERROR: || data - factor * discrete ||
+  const double* coeffs;  // device, [ndofs] entries of the FEVectorBlock
+  const double* data;    // device, [ncells][nq][rd] (L2ERROR)
+  double* b;             // device, [ncells][ardim], updated in place (b[j,item] += ...), or null
+  double* itemval;       // device, [ardim][ncells]: the item's own sum (0 for filtered cells), for the total
+};
+int launch_ii_local(const IiLocalParams& p, cudaStream_t s);
+
 }  // namespace grmp

@@ -410,6 +410,87 @@ __global__ void __launch_bounds__(128) lf_local_kernel(const LfLocalParams p) {
   for (int d = 0; d < nd; d++) p.lbuf[(i64)d * ncells + cell] = lb[d] * itemfactor;
 }
 
+// ItemIntegrator evaluate! (itemintegrator.jl:222-296): one thread per item, reference operation order.
+//   input_i[k] = sum_dof coeffs[dof] * cvals[k,dof,i] * 1 from 0 in dof order (eval_febe!, feevaluator.jl:445-452)
+//   NONE: result = input;  L2NORM (99-108): sum_j (0 + input[j])^2;  L2ERROR (52-69): sum_j (data[j] - input[j]*factor)^2
+//   b[j,item] += result[j] * w_i * |T|  (266 / 291)
+template <int NDMAX, bool RECON>
+__global__ void __launch_bounds__(128) ii_local_kernel(const IiLocalParams p) {
+  const i64 cell = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (cell >= p.g.ncells) return;
+  const int nd = p.e.nd, edim = p.g.dim, rdim = p.e.rd, ardim = p.ardim;
+  const i64 ncells = p.g.ncells;
+  if (!cell_active(p.g, p.reg, cell)) {
+    for (int j = 0; j < ardim; j++) p.itemval[(i64)j * ncells + cell] = 0.0;
+    return;
+  }
+  Geo T;
+  geo_update(p.g, cell, T);
+  if (needs_inverse(p.e)) geo_mapderiv(p.g, cell, T);
+  CellCoef<NDMAX> cc;
+  double rc[RECON ? NDMAX : 1][12];
+  const bool r = is_recon(p.e.op);
+  cell_coefficients<NDMAX>(p.g, cell, r ? p.e.rfam : p.e.fam, r ? p.e.nd2 : nd, p.e.ncomp, cc);
+  if (RECON && r) {
+    for (int a = 0; a < nd; a++)
+      for (int b = 0; b < 12; b++) rc[a][b] = 0.0;
+    recon_coefficients<NDMAX>(p.g, cell, p.e.op, rc);
+  }
+  double c[NDMAX];
+  for (int d = 0; d < nd; d++) c[d] = p.coeffs[p.e.celldofs[cell * nd + d] - 1] * 1.0;
+  double acc[RDMAX], own[RDMAX];
+  for (int j = 0; j < ardim; j++) { acc[j] = p.b ? p.b[cell * ardim + j] : 0.0; own[j] = 0.0; }
+  double cv[RDMAX][NDMAX];
+  const double vol = p.g.vol[cell];
+  for (int i = 0; i < p.nq; i++) {
+    eval_qp<NDMAX, RECON>(p.e, edim, T, cc, rc, i, cv);
+    double in[RDMAX], res[RDMAX];
+    for (int k = 0; k < rdim; k++) in[k] = 0.0;
+    for (int d = 0; d < nd; d++)
+      for (int k = 0; k < rdim; k++) in[k] += c[d] * cv[k][d] * 1.0;
+    if (p.kind == GRMP_II_NONE) {
+      for (int j = 0; j < rdim; j++) res[j] = in[j];
+    } else if (p.kind == GRMP_II_L2NORM) {
+      double rr = 0.0;
+      for (int j = 0; j < rdim; j++) { double t = 0.0; t += in[j]; rr += t * t; }
+      res[0] = rr;
+    } else {
+      const double* dv = p.data + ((size_t)cell * p.nq + i) * rdim;
+      double rr = 0.0;
+      for (int j = 0; j < rdim; j++) { double v = dv[j]; v -= in[j] * p.factor; rr += v * v; }
+      res[0] = rr;
+    }
+    const double wi = p.w[i];
+    for (int j = 0; j < ardim; j++) {
+      const double term = res[j] * wi * vol;
+      acc[j] += term;
+      own[j] += term;
+    }
+  }
+  for (int j = 0; j < ardim; j++) {
+    if (p.b) p.b[cell * ardim + j] = acc[j];
+    p.itemval[(i64)j * ncells + cell] = own[j];
+  }
+}
+
+int launch_ii_local(const IiLocalParams& p, cudaStream_t s) {
+  const bool recon = (p.e.op == GRMP_OP_RECON_ID_RT0 || p.e.op == GRMP_OP_RECON_ID_BDM1);
+  if (p.g.ncells == 0) return GRMP_OK;
+  if (p.e.rd > RDMAX) return fail(GRMP_EUNSUPPORTED, "operator result longer than 9");
+  const unsigned grid = (unsigned)((p.g.ncells + 127) / 128);
+  if (recon) {
+    if (p.e.nd > 16) return fail(GRMP_EUNSUPPORTED, "reconstruction operators support at most 16 local dofs");
+    ii_local_kernel<16, true><<<grid, 128, 0, s>>>(p);
+  } else if (p.e.nd <= 16)
+    ii_local_kernel<16, false><<<grid, 128, 0, s>>>(p);
+  else if (p.e.nd <= 30)
+    ii_local_kernel<30, false><<<grid, 128, 0, s>>>(p);
+  else
+    return fail(GRMP_EUNSUPPORTED, "more than 30 local dofs per cell");
+  GRMP_CUDA(cudaGetLastError());
+  return GRMP_OK;
+}
+
 int launch_blf_local(const BlfLocalParams& p, cudaStream_t s) {
   const int nmax = p.e1.nd > p.e2.nd ? p.e1.nd : p.e2.nd;
   const bool recon = (p.e1.op == GRMP_OP_RECON_ID_RT0 || p.e1.op == GRMP_OP_RECON_ID_BDM1 || p.e2.op == GRMP_OP_RECON_ID_RT0 ||

@@ -129,4 +129,13 @@ int launch_residual_finish(cudaStream_t s, double* r, const double* b, i64 n, co
   return GRMP_OK;
 }
 
+int device_sum(cudaStream_t s, const double* x, i64 n, double* out_dev, DevBuf<unsigned char>* tmp) {
+  if (n <= 0) { GRMP_CUDA(cudaMemsetAsync(out_dev, 0, 8, s)); return GRMP_OK; }
+  size_t tb = 0;
+  GRMP_CUDA(cub::DeviceReduce::Sum(nullptr, tb, x, out_dev, n, s));
+  if (tb > tmp->n) GRMP_TRY(tmp->alloc(std::max<size_t>(tb, 16)));
+  GRMP_CUDA(cub::DeviceReduce::Sum(tmp->p, tb, x, out_dev, n, s));
+  return GRMP_OK;
+}
+
 }  // namespace grmp

@@ -23,4 +23,7 @@ int launch_penalties(cudaStream_t s, const Pattern& pat, double* nzval, const i6
 // r = r - b, r[fixed] = 0, *norm2 = sum r^2 (deterministic two-stage reduction)
 int launch_residual_finish(cudaStream_t s, double* r, const double* b, i64 n, const i64* fixed_dofs_dev, i64 nfixed, double* norm2_dev);
 
+// *out_dev = sum x[0..n) (cub::DeviceReduce: fixed tree for a given n -> deterministic); tmp is reused between calls
+int device_sum(cudaStream_t s, const double* x, i64 n, double* out_dev, DevBuf<unsigned char>* tmp);
+
 }  // namespace grmp

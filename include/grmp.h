@@ -218,6 +218,27 @@ int grmp_lf_set_path(grmp_lf* lf, int path);
 int grmp_lf_assemble(grmp_lf* lf, double factor, int fsrc, const double* fdata, double* b_host, int64_t offset);
 int grmp_lf_stats(grmp_lf* lf, grmp_stats* out);
 
+/* ---- ItemIntegrator with one argument (src/assemblypatterns/itemintegrator.jl:18-21, 160-360): the error norms every example ends
+ * with.  The closed set of kernels evaluated on the device:
+ *   GRMP_II_NONE     NoAction: b[j,item] += (operator evaluation of the FE function)[j] * w_i * |T|       (itemintegrator.jl:262-268)
+ *   GRMP_II_L2NORM   L2NormIntegrator(ncomponents, operator)  (91-110): sum_j input[j]^2
+ *   GRMP_II_L2ERROR  L2ErrorIntegrator(compare_data, operator; factor) (33-78): sum_j (compare_data(x)[j] - factor * input[j])^2, with
+ *                    compare_data tabulated by the host at the quadrature points, data[ncells][nq][resultdim of the operator]
+ * Other user Actions cannot cross a C ABI and stay on the reference path. */
+enum { GRMP_II_NONE = 0, GRMP_II_L2NORM = 1, GRMP_II_L2ERROR = 2 };
+typedef struct grmp_ii grmp_ii;
+int grmp_ii_create(grmp_space* space, int op, int kind, const int32_t* regions, int nregions, int nq, const double* qweights,
+                   const grmp_evaltab* tab, grmp_ii** out);
+int grmp_ii_destroy(grmp_ii* ii);
+/* length of the result per item: the operator's result length (NONE) or 1 */
+int grmp_ii_resultdim(grmp_ii* ii, int* resultdim);
+/* evaluate!(b, AP, FEB) (itemintegrator.jl:160-300): coeffs_host = the entries of the FEVectorBlock (ndofs of the space);
+ * b_host [ncells][resultdim] (Julia: resultdim x nitems, column-major) is updated in place, b[j,item] += ..., bit-identical to the
+ * reference's loop; may be NULL.  total_host[resultdim] (may be NULL) receives what evaluate(AP, FEB) (316-360) returns, the sum over
+ * all items: the reference adds every (item, quadrature point) term to one running sum, the device adds the items' own sums in a
+ * fixed tree order -- deterministic, equal to the reference to rounding (1e-12 relative for the norms, whose terms are >= 0). */
+int grmp_ii_evaluate(grmp_ii* ii, const double* coeffs_host, double factor, const double* data_host, double* b_host, double* total_host);
+
 #ifdef __cplusplus
 }
 #endif

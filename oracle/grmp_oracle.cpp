@@ -65,6 +65,7 @@ enum Op { OP_ID = 1, OP_GRAD = 2, OP_SYMGRAD = 3, OP_DIV = 4, OP_RECON_ID_RT0 = 
 enum Action { ACT_NONE = 0, ACT_HOOKE2D = 1, ACT_HOOKE3D = 2 };
 enum APT { APT_GENERAL = 0, APT_SYMMETRIC = 1, APT_LUMPED = 2 };
 enum FSrc { F_NONE = 0, F_CONST = 1, F_QP_TABLE = 2 };
+enum IIKind { II_NONE = 0, II_L2NORM = 1, II_L2ERROR = 2 };
 
 inline bool is_recon(int op) { return op == OP_RECON_ID_RT0 || op == OP_RECON_ID_BDM1; }
 
@@ -943,6 +944,61 @@ int orc_lf_assemble(double* b, const orc_grid* og, const orc_space* os, int op, 
     const i32* dofs = s.celldofs + item * nd;
     for (int d = 0; d < nd; d++) b[dofs[d] - 1 + offset] += localb[d] * itemfactor;   // 216-220
     std::fill(localb.begin(), localb.end(), 0.0);
+  }
+  return 0;
+}
+
+// ---- ItemIntegrator evaluate! / evaluate (src/assemblypatterns/itemintegrator.jl:160-300, 316-360), one argument ------------
+// kind: II_NONE  -> NoAction: b[j,item] += input_i[j] * w_i * |T|                                   (262-268)
+//       II_L2NORM -> L2NormIntegrator kernel (99-108): temp[j] = 0 + input[j]; result = sum_j temp[j]^2
+//       II_L2ERROR-> L2ErrorIntegrator kernel (52-69): val[j] = data(x_i)[j] - input[j]*factor; result = sum_j val[j]^2
+//                   (data[cell][qp][ncomp] = compare_data evaluated by the host at the quadrature points)
+// input_i[k] = sum_dof coeffs[dof] * cvals[k,dof,i] * 1 accumulated from 0 in dof order (eval_febe!, feevaluator.jl:445-452).
+// b may be NULL; total[resultdim] (may be NULL) is what evaluate() returns: every (item, qp) term added to ONE running sum in
+// loop order (AccumulatingVector, 346-352).
+int orc_ii_evaluate(double* b, double* total, const orc_grid* og, const orc_space* os, int op, int kind, const double* coeffs,
+                    double factor, const double* data, const i32* regions, int nregions, int bonus_quadorder, int* nq_out,
+                    int* resultdim_out) {
+  Grid g = to_grid(og); Space s = to_space(os);
+  int edim = g.dim;
+  int quadorder = bonus_quadorder + polyorder_of(s, edim) + quadorder_shift(op);
+  if (quadorder < 0) quadorder = 0;
+  QRule q; if (!make_qrule(edim, quadorder, q)) return -1;
+  if (nq_out) *nq_out = q.n();
+  Evaluator e; if (!e.init(&g, s, op, q)) return -1;
+  const int nd = e.nd, nq = q.n(), rdim = e.resultdim;
+  const int ardim = (kind == II_NONE) ? rdim : 1;
+  if (resultdim_out) *resultdim_out = ardim;
+  if (!coeffs) return 0;
+  std::vector<double> input(rdim, 0.0), res(ardim, 0.0), c(nd, 0.0);
+  if (total) for (int j = 0; j < ardim; j++) total[j] = 0.0;
+  for (i64 item = 0; item < g.ncells; item++) {
+    if (!in_regions(g, item, regions, nregions)) continue;
+    e.update(item);
+    const i32* dofs = s.celldofs + item * nd;
+    for (int d = 0; d < nd; d++) c[d] = coeffs[dofs[d] - 1] * 1.0;     // get_coeffs! ; coeffs .*= coeff4dofitem (234-236)
+    for (int i = 0; i < nq; i++) {
+      std::fill(input.begin(), input.end(), 0.0);
+      for (int d = 0; d < nd; d++)
+        for (int k = 0; k < rdim; k++) input[k] += c[d] * e.cv(k, d, i) * 1;
+      if (kind == II_NONE) {
+        for (int j = 0; j < rdim; j++) res[j] = input[j];
+      } else if (kind == II_L2NORM) {
+        double r = 0;
+        for (int j = 0; j < rdim; j++) { double t = 0.0; t += input[j]; r += t * t; }
+        res[0] = r;
+      } else {
+        const double* dv = data + ((size_t)item * nq + i) * rdim;
+        double r = 0;
+        for (int j = 0; j < rdim; j++) { double v = dv[j]; v -= input[j] * factor; r += v * v; }
+        res[0] = r;
+      }
+      for (int j = 0; j < ardim; j++) {
+        const double term = res[j] * q.w[i] * g.vol[item];               // 266 / 291
+        if (b) b[(size_t)item * ardim + j] += term;
+        if (total) total[j] += term;
+      }
+    }
   }
   return 0;
 }

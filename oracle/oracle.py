@@ -23,6 +23,7 @@ OP_ID, OP_GRAD, OP_SYMGRAD, OP_DIV, OP_RECON_ID_RT0, OP_RECON_ID_BDM1 = 1, 2, 3,
 ACT_NONE, ACT_HOOKE2D, ACT_HOOKE3D = 0, 1, 2
 APT_GENERAL, APT_SYMMETRIC, APT_LUMPED = 0, 1, 2
 F_NONE, F_CONST, F_QP_TABLE = 0, 1, 2
+II_NONE, II_L2NORM, II_L2ERROR = 0, 1, 2
 
 
 class _Grid(C.Structure):
@@ -60,6 +61,8 @@ def lib():
                                           C.c_double, C.c_int64, C.c_int64, C.c_int]
         _LIB.orc_lf_assemble.argtypes = [C.c_void_p, C.POINTER(_Grid), C.POINTER(_Space), C.c_int, C.c_int, C.c_void_p,
                                          C.c_void_p, C.c_int, C.c_double, C.c_int64, C.c_int, C.c_void_p]
+        _LIB.orc_ii_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_Grid), C.POINTER(_Space), C.c_int, C.c_int, C.c_void_p,
+                                         C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _LIB.orc_quadpoints.argtypes = [C.POINTER(_Grid), C.c_int, C.c_void_p]
         _LIB.orc_qrule.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _LIB.orc_reftables.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -211,6 +214,28 @@ def reftables(fecode, ncomp, edim, xref, nd_all, ncomp_eff):
     der = np.zeros((x.shape[0], edim, nd_all * ncomp_eff))
     _check(lib().orc_reftables(fecode, ncomp, edim, x.shape[0], _p(x), _p(vals), _p(der)))
     return vals, der
+
+
+def ii_evaluate(grid, space, op, coeffs, *, kind=II_NONE, factor=1.0, data=None, regions=(0,), bonus_quadorder=0, itemwise=True, b=None):
+    """evaluate!(b, AP, FEB) / evaluate(AP, FEB) of a one-argument ItemIntegrator -- itemintegrator.jl:160-360.
+    Returns (b[ncells, resultdim] or None, total[resultdim]); total is the reference's running sum over (item, qp);
+    a caller-given b is updated in place (b[j,item] += ...)."""
+    g = _grid_struct(grid, _needs_faces(space))
+    s = _space_struct(space)
+    rg = np.ascontiguousarray(regions, dtype=np.int32)
+    nq, rd = C.c_int(0), C.c_int(0)
+    _check(lib().orc_ii_evaluate(None, None, C.byref(g.s), C.byref(s.s), op, kind, None, 1.0, None, _p(rg), rg.size, bonus_quadorder,
+                                 C.byref(nq), C.byref(rd)))
+    c = np.ascontiguousarray(coeffs, dtype=np.float64)
+    d = None if data is None else np.ascontiguousarray(data, dtype=np.float64)
+    if b is None:
+        b = np.zeros((g.cellnodes.shape[0], rd.value)) if itemwise else None
+    else:
+        assert b.dtype == np.float64 and b.flags.c_contiguous and b.shape == (g.cellnodes.shape[0], rd.value)
+    total = np.zeros(rd.value)
+    _check(lib().orc_ii_evaluate(_p(b), _p(total), C.byref(g.s), C.byref(s.s), op, kind, _p(c), float(factor), _p(d), _p(rg), rg.size,
+                                 bonus_quadorder, None, None))
+    return b, total
 
 
 def quadpoints(grid, order):

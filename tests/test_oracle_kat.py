@@ -280,3 +280,41 @@ def test_pattern_zero_skip_and_flush_semantics():
     O.blf_assemble(A, g, s, s, O.OP_GRAD, O.OP_GRAD, apt=O.APT_SYMMETRIC)
     cp2, rv2, nz2 = A.csc()
     assert np.array_equal(cp, cp2) and np.array_equal(rv, rv2) and np.array_equal(nz, nz2)
+
+
+# ---- ItemIntegrator (itemintegrator.jl:160-360): the error norms the reference's tests end with --------------------------------
+@pytest.mark.parametrize("dim", [2, 3])
+def test_itemintegrator_l2error_of_exact_interpolant_vanishes(dim):
+    """test/runtests.jl:355-509 measure ||u - u_h|| with L2ErrorIntegrator: zero (to 1e-12) when u is in the discrete space, and the
+    closed-form value for a function that is not; integral of the identity reproduces the integral of the polynomial"""
+    g = tri_grid(2) if dim == 2 else tet_grid(1)
+    s = G.FESpace(G.H1P2(1, dim), g)
+    f = (lambda p: p[0] ** 2 + p[1] - 0.5 * p[0] * p[dim - 1])
+    u = nodal_interpolate(s, f)
+    qo = 4                                           # 2 * bonus_quadorder of a quadratic DataFunction
+    xq = O.quadpoints(g, qo + 2)                     # order = bonus + polynomial order of the space (assemblypatterns.jl:559-565)
+    data = np.array([[f(p) for p in cell] for cell in xq])[..., None]
+    b, tot = O.ii_evaluate(g, s, O.OP_ID, u, kind=O.II_L2ERROR, data=data, bonus_quadorder=qo)
+    assert b.shape == (g.ncells, 1) and abs(tot[0]) < TOL ** 2 and abs(b.sum() - tot[0]) < 1e-20
+    # the integral of u itself (NoAction): int x^2 + y - xy/2 (2D) or x^2 + y - xz/2 (3D) over the unit square / cube
+    exact = 1 / 3 + 1 / 2 - 1 / 8
+    _, tot = O.ii_evaluate(g, s, O.OP_ID, u, kind=O.II_NONE, bonus_quadorder=0)
+    assert abs(tot[0] - exact) < TOL
+    # L2 norm of the gradient of u = x (all dims): |grad u|^2 = 1 -> 1
+    u1 = nodal_interpolate(s, lambda p: p[0])
+    _, tot = O.ii_evaluate(g, s, O.OP_GRAD, u1, kind=O.II_L2NORM, bonus_quadorder=2)
+    assert abs(tot[0] - 1.0) < TOL
+    # a function outside the space: || x^3 - I_h x^3 || > 0 and || 0 - x ||^2 = 1/3 with factor
+    z = np.zeros((g.ncells, xq.shape[1], 1))
+    _, tot = O.ii_evaluate(g, s, O.OP_ID, u1, kind=O.II_L2ERROR, data=z, factor=2.0, bonus_quadorder=qo)
+    assert abs(tot[0] - 4.0 / 3.0) < TOL
+
+
+def test_itemintegrator_regions_and_itemwise_sum():
+    g = tri_grid(2)
+    g.cellregions[: g.ncells // 2] = 2
+    s = G.FESpace(G.H1P1(1), g)
+    u = nodal_interpolate(s, lambda p: 1.0)
+    b, tot = O.ii_evaluate(g, s, O.OP_ID, u, kind=O.II_NONE, regions=[2])
+    assert abs(tot[0] - g.cellvolumes[: g.ncells // 2].sum()) < 1e-14
+    assert np.all(b[g.ncells // 2:] == 0) and np.allclose(b[: g.ncells // 2, 0], g.cellvolumes[: g.ncells // 2], rtol=1e-15)
