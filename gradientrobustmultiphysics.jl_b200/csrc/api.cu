@@ -432,7 +432,7 @@ int grmp_blf_symbolic(grmp_blf* b, double factor, int64_t* nnz_out) {
   }
   if (b->path == GRMP_PATH_GENERIC && col_ok && req != GRMP_PATH_GENERIC) {
     const int rc = colpath_build(ctx, p, b->pat, b->w_host, b->t1_vals_host, b->t1_derivs_host, b->t2_vals_host, b->t2_derivs_host,
-                                 cell_req ? -1 : b->ncols_owned, &b->colp);
+                                 cell_req ? -1 : b->ncols_owned, cell_req, &b->colp);
     if (rc == GRMP_OK) {
       b->path = GRMP_PATH_COLUMNS;
       if (cell_req) {

@@ -589,23 +589,24 @@ bool colpath_applicable(const BlfLocalParams& p, int nq, ColPath* cp) {
   cp->variant = -1;
   cp->cf_variant = -1;
   cp->nq = nq;
-  // closed-form kernel first (any quadrature rule: K is the rule's own sum), GRMP_COL_QUADRATURE=1 keeps the quadrature kernels
+  // closed-form kernel where one exists (any quadrature rule: K is the rule's own sum; GRMP_COL_QUADRATURE=1 keeps the quadrature
+  // kernels), and the quadrature kernel whose tables the cell-parallel alternatives share
   if (!getenv("GRMP_COL_QUADRATURE") && p.same_eval)
     for (int v = 0; v < NCFVARIANTS; v++)
-      if (CFVARIANTS[v].match(cp->row, cp->col, p.action)) { cp->cf_variant = v; return true; }
+      if (CFVARIANTS[v].match(cp->row, cp->col, p.action)) { cp->cf_variant = v; break; }
   for (int v = 0; v < NVARIANTS; v++)
-    if (VARIANTS[v].match(cp->row, cp->col, p.action, nq)) { cp->variant = v; break; }
-  if (cp->variant < 0) return false;
-  if ((size_t)VARIANTS[cp->variant].tabR_per_q * nq > TABR_MAX) return false;
-  return true;
+    if (VARIANTS[v].match(cp->row, cp->col, p.action, nq) && (size_t)VARIANTS[v].tabR_per_q * nq <= TABR_MAX) { cp->variant = v; break; }
+  return cp->variant >= 0 || cp->cf_variant >= 0;
 }
 
 int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const std::vector<double>& w, const std::vector<double>& vals1,
                   const std::vector<double>& derivs1, const std::vector<double>& vals2, const std::vector<double>& derivs2, i64 ncols_owned,
-                  ColPath* cp) {
+                  bool quadrature_tables, ColPath* cp) {
   cudaStream_t s = ctx->stream;
   cp->built = false;
   cp->uid = g_next_uid++;
+  if (quadrature_tables) cp->cf_variant = -1;       // the cell-parallel kernels evaluate the quadrature sum themselves
+  if (cp->cf_variant < 0 && cp->variant < 0) return fail(GRMP_EUNSUPPORTED, "no column / cell kernel for this form and quadrature rule");
   const bool cf = cp->cf_variant >= 0;
   const Variant& V = VARIANTS[cf ? 0 : cp->variant];
   const bool tr = !cp->row_is_arg1;

@@ -80,7 +80,7 @@ bool colpath_applicable(const BlfLocalParams& p, int nq, ColPath* cp);
 // one-time build of the records (device), tables (host copies of the caller's tables) ...
 int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const std::vector<double>& w,
                   const std::vector<double>& vals1, const std::vector<double>& derivs1, const std::vector<double>& vals2,
-                  const std::vector<double>& derivs2, i64 ncols_owned, ColPath* cp);
+                  const std::vector<double>& derivs2, i64 ncols_owned, bool quadrature_tables, ColPath* cp);
 // ... and of the per-cell local -> nnz map (+ greedy element colouring when `coloured`) for the cell-parallel kernels
 int cellpath_build(grmp_ctx* ctx, const BlfLocalParams& p, Pattern& pat, bool coloured, ColPath* cp);
 int colpath_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, ColPath& cp, double* nzval);

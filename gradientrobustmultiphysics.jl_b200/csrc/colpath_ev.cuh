@@ -644,72 +644,10 @@ template <int ED_, int NC_, int NDS_, int NBUB_, int OPK_> struct CfH1 {
   }
 };
 
-// ---- vector H1 [SymmetricGradient, SymmetricGradient] with the isotropic Hooke tensor (pdeoperators.jl:256-315): for
-//      u = phi e_c (row), v = psi e_c' (column):  C eps(u) : eps(v) = sum_kl E[c][k][c'][l] d_k phi d_l psi with
-//      c == c': (lambda + 2 mu) d_c d_c + mu sum_{k != c} d_k d_k;   c != c': lambda d_c phi d_c' psi + mu d_c' phi d_c psi
-//      (Voigt form with summed off-diagonals, feevaluator_h1.jl:97-116, offdiagval = 1).
-//      G[c'][c][a][b] = |T| sum_kl Ainv[k][a] E[c][k][c'][l] Ainv[l][b]: the column's block of NC ED^2 numbers is contiguous.
-template <int ED_, int NDS_> struct CfHooke {
-  static constexpr int ED = ED_, NC = ED_, NDS = NDS_, NBUB = 0, OPK = GRMP_OP_SYMGRAD;
-  static constexpr int NSF = NDS, NROW = NC * NDS;
-  static constexpr int NT = ED * ED;                 // K_ab not symmetrised
-  static constexpr bool SYMK = false;
-  static constexpr int GEO_N = NC * NC * ED * ED;
-  static constexpr int STRIDE = (GEO_N + 1) & ~1;
-  using Quad = H1Ev<ED, ED, NDS, 0, GRMP_OP_SYMGRAD>;
-  static constexpr int ACT = ED == 2 ? GRMP_ACT_HOOKE2D : GRMP_ACT_HOOKE3D;
-  __device__ __forceinline__ static void geo(const GridView& g, i64 cell, const double* act_p, double* out) {
-    CellGeo<ED> T;
-    cell_geo<ED>(g, cell, T);
-    const double vol = g.vol[cell], mu = act_p[0], la = act_p[1];
-#pragma unroll
-    for (int cc = 0; cc < NC; cc++)        // column component c'
-#pragma unroll
-      for (int c = 0; c < NC; c++)         // row component c
-#pragma unroll
-        for (int a = 0; a < ED; a++)
-#pragma unroll
-          for (int b = 0; b < ED; b++) {
-            double s;
-            if (c == cc) {
-              s = (la + 2.0 * mu) * T.Ainv[c][a] * T.Ainv[c][b];
-#pragma unroll
-              for (int k = 0; k < ED; k++)
-                if (k != c) s = fma(mu * T.Ainv[k][a], T.Ainv[k][b], s);
-            } else {
-              s = la * T.Ainv[c][a] * T.Ainv[cc][b] + mu * T.Ainv[cc][a] * T.Ainv[c][b];
-            }
-            out[((cc * NC + c) * ED + a) * ED + b] = vol * s;
-          }
-  }
-  template <class F> __device__ __forceinline__ static void column(const double* __restrict__ cr, int l, const double* __restrict__ sK, F&& emit) {
-    const int cl = l / NDS, scol = l - cl * NDS;
-    double G[NC][NT];
-#pragma unroll
-    for (int c = 0; c < NC; c++)
-#pragma unroll
-      for (int t = 0; t < NT; t++) {
-        double v = 0.0;
-#pragma unroll
-        for (int cc = 0; cc < NC; cc++) v = (cc == cl) ? cr[(cc * NC + c) * NT + t] : v;
-        G[c][t] = v;
-      }
-#pragma unroll
-    for (int s = 0; s < NDS; s++) {
-      double k[NT];
-#pragma unroll
-      for (int t = 0; t < NT; t++) k[t] = sK[(t * NSF + s) * CT_PAD + scol];
-#pragma unroll
-      for (int c = 0; c < NC; c++) {
-        double v = 0.0;
-#pragma unroll
-        for (int t = 0; t < NT; t++) v = fma(G[c][t], k[t], v);
-        emit(c * NDS + s, v);
-      }
-    }
-  }
-};
-
+// (A closed form of the Hooke form -- G[c'][c][a][b] = |T| sum_kl Ainv[k][a] E[c][k][c'][l] Ainv[l][b], 16 / 81 numbers per cell -- was
+//  measured and dropped: the 128-byte geometry record per pair made it slower than the quadrature kernel on triangles (2.68 vs
+//  1.52 ms at level 10), and on tetrahedra the contraction of reference tensors loses a digit on entries that are small by
+//  cancellation.  Hooke forms use H1Ev<.., GRMP_OP_SYMGRAD> above.)
 // ---- Hdiv [Identity, Identity] (mass, contravariant Piola, feevaluator_hdiv.jl:2-19): G_t = |T| / det^2 (A^T A)_ab, signs of the
 //      reference functions from CellFaceSigns / orientations (HdivEv::negmask); rows are REFERENCE functions (records map them)
 template <int ED_, int NDALL_> struct CfHdivMass {
@@ -762,7 +700,6 @@ template <int ED_, int NDALL_> struct CfHdivMass {
   Y((CfH1<2, 2, 6, 0, GRMP_OP_ID>)) Y((CfH1<2, 2, 3, 3, GRMP_OP_ID>))                                                     \
   Y((CfH1<3, 1, 4, 0, GRMP_OP_ID>)) Y((CfH1<3, 3, 4, 0, GRMP_OP_ID>)) Y((CfH1<3, 1, 10, 0, GRMP_OP_ID>))                 \
   Y((CfH1<3, 3, 10, 0, GRMP_OP_ID>))                                                                                      \
-  Y((CfHooke<2, 3>)) Y((CfHooke<2, 6>)) Y((CfHooke<3, 4>)) Y((CfHooke<3, 10>))                                            \
   Y((CfHdivMass<2, 3>)) Y((CfHdivMass<2, 6>)) Y((CfHdivMass<3, 4>)) Y((CfHdivMass<3, 16>))
 
 }  // namespace grmp

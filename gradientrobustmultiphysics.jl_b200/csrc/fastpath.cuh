@@ -20,14 +20,9 @@ struct FastP2Tet {
   DevBuf<uint2> tile_dir;         // per tile: blob offset (16-byte units), blob bytes
   DevBuf<unsigned char> blob;     // per tile: header, group table, column / pair records, node coordinates, sorted mirror list
   DevBuf<u32> end_slots;          // per pair, only when a partition produced multi-chain halo columns
-  DevBuf<u32> vcols;              // vertex columns, ordered by the last tile that mirrors a value into their vertex rows
-  DevBuf<uint4> vrec;             // per vertex column (same order): diagonal slot, first slot, #slots | mode << 31, last tile; row mask x4
-  DevBuf<u32> vbeg;               // [nchunks] last tile that writes into a vertex column of chunk k (columns 32 k .. 32 k + 31 of vrec)
-  // control block of one launch, cleared by a memset node in front of the edge kernel:
-  //   [0] tile counter of the dynamic scheduler, [1..1024] progress[cta] = oldest tile the CTA still holds (+1; 0 = not started),
-  //   then one byte per chunk of 32 vertex columns: finalised inside the edge kernel
-  DevBuf<int> ctrl;
-  int lag = 0;                    // the CTA that claims tile t finalises the vertex columns of tile t - lag (GRMP_FAST_LAG)
+  DevBuf<u32> vcols;              // vertex columns
+  DevBuf<uint4> vrec;             // per vertex column: diagonal slot, first slot, #slots
+  DevBuf<int> tile_counter;       // dynamic tile scheduler of the edge kernel
   i64 nvcols = 0;
   DevBuf<unsigned long long> prof; // GRMP_FAST_PROF: cycle counters of the last launch (8 per CTA)
   int grid = 0;                   // CTAs of the last edge-kernel launch

@@ -278,13 +278,7 @@ struct EdgeParams {
   const u32* end_slots;     // [npairs] or null (only partitions have multi-chain columns)
   double factor;
   double* nzval;
-  int* tile_counter;        // dynamic tile scheduler: next unclaimed tile (control block, zero at launch)
-  int* progress;            // [gridDim.x] oldest tile the CTA still holds, + 1 (0 = CTA has not started)
-  unsigned char* fin_flag;  // [nchunks] the chunk's eligible vertex columns are finalised inside this kernel
-  const uint4* vrec;        // vertex-column records ordered by last tile; null: no in-kernel finalisation
-  const u32* cready;        // [nchunks] last tile that writes into a vertex column of chunk k (= columns 32 k .. 32 k + 31)
-  int nchunks, nv;
-  int lag;
+  int* tile_counter;        // dynamic tile scheduler: next unclaimed tile (zero at launch; reset by the diagonal kernel)
   int ntiles;
   u32 in_stride;            // bytes of one input buffer (largest blob)
   u32 slot_elems;           // doubles per warp stage slot
@@ -339,48 +333,6 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar_a, unsigned parity) {
       "DONE:\n"
       "}" ::"r"(mbar_a), "r"(parity)
       : "memory");
-}
-
-// Diagonal of the vertex columns.  The vertex-vertex block of the P2 stiffness matrix is the P1 stiffness matrix K1 scaled
-// entrywise (A[v,v] = 0.6 K1[v,v], A[w,v] = -0.2 K1[w,v]: the local vertex-vertex block is 0.6 / -0.2 S), and the columns of
-// K1 sum to zero (the P1 basis is a partition of unity), hence A[v,v] = 3 * sum_{w != v} A[w,v] over the VERTEX rows w of the
-// column only -- ~15 of its ~65 entries, every one of them mirrored into place by the service warps of the edge kernel.
-// Columns with more than 128 entries (vertices of very high valence) use the plain column sum instead:
-// A[v,v] = -sum_{i != v} A[i,v] (P2 partition of unity).
-// vrec: {diagonal slot | NONE, first slot, #slots | tail-only << 30 | column-sum mode << 31, last tile}, {row-is-vertex mask x4}.
-// One thread per column, slot k adds to partial sum k & 3, slots ascending, partial sums combined in a fixed order -> the result
-// does not depend on WHERE the column is finalised (inside the edge kernel or by the tail kernel).  Loads bypass L1 (the values
-// come from other SMs).  "tail-only": vertex rows beyond slot 15 (high valence, partition boundaries) -- the edge kernel's
-// pipelined path reads the first 16 slots of a column only.
-__device__ __forceinline__ void finalize_vertex_column(const uint4 r, const uint4 m, double* nzval) {
-  if (r.x == NONE) return;
-  const double* c = nzval + r.y;
-  const u32 d = r.x - r.y, n = r.z & 0x3fffffffu;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;     // slot k adds to accumulator k & 3, slots ascending
-  if (!(r.z >> 31)) {
-#pragma unroll
-    for (int wd = 0; wd < 4; wd++) {
-      const u32 word = wd == 0 ? m.x : (wd == 1 ? m.y : (wd == 2 ? m.z : m.w));     // the diagonal itself is never in the mask
-#pragma unroll
-      for (int q = 0; q < 8; q++) {
-        const u32 nib = (word >> (4 * q)) & 15u;
-        if (nib) {
-          const double* cq = c + 32 * wd + 4 * q;
-          const double v0 = (nib & 1u) ? __ldcg(cq) : 0.0, v1 = (nib & 2u) ? __ldcg(cq + 1) : 0.0;
-          const double v2 = (nib & 4u) ? __ldcg(cq + 2) : 0.0, v3 = (nib & 8u) ? __ldcg(cq + 3) : 0.0;
-          s0 += v0; s1 += v1; s2 += v2; s3 += v3;
-        }
-      }
-    }
-    nzval[r.x] = 3.0 * ((s0 + s1) + (s2 + s3));
-  } else {
-    for (u32 k = 0; k < n; k += 4) {
-      const double v0 = (k != d) ? __ldcg(c + k) : 0.0, v1 = (k + 1 < n && k + 1 != d) ? __ldcg(c + k + 1) : 0.0;
-      const double v2 = (k + 2 < n && k + 2 != d) ? __ldcg(c + k + 2) : 0.0, v3 = (k + 3 < n && k + 3 != d) ? __ldcg(c + k + 3) : 0.0;
-      s0 -= v0; s1 -= v1; s2 -= v2; s3 -= v3;
-    }
-    nzval[r.x] = (s0 + s1) + (s2 + s3);
-  }
 }
 
 // service warp: the tile's parked mirror values -> their slots in the vertex columns, in destination order
@@ -456,97 +408,9 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
       t_cur = atomicAdd(p.tile_counter, 1);
       if (t_cur < p.ntiles) dir_cur = __ldg(p.tile_dir + t_cur);
     }
-    // Diagonal of the vertex columns, folded into this kernel: the CTA that claims tile t finalises the vertex columns whose LAST
-    // contributing tile is t - lag (their vertex rows are then complete and mostly still in L2), provided every CTA has written
-    // out all of its tiles <= t - lag.  progress[cta] - 1 = oldest tile the CTA still holds (claimed, not yet written out and
-    // fenced); 0 = the CTA has not started.  A range whose guard fails is left to the tail kernel (fin_flag stays 0), so `lag` is
-    // a performance knob only.
-    int held[3] = {0x7ffffffe, 0x7ffffffe, 0x7ffffffe};       // tile in every input buffer
-    auto publish = [&](int t_a, int t_b) {
-      if (p.vrec == nullptr) return;
-      __threadfence();                                          // this lane's mirror stores before the progress update
-      __syncwarp();
-      if (slane == 0) {
-        int mn = t_a < t_b ? t_a : t_b;
-        for (int i = 0; i < NB; i++) mn = held[i] < mn ? held[i] : mn;
-        *reinterpret_cast<volatile int*>(p.progress + blockIdx.x) = mn + 1;
-      }
-    };
-    // Software pipeline over the iterations of this loop (one chunk of 32 vertex columns per claimed tile, one column per lane):
-    //   stage A: records of chunk k, its ready tile and a snapshot of progress[] are requested;
-    //   stage B (next iteration): guard evaluated on the snapshot (conservative: progress only grows), then the first 16 slots of
-    //            every eligible column are requested;
-    //   stage C (iteration after): sum, store the diagonal.
-    // Nothing here waits for memory in the iteration that issued the request.
-    uint4 a_r = make_uint4(NONE, 0, 0, 0), a_m = make_uint4(0, 0, 0, 0);
-    u32 a_ready = 0; int a_chunk = -1;
-    constexpr int PV = 10;                      // progress[] snapshot: grids of up to 32 PV CTAs (host checks)
-    int a_pv[PV];
-#pragma unroll
-    for (int i = 0; i < PV; i++) a_pv[i] = 0;
-    uint4 b_r = make_uint4(NONE, 0, 0, 0); u32 b_mask = 0; bool b_live = false;
-    double bv[16];
-#pragma unroll
-    for (int u = 0; u < 16; u++) bv[u] = 0.0;
-    auto stage_c = [&]() {
-      if (b_live) {
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {          // same order as finalize_vertex_column: nibble by nibble, slot k -> accumulator k & 3
-          const u32 nib = (b_mask >> (4 * q)) & 15u;
-          if (nib) {
-            s0 += (nib & 1u) ? bv[4 * q] : 0.0; s1 += (nib & 2u) ? bv[4 * q + 1] : 0.0;
-            s2 += (nib & 4u) ? bv[4 * q + 2] : 0.0; s3 += (nib & 8u) ? bv[4 * q + 3] : 0.0;
-          }
-        }
-        p.nzval[b_r.x] = 3.0 * ((s0 + s1) + (s2 + s3));
-      }
-      b_live = false;
-    };
-    auto stage_b = [&]() {
-      if (a_chunk < 0) return;
-      int mn = 0x7fffffff;
-#pragma unroll
-      for (int i = 0; i < PV; i++) mn = a_pv[i] < mn ? a_pv[i] : mn;
-      const int pm = __reduce_min_sync(0xffffffffu, mn);
-      const u32 ready = __shfl_sync(0xffffffffu, a_ready, 0);
-      if (pm - 1 > (int)ready) {               // every CTA has written out (and fenced) all of its tiles <= ready
-        __threadfence();
-        b_live = a_r.x != NONE && !(a_r.z >> 30);
-        b_r = a_r; b_mask = a_m.x;
-        if (b_live) {
-          const double* c = p.nzval + a_r.y;
-#pragma unroll
-          for (int u = 0; u < 16; u++) bv[u] = ((b_mask >> u) & 1u) ? __ldcg(c + u) : 0.0;
-        }
-        if (slane == 0) p.fin_flag[a_chunk] = 1;
-      }
-      a_chunk = -1;
-    };
-    auto stage_a = [&](int k) {
-      if (p.vrec == nullptr || k < 0 || k >= p.nchunks) return;
-      a_chunk = k;
-      const int w = 32 * k + slane;
-      a_r = make_uint4(NONE, 0, 0, 0); a_m = make_uint4(0, 0, 0, 0);
-      if (w < p.nv) { a_r = __ldg(p.vrec + 2 * (size_t)w); a_m = __ldg(p.vrec + 2 * (size_t)w + 1); }
-      a_ready = __ldg(p.cready + k);
-#pragma unroll
-      for (int i = 0; i < PV; i++) {             // requested now, reduced in the next iteration
-        const int c = slane + 32 * i;
-        a_pv[i] = c < (int)gridDim.x ? *reinterpret_cast<volatile const int*>(p.progress + c) : 0x7fffffff;
-      }
-    };
-    auto pipeline = [&](int k) { stage_c(); stage_b(); stage_a(k); };
-    publish(t_cur, 0x7ffffffe);
     for (;; it++) {
       int t_nxt = 0;
       if (slane == 0) t_nxt = atomicAdd(p.tile_counter, 1);    // not consumed before the end of the iteration
-      // progress + diagonal pipeline first: the only stores still in flight are those of the previous iteration (long acknowledged),
-      // so the fences inside do not wait, and the warp would otherwise idle until the consumers release the buffer
-      if (NSVC == 1) {
-        publish(t_cur, 0x7ffffffe);
-        pipeline(__shfl_sync(0xffffffffu, t_cur, 0) - p.lag);
-      }
       if (use >= 1) {
         const long long c0 = clock64();
         mbar_wait(done_a + 8 * b, (unsigned)(use - 1) & 1u);   // all consumer warps have left the tile in this buffer
@@ -554,7 +418,6 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
         if (!(p.dbg & 1)) mirror_writeout(p, smraw + (size_t)b * p.in_stride, slane, 32 * NSVC);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // parked values (generic writes) before the next bulk load
         c_wait += c1 - c0; c_wo += clock64() - c1;
-        held[b] = 0x7ffffffe;
       }
       int t;
       if (NSVC == 1) {
@@ -576,7 +439,6 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
       if (slane == 0) {
         s_tile[b] = t;
         tile_load(p, dir_cur, in_a + b * p.in_stride, full_a + 8 * b, pol_stream);
-        held[b] = t;
         t_cur = t_nxt;
         dir_cur = make_uint2(0, 0);
         if (t_cur < p.ntiles) dir_cur = __ldg(p.tile_dir + t_cur);     // consumed at the next bulk load
@@ -588,11 +450,6 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
       const int b2 = j % NB;
       mbar_wait(done_a + 8 * b2, (unsigned)(j / NB) & 1u);
       if (!(p.dbg & 1)) mirror_writeout(p, smraw + (size_t)b2 * p.in_stride, slane, 32 * NSVC);
-      held[b2] = 0x7ffffffe;
-    }
-    if (NSVC == 1) {
-      publish(0x7ffffffe, 0x7ffffffe);                                  // this CTA holds nothing any more
-      pipeline(-1); pipeline(-1);                                       // drain the diagonal pipeline
     }
     if (p.prof != nullptr && slane == 0) {
       unsigned long long* q = p.prof + 8 * (size_t)blockIdx.x;
@@ -786,20 +643,52 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
   }
 }
 
-// tail kernel: the vertex columns the edge kernel did not finalise itself (those of the last `lag` tiles, columns in column-sum
-// mode, ranges whose guard failed)
-__global__ void __launch_bounds__(256) p2tet_vertex_diag_kernel(const uint4* __restrict__ vrec, i64 nv, double* nzval,
-                                                                const unsigned char* __restrict__ fin_flag) {
-  const i64 w = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  if (w >= nv) return;
-  const uint4 r = __ldg(vrec + 2 * w);
-  if (fin_flag != nullptr && !(r.z >> 30) && fin_flag[w >> 5]) return;
-  finalize_vertex_column(r, __ldg(vrec + 2 * w + 1), nzval);
+// Diagonal of the vertex columns.  The vertex-vertex block of the P2 stiffness matrix is the P1 stiffness matrix K1 scaled
+// entrywise (A[v,v] = 0.6 K1[v,v], A[w,v] = -0.2 K1[w,v]: the local vertex-vertex block is 0.6 / -0.2 S), and the columns of
+// K1 sum to zero (the P1 basis is a partition of unity), hence A[v,v] = 3 * sum_{w != v} A[w,v] over the VERTEX rows w of the
+// column only -- ~15 of its ~65 entries, every one of them mirrored into place by the edge kernel.  Columns with more than 128
+// entries (vertices of very high valence) use the plain column sum instead: A[v,v] = -sum_{i != v} A[i,v] (P2 partition of
+// unity).  Eight lanes per column, fixed shuffle tree -> deterministic.
+// vrec: {diagonal slot | NONE, first slot, #slots, mode}, {row-is-vertex mask x4}.  Also re-arms the edge kernel's tile scheduler.
+__global__ void __launch_bounds__(256) p2tet_vertex_diag_kernel(const uint4* __restrict__ vrec, i64 nv, double* nzval, int* tile_counter) {
+  const i64 w = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 3;
+  const int sub = threadIdx.x & 7;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *tile_counter = 0;
+  uint4 r = make_uint4(NONE, 0, 0, 0), m = make_uint4(0, 0, 0, 0);
+  if (w < nv) { r = __ldg(vrec + 2 * w); m = __ldg(vrec + 2 * w + 1); }
+  double s = 0.0;
+  if (r.x != NONE) {
+    const double* __restrict__ c = nzval + r.y;
+    const u32 d = r.x - r.y;
+    if (r.w == 0) {
+      // the vertex rows are the lowest row indices of the column on an unpartitioned grid: usually only mask word 0 is set
+#pragma unroll
+      for (int wd = 0; wd < 4; wd++) {
+        const u32 word = wd == 0 ? m.x : (wd == 1 ? m.y : (wd == 2 ? m.z : m.w));
+        if (word != 0u) {
+          double v[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {       // slots 32 wd + sub + 8 u: independent loads
+            const u32 k = 32 * wd + sub + 8 * u;
+            const bool take = k != d && ((word >> (sub + 8 * u)) & 1u);   // mask bits exist only for slots < #slots
+            v[u] = take ? c[k] : 0.0;
+          }
+          s += (v[0] + v[1]) + (v[2] + v[3]);
+        }
+      }
+      s *= 3.0;
+    } else {
+      for (u32 k = sub; k < r.z; k += 8) s -= (k == d) ? 0.0 : c[k];
+    }
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  if (sub == 0 && r.x != NONE) nzval[r.x] = s;
 }
 
 // col_kind[row] == 2 marks vertex dofs
-__global__ void find_diag_slots(const u32* vcols, const u32* vlast, i64 nv, const i64* colptr, const i64* rowval, const unsigned char* col_kind,
-                                uint4* vrec) {
+__global__ void find_diag_slots(const u32* vcols, i64 nv, const i64* colptr, const i64* rowval, const unsigned char* col_kind, uint4* vrec) {
   i64 w = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (w >= nv) return;
   const i64 col = vcols[w];
@@ -811,30 +700,8 @@ __global__ void find_diag_slots(const u32* vcols, const u32* vlast, i64 nv, cons
     if (row == col) d = (u32)k;
     else if (masked && col_kind[row] == 2) mask[(k - beg) >> 5] |= 1u << ((k - beg) & 31);
   }
-  const bool tail_only = !masked || mask[1] || mask[2] || mask[3] || (mask[0] >> 16);
-  vrec[2 * w] = make_uint4(d, (u32)beg, (u32)(end - beg) | (tail_only ? 0x40000000u : 0u) | (masked ? 0u : 0x80000000u), vlast[w]);
+  vrec[2 * w] = make_uint4(d, (u32)beg, (u32)(end - beg), masked ? 0u : 1u);
   vrec[2 * w + 1] = make_uint4(mask[0], mask[1], mask[2], mask[3]);
-}
-
-// last tile that mirrors a W value into the vertex rows of a vertex column = last tile with an edge at the vertex
-__global__ void vertex_last_tile(const PackParams p, int* last) {
-  i64 j = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  if (j >= p.ncols || p.col_closed[j] == 2) return;
-  const i64 kb = p.col_pairbeg[j];
-  if (p.col_pairbeg[j + 1] == kb) return;
-  const u32 c0 = p.pair_code[kb];
-  const i32* d0 = p.celldofs + (i64)p.pair_cell[kb] * 10;
-  const int t = (int)p.col_tile[j];
-  atomicMax(last + (d0[c0 & 3] - 1), t);
-  atomicMax(last + (d0[(c0 >> 2) & 3] - 1), t);
-}
-__global__ void vertex_keys(const u32* vcols, const int* last, i64 nv, u32* keys) {
-  i64 w = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  if (w < nv) { const int t = last[vcols[w]]; keys[w] = t < 0 ? 0u : (u32)t; }
-}
-__global__ void chunk_ready(const u32* keys_sorted, i64 nv, i64 nchunks, u32* cready) {
-  const i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  if (k < nchunks) cready[k] = keys_sorted[min(32 * k + 31, nv - 1)];
 }
 
 // closed-form local stiffness of the unit reference tetrahedron, used to verify that the
@@ -937,7 +804,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   };
   const i64 ncells = p.g.ncells, ncols = pat.ncols, nnodes = p.g.nnodes;
   const i64 ncols_owned_eff = (ncols_owned >= 0 && ncols_owned < ncols) ? ncols_owned : ncols;
-  out->ntiles = 0; out->nvcols = 0; out->grid = 0;
+  out->ntiles = 0; out->nvcols = 0;
   if (pat.nnz >= (i64)NONE) return fail(GRMP_EUNSUPPORTED, "fast path: more than 2^32-1 non-zeros on one device");
   // (0) the caller's tables must be the standard P2 basis integrated exactly
   {
@@ -1205,6 +1072,8 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     GRMP_TRY(out->prof.alloc(8 * 1024));
     GRMP_CUDA(cudaMemsetAsync(out->prof.p, 0, out->prof.bytes(), s));
   }
+  GRMP_TRY(out->tile_counter.alloc(1));
+  GRMP_CUDA(cudaMemsetAsync(out->tile_counter.p, 0, sizeof(int), s));
   lap("tile tables upload");
   // (3) pack column / pair records into the tile blobs on the device (slots are looked up in the pattern by (row, col)),
   //     sort every tile's mirror candidates by destination slot
@@ -1245,42 +1114,13 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     GRMP_CUDA(cudaStreamSynchronize(s));      // d_tmp and the sort buffers go out of scope below
   }
   lap("pack kernels + mirror sort");
-  // (4) vertex columns, ordered by the last tile that mirrors a value into their vertex rows (the edge kernel finalises the
-  //     diagonal of a column `lag` tiles after that tile has been claimed); diagonal slots + vertex-row masks
-  {
-    const i64 nv = out->nvcols;
-    DevBuf<u32> d_vc, d_key, d_key2, d_vc2;
-    DevBuf<int> d_last;
-    GRMP_TRY(d_vc.upload(vcols.data(), vcols.size(), s));
-    GRMP_TRY(out->vcols.alloc(vcols.size())); GRMP_TRY(d_key.alloc(vcols.size())); GRMP_TRY(d_key2.alloc(vcols.size()));
-    GRMP_TRY(d_last.alloc(std::max<i64>(ncols, 1)));
-    GRMP_TRY(out->vrec.alloc(2 * vcols.size()));
-    const i64 nchunks = (nv + 31) / 32;
-    GRMP_TRY(out->vbeg.alloc((size_t)std::max<i64>(nchunks, 1)));
-    GRMP_CUDA(cudaMemsetAsync(d_last.p, 0xff, d_last.bytes(), s));
-    GRMP_CUDA(cudaMemsetAsync(out->vbeg.p, 0, out->vbeg.bytes(), s));
-    if (nv > 0) {
-      if (ncols) vertex_last_tile<<<(unsigned)((ncols + 255) / 256), 256, 0, s>>>(pp, d_last.p);
-      vertex_keys<<<(unsigned)((nv + 255) / 256), 256, 0, s>>>(d_vc.p, d_last.p, nv, d_key.p);
-      GRMP_CUDA(cudaGetLastError());
-      size_t tb = 0;
-      GRMP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, d_key.p, d_key2.p, d_vc.p, out->vcols.p, (int)nv, 0, 32, s));
-      DevBuf<unsigned char> d_tmp2;
-      GRMP_TRY(d_tmp2.alloc(std::max<size_t>(tb, 16)));
-      GRMP_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp2.p, tb, d_key.p, d_key2.p, d_vc.p, out->vcols.p, (int)nv, 0, 32, s));
-      chunk_ready<<<(unsigned)((nchunks + 255) / 256), 256, 0, s>>>(d_key2.p, nv, nchunks, out->vbeg.p);
-      find_diag_slots<<<(unsigned)((nv + 255) / 256), 256, 0, s>>>(out->vcols.p, d_key2.p, nv, pat.colptr.p, pat.rowval.p, d_closed.p, out->vrec.p);
-      GRMP_CUDA(cudaGetLastError());
-      GRMP_CUDA(cudaStreamSynchronize(s));      // the sort buffers go out of scope
-    } else {
-      GRMP_CUDA(cudaMemcpyAsync(out->vcols.p, d_vc.p, vcols.size() * 4, cudaMemcpyDeviceToDevice, s));
-      GRMP_CUDA(cudaStreamSynchronize(s));
-    }
+  // (4) vertex columns: list + diagonal slots
+  GRMP_TRY(out->vcols.upload(vcols.data(), vcols.size(), s));
+  GRMP_TRY(out->vrec.alloc(2 * vcols.size()));
+  if (out->nvcols > 0) {
+    find_diag_slots<<<(unsigned)((out->nvcols + 255) / 256), 256, 0, s>>>(out->vcols.p, out->nvcols, pat.colptr.p, pat.rowval.p, d_closed.p, out->vrec.p);
+    GRMP_CUDA(cudaGetLastError());
   }
-  // control block: tile counter, progress[1024], one flag per chunk of 32 vertex columns
-  GRMP_TRY(out->ctrl.alloc((size_t)(1 + 1024) + (size_t)((out->nvcols + 31) / 32 + 3) / 4 + 1));
-  GRMP_CUDA(cudaMemsetAsync(out->ctrl.p, 0, out->ctrl.bytes(), s));
-  out->lag = getenv("GRMP_FAST_LAG") ? atoi(getenv("GRMP_FAST_LAG")) : -1;    // -1: chosen from the grid size at the first launch
   const int smem_attr = (int)std::max<i64>(max_smem, 1024);
   GRMP_TRY(set_smem_attr<3>(smem_attr)); GRMP_TRY(set_smem_attr<4>(smem_attr)); GRMP_TRY(set_smem_attr<5>(smem_attr));
   GRMP_TRY(set_smem_attr<6>(smem_attr)); GRMP_TRY(set_smem_attr<7>(smem_attr));
@@ -1288,15 +1128,14 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   return GRMP_OK;
 }
 
-template <int NW> int edge_grid(FastP2Tet& f, int sm_count, int* grid) {
+template <int NW> int launch_edge(const EdgeParams& ep, FastP2Tet& f, int sm_count, cudaStream_t s) {
   int per_sm = 0;
   GRMP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p2tet_edge_kernel<NW>, (NW + NSVC) * 32, (size_t)f.smem_bytes));
   if (per_sm < 1) return fail(GRMP_ECUDA, "fast path: edge kernel does not fit on an SM");
-  *grid = std::min(std::min(f.ntiles, per_sm * sm_count), 1024);
+  const int grid = std::min(std::min(f.ntiles, per_sm * sm_count), 1024);
+  f.grid = grid;
+  p2tet_edge_kernel<NW><<<grid, (NW + NSVC) * 32, f.smem_bytes, s>>>(ep);
   return GRMP_OK;
-}
-template <int NW> void launch_edge(const EdgeParams& ep, FastP2Tet& f, cudaStream_t s) {
-  p2tet_edge_kernel<NW><<<f.grid, (NW + NSVC) * 32, f.smem_bytes, s>>>(ep);
 }
 
 int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, FastP2Tet& f, i64 geom_version, double* nzval) {
@@ -1306,36 +1145,22 @@ int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pa
     GRMP_CUDA(cudaGetLastError());
     f.geom_version = geom_version;
   }
-  unsigned char* fin_flag = reinterpret_cast<unsigned char*>(f.ctrl.p + 1 + 1024);
   if (f.ntiles > 0) {
-    if (f.grid < 1) {
-      switch (f.nw) {
-        case 3: GRMP_TRY(edge_grid<3>(f, ctx->sm_count, &f.grid)); break;
-        case 4: GRMP_TRY(edge_grid<4>(f, ctx->sm_count, &f.grid)); break;
-        case 5: GRMP_TRY(edge_grid<5>(f, ctx->sm_count, &f.grid)); break;
-        case 6: GRMP_TRY(edge_grid<6>(f, ctx->sm_count, &f.grid)); break;
-        default: GRMP_TRY(edge_grid<7>(f, ctx->sm_count, &f.grid)); break;
-      }
-      // a CTA holds at most nbuf + 2 tiles (input ring, the tile being loaded, the claim made one iteration ahead): when tile t
-      // is claimed, the tiles below t - grid (nbuf + 3) have normally been written out by everybody
-      if (f.lag < 0) f.lag = f.grid * (f.nbuf + 3) + 64;
-    }
-    const bool in_kernel = f.nvcols > 0 && !(dbg & 2) && f.lag < f.ntiles && f.grid <= 320;
-    GRMP_CUDA(cudaMemsetAsync(f.ctrl.p, 0, f.ctrl.bytes(), ctx->stream));
-    EdgeParams ep{f.tile_dir.p, f.blob.p, f.end_slots.p, p.factor, nzval, f.ctrl.p, f.ctrl.p + 1, fin_flag, in_kernel ? f.vrec.p : nullptr,
-                  f.vbeg.p, (int)((f.nvcols + 31) / 32), (int)f.nvcols, f.lag, f.ntiles, f.in_stride, f.slot_elems, f.nbuf, f.prof.p, dbg};
+    EdgeParams ep{f.tile_dir.p, f.blob.p, f.end_slots.p, p.factor, nzval, f.tile_counter.p, f.ntiles, f.in_stride, f.slot_elems, f.nbuf, f.prof.p, dbg};
     switch (f.nw) {
-      case 3: launch_edge<3>(ep, f, ctx->stream); break;
-      case 4: launch_edge<4>(ep, f, ctx->stream); break;
-      case 5: launch_edge<5>(ep, f, ctx->stream); break;
-      case 6: launch_edge<6>(ep, f, ctx->stream); break;
-      default: launch_edge<7>(ep, f, ctx->stream); break;
+      case 3: GRMP_TRY(launch_edge<3>(ep, f, ctx->sm_count, ctx->stream)); break;
+      case 4: GRMP_TRY(launch_edge<4>(ep, f, ctx->sm_count, ctx->stream)); break;
+      case 5: GRMP_TRY(launch_edge<5>(ep, f, ctx->sm_count, ctx->stream)); break;
+      case 6: GRMP_TRY(launch_edge<6>(ep, f, ctx->sm_count, ctx->stream)); break;
+      default: GRMP_TRY(launch_edge<7>(ep, f, ctx->sm_count, ctx->stream)); break;
     }
     GRMP_CUDA(cudaGetLastError());
   }
   if (f.nvcols > 0 && !(dbg & 2)) {
-    p2tet_vertex_diag_kernel<<<(unsigned)((f.nvcols + 255) / 256), 256, 0, ctx->stream>>>(f.vrec.p, f.nvcols, nzval, f.ntiles > 0 ? fin_flag : nullptr);
+    p2tet_vertex_diag_kernel<<<(unsigned)((f.nvcols * 8 + 255) / 256), 256, 0, ctx->stream>>>(f.vrec.p, f.nvcols, nzval, f.tile_counter.p);
     GRMP_CUDA(cudaGetLastError());
+  } else if (f.ntiles > 0) {
+    GRMP_CUDA(cudaMemsetAsync(f.tile_counter.p, 0, sizeof(int), ctx->stream));
   }
   return GRMP_OK;
 }
