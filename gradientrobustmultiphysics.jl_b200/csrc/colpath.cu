@@ -55,6 +55,11 @@ struct ColParams {
 };
 
 template <int NV> __device__ __forceinline__ u32 rec_byte(const u32 (&w)[NV * 4], int i) { return (w[i >> 2] >> (8 * (i & 3))) & 255u; }
+// Pair record: bytes 0-3 cell | local function << 24, bytes 4 .. 4 + NROW slot of every local row inside the column (255: not in
+// the pattern) and, where the record has room, NROW bits "this is the FIRST contribution to the slot": the first contribution is
+// a plain store into the column image (no load, no zero-initialisation pass) -- a fifth of the shared-memory wavefronts of these
+// LSU-bound kernels.
+__host__ __device__ constexpr bool rec_has_first(int nrow, int nv) { return 4 + nrow + (nrow + 7) / 8 <= 16 * nv; }
 
 // geometry record of every cell: [0] CellVolumes, then the row / column evaluator's data (CacheLayout)
 template <class RowEv, class ColEv>
@@ -120,7 +125,9 @@ __global__ void __launch_bounds__(256) col_kernel(const ColParams p) {
   for (int w2 = 0; w2 < warp; w2++) acc_off += s_maxlen[w2] + 1u;     // + 1: trash row of every warp (entries that are not in the pattern)
   // image of the warp's 32 columns: slot k of lane l at [k][l] -> every warp access touches 32 consecutive doubles
   double* const a = img + (size_t)acc_off * 32 + lane;
-  for (u32 k = 0; k < maxlen; k++) a[k * 32] = 0.0;
+  constexpr bool FT = rec_has_first(RowEv::NROW, NV);
+  if (!FT)
+    for (u32 k = 0; k < maxlen; k++) a[k * 32] = 0.0;
   for (u32 k = 0; k < maxnp; k++) {
     u32 w[NV * 4];
 #pragma unroll
@@ -166,7 +173,11 @@ __global__ void __launch_bounds__(256) col_kernel(const ColParams p) {
       // rows that are not in the pattern (slot 255) go to the warp's trash row: no branch per row
       RowEv::emit_rows(RR, A, [&](int r, double v) {
         const u32 o = min(rec_byte<NV>(w, 4 + r), maxlen);
-        a[o * 32] += v;
+        if (FT) {
+          const bool first = (rec_byte<NV>(w, 4 + RowEv::NROW + (r >> 3)) >> (r & 7)) & 1u;
+          const double old = first ? 0.0 : a[o * 32];
+          a[o * 32] = old + v;
+        } else a[o * 32] += v;
       });
     }
   }
@@ -251,7 +262,9 @@ __global__ void __launch_bounds__(256) cf_kernel(const ColParams p) {
   u32 acc_off = 0;
   for (int w2 = 0; w2 < warp; w2++) acc_off += s_maxlen[w2] + 1u;
   double* const a = img + (size_t)acc_off * 32 + lane;
-  for (u32 k = 0; k < maxlen; k++) a[k * 32] = 0.0;
+  constexpr bool FT = rec_has_first(F::NROW, NV);
+  if (!FT)
+    for (u32 k = 0; k < maxlen; k++) a[k * 32] = 0.0;
   const double factor = p.factor;
   for (u32 k = 0; k < maxnp; k++) {
     u32 w[NV * 4];
@@ -275,7 +288,11 @@ __global__ void __launch_bounds__(256) cf_kernel(const ColParams p) {
     if (work) {
       F::column(cr, (int)lc, sK, [&](int r, double v) {
         const u32 o = min(rec_byte<NV>(w, 4 + r), maxlen);     // rows that are not in the pattern go to the warp's trash row
-        a[o * 32] = fma(v, factor, a[o * 32]);
+        if (FT) {
+          const bool first = (rec_byte<NV>(w, 4 + F::NROW + (r >> 3)) >> (r & 7)) & 1u;
+          const double old = first ? 0.0 : a[o * 32];
+          a[o * 32] = fma(v, factor, old);
+        } else a[o * 32] = fma(v, factor, a[o * 32]);
       });
     }
   }
@@ -406,6 +423,8 @@ __global__ void pack_records(PackParams p) {
   const u32 maxnp = __reduce_max_sync(0xffffffffu, np);
   const u32 lt = (1u << lane) - 1u;
   u32 rbase = 0;
+  const bool ft = rec_has_first(p.nrow, p.nv);
+  u32 touched[8] = {0, 0, 0, 0, 0, 0, 0, 0};          // slots of the column that an earlier pair has written
   for (u32 k = 0; k < maxnp; k++) {
     const u32 bal = __ballot_sync(0xffffffffu, k < np);
     const u32 idx = rbase + __popc(bal & lt);
@@ -434,6 +453,12 @@ __global__ void pack_records(PackParams p) {
       }
       const int byte = 4 + r;
       w[byte >> 2] = (w[byte >> 2] & ~(255u << (8 * (byte & 3)))) | (off << (8 * (byte & 3)));
+      if (ft) {      // all-ones default = "first" (rows outside the pattern go to the trash row: a store is as good as an add)
+        const bool first = off == 255u || !active || !((touched[off >> 5] >> (off & 31)) & 1u);
+        if (off != 255u && active) touched[off >> 5] |= 1u << (off & 31);
+        const int fb = 4 + p.nrow + (r >> 3);
+        if (!first) w[fb >> 2] &= ~(1u << (8 * (fb & 3) + (r & 7)));
+      }
     }
     uint4* dst = p.recs + (size_t)(recbase + idx) * p.nv;
     for (int v = 0; v < p.nv; v++) dst[v] = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);

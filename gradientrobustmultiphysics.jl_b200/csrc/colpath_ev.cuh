@@ -689,17 +689,16 @@ template <int ED_, int NDALL_> struct CfHdivMass {
   }
 };
 
-// forms with a closed-form kernel: Y(class, NQ of the rule prepare_assembly! picks -- only used to match the quadrature variant
-// whose records are shared)
+// forms with a closed-form kernel.  Measured against the quadrature kernels on one B200 (profiles/r2_all_configs.md): better for the
+// P2 / Bernardi-Raugel Laplacians, all H1 mass matrices and RT0 / BDM1(2D) mass; NOT listed (quadrature kernel is faster): P1
+// Laplacians (one quadrature point: nothing to save) and the BDM1 mass matrix on tetrahedra (16 x 6 table reads per pair).
 #define GRMP_CF_FORMS(Y)                                                                                                   \
-  Y((CfH1<2, 1, 3, 0, GRMP_OP_GRAD>)) Y((CfH1<2, 2, 3, 0, GRMP_OP_GRAD>)) Y((CfH1<2, 1, 6, 0, GRMP_OP_GRAD>))            \
-  Y((CfH1<2, 2, 6, 0, GRMP_OP_GRAD>)) Y((CfH1<2, 2, 3, 3, GRMP_OP_GRAD>))                                                 \
-  Y((CfH1<3, 1, 4, 0, GRMP_OP_GRAD>)) Y((CfH1<3, 3, 4, 0, GRMP_OP_GRAD>)) Y((CfH1<3, 1, 10, 0, GRMP_OP_GRAD>))           \
-  Y((CfH1<3, 3, 10, 0, GRMP_OP_GRAD>)) Y((CfH1<3, 3, 4, 4, GRMP_OP_GRAD>))                                                \
+  Y((CfH1<2, 1, 6, 0, GRMP_OP_GRAD>)) Y((CfH1<2, 2, 6, 0, GRMP_OP_GRAD>)) Y((CfH1<2, 2, 3, 3, GRMP_OP_GRAD>))            \
+  Y((CfH1<3, 1, 10, 0, GRMP_OP_GRAD>)) Y((CfH1<3, 3, 10, 0, GRMP_OP_GRAD>)) Y((CfH1<3, 3, 4, 4, GRMP_OP_GRAD>))           \
   Y((CfH1<2, 1, 3, 0, GRMP_OP_ID>)) Y((CfH1<2, 2, 3, 0, GRMP_OP_ID>)) Y((CfH1<2, 1, 6, 0, GRMP_OP_ID>))                  \
   Y((CfH1<2, 2, 6, 0, GRMP_OP_ID>)) Y((CfH1<2, 2, 3, 3, GRMP_OP_ID>))                                                     \
   Y((CfH1<3, 1, 4, 0, GRMP_OP_ID>)) Y((CfH1<3, 3, 4, 0, GRMP_OP_ID>)) Y((CfH1<3, 1, 10, 0, GRMP_OP_ID>))                 \
   Y((CfH1<3, 3, 10, 0, GRMP_OP_ID>))                                                                                      \
-  Y((CfHdivMass<2, 3>)) Y((CfHdivMass<2, 6>)) Y((CfHdivMass<3, 4>)) Y((CfHdivMass<3, 16>))
+  Y((CfHdivMass<2, 3>)) Y((CfHdivMass<2, 6>)) Y((CfHdivMass<3, 4>))
 
 }  // namespace grmp
