@@ -398,19 +398,14 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
     int b = 0, use = 0;                                       // buffer of iteration it, how often it has been filled before
     long long c_wait = 0, c_wo = 0;
     const long long c_start = clock64();
-    // tiles are claimed dynamically (SMs do not run at the same speed, a static split leaves the slowest SM as the tail) and ONE
-    // ITERATION AHEAD: under a saturated memory system the atomic and the directory lookup behind it take ~3000 cycles, which
-    // used to sit between the write-out and the next bulk load (GRMP_FAST_PROF: 38 % of the service warp's time, consumers
-    // waiting 23 % of theirs).  Now both are in flight while the warp waits for the consumers and writes the mirrors out.
-    int t_cur = 0;
-    uint2 dir_cur = make_uint2(0, 0);
-    if (slane == 0) {
-      t_cur = atomicAdd(p.tile_counter, 1);
-      if (t_cur < p.ntiles) dir_cur = __ldg(p.tile_dir + t_cur);
-    }
     for (;; it++) {
-      int t_nxt = 0;
-      if (slane == 0) t_nxt = atomicAdd(p.tile_counter, 1);    // not consumed before the end of the iteration
+      int t = 0;
+      uint2 dir = make_uint2(0, 0);
+      if (slane == 0) {
+        // tiles are claimed dynamically: SMs do not run at the same speed, a static split leaves the slowest SM as the tail
+        t = atomicAdd(p.tile_counter, 1);
+        if (t < p.ntiles) dir = __ldg(p.tile_dir + t);
+      }
       if (use >= 1) {
         const long long c0 = clock64();
         mbar_wait(done_a + 8 * b, (unsigned)(use - 1) & 1u);   // all consumer warps have left the tile in this buffer
@@ -419,16 +414,10 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // parked values (generic writes) before the next bulk load
         c_wait += c1 - c0; c_wo += clock64() - c1;
       }
-      int t;
-      if (NSVC == 1) {
-        __syncwarp();                                                   // the write-out of all lanes is ordered before the bulk load
-        t = __shfl_sync(0xffffffffu, t_cur, 0);
-      } else {
-        if (slane == 0) s_next = t_cur;
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * NSVC) : "memory");     // write-out finished by all service warps; s_next visible
-        t = *reinterpret_cast<volatile int*>(&s_next);
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * NSVC) : "memory");     // everybody has read s_next
-      }
+      if (slane == 0) s_next = t;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * NSVC) : "memory");     // write-out finished by all service warps; s_next visible
+      t = *reinterpret_cast<volatile int*>(&s_next);
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * NSVC) : "memory");     // everybody has read s_next
       if (t >= p.ntiles) {
         if (slane == 0) {
           s_tile[b] = -1;
@@ -438,10 +427,7 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
       }
       if (slane == 0) {
         s_tile[b] = t;
-        tile_load(p, dir_cur, in_a + b * p.in_stride, full_a + 8 * b, pol_stream);
-        t_cur = t_nxt;
-        dir_cur = make_uint2(0, 0);
-        if (t_cur < p.ntiles) dir_cur = __ldg(p.tile_dir + t_cur);     // consumed at the next bulk load
+        tile_load(p, dir, in_a + b * p.in_stride, full_a + 8 * b, pol_stream);
       }
       if (++b == NB) { b = 0; use++; }
     }
@@ -704,6 +690,238 @@ __global__ void find_diag_slots(const u32* vcols, i64 nv, const i64* colptr, con
   vrec[2 * w + 1] = make_uint4(mask[0], mask[1], mask[2], mask[3]);
 }
 
+// ==== device-side build (J3): ring order of every edge column and tile packing on the GPU ==========================================
+// The host build below (GRMP_FAST_HOST_BUILD=1) is kept for cross-validation: both produce the same ring orders and the same matrix
+// bit for bit; the device build cuts tiles additionally at chunk boundaries (chunks of TB_CHUNK columns are packed independently).
+constexpr int MAXRING = 64;          // cells around one edge that the device ring ordering handles (host build: 255)
+constexpr int TB_CHUNK = 16384;      // columns per independently packed chunk (~70 tiles)
+constexpr int TB_HASH = 4096;        // open-addressing node set of the tile being filled; the device build is used when a blob holds < TB_HASH / 2 nodes
+enum { CK_OPEN = 0, CK_CLOSED = 1, CK_VERTEX = 2 };
+
+struct RingParams {
+  const u32* gcell; const u32* gsrc; const i64* pairbeg; const i64* colptr; const i32* cellnodes;
+  i64 ncells, ncols, ncols_owned;
+  u32* pair_cell; u32* pair_code; u32* col_of_pair; i32* pair_in; i32* pair_out; i32* col_P; i32* col_Q; unsigned char* col_closed;
+  int* flags;      // [0] error code, [1] a multi-chain column exists (PF_END)
+};
+
+// thread per column: the host loop (2a) below, line for line
+__global__ void __launch_bounds__(128) ring_order_kernel(const RingParams p) {
+  const i64 j = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (j >= p.ncols) return;
+  const i64 kb = p.pairbeg[j], ke = p.pairbeg[j + 1];
+  p.col_closed[j] = CK_VERTEX;
+  if (ke == kb) return;
+  const i64 len = p.colptr[j + 1] - p.colptr[j];
+  const int lj0 = (int)(p.gsrc[kb] / (u32)p.ncells);
+  if (lj0 < 4) {   // vertex column: filled by mirrors + the diagonal kernel
+    for (i64 k = kb; k < ke; k++) { p.pair_cell[k] = p.gcell[k]; p.pair_code[k] = 0; p.col_of_pair[k] = (u32)j; }
+    return;
+  }
+  if (len > 254 || ke - kb > MAXRING) { atomicMax(p.flags, ke - kb > MAXRING ? 7 : 1); return; }
+  const int n = (int)(ke - kb);
+  u32 rc[MAXRING]; unsigned char rl[MAXRING]; i32 nR[MAXRING], nS[MAXRING];    // cell, local ids P | Q<<2 | R<<4 | S<<6, ring nodes
+  i32 P0 = 0, Q0 = 0;
+  for (int t = 0; t < n; t++) {
+    const u32 c = p.gcell[kb + t];
+    const int lj = (int)(p.gsrc[kb + t] / (u32)p.ncells);
+    if (lj < 4) { atomicMax(p.flags, 2); return; }
+    int pl, ql; edge_nodes(lj - 4, pl, ql);
+    int rloc = -1, sloc = -1;
+    for (int v = 0; v < 4; v++) if (v != pl && v != ql) { if (rloc < 0) rloc = v; else sloc = v; }
+    const int4 cn4 = __ldg(reinterpret_cast<const int4*>(p.cellnodes) + c);
+    const i32 cn[4] = {cn4.x, cn4.y, cn4.z, cn4.w};
+    if (t == 0) { P0 = cn[pl]; Q0 = cn[ql]; }
+    if (cn[pl] != P0) { const int tmp = pl; pl = ql; ql = tmp; }
+    if (cn[pl] != P0 || cn[ql] != Q0) { atomicMax(p.flags, 3); return; }
+    rc[t] = c; rl[t] = (unsigned char)(pl | (ql << 2) | (rloc << 4) | (sloc << 6)); nR[t] = cn[rloc]; nS[t] = cn[sloc];
+  }
+  p.col_P[j] = P0; p.col_Q[j] = Q0;
+  bool closed = true;
+  u64 deg1R = 0, deg1S = 0;       // bit t: the R / S node of cell t has degree 1
+  for (int t = 0; t < n; t++) {
+    int dR = 0, dS = 0;
+    for (int u = 0; u < n; u++) {
+      dR += (nR[u] == nR[t]) + (nS[u] == nR[t]);
+      dS += (nR[u] == nS[t]) + (nS[u] == nS[t]);
+    }
+    if (dR > 2 || dS > 2) { atomicMax(p.flags, 4); return; }
+    if (dR == 1) deg1R |= 1ull << t;
+    if (dS == 1) deg1S |= 1ull << t;
+    if (dR == 1 || dS == 1) closed = false;
+  }
+  u64 used = 0;
+  int step = 0, nchains = 0;
+  while (step < n) {
+    int start = -1, start_in_is_R = 1;
+    if (closed) { if (step != 0) { atomicMax(p.flags, 5); return; } start = 0; }
+    else
+      for (int t = 0; t < n && start < 0; t++)
+        if (!((used >> t) & 1ull)) { if ((deg1R >> t) & 1ull) { start = t; start_in_is_R = 1; } else if ((deg1S >> t) & 1ull) { start = t; start_in_is_R = 0; } }
+    if (start < 0) { atomicMax(p.flags, 6); return; }
+    if (nchains > 0 && j < p.ncols_owned) { atomicMax(p.flags, 8); return; }
+    int curp = start;
+    const i32 first_in = start_in_is_R ? nR[start] : nS[start];
+    i32 vin = first_in;
+    bool chain_first = true;
+    while (true) {
+      used |= 1ull << curp;
+      const bool inR = (nR[curp] == vin);
+      const int Pl = rl[curp] & 3, Ql = (rl[curp] >> 2) & 3, Rl = (rl[curp] >> 4) & 3, Sl = (rl[curp] >> 6) & 3;
+      const int I = inR ? Rl : Sl, O = inR ? Sl : Rl;
+      const i32 vout = inR ? nS[curp] : nR[curp];
+      const i64 k = kb + step;
+      u32 fl = 0u;
+      if (chain_first && nchains > 0) fl |= PF_RESET;
+      p.pair_cell[k] = rc[curp];
+      u32 code = (u32)(Pl | (Ql << 2) | (I << 4) | (O << 6)) | (fl << 8);
+      p.col_of_pair[k] = (u32)j;
+      p.pair_in[k] = vin; p.pair_out[k] = vout;
+      step++; chain_first = false;
+      int nxt = -1;
+      for (int u = 0; u < n; u++) if (!((used >> u) & 1ull) && (nR[u] == vout || nS[u] == vout)) { nxt = u; break; }
+      if (nxt < 0) {
+        if (closed && (step != n || vout != first_in)) { atomicMax(p.flags, 9); return; }
+        if (!closed && step < n) { code |= (PF_END << 8); p.flags[1] = 1; }
+        p.pair_code[k] = code;
+        break;
+      }
+      p.pair_code[k] = code;
+      vin = vout; curp = nxt;
+    }
+    nchains++;
+  }
+  p.col_closed[j] = closed ? CK_CLOSED : CK_OPEN;
+}
+
+struct TileBuildParams {
+  const i64* pairbeg; const i64* colptr; const unsigned char* col_closed; const i32* pair_in; const i32* pair_out; const i32* col_P; const i32* col_Q;
+  i64 ncols;
+  int nw; i64 slot_cap, blob_cap; u32 cols_off;
+  // phase 1 outputs / phase 2 inputs, per chunk
+  int* chunk_ntiles; int* chunk_nnodes;       // counts (phase 1), exclusive offsets (phase 2)
+  int emit;
+  // phase 2 outputs
+  TileHdr* hdr; uint4* groups; u32* tile_nodeids; u32* col_tile; u32* col_pq; u32* col_abase; u32* col_group; u32* col_gcount; u32* pair_io;
+  int* flags;       // [2] max group nnz, [3] error
+};
+
+// one thread per chunk of TB_CHUNK columns: the host loop (2b) below with the tile's node set in a shared-memory hash table.
+// Phase 1 (emit = 0) counts tiles and tile nodes of the chunk, phase 2 (emit = 1) writes everything at the scanned offsets.
+__global__ void __launch_bounds__(32) tile_build_kernel(const TileBuildParams p) {
+  __shared__ u32 h_node[TB_HASH];      // node id
+  __shared__ u32 h_tag[TB_HASH];       // tile generation << 12 | tile-local id
+  if (threadIdx.x != 0) return;
+  const i64 chunk = blockIdx.x;
+  const i64 j0 = chunk * TB_CHUNK, j1 = min(j0 + (i64)TB_CHUNK, p.ncols);
+  for (int i = 0; i < TB_HASH; i++) { h_node[i] = 0xffffffffu; h_tag[i] = 0xffffffffu; }
+  const int NW = p.nw;
+  int tile_base = 0, node_base = 0;
+  if (p.emit) { tile_base = p.chunk_ntiles[chunk]; node_base = p.chunk_nnodes[chunk]; }
+  int cur_tile = 0;                        // chunk-local tile index = hash generation
+  int cur_cols = 0, cur_nodes = 0, cur_groups = 0, grp_cols = 0;
+  i64 grp_nnz = 0, cur_nnz = 0, cur_pairs = 0, tile_first_col = 0, tile_pair_base = 0, grp_first_col = 0;
+  int nodes_total = 0, tile_node_base = 0, max_slot = 0;
+  uint4 cur_grp[9];
+  auto lookup = [&](u32 v, bool insert) -> int {      // tile-local id of node v in the open tile, -1 if absent (inserted when asked)
+    u32 h = (v * 2654435761u) & (TB_HASH - 1);
+    for (;;) {
+      const bool live = h_node[h] != 0xffffffffu && (h_tag[h] >> 12) == (u32)cur_tile;
+      if (live && h_node[h] == v) return (int)(h_tag[h] & 0xfffu);
+      if (!live) {
+        if (!insert) return -1;
+        h_node[h] = v; h_tag[h] = ((u32)cur_tile << 12) | (u32)cur_nodes;
+        if (p.emit) p.tile_nodeids[(size_t)node_base + nodes_total] = v;
+        nodes_total++;
+        return cur_nodes++;
+      }
+      h = (h + 1) & (TB_HASH - 1);
+    }
+  };
+  auto close_group = [&](i64 end_col) {
+    if (!p.emit) return;
+    for (i64 c = grp_first_col; c < end_col; c++) { p.col_group[c] = (u32)grp_first_col; p.col_gcount[c] = (u32)(end_col - grp_first_col); }
+  };
+  auto close_tile = [&](i64 end_col) {
+    if (cur_cols == 0) return;
+    if (grp_cols > 0) { max_slot = max(max_slot, (int)grp_nnz); cur_groups++; close_group(end_col); }
+    if (p.emit) {
+      const i64 g0 = p.colptr[tile_first_col] - 1;
+      TileHdr h;
+      h.c0 = (int)tile_first_col; h.ncol = (int)(end_col - tile_first_col); h.nnodes = cur_nodes; h.npairs = (int)cur_pairs;
+      h.g0lo = (u32)(g0 & 0xffffffffll); h.g0hi = (u32)(g0 >> 32); h.nnz = (int)cur_nnz; h.blob16 = 0;
+      h.pair_base = (u32)tile_pair_base; h.node_base = (u32)(node_base + tile_node_base);
+      h.cols_off = p.cols_off;
+      h.blob_bytes = blob_size(p.cols_off, (u32)h.ncol, (u32)cur_pairs, (u32)cur_nodes);
+      p.hdr[tile_base + cur_tile] = h;
+      for (int w2 = cur_groups; w2 <= NW; w2++) cur_grp[w2] = make_uint4((u32)h.ncol, (u32)cur_nnz, (u32)cur_pairs, 0);
+      for (int w2 = 0; w2 <= NW; w2++) p.groups[(size_t)(tile_base + cur_tile) * (NW + 1) + w2] = cur_grp[w2];
+    }
+    cur_groups = 0; grp_cols = 0; grp_nnz = 0;
+    tile_node_base = nodes_total;
+    cur_tile++; cur_cols = 0; cur_nodes = 0; cur_nnz = 0; cur_pairs = 0;
+    if (cur_tile >= (1 << 19)) p.flags[3] = 1;       // generation field of the hash tags
+  };
+  for (i64 j = j0; j < j1; j++) {
+    const i64 kb = p.pairbeg[j], ke = p.pairbeg[j + 1];
+    const i64 len = p.colptr[j + 1] - p.colptr[j];
+    if (ke == kb || p.col_closed[j] == CK_VERTEX) { close_tile(j); continue; }
+    const int n = (int)(ke - kb);
+    const u32 P0 = (u32)p.col_P[j], Q0 = (u32)p.col_Q[j];
+    for (int attempt = 0; attempt < 2; attempt++) {
+      // distinct nodes of the column that the open tile does not hold yet
+      u32 fresh_list[2 * MAXRING + 2];
+      int fresh = 0;
+      auto consider = [&](u32 v) {
+        if (lookup(v, false) >= 0) return;
+        for (int i = 0; i < fresh; i++) if (fresh_list[i] == v) return;
+        fresh_list[fresh++] = v;
+      };
+      consider(P0); consider(Q0);
+      for (int t = 0; t < n; t++) { consider((u32)p.pair_in[kb + t]); consider((u32)p.pair_out[kb + t]); }
+      const bool over = (i64)blob_size(p.cols_off, (u32)(cur_cols + 1), (u32)(cur_pairs + n), (u32)(cur_nodes + fresh)) > p.blob_cap;
+      const bool grp_full = grp_cols > 0 && (grp_cols == 32 || grp_nnz + len > p.slot_cap);
+      if (cur_cols > 0 && ((grp_full && cur_groups + 1 >= NW) || over || cur_nodes + fresh > MAX_TILE_NODES || cur_pairs + n > 65535)) { close_tile(j); continue; }
+      if (len > p.slot_cap) { p.flags[3] = 2; return; }
+      if (cur_cols == 0) { tile_first_col = j; tile_pair_base = kb; }
+      if (grp_full) { max_slot = max(max_slot, (int)grp_nnz); cur_groups++; grp_cols = 0; grp_nnz = 0; close_group(j); }
+      if (grp_cols == 0) { cur_grp[cur_groups] = make_uint4((u32)cur_cols, (u32)cur_nnz, (u32)cur_pairs, 0); grp_first_col = j; }
+      if (p.emit) p.col_abase[j] = (u32)grp_nnz;
+      grp_cols++; grp_nnz += len;
+      const int lp = lookup(P0, true), lq = lookup(Q0, true);
+      for (int t = 0; t < n; t++) {
+        const int li = lookup((u32)p.pair_in[kb + t], true), lo = lookup((u32)p.pair_out[kb + t], true);
+        if (p.emit) p.pair_io[kb + t] = (u32)li | ((u32)lo << 12);
+      }
+      if (p.emit) { p.col_pq[j] = (u32)lp | ((u32)lq << 12); p.col_tile[j] = (u32)(tile_base + cur_tile); }
+      cur_cols++; cur_nnz += len; cur_pairs += n;
+      break;
+    }
+  }
+  close_tile(j1);
+  if (!p.emit) { p.chunk_ntiles[chunk] = cur_tile; p.chunk_nnodes[chunk] = nodes_total; }
+  atomicMax(p.flags + 2, max_slot);
+}
+
+// per tile: blob size / mirror candidates (inputs of the two scans), then the scanned offsets back into the headers
+__global__ void tile_sizes(const TileHdr* hdr, int ntiles, i64* blob16, int* mir) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > ntiles) return;
+  blob16[t] = t < ntiles ? (i64)(hdr[t].blob_bytes / 16) : 0;
+  mir[t] = t < ntiles ? 5 * hdr[t].ncol + hdr[t].npairs : 0;
+}
+__global__ void tile_offsets(TileHdr* hdr, int ntiles, const i64* blob16_scan, uint2* tile_dir, int* maxblob) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  hdr[t].blob16 = (u32)blob16_scan[t];
+  tile_dir[t] = make_uint2((u32)blob16_scan[t], hdr[t].blob_bytes);
+  atomicMax(maxblob, (int)hdr[t].blob_bytes);
+}
+__global__ void flag_vertex_columns(const unsigned char* col_closed, const i64* pairbeg, i64 ncols, unsigned char* isv) {
+  const i64 j = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (j < ncols) isv[j] = (col_closed[j] == CK_VERTEX && pairbeg[j + 1] > pairbeg[j]) ? 1 : 0;
+}
+
 // closed-form local stiffness of the unit reference tetrahedron, used to verify that the
 // caller's tables describe the standard P2 basis (src/fedefs/h1_p2.jl:223-239)
 void reference_local_closed_form(double K[10][10]) {
@@ -788,6 +1006,197 @@ bool fast_p2tet_applicable(const BlfLocalParams& p) {
          (p.apt == GRMP_APT_SYMMETRIC || (p.apt == GRMP_APT_BILINEARFORM && !p.transposed));
 }
 
+// Device build: ring orders, tiles, records, mirror lists and vertex-column records without a round trip through the host
+// (only counters come back).  Same outputs as the host build below.
+static int fast_p2tet_build_device(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const DofGather& dg, i64 ncols_owned_eff, int NW,
+                                   int NBUF, i64 SLOT_CAP, i64 BLOB_CAP, u32 cols_off, FastP2Tet* out) {
+  cudaStream_t s = ctx->stream;
+  const bool verbose = getenv("GRMP_VERBOSE") != nullptr;
+  auto t_start = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!verbose) return;
+    cudaStreamSynchronize(s);
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[grmp fast build, device] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - t_start).count());
+    t_start = t;
+  };
+  const i64 ncells = p.g.ncells, ncols = pat.ncols, npairs = dg.ncontrib;
+  const i64 np1 = std::max<i64>(npairs, 1), nc1 = std::max<i64>(ncols, 1);
+  DevBuf<u32> d_cell, d_io, d_code, d_colof, d_coltile, d_colpq, d_abase, d_colgroup, d_colgcount;
+  DevBuf<i32> d_in, d_out, d_P, d_Q;
+  DevBuf<unsigned char> d_closed;
+  DevBuf<int> d_flags;
+  GRMP_TRY(d_cell.alloc(np1)); GRMP_TRY(d_io.alloc(np1)); GRMP_TRY(d_code.alloc(np1)); GRMP_TRY(d_colof.alloc(np1));
+  GRMP_TRY(d_in.alloc(np1)); GRMP_TRY(d_out.alloc(np1)); GRMP_TRY(d_P.alloc(nc1)); GRMP_TRY(d_Q.alloc(nc1)); GRMP_TRY(d_closed.alloc(nc1));
+  GRMP_TRY(d_coltile.alloc(nc1)); GRMP_TRY(d_colpq.alloc(nc1)); GRMP_TRY(d_abase.alloc(nc1)); GRMP_TRY(d_colgroup.alloc(nc1)); GRMP_TRY(d_colgcount.alloc(nc1));
+  GRMP_TRY(d_flags.alloc(4));
+  GRMP_CUDA(cudaMemsetAsync(d_flags.p, 0, 16, s));
+  GRMP_CUDA(cudaMemsetAsync(d_io.p, 0, d_io.bytes(), s)); GRMP_CUDA(cudaMemsetAsync(d_code.p, 0, d_code.bytes(), s));
+  GRMP_CUDA(cudaMemsetAsync(d_coltile.p, 0xff, d_coltile.bytes(), s)); GRMP_CUDA(cudaMemsetAsync(d_colpq.p, 0, d_colpq.bytes(), s));
+  GRMP_CUDA(cudaMemsetAsync(d_abase.p, 0, d_abase.bytes(), s)); GRMP_CUDA(cudaMemsetAsync(d_colgroup.p, 0, d_colgroup.bytes(), s));
+  GRMP_CUDA(cudaMemsetAsync(d_colgcount.p, 0, d_colgcount.bytes(), s));
+  GRMP_CUDA(cudaMemsetAsync(d_P.p, 0, d_P.bytes(), s)); GRMP_CUDA(cudaMemsetAsync(d_Q.p, 0, d_Q.bytes(), s));
+  // (2a) ring order of every edge column
+  RingParams rp{dg.gcell.p, dg.gsrc.p, dg.segptr.p, pat.colptr.p, p.g.cellnodes, ncells, ncols, ncols_owned_eff,
+                d_cell.p, d_code.p, d_colof.p, d_in.p, d_out.p, d_P.p, d_Q.p, d_closed.p, d_flags.p};
+  if (ncols) ring_order_kernel<<<(unsigned)((ncols + 127) / 128), 128, 0, s>>>(rp);
+  GRMP_CUDA(cudaGetLastError());
+  int hflags[4] = {0, 0, 0, 0};
+  GRMP_CUDA(cudaMemcpyAsync(hflags, d_flags.p, 16, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  if (hflags[0]) {
+    static const char* msg[] = {"", "fast path: an edge column has more than 254 entries", "fast path: mixed dof types in one column",
+                                "fast path: inconsistent edge column", "fast path: non-manifold edge star", "fast path: edge star is not a single ring",
+                                "fast path: edge star mixes a ring and chains", "fast path: more than 64 cells around an edge (GRMP_FAST_HOST_BUILD=1 handles 255)",
+                                "fast path: an owned edge star is not a single chain", "fast path: edge ring does not close"};
+    return fail(GRMP_EUNSUPPORTED, msg[std::min(hflags[0], 9)]);
+  }
+  const bool any_end = hflags[1] != 0;
+  lap("ring order");
+  // (2b) tiles: chunks of TB_CHUNK columns packed independently, count pass + emit pass
+  const i64 nchunks = (ncols + TB_CHUNK - 1) / TB_CHUNK;
+  DevBuf<int> d_cnt_t, d_cnt_n, d_off_t, d_off_n;
+  GRMP_TRY(d_cnt_t.alloc(nchunks + 1)); GRMP_TRY(d_cnt_n.alloc(nchunks + 1)); GRMP_TRY(d_off_t.alloc(nchunks + 1)); GRMP_TRY(d_off_n.alloc(nchunks + 1));
+  GRMP_CUDA(cudaMemsetAsync(d_cnt_t.p, 0, d_cnt_t.bytes(), s)); GRMP_CUDA(cudaMemsetAsync(d_cnt_n.p, 0, d_cnt_n.bytes(), s));
+  TileBuildParams tb{};
+  tb.pairbeg = dg.segptr.p; tb.colptr = pat.colptr.p; tb.col_closed = d_closed.p; tb.pair_in = d_in.p; tb.pair_out = d_out.p; tb.col_P = d_P.p; tb.col_Q = d_Q.p;
+  tb.ncols = ncols; tb.nw = NW; tb.slot_cap = SLOT_CAP; tb.blob_cap = BLOB_CAP; tb.cols_off = cols_off;
+  tb.chunk_ntiles = d_cnt_t.p; tb.chunk_nnodes = d_cnt_n.p; tb.emit = 0; tb.flags = d_flags.p;
+  if (nchunks) tile_build_kernel<<<(unsigned)nchunks, 32, 0, s>>>(tb);
+  GRMP_CUDA(cudaGetLastError());
+  DevBuf<unsigned char> d_tmp;
+  auto scan_int = [&](const int* in, int* outp, i64 n) -> int {
+    size_t tbytes = 0;
+    GRMP_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tbytes, in, outp, n, s));
+    if (tbytes > d_tmp.n) GRMP_TRY(d_tmp.alloc(std::max<size_t>(tbytes, 16)));
+    GRMP_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, tbytes, in, outp, n, s));
+    return GRMP_OK;
+  };
+  GRMP_TRY(scan_int(d_cnt_t.p, d_off_t.p, nchunks + 1));
+  GRMP_TRY(scan_int(d_cnt_n.p, d_off_n.p, nchunks + 1));
+  int tot[2] = {0, 0};
+  GRMP_CUDA(cudaMemcpyAsync(&tot[0], d_off_t.p + nchunks, 4, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaMemcpyAsync(&tot[1], d_off_n.p + nchunks, 4, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaMemcpyAsync(hflags, d_flags.p, 16, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  if (hflags[3] == 2) return fail(GRMP_EUNSUPPORTED, "fast path: a single column exceeds the stage slot");
+  if (hflags[3]) return fail(GRMP_EUNSUPPORTED, "fast path: too many tiles in one chunk");
+  const int ntiles = tot[0];
+  const i64 nnodes_total = tot[1];
+  DevBuf<uint4> d_groups;
+  DevBuf<u32>& d_nodeids = out->tile_nodeids;
+  DevBuf<int4>& d_hdr = out->tile_hdr;
+  GRMP_TRY(d_hdr.alloc((size_t)std::max(ntiles, 1) * 3)); GRMP_TRY(d_groups.alloc((size_t)std::max(ntiles, 1) * (NW + 1)));
+  GRMP_TRY(d_nodeids.alloc(std::max<i64>(nnodes_total, 1)));
+  GRMP_CUDA(cudaMemsetAsync(d_hdr.p, 0, d_hdr.bytes(), s)); GRMP_CUDA(cudaMemsetAsync(d_groups.p, 0, d_groups.bytes(), s));
+  GRMP_CUDA(cudaMemsetAsync(d_nodeids.p, 0, d_nodeids.bytes(), s));
+  tb.chunk_ntiles = d_off_t.p; tb.chunk_nnodes = d_off_n.p; tb.emit = 1;
+  tb.hdr = reinterpret_cast<TileHdr*>(d_hdr.p); tb.groups = d_groups.p; tb.tile_nodeids = d_nodeids.p; tb.col_tile = d_coltile.p; tb.col_pq = d_colpq.p;
+  tb.col_abase = d_abase.p; tb.col_group = d_colgroup.p; tb.col_gcount = d_colgcount.p; tb.pair_io = d_io.p;
+  if (nchunks) tile_build_kernel<<<(unsigned)nchunks, 32, 0, s>>>(tb);
+  GRMP_CUDA(cudaGetLastError());
+  // blob offsets and mirror-candidate offsets: scans over the tiles
+  DevBuf<i64> d_b16, d_b16s;
+  DevBuf<int> d_mir, d_mirbase, d_maxblob;
+  GRMP_TRY(d_b16.alloc(ntiles + 1)); GRMP_TRY(d_b16s.alloc(ntiles + 1)); GRMP_TRY(d_mir.alloc(ntiles + 1)); GRMP_TRY(d_mirbase.alloc(ntiles + 1));
+  GRMP_TRY(d_maxblob.alloc(1));
+  GRMP_CUDA(cudaMemsetAsync(d_maxblob.p, 0, 4, s));
+  tile_sizes<<<(unsigned)((ntiles + 1 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const TileHdr*>(d_hdr.p), ntiles, d_b16.p, d_mir.p);
+  {
+    size_t tbytes = 0;
+    GRMP_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tbytes, d_b16.p, d_b16s.p, ntiles + 1, s));
+    if (tbytes > d_tmp.n) GRMP_TRY(d_tmp.alloc(std::max<size_t>(tbytes, 16)));
+    GRMP_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, tbytes, d_b16.p, d_b16s.p, ntiles + 1, s));
+  }
+  GRMP_TRY(scan_int(d_mir.p, d_mirbase.p, ntiles + 1));
+  GRMP_TRY(out->tile_dir.alloc(std::max(ntiles, 1)));
+  GRMP_CUDA(cudaMemsetAsync(out->tile_dir.p, 0, out->tile_dir.bytes(), s));
+  if (ntiles) tile_offsets<<<(unsigned)((ntiles + 255) / 256), 256, 0, s>>>(reinterpret_cast<TileHdr*>(d_hdr.p), ntiles, d_b16s.p, out->tile_dir.p, d_maxblob.p);
+  GRMP_CUDA(cudaGetLastError());
+  i64 blob_total16 = 0;
+  int nmir_total = 0, max_blob = 0;
+  GRMP_CUDA(cudaMemcpyAsync(&blob_total16, d_b16s.p + ntiles, 8, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaMemcpyAsync(&nmir_total, d_mirbase.p + ntiles, 4, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaMemcpyAsync(&max_blob, d_maxblob.p, 4, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaMemcpyAsync(hflags, d_flags.p, 16, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  const i64 max_slot = hflags[2];
+  lap("tiles (chunks)");
+  const i64 slot_elems = (max_slot + 2 + 1) & ~1ll;
+  const i64 max_smem = (i64)NBUF * max_blob + NW * 8 * slot_elems;
+  if (max_smem > 220 * 1024) return fail(GRMP_EUNSUPPORTED, "fast path: a single column exceeds the shared-memory tile");
+  if (max_blob > 8 * 65535) return fail(GRMP_EUNSUPPORTED, "fast path: tile blob exceeds the 16-bit word index of the mirror list");
+  if (blob_total16 >= (i64)NONE) return fail(GRMP_EUNSUPPORTED, "fast path: record blob exceeds 64 GB");
+  out->ntiles = ntiles; out->npairs = npairs; out->smem_bytes = (int)std::max<i64>(max_smem, 1024); out->in_stride = (u32)max_blob;
+  out->slot_elems = (u32)slot_elems;
+  out->prof.release();
+  if (getenv("GRMP_FAST_PROF")) {
+    GRMP_TRY(out->prof.alloc(8 * 1024));
+    GRMP_CUDA(cudaMemsetAsync(out->prof.p, 0, out->prof.bytes(), s));
+  }
+  GRMP_TRY(out->tile_counter.alloc(1));
+  GRMP_CUDA(cudaMemsetAsync(out->tile_counter.p, 0, sizeof(int), s));
+  // (3) records into the blobs, mirror candidates sorted by destination
+  DevBuf<u32> d_mkey, d_mval, d_mkey2, d_mval2;
+  const i64 nm1 = std::max<i64>(nmir_total, 1);
+  GRMP_TRY(d_mkey.alloc(nm1)); GRMP_TRY(d_mval.alloc(nm1)); GRMP_TRY(d_mkey2.alloc(nm1)); GRMP_TRY(d_mval2.alloc(nm1));
+  GRMP_CUDA(cudaMemsetAsync(d_mkey.p, 0xff, d_mkey.bytes(), s));
+  GRMP_TRY(out->blob.alloc(std::max<size_t>((size_t)blob_total16 * 16, 16)));
+  GRMP_CUDA(cudaMemsetAsync(out->blob.p, 0, out->blob.bytes(), s));
+  out->end_slots.release();
+  if (any_end) GRMP_TRY(out->end_slots.alloc(np1));
+  PackParams pp{d_cell.p, d_io.p, d_code.p, dg.segptr.p, pat.colptr.p, pat.rowval.p, p.e1.celldofs, d_colof.p, d_closed.p,
+                d_coltile.p, d_colpq.p, d_abase.p, d_colgroup.p, d_colgcount.p, reinterpret_cast<const TileHdr*>(d_hdr.p), d_mirbase.p, npairs, ncols,
+                out->blob.p, out->end_slots.p, d_mkey.p, d_mval.p};
+  if (npairs && ntiles) pack_pairs<<<(unsigned)((npairs + 255) / 256), 256, 0, s>>>(pp);
+  if (ncols && ntiles) pack_cols<<<(unsigned)((ncols + 255) / 256), 256, 0, s>>>(pp);
+  GRMP_CUDA(cudaGetLastError());
+  if (ntiles > 0) {
+    size_t tmp_bytes = 0;
+    GRMP_CUDA(cub::DeviceSegmentedSort::SortPairs(nullptr, tmp_bytes, d_mkey.p, d_mkey2.p, d_mval.p, d_mval2.p, nmir_total, ntiles,
+                                                  d_mirbase.p, d_mirbase.p + 1, s));
+    DevBuf<unsigned char> d_tmp2;
+    GRMP_TRY(d_tmp2.alloc(std::max<size_t>(tmp_bytes, 16)));
+    GRMP_CUDA(cub::DeviceSegmentedSort::SortPairs(d_tmp2.p, tmp_bytes, d_mkey.p, d_mkey2.p, d_mval.p, d_mval2.p, nmir_total, ntiles,
+                                                  d_mirbase.p, d_mirbase.p + 1, s));
+    pack_tile_rest<<<ntiles, 128, 0, s>>>(reinterpret_cast<const TileHdr*>(d_hdr.p), d_groups.p, NW, d_nodeids.p, p.g.coords, d_mirbase.p,
+                                          d_mkey2.p, d_mval2.p, out->blob.p);
+    GRMP_CUDA(cudaGetLastError());
+    GRMP_CUDA(cudaStreamSynchronize(s));
+  }
+  lap("pack kernels + mirror sort");
+  // (4) vertex columns: compacted list + diagonal slots
+  {
+    DevBuf<unsigned char> d_isv;
+    DevBuf<i64> d_nsel;
+    GRMP_TRY(d_isv.alloc(nc1)); GRMP_TRY(d_nsel.alloc(1)); GRMP_TRY(out->vcols.alloc(nc1));
+    if (ncols) flag_vertex_columns<<<(unsigned)((ncols + 255) / 256), 256, 0, s>>>(d_closed.p, dg.segptr.p, ncols, d_isv.p);
+    GRMP_CUDA(cudaMemsetAsync(d_nsel.p, 0, 8, s));
+    if (ncols) {
+      cub::CountingInputIterator<u32> it(0);
+      size_t tbytes = 0;
+      GRMP_CUDA(cub::DeviceSelect::Flagged(nullptr, tbytes, it, d_isv.p, out->vcols.p, d_nsel.p, (int)ncols, s));
+      if (tbytes > d_tmp.n) GRMP_TRY(d_tmp.alloc(std::max<size_t>(tbytes, 16)));
+      GRMP_CUDA(cub::DeviceSelect::Flagged(d_tmp.p, tbytes, it, d_isv.p, out->vcols.p, d_nsel.p, (int)ncols, s));
+    }
+    i64 nsel = 0;
+    GRMP_CUDA(cudaMemcpyAsync(&nsel, d_nsel.p, 8, cudaMemcpyDeviceToHost, s));
+    GRMP_CUDA(cudaStreamSynchronize(s));
+    out->nvcols = nsel;
+    GRMP_TRY(out->vrec.alloc((size_t)std::max<i64>(2 * nsel, 2)));
+    if (nsel > 0) {
+      find_diag_slots<<<(unsigned)((nsel + 255) / 256), 256, 0, s>>>(out->vcols.p, nsel, pat.colptr.p, pat.rowval.p, d_closed.p, out->vrec.p);
+      GRMP_CUDA(cudaGetLastError());
+    }
+  }
+  const int smem_attr = (int)std::max<i64>(max_smem, 1024);
+  GRMP_TRY(set_smem_attr<3>(smem_attr)); GRMP_TRY(set_smem_attr<4>(smem_attr)); GRMP_TRY(set_smem_attr<5>(smem_attr));
+  GRMP_TRY(set_smem_attr<6>(smem_attr)); GRMP_TRY(set_smem_attr<7>(smem_attr));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  lap("vertex columns");
+  return GRMP_OK;
+}
+
 int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, const std::vector<double>& w,
                      const std::vector<double>& derivs, i64 ncols_owned, i64 geom_version, FastP2Tet* out) {
   // halo columns (>= ncols_owned) are processed too: their mirrors complete the owned vertex columns;
@@ -823,16 +1232,6 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   GRMP_TRY(build_dofgather(s, p.e1.celldofs, ncells, 10, ncols, &dg));
   const i64 npairs = dg.ncontrib;
   if (npairs >= (i64)NONE) return fail(GRMP_EUNSUPPORTED, "fast path: more than 2^32-1 pairs");
-  std::vector<u32> h_cell(npairs), h_src(npairs);
-  std::vector<i64> h_pairbeg(ncols + 1), h_colptr(ncols + 1);
-  std::vector<i32> h_cn((size_t)ncells * 4);
-  GRMP_CUDA(cudaMemcpyAsync(h_cell.data(), dg.gcell.p, npairs * 4, cudaMemcpyDeviceToHost, s));
-  GRMP_CUDA(cudaMemcpyAsync(h_src.data(), dg.gsrc.p, npairs * 4, cudaMemcpyDeviceToHost, s));
-  GRMP_CUDA(cudaMemcpyAsync(h_pairbeg.data(), dg.segptr.p, (ncols + 1) * 8, cudaMemcpyDeviceToHost, s));
-  GRMP_CUDA(cudaMemcpyAsync(h_colptr.data(), pat.colptr.p, (ncols + 1) * 8, cudaMemcpyDeviceToHost, s));
-  GRMP_CUDA(cudaMemcpyAsync(h_cn.data(), p.g.cellnodes, (size_t)ncells * 16, cudaMemcpyDeviceToHost, s));
-  GRMP_CUDA(cudaStreamSynchronize(s));
-  lap("dof gather + downloads");
   // tile shape (tunable for experiments: GRMP_FAST_NW in 3..7, GRMP_FAST_SLOT, GRMP_FAST_SMEM_KB)
   int NW = getenv("GRMP_FAST_NW") ? atoi(getenv("GRMP_FAST_NW")) : NW_DEFAULT;
   if (NW < 3 || NW > 7) NW = NW_DEFAULT;
@@ -847,6 +1246,18 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   out->nw = NW;
   out->nbuf = NBUF;
   out->geom_version = geom_version;
+  const bool device_build = !getenv("GRMP_FAST_HOST_BUILD") && BLOB_CAP / 24 < TB_HASH / 2;
+  if (device_build) return fast_p2tet_build_device(ctx, p, pat, dg, ncols_owned_eff, NW, NBUF, SLOT_CAP, BLOB_CAP, cols_off, out);
+  std::vector<u32> h_cell(npairs), h_src(npairs);
+  std::vector<i64> h_pairbeg(ncols + 1), h_colptr(ncols + 1);
+  std::vector<i32> h_cn((size_t)ncells * 4);
+  GRMP_CUDA(cudaMemcpyAsync(h_cell.data(), dg.gcell.p, npairs * 4, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaMemcpyAsync(h_src.data(), dg.gsrc.p, npairs * 4, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaMemcpyAsync(h_pairbeg.data(), dg.segptr.p, (ncols + 1) * 8, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaMemcpyAsync(h_colptr.data(), pat.colptr.p, (ncols + 1) * 8, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaMemcpyAsync(h_cn.data(), p.g.cellnodes, (size_t)ncells * 16, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  lap("dof gather + downloads");
   // (2) host: ring order of every edge column, tiles over the edge columns, list of vertex columns
   std::vector<u32> pair_cell(npairs), pair_io(npairs), pair_code(npairs), col_of_pair(npairs), vcols;
   std::vector<unsigned char> col_closed(ncols, 2);

@@ -289,6 +289,30 @@ def test_fast_p2tet_matches_generic_and_is_deterministic():
     assert abs(A - A.T).max() < 1e-12 * np.abs(b[2]).max()
 
 
+@pytest.mark.parametrize("grid", ["uniform L3", "perturbed L3", "delaunay"])
+def test_fast_p2tet_device_build_equals_host_build(grid, monkeypatch):
+    """the record build of the ring-walk kernel runs on the GPU (ring order per edge column, tiles packed in chunks); the host build
+    (GRMP_FAST_HOST_BUILD=1) is kept for cross-validation: same pattern, same values bit for bit (the ring orders are the same, the
+    tilings differ only by the cuts at chunk boundaries, and no value depends on the tiling)"""
+    if grid == "delaunay":
+        g = delaunay_tet_grid(300, 5)
+    else:
+        g = tet_grid(3, grid.startswith("perturbed"))
+    s = G.FESpace(G.H1P2(1, 3), g)
+    out = []
+    for host in (False, True):
+        if host:
+            monkeypatch.setenv("GRMP_FAST_HOST_BUILD", "1")
+        else:
+            monkeypatch.delenv("GRMP_FAST_HOST_BUILD", raising=False)
+        AP = G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [s, s])
+        G.blf_set_path(AP, G._lib.PATH_FAST)
+        out.append(G.assemble_csc(AP, 1.5))
+        assert G.blf_stats(AP).path == G._lib.PATH_FAST
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+
+
 def test_fast_p2tet_follows_geometry_updates():
     """the fast path keeps tile-blocked copies of the node coordinates: grmp_grid_update_geometry must refresh them"""
     g = tet_grid(2, True)
