@@ -412,4 +412,77 @@ function GRMP.assemble!(b::FEVectorBlock{Float64,Float64,Int32}, AP::AssemblyPat
     return nothing
 end
 
+# ---- ItemIntegrator (src/assemblypatterns/itemintegrator.jl:160-360), one argument -------------------------------------------------
+# The library evaluates NoAction and the kernels of L2NormIntegrator / L2ErrorIntegrator; an ItemIntegrator carries them as opaque
+# closures, so the device versions are constructed explicitly:
+#     II = GRMPCuda.L2ErrorIntegrator(u_exact, Identity; quadorder = 4)       # same arguments as the reference constructor
+#     err2 = GRMPCuda.evaluate(II, Solution[1])                               # = evaluate(L2ErrorIntegrator(...), Solution[1])
+struct DeviceItemIntegrator
+    operator::DataType
+    kind::Int                      # GRMP_II_NONE / L2NORM / L2ERROR
+    data::Union{Nothing,GRMP.AbstractUserDataType}
+    factor::Float64
+    bonus_quadorder::Int
+    regions::Vector{Int}
+end
+ItemIntegrator(operator::DataType; regions = [0]) = DeviceItemIntegrator(operator, 0, nothing, 1.0, 0, regions)
+L2NormIntegrator(ncomponents::Int, operator::DataType; quadorder = 2, regions = [0]) = DeviceItemIntegrator(operator, 1, nothing, 1.0, quadorder, regions)
+L2ErrorIntegrator(compare_data, operator::DataType = Identity; quadorder = "auto", factor = 1, regions = [0]) =
+    DeviceItemIntegrator(operator, 2, compare_data, Float64(factor), quadorder == "auto" ? 2 * compare_data.bonus_quadorder : quadorder, regions)
+
+function prepare(II::DeviceItemIntegrator, FES::FESpace{Float64,Int32,FEType}) where {FEType}
+    xgrid = FES.xgrid
+    EG = xgrid[UniqueCellGeometries][1]
+    order = max(II.bonus_quadorder + GRMP.get_polynomialorder(FEType, EG) + GRMP.QuadratureOrderShift4Operator(II.operator), 0)   # assemblypatterns.jl:559-565
+    qf = QuadratureRule{Float64,EG}(order)
+    ev = FEEvaluator(FES, II.operator, qf)
+    v, dv, t = evaltab(ev)
+    w = Vector{Float64}(qf.w)
+    regions = II.regions == [0] ? Int32[] : Vector{Int32}(II.regions)
+    h = Ref{Ptr{Cvoid}}()
+    GC.@preserve v dv w regions check(ccall((:grmp_ii_create, lib), Cint,
+        (Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Cint, Cint, Ptr{Float64}, Ref{EvalTab}, Ref{Ptr{Cvoid}}),
+        device_space(FES).h, opcode(II.operator), II.kind, isempty(regions) ? C_NULL : pointer(regions), length(regions), length(w), w, t, h))
+    return h[], ev, qf
+end
+
+# compare_data at the quadrature points, evaluated like L2error_function does (itemintegrator.jl:52-69) -> [resultdim, nq, ncells]
+function tabulate_data(data, ev, qf, xgrid)
+    ncells = num_sources(xgrid[CellNodes]); rd = data.argsizes[1]
+    tab = zeros(Float64, rd, length(qf.w), ncells)
+    x = zeros(Float64, size(xgrid[Coordinates], 1))
+    for cell = 1:ncells
+        update_trafo!(ev.L2G, cell)
+        for i = 1:length(qf.w)
+            eval_trafo!(x, ev.L2G, ev.xref[i])
+            if GRMP.is_xdependent(data); data.x = x; end
+            GRMP.eval_data!(data)
+            @views tab[:, i, cell] .= data.val[1:rd]
+        end
+    end
+    return vec(tab)
+end
+
+"`evaluate!(b, II, FEB)`: b[j, item] += ... (itemintegrator.jl:160-300); `evaluate(II, FEB)`: the accumulation over all items (316-360)"
+function evaluate!(b::Matrix{Float64}, II::DeviceItemIntegrator, FEB::FEVectorBlock{Float64,Float64,Int32}; total = nothing)
+    h, ev, qf = prepare(II, FEB.FES)
+    try
+        data = II.kind == 2 ? tabulate_data(II.data, ev, qf, FEB.FES.xgrid) : Float64[]
+        coeffs = FEB.entries[FEB.offset+1:FEB.last_index]
+        GC.@preserve data coeffs b check(ccall((:grmp_ii_evaluate, lib), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            h, coeffs, II.factor, isempty(data) ? C_NULL : pointer(data), isempty(b) ? C_NULL : pointer(b), total === nothing ? C_NULL : pointer(total)))
+    finally
+        ccall((:grmp_ii_destroy, lib), Cint, (Ptr{Cvoid},), h)
+    end
+    return nothing
+end
+function evaluate(II::DeviceItemIntegrator, FEB::FEVectorBlock{Float64,Float64,Int32})
+    rd = Ref{Cint}(0)
+    total = zeros(Float64, 16)
+    evaluate!(Matrix{Float64}(undef, 0, 0), II, FEB; total = total)
+    n = II.kind == 0 ? GRMP.Length4Operator(II.operator, size(FEB.FES.xgrid[Coordinates], 1), get_ncomponents(eltype(FEB.FES))) : 1
+    return n == 1 ? total[1] : total[1:n]
+end
+
 end # module
