@@ -140,6 +140,10 @@ struct grmp_blf {
   double last_matmul_ms = 0.0;
   bool have_pattern = false, have_values = false;
   DevBuf<double> lbuf, nzval;
+  grmp_space* sa = nullptr;       // fixed (coefficient) argument of a trilinear form
+  int opa = 0, aq_rd = 0;
+  EvalTables ta;
+  DevBuf<double> acoeffs, aq, aq_scratch;
   FastP2Tet fast;
   i64 ncols_owned = -1;
   double p2tet_kappa = 0.0;       // cancellation indicator of the grid (AUTO guard of the ring-walk kernel)
@@ -183,6 +187,8 @@ static int fill_blf_params(grmp_blf* b, double factor, BlfLocalParams* p) {
   p->action = b->action; p->act_p[0] = b->act_p[0]; p->act_p[1] = b->act_p[1];
   p->apt = b->apt; p->transposed = b->transposed; p->reg = b->reg; p->nq = b->nq; p->w = b->w.p; p->factor = factor;
   p->nrows_key = b->out_rows();
+  p->aq = b->aq.p; p->aq_rd = b->aq_rd;
+  if (b->action == GRMP_ACT_CONVECTION && (!b->sa || !b->aq.p)) return fail(GRMP_ESTATE, "GRMP_ACT_CONVECTION: call grmp_blf_set_fixed_argument first");
   p->keys = nullptr; p->lbuf = nullptr;
   return GRMP_OK;
 }
@@ -204,9 +210,8 @@ static int blf_numeric_launch(grmp_blf* b, BlfLocalParams& p, cudaStream_t s) {
   if (b->path == GRMP_PATH_FAST) {
     GRMP_TRY(fast_p2tet_numeric(ctx, p, b->pat, b->fast, b->s1->grid->geom_version, b->nzval.p));
     b->st.kernel_launches = 2;
-    // halo columns (owned by another rank) are walked for their mirrors only; what they staged is not a matrix column
-    if (b->halo_first_slot >= 0 && b->halo_first_slot < b->pat.nnz)
-      GRMP_CUDA(cudaMemsetAsync(b->nzval.p + b->halo_first_slot, 0, (size_t)(b->pat.nnz - b->halo_first_slot) * 8, s));
+    // halo columns (owned by another rank) are walked for their mirrors only; the kernels never store into their slots, which
+    // were zeroed once by the symbolic pass
   } else if (b->path == GRMP_PATH_COLUMNS) {
     GRMP_TRY(colpath_numeric(ctx, p, b->pat, b->colp, b->nzval.p));
     b->st.kernel_launches = 1 + (i64)b->colp.classes.size();    // geometry records + one launch per tile class
@@ -351,7 +356,9 @@ int grmp_blf_create(grmp_space* s1, grmp_space* s2, int op1, int op2, int action
   if (!s1 || !s2 || !qweights || !tab1 || !out || nq <= 0) return fail(GRMP_EINVAL, "grmp_blf_create: bad argument");
   if (s1->grid != s2->grid) return fail(GRMP_EINVAL, "spaces live on different grids");
   if (apt < 0 || apt > 2) return fail(GRMP_EINVAL, "unknown assembly pattern type");
-  if (action != GRMP_ACT_NONE && !act_params) return fail(GRMP_EINVAL, "action parameters missing");
+  if (action < GRMP_ACT_NONE || action > GRMP_ACT_CONVECTION) return fail(GRMP_EINVAL, "unknown action");
+  if ((action == GRMP_ACT_HOOKE2D || action == GRMP_ACT_HOOKE3D) && !act_params) return fail(GRMP_EINVAL, "action parameters missing");
+  if (action == GRMP_ACT_CONVECTION && apt != GRMP_APT_BILINEARFORM) return fail(GRMP_EINVAL, "the convection form is a general BilinearForm");
   grmp_blf* b = new grmp_blf();
   cudaStream_t st = s1->grid->ctx->stream;
   b->s1 = s1; b->s2 = s2; b->op1 = op1; b->op2 = op2; b->action = action; b->apt = apt; b->transposed = transposed_assembly ? 1 : 0;
@@ -371,6 +378,12 @@ int grmp_blf_create(grmp_space* s1, grmp_space* s2, int op1, int op2, int action
     if (!rc && t2->refvals) b->t2_vals_host.assign(t2->refvals, t2->refvals + (size_t)nq * t2->nd_all * t2->ncomp);
   }
   BlfLocalParams p;
+  if (!rc && action == GRMP_ACT_CONVECTION) {   // validated when the fixed argument arrives
+    if (cudaStreamSynchronize(st) != cudaSuccess) rc = fail(GRMP_ECUDA, "upload failed");
+    if (rc) { delete b; return rc; }
+    *out = b;
+    return GRMP_OK;
+  }
   if (!rc) rc = fill_blf_params(b, 1.0, &p);   // validates the combination
   if (!rc) {
     const int ar = (action == GRMP_ACT_NONE) ? p.e1.rd : (action == GRMP_ACT_HOOKE2D ? 3 : 6);
@@ -385,6 +398,42 @@ int grmp_blf_create(grmp_space* s1, grmp_space* s2, int op1, int op2, int action
 }
 
 int grmp_blf_destroy(grmp_blf* b) { delete b; return GRMP_OK; }
+
+int grmp_blf_set_fixed_argument(grmp_blf* b, grmp_space* sa, int op_a, const grmp_evaltab* tab_a, const double* coeffs_host, int keep_pattern) {
+  if (!b || !sa || !tab_a || !coeffs_host) return fail(GRMP_EINVAL, "grmp_blf_set_fixed_argument: NULL argument");
+  if (b->action != GRMP_ACT_CONVECTION) return fail(GRMP_EINVAL, "the form was not created with GRMP_ACT_CONVECTION");
+  if (sa->grid != b->s1->grid) return fail(GRMP_EINVAL, "spaces live on different grids");
+  grmp_ctx* ctx = sa->grid->ctx;
+  cudaStream_t s = ctx->stream;
+  GRMP_CUDA(cudaSetDevice(ctx->device));
+  if (b->sa != sa || b->opa != op_a || (!b->ta.refvals.p && !b->ta.refderivs.p)) {
+    GRMP_TRY(upload_tables(tab_a, b->nq, sa->grid->dim, s, &b->ta));
+    b->sa = sa; b->opa = op_a;
+  }
+  // a(x_q) = operator evaluation of the coefficient function at the quadrature points of every cell
+  IiLocalParams ip{};
+  ip.g = sa->grid->view();
+  GRMP_TRY(make_evalview(sa, op_a, b->ta, &ip.e));
+  EvalView e1;
+  GRMP_TRY(make_evalview(b->s1, b->op1, b->t1, &e1));
+  EvalView e2 = e1;
+  if (!b->same_eval) GRMP_TRY(make_evalview(b->s2, b->op2, b->t2, &e2));
+  if (ip.e.rd < 1 || e1.rd % ip.e.rd || e1.rd / ip.e.rd != e2.rd)
+    return fail(GRMP_EINVAL, "convection: operator lengths do not fit (ansatz = ncomponents x xdim, coefficient = xdim, test = ncomponents)");
+  const i64 ncells = sa->grid->ncells;
+  b->aq_rd = ip.e.rd;
+  ip.reg.n = 0; ip.nq = b->nq; ip.w = b->w.p; ip.kind = GRMP_II_NONE; ip.ardim = ip.e.rd; ip.factor = 1.0;
+  GRMP_TRY(b->acoeffs.upload(coeffs_host, (size_t)sa->ndofs, s));
+  const size_t nt = (size_t)std::max<i64>(ncells * b->nq * ip.e.rd, 1);
+  if (b->aq.n < nt) GRMP_TRY(b->aq.alloc(nt));
+  if (b->aq_scratch.n < (size_t)std::max<i64>(ncells * ip.e.rd, 1)) GRMP_TRY(b->aq_scratch.alloc((size_t)std::max<i64>(ncells * ip.e.rd, 1)));
+  ip.coeffs = b->acoeffs.p; ip.data = nullptr; ip.b = nullptr; ip.itemval = b->aq_scratch.p; ip.qtable = b->aq.p;
+  GRMP_TRY(launch_ii_local(ip, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  if (!keep_pattern) b->have_pattern = false;
+  b->have_values = false;
+  return GRMP_OK;
+}
 
 int grmp_blf_set_path(grmp_blf* b, int path) {
   if (!b || path < 0 || path > GRMP_PATH_COLOURED) return fail(GRMP_EINVAL, "grmp_blf_set_path: bad argument");
@@ -456,6 +505,10 @@ int grmp_blf_symbolic(grmp_blf* b, double factor, int64_t* nnz_out) {
     i64 cpv = 0;
     GRMP_CUDA(cudaMemcpy(&cpv, b->pat.colptr.p + b->ncols_owned, 8, cudaMemcpyDeviceToHost));
     b->halo_first_slot = cpv - 1;
+    if (b->halo_first_slot < b->pat.nnz) {
+      GRMP_CUDA(cudaMemsetAsync(b->nzval.p + b->halo_first_slot, 0, (size_t)(b->pat.nnz - b->halo_first_slot) * 8, s));
+      GRMP_CUDA(cudaStreamSynchronize(s));
+    }
   }
   if (nnz_out) *nnz_out = b->pat.nnz;
   return GRMP_OK;

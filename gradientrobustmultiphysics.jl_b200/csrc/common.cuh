@@ -152,6 +152,8 @@ struct BlfLocalParams {
   int nq;
   const double* w;     // [nq]
   double factor;
+  const double* aq;    // GRMP_ACT_CONVECTION: a(x_q) of the fixed argument, [ncells][nq][aq_rd]
+  int aq_rd;
   i64 nrows_key;       // key = col * nrows_key + row (0-based, output orientation)
   // outputs (exactly one of them non-null)
   u64* keys;           // [ncells*nd1*nd2] : symbolic pass, ~0 for masked-out contributions
@@ -187,6 +189,7 @@ struct IiLocalParams {
   const double* data;    // device, [ncells][nq][rd] (L2ERROR)
   double* b;             // device, [ncells][ardim], updated in place (b[j,item] += ...), or null
   double* itemval;       // device, [ardim][ncells]: the item's own sum (0 for filtered cells), for the total
+  double* qtable;        // device, [ncells][nq][rd] or null: the operator evaluation itself (fixed arguments of trilinear forms)
 };
 int launch_ii_local(const IiLocalParams& p, cudaStream_t s);
 

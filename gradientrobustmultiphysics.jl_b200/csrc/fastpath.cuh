@@ -24,6 +24,7 @@ struct FastP2Tet {
   DevBuf<uint4> vrec;             // per vertex column: diagonal slot, first slot, #slots
   DevBuf<int> tile_counter;       // dynamic tile scheduler of the edge kernel
   i64 nvcols = 0;
+  i64 halo_first = -1;            // first nzval slot of the columns another rank owns (>= nnz: none): never written by the kernels
   DevBuf<unsigned long long> prof; // GRMP_FAST_PROF: cycle counters of the last launch (8 per CTA)
   int grid = 0;                   // CTAs of the last edge-kernel launch
 };

@@ -132,6 +132,7 @@ struct PackParams {
   i64 npairs, ncols;
   unsigned char* blob;
   u32* end_slots;           // [npairs] or null
+  u32 halo_first;           // mirrors into columns another rank owns (slots >= halo_first) are dropped
   u32* mkey;                // mirror candidates: destination slot (NONE = not in the pattern / no value)
   u32* mval;                //                    source word inside the blob
 };
@@ -150,7 +151,9 @@ __device__ __forceinline__ i64 find_slot(const PackParams& p, i64 row0, i64 col0
 __device__ __forceinline__ u32 off8(i64 o) { return (o < 0 || o > 254) ? 255u : (u32)o; }
 __device__ __forceinline__ u32 gslot(const PackParams& p, i64 row0, i64 col0) {
   i64 o = find_slot(p, row0, col0);
-  return o < 0 ? NONE : (u32)(p.colptr[col0] - 1 + o);
+  if (o < 0) return NONE;
+  const u32 g = (u32)(p.colptr[col0] - 1 + o);
+  return g >= p.halo_first ? NONE : g;     // halo columns are not assembled on this rank
 }
 
 __global__ void pack_pairs(PackParams p) {
@@ -278,6 +281,7 @@ struct EdgeParams {
   const u32* end_slots;     // [npairs] or null (only partitions have multi-chain columns)
   double factor;
   double* nzval;
+  i64 halo_first;           // first slot of the halo columns: group ranges are stored up to here only
   int* tile_counter;        // dynamic tile scheduler: next unclaimed tile (zero at launch; reset by the diagonal kernel)
   int ntiles;
   u32 in_stride;            // bytes of one input buffer (largest blob)
@@ -461,7 +465,8 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
     const int col = (int)gr0.x + lane;                      // tile-local column of this lane
     const bool has_col = col < (int)gr1.x && !(p.dbg & 4);
     const i64 g0 = ((i64)(u32)h1.x | ((i64)h1.y << 32)) + gr0.y;   // first nzval slot of the group
-    const int nnz_w = (int)(gr1.y - gr0.y);
+    // halo columns (a suffix of the slot range) are walked for their mirrors only: nothing of them is stored
+    const int nnz_w = (int)max((i64)0, min((i64)(gr1.y - gr0.y), p.halo_first - g0));
     const u32 cols_off = (u32)h2.w, pairs_off = off_pairs(cols_off, (u32)h0.y), xyz_off = off_xyz(cols_off, (u32)h0.y, (u32)h0.w);
     const double* __restrict__ X = reinterpret_cast<const double*>(in + xyz_off);
     // stage[i] mirrors nzval[g0 + i]; it is shifted by one element when g0 is odd so that shared and global addresses of the
@@ -917,9 +922,9 @@ __global__ void tile_offsets(TileHdr* hdr, int ntiles, const i64* blob16_scan, u
   tile_dir[t] = make_uint2((u32)blob16_scan[t], hdr[t].blob_bytes);
   atomicMax(maxblob, (int)hdr[t].blob_bytes);
 }
-__global__ void flag_vertex_columns(const unsigned char* col_closed, const i64* pairbeg, i64 ncols, unsigned char* isv) {
+__global__ void flag_vertex_columns(const unsigned char* col_closed, const i64* pairbeg, i64 ncols, i64 ncols_owned, unsigned char* isv) {
   const i64 j = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  if (j < ncols) isv[j] = (col_closed[j] == CK_VERTEX && pairbeg[j + 1] > pairbeg[j]) ? 1 : 0;
+  if (j < ncols) isv[j] = (j < ncols_owned && col_closed[j] == CK_VERTEX && pairbeg[j + 1] > pairbeg[j]) ? 1 : 0;
 }
 
 // closed-form local stiffness of the unit reference tetrahedron, used to verify that the
@@ -1147,7 +1152,7 @@ static int fast_p2tet_build_device(grmp_ctx* ctx, const BlfLocalParams& p, const
   if (any_end) GRMP_TRY(out->end_slots.alloc(np1));
   PackParams pp{d_cell.p, d_io.p, d_code.p, dg.segptr.p, pat.colptr.p, pat.rowval.p, p.e1.celldofs, d_colof.p, d_closed.p,
                 d_coltile.p, d_colpq.p, d_abase.p, d_colgroup.p, d_colgcount.p, reinterpret_cast<const TileHdr*>(d_hdr.p), d_mirbase.p, npairs, ncols,
-                out->blob.p, out->end_slots.p, d_mkey.p, d_mval.p};
+                out->blob.p, out->end_slots.p, (u32)std::min<i64>(out->halo_first, (i64)NONE), d_mkey.p, d_mval.p};
   if (npairs && ntiles) pack_pairs<<<(unsigned)((npairs + 255) / 256), 256, 0, s>>>(pp);
   if (ncols && ntiles) pack_cols<<<(unsigned)((ncols + 255) / 256), 256, 0, s>>>(pp);
   GRMP_CUDA(cudaGetLastError());
@@ -1170,7 +1175,7 @@ static int fast_p2tet_build_device(grmp_ctx* ctx, const BlfLocalParams& p, const
     DevBuf<unsigned char> d_isv;
     DevBuf<i64> d_nsel;
     GRMP_TRY(d_isv.alloc(nc1)); GRMP_TRY(d_nsel.alloc(1)); GRMP_TRY(out->vcols.alloc(nc1));
-    if (ncols) flag_vertex_columns<<<(unsigned)((ncols + 255) / 256), 256, 0, s>>>(d_closed.p, dg.segptr.p, ncols, d_isv.p);
+    if (ncols) flag_vertex_columns<<<(unsigned)((ncols + 255) / 256), 256, 0, s>>>(d_closed.p, dg.segptr.p, ncols, ncols_owned_eff, d_isv.p);
     GRMP_CUDA(cudaMemsetAsync(d_nsel.p, 0, 8, s));
     if (ncols) {
       cub::CountingInputIterator<u32> it(0);
@@ -1214,6 +1219,13 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   const i64 ncells = p.g.ncells, ncols = pat.ncols, nnodes = p.g.nnodes;
   const i64 ncols_owned_eff = (ncols_owned >= 0 && ncols_owned < ncols) ? ncols_owned : ncols;
   out->ntiles = 0; out->nvcols = 0;
+  out->halo_first = pat.nnz;
+  if (ncols_owned_eff < ncols) {
+    i64 cpv = 0;
+    GRMP_CUDA(cudaMemcpyAsync(&cpv, pat.colptr.p + ncols_owned_eff, 8, cudaMemcpyDeviceToHost, s));
+    GRMP_CUDA(cudaStreamSynchronize(s));
+    out->halo_first = cpv - 1;
+  }
   if (pat.nnz >= (i64)NONE) return fail(GRMP_EUNSUPPORTED, "fast path: more than 2^32-1 non-zeros on one device");
   // (0) the caller's tables must be the standard P2 basis integrated exactly
   {
@@ -1418,7 +1430,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     if (ke == kb) { close_tile(j); continue; }
     if (col_closed[j] == 2) {   // vertex column
       close_tile(j);
-      vcols.push_back((u32)j);
+      if (j < ncols_owned_eff) vcols.push_back((u32)j);
       continue;
     }
     const int n = (int)(ke - kb);
@@ -1506,7 +1518,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   if (any_end) GRMP_TRY(out->end_slots.alloc(std::max<i64>(npairs, 1)));
   PackParams pp{d_cell.p, d_io.p, d_code.p, dg.segptr.p, pat.colptr.p, pat.rowval.p, p.e1.celldofs, d_colof.p, d_closed.p,
                 d_coltile.p, d_colpq.p, d_abase.p, d_colgroup.p, d_colgcount.p, reinterpret_cast<const TileHdr*>(d_hdr.p), d_mirbase.p, npairs, ncols,
-                out->blob.p, out->end_slots.p, d_mkey.p, d_mval.p};
+                out->blob.p, out->end_slots.p, (u32)std::min<i64>(out->halo_first, (i64)NONE), d_mkey.p, d_mval.p};
   lap("pair arrays upload");
   if (npairs) pack_pairs<<<(unsigned)((npairs + 255) / 256), 256, 0, s>>>(pp);
   if (ncols) pack_cols<<<(unsigned)((ncols + 255) / 256), 256, 0, s>>>(pp);
@@ -1557,7 +1569,7 @@ int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pa
     f.geom_version = geom_version;
   }
   if (f.ntiles > 0) {
-    EdgeParams ep{f.tile_dir.p, f.blob.p, f.end_slots.p, p.factor, nzval, f.tile_counter.p, f.ntiles, f.in_stride, f.slot_elems, f.nbuf, f.prof.p, dbg};
+    EdgeParams ep{f.tile_dir.p, f.blob.p, f.end_slots.p, p.factor, nzval, f.halo_first, f.tile_counter.p, f.ntiles, f.in_stride, f.slot_elems, f.nbuf, f.prof.p, dbg};
     switch (f.nw) {
       case 3: GRMP_TRY(launch_edge<3>(ep, f, ctx->sm_count, ctx->stream)); break;
       case 4: GRMP_TRY(launch_edge<4>(ep, f, ctx->sm_count, ctx->stream)); break;

@@ -328,6 +328,13 @@ __global__ void __launch_bounds__(128) blf_local_kernel(const BlfLocalParams p) 
       double ar[RDMAX];
       if (p.action == GRMP_ACT_NONE) {
         for (int k = 0; k < rdim; k++) ar[k] = cv1[k][di];
+      } else if (p.action == GRMP_ACT_CONVECTION) {   // pdeoperators.jl:459-467 on [a(x_i), operator evaluation of dof di]
+        const double* a = p.aq + ((size_t)cell * p.nq + i) * p.aq_rd;
+        for (int j = 0; j < rdim; j++) {
+          double r = 0.0;
+          for (int k = 0; k < p.aq_rd; k++) r += a[k] * cv1[j * p.aq_rd + k][di];
+          ar[j] = r;
+        }
       } else {
         double in[RDMAX];
         for (int k = 0; k < p.e1.rd; k++) in[k] = cv1[k][di];
@@ -422,6 +429,8 @@ __global__ void __launch_bounds__(128) ii_local_kernel(const IiLocalParams p) {
   const i64 ncells = p.g.ncells;
   if (!cell_active(p.g, p.reg, cell)) {
     for (int j = 0; j < ardim; j++) p.itemval[(i64)j * ncells + cell] = 0.0;
+    if (p.qtable)
+      for (int k = 0; k < p.nq * rdim; k++) p.qtable[(size_t)cell * p.nq * rdim + k] = 0.0;
     return;
   }
   Geo T;
@@ -448,6 +457,8 @@ __global__ void __launch_bounds__(128) ii_local_kernel(const IiLocalParams p) {
     for (int k = 0; k < rdim; k++) in[k] = 0.0;
     for (int d = 0; d < nd; d++)
       for (int k = 0; k < rdim; k++) in[k] += c[d] * cv[k][d] * 1.0;
+    if (p.qtable)
+      for (int k = 0; k < rdim; k++) p.qtable[((size_t)cell * p.nq + i) * rdim + k] = in[k];
     if (p.kind == GRMP_II_NONE) {
       for (int j = 0; j < rdim; j++) res[j] = in[j];
     } else if (p.kind == GRMP_II_L2NORM) {

@@ -41,7 +41,8 @@ enum { GRMP_FE_H1P1 = 1, GRMP_FE_H1P2 = 2, GRMP_FE_H1BR = 3, GRMP_FE_HDIVRT0 = 4
 /* function operators (src/functionoperators.jl:13-153) */
 enum { GRMP_OP_ID = 1, GRMP_OP_GRAD = 2, GRMP_OP_SYMGRAD = 3, GRMP_OP_DIV = 4, GRMP_OP_RECON_ID_RT0 = 5, GRMP_OP_RECON_ID_BDM1 = 6 };
 /* actions evaluated on the device (src/actions.jl:96-110 NoAction; src/pdeoperators.jl:265-270, 304-312 Hooke tensors) */
-enum { GRMP_ACT_NONE = 0, GRMP_ACT_HOOKE2D = 1, GRMP_ACT_HOOKE3D = 2 };
+enum { GRMP_ACT_NONE = 0, GRMP_ACT_HOOKE2D = 1, GRMP_ACT_HOOKE3D = 2,
+       GRMP_ACT_CONVECTION = 3 /* needs a fixed argument, see grmp_blf_set_fixed_argument */ };
 /* assembly pattern types (src/assemblypatterns/bilinearform.jl:7-21) */
 enum { GRMP_APT_BILINEARFORM = 0, GRMP_APT_SYMMETRIC = 1, GRMP_APT_LUMPED = 2 };
 /* right-hand side data of a LinearForm (fdot_action, src/actions.jl:119-128) */
@@ -137,6 +138,16 @@ int grmp_blf_destroy(grmp_blf* blf);
 /* choose the numeric back end before grmp_blf_symbolic (default GRMP_PATH_AUTO: the fast
  * owner-computes kernel where one exists for the form, else the generic two-phase path) */
 int grmp_blf_set_path(grmp_blf* blf, int path);
+
+/* Trilinear forms: assemble!(A, AP, FEB; fixed_arguments = [1]) with three FESpaces (src/assemblypatterns/bilinearform.jl:235-257): the
+ * operator evaluation of the coefficient argument FEB[1] at every quadrature point is the first part of the action input.  On the device:
+ * the Picard-linearised convection term of ConvectionOperator(a_from, a_operator, xdim, ncomponents; a_to = 1) (src/pdeoperators.jl:435-510),
+ * action GRMP_ACT_CONVECTION: result[j] = sum_k a(x_q)[k] * (ansatz operator evaluation)[(j-1) xdim + k], i.e. ((a . grad) u, v).
+ * space_a / op_a / tab_a describe FEB[1].FES and its operator, coeffs_host its entries (ndofs of space_a).  The table a(x_q) is evaluated on
+ * the device in the reference's order (eval_febe!, feevaluator.jl:445-452).  The reference's pattern depends on the values: call
+ * grmp_blf_symbolic afterwards, or pass keep_pattern = 1 to reassemble on the frozen pattern (the next Picard iteration). */
+int grmp_blf_set_fixed_argument(grmp_blf* blf, grmp_space* space_a, int op_a, const grmp_evaltab* tab_a, const double* coeffs_host,
+                                int keep_pattern);
 
 /* One-time symbolic pass on the GPU = what rawupdateindex! + flush! build on first
  * assembly (fematrix.jl:54-58, pdeoperators.jl:992): the pattern is the union of local

@@ -62,7 +62,7 @@ inline Dual operator/(const Dual& a, double b) { Dual r; r.v = a.v / b; for (int
 // -------------------------------------------------------------------------------------
 enum FEType { H1P1 = 1, H1P2 = 2, H1BR = 3, HDIVRT0 = 4, HDIVBDM1 = 5, L2P0 = 6 };
 enum Op { OP_ID = 1, OP_GRAD = 2, OP_SYMGRAD = 3, OP_DIV = 4, OP_RECON_ID_RT0 = 5, OP_RECON_ID_BDM1 = 6 };
-enum Action { ACT_NONE = 0, ACT_HOOKE2D = 1, ACT_HOOKE3D = 2 };
+enum Action { ACT_NONE = 0, ACT_HOOKE2D = 1, ACT_HOOKE3D = 2, ACT_CONVECTION = 3 };
 enum APT { APT_GENERAL = 0, APT_SYMMETRIC = 1, APT_LUMPED = 2 };
 enum FSrc { F_NONE = 0, F_CONST = 1, F_QP_TABLE = 2 };
 enum IIKind { II_NONE = 0, II_L2NORM = 1, II_L2ERROR = 2 };
@@ -811,6 +811,16 @@ void orc_matrix_get(void* A, i64* colptr, i64* rowval, double* nzval) {
   for (size_t k = 0; k < a->rowval.size(); k++) { rowval[k] = a->rowval[k] + 1; nzval[k] = a->nzval[k]; }
 }
 
+// ---- fixed (coefficient) argument of a trilinear form: assemble!(A, AP, FEB; fixed_arguments = [1]) with nFE = 3
+// (bilinearform.jl:235-257: the operator evaluation of FEB[1] at every quadrature point is the first part of the action input).
+// Set before orc_blf_assemble, cleared with sa = NULL.  Used with ACT_CONVECTION, the kernel of ConvectionOperator(a_from, a_operator,
+// xdim, ncomponents; a_to = 1) (pdeoperators.jl:435-510): result[j] = sum_k input[k] * input[xdim + (j-1) xdim + k].
+static orc_space g_fixed_space; static bool g_fixed_on = false; static int g_fixed_op = 0; static const double* g_fixed_coeffs = nullptr;
+void orc_set_fixed_argument(const orc_space* sa, int op_a, const double* coeffs) {
+  g_fixed_on = sa != nullptr;
+  if (sa) { g_fixed_space = *sa; g_fixed_op = op_a; g_fixed_coeffs = coeffs; }
+}
+
 // ---- BilinearForm assemble! (src/assemblypatterns/bilinearform.jl:92-380) ------------
 // apply_action_to == [1] (all operators on the path, pdeoperators.jl:164,188,222,272)
 int orc_blf_assemble(void* Aptr, const orc_grid* og, const orc_space* os1, const orc_space* os2, int op1, int op2,
@@ -822,17 +832,28 @@ int orc_blf_assemble(void* Aptr, const orc_grid* og, const orc_space* os1, const
   int edim = g.dim;
   // prepare_assembly! : quadrature order (assemblypatterns.jl:559-565)
   int quadorder = bonus_quadorder + polyorder_of(s1, edim) + quadorder_shift(op1) + polyorder_of(s2, edim) + quadorder_shift(op2);
+  Space sa{}; Evaluator ea;
+  if (g_fixed_on) { sa = to_space(&g_fixed_space); quadorder += polyorder_of(sa, edim) + quadorder_shift(g_fixed_op); }   // all FE of the pattern, 559-565
   if (quadorder < 0) quadorder = 0;
   QRule q; if (!make_qrule(edim, quadorder, q)) return -1;
   Evaluator e1, e2store; Evaluator* e2 = &e2store;
   if (!e1.init(&g, s1, op1, q)) return -1;
+  if (g_fixed_on && !ea.init(&g, sa, g_fixed_op, q)) return -1;
+  if ((action == ACT_CONVECTION) != g_fixed_on) { g_err = "ACT_CONVECTION needs a fixed argument (and vice versa)"; return -1; }
   bool same = (s1.celldofs == s2.celldofs && s1.fe == s2.fe && s1.ncomp == s2.ncomp && op1 == op2);  // evaluator reuse 567-584
   if (same) e2 = &e1; else if (!e2store.init(&g, s2, op2, q)) return -1;
   int nd1 = e1.nd, nd2 = e2->nd, nq = q.n();
   int rdim_action;   // action_resultdim
   int in_dim = e1.resultdim;
+  const int adim = g_fixed_on ? ea.resultdim : 0;      // offsets[nFE-1] = basisdim of the fixed argument (150-152)
   if (action == ACT_NONE) rdim_action = e1.resultdim;
+  else if (action == ACT_CONVECTION) {
+    if (adim < 1 || in_dim % adim) { g_err = "convection: ansatz operator length is not a multiple of the coefficient length"; return -1; }
+    rdim_action = in_dim / adim;
+  }
   else { rdim_action = (action == ACT_HOOKE2D) ? 3 : 6; if (in_dim != rdim_action) { g_err = "action/operator size mismatch"; return -1; } }
+  std::vector<double> aq((size_t)std::max(adim, 1) * q.n(), 0.0), ca(g_fixed_on ? ea.nd : 0);
+  if (g_fixed_on && g_magnitude_mode) { g_err = "magnitude mode: no fixed arguments"; return -1; }
   if (rdim_action != e2->resultdim) { g_err = "operator result dimensions do not match"; return -1; }
   std::vector<double> local((size_t)nd1 * nd2, 0.0), action_result(rdim_action), action_input(in_dim);
   const bool mag = g_magnitude_mode;
@@ -843,11 +864,28 @@ int orc_blf_assemble(void* Aptr, const orc_grid* og, const orc_space* os1, const
   for (i64 item = 0; item < g.ncells; item++) {
     if (!in_regions(g, item, regions, nregions)) continue;
     e1.update(item); if (e2 != &e1) e2->update(item);       // update_assembly! (assemblypatterns.jl:251-276)
+    if (g_fixed_on) {                                       // 235-257: FEB[1] evaluated at the quadrature points, eval_febe! from 0 in dof order
+      ea.update(item);
+      const i32* da = sa.celldofs + item * ea.nd;
+      for (int d = 0; d < ea.nd; d++) ca[d] = g_fixed_coeffs[da[d] - 1] * 1.0;
+      std::fill(aq.begin(), aq.end(), 0.0);
+      for (int i = 0; i < nq; i++)
+        for (int d = 0; d < ea.nd; d++)
+          for (int k = 0; k < adim; k++) aq[(size_t)i * adim + k] += ca[d] * ea.cv(k, d, i) * 1;
+    }
     const bool locsym = is_symmetric;                       // dofitems[1] == dofitems[2] for continuous operators
     for (int i = 0; i < nq; i++) {
       for (int di = 0; di < nd1; di++) {
         if (action == ACT_NONE) {                           // 306-308
           for (int k = 0; k < rdim_action; k++) action_result[k] = e1.cv(k, di, i) * 1.0 * 1.0;
+        } else if (action == ACT_CONVECTION) {              // 310-313 with the input [a(x_i), operator evaluation of dof di]
+          for (int k = 0; k < in_dim; k++) action_input[k] = e1.cv(k, di, i) * 1.0 * 1.0;
+          const double* a = &aq[(size_t)i * adim];
+          for (int j = 0; j < rdim_action; j++) {           // pdeoperators.jl:459-467
+            double r = 0;
+            for (int k = 0; k < adim; k++) r += a[k] * action_input[(size_t)j * adim + k];
+            action_result[j] = r;
+          }
         } else {                                            // 310-313
           for (int k = 0; k < in_dim; k++) action_input[k] = e1.cv(k, di, i) * 1.0 * 1.0;
           apply_action(action, act_params, action_input.data(), action_result.data());

@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 OP_ID, OP_GRAD, OP_SYMGRAD, OP_DIV, OP_RECON_ID_RT0, OP_RECON_ID_BDM1 = 1, 2, 3, 4, 5, 6
-ACT_NONE, ACT_HOOKE2D, ACT_HOOKE3D = 0, 1, 2
+ACT_NONE, ACT_HOOKE2D, ACT_HOOKE3D, ACT_CONVECTION = 0, 1, 2, 3
 APT_GENERAL, APT_SYMMETRIC, APT_LUMPED = 0, 1, 2
 F_NONE, F_CONST, F_QP_TABLE = 0, 1, 2
 II_NONE, II_L2NORM, II_L2ERROR = 0, 1, 2
@@ -63,6 +63,7 @@ def lib():
                                          C.c_void_p, C.c_int, C.c_double, C.c_int64, C.c_int, C.c_void_p]
         _LIB.orc_ii_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_Grid), C.POINTER(_Space), C.c_int, C.c_int, C.c_void_p,
                                          C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        _LIB.orc_set_fixed_argument.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _LIB.orc_quadpoints.argtypes = [C.POINTER(_Grid), C.c_int, C.c_void_p]
         _LIB.orc_qrule.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _LIB.orc_reftables.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -150,17 +151,27 @@ class OracleMatrix:
 
 def blf_assemble(A: OracleMatrix, grid, space1, space2, op1, op2, *, action=ACT_NONE, act_params=None, apt=APT_GENERAL,
                  regions=(0,), factor=1.0, transposed_assembly=False, transpose_copy: OracleMatrix | None = None,
-                 factor_transpose=None, offsetX=0, offsetY=0, bonus_quadorder=0):
-    """assemble!(A, AP; factor, transposed_assembly, transpose_copy, offsetX, offsetY) -- bilinearform.jl:92-380"""
-    g = _grid_struct(grid, _needs_faces(space1, space2))
+                 factor_transpose=None, offsetX=0, offsetY=0, bonus_quadorder=0, fixed=None):
+    """assemble!(A, AP; factor, transposed_assembly, transpose_copy, offsetX, offsetY) -- bilinearform.jl:92-380.
+    fixed = (space_a, op_a, coefficients): assemble!(A, AP, FEB; fixed_arguments = [1]) of a trilinear form (235-257), used with
+    action = ACT_CONVECTION"""
+    g = _grid_struct(grid, _needs_faces(space1, space2) or (fixed is not None and _needs_faces(fixed[0])))
     s1 = _space_struct(space1)
     s2 = s1 if space2 is space1 else _space_struct(space2)
     ap = None if act_params is None else np.ascontiguousarray(act_params, dtype=np.float64)
     rg = np.ascontiguousarray(regions, dtype=np.int32)
     ft = factor if factor_transpose is None else factor_transpose
-    _check(lib().orc_blf_assemble(A.h, C.byref(g.s), C.byref(s1.s), C.byref(s2.s), op1, op2, action, _p(ap), apt, _p(rg), rg.size,
-                                  float(factor), int(transposed_assembly), transpose_copy.h if transpose_copy else None,
-                                  float(ft), offsetX, offsetY, bonus_quadorder))
+    if fixed is not None:
+        sa = _space_struct(fixed[0])
+        ca = np.ascontiguousarray(fixed[2], dtype=np.float64)
+        lib().orc_set_fixed_argument(C.byref(sa.s), int(fixed[1]), _p(ca))
+    try:
+        _check(lib().orc_blf_assemble(A.h, C.byref(g.s), C.byref(s1.s), C.byref(s2.s), op1, op2, action, _p(ap), apt, _p(rg), rg.size,
+                                      float(factor), int(transposed_assembly), transpose_copy.h if transpose_copy else None,
+                                      float(ft), offsetX, offsetY, bonus_quadorder))
+    finally:
+        if fixed is not None:
+            lib().orc_set_fixed_argument(None, 0, None)
 
 
 def set_magnitude_mode(on: bool):
