@@ -134,6 +134,18 @@ class DataFunction:
             self.dependencies = ""
 
 
+class ConvectionAction:
+    """kernel of ConvectionOperator(a_from, a_operator, xdim, ncomponents; a_to = 1) (pdeoperators.jl:459-468):
+    result[j] = sum_k input[k] * input[xdim + (j-1) xdim + k], input = [a(x), ansatz operator evaluation]; evaluated on the device
+    (GRMP_ACT_CONVECTION) with the coefficient function a as the fixed argument of a trilinear form"""
+    code = 3
+    params = None
+
+    def __init__(self, xdim, ncomponents, bonus_quadorder=0, name="convection"):
+        self.xdim, self.ncomponents, self.bonus_quadorder, self.name = xdim, ncomponents, bonus_quadorder, name
+        self.argsizes = [ncomponents, xdim + ncomponents * xdim]
+
+
 class _FDotAction:
     """fdot_action(data) (actions.jl:119-128)"""
     code = 0
@@ -208,13 +220,22 @@ class AssemblyPattern:
         self.action, self.apply_action_to, self.regions = action, apply_action_to, list(regions)
         self.last_allocations = 0
         self.AM = None                      # prepared state (quadrature, tables, device handle)
+        self.fixed = None                   # (FESpace, operator) of the coefficient argument of a trilinear form (FES[1] of nFE = 3)
 
     def __repr__(self):
         return f"AssemblyPattern({self.name}, {self.FES}, {self.operators})"
 
 
 def DiscreteBilinearForm(operators, FES, action=None, name="BLF", regions=(0,), apply_action_to=(1,)):
-    assert len(operators) == len(FES) == 2, "each FESpace needs an operator and vice versa"
+    assert len(operators) == len(FES), "each FESpace needs an operator and vice versa"
+    if len(FES) == 3:
+        # trilinear form with one coefficient argument: FES = [FES_a, FES_ansatz, FES_test] (bilinearform.jl:60-64, 235-257)
+        if not isinstance(action, ConvectionAction):
+            raise NotImplementedError("trilinear forms: the convection kernel runs on the device; other actions are user closures")
+        AP = AssemblyPattern(APT_BilinearForm, name, FES[1:], operators[1:], action, [1], regions)
+        AP.fixed = (FES[0], _op(operators[0]))
+        return AP
+    assert len(FES) == 2, "bilinear forms take two FESpaces (+ one coefficient argument)"
     assert list(apply_action_to) == [1], "the ported path applies the action to argument 1 (all operators on the path do)"
     return AssemblyPattern(APT_BilinearForm, name, FES, operators, action or NoAction(), [1], regions)
 
@@ -267,6 +288,8 @@ def quadrature_order(AP: AssemblyPattern):
     q = AP.action.bonus_quadorder
     for F, o in zip(AP.FES, AP.operators):
         q += F.fetype.polynomialorder(edim) - o.needed_derivative
+    if getattr(AP, "fixed", None) is not None:          # every FESpace of the pattern counts, coefficient arguments included
+        q += AP.fixed[0].fetype.polynomialorder(edim) - AP.fixed[1].needed_derivative
     return max(q, 0)
 
 
@@ -303,8 +326,11 @@ def prepare_assembly(AP: AssemblyPattern, transposed_assembly=False):
         t2, k2 = _tables(AP.FES[1], AP.operators[1], P.qf)
         P.keep += [k1, k2]
         act = AP.action
-        if not isinstance(act, (NoAction, HookeAction)):
-            raise NotImplementedError("bilinear forms support NoAction and the Hooke tensor actions on the device")
+        if not isinstance(act, (NoAction, HookeAction, ConvectionAction)):
+            raise NotImplementedError("bilinear forms support NoAction, the Hooke tensor actions and the convection kernel on the device")
+        if isinstance(act, ConvectionAction):
+            P.fixed_tab, kf = _tables(AP.fixed[0], AP.fixed[1], P.qf)
+            P.keep.append(kf)
         _lib.check(L.grmp_blf_create(s1, s2, AP.operators[0].code, AP.operators[1].code, act.code, _lib.ptr(act.params), AP.APT,
                                      int(bool(transposed_assembly)), _lib.ptr(regions), regions.size, len(P.qf), _lib.ptr(w), C.byref(t1), C.byref(t2), C.byref(h)))
         P.kind = "blf"
@@ -405,8 +431,18 @@ def _embed(block: FEMatrixBlock, colptr, rowval, nzval):
 def assemble(target, AP: AssemblyPattern, FEB=(), factor=1, factor_transpose=None, transposed_assembly=False, transpose_copy=None,
              skip_preps=False, fixed_arguments=None, offset=0, fdata=None):
     """assemble!(A::FEMatrixBlock, AP; ...) / assemble!(b::FEVectorBlock | Vector, AP; ...)"""
-    if len(FEB) != 0:
-        raise NotImplementedError("assembly with FEB coefficient arguments is a 'next' row (SURVEY.md 8f N4)")
+    if len(FEB) != 0 and not (AP.fixed is not None and len(FEB) == 1 and AP.APT == APT_BilinearForm):
+        raise NotImplementedError("FEB coefficient arguments: one fixed argument of a trilinear convection form is on the device "
+                                  "(SURVEY.md 8f N4); anything else stays with the reference")
+    if AP.fixed is not None:
+        assert len(FEB) == 1 and FEB[0].FES is AP.fixed[0], "trilinear form: FEB = [block of the coefficient function]"
+        tr = bool(transposed_assembly)
+        if AP.AM is None or AP.AM.kind != "blf" or AP.AM.transposed != tr:
+            prepare_assembly(AP, tr)
+        blk = FEB[0]
+        coeffs = np.ascontiguousarray(blk.entries[blk.offset:blk.offset + blk.FES.ndofs])
+        _lib.check(_lib.lib().grmp_blf_set_fixed_argument(AP.AM.h, device_space(AP.fixed[0]), AP.fixed[1].code, C.byref(AP.AM.fixed_tab),
+                                                          _lib.ptr(coeffs), int(bool(skip_preps and AP.AM.have_pattern))))
     if AP.APT == APT_LinearForm:
         return _assemble_lf(target, AP, factor=factor, skip_preps=skip_preps, offset=offset)
     assert isinstance(target, FEMatrixBlock), "assemble into an FEMatrixBlock (A[j,k])"

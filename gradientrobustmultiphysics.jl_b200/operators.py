@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .assembly import (APT_BilinearForm, APT_LinearForm, APT_SymmetricBilinearForm, AssemblyPattern, DataFunction, Divergence,
+from .assembly import (APT_BilinearForm, APT_LinearForm, APT_SymmetricBilinearForm, AssemblyPattern, ConvectionAction, DataFunction, Divergence,
                        Gradient, HookeAction, Identity, NoAction, SymmetricGradient, _FDotAction, _op, assemble, fdot_action)
 from .fespace import FEMatrixBlock, FEVectorBlock
 
@@ -28,6 +28,7 @@ class PDEOperator:
         self.transposed_assembly = False
         self.transposed_copy = False
         self.transpose_factor = None
+        self.fixed_arguments = []
         self.fixed_arguments_ids = []
 
     def __repr__(self):
@@ -101,10 +102,31 @@ def LinearForm(operator, data=None, name="auto", regions=(0,), factor=1, store=F
     return O
 
 
-def create_assembly_pattern(O: PDEOperator, target):
-    """pdeoperators.jl:910-971 (no fixed arguments)"""
+def ConvectionOperator(a_from: int, a_operator, xdim: int, ncomponents: int, name="auto", a_to=1, factor=1, ansatz_operator=Gradient,
+                       test_operator=Identity, regions=(0,), newton=False, store=False, transposed_assembly=True, bonus_quadorder=0):
+    """ConvectionOperator(a_from, a_operator, xdim, ncomponents; a_to = 1, ...) (pdeoperators.jl:435-510): the Picard-linearised
+    convection term ((a . grad) u, v) as a trilinear form whose first argument is the coefficient function CurrentSolution[a_from]"""
+    if newton or a_to != 1:
+        raise NotImplementedError("ConvectionOperator: the Picard form with the coefficient in position 1 is on the device "
+                                  "(newton = true is a NonlinearForm, SURVEY.md 8f N4)")
+    if name == "auto":
+        name = f"(({_op(a_operator)}(#1) . {_op(ansatz_operator)}) #A, {_op(test_operator)}(#T))"
+    O = PDEOperator(APT_BilinearForm, name, [a_operator, ansatz_operator, test_operator], ConvectionAction(xdim, ncomponents, bonus_quadorder),
+                    [1, 2], factor, regions, store)
+    O.fixed_arguments = [a_to]
+    O.fixed_arguments_ids = [a_from]
+    O.transposed_assembly = transposed_assembly
+    return O
+
+
+def create_assembly_pattern(O: PDEOperator, target, CurrentSolution=None):
+    """pdeoperators.jl:910-971"""
     if isinstance(target, FEMatrixBlock):
         FES = [target.FESY, target.FESX] if O.transposed_assembly else [target.FESX, target.FESY]
+        if O.fixed_arguments_ids:       # 922-927: the FESpaces of the fixed arguments come first
+            from .assembly import DiscreteBilinearForm
+            fixedFES = [CurrentSolution[i].FES for i in O.fixed_arguments_ids]
+            return DiscreteBilinearForm(O.operators4arguments, fixedFES + FES, O.action, name=O.name, regions=O.regions)
         return AssemblyPattern(O.APT, O.name, FES, O.operators4arguments, O.action, O.apply_action_to, O.regions)
     if isinstance(target, FEVectorBlock):
         if O.APT != APT_LinearForm:
@@ -119,10 +141,13 @@ def assemble_operator(target, O: PDEOperator, CurrentSolution=None, Pattern=None
     if Pattern is None:
         Pattern = getattr(O, "_pattern", None)
         if Pattern is None or Pattern.FES[0].xgrid is not (target.FESX if isinstance(target, FEMatrixBlock) else target.FES).xgrid:
-            Pattern = create_assembly_pattern(O, target)
+            Pattern = create_assembly_pattern(O, target, CurrentSolution)
             O._pattern = Pattern
     if isinstance(target, FEMatrixBlock):
-        if At is not None:
+        if O.fixed_arguments_ids:      # pdeoperators.jl:986-987
+            assemble(target, Pattern, [CurrentSolution[i] for i in O.fixed_arguments_ids], skip_preps=skip_preps,
+                     transposed_assembly=O.transposed_assembly, factor=O.factor, fixed_arguments=O.fixed_arguments)
+        elif At is not None:
             ft = O.factor if O.transpose_factor is None else O.transpose_factor
             assemble(target, Pattern, skip_preps=skip_preps, transposed_assembly=O.transposed_assembly, factor=O.factor,
                      transpose_copy=At, factor_transpose=ft)

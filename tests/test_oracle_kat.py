@@ -318,3 +318,30 @@ def test_itemintegrator_regions_and_itemwise_sum():
     b, tot = O.ii_evaluate(g, s, O.OP_ID, u, kind=O.II_NONE, regions=[2])
     assert abs(tot[0] - g.cellvolumes[: g.ncells // 2].sum()) < 1e-14
     assert np.all(b[g.ncells // 2:] == 0) and np.allclose(b[: g.ncells // 2, 0], g.cellvolumes[: g.ncells // 2], rtol=1e-15)
+
+
+# ---- trilinear convection form (bilinearform.jl:235-257 with the kernel of pdeoperators.jl:459-467) -----------------------------
+@pytest.mark.parametrize("dim", [2, 3])
+def test_convection_trilinear_form_of_polynomials(dim):
+    """((a . grad) u, v) for polynomial a, u, v in the discrete spaces is integrated exactly: a = (1, 2[, -1]) constant,
+    u = (x^2, x y[, z]), v = (1, y[, x]); and the form is linear in a"""
+    g = tri_grid(2) if dim == 2 else tet_grid(1)
+    sv = G.FESpace(G.H1P2(dim, dim), g)
+    if dim == 2:
+        fa, fu, fv = (lambda p: [1.0, 2.0]), (lambda p: [p[0] ** 2, p[0] * p[1]]), (lambda p: [1.0, p[1]])
+        exact = 1 + 1 / 3 + 1 / 2                      # int 2x + (y + 2x) y over the unit square
+    else:
+        fa, fu, fv = (lambda p: [1.0, 2.0, -1.0]), (lambda p: [p[0] ** 2, p[0] * p[1], p[2]]), (lambda p: [1.0, p[1], p[0]])
+        exact = 1 + 1 / 3 + 1 / 2 - 1 / 2              # ... + (-1) * x over the unit cube
+    a, u, v = (nodal_interpolate(sv, f) for f in (fa, fu, fv))
+    A = O.OracleMatrix(sv.ndofs, sv.ndofs)
+    O.blf_assemble(A, g, sv, sv, O.OP_GRAD, O.OP_ID, action=O.ACT_CONVECTION, transposed_assembly=True, fixed=(sv, O.OP_ID, a))
+    M = A.toscipy()
+    assert abs(v @ (M @ u) - exact) < TOL
+    A2 = O.OracleMatrix(sv.ndofs, sv.ndofs)
+    O.blf_assemble(A2, g, sv, sv, O.OP_GRAD, O.OP_ID, action=O.ACT_CONVECTION, transposed_assembly=True, fixed=(sv, O.OP_ID, -2.0 * a))
+    assert abs(v @ (A2.toscipy() @ u) + 2.0 * exact) < TOL
+    # a = 0: every contribution is an exact zero, _addnz inserts nothing (fematrix.jl:54-58)
+    A0 = O.OracleMatrix(sv.ndofs, sv.ndofs)
+    O.blf_assemble(A0, g, sv, sv, O.OP_GRAD, O.OP_ID, action=O.ACT_CONVECTION, transposed_assembly=True, fixed=(sv, O.OP_ID, 0.0 * a))
+    assert A0.csc()[1].size == 0
