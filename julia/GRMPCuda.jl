@@ -13,7 +13,8 @@
 #     assemble!(A::FEMatrixBlock{Float64,Int64,Float64,Int32}, AP::AssemblyPattern{<:APT_BilinearForm,Float64,ON_CELLS,Float64,Int32}; ...)
 #     assemble!(b::FEVectorBlock{Float64,Float64,Int32},       AP::AssemblyPattern{<:APT_LinearForm,Float64,ON_CELLS,Float64,Int32}; ...)
 # which are more specific than the reference's, so PDEDescription / add_operator! / solve! reach them unchanged.  Calls WITH
-# coefficient arguments (FEB, row N4 of SURVEY.md 8f) never dispatch here.  Inside, `blf_plan` / `lf_plan` decide whether the
+# coefficient arguments (FEB, row N4 of SURVEY.md 8f) dispatch to a third method further down that takes the Picard convection form
+# of ConvectionOperator and hands everything else back.  Inside, `blf_plan` / `lf_plan` decide whether the
 # (FEType, operator, action) triple is on the device path; everything else is handed back to the reference method with
 # `invoke` and ALL keyword arguments -- the library itself has no CPU fallback, the reference loop simply stays reachable.
 module GRMPCuda
@@ -408,6 +409,74 @@ function GRMP.assemble!(b::FEVectorBlock{Float64,Float64,Int32}, AP::AssemblyPat
     GC.@preserve fdata entries check(ccall((:grmp_lf_assemble, lib), Cint,
         (Ptr{Cvoid}, Float64, Cint, Ptr{Float64}, Ptr{Float64}, Int64),
         d.h, Float64(factor), plan.fsrc, isempty(fdata) ? C_NULL : pointer(fdata), entries, b.offset))
+    AP.last_allocations = 0
+    return nothing
+end
+
+# ---- trilinear forms with one coefficient argument (SURVEY.md 8f N4, first slice) ---------------------------------------------------
+# assemble!(A, AP, FEB; fixed_arguments = [1]) with three FESpaces (bilinearform.jl:235-257), as `assemble_operator!` calls it for a
+# ConvectionOperator(a_from, a_operator, xdim, ncomponents; a_to = 1) (pdeoperators.jl:435-510, 986-987).  The kernel is an opaque closure:
+# it is PROBED on random inputs and accepted only if it is result[j] = sum_k input[k] * input[xdim + (j-1) xdim + k].
+function is_convection_kernel(action, xdim::Int, nc::Int)
+    action isa GRMP.DefaultUserAction || return false
+    (GRMP.is_xdependent(action) || GRMP.is_timedependent(action) || GRMP.is_itemdependent(action) || GRMP.is_xrefdependent(action)) && return false
+    action.argsizes[1] == nc && action.argsizes[2] == xdim + nc * xdim || return false
+    r = zeros(nc)
+    for trial = 1:3
+        x = [sin(1.0 + 0.7 * i * trial) for i = 1:xdim+nc*xdim]
+        fill!(r, 0); action.kernel(r, x)
+        for j = 1:nc
+            e = 0.0
+            for k = 1:xdim; e += x[k] * x[xdim+(j-1)*xdim+k]; end
+            r[j] == e || return false
+        end
+    end
+    return true
+end
+
+const TRIPATTERNS = WeakKeyDict{Any,Dict{Bool,DBlf}}()
+
+function GRMP.assemble!(A::FEMatrixBlock{Float64,Int64,Float64,Int32}, AP::AssemblyPattern{APT,Float64,ON_CELLS,Float64,Int32},
+        FEB::Array{<:FEVectorBlock{Float64,Float64,Int32},1};
+        factor = 1, factor_transpose = factor, skip_preps::Bool = false, fixed_arguments = nothing,
+        transposed_assembly::Bool = false, transpose_copy = nothing) where {APT<:GRMP.APT_BilinearForm}
+    fallback() = invoke(GRMP.assemble!, Tuple{FEMatrixBlock,AssemblyPattern{APT,Float64,ON_CELLS},Array{<:FEVectorBlock{Float64,Float64,Int32},1}},
+                        A, AP, FEB; factor, factor_transpose, skip_preps, fixed_arguments, transposed_assembly, transpose_copy)
+    (length(AP.FES) == 3 && length(FEB) == 1 && transpose_copy === nothing && APT === GRMP.APT_BilinearForm &&
+     (fixed_arguments === nothing || fixed_arguments == [1])) || return fallback()
+    xdim = size(AP.FES[1].xgrid[Coordinates], 1)
+    oa, o1, o2 = opcode(AP.operators[1]), opcode(AP.operators[2]), opcode(AP.operators[3])
+    (oa === nothing || o1 === nothing || o2 === nothing || any(F -> fecode(eltype(F)) === nothing, AP.FES)) && return fallback()
+    nc = GRMP.Length4Operator(AP.operators[3], xdim, get_ncomponents(eltype(AP.FES[3])))
+    is_convection_kernel(AP.action, GRMP.Length4Operator(AP.operators[1], xdim, get_ncomponents(eltype(AP.FES[1]))), nc) || return fallback()
+    skip_preps || GRMP.prepare_assembly!(AP)
+    byor = get!(() -> Dict{Bool,DBlf}(), TRIPATTERNS, AP)
+    d = get(byor, transposed_assembly, nothing)
+    fresh = d === nothing
+    if fresh
+        e1 = GRMP.get_basisevaler(AP.AM, 2, 1); e2 = GRMP.get_basisevaler(AP.AM, 3, 1)
+        v1, d1, t1 = evaltab(e1); v2, d2, t2 = evaltab(e2)
+        w = Vector{Float64}(GRMP.get_qweights(AP.AM))
+        regions = AP.regions == [0] ? Int32[] : Vector{Int32}(AP.regions)
+        s1, s2 = device_space(AP.FES[2]), device_space(AP.FES[3])
+        h = Ref{Ptr{Cvoid}}()
+        GC.@preserve v1 d1 v2 d2 w regions check(ccall((:grmp_blf_create, lib), Cint,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float64}, Cint, Cint, Ptr{Int32}, Cint, Cint, Ptr{Float64}, Ref{EvalTab}, Ref{EvalTab}, Ref{Ptr{Cvoid}}),
+            s1.h, s2.h, o1, o2, 3, C_NULL, 0, transposed_assembly, isempty(regions) ? C_NULL : pointer(regions), length(regions), length(w), w, t1, t2, h))
+        d = byor[transposed_assembly] = DBlf(h[], 0, Int64[], Int64[], Float64(factor), transposed_assembly, (s1, s2))
+        finalizer(x -> destroy(:grmp_blf_destroy, x), d)
+    end
+    # the coefficient function: FEB[1] evaluated at the quadrature points on the device
+    ea = GRMP.get_basisevaler(AP.AM, 1, 1)
+    va, da, ta = evaltab(ea)
+    coeffs = FEB[1].entries[FEB[1].offset+1:FEB[1].last_index]
+    keep = skip_preps && !fresh
+    GC.@preserve va da coeffs check(ccall((:grmp_blf_set_fixed_argument, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ref{EvalTab}, Ptr{Float64}, Cint),
+        d.h, device_space(AP.FES[1]).h, oa, ta, coeffs, keep))
+    keep || symbolic!(d, A, Float64(factor))
+    nzval = Vector{Float64}(undef, d.nnz)
+    check(ccall((:grmp_blf_numeric, lib), Cint, (Ptr{Cvoid}, Float64, Ptr{Float64}), d.h, Float64(factor), nzval))
+    install_block!(A, SparseMatrixCSC(size(A, 1), size(A, 2), d.colptr, d.rowval, nzval))
     AP.last_allocations = 0
     return nothing
 end
