@@ -252,8 +252,15 @@ def DiscreteLumpedBilinearForm(operators, FES, action=None, name="lumpedBLF", re
 
 def DiscreteLinearForm(operators, FES, action=None, name="LF", regions=(0,)):
     assert len(operators) == len(FES), "each FESpace needs an operator and vice versa"
+    if len(FES) == 2:
+        # one coefficient argument, NoAction: FES = [FES_a, FES_test] (linearform.jl:29-33, 130-178)
+        if action is not None and not isinstance(action, NoAction):
+            raise NotImplementedError("LinearForms with a coefficient argument: NoAction runs on the device, user actions stay with the reference")
+        AP = AssemblyPattern(APT_LinearForm, name, FES[1:], operators[1:], NoAction(), [1], regions)
+        AP.fixed = (FES[0], _op(operators[0]))
+        return AP
     if len(FES) != 1:
-        raise NotImplementedError("LinearForms with FEB coefficient arguments are a 'next' row (SURVEY.md 8f N4)")
+        raise NotImplementedError("LinearForms with several coefficient arguments are a 'next' row (SURVEY.md 8f N4)")
     return AssemblyPattern(APT_LinearForm, name, FES, operators, action or NoAction(), [1], regions)
 
 
@@ -431,6 +438,9 @@ def _embed(block: FEMatrixBlock, colptr, rowval, nzval):
 def assemble(target, AP: AssemblyPattern, FEB=(), factor=1, factor_transpose=None, transposed_assembly=False, transpose_copy=None,
              skip_preps=False, fixed_arguments=None, offset=0, fdata=None):
     """assemble!(A::FEMatrixBlock, AP; ...) / assemble!(b::FEVectorBlock | Vector, AP; ...)"""
+    if AP.APT == APT_LinearForm and AP.fixed is not None:
+        assert len(FEB) == 1 and FEB[0].FES is AP.fixed[0], "LinearForm with a coefficient argument: FEB = [block of the coefficient function]"
+        return _assemble_lf(target, AP, factor=factor, skip_preps=skip_preps, offset=offset, feb=FEB[0])
     if len(FEB) != 0 and not (AP.fixed is not None and len(FEB) == 1 and AP.APT == APT_BilinearForm):
         raise NotImplementedError("FEB coefficient arguments: one fixed argument of a trilinear convection form is on the device "
                                   "(SURVEY.md 8f N4); anything else stays with the reference")
@@ -489,7 +499,7 @@ def _qp_table(AP, P):
     return 2, np.ascontiguousarray(vals.reshape(g.ncells, len(P.qf), -1))
 
 
-def _assemble_lf(b, AP, factor=1, skip_preps=False, offset=0):
+def _assemble_lf(b, AP, factor=1, skip_preps=False, offset=0, feb=None):
     L = _lib.lib()
     if AP.AM is None or not skip_preps:
         if AP.AM is None or AP.AM.kind != "lf":
@@ -501,6 +511,15 @@ def _assemble_lf(b, AP, factor=1, skip_preps=False, offset=0):
     else:
         entries = b
     assert entries.dtype == np.float64 and entries.flags.c_contiguous
+    if feb is not None:
+        if not hasattr(P, "fixed_tab"):
+            P.fixed_tab, kf = _tables(AP.fixed[0], AP.fixed[1], P.qf)
+            P.keep.append(kf)
+        coeffs = np.ascontiguousarray(feb.entries[feb.offset:feb.offset + feb.FES.ndofs])
+        _lib.check(L.grmp_lf_assemble_feb(P.h, float(factor), device_space(AP.fixed[0]), AP.fixed[1].code, C.byref(P.fixed_tab), _lib.ptr(coeffs),
+                                          _lib.ptr(entries), int(offset)))
+        AP.last_allocations = 0
+        return None
     if isinstance(AP.action, _FDotAction):
         fsrc, fd = _qp_table(AP, P)
         rd = AP.operators[0]

@@ -160,9 +160,11 @@ struct grmp_lf {
   std::vector<double> w_host, vals_host, derivs_host;
   i64 topo_grid = 0, topo_sp = 0;
   RegionFilter reg;
-  DevBuf<double> w, lbuf, b, fdata;
+  DevBuf<double> w, lbuf, b, fdata, acoeffs, ascratch;
   DevBuf<unsigned char> active;
-  EvalTables tab;
+  EvalTables tab, ta;
+  grmp_space* sa = nullptr;      // coefficient argument of grmp_lf_assemble_feb
+  int opa = 0;
   DofGather dg;
   grmp_stats st{};
 };
@@ -799,9 +801,9 @@ int grmp_lf_set_path(grmp_lf* l, int path) {
   return GRMP_OK;
 }
 
-int grmp_lf_assemble(grmp_lf* l, double factor, int fsrc, const double* fdata, double* b_host, int64_t offset) {
+static int lf_assemble_impl(grmp_lf* l, double factor, int fsrc, const double* fdata, bool fdata_resident, double* b_host, int64_t offset) {
   if (!l || !b_host) return fail(GRMP_EINVAL, "grmp_lf_assemble: NULL argument");
-  if (fsrc != GRMP_F_NONE && !fdata) return fail(GRMP_EINVAL, "fdata missing");
+  if (fsrc != GRMP_F_NONE && !fdata && !fdata_resident) return fail(GRMP_EINVAL, "fdata missing");
   grmp_space* sp = l->sp;
   grmp_ctx* ctx = sp->grid->ctx;
   cudaStream_t s = ctx->stream;
@@ -824,7 +826,8 @@ int grmp_lf_assemble(grmp_lf* l, double factor, int fsrc, const double* fdata, d
       else if (rc != GRMP_EUNSUPPORTED || l->path_req != GRMP_PATH_AUTO) { l->fast_tried = false; return rc; }
     }
   }
-  if (fsrc == GRMP_F_CONST) GRMP_TRY(l->fdata.upload(fdata, (size_t)p.e.rd, s));
+  if (fdata_resident) { /* l->fdata already holds the table (grmp_lf_assemble_feb) */ }
+  else if (fsrc == GRMP_F_CONST) GRMP_TRY(l->fdata.upload(fdata, (size_t)p.e.rd, s));
   else if (fsrc == GRMP_F_QP_TABLE) GRMP_TRY(l->fdata.upload(fdata, (size_t)sp->grid->ncells * l->nq * p.e.rd, s));
   p.fdata = l->fdata.p; p.lbuf = l->lbuf.p; p.active = l->active.p;
   GRMP_CUDA(cudaMemcpyAsync(l->b.p, b_host + offset, (size_t)sp->ndofs * 8, cudaMemcpyHostToDevice, s));
@@ -900,6 +903,39 @@ int grmp_ii_evaluate(grmp_ii* ii, const double* coeffs_host, double factor, cons
   if (b_host) GRMP_CUDA(cudaMemcpyAsync(b_host, ii->b.p, (size_t)ncells * ardim * 8, cudaMemcpyDeviceToHost, s));
   GRMP_CUDA(cudaStreamSynchronize(s));
   return GRMP_OK;
+}
+
+int grmp_lf_assemble(grmp_lf* l, double factor, int fsrc, const double* fdata, double* b_host, int64_t offset) {
+  return lf_assemble_impl(l, factor, fsrc, fdata, false, b_host, offset);
+}
+
+int grmp_lf_assemble_feb(grmp_lf* l, double factor, grmp_space* sa, int op_a, const grmp_evaltab* tab_a, const double* coeffs_host,
+                         double* b_host, int64_t offset) {
+  if (!l || !sa || !tab_a || !coeffs_host || !b_host) return fail(GRMP_EINVAL, "grmp_lf_assemble_feb: NULL argument");
+  grmp_space* sp = l->sp;
+  if (sa->grid != sp->grid) return fail(GRMP_EINVAL, "spaces live on different grids");
+  grmp_ctx* ctx = sp->grid->ctx;
+  cudaStream_t s = ctx->stream;
+  GRMP_CUDA(cudaSetDevice(ctx->device));
+  if (l->sa != sa || l->opa != op_a || (!l->ta.refvals.p && !l->ta.refderivs.p)) {
+    GRMP_TRY(upload_tables(tab_a, l->nq, sa->grid->dim, s, &l->ta));
+    l->sa = sa; l->opa = op_a;
+  }
+  IiLocalParams ip{};
+  ip.g = sa->grid->view();
+  GRMP_TRY(make_evalview(sa, op_a, l->ta, &ip.e));
+  EvalView et;
+  GRMP_TRY(make_evalview(sp, l->op, l->tab, &et));
+  if (ip.e.rd != et.rd) return fail(GRMP_EINVAL, "operator result lengths of the coefficient argument and the test function differ");
+  const i64 ncells = sa->grid->ncells;
+  ip.reg.n = 0; ip.nq = l->nq; ip.w = l->w.p; ip.kind = GRMP_II_NONE; ip.ardim = ip.e.rd; ip.factor = 1.0;
+  GRMP_TRY(l->acoeffs.upload(coeffs_host, (size_t)sa->ndofs, s));
+  const size_t nt = (size_t)std::max<i64>(ncells * l->nq * ip.e.rd, 1);
+  if (l->fdata.n < nt) GRMP_TRY(l->fdata.alloc(nt));
+  if (l->ascratch.n < (size_t)std::max<i64>(ncells * ip.e.rd, 1)) GRMP_TRY(l->ascratch.alloc((size_t)std::max<i64>(ncells * ip.e.rd, 1)));
+  ip.coeffs = l->acoeffs.p; ip.itemval = l->ascratch.p; ip.qtable = l->fdata.p;
+  GRMP_TRY(launch_ii_local(ip, s));
+  return lf_assemble_impl(l, factor, GRMP_F_QP_TABLE, nullptr, true, b_host, offset);
 }
 
 int grmp_lf_stats(grmp_lf* l, grmp_stats* out) {

@@ -227,6 +227,13 @@ int grmp_lf_set_path(grmp_lf* lf, int path);
  * (fdata[resultdim]) or GRMP_F_QP_TABLE (fdata[ncells][nq][resultdim], the host-evaluated
  * DataFunction).  b_host has length >= ndofs + offset and is updated in place. */
 int grmp_lf_assemble(grmp_lf* lf, double factor, int fsrc, const double* fdata, double* b_host, int64_t offset);
+/* assemble!(b, AP, FEB) of a LinearForm with ONE coefficient argument and NoAction (linearform.jl:130-178 with nFE = 2): the operator
+ * evaluation of FEB[1] at the quadrature points takes the place of f, b[dof + offset] += int op_a(FEB[1]) . op(v_dof).  space_a / op_a /
+ * tab_a describe FEB[1].FES and its operator (same result length as the test operator), coeffs_host its entries; the evaluation runs on
+ * the device in the reference's order (eval_febe!, feevaluator.jl:445-452).  The rule of the linear form must be the one prepare_assembly!
+ * picks for BOTH FESpaces (assemblypatterns.jl:559-565). */
+int grmp_lf_assemble_feb(grmp_lf* lf, double factor, grmp_space* space_a, int op_a, const grmp_evaltab* tab_a, const double* coeffs_host,
+                         double* b_host, int64_t offset);
 int grmp_lf_stats(grmp_lf* lf, grmp_stats* out);
 
 /* ---- ItemIntegrator with one argument (src/assemblypatterns/itemintegrator.jl:18-21, 160-360): the error norms every example ends

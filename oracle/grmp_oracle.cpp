@@ -1041,6 +1041,31 @@ int orc_ii_evaluate(double* b, double* total, const orc_grid* og, const orc_spac
   return 0;
 }
 
+// operator evaluation of an FE function at the quadrature points of every cell (eval_febe!, feevaluator.jl:445-452, as the assembly
+// loops evaluate their coefficient arguments: linearform.jl:141-160, bilinearform.jl:235-257): table[cell][qp][resultdim]
+int orc_feb_table(const orc_grid* og, const orc_space* os, int op, const double* coeffs, int order, double* table, int* nq_out, int* rd_out) {
+  Grid g = to_grid(og); Space s = to_space(os);
+  QRule q; if (!make_qrule(g.dim, order < 0 ? 0 : order, q)) return -1;
+  Evaluator e; if (!e.init(&g, s, op, q)) return -1;
+  if (nq_out) *nq_out = q.n();
+  if (rd_out) *rd_out = e.resultdim;
+  if (!table) return 0;
+  const int nd = e.nd, nq = q.n(), rd = e.resultdim;
+  std::vector<double> c(nd);
+  for (i64 item = 0; item < g.ncells; item++) {
+    e.update(item);
+    const i32* dofs = s.celldofs + item * nd;
+    for (int d = 0; d < nd; d++) c[d] = coeffs[dofs[d] - 1] * 1.0;
+    for (int i = 0; i < nq; i++) {
+      double* t = table + ((size_t)item * nq + i) * rd;
+      for (int k = 0; k < rd; k++) t[k] = 0.0;
+      for (int d = 0; d < nd; d++)
+        for (int k = 0; k < rd; k++) t[k] += c[d] * e.cv(k, d, i) * 1;
+    }
+  }
+  return 0;
+}
+
 // physical quadrature points x = b + A*xref of every cell (eval_trafo!, linearform.jl:197-201):
 // xq[cell][qp][dim]; used by tests to tabulate f independently of the host mirror
 int orc_quadpoints(const orc_grid* og, int order, double* xq) {

@@ -63,6 +63,7 @@ def lib():
                                          C.c_void_p, C.c_int, C.c_double, C.c_int64, C.c_int, C.c_void_p]
         _LIB.orc_ii_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_Grid), C.POINTER(_Space), C.c_int, C.c_int, C.c_void_p,
                                          C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        _LIB.orc_feb_table.argtypes = [C.POINTER(_Grid), C.POINTER(_Space), C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB.orc_set_fixed_argument.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _LIB.orc_quadpoints.argtypes = [C.POINTER(_Grid), C.c_int, C.c_void_p]
         _LIB.orc_qrule.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -247,6 +248,18 @@ def ii_evaluate(grid, space, op, coeffs, *, kind=II_NONE, factor=1.0, data=None,
     _check(lib().orc_ii_evaluate(_p(b), _p(total), C.byref(g.s), C.byref(s.s), op, kind, _p(c), float(factor), _p(d), _p(rg), rg.size,
                                  bonus_quadorder, None, None))
     return b, total
+
+
+def feb_table(grid, space, op, coeffs, order):
+    """operator evaluation of the FE function at the quadrature points of the rule of this order: [ncells, nq, resultdim]"""
+    g = _grid_struct(grid, _needs_faces(space))
+    s = _space_struct(space)
+    nq, rd = C.c_int(0), C.c_int(0)
+    _check(lib().orc_feb_table(C.byref(g.s), C.byref(s.s), op, None, order, None, C.byref(nq), C.byref(rd)))
+    c = np.ascontiguousarray(coeffs, dtype=np.float64)
+    t = np.zeros((g.cellnodes.shape[0], nq.value, rd.value))
+    _check(lib().orc_feb_table(C.byref(g.s), C.byref(s.s), op, _p(c), order, _p(t), None, None))
+    return t
 
 
 def quadpoints(grid, order):

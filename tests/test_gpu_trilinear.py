@@ -72,3 +72,49 @@ def test_convection_needs_its_coefficient():
     AP = G.DiscreteBilinearForm([G.Identity, G.Gradient, G.Identity], [sv, sv, sv], G.ConvectionAction(2, 2))
     with pytest.raises(G._lib.GrmpError):
         G.assemble_csc(AP, 1.0)                      # no fixed argument set: GRMP_ESTATE, nothing is assembled
+
+
+LF_FEB_CASES = [
+    ("P2 test, P1 coefficient, id-id, tri", 2, 3, True, lambda d: G.H1P2(1, d), G.Identity, lambda d: G.H1P1(1), G.Identity),
+    ("P2{2} test, grad of P2 scalar as coefficient, tri", 2, 2, True, lambda d: G.H1P2(d, d), G.Identity, lambda d: G.H1P2(1, d), G.Gradient),
+    ("RT0 test, P1{3} coefficient, tet", 3, 1, False, lambda d: G.HDIVRT0(d), G.Identity, lambda d: G.H1P1(d), G.Identity),
+    ("P0 test, div of BR coefficient, tri", 2, 2, True, lambda d: G.L2P0(1), G.Identity, lambda d: G.H1BR(d), G.Divergence),
+]
+
+
+@pytest.mark.parametrize("case", LF_FEB_CASES, ids=[c[0] for c in LF_FEB_CASES])
+@pytest.mark.parametrize("path", ["generic", "auto"])
+def test_linearform_with_coefficient_argument(case, path):
+    """assemble!(b, AP, FEB) with nFE = 2 and NoAction (linearform.jl:130-178): b[dof] += int op_a(FEB[1]) . op(v_dof)"""
+    _, dim, L, pert, fet, opt, fea, opa = case
+    g = grid(dim, L, pert)
+    st, sa = G.FESpace(fet(dim), g), G.FESpace(fea(dim), g)
+    sol = G.FEVector([sa, st])
+    rng = np.random.default_rng(5)
+    sol.entries[:] = rng.standard_normal(sol.entries.size)
+    old = G.assembly.DEFAULT_PATH
+    G.assembly.DEFAULT_PATH = G._lib.PATH_GENERIC if path == "generic" else G._lib.PATH_AUTO
+    try:
+        AP = G.DiscreteLinearForm([opa, opt], [sa, st])
+        b = G.FEVector([sa, st])
+        b.entries[:] = 0.5
+        G.assemble(b[2], AP, [sol[1]], factor=1.5)
+    finally:
+        G.assembly.DEFAULT_PATH = old
+    qo = G.quadrature_order(AP)
+    P = AP.AM
+    opt_c, opa_c = G.assembly._op(opt), G.assembly._op(opa)
+    O.qrule_override(dim, qo, P.qf.xref, P.qf.w)
+    try:
+        table = O.feb_table(g, sa, opa_c.code, sol.entries[: sa.ndofs], qo)
+        ob = np.full(st.ndofs, 0.5)
+        bonus = qo - (st.fetype.polynomialorder(dim) - opt_c.needed_derivative)      # the oracle adds the test space's own order
+        O.lf_assemble(ob, g, st, opt_c.code, fsrc=O.F_QP_TABLE, fdata=table, factor=1.5, bonus_quadorder=bonus)
+    finally:
+        O.qrule_override(dim, qo)
+    assert np.all(b.entries[: sa.ndofs] == 0.5)
+    got = b.entries[sa.ndofs:]
+    if path == "generic":
+        assert np.array_equal(got, ob), f"max abs diff {np.abs(got - ob).max():.3e}"
+    else:
+        assert np.abs(got - ob).max() <= 1e-12 * np.abs(ob - 0.5).max()
