@@ -23,7 +23,7 @@ EXPORTS = [
     "grmp_blf_numeric_steps", "grmp_blf_set_owned_columns", "grmp_space_create", "grmp_space_destroy", "grmp_blf_create",
     "grmp_blf_destroy", "grmp_blf_set_path", "grmp_blf_symbolic", "grmp_blf_get_pattern", "grmp_blf_numeric",
     "grmp_blf_get_values", "grmp_blf_transpose_copy", "grmp_blf_stats", "grmp_blf_device_values", "grmp_lf_create",
-    "grmp_lf_destroy", "grmp_lf_assemble", "grmp_lf_stats", "grmp_blf_set_fixed_argument", "grmp_lf_assemble_feb", "grmp_ii_create", "grmp_ii_destroy", "grmp_ii_resultdim", "grmp_ii_evaluate", "grmp_blf_assemble_host", "grmp_blf_device_csc", "grmp_blf_matmul",
+    "grmp_lf_destroy", "grmp_lf_assemble", "grmp_lf_stats", "grmp_blf_set_fixed_argument", "grmp_blf_set_newton_argument", "grmp_blf_newton_rhs", "grmp_lf_assemble_feb", "grmp_ii_create", "grmp_ii_destroy", "grmp_ii_resultdim", "grmp_ii_evaluate", "grmp_blf_assemble_host", "grmp_blf_device_csc", "grmp_blf_matmul",
     "grmp_blf_matmul_device", "grmp_blf_residual", "grmp_blf_apply_penalties", "grmp_lf_set_path",
 ]
 
@@ -96,6 +96,8 @@ def lib():
         L.grmp_lf_set_path.argtypes = [vp, i32]
         L.grmp_lf_assemble.argtypes = [vp, dbl, i32, vp, vp, i64]
         L.grmp_lf_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.grmp_blf_set_newton_argument.argtypes = [vp, i32, C.POINTER(EvalTab), vp, i32]
+        L.grmp_blf_newton_rhs.argtypes = [vp, vp, i64]
         L.grmp_lf_assemble_feb.argtypes = [vp, dbl, vp, i32, C.POINTER(EvalTab), vp, vp, i64]
         L.grmp_blf_device_csc.argtypes = [vp, C.POINTER(DeviceCSC)]
         L.grmp_blf_matmul.argtypes = [vp, vp, vp, dbl, i32]

@@ -146,6 +146,17 @@ class ConvectionAction:
         self.argsizes = [ncomponents, xdim + ncomponents * xdim]
 
 
+class NewtonConvectionAction:
+    """OperatorWithUserJacobian(convection_function_fe_1, convection_jacobian, argsizes) of ConvectionOperator(...; newton = true)
+    (pdeoperators.jl:459-493), evaluated on the device (GRMP_ACT_NEWTON_CONVECTION)"""
+    code = 4
+    params = None
+
+    def __init__(self, xdim, ncomponents, bonus_quadorder=0, name="convection [Newton]"):
+        self.xdim, self.ncomponents, self.bonus_quadorder, self.name = xdim, ncomponents, bonus_quadorder, name
+        self.argsizes = [ncomponents, xdim + ncomponents * xdim, xdim + ncomponents * xdim]
+
+
 class _FDotAction:
     """fdot_action(data) (actions.jl:119-128)"""
     code = 0
@@ -208,7 +219,7 @@ def device_space(FES: FESpace):
 
 
 # ---- assembly patterns ---------------------------------------------------------------------------
-APT_BilinearForm, APT_SymmetricBilinearForm, APT_LumpedBilinearForm, APT_LinearForm, APT_ItemIntegrator = 0, 1, 2, 10, 20
+APT_BilinearForm, APT_SymmetricBilinearForm, APT_LumpedBilinearForm, APT_LinearForm, APT_ItemIntegrator, APT_NonlinearForm = 0, 1, 2, 10, 20, 30
 
 
 class AssemblyPattern:
@@ -248,6 +259,39 @@ def DiscreteSymmetricBilinearForm(operators, FES, action=None, name="symBLF", re
 def DiscreteLumpedBilinearForm(operators, FES, action=None, name="lumpedBLF", regions=(0,), apply_action_to=(1,)):
     assert len(operators) == len(FES) == 2, "each FESpace needs an operator and vice versa"
     return AssemblyPattern(APT_LumpedBilinearForm, name, FES, operators, action or NoAction(), [1], regions)
+
+
+def DiscreteNonlinearForm(operators, FES, action, name="NLF", regions=(0,)):
+    """AssemblyPattern{APT_NonlinearForm} (nonlinearform.jl:1-40) for the Newton convection form: operators = [a_operator,
+    ansatz_operator, test_operator], all three FESpaces the space of the unknown (nonlinearform.jl:110-112)"""
+    assert len(operators) == len(FES) == 3 and FES[0] is FES[1] is FES[2], "the nonlinearity depends on one unknown"
+    if not isinstance(action, NewtonConvectionAction):
+        raise NotImplementedError("NonlinearForm: the Newton convection kernel runs on the device; other kernels are user closures")
+    AP = AssemblyPattern(APT_NonlinearForm, name, FES[1:], operators[1:], action, [1], regions)
+    AP.fixed = (FES[0], _op(operators[0]))
+    return AP
+
+
+def full_assemble(A, b, AP: AssemblyPattern, FEB, factor=1, transposed_assembly=False, skip_preps=False):
+    """full_assemble!(A, b, AP, FEB; factor, transposed_assembly, skip_preps) (nonlinearform.jl:44-245): Jacobian into the matrix
+    block A, DN(u) u - N(u) into the vector block b (may be None)"""
+    assert AP.APT == APT_NonlinearForm and isinstance(A, FEMatrixBlock)
+    blk = FEB[0] if isinstance(FEB, (list, tuple)) else FEB
+    assert blk.FES is AP.fixed[0]
+    tr = bool(transposed_assembly)
+    if AP.AM is None or AP.AM.kind != "blf" or AP.AM.transposed != tr:
+        prepare_assembly(AP, tr)
+    P = AP.AM
+    coeffs = np.ascontiguousarray(blk.entries[blk.offset:blk.offset + blk.FES.ndofs])
+    _lib.check(_lib.lib().grmp_blf_set_newton_argument(P.h, AP.fixed[1].code, C.byref(P.fixed_tab), _lib.ptr(coeffs),
+                                                       int(bool(skip_preps and P.have_pattern))))
+    cp, rv, nz = assemble_csc(AP, factor, skip_preps, transposed_assembly)
+    A.parent.add_csc(*_embed(A, cp, rv, nz))
+    if b is not None:
+        assert isinstance(b, FEVectorBlock) and b.FES is AP.FES[1]
+        _lib.check(_lib.lib().grmp_blf_newton_rhs(P.h, _lib.ptr(b.entries), int(b.offset)))
+    AP.last_allocations = 0
+    return None
 
 
 def DiscreteLinearForm(operators, FES, action=None, name="LF", regions=(0,)):
@@ -333,12 +377,12 @@ def prepare_assembly(AP: AssemblyPattern, transposed_assembly=False):
         t2, k2 = _tables(AP.FES[1], AP.operators[1], P.qf)
         P.keep += [k1, k2]
         act = AP.action
-        if not isinstance(act, (NoAction, HookeAction, ConvectionAction)):
-            raise NotImplementedError("bilinear forms support NoAction, the Hooke tensor actions and the convection kernel on the device")
-        if isinstance(act, ConvectionAction):
+        if not isinstance(act, (NoAction, HookeAction, ConvectionAction, NewtonConvectionAction)):
+            raise NotImplementedError("bilinear forms support NoAction, the Hooke tensor actions and the convection kernels on the device")
+        if isinstance(act, (ConvectionAction, NewtonConvectionAction)):
             P.fixed_tab, kf = _tables(AP.fixed[0], AP.fixed[1], P.qf)
             P.keep.append(kf)
-        _lib.check(L.grmp_blf_create(s1, s2, AP.operators[0].code, AP.operators[1].code, act.code, _lib.ptr(act.params), AP.APT,
+        _lib.check(L.grmp_blf_create(s1, s2, AP.operators[0].code, AP.operators[1].code, act.code, _lib.ptr(act.params), 0 if AP.APT == APT_NonlinearForm else AP.APT,
                                      int(bool(transposed_assembly)), _lib.ptr(regions), regions.size, len(P.qf), _lib.ptr(w), C.byref(t1), C.byref(t2), C.byref(h)))
         P.kind = "blf"
         if DEFAULT_PATH != _lib.PATH_AUTO:

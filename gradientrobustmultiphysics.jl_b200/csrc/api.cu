@@ -143,7 +143,10 @@ struct grmp_blf {
   grmp_space* sa = nullptr;       // fixed (coefficient) argument of a trilinear form
   int opa = 0, aq_rd = 0;
   EvalTables ta;
-  DevBuf<double> acoeffs, aq, aq_scratch;
+  DevBuf<double> acoeffs, aq, aq_scratch, gq, rbuf, rhs;
+  DevBuf<unsigned char> nl_active;
+  DofGather nl_dg;
+  bool nl_dg_built = false;
   FastP2Tet fast;
   i64 ncols_owned = -1;
   double p2tet_kappa = 0.0;       // cancellation indicator of the grid (AUTO guard of the ring-walk kernel)
@@ -190,7 +193,12 @@ static int fill_blf_params(grmp_blf* b, double factor, BlfLocalParams* p) {
   p->apt = b->apt; p->transposed = b->transposed; p->reg = b->reg; p->nq = b->nq; p->w = b->w.p; p->factor = factor;
   p->nrows_key = b->out_rows();
   p->aq = b->aq.p; p->aq_rd = b->aq_rd;
+  p->gq = b->gq.p; p->rbuf = nullptr; p->active = nullptr;
   if (b->action == GRMP_ACT_CONVECTION && (!b->sa || !b->aq.p)) return fail(GRMP_ESTATE, "GRMP_ACT_CONVECTION: call grmp_blf_set_fixed_argument first");
+  if (b->action == GRMP_ACT_NEWTON_CONVECTION) {
+    if (!b->sa || !b->aq.p || !b->gq.p) return fail(GRMP_ESTATE, "GRMP_ACT_NEWTON_CONVECTION: call grmp_blf_set_newton_argument first");
+    GRMP_TRY(make_evalview(b->s1, b->opa, b->ta, &p->ea));
+  }
   p->keys = nullptr; p->lbuf = nullptr;
   return GRMP_OK;
 }
@@ -224,6 +232,12 @@ static int blf_numeric_launch(grmp_blf* b, BlfLocalParams& p, cudaStream_t s) {
   } else {
     const size_t nl = (size_t)p.e1.nd * p.e2.nd * p.g.ncells;
     if (b->lbuf.n != nl) GRMP_TRY(b->lbuf.alloc(nl));
+    if (b->action == GRMP_ACT_NEWTON_CONVECTION) {
+      const size_t nr = (size_t)std::max<i64>((i64)p.e2.nd * p.g.ncells, 1);
+      if (b->rbuf.n != nr) GRMP_TRY(b->rbuf.alloc(nr));
+      if (b->nl_active.n != (size_t)std::max<i64>(p.g.ncells, 1)) GRMP_TRY(b->nl_active.alloc((size_t)std::max<i64>(p.g.ncells, 1)));
+      p.rbuf = b->rbuf.p; p.active = b->nl_active.p;
+    }
     p.lbuf = b->lbuf.p;
     GRMP_TRY(launch_blf_local(p, s));
     GRMP_TRY(launch_gather(s, b->pat, b->lbuf.p, b->nzval.p));
@@ -358,7 +372,8 @@ int grmp_blf_create(grmp_space* s1, grmp_space* s2, int op1, int op2, int action
   if (!s1 || !s2 || !qweights || !tab1 || !out || nq <= 0) return fail(GRMP_EINVAL, "grmp_blf_create: bad argument");
   if (s1->grid != s2->grid) return fail(GRMP_EINVAL, "spaces live on different grids");
   if (apt < 0 || apt > 2) return fail(GRMP_EINVAL, "unknown assembly pattern type");
-  if (action < GRMP_ACT_NONE || action > GRMP_ACT_CONVECTION) return fail(GRMP_EINVAL, "unknown action");
+  if (action < GRMP_ACT_NONE || action > GRMP_ACT_NEWTON_CONVECTION) return fail(GRMP_EINVAL, "unknown action");
+  if (action == GRMP_ACT_NEWTON_CONVECTION && (apt != GRMP_APT_BILINEARFORM || s1 != s2)) return fail(GRMP_EINVAL, "the Newton convection form lives on one space and is a general form");
   if ((action == GRMP_ACT_HOOKE2D || action == GRMP_ACT_HOOKE3D) && !act_params) return fail(GRMP_EINVAL, "action parameters missing");
   if (action == GRMP_ACT_CONVECTION && apt != GRMP_APT_BILINEARFORM) return fail(GRMP_EINVAL, "the convection form is a general BilinearForm");
   grmp_blf* b = new grmp_blf();
@@ -380,7 +395,7 @@ int grmp_blf_create(grmp_space* s1, grmp_space* s2, int op1, int op2, int action
     if (!rc && t2->refvals) b->t2_vals_host.assign(t2->refvals, t2->refvals + (size_t)nq * t2->nd_all * t2->ncomp);
   }
   BlfLocalParams p;
-  if (!rc && action == GRMP_ACT_CONVECTION) {   // validated when the fixed argument arrives
+  if (!rc && (action == GRMP_ACT_CONVECTION || action == GRMP_ACT_NEWTON_CONVECTION)) {   // validated when the fixed argument arrives
     if (cudaStreamSynchronize(st) != cudaSuccess) rc = fail(GRMP_ECUDA, "upload failed");
     if (rc) { delete b; return rc; }
     *out = b;
@@ -400,6 +415,63 @@ int grmp_blf_create(grmp_space* s1, grmp_space* s2, int op1, int op2, int action
 }
 
 int grmp_blf_destroy(grmp_blf* b) { delete b; return GRMP_OK; }
+
+int grmp_blf_set_newton_argument(grmp_blf* b, int op_a, const grmp_evaltab* tab_a, const double* coeffs_host, int keep_pattern) {
+  if (!b || !tab_a || !coeffs_host) return fail(GRMP_EINVAL, "grmp_blf_set_newton_argument: NULL argument");
+  if (b->action != GRMP_ACT_NEWTON_CONVECTION) return fail(GRMP_EINVAL, "the form was not created with GRMP_ACT_NEWTON_CONVECTION");
+  grmp_space* su = b->s1;
+  grmp_ctx* ctx = su->grid->ctx;
+  cudaStream_t s = ctx->stream;
+  GRMP_CUDA(cudaSetDevice(ctx->device));
+  if (b->sa != su || b->opa != op_a || (!b->ta.refvals.p && !b->ta.refderivs.p)) {
+    GRMP_TRY(upload_tables(tab_a, b->nq, su->grid->dim, s, &b->ta));
+    b->sa = su; b->opa = op_a;
+  }
+  const i64 ncells = su->grid->ncells;
+  GRMP_TRY(b->acoeffs.upload(coeffs_host, (size_t)su->ndofs, s));
+  // the current iterate at the quadrature points: a_operator(u) and ansatz_operator(u) (nonlinearform.jl:124-141)
+  for (int which = 0; which < 2; which++) {
+    IiLocalParams ip{};
+    ip.g = su->grid->view();
+    GRMP_TRY(make_evalview(su, which == 0 ? op_a : b->op1, which == 0 ? b->ta : b->t1, &ip.e));
+    ip.reg.n = 0; ip.nq = b->nq; ip.w = b->w.p; ip.kind = GRMP_II_NONE; ip.ardim = ip.e.rd; ip.factor = 1.0;
+    DevBuf<double>& tab = which == 0 ? b->aq : b->gq;
+    const size_t nt = (size_t)std::max<i64>(ncells * b->nq * ip.e.rd, 1);
+    if (tab.n < nt) GRMP_TRY(tab.alloc(nt));
+    if (b->aq_scratch.n < (size_t)std::max<i64>(ncells * ip.e.rd, 1)) GRMP_TRY(b->aq_scratch.alloc((size_t)std::max<i64>(ncells * ip.e.rd, 1)));
+    ip.coeffs = b->acoeffs.p; ip.itemval = b->aq_scratch.p; ip.qtable = tab.p;
+    GRMP_TRY(launch_ii_local(ip, s));
+    if (which == 0) b->aq_rd = ip.e.rd;
+  }
+  EvalView e1, e2;
+  GRMP_TRY(make_evalview(b->s1, b->op1, b->t1, &e1));
+  GRMP_TRY(make_evalview(b->s2, b->op2, b->same_eval ? b->t1 : b->t2, &e2));
+  if (b->aq_rd < 1 || e1.rd % b->aq_rd || e1.rd / b->aq_rd != e2.rd || e1.rd > 9)
+    return fail(GRMP_EINVAL, "Newton convection: operator lengths do not fit (ansatz = ncomponents x xdim, a_operator = xdim, test = ncomponents)");
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  if (!keep_pattern) b->have_pattern = false;
+  b->have_values = false;
+  return GRMP_OK;
+}
+
+int grmp_blf_newton_rhs(grmp_blf* b, double* b_host, int64_t offset) {
+  if (!b || !b_host) return fail(GRMP_EINVAL, "grmp_blf_newton_rhs: NULL argument");
+  if (b->action != GRMP_ACT_NEWTON_CONVECTION) return fail(GRMP_EINVAL, "not a Newton form");
+  if (!b->have_values || !b->rbuf.p) return fail(GRMP_ESTATE, "grmp_blf_newton_rhs needs a prior grmp_blf_numeric");
+  grmp_space* sp = b->s2;
+  grmp_ctx* ctx = sp->grid->ctx;
+  cudaStream_t s = ctx->stream;
+  GRMP_CUDA(cudaSetDevice(ctx->device));
+  if (!b->nl_dg_built) {
+    GRMP_TRY(build_dofgather(s, sp->celldofs.p, sp->grid->ncells, sp->nd, sp->ndofs, &b->nl_dg));
+    b->nl_dg_built = true;
+  }
+  GRMP_TRY(b->rhs.upload(b_host + offset, (size_t)sp->ndofs, s));
+  GRMP_TRY(launch_lf_gather(s, b->nl_dg, b->rbuf.p, b->nl_active.p, b->rhs.p));
+  GRMP_CUDA(cudaMemcpyAsync(b_host + offset, b->rhs.p, (size_t)sp->ndofs * 8, cudaMemcpyDeviceToHost, s));
+  GRMP_CUDA(cudaStreamSynchronize(s));
+  return GRMP_OK;
+}
 
 int grmp_blf_set_fixed_argument(grmp_blf* b, grmp_space* sa, int op_a, const grmp_evaltab* tab_a, const double* coeffs_host, int keep_pattern) {
   if (!b || !sa || !tab_a || !coeffs_host) return fail(GRMP_EINVAL, "grmp_blf_set_fixed_argument: NULL argument");

@@ -152,8 +152,12 @@ struct BlfLocalParams {
   int nq;
   const double* w;     // [nq]
   double factor;
-  const double* aq;    // GRMP_ACT_CONVECTION: a(x_q) of the fixed argument, [ncells][nq][aq_rd]
+  const double* aq;    // GRMP_ACT_CONVECTION / NEWTON_CONVECTION: a(x_q) of the fixed argument, [ncells][nq][aq_rd]
   int aq_rd;
+  EvalView ea;         // NEWTON_CONVECTION: a_operator on the ansatz space (evaluation of the ansatz functions themselves)
+  const double* gq;    //   ansatz operator of the current iterate at the quadrature points, [ncells][nq][e1.rd]
+  double* rbuf;        //   [nd2][ncells] right-hand side contributions (numeric pass) or null
+  unsigned char* active;   // [ncells] region filter result for the right-hand side gather, or null
   i64 nrows_key;       // key = col * nrows_key + row (0-based, output orientation)
   // outputs (exactly one of them non-null)
   u64* keys;           // [ncells*nd1*nd2] : symbolic pass, ~0 for masked-out contributions

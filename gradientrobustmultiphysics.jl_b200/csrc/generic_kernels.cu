@@ -502,12 +502,102 @@ int launch_ii_local(const IiLocalParams& p, cudaStream_t s) {
   return GRMP_OK;
 }
 
+// NonlinearForm full_assemble! for the Newton convection form (nonlinearform.jl:114-233, kernel / jacobian pdeoperators.jl:459-488):
+// one thread per cell, the oracle's (= the reference's) operation order.  in = [a_operator(u), ansatz_operator(u)](x_i) comes from the
+// tables aq / gq; jac in2 runs over the stored columns of the sparse jacobian in ascending order.
+template <int NDMAX>
+__global__ void __launch_bounds__(128) nlf_local_kernel(const BlfLocalParams p) {
+  const i64 cell = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (cell >= p.g.ncells) return;
+  const int nd = p.e1.nd, nloc = nd * nd, edim = p.g.dim;
+  const i64 ncells = p.g.ncells;
+  const bool act = cell_active(p.g, p.reg, cell);
+  if (p.active) p.active[cell] = act ? 1 : 0;
+  if (!act) {
+    if (p.keys)
+      for (int e = 0; e < nloc; e++) p.keys[cell * nloc + e] = ~0ull;
+    return;
+  }
+  Geo T;
+  geo_update(p.g, cell, T);
+  geo_mapderiv(p.g, cell, T);
+  CellCoef<NDMAX> cc;
+  double rcd[1][12];
+  cell_coefficients<NDMAX>(p.g, cell, p.e1.fam, nd, p.e1.ncomp, cc);
+  double loc[NDMAX * NDMAX], lb[NDMAX];
+  for (int e = 0; e < nloc; e++) loc[e] = 0.0;
+  for (int d = 0; d < nd; d++) lb[d] = 0.0;
+  double cvg[RDMAX][NDMAX], cva[RDMAX][NDMAX], cvts[RDMAX][NDMAX];
+  const int xdim = p.aq_rd, gdim = p.e1.rd, nc = p.e2.rd;
+  const bool t_is_a = p.e2.op == p.ea.op, t_is_g = p.e2.op == p.e1.op;
+  double(*cvt)[NDMAX] = t_is_a ? cva : (t_is_g ? cvg : cvts);
+  for (int i = 0; i < p.nq; i++) {
+    eval_qp<NDMAX, false>(p.e1, edim, T, cc, rcd, i, cvg);
+    eval_qp<NDMAX, false>(p.ea, edim, T, cc, rcd, i, cva);
+    if (!t_is_a && !t_is_g) eval_qp<NDMAX, false>(p.e2, edim, T, cc, rcd, i, cvts);
+    const double* a = p.aq + ((size_t)cell * p.nq + i) * xdim;
+    const double* gr = p.gq + ((size_t)cell * p.nq + i) * gdim;
+    const double wi = p.w[i];
+    double value[RDMAX], res[RDMAX];
+    for (int j = 0; j < nc; j++) { double r = 0.0; for (int k = 0; k < xdim; k++) r += a[k] * gr[j * xdim + k]; value[j] = r; }
+    for (int di = 0; di < nd; di++) {
+      for (int j = 0; j < nc; j++) res[j] = 0.0;
+      for (int k = 0; k < xdim; k++)
+        for (int j = 0; j < nc; j++) res[j] += gr[j * xdim + k] * cva[k][di];
+      for (int j = 0; j < nc; j++)
+        for (int k = 0; k < xdim; k++) res[j] += a[k] * cvg[j * xdim + k][di];
+      for (int dj = 0; dj < nd; dj++) {
+        double t = 0.0;
+        for (int k = 0; k < nc; k++) t += res[k] * cvt[k][dj];
+        loc[di * nd + dj] += t * wi;
+      }
+    }
+    for (int j = 0; j < nc; j++) res[j] = 0.0;
+    for (int k = 0; k < xdim; k++)
+      for (int j = 0; j < nc; j++) res[j] += gr[j * xdim + k] * a[k];
+    for (int j = 0; j < nc; j++)
+      for (int k = 0; k < xdim; k++) res[j] += a[k] * gr[j * xdim + k];
+    for (int dj = 0; dj < nd; dj++) {
+      double t = 0.0;
+      for (int k = 0; k < nc; k++) t += (res[k] - value[k]) * cvt[k][dj];
+      lb[dj] += t * wi;
+    }
+  }
+  const double itemfactor = p.g.vol[cell] * p.factor * 1.0;
+  const i32* d1 = p.e1.celldofs + cell * nd;
+  for (int di = 0; di < nd; di++)
+    for (int dj = 0; dj < nd; dj++) {
+      const double l = loc[di * nd + dj];
+      if (p.keys) {
+        u64 key = ~0ull;
+        if (l != 0) {       // _addnz(A, acol, arow, local, itemfactor): the test is on the unscaled entry
+          i64 r = d1[di] - 1, c = d1[dj] - 1;
+          if (p.transposed) { i64 t = r; r = c; c = t; }
+          key = (u64)c * (u64)p.nrows_key + (u64)r;
+        }
+        p.keys[cell * nloc + di * nd + dj] = key;
+      } else {
+        p.lbuf[(i64)(di * nd + dj) * ncells + cell] = l * itemfactor;
+      }
+    }
+  if (p.rbuf)
+    for (int dj = 0; dj < nd; dj++) p.rbuf[(i64)dj * ncells + cell] = lb[dj] * itemfactor;
+}
+
 int launch_blf_local(const BlfLocalParams& p, cudaStream_t s) {
   const int nmax = p.e1.nd > p.e2.nd ? p.e1.nd : p.e2.nd;
   const bool recon = (p.e1.op == GRMP_OP_RECON_ID_RT0 || p.e1.op == GRMP_OP_RECON_ID_BDM1 || p.e2.op == GRMP_OP_RECON_ID_RT0 ||
                       p.e2.op == GRMP_OP_RECON_ID_BDM1);
   if (p.g.ncells == 0) return GRMP_OK;
   const unsigned grid = (unsigned)((p.g.ncells + 127) / 128);
+  if (p.action == GRMP_ACT_NEWTON_CONVECTION) {
+    if (recon || p.e1.fam == FAM_RT0 || p.e1.fam == FAM_BDM1) return fail(GRMP_EUNSUPPORTED, "Newton convection form: H1 spaces only");
+    if (nmax <= 16) nlf_local_kernel<16><<<grid, 128, 0, s>>>(p);
+    else if (nmax <= 30) nlf_local_kernel<30><<<grid, 128, 0, s>>>(p);
+    else return fail(GRMP_EUNSUPPORTED, "more than 30 local dofs per cell");
+    GRMP_CUDA(cudaGetLastError());
+    return GRMP_OK;
+  }
   if (recon) {
     if (nmax > 16) return fail(GRMP_EUNSUPPORTED, "reconstruction operators support at most 16 local dofs");
     blf_local_kernel<16, true><<<grid, 128, 0, s>>>(p);

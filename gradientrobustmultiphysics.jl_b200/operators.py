@@ -12,7 +12,8 @@ from __future__ import annotations
 
 import numpy as np
 
-from .assembly import (APT_BilinearForm, APT_LinearForm, APT_SymmetricBilinearForm, AssemblyPattern, ConvectionAction, DataFunction, Divergence,
+from .assembly import (APT_BilinearForm, APT_LinearForm, APT_NonlinearForm, APT_SymmetricBilinearForm, AssemblyPattern, ConvectionAction,
+                       NewtonConvectionAction, DiscreteNonlinearForm, full_assemble, DataFunction, Divergence,
                        Gradient, HookeAction, Identity, NoAction, SymmetricGradient, _FDotAction, _op, assemble, fdot_action)
 from .fespace import FEMatrixBlock, FEVectorBlock
 
@@ -106,9 +107,17 @@ def ConvectionOperator(a_from: int, a_operator, xdim: int, ncomponents: int, nam
                        test_operator=Identity, regions=(0,), newton=False, store=False, transposed_assembly=True, bonus_quadorder=0):
     """ConvectionOperator(a_from, a_operator, xdim, ncomponents; a_to = 1, ...) (pdeoperators.jl:435-510): the Picard-linearised
     convection term ((a . grad) u, v) as a trilinear form whose first argument is the coefficient function CurrentSolution[a_from]"""
-    if newton or a_to != 1:
-        raise NotImplementedError("ConvectionOperator: the Picard form with the coefficient in position 1 is on the device "
-                                  "(newton = true is a NonlinearForm, SURVEY.md 8f N4)")
+    if newton:      # NonlinearForm(test_operator, [a_operator, ansatz_operator], [a_from, a_from], kernel, argsizes; jacobian) (pdeoperators.jl:481-493)
+        if name == "auto":
+            name = f"(({_op(a_operator)}(#1) . {_op(ansatz_operator)}) #1, {_op(test_operator)}(#T)) [Newton]"
+        O = PDEOperator(APT_NonlinearForm, name, [a_operator, ansatz_operator, test_operator], NewtonConvectionAction(xdim, ncomponents, bonus_quadorder),
+                        [1, 2], factor, regions, store)
+        O.fixed_arguments = [1, 2]
+        O.fixed_arguments_ids = [a_from, a_from]
+        O.transposed_assembly = True
+        return O
+    if a_to != 1:
+        raise NotImplementedError("ConvectionOperator: the coefficient in position 1 (a_to = 1) is on the device")
     if name == "auto":
         name = f"(({_op(a_operator)}(#1) . {_op(ansatz_operator)}) #A, {_op(test_operator)}(#T))"
     O = PDEOperator(APT_BilinearForm, name, [a_operator, ansatz_operator, test_operator], ConvectionAction(xdim, ncomponents, bonus_quadorder),
@@ -117,6 +126,21 @@ def ConvectionOperator(a_from: int, a_operator, xdim: int, ncomponents: int, nam
     O.fixed_arguments_ids = [a_from]
     O.transposed_assembly = transposed_assembly
     return O
+
+
+def full_assemble_operator(A: FEMatrixBlock, b: FEVectorBlock, O: PDEOperator, CurrentSolution, Pattern=None, skip_preps=False):
+    """the NonlinearForm branch of the operator assembly (pdeoperators.jl:1094-1140): full_assemble!(A, b, Pattern, CurrentSolution[ids];
+    factor, transposed_assembly)"""
+    assert O.APT == APT_NonlinearForm
+    fes = CurrentSolution[O.fixed_arguments_ids[0]].FES
+    if Pattern is None:
+        Pattern = getattr(O, "_pattern", None)
+        if Pattern is None or Pattern.FES[0] is not fes:
+            Pattern = DiscreteNonlinearForm(O.operators4arguments, [fes, fes, A.FESX], O.action, name=O.name, regions=O.regions)
+            O._pattern = Pattern
+    full_assemble(A, b, Pattern, [CurrentSolution[O.fixed_arguments_ids[0]]], factor=O.factor, transposed_assembly=O.transposed_assembly,
+                  skip_preps=skip_preps)
+    return Pattern
 
 
 def create_assembly_pattern(O: PDEOperator, target, CurrentSolution=None):

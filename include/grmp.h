@@ -42,7 +42,8 @@ enum { GRMP_FE_H1P1 = 1, GRMP_FE_H1P2 = 2, GRMP_FE_H1BR = 3, GRMP_FE_HDIVRT0 = 4
 enum { GRMP_OP_ID = 1, GRMP_OP_GRAD = 2, GRMP_OP_SYMGRAD = 3, GRMP_OP_DIV = 4, GRMP_OP_RECON_ID_RT0 = 5, GRMP_OP_RECON_ID_BDM1 = 6 };
 /* actions evaluated on the device (src/actions.jl:96-110 NoAction; src/pdeoperators.jl:265-270, 304-312 Hooke tensors) */
 enum { GRMP_ACT_NONE = 0, GRMP_ACT_HOOKE2D = 1, GRMP_ACT_HOOKE3D = 2,
-       GRMP_ACT_CONVECTION = 3 /* needs a fixed argument, see grmp_blf_set_fixed_argument */ };
+       GRMP_ACT_CONVECTION = 3 /* needs a fixed argument, see grmp_blf_set_fixed_argument */,
+       GRMP_ACT_NEWTON_CONVECTION = 4 /* NonlinearForm, see grmp_blf_set_newton_argument */ };
 /* assembly pattern types (src/assemblypatterns/bilinearform.jl:7-21) */
 enum { GRMP_APT_BILINEARFORM = 0, GRMP_APT_SYMMETRIC = 1, GRMP_APT_LUMPED = 2 };
 /* right-hand side data of a LinearForm (fdot_action, src/actions.jl:119-128) */
@@ -148,6 +149,18 @@ int grmp_blf_set_path(grmp_blf* blf, int path);
  * grmp_blf_symbolic afterwards, or pass keep_pattern = 1 to reassemble on the frozen pattern (the next Picard iteration). */
 int grmp_blf_set_fixed_argument(grmp_blf* blf, grmp_space* space_a, int op_a, const grmp_evaltab* tab_a, const double* coeffs_host,
                                 int keep_pattern);
+
+/* NonlinearForm full_assemble!(A, b, AP, FEB) (src/assemblypatterns/nonlinearform.jl:44-245) for the Newton form of the convection term,
+ * ConvectionOperator(a_from, a_operator, xdim, ncomponents; newton = true) (src/pdeoperators.jl:459-493): Jacobian matrix of
+ * N(u) = ((a_operator(u) . ansatz_operator) u, test) at the current iterate and the right-hand side DN(u) u - N(u).
+ * The form is created with grmp_blf_create(space_u, space_u, ansatz_operator, test_operator, GRMP_ACT_NEWTON_CONVECTION, NULL,
+ * GRMP_APT_BILINEARFORM, transposed_assembly = 1, ...) and the rule prepare_assembly! picks for its THREE FESpaces; op_a / tab_a are
+ * a_operator and its evaluator tables on space_u, coeffs_host the entries of the current iterate.  As in the reference the zero test of
+ * _addnz is made on the unscaled local entry (nonlinearform.jl:216-221), so the pattern depends on the iterate: run grmp_blf_symbolic
+ * afterwards, or pass keep_pattern = 1 for the next Newton step on the frozen pattern. */
+int grmp_blf_set_newton_argument(grmp_blf* blf, int op_a, const grmp_evaltab* tab_a, const double* coeffs_host, int keep_pattern);
+/* right-hand side of the last numeric call: b[dof + offset] += localb * itemfactor in cell order (nonlinearform.jl:226-233) */
+int grmp_blf_newton_rhs(grmp_blf* blf, double* b_host, int64_t offset);
 
 /* One-time symbolic pass on the GPU = what rawupdateindex! + flush! build on first
  * assembly (fematrix.jl:54-58, pdeoperators.jl:992): the pattern is the union of local

@@ -481,6 +481,73 @@ function GRMP.assemble!(A::FEMatrixBlock{Float64,Int64,Float64,Int32}, AP::Assem
     return nothing
 end
 
+# ---- NonlinearForm: Newton form of the convection term (SURVEY.md 8f N4) -------------------------------------------------------------
+# full_assemble!(A, b, AP, FEB; factor, transposed_assembly, skip_preps) (nonlinearform.jl:44-245) for the pattern that
+# ConvectionOperator(a_from, a_operator, xdim, ncomponents; newton = true) creates (pdeoperators.jl:459-493): the kernel AND the user
+# jacobian are probed (value[j] = sum_k in[k] in[xdim+(j-1)xdim+k]; jac[j,k] = in[xdim+(j-1)xdim+k], jac[j,xdim+(j-1)xdim+k] = in[k]).
+function is_newton_convection(h, xdim::Int, nc::Int)
+    h isa GRMP.OperatorWithUserJacobian || return false
+    n = xdim + nc * xdim
+    (h.argsizes[1] == nc && h.argsizes[2] == n) || return false
+    x = [cos(0.3 + 0.9 * i) for i = 1:n]
+    GRMP.eval_jacobian!(h, x)
+    J = Matrix(h.jac)
+    for j = 1:nc
+        e = 0.0
+        for k = 1:xdim; e += x[k] * x[xdim+(j-1)*xdim+k]; end
+        h.val[j] == e || return false
+        for c = 1:n
+            expect = c <= xdim ? x[xdim+(j-1)*xdim+c] : (xdim + (j - 1) * xdim < c <= xdim + j * xdim ? x[c-xdim-(j-1)*xdim] : 0.0)
+            J[j, c] == expect || return false
+        end
+    end
+    return true
+end
+
+const NLPATTERNS = WeakKeyDict{Any,DBlf}()
+
+function GRMP.full_assemble!(A::FEMatrixBlock{Float64,Int64,Float64,Int32}, b::FEVectorBlock{Float64,Float64,Int32},
+        AP::AssemblyPattern{APT,Float64,ON_CELLS,Float64,Int32}, FEB::Array{<:FEVectorBlock{Float64,Float64,Int32},1};
+        factor = 1, transposed_assembly::Bool = false, skip_preps::Bool = false) where {APT<:GRMP.APT_NonlinearForm}
+    fallback() = invoke(GRMP.full_assemble!, Tuple{FEMatrixBlock,FEVectorBlock,AssemblyPattern{APT,Float64,ON_CELLS},Array{<:FEVectorBlock{Float64,Float64,Int32},1}},
+                        A, b, AP, FEB; factor, transposed_assembly, skip_preps)
+    (length(AP.FES) == 3 && AP.FES[1] === AP.FES[2] === AP.FES[3] && AP.newton_args == [1, 2] && FEB[1] === FEB[2]) || return fallback()
+    xdim = size(AP.FES[1].xgrid[Coordinates], 1)
+    oa, og, ot = opcode(AP.operators[1]), opcode(AP.operators[2]), opcode(AP.operators[3])
+    (oa === nothing || og === nothing || ot === nothing || fecode(eltype(AP.FES[1])) === nothing) && return fallback()
+    nc = GRMP.Length4Operator(AP.operators[3], xdim, get_ncomponents(eltype(AP.FES[3])))
+    is_newton_convection(AP.action, GRMP.Length4Operator(AP.operators[1], xdim, get_ncomponents(eltype(AP.FES[1]))), nc) || return fallback()
+    skip_preps || GRMP.prepare_assembly!(AP)
+    fresh = !haskey(NLPATTERNS, AP)
+    d = get!(NLPATTERNS, AP) do
+        e1 = GRMP.get_basisevaler(AP.AM, 2, 1); e2 = GRMP.get_basisevaler(AP.AM, 3, 1)
+        v1, d1, t1 = evaltab(e1); v2, d2, t2 = evaltab(e2)
+        w = Vector{Float64}(GRMP.get_qweights(AP.AM))
+        regions = AP.regions == [0] ? Int32[] : Vector{Int32}(AP.regions)
+        su = device_space(AP.FES[1])
+        h = Ref{Ptr{Cvoid}}()
+        GC.@preserve v1 d1 v2 d2 w regions check(ccall((:grmp_blf_create, lib), Cint,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float64}, Cint, Cint, Ptr{Int32}, Cint, Cint, Ptr{Float64}, Ref{EvalTab}, Ref{EvalTab}, Ref{Ptr{Cvoid}}),
+            su.h, su.h, og, ot, 4, C_NULL, 0, transposed_assembly, isempty(regions) ? C_NULL : pointer(regions), length(regions), length(w), w, t1, t2, h))
+        x = DBlf(h[], 0, Int64[], Int64[], Float64(factor), transposed_assembly, (su, su))
+        finalizer(y -> destroy(:grmp_blf_destroy, y), x)
+        x
+    end
+    ea = GRMP.get_basisevaler(AP.AM, 1, 1)
+    va, da, ta = evaltab(ea)
+    coeffs = FEB[1].entries[FEB[1].offset+1:FEB[1].last_index]
+    keep = skip_preps && !fresh
+    GC.@preserve va da coeffs check(ccall((:grmp_blf_set_newton_argument, lib), Cint, (Ptr{Cvoid}, Cint, Ref{EvalTab}, Ptr{Float64}, Cint), d.h, oa, ta, coeffs, keep))
+    keep || symbolic!(d, A, Float64(factor))
+    nzval = Vector{Float64}(undef, d.nnz)
+    check(ccall((:grmp_blf_numeric, lib), Cint, (Ptr{Cvoid}, Float64, Ptr{Float64}), d.h, Float64(factor), nzval))
+    install_block!(A, SparseMatrixCSC(size(A, 1), size(A, 2), d.colptr, d.rowval, nzval))
+    entries = b.entries
+    GC.@preserve entries check(ccall((:grmp_blf_newton_rhs, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), d.h, entries, b.offset))
+    AP.last_allocations = 0
+    return nothing
+end
+
 # ---- ItemIntegrator (src/assemblypatterns/itemintegrator.jl:160-360), one argument -------------------------------------------------
 # The library evaluates NoAction and the kernels of L2NormIntegrator / L2ErrorIntegrator; an ItemIntegrator carries them as opaque
 # closures, so the device versions are constructed explicitly:

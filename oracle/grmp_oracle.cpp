@@ -953,6 +953,85 @@ int orc_blf_assemble(void* Aptr, const orc_grid* og, const orc_space* os1, const
   return 0;
 }
 
+// ---- NonlinearForm full_assemble! (src/assemblypatterns/nonlinearform.jl:44-245) for the Newton form of the convection term:
+// ConvectionOperator(a_from, a_operator, xdim, ncomponents; newton = true) = NonlinearForm(test_operator, [a_operator, ansatz_operator],
+// [a_from, a_from], convection_function_fe_1, argsizes; jacobian = convection_jacobian) (pdeoperators.jl:459-493): all three FESpaces are the
+// space of the unknown u, operators [op_a (Identity), op_g (Gradient), op_t (test)], newton_args = [1, 2].
+//   input_i = [op_a(u)(x_i), op_g(u)(x_i)] (eval_febe! from 0 in dof order, 124-141);
+//   value[j] = sum_k input[k] input[xdim + (j-1) xdim + k];  jac[j,k] = input[xdim + (j-1) xdim + k], jac[j, xdim + (j-1) xdim + k] = input[k]
+//   (sparse jacobian: mul! runs over the stored columns in ascending order, plain multiply and add);
+//   matrix: for every ansatz dof: input2 = [op_a(phi_dof), op_g(phi_dof)], result = jac input2, local[dof_i,dof_j] += (result . op_t(v_dof_j)) w_i (167-187);
+//   rhs:    result = jac input_i, localb[dof_j] += ((result - value) . op_t(v_dof_j)) w_i (189-201);
+//   _addnz(A, acol, arow, local, itemfactor) -- the zero test is on the UNSCALED local entry (216-221); localb .*= itemfactor; b += localb (226-233).
+int orc_nlf_convection(void* Aptr, double* b, const orc_grid* og, const orc_space* os, int op_a, int op_g, int op_t, const double* coeffs,
+                       const i32* regions, int nregions, double factor, int transposed_assembly, i64 offsetX, i64 offsetY, int bonus_quadorder) {
+  ExtSparse* A = (ExtSparse*)Aptr;
+  Grid g = to_grid(og); Space s = to_space(os);
+  const int edim = g.dim;
+  int quadorder = bonus_quadorder + 3 * polyorder_of(s, edim) + quadorder_shift(op_a) + quadorder_shift(op_g) + quadorder_shift(op_t);
+  if (quadorder < 0) quadorder = 0;
+  QRule q; if (!make_qrule(edim, quadorder, q)) return -1;
+  Evaluator ea, eg, etst; Evaluator* et = &etst;
+  if (!ea.init(&g, s, op_a, q) || !eg.init(&g, s, op_g, q)) return -1;
+  if (op_t == op_a) et = &ea; else if (op_t == op_g) et = &eg; else if (!etst.init(&g, s, op_t, q)) return -1;   // evaluator reuse (assemblypatterns.jl:567-584)
+  const int nd = ea.nd, nq = q.n(), xdim = ea.resultdim, gdim = eg.resultdim;
+  if (xdim < 1 || gdim % xdim) { g_err = "convection: operator lengths do not fit"; return -1; }
+  const int nc = gdim / xdim;
+  if (et->resultdim != nc) { g_err = "convection: test operator length"; return -1; }
+  const int nin = xdim + gdim;
+  std::vector<double> input((size_t)nq * nin), in2(nin), res(nc), value(nc), local((size_t)nd * nd, 0.0), localb(nd, 0.0), c(nd);
+  auto jacmul = [&](const double* in, const double* x, double* y) {     // y = jac(in) x, stored columns ascending
+    for (int j = 0; j < nc; j++) y[j] = 0.0;
+    for (int k = 0; k < xdim; k++)
+      for (int j = 0; j < nc; j++) y[j] += in[xdim + j * xdim + k] * x[k];
+    for (int j = 0; j < nc; j++)
+      for (int k = 0; k < xdim; k++) y[j] += in[k] * x[xdim + j * xdim + k];
+  };
+  for (i64 item = 0; item < g.ncells; item++) {
+    if (!in_regions(g, item, regions, nregions)) continue;
+    ea.update(item); eg.update(item); if (et != &ea && et != &eg) et->update(item);
+    const i32* dofs = s.celldofs + item * nd;
+    for (int d = 0; d < nd; d++) c[d] = coeffs[dofs[d] - 1] * 1.0;
+    std::fill(input.begin(), input.end(), 0.0);
+    for (int i = 0; i < nq; i++) {
+      double* in = &input[(size_t)i * nin];
+      for (int d = 0; d < nd; d++) for (int k = 0; k < xdim; k++) in[k] += c[d] * ea.cv(k, d, i) * 1;
+      for (int d = 0; d < nd; d++) for (int k = 0; k < gdim; k++) in[xdim + k] += c[d] * eg.cv(k, d, i) * 1;
+    }
+    for (int i = 0; i < nq; i++) {
+      const double* in = &input[(size_t)i * nin];
+      for (int j = 0; j < nc; j++) { double r = 0; for (int k = 0; k < xdim; k++) r += in[k] * in[xdim + j * xdim + k]; value[j] = r; }
+      for (int di = 0; di < nd; di++) {
+        for (int k = 0; k < xdim; k++) in2[k] = ea.cv(k, di, i) * 1;
+        for (int k = 0; k < gdim; k++) in2[xdim + k] = eg.cv(k, di, i) * 1;
+        jacmul(in, in2.data(), res.data());
+        for (int dj = 0; dj < nd; dj++) {
+          double t = 0; for (int k = 0; k < nc; k++) t += res[k] * et->cv(k, dj, i);
+          local[(size_t)di * nd + dj] += t * q.w[i];
+        }
+      }
+      for (int dj = 0; dj < nd; dj++) {
+        jacmul(in, in, res.data());
+        double t = 0; for (int k = 0; k < nc; k++) t += (res[k] - value[k]) * et->cv(k, dj, i);
+        localb[dj] += t * q.w[i];
+      }
+    }
+    const double itemfactor = g.vol[item] * factor * 1.0;
+    for (int di = 0; di < nd; di++) {
+      const i64 arow = dofs[di] + offsetY;
+      for (int dj = 0; dj < nd; dj++) {
+        const i64 acol = dofs[dj] + offsetX;
+        const double v = local[(size_t)di * nd + dj];
+        if (transposed_assembly) addnz(A, acol, arow, v, itemfactor); else addnz(A, arow, acol, v, itemfactor);
+      }
+    }
+    std::fill(local.begin(), local.end(), 0.0);
+    if (b) for (int dj = 0; dj < nd; dj++) { localb[dj] *= itemfactor; b[dofs[dj] - 1 + offsetX] += localb[dj]; }
+    std::fill(localb.begin(), localb.end(), 0.0);
+  }
+  return 0;
+}
+
 // ---- LinearForm assemble! (src/assemblypatterns/linearform.jl:47-237), nFE == 1 ------
 // fsrc: F_NONE -> no action (action_input = ones, 74-75); F_CONST -> fdata[resultdim];
 // F_QP_TABLE -> fdata[cell][qp][resultdim] (fdot_action evaluated by the host, actions.jl:119-128)

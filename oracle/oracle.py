@@ -63,6 +63,8 @@ def lib():
                                          C.c_void_p, C.c_int, C.c_double, C.c_int64, C.c_int, C.c_void_p]
         _LIB.orc_ii_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_Grid), C.POINTER(_Space), C.c_int, C.c_int, C.c_void_p,
                                          C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        _LIB.orc_nlf_convection.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_Grid), C.POINTER(_Space), C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                            C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int64, C.c_int64, C.c_int]
         _LIB.orc_feb_table.argtypes = [C.POINTER(_Grid), C.POINTER(_Space), C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB.orc_set_fixed_argument.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _LIB.orc_quadpoints.argtypes = [C.POINTER(_Grid), C.c_int, C.c_void_p]
@@ -248,6 +250,18 @@ def ii_evaluate(grid, space, op, coeffs, *, kind=II_NONE, factor=1.0, data=None,
     _check(lib().orc_ii_evaluate(_p(b), _p(total), C.byref(g.s), C.byref(s.s), op, kind, _p(c), float(factor), _p(d), _p(rg), rg.size,
                                  bonus_quadorder, None, None))
     return b, total
+
+
+def nlf_convection(A: OracleMatrix, b, grid, space, coeffs, *, op_a=OP_ID, op_g=OP_GRAD, op_t=OP_ID, regions=(0,), factor=1.0,
+                   transposed_assembly=True, offsetX=0, offsetY=0, bonus_quadorder=0):
+    """full_assemble!(A, b, AP, FEB) of the Newton convection form (nonlinearform.jl:44-245, pdeoperators.jl:459-493)"""
+    g = _grid_struct(grid, _needs_faces(space))
+    s = _space_struct(space)
+    c = np.ascontiguousarray(coeffs, dtype=np.float64)
+    rg = np.ascontiguousarray(regions, dtype=np.int32)
+    assert b is None or (b.dtype == np.float64 and b.flags.c_contiguous)
+    _check(lib().orc_nlf_convection(A.h, _p(b), C.byref(g.s), C.byref(s.s), op_a, op_g, op_t, _p(c), _p(rg), rg.size, float(factor),
+                                    int(transposed_assembly), offsetX, offsetY, bonus_quadorder))
 
 
 def feb_table(grid, space, op, coeffs, order):

@@ -118,3 +118,47 @@ def test_linearform_with_coefficient_argument(case, path):
         assert np.array_equal(got, ob), f"max abs diff {np.abs(got - ob).max():.3e}"
     else:
         assert np.abs(got - ob).max() <= 1e-12 * np.abs(ob - 0.5).max()
+
+
+NLF_CASES = [
+    ("P2 tri", 2, 2, True, lambda d: G.H1P2(d, d)),
+    ("P1 tri axis aligned", 2, 3, False, lambda d: G.H1P1(d)),
+    ("BR tri", 2, 2, True, lambda d: G.H1BR(d)),
+    ("P2 tet", 3, 1, True, lambda d: G.H1P2(d, d)),
+]
+
+
+@pytest.mark.parametrize("case", NLF_CASES, ids=[c[0] for c in NLF_CASES])
+def test_newton_convection_form_parity(case):
+    """full_assemble!(A, b, AP, FEB) of ConvectionOperator(...; newton = true) (nonlinearform.jl:44-245): Jacobian matrix and right-hand
+    side bit-identical to the oracle's restatement (which follows the reference's sparse-jacobian mul! order; a dense jacobian would go
+    through BLAS gemv, whose rounding is build dependent -- 1e-12 is the meaningful bar against the reference itself)"""
+    _, dim, L, pert, fe = case
+    g = grid(dim, L, pert)
+    sv = G.FESpace(fe(dim), g)
+    sol = G.FEVector([sv])
+    sol.entries[:] = np.random.default_rng(21).standard_normal(sv.ndofs)
+    A = G.FEMatrix([sv])
+    b = G.FEVector([sv])
+    b.entries[:] = 0.25
+    Op = G.ConvectionOperator(1, G.Identity, dim, dim, newton=True, factor=1.25)
+    AP = G.full_assemble_operator(A[1, 1], b[1], Op, sol)
+    assert G.blf_stats(AP).path == G._lib.PATH_GENERIC
+    cp, rv, nz = AP.AM.colptr, AP.AM.rowval, G.fetch_values(AP)
+    qo = G.quadrature_order(AP)
+    P = AP.AM
+    O.qrule_override(dim, qo, P.qf.xref, P.qf.w)
+    try:
+        OA = O.OracleMatrix(sv.ndofs, sv.ndofs)
+        ob = np.full(sv.ndofs, 0.25)
+        O.nlf_convection(OA, ob, g, sv, sol.entries, factor=1.25)
+        ocp, orv, onz = OA.csc()
+    finally:
+        O.qrule_override(dim, qo)
+    assert np.array_equal(cp, ocp) and np.array_equal(rv, orv), "pattern differs"
+    assert np.array_equal(nz, onz), f"jacobian not bit-identical, max abs diff {np.abs(nz - onz).max():.3e}"
+    assert np.array_equal(b.entries, ob), f"rhs not bit-identical, max abs diff {np.abs(b.entries - ob).max():.3e}"
+    # Newton identity on the device result: A u = 2 (b - 0.25)
+    import scipy.sparse as sp_
+    M = sp_.csc_matrix((nz, rv - 1, cp - 1), shape=(sv.ndofs, sv.ndofs))
+    assert np.abs(M @ sol.entries - 2 * (b.entries - 0.25)).max() < 1e-10 * np.abs(b.entries - 0.25).max()

@@ -345,3 +345,27 @@ def test_convection_trilinear_form_of_polynomials(dim):
     A0 = O.OracleMatrix(sv.ndofs, sv.ndofs)
     O.blf_assemble(A0, g, sv, sv, O.OP_GRAD, O.OP_ID, action=O.ACT_CONVECTION, transposed_assembly=True, fixed=(sv, O.OP_ID, 0.0 * a))
     assert A0.csc()[1].size == 0
+
+
+# ---- NonlinearForm: Newton form of the convection term (nonlinearform.jl:44-245, pdeoperators.jl:459-493) ----------------------
+@pytest.mark.parametrize("dim", [2, 3])
+def test_newton_convection_form_identities(dim):
+    """N(u) = ((u . grad) u, v) is quadratic: DN(u) u = 2 N(u), so the assembled pair satisfies A u = 2 b with b = DN(u) u - N(u) = N(u);
+    N(u) equals the Picard form with a = u applied to u; and for u = (x, -y[, 0]) the rhs is the load vector of (x, y[, 0])"""
+    g = G.perturb_interior_nodes(tri_grid(2) if dim == 2 else tet_grid(1))
+    sv = G.FESpace(G.H1P2(dim, dim), g)
+    u = nodal_interpolate(sv, (lambda p: [p[0], -p[1]]) if dim == 2 else (lambda p: [p[0], -p[1], 0.0]))
+    V = nodal_interpolate(sv, lambda p: [1.0] * dim)
+    A = O.OracleMatrix(sv.ndofs, sv.ndofs)
+    b = np.zeros(sv.ndofs)
+    O.nlf_convection(A, b, g, sv, u)
+    assert abs(V @ b - 1.0) < TOL                      # int x + y over the unit square / cube
+    assert np.abs(A.toscipy() @ u - 2 * b).max() < TOL
+    w = np.random.default_rng(3).standard_normal(sv.ndofs)
+    A2 = O.OracleMatrix(sv.ndofs, sv.ndofs)
+    b2 = np.zeros(sv.ndofs)
+    O.nlf_convection(A2, b2, g, sv, w, factor=0.5)
+    assert np.abs(A2.toscipy() @ w - 2 * b2).max() < 1e-11 * np.abs(b2).max()
+    AP = O.OracleMatrix(sv.ndofs, sv.ndofs)
+    O.blf_assemble(AP, g, sv, sv, O.OP_GRAD, O.OP_ID, action=O.ACT_CONVECTION, transposed_assembly=True, factor=0.5, fixed=(sv, O.OP_ID, w))
+    assert np.abs(AP.toscipy() @ w - b2).max() < 1e-11 * np.abs(b2).max()
