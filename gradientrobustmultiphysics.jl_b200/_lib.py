@@ -18,7 +18,7 @@ PATH_AUTO, PATH_GENERIC, PATH_FAST, PATH_P2TET, PATH_COLUMNS, PATH_ATOMIC, PATH_
 PATH_NAMES = {1: "generic", 2: "p2tet", 3: "columns", 4: "atomic", 5: "coloured"}
 
 EXPORTS = [
-    "grmp_last_error", "grmp_init", "grmp_finalize", "grmp_device_synchronize", "grmp_grid_create", "grmp_grid_set_faces",
+    "grmp_last_error", "grmp_init", "grmp_finalize", "grmp_device_synchronize", "grmp_grid_create", "grmp_grid_create_bfaces", "grmp_grid_set_faces",
     "grmp_grid_update_geometry", "grmp_grid_update_cells", "grmp_grid_destroy", "grmp_space_update_dofs",
     "grmp_blf_numeric_steps", "grmp_blf_set_owned_columns", "grmp_space_create", "grmp_space_destroy", "grmp_blf_create",
     "grmp_blf_destroy", "grmp_blf_set_path", "grmp_blf_symbolic", "grmp_blf_get_pattern", "grmp_blf_numeric",
@@ -70,6 +70,7 @@ def lib():
         L.grmp_finalize.argtypes = [vp]
         L.grmp_device_synchronize.argtypes = [vp]
         L.grmp_grid_create.argtypes = [vp, i32, i64, vp, i64, vp, vp, vp, C.POINTER(vp)]
+        L.grmp_grid_create_bfaces.argtypes = [vp, i32, i64, vp, i64, vp, vp, vp, C.POINTER(vp)]
         L.grmp_grid_set_faces.argtypes = [vp, i64, vp, vp, vp, vp, vp]
         L.grmp_grid_update_geometry.argtypes = [vp, vp, vp]
         L.grmp_grid_destroy.argtypes = [vp]

@@ -190,8 +190,12 @@ def device_grid(xgrid, need_faces=False):
     if d is None:
         h = C.c_void_p()
         vol = np.ascontiguousarray(xgrid.cellvolumes)
-        _lib.check(L.grmp_grid_create(_lib.context(), xgrid.dim, xgrid.nnodes, _lib.ptr(xgrid.coords), xgrid.ncells,
-                                      _lib.ptr(xgrid.cellnodes), _lib.ptr(vol), _lib.ptr(xgrid.cellregions), C.byref(h)))
+        if getattr(xgrid, "embedded", False):      # ON_BFACES: BFaceNodes / BFaceVolumes / BFaceRegions as the items
+            _lib.check(L.grmp_grid_create_bfaces(_lib.context(), xgrid.xdim, xgrid.nnodes, _lib.ptr(xgrid.coords), xgrid.ncells,
+                                                 _lib.ptr(xgrid.cellnodes), _lib.ptr(vol), _lib.ptr(xgrid.cellregions), C.byref(h)))
+        else:
+            _lib.check(L.grmp_grid_create(_lib.context(), xgrid.dim, xgrid.nnodes, _lib.ptr(xgrid.coords), xgrid.ncells,
+                                          _lib.ptr(xgrid.cellnodes), _lib.ptr(vol), _lib.ptr(xgrid.cellregions), C.byref(h)))
         d = {"h": h, "faces": False}
         xgrid._dev = d
         weakref.finalize(xgrid, _release, "grmp_grid_destroy", h)
@@ -203,7 +207,7 @@ def device_grid(xgrid, need_faces=False):
     return d["h"]
 
 
-def device_space(FES: FESpace):
+def device_space(FES):
     need_faces = FES.fetype.code in (3, 4, 5)
     gh = device_grid(FES.xgrid, need_faces)
     d = getattr(FES, "_dev", None)
@@ -223,23 +227,31 @@ APT_BilinearForm, APT_SymmetricBilinearForm, APT_LumpedBilinearForm, APT_LinearF
 
 
 class AssemblyPattern:
-    """AssemblyPattern{APT,T,AT} (assemblypatterns.jl:312-326), AT = ON_CELLS only"""
+    """AssemblyPattern{APT,T,AT} (assemblypatterns.jl:312-326), AT = ON_CELLS, or ON_BFACES for Identity forms of H1P1 / H1P2"""
 
-    def __init__(self, APT, name, FES, operators, action, apply_action_to, regions):
-        self.APT, self.name, self.FES = APT, name, list(FES)
+    def __init__(self, APT, name, FES, operators, action, apply_action_to, regions, AT="ON_CELLS"):
+        if AT not in ("ON_CELLS", "ON_BFACES"):
+            raise NotImplementedError(f"assembly type {AT}: ON_CELLS and ON_BFACES are on the device")
+        self.APT, self.name, self.FES, self.AT = APT, name, list(FES), AT
         self.operators = [_op(o) for o in operators]
         self.action, self.apply_action_to, self.regions = action, apply_action_to, list(regions)
         self.last_allocations = 0
         self.AM = None                      # prepared state (quadrature, tables, device handle)
         self.fixed = None                   # (FESpace, operator) of the coefficient argument of a trilinear form (FES[1] of nFE = 3)
 
+    def item_space(self, i):
+        """the space as the item loop sees it: ItemDofs = Dofmap4AssemblyType(FES, AT) (assemblypatterns.jl:414-420)"""
+        F = self.FES[i]
+        return F.on_bfaces() if self.AT == "ON_BFACES" else F
+
     def __repr__(self):
         return f"AssemblyPattern({self.name}, {self.FES}, {self.operators})"
 
 
-def DiscreteBilinearForm(operators, FES, action=None, name="BLF", regions=(0,), apply_action_to=(1,)):
+def DiscreteBilinearForm(operators, FES, action=None, name="BLF", regions=(0,), apply_action_to=(1,), AT="ON_CELLS"):
     assert len(operators) == len(FES), "each FESpace needs an operator and vice versa"
     if len(FES) == 3:
+        assert AT == "ON_CELLS"
         # trilinear form with one coefficient argument: FES = [FES_a, FES_ansatz, FES_test] (bilinearform.jl:60-64, 235-257)
         if not isinstance(action, ConvectionAction):
             raise NotImplementedError("trilinear forms: the convection kernel runs on the device; other actions are user closures")
@@ -248,17 +260,17 @@ def DiscreteBilinearForm(operators, FES, action=None, name="BLF", regions=(0,), 
         return AP
     assert len(FES) == 2, "bilinear forms take two FESpaces (+ one coefficient argument)"
     assert list(apply_action_to) == [1], "the ported path applies the action to argument 1 (all operators on the path do)"
-    return AssemblyPattern(APT_BilinearForm, name, FES, operators, action or NoAction(), [1], regions)
+    return AssemblyPattern(APT_BilinearForm, name, FES, operators, action or NoAction(), [1], regions, AT)
 
 
-def DiscreteSymmetricBilinearForm(operators, FES, action=None, name="symBLF", regions=(0,), apply_action_to=(1,)):
+def DiscreteSymmetricBilinearForm(operators, FES, action=None, name="symBLF", regions=(0,), apply_action_to=(1,), AT="ON_CELLS"):
     assert len(operators) == len(FES) == 2, "each FESpace needs an operator and vice versa"
-    return AssemblyPattern(APT_SymmetricBilinearForm, name, FES, operators, action or NoAction(), [1], regions)
+    return AssemblyPattern(APT_SymmetricBilinearForm, name, FES, operators, action or NoAction(), [1], regions, AT)
 
 
-def DiscreteLumpedBilinearForm(operators, FES, action=None, name="lumpedBLF", regions=(0,), apply_action_to=(1,)):
+def DiscreteLumpedBilinearForm(operators, FES, action=None, name="lumpedBLF", regions=(0,), apply_action_to=(1,), AT="ON_CELLS"):
     assert len(operators) == len(FES) == 2, "each FESpace needs an operator and vice versa"
-    return AssemblyPattern(APT_LumpedBilinearForm, name, FES, operators, action or NoAction(), [1], regions)
+    return AssemblyPattern(APT_LumpedBilinearForm, name, FES, operators, action or NoAction(), [1], regions, AT)
 
 
 def DiscreteNonlinearForm(operators, FES, action, name="NLF", regions=(0,)):
@@ -294,9 +306,10 @@ def full_assemble(A, b, AP: AssemblyPattern, FEB, factor=1, transposed_assembly=
     return None
 
 
-def DiscreteLinearForm(operators, FES, action=None, name="LF", regions=(0,)):
+def DiscreteLinearForm(operators, FES, action=None, name="LF", regions=(0,), AT="ON_CELLS"):
     assert len(operators) == len(FES), "each FESpace needs an operator and vice versa"
     if len(FES) == 2:
+        assert AT == "ON_CELLS"
         # one coefficient argument, NoAction: FES = [FES_a, FES_test] (linearform.jl:29-33, 130-178)
         if action is not None and not isinstance(action, NoAction):
             raise NotImplementedError("LinearForms with a coefficient argument: NoAction runs on the device, user actions stay with the reference")
@@ -305,14 +318,14 @@ def DiscreteLinearForm(operators, FES, action=None, name="LF", regions=(0,)):
         return AP
     if len(FES) != 1:
         raise NotImplementedError("LinearForms with several coefficient arguments are a 'next' row (SURVEY.md 8f N4)")
-    return AssemblyPattern(APT_LinearForm, name, FES, operators, action or NoAction(), [1], regions)
+    return AssemblyPattern(APT_LinearForm, name, FES, operators, action or NoAction(), [1], regions, AT)
 
 
 def _geometry(xgrid):
-    return "Triangle2D" if xgrid.dim == 2 else "Tetrahedron3D"
+    return {1: "Edge1D", 2: "Triangle2D", 3: "Tetrahedron3D"}[xgrid.dim]
 
 
-def _tables(FES: FESpace, op, qf):
+def _tables(FES, op, qf):
     """reference tables of FEEvaluator(FES, op, qf) as a grmp_evaltab (+ arrays kept alive)"""
     edim = FES.xgrid.dim
     fe = op.FETypeReconst if isinstance(op, ReconstructionIdentity) else FES.fetype
@@ -335,7 +348,7 @@ class _Prepared:
 
 def quadrature_order(AP: AssemblyPattern):
     """assemblypatterns.jl:559-565"""
-    edim = AP.FES[0].xgrid.dim
+    edim = AP.item_space(0).xgrid.dim
     q = AP.action.bonus_quadorder
     for F, o in zip(AP.FES, AP.operators):
         q += F.fetype.polynomialorder(edim) - o.needed_derivative
@@ -348,7 +361,7 @@ def prepare_assembly(AP: AssemblyPattern, transposed_assembly=False):
     """prepare_assembly!(AP): quadrature rule, evaluator tables, device-side pattern object"""
     L = _lib.lib()
     P = _Prepared()
-    xgrid = AP.FES[0].xgrid
+    xgrid = AP.item_space(0).xgrid
     P.quadorder = quadrature_order(AP)
     P.qf = QuadratureRule(_geometry(xgrid), P.quadorder)
     P.keep = []
@@ -363,8 +376,8 @@ def prepare_assembly(AP: AssemblyPattern, transposed_assembly=False):
                                     C.byref(tab), C.byref(h)))
         P.kind = "ii"
     elif AP.APT == APT_LinearForm:
-        sp = device_space(AP.FES[0])
-        tab, keep = _tables(AP.FES[0], AP.operators[0], P.qf)
+        sp = device_space(AP.item_space(0))
+        tab, keep = _tables(AP.item_space(0), AP.operators[0], P.qf)
         P.keep.append(keep)
         _lib.check(L.grmp_lf_create(sp, AP.operators[0].code, _lib.ptr(regions), regions.size, len(P.qf), _lib.ptr(w), C.byref(tab),
                                     C.byref(h)))
@@ -372,9 +385,9 @@ def prepare_assembly(AP: AssemblyPattern, transposed_assembly=False):
         if DEFAULT_PATH != _lib.PATH_AUTO:
             _lib.check(L.grmp_lf_set_path(h, _lib.PATH_GENERIC if DEFAULT_PATH == _lib.PATH_GENERIC else _lib.PATH_COLUMNS))
     else:
-        s1, s2 = device_space(AP.FES[0]), device_space(AP.FES[1])
-        t1, k1 = _tables(AP.FES[0], AP.operators[0], P.qf)
-        t2, k2 = _tables(AP.FES[1], AP.operators[1], P.qf)
+        s1, s2 = device_space(AP.item_space(0)), device_space(AP.item_space(1))
+        t1, k1 = _tables(AP.item_space(0), AP.operators[0], P.qf)
+        t2, k2 = _tables(AP.item_space(1), AP.operators[1], P.qf)
         P.keep += [k1, k2]
         act = AP.action
         if not isinstance(act, (NoAction, HookeAction, ConvectionAction, NewtonConvectionAction)):
@@ -524,7 +537,7 @@ def assemble(target, AP: AssemblyPattern, FEB=(), factor=1, factor_transpose=Non
 def _qp_table(AP, P):
     """host evaluation of the DataFunction at x = b + A*xref (eval_trafo!, linearform.jl:197-201)"""
     data = AP.action.data
-    g = AP.FES[0].xgrid
+    g = AP.item_space(0).xgrid
     if data.constant is not None:
         return 1, data.constant
     x = g.coords
@@ -534,7 +547,7 @@ def _qp_table(AP, P):
     for j in range(g.dim):
         Aj = x[cn[:, j + 1]] - b                     # column j of A
         xq += Aj[:, None, :] * P.qf.xref[None, :, j, None]
-    flat = xq.reshape(-1, g.dim)
+    flat = xq.reshape(-1, x.shape[1])
     try:
         vals = np.asarray(data.kernel(flat.T), dtype=np.float64)       # vectorised: f(x[dim, npts]) -> [ncomp, npts]
         vals = vals.reshape(-1, flat.shape[0]).T

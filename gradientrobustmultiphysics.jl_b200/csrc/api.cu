@@ -38,7 +38,7 @@ static int fe_family(int fetype) {
 }
 
 static int fe_local_dofs(int fetype, int ncomp, int edim, int* nd, int* nd_all, int* ncomp_eff) {
-  const int nn = edim + 1, nf = edim + 1, ne = (edim == 2) ? 3 : 6;
+  const int nn = edim + 1, nf = edim + 1, ne = (edim == 1) ? 1 : (edim == 2) ? 3 : 6;   // Edge1D: the interior dof takes the edge slot ("N1I1")
   *ncomp_eff = ncomp;
   switch (fetype) {
     case GRMP_FE_H1P1: *nd = *nd_all = nn * ncomp; return GRMP_OK;
@@ -61,6 +61,8 @@ int make_evalview(const grmp_space* sp, int op, const EvalTables& tab, EvalView*
   e.rd = op_resultdim(op, nc, edim);
   if (e.rd < 0) return fail(GRMP_EUNSUPPORTED, "unknown operator code");
   if (e.rd > 9) return fail(GRMP_EUNSUPPORTED, "operator result dimension > 9");
+  if (sp->grid->xdim != edim && !(e.fam == FAM_H1 && op == GRMP_OP_ID))
+    return fail(GRMP_EUNSUPPORTED, "boundary-face grids: Identity of H1P1 / H1P2 / L2P0 only");
   const bool hdiv = (e.fam == FAM_RT0 || e.fam == FAM_BDM1);
   if (hdiv && !(op == GRMP_OP_ID || op == GRMP_OP_DIV)) return fail(GRMP_EUNSUPPORTED, "Hdiv elements: Identity / Divergence only");
   if (sp->fetype == GRMP_FE_L2P0 && op != GRMP_OP_ID) return fail(GRMP_EUNSUPPORTED, "L2P0: Identity only");
@@ -112,7 +114,7 @@ using namespace grmp;
 
 GridView grmp_grid::view() const {
   GridView v{};
-  v.dim = dim; v.nnodes = nnodes; v.ncells = ncells; v.nfaces = nfaces;
+  v.dim = dim; v.xdim = xdim; v.nnodes = nnodes; v.ncells = ncells; v.nfaces = nfaces;
   v.coords = coords.p; v.cellnodes = cellnodes.p; v.vol = vol.p; v.regions = has_regions ? regions.p : nullptr;
   v.cellfaces = cellfaces.p; v.signs = signs.p; v.orient = orient.p; v.fnormals = fnormals.p; v.fvol = fvol.p;
   return v;
@@ -295,7 +297,7 @@ int grmp_grid_create(grmp_ctx* ctx, int dim, int64_t nnodes, const double* coord
   if (nnodes < 0 || ncells < 0) return fail(GRMP_EINVAL, "negative size");
   GRMP_CUDA(cudaSetDevice(ctx->device));
   grmp_grid* g = new grmp_grid();
-  g->ctx = ctx; g->dim = dim; g->nnodes = nnodes; g->ncells = ncells; g->nfaces = 0;
+  g->ctx = ctx; g->dim = dim; g->xdim = dim; g->nnodes = nnodes; g->ncells = ncells; g->nfaces = 0;
   int rc = g->coords.upload(coords, (size_t)nnodes * dim, ctx->stream);
   if (!rc) rc = g->cellnodes.upload(cellnodes, (size_t)ncells * (dim + 1), ctx->stream);
   if (!rc) rc = g->vol.upload(cellvolumes, (size_t)ncells, ctx->stream);
@@ -306,9 +308,30 @@ int grmp_grid_create(grmp_ctx* ctx, int dim, int64_t nnodes, const double* coord
   return GRMP_OK;
 }
 
+// ON_BFACES assembly (src/assemblypatterns.jl:400-440 with AT = ON_BFACES; boundarydata.jl:297-347): the boundary faces as items
+int grmp_grid_create_bfaces(grmp_ctx* ctx, int xdim, int64_t nnodes, const double* coords, int64_t nbfaces, const int32_t* bfacenodes,
+                            const double* bfacevolumes, const int32_t* bfaceregions, grmp_grid** out) {
+  if (!ctx || !out || !coords || !bfacenodes || !bfacevolumes) return fail(GRMP_EINVAL, "grmp_grid_create_bfaces: NULL argument");
+  if (xdim != 2 && xdim != 3) return fail(GRMP_EUNSUPPORTED, "boundary faces of Triangle2D / Tetrahedron3D grids only");
+  if (nnodes < 0 || nbfaces < 0) return fail(GRMP_EINVAL, "negative size");
+  GRMP_CUDA(cudaSetDevice(ctx->device));
+  grmp_grid* g = new grmp_grid();
+  const int edim = xdim - 1;
+  g->ctx = ctx; g->dim = edim; g->xdim = xdim; g->nnodes = nnodes; g->ncells = nbfaces; g->nfaces = 0;
+  int rc = g->coords.upload(coords, (size_t)nnodes * xdim, ctx->stream);
+  if (!rc) rc = g->cellnodes.upload(bfacenodes, (size_t)nbfaces * (edim + 1), ctx->stream);
+  if (!rc) rc = g->vol.upload(bfacevolumes, (size_t)nbfaces, ctx->stream);
+  if (!rc && bfaceregions) { rc = g->regions.upload(bfaceregions, (size_t)nbfaces, ctx->stream); g->has_regions = true; }
+  if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(GRMP_ECUDA, "upload failed");
+  if (rc) { delete g; return rc; }
+  *out = g;
+  return GRMP_OK;
+}
+
 int grmp_grid_set_faces(grmp_grid* g, int64_t nfaces, const int32_t* cellfaces, const int32_t* cellfacesigns,
                         const int32_t* cellfaceorient, const double* facenormals, const double* facevolumes) {
   if (!g || !cellfaces || !cellfacesigns || !facenormals || !facevolumes) return fail(GRMP_EINVAL, "grmp_grid_set_faces: NULL argument");
+  if (g->xdim != g->dim) return fail(GRMP_EUNSUPPORTED, "boundary-face grids carry no face data");
   cudaStream_t s = g->ctx->stream;
   const size_t nf = g->dim + 1;
   GRMP_TRY(g->cellfaces.upload(cellfaces, (size_t)g->ncells * nf, s));
@@ -324,7 +347,7 @@ int grmp_grid_set_faces(grmp_grid* g, int64_t nfaces, const int32_t* cellfaces, 
 int grmp_grid_update_geometry(grmp_grid* g, const double* coords, const double* cellvolumes) {
   if (!g || !coords || !cellvolumes) return fail(GRMP_EINVAL, "grmp_grid_update_geometry: NULL argument");
   cudaStream_t s = g->ctx->stream;
-  GRMP_TRY(g->coords.upload(coords, (size_t)g->nnodes * g->dim, s));
+  GRMP_TRY(g->coords.upload(coords, (size_t)g->nnodes * g->xdim, s));
   GRMP_TRY(g->vol.upload(cellvolumes, (size_t)g->ncells, s));
   GRMP_CUDA(cudaStreamSynchronize(s));
   g->geom_version++;
@@ -525,8 +548,9 @@ int grmp_blf_symbolic(grmp_blf* b, double factor, int64_t* nnz_out) {
   const i64 ncells = p.g.ncells;
   const int nloc = p.e1.nd * p.e2.nd;
   const int req = b->path_req;
-  const bool p2_ok = fast_p2tet_applicable(p);
-  const bool col_ok = colpath_applicable(p, b->nq, &b->colp);
+  const bool cellgrid = (p.g.xdim == p.g.dim);   // boundary-face grids: generic path (their items are embedded, the column kernels' geometry is not)
+  const bool p2_ok = cellgrid && fast_p2tet_applicable(p);
+  const bool col_ok = cellgrid && colpath_applicable(p, b->nq, &b->colp);
   const bool cell_req = (req == GRMP_PATH_ATOMIC || req == GRMP_PATH_COLOURED);
   if (req == GRMP_PATH_FAST && !p2_ok && !col_ok) return fail(GRMP_EUNSUPPORTED, "no fast path for this form");
   if ((req == GRMP_PATH_COLUMNS || cell_req) && !col_ok) return fail(GRMP_EUNSUPPORTED, "no column / cell kernel for this form");
@@ -629,7 +653,7 @@ int grmp_blf_assemble_host(grmp_blf* b, double factor, const double* coords, con
   // geometry is what may change on a frozen pattern: it goes first on the compute stream.  The topology arrays, when the
   // caller hands them over, travel on the copy stream concurrently with the kernels and the download (PCIe is full duplex)
   // and are compared with the arrays of the symbolic pass.
-  GRMP_TRY(g->coords.upload(coords, (size_t)g->nnodes * g->dim, s));
+  GRMP_TRY(g->coords.upload(coords, (size_t)g->nnodes * g->xdim, s));
   GRMP_TRY(g->vol.upload(cellvolumes, (size_t)g->ncells, s));
   g->geom_version++;
   const bool check = cellnodes || celldofs_row || celldofs_col;
@@ -891,7 +915,7 @@ static int lf_assemble_impl(grmp_lf* l, double factor, int fsrc, const double* f
     l->path = GRMP_PATH_GENERIC;
     if (l->path_req != GRMP_PATH_GENERIC) {
       int rc = GRMP_EUNSUPPORTED;
-      if (lfpath_applicable(p.e, sp->grid->dim, l->nq, &l->lfp))
+      if (sp->grid->xdim == sp->grid->dim && lfpath_applicable(p.e, sp->grid->dim, l->nq, &l->lfp))
         rc = lfpath_build(ctx, p.g, p.e, l->reg, l->w_host, l->vals_host, l->derivs_host, sp->ndofs, &l->lfp);
       else set_error("no linear form kernel for this evaluator");
       if (rc == GRMP_OK) l->path = GRMP_PATH_COLUMNS;

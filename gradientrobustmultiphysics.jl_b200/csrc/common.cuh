@@ -61,7 +61,8 @@ template <class T> struct DevBuf {
 
 // ---- device views passed to kernels by value -------------------------------------------------
 struct GridView {
-  int dim;
+  int dim;                  // dimension of the items
+  int xdim;                 // dimension of the coordinates (> dim: boundary-face items, no affine inverse)
   i64 nnodes, ncells, nfaces;
   const double* coords;     // [nnodes][dim]
   const i32* cellnodes;     // [ncells][dim+1], 1-based
@@ -110,7 +111,8 @@ struct grmp_ctx {
 
 struct grmp_grid {
   grmp_ctx* ctx;
-  int dim;
+  int dim;                        // dimension of the items (cells; boundary faces for grmp_grid_create_bfaces)
+  int xdim;                       // dimension of the coordinates (== dim for cell grids)
   grmp::i64 nnodes, ncells, nfaces;
   grmp::DevBuf<double> coords, vol, fnormals, fvol;
   grmp::DevBuf<grmp::i32> cellnodes, regions, cellfaces, signs, orient;

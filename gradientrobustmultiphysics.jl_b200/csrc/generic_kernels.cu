@@ -27,6 +27,7 @@ struct Geo {
 // update_trafo! : A[:,j] = x_{j+1} - x_1 ; det from A
 __device__ __forceinline__ void geo_update(const GridView& g, i64 cell, Geo& T) {
   const int d = g.dim;
+  if (g.xdim != d) return;   // boundary-face items: only Identity evaluators are admitted (make_evalview), they need no map
   const i32* cn = g.cellnodes + cell * (d + 1);
   const double* x0 = g.coords + (i64)(cn[0] - 1) * d;
   double b[3];

@@ -88,7 +88,7 @@ def _nn(edim):
 
 
 def _ne(edim):
-    return 3 if edim == 2 else 6
+    return {1: 1, 2: 3, 3: 6}[edim]      # Edge1D: the interior dof takes the edge slot
 
 
 class FEType:
@@ -131,6 +131,9 @@ class H1P1(FEType):
     def dofmap_pattern(self, edim):
         return "N1"
 
+    def bface_dofmap_pattern(self, fdim):   # h1_p1.jl:29
+        return "N1"
+
     def basis(self, rb, x, edim):     # h1_p1.jl:64-75
         for k in range(1, self.ncomponents + 1):
             r = (edim + 1) * k - edim - 1
@@ -157,8 +160,18 @@ class H1P2(FEType):
     def dofmap_pattern(self, edim):   # h1_p2.jl:107-113
         return "N1F1" if edim == 2 else "N1E1"
 
-    def basis(self, rb, x, edim):     # h1_p2.jl:208-239
-        if edim == 2:
+    def bface_dofmap_pattern(self, fdim):   # h1_p2.jl:37-38
+        return "N1I1" if fdim == 1 else "N1E1"
+
+    def basis(self, rb, x, edim):     # h1_p2.jl:123-132 (Edge1D), 208-239
+        if edim == 1:
+            rb.last = 1.0 - x[0]
+            for k in range(1, self.ncomponents + 1):
+                l = rb.last
+                rb[3 * k - 3, k - 1] = 2.0 * l * (l - 0.5)
+                rb[3 * k - 2, k - 1] = 2.0 * x[0] * (x[0] - 0.5)
+                rb[3 * k - 1, k - 1] = 4.0 * l * x[0]
+        elif edim == 2:
             rb.last = 1.0 - x[0] - x[1]
             for k in range(1, self.ncomponents + 1):
                 l = rb.last

@@ -128,8 +128,64 @@ class FESpace:
         self._celldofs = np.ascontiguousarray(dm, dtype=np.int32)
         return self._celldofs
 
+    # dofmaps.jl:201-363 with DM = BFaceDofs (patterns: h1_p1.jl:29 "N1", h1_p2.jl:37-38 "N1I1" / "N1E1")
+    @property
+    def bfacedofs(self) -> np.ndarray:
+        if getattr(self, "_bfacedofs", None) is not None:
+            return self._bfacedofs
+        g = self.xgrid
+        pattern = self.fetype.bface_dofmap_pattern(g.dim - 1)
+        nb = g.bfacenodes.shape[0]
+        cols = []
+        for c in range(self.ncomponents):
+            offset = c * self.coffset
+            for ch, each, q in parse_pattern(pattern):
+                assert each and q == 1
+                if ch == "N":
+                    adj, nitems = g.bfacenodes.astype(np.int64), g.nnodes
+                elif ch == "I":                      # interior dof of the face = face dof of the parent space
+                    adj, nitems = g.bfacefaces.astype(np.int64)[:, None], g.nfaces
+                elif ch == "E":
+                    adj, nitems = g.bfaceedges.astype(np.int64), g.nedges
+                else:
+                    raise NotImplementedError(f"BFaceDofs pattern segment {ch}")
+                for n in range(adj.shape[1]):
+                    cols.append(adj[:, n] + offset)
+                offset += nitems
+        dm = np.stack(cols, axis=1) if nb else np.zeros((0, len(cols)), np.int64)
+        assert dm.max(initial=0) <= self.ndofs
+        self._bfacedofs = np.ascontiguousarray(dm, dtype=np.int32)
+        return self._bfacedofs
+
+    def on_bfaces(self):
+        """item view of this space for ON_BFACES assembly: same dofs, items = boundary faces, ItemDofs = BFaceDofs"""
+        if getattr(self, "_bfspace", None) is None:
+            self._bfspace = BFaceSpace(self)
+        return self._bfspace
+
     def __repr__(self):
         return f"FESpace({self.name}, ndofs={self.ndofs})"
+
+
+class BFaceSpace:
+    """FES[BFaceDofs] + the face geometry (Dofmap4AssemblyType(ON_BFACES), dofmaps.jl:45)"""
+
+    def __init__(self, parent: FESpace):
+        if parent.broken or not hasattr(parent.fetype, "bface_dofmap_pattern"):
+            raise NotImplementedError(f"ON_BFACES assembly: H1P1 / H1P2 spaces, got {parent.name}")
+        self.parent = parent
+        self.fetype = parent.fetype
+        self.xgrid = parent.xgrid.bface_grid()
+        self.broken = False
+        self.edim = self.xgrid.dim
+        self.ncomponents = parent.ncomponents
+        self.ndofs = parent.ndofs
+        self.nd_cell = parent.fetype.ndofs(self.edim)
+        self.name = parent.name + " [ON_BFACES]"
+
+    @property
+    def celldofs(self):
+        return self.parent.bfacedofs
 
 
 class FEVectorBlock:

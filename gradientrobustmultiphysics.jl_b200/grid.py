@@ -216,6 +216,68 @@ class ExtendableGrid:
         return self._cache["bfacefaces"]
 
 
+    @property
+    def bfacevolumes(self):
+        """BFaceVolumes: length (2D) / area (3D) of every boundary face"""
+        if "bfacevolumes" not in self._cache:
+            x = self.coords
+            bn = self.bfacenodes.astype(np.int64) - 1
+            a = x[bn[:, 1]] - x[bn[:, 0]]
+            if self.dim == 2:
+                self._cache["bfacevolumes"] = np.sqrt((a * a).sum(axis=1))
+            else:
+                n = np.cross(a, x[bn[:, 2]] - x[bn[:, 0]])
+                self._cache["bfacevolumes"] = np.sqrt((n * n).sum(axis=1)) / 2
+        return self._cache["bfacevolumes"]
+
+    @property
+    def bfaceedges(self):
+        """FaceEdges[:, BFaceFaces] in 3D: the edges (1,2), (2,3), (3,1) of every boundary triangle, nodes in BFaceNodes order"""
+        if "bfaceedges" not in self._cache:
+            assert self.dim == 3
+            en = np.sort(self.edgenodes.astype(np.int64), axis=1)
+            bn = self.bfacenodes.astype(np.int64)
+            pairs = np.sort(bn[:, [[0, 1], [1, 2], [2, 0]]].reshape(-1, 2), axis=1)
+            ids, _ = _first_encounter_unique(np.concatenate([en, pairs]))
+            be = ids[en.shape[0]:]
+            assert be.max(initial=-1) < en.shape[0], "boundary face with an edge that no cell has"
+            self._cache["bfaceedges"] = (be.reshape(-1, 3) + 1).astype(np.int32)
+        return self._cache["bfaceedges"]
+
+    def bface_grid(self):
+        """the boundary faces as assembly items (AT = ON_BFACES)"""
+        if "bface_grid" not in self._cache:
+            self._cache["bface_grid"] = BFaceGrid(self)
+        return self._cache["bface_grid"]
+
+
+class BFaceGrid:
+    """Item view for ON_BFACES assembly (assemblypatterns.jl:400-440 with GridComponent*4AssemblyType(ON_BFACES)): items = boundary
+    faces (Edge1D in 2D, Triangle2D in 3D) with BFaceNodes / BFaceVolumes / BFaceRegions in the roles of the cell components;
+    coordinates keep the dimension of the parent grid."""
+    embedded = True
+
+    def __init__(self, parent: "ExtendableGrid"):
+        self.parent = parent
+        self.dim = parent.dim - 1
+        self.xdim = parent.dim
+        self.coords = parent.coords
+        self.cellnodes = parent.bfacenodes
+        self.cellregions = parent.bfaceregions
+
+    @property
+    def cellvolumes(self):
+        return self.parent.bfacevolumes
+
+    @property
+    def nnodes(self):
+        return self.coords.shape[0]
+
+    @property
+    def ncells(self):
+        return self.cellnodes.shape[0]
+
+
 # ----------------------------------------------------------------------------------
 # generators
 # ----------------------------------------------------------------------------------

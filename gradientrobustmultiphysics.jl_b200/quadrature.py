@@ -1,7 +1,7 @@
 """Quadrature rules of the reference (host mirror of src/quadrature.jl).
 
 `QuadratureRule(geometry, order)` returns the same points/weights the reference's
-`QuadratureRule{T,EG}(order)` constructs (quadrature.jl:173-195 Triangle2D, 268-325
+`QuadratureRule{T,EG}(order)` constructs (quadrature.jl:130-148 Edge1D, 173-195 Triangle2D, 268-325
 Tetrahedron3D, 332-502 symmetric rules, 528-562 Stroud conical product).  In production
 the Julia host passes `qf.xref` / `qf.w` to libgrmp_cuda unchanged; this mirror produces
 them in-container.  Weights sum to 1 (the cell volume is applied later,
@@ -16,7 +16,9 @@ class QuadratureRule:
     def __init__(self, geometry: str, order: int):
         self.geometry = geometry
         self.order = order
-        if geometry == "Triangle2D":
+        if geometry == "Edge1D":
+            self.xref, self.w, self.name = _edge(order)
+        elif geometry == "Triangle2D":
             self.xref, self.w, self.name = _triangle(order)
         elif geometry == "Tetrahedron3D":
             self.xref, self.w, self.name = _tetrahedron(order)
@@ -27,6 +29,20 @@ class QuadratureRule:
 
     def __len__(self):
         return self.w.size
+
+
+def _edge(order):
+    """quadrature.jl:130-148, generic Gauss rule 506-525"""
+    if order <= 1:
+        return np.array([[0.5]]), np.array([1.0]), "midpoint rule"
+    if order == 2:
+        return np.array([[0.0], [0.5], [1.0]]), np.array([1.0 / 6, 2.0 / 3, 1.0 / 6]), "Simpson's rule"
+    n = order // 2 + 1
+    k = np.arange(1, n)
+    gamma = k / np.sqrt(4.0 * k**2 - 1.0)
+    r, V = np.linalg.eigh(np.diag(gamma, 1) + np.diag(gamma, -1))
+    w = 2 * V[0, :] ** 2
+    return (0.5 * r + 0.5)[:, None], 0.5 * w, f"generic Gauss rule of order {order}"
 
 
 def _stroud(order):

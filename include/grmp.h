@@ -105,6 +105,15 @@ int grmp_device_synchronize(grmp_ctx* ctx);
 int grmp_grid_create(grmp_ctx* ctx, int dim, int64_t nnodes, const double* coords, int64_t ncells,
                      const int32_t* cellnodes, const double* cellvolumes, const int32_t* cellregions,
                      grmp_grid** out);
+/* The boundary faces as assembly items: AT = ON_BFACES (assemblypatterns.jl:400-440 reads BFaceNodes / BFaceVolumes /
+ * BFaceRegions through GridComponent*4AssemblyType and FES[BFaceDofs] through Dofmap4AssemblyType, dofmaps.jl:45; call
+ * sites: the best-approximation Dirichlet data of boundarydata.jl:297-347).  The returned grid has item dimension
+ * xdim-1 (Edge1D / Triangle2D); spaces on it take FES[BFaceDofs] as `celldofs`.  Identity evaluators of H1P1 / H1P2
+ * (scalar or vector valued) are admitted, everything else returns GRMP_EUNSUPPORTED and stays with the reference.
+ * All forms on such a grid run on the bit-exact path. */
+int grmp_grid_create_bfaces(grmp_ctx* ctx, int xdim, int64_t nnodes, const double* coords, int64_t nbfaces,
+                            const int32_t* bfacenodes, const double* bfacevolumes, const int32_t* bfaceregions,
+                            grmp_grid** out);
 /* CellFaces / CellFaceSigns / CellFaceOrientations / FaceNormals / FaceVolumes
  * (hdiv_rt0.jl:106-116, hdiv_bdm1.jl coefficient + subset closures, h1v_br.jl:150-162,
  * 253-273, reconstructions.jl:27-30).  cellfaceorient may be NULL in 2D. */

@@ -10,8 +10,9 @@
 #     assemble!(b::Union{AbstractArray{T,1},AbstractArray{T,2}}, AP::AssemblyPattern{<:APT_LinearForm,...}, FEB = []; ...)   linearform.jl:47-54
 # and `assemble_operator!` (pdeoperators.jl:978-1006) calls them WITHOUT the FEB argument for every operator that has no
 # fixed arguments.  This file adds the two-argument methods
-#     assemble!(A::FEMatrixBlock{Float64,Int64,Float64,Int32}, AP::AssemblyPattern{<:APT_BilinearForm,Float64,ON_CELLS,Float64,Int32}; ...)
-#     assemble!(b::FEVectorBlock{Float64,Float64,Int32},       AP::AssemblyPattern{<:APT_LinearForm,Float64,ON_CELLS,Float64,Int32}; ...)
+#     assemble!(A::FEMatrixBlock{Float64,Int64,Float64,Int32}, AP::AssemblyPattern{<:APT_BilinearForm,Float64,AT,Float64,Int32}; ...)
+#     assemble!(b::FEVectorBlock{Float64,Float64,Int32},       AP::AssemblyPattern{<:APT_LinearForm,Float64,AT,Float64,Int32}; ...)
+#   with AT = ON_CELLS, or ON_BFACES for the Identity forms of H1P1 / H1P2 (best-approximation boundary data, boundarydata.jl:297-347)
 # which are more specific than the reference's, so PDEDescription / add_operator! / solve! reach them unchanged.  Calls WITH
 # coefficient arguments (FEB, row N4 of SURVEY.md 8f) dispatch to a third method further down that takes the Picard convection form
 # of ConvectionOperator and hands everything else back.  Inside, `blf_plan` / `lf_plan` decide whether the
@@ -118,6 +119,24 @@ function device_grid(xgrid::ExtendableGrid{Float64,Int32}; faces = false)
     return g
 end
 
+# AT = ON_BFACES: the boundary faces as items (BFaceNodes / BFaceVolumes / BFaceRegions, assemblypatterns.jl:400-440)
+const BGRIDS = WeakKeyDict{Any,DGrid}()
+function device_grid(xgrid::ExtendableGrid{Float64,Int32}, ::Type{ON_BFACES})
+    get!(BGRIDS, xgrid) do
+        coords = xgrid[Coordinates]; bn = Matrix{Int32}(xgrid[BFaceNodes])
+        vol = Vector{Float64}(xgrid[BFaceVolumes]); reg = Vector{Int32}(xgrid[BFaceRegions])
+        h = Ref{Ptr{Cvoid}}()
+        ctx = context()
+        GC.@preserve coords bn vol reg check(ccall((:grmp_grid_create_bfaces, lib), Cint,
+            (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Ref{Ptr{Cvoid}}),
+            ctx.h, size(coords, 1), size(coords, 2), coords, size(bn, 2), bn, vol, reg, h))
+        d = DGrid(h[], false, ctx)
+        finalizer(x -> destroy(:grmp_grid_destroy, x), d)
+        d
+    end
+end
+device_grid(xgrid::ExtendableGrid{Float64,Int32}, ::Type{ON_CELLS}; faces = false) = device_grid(xgrid; faces)
+
 "`update_geometry!(xgrid)`: the coordinates of a grid moved in place (same topology) -- re-upload Coordinates / CellVolumes"
 function update_geometry!(xgrid::ExtendableGrid{Float64,Int32})
     haskey(GRIDS, xgrid) || return nothing
@@ -143,6 +162,27 @@ function device_space(FES::FESpace{Float64,Int32,FEType}) where {FEType}
         d
     end
 end
+
+const BSPACES = WeakKeyDict{Any,DSpace}()
+function device_space(FES::FESpace{Float64,Int32,FEType}, ::Type{ON_BFACES}) where {FEType}
+    get!(BSPACES, FES) do
+        g = device_grid(FES.xgrid, ON_BFACES)
+        nb = num_sources(FES.xgrid[BFaceNodes])
+        colentries = Matrix{Int32}(reshape(FES[BFaceDofs].colentries, :, nb))       # Dofmap4AssemblyType(ON_BFACES), dofmaps.jl:45
+        h = Ref{Ptr{Cvoid}}()
+        GC.@preserve colentries check(ccall((:grmp_space_create, lib), Cint,
+            (Ptr{Cvoid}, Cint, Cint, Int64, Cint, Ptr{Int32}, Ref{Ptr{Cvoid}}),
+            g.h, fecode(FEType), get_ncomponents(FEType), FES.ndofs, size(colentries, 1), colentries, h))
+        d = DSpace(h[], g)
+        finalizer(x -> destroy(:grmp_space_destroy, x), d)
+        d
+    end
+end
+device_space(FES::FESpace{Float64,Int32}, ::Type{ON_CELLS}) = device_space(FES)
+const DeviceAT = Union{ON_CELLS,ON_BFACES}
+# ON_BFACES: Identity of H1P1 / H1P2 (the best-approximation boundary data of boundarydata.jl:297-347); everything else on
+# boundary faces (NormalFlux, TangentFlux, face bubbles of H1BR) stays with the reference
+bface_ok(AP) = all(F -> eltype(F) <: Union{H1P1,H1P2} && !F.broken, AP.FES) && all(o -> o == Identity, AP.operators)
 
 # tables straight out of the reference's FEEvaluator (feevaluator.jl:34-138): ForwardDiff's bits travel unchanged
 function evaltab(ev)   # ev::GRMP.SingleFEEvaluator
@@ -184,8 +224,9 @@ function hooke_parameters(action)
 end
 
 struct BlfPlan; act::Int; par::Vector{Float64}; ops::Tuple{Int,Int}; end
-function blf_plan(AP::AssemblyPattern{APT}) where {APT}
+function blf_plan(AP::AssemblyPattern{APT,Tv,AT}) where {APT,Tv,AT}
     length(AP.FES) == 2 && length(AP.operators) == 2 || return nothing
+    AT <: ON_BFACES && !(bface_ok(AP) && AP.action isa NoAction) && return nothing
     AP.FES[1].xgrid === AP.FES[2].xgrid || return nothing
     AP.FES[1].xgrid[UniqueCellGeometries] in ([Triangle2D], [Tetrahedron3D]) || return nothing
     all(F -> fecode(eltype(F)) !== nothing && !F.broken || eltype(F) <: L2P0, AP.FES) || return nothing
@@ -203,13 +244,13 @@ end
 # (the reference's own contract for reassembly, solvers.jl:556) or when nothing that defines it changed.
 const PATTERNS = WeakKeyDict{Any,Dict{Bool,DBlf}}()
 
-function build_blf(A, AP::AssemblyPattern{APT}, plan::BlfPlan, factor, transposed_assembly) where {APT}
+function build_blf(A, AP::AssemblyPattern{APT,Tv,AT}, plan::BlfPlan, factor, transposed_assembly) where {APT,Tv,AT}
     e1 = GRMP.get_basisevaler(AP.AM, 1, 1); e2 = GRMP.get_basisevaler(AP.AM, 2, 1)
     v1, d1, t1 = evaltab(e1); v2, d2, t2 = evaltab(e2)
     w = Vector{Float64}(GRMP.get_qweights(AP.AM))
     par = plan.par
     regions = AP.regions == [0] ? Int32[] : Vector{Int32}(AP.regions)
-    s1, s2 = device_space(AP.FES[1]), device_space(AP.FES[2])
+    s1, s2 = device_space(AP.FES[1], AT), device_space(AP.FES[2], AT)
     h = Ref{Ptr{Cvoid}}()
     GC.@preserve v1 d1 v2 d2 w par regions check(ccall((:grmp_blf_create, lib), Cint,
         (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float64}, Cint, Cint, Ptr{Int32}, Cint, Cint, Ptr{Float64}, Ref{EvalTab}, Ref{EvalTab}, Ref{Ptr{Cvoid}}),
@@ -237,13 +278,13 @@ skip_preps = true: numeric assembly on the frozen pattern (grmp_blf_numeric).  T
 (single-block matrix with an empty target: `A.entries.cscmatrix = SparseMatrixCSC(m, n, colptr, rowval, nzval)`; otherwise
 an addblock!-style merge), the transposed copy likewise.
 """
-function GRMP.assemble!(A::FEMatrixBlock{Float64,Int64,Float64,Int32}, AP::AssemblyPattern{APT,Float64,ON_CELLS,Float64,Int32};
+function GRMP.assemble!(A::FEMatrixBlock{Float64,Int64,Float64,Int32}, AP::AssemblyPattern{APT,Float64,AT,Float64,Int32};
         factor = 1, factor_transpose = factor, skip_preps::Bool = false, fixed_arguments = nothing,
-        transposed_assembly::Bool = false, transpose_copy = nothing) where {APT<:GRMP.APT_BilinearForm}
+        transposed_assembly::Bool = false, transpose_copy = nothing) where {APT<:GRMP.APT_BilinearForm,AT<:DeviceAT}
     plan = blf_plan(AP)
     if plan === nothing || !(transpose_copy === nothing || transpose_copy isa FEMatrixBlock{Float64,Int64,Float64,Int32})
         # not on the device path: the reference's own loop, all keywords forwarded
-        return invoke(GRMP.assemble!, Tuple{AbstractArray{Float64,2},AssemblyPattern{APT,Float64,ON_CELLS,Float64,Int32}}, A, AP;
+        return invoke(GRMP.assemble!, Tuple{AbstractArray{Float64,2},AssemblyPattern{APT,Float64,AT,Float64,Int32}}, A, AP;
                       factor, factor_transpose, skip_preps, fixed_arguments, transposed_assembly, transpose_copy)
     end
     skip_preps || GRMP.prepare_assembly!(AP)
@@ -327,8 +368,9 @@ end
 
 # ---- LinearForm ------------------------------------------------------------------------------------------------------
 struct LfPlan; op::Int; fsrc::Int; end
-function lf_plan(AP::AssemblyPattern)
+function lf_plan(AP::AssemblyPattern{APT,Tv,AT}) where {APT,Tv,AT}
     length(AP.FES) == 1 && length(AP.operators) == 1 || return nothing
+    AT <: ON_BFACES && !bface_ok(AP) && return nothing
     F = AP.FES[1]
     F.xgrid[UniqueCellGeometries] in ([Triangle2D], [Tetrahedron3D]) || return nothing
     (fecode(eltype(F)) !== nothing && (!F.broken || eltype(F) <: L2P0)) || return nothing
@@ -346,13 +388,13 @@ const LFS = WeakKeyDict{Any,DLf}()
 
 # f at the quadrature points of every cell, evaluated exactly as the reference loop does it (linearform.jl:197-201:
 # update_trafo! / eval_trafo!(action.x, L2G, xref[i]); eval_action!(action, input)) -> table [ncells][nq][resultdim]
-function tabulate_action(AP::AssemblyPattern, ev, nq::Int)
+function tabulate_action(AP::AssemblyPattern{APT,Tv,AT}, ev, nq::Int) where {APT,Tv,AT}
     action = AP.action
     rd = action.argsizes[1]
     xgrid = AP.FES[1].xgrid
-    ncells = num_sources(xgrid[CellNodes])
+    ncells = num_sources(xgrid[GRMP.GridComponentNodes4AssemblyType(AT)])       # items: cells, or boundary faces (ev.L2G is the transformer of AT)
     regions = AP.regions; allitems = regions == [0]
-    xreg = xgrid[CellRegions]
+    xreg = xgrid[GRMP.GridComponentRegions4AssemblyType(AT)]
     input = zeros(Float64, 0)
     if !GRMP.is_xdependent(action)
         GRMP.eval_action!(action, input)
@@ -378,14 +420,29 @@ b[dof + b.offset] += contributions in cell order.  A DataFunction cannot cross t
 quadrature points (GRMP_F_QP_TABLE) or passed as a constant (GRMP_F_CONST); the basis evaluation, contraction and scatter
 run on the device.
 """
-function GRMP.assemble!(b::FEVectorBlock{Float64,Float64,Int32}, AP::AssemblyPattern{APT,Float64,ON_CELLS,Float64,Int32};
-        skip_preps::Bool = false, factor = 1, fixed_arguments = nothing) where {APT<:GRMP.APT_LinearForm}
+function GRMP.assemble!(b::FEVectorBlock{Float64,Float64,Int32}, AP::AssemblyPattern{APT,Float64,AT,Float64,Int32};
+        skip_preps::Bool = false, factor = 1, fixed_arguments = nothing) where {APT<:GRMP.APT_LinearForm,AT<:DeviceAT}
     plan = lf_plan(AP)
     if plan === nothing
-        return invoke(GRMP.assemble!, Tuple{Union{AbstractArray{Float64,1},AbstractArray{Float64,2}},AssemblyPattern{APT,Float64,ON_CELLS,Float64,Int32}},
+        return invoke(GRMP.assemble!, Tuple{Union{AbstractArray{Float64,1},AbstractArray{Float64,2}},AssemblyPattern{APT,Float64,AT,Float64,Int32}},
                       b, AP; skip_preps, factor, fixed_arguments)
     end
     @assert b.FES == AP.FES[1]
+    return lf_device!(b.entries, AP, plan, skip_preps, Float64(factor), b.offset)
+end
+# the plain-vector call of boundarydata.jl:315 (`assemble!(b, RHS_bnd)` with b::Array{T,1}): boundary forms only, so that the
+# method table of cell forms on plain vectors stays the reference's
+function GRMP.assemble!(b::Vector{Float64}, AP::AssemblyPattern{APT,Float64,ON_BFACES,Float64,Int32};
+        skip_preps::Bool = false, factor = 1, fixed_arguments = nothing, offset = 0) where {APT<:GRMP.APT_LinearForm}
+    plan = lf_plan(AP)
+    if plan === nothing
+        return invoke(GRMP.assemble!, Tuple{Union{AbstractArray{Float64,1},AbstractArray{Float64,2}},AssemblyPattern{APT,Float64,ON_BFACES,Float64,Int32}},
+                      b, AP; skip_preps, factor, fixed_arguments, offset)
+    end
+    return lf_device!(b, AP, plan, skip_preps, Float64(factor), offset)
+end
+
+function lf_device!(entries::Vector{Float64}, AP::AssemblyPattern{APT,Float64,AT}, plan::LfPlan, skip_preps::Bool, factor::Float64, offset) where {APT,AT}
     skip_preps || GRMP.prepare_assembly!(AP)
     ev = GRMP.get_basisevaler(AP.AM, 1, 1)
     w = Vector{Float64}(GRMP.get_qweights(AP.AM))
@@ -395,7 +452,7 @@ function GRMP.assemble!(b::FEVectorBlock{Float64,Float64,Int32}, AP::AssemblyPat
     d = get!(LFS, AP) do
         v, dv, t = evaltab(ev)
         regions = AP.regions == [0] ? Int32[] : Vector{Int32}(AP.regions)
-        s = device_space(AP.FES[1])
+        s = device_space(AP.FES[1], AT)
         h = Ref{Ptr{Cvoid}}()
         GC.@preserve v dv w regions check(ccall((:grmp_lf_create, lib), Cint,
             (Ptr{Cvoid}, Cint, Ptr{Int32}, Cint, Cint, Ptr{Float64}, Ref{EvalTab}, Ref{Ptr{Cvoid}}),
@@ -405,10 +462,9 @@ function GRMP.assemble!(b::FEVectorBlock{Float64,Float64,Int32}, AP::AssemblyPat
         l
     end
     fdata = plan.fsrc == F_NONE ? Float64[] : tabulate_action(AP, ev, length(w))
-    entries = b.entries
     GC.@preserve fdata entries check(ccall((:grmp_lf_assemble, lib), Cint,
         (Ptr{Cvoid}, Float64, Cint, Ptr{Float64}, Ptr{Float64}, Int64),
-        d.h, Float64(factor), plan.fsrc, isempty(fdata) ? C_NULL : pointer(fdata), entries, b.offset))
+        d.h, factor, plan.fsrc, isempty(fdata) ? C_NULL : pointer(fdata), entries, offset))
     AP.last_allocations = 0
     return nothing
 end

@@ -93,9 +93,17 @@ template <class T> void basis_H1P1(RefB<T>& rb, const T* x, int edim, int ncomp)
     }
   }
 }
-// src/fedefs/h1_p2.jl:208-220 (Triangle2D), 223-239 (Tetrahedron3D)
+// src/fedefs/h1_p2.jl:123-132 (Edge1D: the boundary faces of a 2D grid), 208-220 (Triangle2D), 223-239 (Tetrahedron3D)
 template <class T> void basis_H1P2(RefB<T>& rb, const T* x, int edim, int ncomp) {
-  if (edim == 2) {
+  if (edim == 1) {
+    rb.last() = 1.0 - x[0];
+    for (int k = 1; k <= ncomp; k++) {
+      T l = rb.last();
+      rb(3 * k - 3, k - 1) = 2.0 * l * (l - 0.5);
+      rb(3 * k - 2, k - 1) = 2.0 * x[0] * (x[0] - 0.5);
+      rb(3 * k - 1, k - 1) = 4.0 * l * x[0];
+    }
+  } else if (edim == 2) {
     rb.last() = 1.0 - x[0] - x[1];
     for (int k = 1; k <= ncomp; k++) {
       T l = rb.last();
@@ -200,7 +208,7 @@ struct FEInfo { int ncomp, nd, nd_all, polyorder; bool coeffs, hdiv; };
 FEInfo fe_info(int fe, int ncomp, int edim) {
   FEInfo r{};
   r.ncomp = ncomp; r.coeffs = false; r.hdiv = false;
-  int nn = edim + 1, nf = edim + 1, ne = (edim == 2) ? 3 : 6;
+  int nn = edim + 1, nf = edim + 1, ne = (edim == 1) ? 1 : (edim == 2) ? 3 : 6;   // Edge1D: "N1I1" (h1_p2.jl:37)
   switch (fe) {
     case H1P1: r.nd = r.nd_all = nn * ncomp; r.polyorder = 1; break;
     case H1P2: r.nd = r.nd_all = (nn + ne) * ncomp; r.polyorder = 2; break;
@@ -347,7 +355,20 @@ QRule g_override; int g_override_edim = -1, g_override_order = -1;
 bool make_qrule(int edim, int order, QRule& q) {
   if (edim == g_override_edim && order == g_override_order) { q = g_override; return true; }
   q = QRule(); q.dim = edim;
-  if (edim == 2) {                                          // quadrature.jl:173-195
+  if (edim == 1) {                                          // quadrature.jl:130-148, Gauss rule 506-525
+    if (order <= 1) { q.xref = {0.5}; q.w = {1.0}; }
+    else if (order == 2) { q.xref = {0.0, 0.5, 1.0}; q.w = {1.0 / 6, 2.0 / 3, 1.0 / 6}; }
+    else {
+      int n = order / 2 + 1;
+      std::vector<double> A((size_t)n * n, 0.0), r, vec;
+      for (int k = 1; k <= n - 1; k++) {
+        double g = k / std::sqrt(4.0 * k * k - 1.0);
+        A[(k - 1) * n + k] = g; A[k * n + (k - 1)] = g;
+      }
+      sym_eigen(n, A, r, vec);
+      for (int j = 0; j < n; j++) { q.xref.push_back(.5 * r[j] + .5); q.w.push_back(.5 * (2 * vec[0 * n + j] * vec[0 * n + j])); }
+    }
+  } else if (edim == 2) {                                          // quadrature.jl:173-195
     if (order <= 1) { q.xref = {1.0 / 3, 1.0 / 3}; q.w = {1.0}; }
     else if (order == 2) { q.xref = {0.5, 0.5, 0.0, 0.5, 0.5, 0.0}; q.w = {1.0 / 3, 1.0 / 3, 1.0 / 3}; }
     else if (order == 8) q = symmetric_rule_tri8();

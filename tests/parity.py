@@ -29,13 +29,13 @@ _APT = {G.assembly.APT_BilinearForm: O.APT_GENERAL, G.assembly.APT_SymmetricBili
 def oracle_blf(AP, factor, transpose_copy=False, **kw):
     """oracle assemble! on the same quadrature table the host hands to the library (the eigen-generated
     Stroud rules agree between generators only to rounding; hard-coded rules are identical)"""
-    s1, s2 = AP.FES
+    s1, s2 = AP.item_space(0), AP.item_space(1)       # ON_BFACES: the boundary-face views (BFaceDofs, BFaceVolumes, BFaceRegions)
     A = O.OracleMatrix(s2.ndofs, s1.ndofs) if kw.get("transposed_assembly") else O.OracleMatrix(s1.ndofs, s2.ndofs)
     At = O.OracleMatrix(s2.ndofs, s1.ndofs) if transpose_copy else None
     act = AP.action
     dim = s1.xgrid.dim
     qo = G.quadrature_order(AP)
-    qf = G.QuadratureRule("Triangle2D" if dim == 2 else "Tetrahedron3D", qo)
+    qf = G.QuadratureRule({1: "Edge1D", 2: "Triangle2D", 3: "Tetrahedron3D"}[dim], qo)
     O.qrule_override(dim, qo, qf.xref, qf.w)
     try:
         O.blf_assemble(A, s1.xgrid, s1, s2, AP.operators[0].code, AP.operators[1].code, action=act.code, act_params=act.params,

@@ -1,0 +1,121 @@
+"""ON_BFACES assembly (the best-approximation Dirichlet data of boundarydata.jl:297-347): boundary mass matrix
+`DiscreteSymmetricBilinearForm([Identity, Identity], [FE, FE]; AT = ON_BFACES, regions)` and boundary right-hand side
+`DiscreteLinearForm([Identity], [FE], fdot_action(data); AT = ON_BFACES, regions)` on the device against the oracle, bit for bit
+(forms on boundary-face items run on the bit-exact path), then the best-approximation problem itself."""
+import numpy as np
+import pytest
+
+import grmp_b200 as G
+import oracle as O
+from parity import oracle_blf
+
+pytestmark = pytest.mark.gpu
+
+
+def _grid(dim, level, jitter=False):
+    g = G.uniform_refine(G.grid_unitsquare() if dim == 2 else G.grid_unitcube(), level)
+    return G.perturb_interior_nodes(g, 0.15) if jitter else g
+
+
+CASES = [
+    ("P1 2D", 2, 3, lambda: G.H1P1(1), [0]),
+    ("P1x2 2D regions 1,3", 2, 2, lambda: G.H1P1(2), [1, 3]),
+    ("P2 2D", 2, 3, lambda: G.H1P2(1, 2), [0]),
+    ("P2x2 2D regions 2,4", 2, 2, lambda: G.H1P2(2, 2), [2, 4]),
+    ("P1 3D", 3, 2, lambda: G.H1P1(1), [0]),
+    ("P2 3D regions 1,5,6", 3, 1, lambda: G.H1P2(1, 3), [1, 5, 6]),
+    ("P2x3 3D", 3, 1, lambda: G.H1P2(3, 3), [0]),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("apt", ["symmetric", "general"])
+def test_boundary_mass_matrix_bit_equal(case, apt):
+    _, dim, level, fef, regions = case
+    g = _grid(dim, level)
+    s = G.FESpace(fef(), g)
+    ctor = G.DiscreteSymmetricBilinearForm if apt == "symmetric" else G.DiscreteBilinearForm
+    AP = ctor([G.Identity, G.Identity], [s, s], regions=regions, AT="ON_BFACES")
+    cp, rv, nz = G.assemble_csc(AP, 1.25)
+    assert AP.AM is not None and G.blf_stats(AP).path == G._lib.PATH_GENERIC
+    ocp, orv, onz = oracle_blf(AP, 1.25)
+    assert np.array_equal(cp, ocp) and np.array_equal(rv, orv)
+    assert np.array_equal(nz, onz), f"max abs diff {np.abs(nz - onz).max():.3e}"
+    # size-independent property: 1' M 1 = ncomp * measure of the selected boundary part
+    bg = g.bface_grid()
+    sel = np.ones(bg.ncells, bool) if regions == [0] else np.isin(bg.cellregions, regions)
+    assert abs(nz.sum() - 1.25 * s.fetype.ncomponents * bg.cellvolumes[sel].sum()) < 1e-12
+
+
+def _xq(bg, qf):
+    x = bg.coords
+    cn = bg.cellnodes.astype(np.int64) - 1
+    xq = np.repeat(x[cn[:, 0]][:, None, :], len(qf), axis=1).copy()
+    for j in range(bg.dim):
+        xq += (x[cn[:, j + 1]] - x[cn[:, 0]])[:, None, :] * qf.xref[None, :, j, None]
+    return xq
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_boundary_linearform_bit_equal(case):
+    _, dim, level, fef, regions = case
+    g = _grid(dim, level, jitter=True)
+    s = G.FESpace(fef(), g)
+    nc = s.fetype.ncomponents
+    data = G.DataFunction(lambda x: np.stack([np.cos(x[0] + k) * x[1] + (x[2] ** 2 if len(x) > 2 else 0.5) for k in range(nc)]), [nc, dim],
+                          bonus_quadorder=3)
+    AP = G.DiscreteLinearForm([G.Identity], [s], G.fdot_action(data), regions=regions, AT="ON_BFACES")
+    b = G.FEVector([s])
+    b.entries[:] = -0.5
+    G.assemble(b[1], AP, factor=0.75)
+    bs = s.on_bfaces()
+    bg = bs.xgrid
+    P = AP.AM
+    qo = P.quadorder
+    assert qo == s.fetype.polynomialorder(bg.dim) + 3
+    table = np.asarray(data.kernel(_xq(bg, P.qf).reshape(-1, dim).T), dtype=np.float64).reshape(nc, -1).T.reshape(bg.ncells, len(P.qf), nc)
+    ob = np.full(s.ndofs, -0.5)
+    O.qrule_override(bg.dim, qo, P.qf.xref, P.qf.w)
+    try:
+        O.lf_assemble(ob, bg, bs, O.OP_ID, fsrc=O.F_QP_TABLE, fdata=table, regions=regions, factor=0.75, bonus_quadorder=3)
+    finally:
+        O.qrule_override(bg.dim, qo)
+    assert np.array_equal(b.entries, ob), f"max abs diff {np.abs(b.entries - ob).max():.3e}"
+    # interior dofs are untouched
+    touched = np.zeros(s.ndofs, bool)
+    touched[bs.celldofs.astype(np.int64).ravel() - 1] = True
+    assert np.all(b.entries[~touched] == -0.5)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_best_approximation_reproduces_quadratic_boundary_data(dim):
+    """boundarydata.jl:297-347: M_bnd u = b_bnd on the boundary dofs; P2 reproduces a quadratic exactly"""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    g = _grid(dim, 2 if dim == 2 else 1, jitter=True)
+    s = G.FESpace(G.H1P2(1, dim), g)
+    u = lambda x: 1.0 + x[0] * x[1] - 2.0 * x[dim - 1] ** 2 + 0.5 * x[0]
+    data = G.DataFunction(lambda x: np.stack([u(x)]), [1, dim], bonus_quadorder=2)
+    A = G.DiscreteSymmetricBilinearForm([G.Identity, G.Identity], [s, s], AT="ON_BFACES")
+    cp, rv, nz = G.assemble_csc(A, 1.0)
+    b = G.FEVector([s])
+    G.assemble(b[1], G.DiscreteLinearForm([G.Identity], [s], G.fdot_action(data), AT="ON_BFACES"))
+    M = sp.csc_matrix((nz, rv - 1, cp - 1), shape=(s.ndofs, s.ndofs))
+    bd = np.unique(s.bfacedofs.astype(np.int64).ravel() - 1)
+    sol = spla.spsolve(M[bd][:, bd].tocsc(), b.entries[bd])
+    # nodal values: vertices, then edge midpoints (face dofs in 2D, edge dofs in 3D)
+    en = (g.facenodes if dim == 2 else g.edgenodes).astype(np.int64) - 1
+    xdof = np.concatenate([g.coords, 0.5 * (g.coords[en[:, 0]] + g.coords[en[:, 1]])])
+    exact = u(xdof[bd].T)
+    assert np.abs(sol - exact).max() < 1e-11
+
+
+def test_only_identity_of_h1_spaces_is_admitted():
+    g = _grid(2, 1)
+    s = G.FESpace(G.H1P1(1), g)
+    with pytest.raises(G._lib.GrmpError):
+        G.assemble_csc(G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [s, s], AT="ON_BFACES"))
+    with pytest.raises(NotImplementedError):
+        G.assemble_csc(G.DiscreteSymmetricBilinearForm([G.Identity, G.Identity], [G.FESpace(G.HDIVRT0(2), g)] * 2, AT="ON_BFACES"))
+    with pytest.raises(NotImplementedError):
+        G.DiscreteSymmetricBilinearForm([G.Identity, G.Identity], [s, s], AT="ON_FACES")

@@ -369,3 +369,85 @@ def test_newton_convection_form_identities(dim):
     AP = O.OracleMatrix(sv.ndofs, sv.ndofs)
     O.blf_assemble(AP, g, sv, sv, O.OP_GRAD, O.OP_ID, action=O.ACT_CONVECTION, transposed_assembly=True, factor=0.5, fixed=(sv, O.OP_ID, w))
     assert np.abs(AP.toscipy() @ w - b2).max() < 1e-11 * np.abs(b2).max()
+
+
+# ---- ON_BFACES items: Edge1D rules, face bases, BFaceDofs (boundarydata.jl:297-347) ------------------------------------------
+def test_quadrature_exactness_edge1d():
+    # runtests.jl:94-103 -- QuadratureRule{Float64,Edge1D}(order), order 1..12, integrates x^k exactly on [0, 1]
+    for order in range(0, 13):
+        x, w = O.qrule(1, order)
+        hx = G.QuadratureRule("Edge1D", order)
+        assert np.abs(hx.xref - x).max() < 1e-15 and np.abs(hx.w - w).max() < 1e-15      # host mirror == oracle
+        assert abs(w.sum() - 1) < 1e-14
+        for k in range(order + 1):
+            assert abs((w * x[:, 0] ** k).sum() - 1.0 / (k + 1)) < 2e-14, (order, k)
+    x, w = O.qrule(1, 2)
+    assert np.array_equal(x[:, 0], [0.0, 0.5, 1.0]) and np.array_equal(w, [1 / 6, 2 / 3, 1 / 6])          # Simpson, quadrature.jl:136-142
+
+
+def _bface_mass(space, **kw):
+    sb = space.on_bfaces()
+    A = O.OracleMatrix(space.ndofs, space.ndofs)
+    O.blf_assemble(A, sb.xgrid, sb, sb, O.OP_ID, O.OP_ID, apt=O.APT_SYMMETRIC, **kw)
+    return A.toscipy()
+
+
+def test_edge1d_p2_boundary_mass_known_answer():
+    # one boundary edge of length h carries h/30 [4 -1 2; -1 4 2; 2 2 16] (node, node, midpoint)
+    g = G.reference_domain("Triangle2D")
+    s = G.FESpace(G.H1P2(1, 2), g)
+    M = _bface_mass(s, regions=[1]).toarray()              # bface 1 = nodes (1, 2), length 1
+    d = s.bfacedofs[0].astype(np.int64) - 1
+    ref = np.array([[4, -1, 2], [-1, 4, 2], [2, 2, 16]]) / 30.0
+    assert np.abs(M[np.ix_(d, d)] - ref).max() < 1e-15
+    rest = M.copy()
+    rest[np.ix_(d, d)] = 0
+    assert np.all(rest == 0)
+    # P1: h/6 [2 1; 1 2] on the hypotenuse (length sqrt 2)
+    s1 = G.FESpace(G.H1P1(1), g)
+    M1 = _bface_mass(s1, regions=[2]).toarray()
+    d = s1.bfacedofs[1].astype(np.int64) - 1
+    assert np.abs(M1[np.ix_(d, d)] - math.sqrt(2) / 6 * np.array([[2, 1], [1, 2]])).max() < 1e-15
+
+
+@pytest.mark.parametrize("dim,fe", [(2, "P1"), (2, "P2"), (3, "P1"), (3, "P2")])
+def test_bfacedofs_are_the_trace_of_celldofs(dim, fe):
+    """every BFaceDof is a dof of the cell behind the face, sitting where the cell's basis function does not vanish on it"""
+    g = G.perturb_interior_nodes(tri_grid(2) if dim == 2 else tet_grid(1), 0.1)
+    s = G.FESpace(G.H1P1(2) if fe == "P1" else G.H1P2(2, dim), g)
+    bd = s.bfacedofs
+    nn = dim
+    assert bd.shape == (g.bfacenodes.shape[0], 2 * (nn if fe == "P1" else nn + (1 if dim == 2 else 3)))
+    cell_of_face = g.facecells[g.bfacefaces.astype(np.int64) - 1, 0].astype(np.int64) - 1
+    for b in range(bd.shape[0]):
+        assert set(bd[b]) <= set(s.celldofs[cell_of_face[b]])
+    # the boundary mass matrix sees the measure of the boundary, per component
+    M = _bface_mass(s)
+    assert abs(M.sum() - 2 * g.bfacevolumes.sum()) < 1e-12
+    assert abs(g.bfacevolumes.sum() - (4.0 if dim == 2 else 6.0)) < 1e-13
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_boundary_best_approximation_oracle(dim):
+    """runtests.jl:355-509 in spirit, on the boundary: M_bnd u = b_bnd reproduces the trace of a quadratic in P2"""
+    g = G.perturb_interior_nodes(tri_grid(2) if dim == 2 else tet_grid(1), 0.1)
+    s = G.FESpace(G.H1P2(1, dim), g)
+    sb = s.on_bfaces()
+    bg = sb.xgrid
+    u = lambda x: 0.25 - x[0] * x[dim - 1] + 3.0 * x[1] ** 2
+    qo = 4
+    xr, w = O.qrule(bg.dim, qo)
+    x = bg.coords
+    cn = bg.cellnodes.astype(np.int64) - 1
+    xq = np.repeat(x[cn[:, 0]][:, None, :], w.size, axis=1).copy()
+    for j in range(bg.dim):
+        xq += (x[cn[:, j + 1]] - x[cn[:, 0]])[:, None, :] * xr[None, :, j, None]
+    table = u(xq.reshape(-1, dim).T).reshape(bg.ncells, w.size, 1)
+    b = np.zeros(s.ndofs)
+    O.lf_assemble(b, bg, sb, O.OP_ID, fsrc=O.F_QP_TABLE, fdata=table, bonus_quadorder=2)
+    M = _bface_mass(s).tocsc()
+    bdofs = np.unique(s.bfacedofs.astype(np.int64).ravel() - 1)
+    sol = spla.spsolve(M[bdofs][:, bdofs].tocsc(), b[bdofs])
+    en = (g.facenodes if dim == 2 else g.edgenodes).astype(np.int64) - 1
+    xdof = np.concatenate([g.coords, 0.5 * (g.coords[en[:, 0]] + g.coords[en[:, 1]])])
+    assert np.abs(sol - u(xdof[bdofs].T)).max() < 100 * TOL
