@@ -9,6 +9,7 @@ Layout:
   fespace.py     FESpace / CellDofs / FEVector / FEMatrix
   assembly.py    AssemblyPattern, assemble!      (src/assemblypatterns/*.jl)
   operators.py   LaplaceOperator ... assemble_operator!   (src/pdeoperators.jl)
+  boundarydata.py  Dirichlet boundary data: interpolated / homogeneous / best-approximation (src/boundarydata.jl)
 """
 from .grid import (ExtendableGrid, grid_unitsquare, grid_unitcube, reference_domain, uniform_refine,
                    perturb_interior_nodes)
@@ -22,4 +23,6 @@ from .assembly import (Identity, Gradient, SymmetricGradient, Divergence, Recons
                        device_csc, fetch_values, ItemIntegrator, L2NormIntegrator, L2ErrorIntegrator, evaluate, evaluate_itemwise)
 from .operators import (PDEOperator, LaplaceOperator, ReactionOperator, LagrangeMultiplier, ConvectionOperator, full_assemble_operator, HookStiffnessOperator2D,
                         HookStiffnessOperator3D, BilinearForm, LinearForm, create_assembly_pattern, assemble_operator)
+from .boundarydata import (BoundaryData, boundarydata, HomogeneousDirichletBoundary, InterpolateDirichletBoundary,
+                           BestapproxDirichletBoundary)
 from . import _lib, assembly, partition

@@ -119,3 +119,51 @@ def test_only_identity_of_h1_spaces_is_admitted():
         G.assemble_csc(G.DiscreteSymmetricBilinearForm([G.Identity, G.Identity], [G.FESpace(G.HDIVRT0(2), g)] * 2, AT="ON_BFACES"))
     with pytest.raises(NotImplementedError):
         G.DiscreteSymmetricBilinearForm([G.Identity, G.Identity], [s, s], AT="ON_FACES")
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_poisson_with_mixed_dirichlet_data_end_to_end(dim):
+    """solve! flow of the reference (solvers.jl:600-668) with every Dirichlet type of boundarydata.jl: assemble on the device,
+    boundarydata -> fixed dofs, penalties on the device-resident matrix, host solve, residual on the device.  P2 + quadratic
+    solution: every step is exact up to rounding, so the nodal values come back."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    g = _grid(dim, 2 if dim == 2 else 1, jitter=True)
+    s = G.FESpace(G.H1P2(1, dim), g)
+    u = lambda x: x[0] ** 2 + x[0] * x[1] - (x[dim - 1] ** 2 if dim == 3 else 0.0) + 1.0        # -Laplace u = -2 (2D), 0 (3D)
+    udata = G.DataFunction(lambda x: np.stack([u(x)]), [1, dim], bonus_quadorder=2)
+    A = G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [s, s])
+    cp, rv, _ = G.assemble_csc(A, 1.0)
+    rhs = G.FEVector([s])
+    G.assemble(rhs[1], G.DiscreteLinearForm([G.Identity], [s], G.fdot_action(G.DataFunction([-2.0 if dim == 2 else 0.0]))))
+    sol = G.FEVector([s])
+    nreg = int(g.bfaceregions.max())
+    O = [G.BoundaryData(G.InterpolateDirichletBoundary, data=udata, regions=[1]),
+         G.BoundaryData(G.BestapproxDirichletBoundary, data=udata, regions=list(range(2, nreg + 1)))]
+    fixed = G.boundarydata(sol[1], O)
+    assert np.array_equal(np.sort(fixed), np.unique(s.bfacedofs))
+    penalty = 1e60
+    G.apply_penalties(A, fixed, penalty)
+    rhs.entries[fixed - 1] = penalty * sol.entries[fixed - 1]
+    nz = G.fetch_values(A)
+    M = sp.csc_matrix((nz, rv - 1, cp - 1), shape=(s.ndofs, s.ndofs))
+    x = spla.spsolve(M, rhs.entries)
+    en = (g.facenodes if dim == 2 else g.edgenodes).astype(np.int64) - 1
+    xdof = np.concatenate([g.coords, 0.5 * (g.coords[en[:, 0]] + g.coords[en[:, 1]])])
+    assert np.abs(x - u(xdof.T)).max() < 1e-10
+    _, nrm = G.residual(A, x, rhs.entries, fixed_dofs=fixed, want_vector=False)
+    assert nrm < 1e-20
+
+
+def test_homogeneous_boundary_and_order_of_fixed_dofs():
+    g = _grid(2, 1)
+    s = G.FESpace(G.H1P1(2), g)
+    t = G.FEVector([s])
+    t.entries[:] = 7.0
+    O = [G.BoundaryData(G.HomogeneousDirichletBoundary, regions=[1, 3])]
+    fixed = G.boundarydata(t[1], O)
+    sel = np.isin(g.bfaceregions, [1, 3])
+    expect = s.bfacedofs[sel].astype(np.int64).ravel()
+    _, first = np.unique(expect, return_index=True)
+    assert np.array_equal(fixed, expect[np.sort(first)])           # Base.unique order (boundarydata.jl:246)
+    assert np.all(t.entries[fixed - 1] == 0) and np.count_nonzero(t.entries == 7.0) == s.ndofs - fixed.size

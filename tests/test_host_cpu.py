@@ -205,3 +205,29 @@ def test_oracle_reproduces_committed_golden_fixtures():
         for k in range(d["colptr"][j] - 1, d["colptr"][j + 1] - 1):
             M[d["rowval"][k] - 1, j] = d["nzval"][k]
     assert np.abs(M - 0.5 / 12 * np.array([[2, 1, 1], [1, 2, 1], [1, 1, 2]])).max() < 1e-16
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_interpolated_and_homogeneous_boundary_data_host_part(dim):
+    """boundarydata.jl:100-258 (no device work): P2 interpolation on boundary faces = nodal values + edge-mean preserving edge dofs,
+    exact for a quadratic trace; homogeneous regions are zeroed; fixed dofs come back in first-occurrence order"""
+    g = G.perturb_interior_nodes(G.uniform_refine(G.grid_unitsquare() if dim == 2 else G.grid_unitcube(), 1), 0.1)
+    s = G.FESpace(G.H1P2(2, dim), g)
+    u = lambda x: np.stack([1.0 + x[0] * x[1] - 2.0 * x[dim - 1] ** 2, x[0] ** 2 - 0.5 * x[1]])
+    data = G.DataFunction(u, [2, dim], bonus_quadorder=2)
+    t = G.FEVector([s])
+    t.entries[:] = 9.0
+    O = [G.BoundaryData(G.InterpolateDirichletBoundary, data=data, regions=[1, 2]), G.BoundaryData(G.HomogeneousDirichletBoundary, regions=[4])]
+    fixed = G.boundarydata(t[1], O)
+    assert len(set(fixed)) == fixed.size
+    reg12 = np.unique(s.bfacedofs[np.isin(g.bfaceregions, [1, 2])])
+    reg4 = np.unique(s.bfacedofs[np.isin(g.bfaceregions, [4])])
+    assert set(fixed) == set(reg12) | set(reg4)
+    en = (g.facenodes if dim == 2 else g.edgenodes).astype(np.int64) - 1
+    xdof = np.concatenate([g.coords, 0.5 * (g.coords[en[:, 0]] + g.coords[en[:, 1]])])
+    exact = np.concatenate(list(u(xdof.T)))                  # component-major dof numbering
+    only12 = np.setdiff1d(reg12, reg4) - 1
+    assert np.abs(t.entries[only12] - exact[only12]).max() < 1e-13
+    assert np.all(t.entries[reg4 - 1] == 0.0)
+    untouched = np.setdiff1d(np.arange(s.ndofs), fixed - 1)
+    assert np.all(t.entries[untouched] == 9.0)
