@@ -700,28 +700,37 @@ int grmp_blf_numeric_steps(grmp_blf* b, double factor, int nsteps, double* total
   GRMP_CUDA(cudaSetDevice(ctx->device));
   BlfLocalParams p;
   GRMP_TRY(fill_blf_params(b, factor, &p));
+  // Steps are replayed as a CUDA graph holding a chunk of steps: smaller gaps between the launches, and the programmatic edges
+  // between the kernels of consecutive steps (fast path) survive inside the graph.  The graph is set-up work like the symbolic
+  // pass: captured and instantiated before the timed region starts (capturing launches nothing).
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int chunk = 0;
+  if (nsteps > 2 && !getenv("GRMP_NO_GRAPH")) {
+    chunk = std::min(nsteps, getenv("GRMP_GRAPH_STEPS") ? std::max(1, atoi(getenv("GRMP_GRAPH_STEPS"))) : 8);
+    GRMP_TRY(blf_numeric_launch(b, p, s));      // one plain step first: lazy one-time work (coordinate repack, attributes) stays out of the capture
+    GRMP_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    int rc = GRMP_OK;
+    for (int j = 0; j < chunk && rc == GRMP_OK; j++) rc = blf_numeric_launch(b, p, s);
+    const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (!(rc == GRMP_OK && ce == cudaSuccess && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess)) {
+      (void)cudaGetLastError();     // capture not possible: plain launches below
+      if (exec) cudaGraphExecDestroy(exec);
+      exec = nullptr;
+    } else {
+      cudaGraphUpload(exec, s);
+    }
+  }
   GRMP_CUDA(cudaStreamSynchronize(s));
   GRMP_CUDA(cudaEventRecord(ctx->ev0, s));
   int k = 0;
-  if (nsteps > 0) { GRMP_TRY(blf_numeric_launch(b, p, s)); k = 1; }
-  if (nsteps > 2 && !getenv("GRMP_NO_GRAPH")) {
-    // the remaining steps replay one captured step (two kernels) as a CUDA graph: smaller gaps between the launches
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
-    GRMP_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    const int rc = blf_numeric_launch(b, p, s);
-    const cudaError_t ce = cudaStreamEndCapture(s, &graph);
-    if (rc == GRMP_OK && ce == cudaSuccess && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
-      for (; k < nsteps; k++) GRMP_CUDA(cudaGraphLaunch(exec, s));
-    } else {
-      (void)cudaGetLastError();     // capture not possible: plain launches below
-    }
-    if (exec) cudaGraphExecDestroy(exec);
-    if (graph) cudaGraphDestroy(graph);
-  }
+  if (exec)
+    for (; k + chunk <= nsteps; k += chunk) GRMP_CUDA(cudaGraphLaunch(exec, s));
   for (; k < nsteps; k++) GRMP_TRY(blf_numeric_launch(b, p, s));
   GRMP_CUDA(cudaEventRecord(ctx->ev1, s));
   GRMP_CUDA(cudaStreamSynchronize(s));
+  if (exec) cudaGraphExecDestroy(exec);
+  if (graph) cudaGraphDestroy(graph);
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   if (total_ms) *total_ms = ms;

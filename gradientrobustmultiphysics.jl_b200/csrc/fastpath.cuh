@@ -22,7 +22,7 @@ struct FastP2Tet {
   DevBuf<u32> end_slots;          // per pair, only when a partition produced multi-chain halo columns
   DevBuf<u32> vcols;              // vertex columns
   DevBuf<uint4> vrec;             // per vertex column: diagonal slot, first slot, #slots
-  DevBuf<int> tile_counter;       // dynamic tile scheduler of the edge kernel
+  DevBuf<unsigned long long> tile_counter;   // dynamic tile scheduler of the edge kernel: running claim counter, never reset
   i64 nvcols = 0;
   i64 halo_first = -1;            // first nzval slot of the columns another rank owns (>= nnz: none): never written by the kernels
   DevBuf<unsigned long long> prof; // GRMP_FAST_PROF: cycle counters of the last launch (8 per CTA)

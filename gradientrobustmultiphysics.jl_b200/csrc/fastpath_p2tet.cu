@@ -282,7 +282,11 @@ struct EdgeParams {
   double factor;
   double* nzval;
   i64 halo_first;           // first slot of the halo columns: group ranges are stored up to here only
-  int* tile_counter;        // dynamic tile scheduler: next unclaimed tile (zero at launch; reset by the diagonal kernel)
+  unsigned long long* tile_counter;   // dynamic tile scheduler: running claim counter.  Every CTA claims until its first miss, so one launch
+                            // advances it by exactly claims_per_step = ntiles + gridDim.x and claim c belongs to tile c % claims_per_step:
+                            // no reset between launches, which lets the next launch start (programmatic dependent launch) before
+                            // the diagonal kernel of this one has finished
+  u32 claims_per_step;
   int ntiles;
   u32 in_stride;            // bytes of one input buffer (largest blob)
   u32 slot_elems;           // doubles per warp stage slot
@@ -292,6 +296,10 @@ struct EdgeParams {
                             // walk, 8 skip the bulk stores, 16 mirror stores without the evict-last hint, 32 / 64 evict-first hint on the
                             // bulk stores / blob loads
 };
+
+// programmatic dependent launch (no-ops when the kernel was launched without the attribute)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ double fast_rcp(double d) {   // 1/d to ~1 ulp for normal d: MUFU.RCP64H + two Newton steps
   double r;
@@ -393,8 +401,14 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // the diagonal kernel may become resident as the CTAs of this grid retire; it waits for the whole grid before it reads
+    pdl_launch_dependents();
   }
   __syncthreads();
+  // Until pdl_wait() this kernel only reads what no earlier kernel of the stream writes after the symbolic pass (blobs, tile
+  // directory) and claims tiles: with a programmatic launch the first tile is loaded and walked while the previous step's
+  // diagonal kernel drains.  Every thread passes pdl_wait() before its first global store.
+  bool waited = false;
   if (warp >= NW) {   // ---- service warps ----
     const u64 pol_stream = l2_policy_evict_first();
     const int slane = tid - NW * 32;                        // 0 .. 32 NSVC - 1; thread 0 of the service warps loads tiles
@@ -407,13 +421,14 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
       uint2 dir = make_uint2(0, 0);
       if (slane == 0) {
         // tiles are claimed dynamically: SMs do not run at the same speed, a static split leaves the slowest SM as the tail
-        t = atomicAdd(p.tile_counter, 1);
+        t = (int)(atomicAdd(p.tile_counter, 1ull) % p.claims_per_step);
         if (t < p.ntiles) dir = __ldg(p.tile_dir + t);
       }
       if (use >= 1) {
         const long long c0 = clock64();
         mbar_wait(done_a + 8 * b, (unsigned)(use - 1) & 1u);   // all consumer warps have left the tile in this buffer
         const long long c1 = clock64();
+        if (!waited) { pdl_wait(); waited = true; }
         if (!(p.dbg & 1)) mirror_writeout(p, smraw + (size_t)b * p.in_stride, slane, 32 * NSVC);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // parked values (generic writes) before the next bulk load
         c_wait += c1 - c0; c_wo += clock64() - c1;
@@ -439,8 +454,10 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
     for (int j = (it >= NB - 1 ? it - (NB - 1) : 0); j < it; j++) {
       const int b2 = j % NB;
       mbar_wait(done_a + 8 * b2, (unsigned)(j / NB) & 1u);
+      if (!waited) { pdl_wait(); waited = true; }
       if (!(p.dbg & 1)) mirror_writeout(p, smraw + (size_t)b2 * p.in_stride, slane, 32 * NSVC);
     }
+    if (!waited) pdl_wait();
     if (p.prof != nullptr && slane == 0) {
       unsigned long long* q = p.prof + 8 * (size_t)blockIdx.x;
       q[0] = (unsigned long long)c_wait; q[1] = (unsigned long long)c_wo; q[2] = (unsigned long long)(clock64() - c_start); q[7] = (unsigned long long)it;
@@ -606,6 +623,7 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // stage writes -> visible to the bulk store
     __syncwarp();
+    if (!waited) { pdl_wait(); waited = true; }
     {
       // the group's nzval range is contiguous: one TMA bulk store (cp.async.bulk shared -> global) of the 16-byte aligned
       // body, the (at most one) unaligned element at either end by ordinary stores
@@ -628,6 +646,7 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
     if (++cur == NB) { cur = 0; use++; }
   }
   if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must stay alive until read
+  if (!waited) pdl_wait();
   if (p.prof != nullptr && tid == 0) {
     unsigned long long* q = p.prof + 8 * (size_t)blockIdx.x;
     q[3] = (unsigned long long)cc_wait; q[4] = (unsigned long long)(clock64() - cc_start);
@@ -640,13 +659,15 @@ __global__ void __launch_bounds__((NW + NSVC) * 32, (NW >= 5 ? 2 : NW == 4 ? 3 :
 // column only -- ~15 of its ~65 entries, every one of them mirrored into place by the edge kernel.  Columns with more than 128
 // entries (vertices of very high valence) use the plain column sum instead: A[v,v] = -sum_{i != v} A[i,v] (P2 partition of
 // unity).  Eight lanes per column, fixed shuffle tree -> deterministic.
-// vrec: {diagonal slot | NONE, first slot, #slots, mode}, {row-is-vertex mask x4}.  Also re-arms the edge kernel's tile scheduler.
-__global__ void __launch_bounds__(256) p2tet_vertex_diag_kernel(const uint4* __restrict__ vrec, i64 nv, double* nzval, int* tile_counter) {
+// vrec: {diagonal slot | NONE, first slot, #slots, mode}, {row-is-vertex mask x4}.
+__global__ void __launch_bounds__(256) p2tet_vertex_diag_kernel(const uint4* __restrict__ vrec, i64 nv, double* nzval) {
   const i64 w = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 3;
   const int sub = threadIdx.x & 7;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *tile_counter = 0;
+  // once the last wave of this grid is resident the next step's edge kernel may start loading its first tiles
+  if (threadIdx.x == 0) pdl_launch_dependents();
   uint4 r = make_uint4(NONE, 0, 0, 0), m = make_uint4(0, 0, 0, 0);
-  if (w < nv) { r = __ldg(vrec + 2 * w); m = __ldg(vrec + 2 * w + 1); }
+  if (w < nv) { r = __ldg(vrec + 2 * w); m = __ldg(vrec + 2 * w + 1); }      // records of the symbolic pass: not written by the edge kernel
+  pdl_wait();                                                                 // the edge kernel's stores (all of nzval) are complete and visible
   double s = 0.0;
   if (r.x != NONE) {
     const double* __restrict__ c = nzval + r.y;
@@ -1140,7 +1161,7 @@ static int fast_p2tet_build_device(grmp_ctx* ctx, const BlfLocalParams& p, const
     GRMP_CUDA(cudaMemsetAsync(out->prof.p, 0, out->prof.bytes(), s));
   }
   GRMP_TRY(out->tile_counter.alloc(1));
-  GRMP_CUDA(cudaMemsetAsync(out->tile_counter.p, 0, sizeof(int), s));
+  GRMP_CUDA(cudaMemsetAsync(out->tile_counter.p, 0, sizeof(unsigned long long), s));
   // (3) records into the blobs, mirror candidates sorted by destination
   DevBuf<u32> d_mkey, d_mval, d_mkey2, d_mval2;
   const i64 nm1 = std::max<i64>(nmir_total, 1);
@@ -1496,7 +1517,7 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
     GRMP_CUDA(cudaMemsetAsync(out->prof.p, 0, out->prof.bytes(), s));
   }
   GRMP_TRY(out->tile_counter.alloc(1));
-  GRMP_CUDA(cudaMemsetAsync(out->tile_counter.p, 0, sizeof(int), s));
+  GRMP_CUDA(cudaMemsetAsync(out->tile_counter.p, 0, sizeof(unsigned long long), s));
   lap("tile tables upload");
   // (3) pack column / pair records into the tile blobs on the device (slots are looked up in the pattern by (row, col)),
   //     sort every tile's mirror candidates by destination slot
@@ -1551,39 +1572,60 @@ int fast_p2tet_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat,
   return GRMP_OK;
 }
 
-template <int NW> int launch_edge(const EdgeParams& ep, FastP2Tet& f, int sm_count, cudaStream_t s) {
+template <int NW> int launch_edge(const EdgeParams& ep, FastP2Tet& f, int sm_count, cudaStream_t s, bool pdl) {
   int per_sm = 0;
   GRMP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p2tet_edge_kernel<NW>, (NW + NSVC) * 32, (size_t)f.smem_bytes));
   if (per_sm < 1) return fail(GRMP_ECUDA, "fast path: edge kernel does not fit on an SM");
   const int grid = std::min(std::min(f.ntiles, per_sm * sm_count), 1024);
   f.grid = grid;
-  p2tet_edge_kernel<NW><<<grid, (NW + NSVC) * 32, f.smem_bytes, s>>>(ep);
+  EdgeParams e2 = ep;
+  e2.claims_per_step = (u32)(f.ntiles + grid);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((NW + NSVC) * 32); cfg.dynamicSmemBytes = (size_t)f.smem_bytes; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  GRMP_CUDA(cudaLaunchKernelEx(&cfg, p2tet_edge_kernel<NW>, e2));
   return GRMP_OK;
 }
 
 int fast_p2tet_numeric(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, FastP2Tet& f, i64 geom_version, double* nzval) {
   static const int dbg = getenv("GRMP_DEBUG_FLAGS") ? atoi(getenv("GRMP_DEBUG_FLAGS")) : 0;
+  // programmatic dependent launch (GRMP_NO_PDL=1 disables it): the edge kernel may overlap the tail of the kernel before it in the
+  // stream only if that kernel is the previous step's diagonal kernel -- not when the tile coordinates were just rewritten
+  // GRMP_PDL: bit 0 = the diagonal kernel is a programmatic dependent of the edge kernel, bit 1 = the edge kernel of the diagonal kernel before it.
+  // Measured (profiles/r2_metric_kernel_experiments.md, 5): bit 1 gains 0.1 % at level 6 and 1.2 % at level 5 (= one rank of eight); bit 0 lets
+  // idle diagonal CTAs take the SMs of retired edge CTAs and costs 1.5 % at level 6 -> default 2
+  const int pdl_mode = getenv("GRMP_NO_PDL") ? 0 : (getenv("GRMP_PDL") ? atoi(getenv("GRMP_PDL")) : 2);
+  const bool use_pdl = (pdl_mode & 1) != 0;
+  // ... and only if a diagonal kernel separates consecutive edge kernels (two edge grids must never claim tiles concurrently)
+  bool pdl_edge = (pdl_mode & 2) && f.nvcols > 0 && !(dbg & 2);
   if (f.ntiles > 0 && f.geom_version != geom_version) {
+    pdl_edge = false;
     repack_tile_coords<<<f.ntiles, 128, 0, ctx->stream>>>(reinterpret_cast<const TileHdr*>(f.tile_hdr.p), f.tile_nodeids.p, p.g.coords, f.blob.p);
     GRMP_CUDA(cudaGetLastError());
     f.geom_version = geom_version;
   }
   if (f.ntiles > 0) {
-    EdgeParams ep{f.tile_dir.p, f.blob.p, f.end_slots.p, p.factor, nzval, f.halo_first, f.tile_counter.p, f.ntiles, f.in_stride, f.slot_elems, f.nbuf, f.prof.p, dbg};
+    EdgeParams ep{f.tile_dir.p, f.blob.p, f.end_slots.p, p.factor, nzval, f.halo_first, f.tile_counter.p, 0u, f.ntiles, f.in_stride, f.slot_elems, f.nbuf, f.prof.p, dbg};
     switch (f.nw) {
-      case 3: GRMP_TRY(launch_edge<3>(ep, f, ctx->sm_count, ctx->stream)); break;
-      case 4: GRMP_TRY(launch_edge<4>(ep, f, ctx->sm_count, ctx->stream)); break;
-      case 5: GRMP_TRY(launch_edge<5>(ep, f, ctx->sm_count, ctx->stream)); break;
-      case 6: GRMP_TRY(launch_edge<6>(ep, f, ctx->sm_count, ctx->stream)); break;
-      default: GRMP_TRY(launch_edge<7>(ep, f, ctx->sm_count, ctx->stream)); break;
+      case 3: GRMP_TRY(launch_edge<3>(ep, f, ctx->sm_count, ctx->stream, pdl_edge)); break;
+      case 4: GRMP_TRY(launch_edge<4>(ep, f, ctx->sm_count, ctx->stream, pdl_edge)); break;
+      case 5: GRMP_TRY(launch_edge<5>(ep, f, ctx->sm_count, ctx->stream, pdl_edge)); break;
+      case 6: GRMP_TRY(launch_edge<6>(ep, f, ctx->sm_count, ctx->stream, pdl_edge)); break;
+      default: GRMP_TRY(launch_edge<7>(ep, f, ctx->sm_count, ctx->stream, pdl_edge)); break;
     }
     GRMP_CUDA(cudaGetLastError());
   }
   if (f.nvcols > 0 && !(dbg & 2)) {
-    p2tet_vertex_diag_kernel<<<(unsigned)((f.nvcols * 8 + 255) / 256), 256, 0, ctx->stream>>>(f.vrec.p, f.nvcols, nzval, f.tile_counter.p);
-    GRMP_CUDA(cudaGetLastError());
-  } else if (f.ntiles > 0) {
-    GRMP_CUDA(cudaMemsetAsync(f.tile_counter.p, 0, sizeof(int), ctx->stream));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((f.nvcols * 8 + 255) / 256)); cfg.blockDim = dim3(256); cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (use_pdl && f.ntiles > 0) ? 1 : 0;
+    GRMP_CUDA(cudaLaunchKernelEx(&cfg, p2tet_vertex_diag_kernel, (const uint4*)f.vrec.p, (i64)f.nvcols, nzval));
   }
   return GRMP_OK;
 }
