@@ -103,6 +103,27 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa(local_rank):
+    """N > 1: run this rank (and first-touch its pinned buffers) on the CPUs closest to its GPU (nvmlDeviceGetCpuAffinity);
+    returns the CPU list or None.  GRMP_BENCH_NO_BIND=1 disables it."""
+    if os.environ.get("GRMP_BENCH_NO_BIND"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hdl = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(hdl, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed and len(allowed) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, allowed)
+            return allowed
+    except Exception:
+        pass
+    return None
+
+
 def build_problem(level):
     import grmp_b200 as G
     t = time.time()
@@ -197,6 +218,7 @@ def run_gpu(args):
         args.gpus = world
     torch.cuda.set_device(local_rank)
     dist = None
+    bound = bind_to_gpu_numa(local_rank) if world > 1 else None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -363,6 +385,7 @@ def run_gpu(args):
                                  "(grmp_blf_residual, solvers.jl:661-668)"},
         "gpu_launches": launches,
         "roofline": roofline,
+        "host_affinity": ({"rank0_cpus": bound} if bound else None),
         "per_rank_ms": {"min": srt[0], "median": srt[len(srt) // 2], "max": srt[-1], "all": per_rank_ms},
         "parity": par,
         "cpu_baseline": cpu,
