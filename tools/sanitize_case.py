@@ -31,3 +31,27 @@ print("lf sum", b.entries.sum())
 u = G.FEVector([s])
 u.entries[:] = 1.0
 print("integral of 1 =", G.evaluate(G.ItemIntegrator([G.Identity]), u[1]))
+# several steps back to back: the edge kernel runs as a programmatic dependent of the previous diagonal kernel (multi-step graph)
+import ctypes as C
+ms = C.c_double(0)
+G._lib.check(G._lib.lib().grmp_blf_numeric_steps(AP.AM.h, 1.0, 12, C.byref(ms)))
+print("12 chained steps equal the single step:", np.array_equal(G.fetch_values(AP), nz))
+# boundary-face items (ON_BFACES), convection form with a coefficient argument, Newton form
+for gg, fe in ((g2, G.H1P2(2, 2)), (g, G.H1P2(1, 3))):
+    sb = G.FESpace(fe, gg)
+    M = G.assemble_csc(G.DiscreteSymmetricBilinearForm([G.Identity, G.Identity], [sb, sb], AT="ON_BFACES"), 1.0)[2]
+    bb = G.FEVector([sb])
+    G.assemble(bb[1], G.DiscreteLinearForm([G.Identity], [sb], G.fdot_action(G.DataFunction(np.ones(fe.ncomponents))), AT="ON_BFACES"))
+    print("boundary measure x ncomp:", M.sum(), bb.entries.sum())
+sv = G.FESpace(G.H1P2(2, 2), g2)
+a = G.FEVector([sv])
+a.entries[:] = np.linspace(0.0, 1.0, sv.ndofs)
+Oc = G.ConvectionOperator(1, G.Identity, 2, 2)
+A = G.FEMatrix([sv])
+G.assemble_operator(A[1, 1], Oc, CurrentSolution=a)
+print("convection nnz", A.nnz)
+On = G.ConvectionOperator(1, G.Identity, 2, 2, newton=True)
+A2 = G.FEMatrix([sv])
+rhs = G.FEVector([sv])
+G.full_assemble_operator(A2[1, 1], rhs[1], On, CurrentSolution=a)
+print("newton nnz", A2.nnz, float(np.abs(rhs.entries).sum()) > 0)
