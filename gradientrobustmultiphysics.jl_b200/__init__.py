@@ -16,7 +16,7 @@ from .grid import (ExtendableGrid, grid_unitsquare, grid_unitcube, reference_dom
 from .quadrature import QuadratureRule
 from .fedefs import H1P1, H1P2, H1Pk, H1BR, HDIVRT0, HDIVBDM1, L2P0, reference_tables
 from .fespace import FESpace, FEVector, FEMatrix, FEMatrixBlock, FEVectorBlock
-from .assembly import (Identity, Gradient, SymmetricGradient, Divergence, ReconstructionIdentity, NoAction, HookeAction, ConvectionAction, NewtonConvectionAction, DiscreteNonlinearForm, full_assemble, Action,
+from .assembly import (Identity, NormalFlux, fdotn_action, Gradient, SymmetricGradient, Divergence, ReconstructionIdentity, NoAction, HookeAction, ConvectionAction, NewtonConvectionAction, DiscreteNonlinearForm, full_assemble, Action,
                        DataFunction, fdot_action, AssemblyPattern, DiscreteBilinearForm, DiscreteSymmetricBilinearForm,
                        DiscreteLumpedBilinearForm, DiscreteLinearForm, prepare_assembly, assemble, assemble_csc, blf_set_path,
                        blf_stats, quadrature_order, device_grid, device_space, addblock_matmul, residual, apply_penalties,

@@ -78,7 +78,13 @@ class ReconstructionIdentity(AbstractFunctionOperator):
         return hash(("R", self.code))
 
 
+class _NormalFlux(AbstractFunctionOperator):
+    """NormalFlux (functionoperators.jl:49): v_h . n_F of an Hdiv function on (boundary) faces, feevaluator_hdiv.jl:42-50"""
+    code, name = 7, "NormalFlux"
+
+
 Identity = _Identity()
+NormalFlux = _NormalFlux()
 Gradient = _Gradient()
 SymmetricGradient = _SymmetricGradient
 Divergence = _Divergence()
@@ -171,6 +177,21 @@ def fdot_action(data):
     return _FDotAction(data)
 
 
+class _FDotNAction(_FDotAction):
+    """fdotn_action(data, xgrid; bfaces = true) (actions.jl:175-192): f(x) . n_F of the boundary face, one component"""
+
+    def __init__(self, data: DataFunction, xgrid):
+        super().__init__(data)
+        self.xgrid = xgrid
+        self.name = data.name + "⋅n"
+
+
+def fdotn_action(data, xgrid, bfaces=True):
+    if not bfaces:
+        raise NotImplementedError("fdotn_action on all faces belongs to ON_FACES assembly (not on the device)")
+    return _FDotNAction(data, xgrid)
+
+
 # numeric back end requested for newly prepared bilinear forms (include/grmp.h GRMP_PATH_*); tests pin the bit-exact path here
 DEFAULT_PATH = _lib.PATH_AUTO
 
@@ -208,7 +229,7 @@ def device_grid(xgrid, need_faces=False):
 
 
 def device_space(FES):
-    need_faces = FES.fetype.code in (3, 4, 5)
+    need_faces = FES.fetype.code in (3, 4, 5) and not getattr(FES.xgrid, "embedded", False)    # face bases carry no coefficients
     gh = device_grid(FES.xgrid, need_faces)
     d = getattr(FES, "_dev", None)
     if d is None:
@@ -332,7 +353,7 @@ def _tables(FES, op, qf):
     vals, der = reference_tables(fe, edim, qf.xref, op.needed_derivative > 0)
     vals = np.ascontiguousarray(vals)
     der = None if der is None else np.ascontiguousarray(der)
-    tab = _lib.EvalTab(fe.ndofs_all(edim), fe.ncomponents, _lib.ptr(vals), _lib.ptr(der))
+    tab = _lib.EvalTab(fe.ndofs_all(edim), vals.shape[2], _lib.ptr(vals), _lib.ptr(der))
     return tab, (vals, der)
 
 
@@ -538,8 +559,20 @@ def _qp_table(AP, P):
     """host evaluation of the DataFunction at x = b + A*xref (eval_trafo!, linearform.jl:197-201)"""
     data = AP.action.data
     g = AP.item_space(0).xgrid
+    if isinstance(AP.action, _FDotNAction):     # f(x) . n_F per boundary face: item dependent, always a table
+        pg = g.parent
+        nrm = pg.facenormals[pg.bfacefaces.astype(np.int64) - 1]
+        if data.constant is not None:
+            vals = np.broadcast_to(data.constant, (g.ncells, len(P.qf), data.constant.size))
+        else:
+            vals = _qp_table_values(data, g, P)
+        return 2, np.ascontiguousarray((vals * nrm[:, None, :]).sum(axis=2)[:, :, None])
     if data.constant is not None:
         return 1, data.constant
+    return 2, _qp_table_values(data, g, P)
+
+
+def _qp_table_values(data, g, P):
     x = g.coords
     cn = g.cellnodes.astype(np.int64) - 1
     b = x[cn[:, 0]]
@@ -553,7 +586,7 @@ def _qp_table(AP, P):
         vals = vals.reshape(-1, flat.shape[0]).T
     except Exception:
         vals = np.array([np.atleast_1d(data.kernel(p)) for p in flat], dtype=np.float64)
-    return 2, np.ascontiguousarray(vals.reshape(g.ncells, len(P.qf), -1))
+    return np.ascontiguousarray(vals.reshape(g.ncells, len(P.qf), -1))
 
 
 def _assemble_lf(b, AP, factor=1, skip_preps=False, offset=0, feb=None):
@@ -666,4 +699,4 @@ def evaluate(AP: AssemblyPattern, FEB, skip_preps=False):
 def _resultdim(AP):
     F, o = AP.FES[-1], AP.operators[-1]
     edim, nc = F.xgrid.dim, F.fetype.ncomponents
-    return {1: nc, 5: nc, 6: nc, 2: edim * nc, 3: (3 if edim == 2 else 6), 4: max(1, nc // edim)}[o.code]
+    return {1: nc, 5: nc, 6: nc, 7: 1, 2: edim * nc, 3: (3 if edim == 2 else 6), 4: max(1, nc // edim)}[o.code]

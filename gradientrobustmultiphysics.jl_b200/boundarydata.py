@@ -1,4 +1,5 @@
-"""Dirichlet boundary data (host mirror of src/boundarydata.jl:60-420) for H1P1 / H1P2 spaces.
+"""Dirichlet boundary data (host mirror of src/boundarydata.jl:60-420) for H1P1 / H1P2 spaces (Identity trace) and HDIVRT0 / HDIVBDM1
+spaces (NormalFlux trace, best approximation and homogeneous data).
 
 `boundarydata(Target, O)` fills the boundary dofs of `Target` and returns `fixed_dofs` (1-based), in the reference's order:
 interpolated regions, homogeneous regions, best-approximation regions.  What it costs on the device is the best-approximation
@@ -11,8 +12,9 @@ from __future__ import annotations
 
 import numpy as np
 
-from .assembly import DataFunction, DiscreteLinearForm, DiscreteSymmetricBilinearForm, Identity, assemble, assemble_csc, fdot_action
-from .fedefs import H1P1, H1P2
+from .assembly import (DataFunction, DiscreteLinearForm, DiscreteSymmetricBilinearForm, Identity, NormalFlux, assemble, assemble_csc, fdot_action,
+                       fdotn_action)
+from .fedefs import H1P1, H1P2, HDIVBDM1, HDIVRT0
 from .fespace import FEVector, FEVectorBlock
 from .quadrature import QuadratureRule
 
@@ -77,8 +79,13 @@ def _interpolate_bfaces(Target, FES, data, bfaces):
 def boundarydata(Target: FEVectorBlock, O, fixed_penalty=1e60):
     """boundarydata!(Target, O; fixed_penalty) -> fixed_dofs (1-based, the reference's order)"""
     FES = Target.FES
-    if not isinstance(FES.fetype, (H1P1, H1P2)) or FES.broken:
-        raise NotImplementedError("boundary data on the device path: H1P1 / H1P2 spaces (Identity trace); others stay with the reference")
+    hdiv = isinstance(FES.fetype, (HDIVRT0, HDIVBDM1))
+    if not isinstance(FES.fetype, (H1P1, H1P2, HDIVRT0, HDIVBDM1)) or FES.broken:
+        raise NotImplementedError("boundary data on the device path: H1P1 / H1P2 (Identity trace) and HDIVRT0 / HDIVBDM1 (NormalFlux); others stay "
+                                  "with the reference")
+    if hdiv and any(bd.btype == InterpolateDirichletBoundary for bd in O):
+        raise NotImplementedError("interpolated Hdiv boundary data (face moments, hdiv_rt0.jl:37-52) stays with the reference; use the best approximation")
+    Dbop = NormalFlux if hdiv else Identity            # DefaultDirichletBoundaryOperator4FE (boundarydata.jl:27-29)
     g = FES.xgrid
     bdm = FES.bfacedofs.astype(np.int64)
     breg = g.bfaceregions
@@ -108,10 +115,11 @@ def boundarydata(Target: FEVectorBlock, O, fixed_penalty=1e60):
         for bd in ba:
             _, bd.bdofs = dofs_of(bd.bregions)
             baregions += bd.bregions
-            rhs = DiscreteLinearForm([Identity], [FES], fdot_action(bd.data), regions=bd.bregions, AT="ON_BFACES", name="RHS bnd data bestapprox")
+            action = fdotn_action(bd.data, g, bfaces=True) if hdiv else fdot_action(bd.data)          # boundarydata.jl:299-303
+            rhs = DiscreteLinearForm([Dbop], [FES], action, regions=bd.bregions, AT="ON_BFACES", name="RHS bnd data bestapprox")
             assemble(b[1], rhs)
             badofs = _unique_in_order(np.concatenate([badofs, bd.bdofs]))
-        lhs = DiscreteSymmetricBilinearForm([Identity, Identity], [FES, FES], regions=baregions, AT="ON_BFACES", name="LHS bnd data bestapprox")
+        lhs = DiscreteSymmetricBilinearForm([Dbop, Dbop], [FES, FES], regions=baregions, AT="ON_BFACES", name="LHS bnd data bestapprox")
         cp, rv, nz = assemble_csc(lhs, 1.0)
         A = sp.csc_matrix((nz, rv - 1, cp - 1), shape=(FES.ndofs, FES.ndofs)).tolil()
         rhsv = b.entries.copy()

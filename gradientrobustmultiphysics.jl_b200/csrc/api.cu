@@ -23,6 +23,7 @@ int op_resultdim(int op, int ncomp, int edim) {   // Length4Operator, src/functi
     case GRMP_OP_GRAD: return edim * ncomp;
     case GRMP_OP_SYMGRAD: return ((edim == 2) ? 3 : 6) * ((ncomp + edim - 1) / edim);
     case GRMP_OP_DIV: return (ncomp + edim - 1) / edim;
+    case GRMP_OP_NORMALFLUX: return 1;
   }
   return -1;
 }
@@ -37,7 +38,12 @@ static int fe_family(int fetype) {
   return -1;
 }
 
-static int fe_local_dofs(int fetype, int ncomp, int edim, int* nd, int* nd_all, int* ncomp_eff) {
+static int fe_local_dofs(int fetype, int ncomp, int edim, int* nd, int* nd_all, int* ncomp_eff, bool on_faces = false) {
+  if (on_faces && (fetype == GRMP_FE_HDIVRT0 || fetype == GRMP_FE_HDIVBDM1)) {   // normal-flux face bases: scalar valued, "i1" / "i2" / "i3"
+    *ncomp_eff = 1;
+    *nd = *nd_all = (fetype == GRMP_FE_HDIVRT0) ? 1 : edim + 1;
+    return GRMP_OK;
+  }
   const int nn = edim + 1, nf = edim + 1, ne = (edim == 1) ? 1 : (edim == 2) ? 3 : 6;   // Edge1D: the interior dof takes the edge slot ("N1I1")
   *ncomp_eff = ncomp;
   switch (fetype) {
@@ -53,25 +59,28 @@ static int fe_local_dofs(int fetype, int ncomp, int edim, int* nd, int* nd_all, 
 
 int make_evalview(const grmp_space* sp, int op, const EvalTables& tab, EvalView* out) {
   const int edim = sp->grid->dim;
+  const bool on_faces = sp->grid->xdim != edim;
   EvalView e{};
   int nd, nd_all, nc;
-  GRMP_TRY(fe_local_dofs(sp->fetype, sp->ncomp, edim, &nd, &nd_all, &nc));
+  GRMP_TRY(fe_local_dofs(sp->fetype, sp->ncomp, edim, &nd, &nd_all, &nc, on_faces));
   e.fam = fe_family(sp->fetype);
   e.op = op; e.ncomp = nc; e.nd = nd; e.nd_all = nd_all;
   e.rd = op_resultdim(op, nc, edim);
   if (e.rd < 0) return fail(GRMP_EUNSUPPORTED, "unknown operator code");
   if (e.rd > 9) return fail(GRMP_EUNSUPPORTED, "operator result dimension > 9");
-  if (sp->grid->xdim != edim && !(e.fam == FAM_H1 && op == GRMP_OP_ID))
-    return fail(GRMP_EUNSUPPORTED, "boundary-face grids: Identity of H1P1 / H1P2 / L2P0 only");
+  const bool hdiv_fam = (e.fam == FAM_RT0 || e.fam == FAM_BDM1);
+  if (on_faces && !((e.fam == FAM_H1 && op == GRMP_OP_ID) || (hdiv_fam && op == GRMP_OP_NORMALFLUX)))
+    return fail(GRMP_EUNSUPPORTED, "boundary-face grids: Identity of H1P1 / H1P2 and NormalFlux of HDIVRT0 / HDIVBDM1 only");
+  if (!on_faces && op == GRMP_OP_NORMALFLUX) return fail(GRMP_EUNSUPPORTED, "NormalFlux lives on boundary-face grids (grmp_grid_create_bfaces)");
   const bool hdiv = (e.fam == FAM_RT0 || e.fam == FAM_BDM1);
-  if (hdiv && !(op == GRMP_OP_ID || op == GRMP_OP_DIV)) return fail(GRMP_EUNSUPPORTED, "Hdiv elements: Identity / Divergence only");
+  if (hdiv && !on_faces && !(op == GRMP_OP_ID || op == GRMP_OP_DIV)) return fail(GRMP_EUNSUPPORTED, "Hdiv elements: Identity / Divergence only");
   if (sp->fetype == GRMP_FE_L2P0 && op != GRMP_OP_ID) return fail(GRMP_EUNSUPPORTED, "L2P0: Identity only");
   if (op == GRMP_OP_SYMGRAD && nc != edim) return fail(GRMP_EINVAL, "SymmetricGradient requires ncomponents == dim");
   const bool recon = (op == GRMP_OP_RECON_ID_RT0 || op == GRMP_OP_RECON_ID_BDM1);
   if (recon && sp->fetype != GRMP_FE_H1BR) return fail(GRMP_EUNSUPPORTED, "ReconstructionIdentity is ported for H1BR only");
-  if ((hdiv || sp->fetype == GRMP_FE_H1BR) && !sp->grid->has_faces)
+  if ((hdiv || sp->fetype == GRMP_FE_H1BR) && !on_faces && !sp->grid->has_faces)
     return fail(GRMP_ESTATE, "grid face data missing: call grmp_grid_set_faces first");
-  if (e.fam == FAM_BDM1 && edim == 3 && sp->grid->orient.n == 0) return fail(GRMP_ESTATE, "CellFaceOrientations missing (BDM1 3D)");
+  if (e.fam == FAM_BDM1 && !on_faces && edim == 3 && sp->grid->orient.n == 0) return fail(GRMP_ESTATE, "CellFaceOrientations missing (BDM1 3D)");
   if (recon && op == GRMP_OP_RECON_ID_BDM1 && edim == 3 && sp->grid->orient.n == 0)
     return fail(GRMP_ESTATE, "CellFaceOrientations missing (BR->BDM1 3D)");
   e.tab_nd = nd_all; e.tab_nc = nc;
@@ -369,7 +378,7 @@ int grmp_grid_destroy(grmp_grid* g) { delete g; return GRMP_OK; }
 int grmp_space_create(grmp_grid* grid, int fetype, int ncomp, int64_t ndofs, int nd_cell, const int32_t* celldofs, grmp_space** out) {
   if (!grid || !celldofs || !out) return fail(GRMP_EINVAL, "grmp_space_create: NULL argument");
   int nd, nd_all, nc;
-  GRMP_TRY(fe_local_dofs(fetype, ncomp, grid->dim, &nd, &nd_all, &nc));
+  GRMP_TRY(fe_local_dofs(fetype, ncomp, grid->dim, &nd, &nd_all, &nc, grid->xdim != grid->dim));
   if (nd != nd_cell) return fail(GRMP_EINVAL, "nd_cell does not match the FEType on this geometry");
   grmp_space* s = new grmp_space();
   s->grid = grid; s->fetype = fetype; s->ncomp = ncomp; s->nd = nd; s->ndofs = ndofs;

@@ -27,7 +27,7 @@ struct Geo {
 // update_trafo! : A[:,j] = x_{j+1} - x_1 ; det from A
 __device__ __forceinline__ void geo_update(const GridView& g, i64 cell, Geo& T) {
   const int d = g.dim;
-  if (g.xdim != d) return;   // boundary-face items: only Identity evaluators are admitted (make_evalview), they need no map
+  if (g.xdim != d) { T.det = g.vol[cell]; return; }   // boundary-face items: Identity / NormalFlux evaluators only (make_evalview); no affine map, det carries |F|
   const i32* cn = g.cellnodes + cell * (d + 1);
   const double* x0 = g.coords + (i64)(cn[0] - 1) * d;
   double b[3];
@@ -88,6 +88,7 @@ __device__ void cell_coefficients(const GridView& g, i64 cell, int fam, int ndc,
     c.subset[dof] = dof;
     for (int k = 0; k < ncomp; k++) c.co[k][dof] = 1.0;
   }
+  if (g.xdim != d) return;   // face bases carry no coefficients (the boundary face is the first face of its only cell: sign +1)
   if (fam == FAM_H1BR) {  // h1v_br.jl:150-162, 253-273: bubble columns = face normal
     const i32* cf = g.cellfaces + cell * nf;
     for (int f = 0; f < nf; f++)
@@ -194,6 +195,10 @@ __device__ void eval_qp(const EvalView& e, int edim, const Geo& T, const CellCoe
           if (rc[di][dj] != 0) acc += rc[di][dj] * te[k][dj];
         cv[k][di] = acc;
       }
+    return;
+  }
+  if (e.op == GRMP_OP_NORMALFLUX) {  // feevaluator_hdiv.jl:42-50: refbasisvals / |F|
+    for (int dof = 0; dof < nd; dof++) cv[0][dof] = rv[dof * e.tab_nc] / T.det;
     return;
   }
   if (e.fam == FAM_RT0 || e.fam == FAM_BDM1) {

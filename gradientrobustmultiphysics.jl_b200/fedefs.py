@@ -258,17 +258,25 @@ class HDIVRT0(FEType):
         self.ncomponents = edim
         self.name = f"HDIVRT0{{{edim}}}"
 
-    def ndofs(self, edim):
-        return _nn(edim)
+    def ndofs(self, edim):            # hdiv_rt0.jl:21-22
+        return 1 if edim < self.edim else _nn(edim)
 
-    def polynomialorder(self, edim):
-        return 1
+    def ncomponents_on(self, edim):   # the face basis is the (scalar) normal flux
+        return 1 if edim < self.edim else self.ncomponents
+
+    def polynomialorder(self, edim):  # hdiv_rt0.jl:24-27
+        return 0 if edim < self.edim else 1
 
     def dofmap_pattern(self, edim):
         return "f1"
 
-    def basis(self, rb, x, edim):     # hdiv_rt0.jl:67-73, 84-92
-        if edim == 2:
+    def bface_dofmap_pattern(self, fdim):   # hdiv_rt0.jl:30
+        return "i1"
+
+    def basis(self, rb, x, edim):     # hdiv_rt0.jl:61-65 (faces), 67-73, 84-92
+        if edim < self.edim:
+            rb[0, 0] = 1.0
+        elif edim == 2:
             rb[0, 0] = x[0];        rb[0, 1] = x[1] - 1.0
             rb[1, 0] = x[0];        rb[1, 1] = x[1]
             rb[2, 0] = x[0] - 1.0;  rb[2, 1] = x[1]
@@ -290,11 +298,16 @@ class HDIVBDM1(FEType):
         self.ncomponents = edim
         self.name = f"HDIVBDM1{{{edim}}}"
 
-    def ndofs(self, edim):
-        return edim * _nn(edim)
+    def ndofs(self, edim):            # hdiv_bdm1.jl:20-23
+        return edim + 1 if edim < self.edim else edim * _nn(edim)
 
     def ndofs_all(self, edim):
+        if edim < self.edim:
+            return edim + 1
         return 2 * _nn(edim) if edim == 2 else 4 * _nn(edim)
+
+    def ncomponents_on(self, edim):
+        return 1 if edim < self.edim else self.ncomponents
 
     def polynomialorder(self, edim):
         return 1
@@ -302,8 +315,18 @@ class HDIVBDM1(FEType):
     def dofmap_pattern(self, edim):
         return "f2" if edim == 2 else "f3"
 
+    def bface_dofmap_pattern(self, fdim):   # hdiv_bdm1.jl:33, 36
+        return "i2" if fdim == 1 else "i3"
+
     def basis(self, rb, x, edim):
-        if edim == 2:
+        if edim < self.edim:          # normal-flux face bases, hdiv_bdm1.jl:74-79, 109-115
+            rb[0, 0] = 1.0
+            if edim == 1:
+                rb[1, 0] = 12.0 * (x[0] - 0.5)
+            else:
+                rb[1, 0] = 12.0 * (2.0 * x[0] + x[1] - 1.0)
+                rb[2, 0] = 12.0 * (2.0 * x[1] + x[0] - 1.0)
+        elif edim == 2:
             rb[0, 0] = x[0];        rb[0, 1] = x[1] - 1.0
             rb[2, 0] = x[0];        rb[2, 1] = x[1]
             rb[4, 0] = x[0] - 1.0;  rb[4, 1] = x[1]
@@ -361,7 +384,8 @@ def reference_tables(fetype: FEType, edim: int, xref: np.ndarray, derivatives: b
     Returns (values[nq, nd_all, ncomp], derivs[nq, edim, nd_all*ncomp] or None); these
     are laid out exactly as include/grmp.h expects them."""
     nq = xref.shape[0]
-    nda, nc = fetype.ndofs_all(edim), fetype.ncomponents
+    nda = fetype.ndofs_all(edim)
+    nc = fetype.ncomponents_on(edim) if hasattr(fetype, "ncomponents_on") else fetype.ncomponents
     vals = np.zeros((nq, nda, nc))
     der = np.zeros((nq, edim, nda * nc)) if derivatives else None
     for i in range(nq):

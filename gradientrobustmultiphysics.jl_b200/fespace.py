@@ -137,10 +137,13 @@ class FESpace:
         pattern = self.fetype.bface_dofmap_pattern(g.dim - 1)
         nb = g.bfacenodes.shape[0]
         cols = []
+        segs = parse_pattern(pattern)
         for c in range(self.ncomponents):
             offset = c * self.coffset
-            for ch, each, q in parse_pattern(pattern):
-                assert each and q == 1
+            for ch, each, q in segs:
+                if not each:
+                    continue
+                assert q == 1
                 if ch == "N":
                     adj, nitems = g.bfacenodes.astype(np.int64), g.nnodes
                 elif ch == "I":                      # interior dof of the face = face dof of the parent space
@@ -152,6 +155,15 @@ class FESpace:
                 for n in range(adj.shape[1]):
                     cols.append(adj[:, n] + offset)
                 offset += nitems
+        offset = self.ncomponents * self.coffset
+        for ch, each, q in segs:                     # "i<q>": q face dofs not tied to a component (Hdiv normal-flux dofs), dofmaps.jl:338-343
+            if each:
+                continue
+            if ch != "i":
+                raise NotImplementedError(f"BFaceDofs pattern segment {ch}")
+            for m in range(q):
+                cols.append(g.bfacefaces.astype(np.int64) + offset)
+                offset += g.nfaces
         dm = np.stack(cols, axis=1) if nb else np.zeros((0, len(cols)), np.int64)
         assert dm.max(initial=0) <= self.ndofs
         self._bfacedofs = np.ascontiguousarray(dm, dtype=np.int32)
@@ -172,10 +184,11 @@ class BFaceSpace:
 
     def __init__(self, parent: FESpace):
         if parent.broken or not hasattr(parent.fetype, "bface_dofmap_pattern"):
-            raise NotImplementedError(f"ON_BFACES assembly: H1P1 / H1P2 spaces, got {parent.name}")
+            raise NotImplementedError(f"ON_BFACES assembly: H1P1 / H1P2 / HDIVRT0 / HDIVBDM1 spaces, got {parent.name}")
         self.parent = parent
         self.fetype = parent.fetype
-        self.xgrid = parent.xgrid.bface_grid()
+        # Hdiv face bases are moments with respect to the face's own node order (FaceNodes): the items must carry that order
+        self.xgrid = parent.xgrid.bface_grid(face_order=bool(getattr(parent.fetype, "hdiv", False)))
         self.broken = False
         self.edim = self.xgrid.dim
         self.ncomponents = parent.ncomponents

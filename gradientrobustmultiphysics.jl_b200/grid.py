@@ -244,11 +244,12 @@ class ExtendableGrid:
             self._cache["bfaceedges"] = (be.reshape(-1, 3) + 1).astype(np.int32)
         return self._cache["bfaceedges"]
 
-    def bface_grid(self):
-        """the boundary faces as assembly items (AT = ON_BFACES)"""
-        if "bface_grid" not in self._cache:
-            self._cache["bface_grid"] = BFaceGrid(self)
-        return self._cache["bface_grid"]
+    def bface_grid(self, face_order=False):
+        """the boundary faces as assembly items (AT = ON_BFACES); face_order: item nodes in FaceNodes order instead of BFaceNodes order"""
+        key = "bface_grid_f" if face_order else "bface_grid"
+        if key not in self._cache:
+            self._cache[key] = BFaceGrid(self, face_order)
+        return self._cache[key]
 
 
 class BFaceGrid:
@@ -257,12 +258,13 @@ class BFaceGrid:
     coordinates keep the dimension of the parent grid."""
     embedded = True
 
-    def __init__(self, parent: "ExtendableGrid"):
+    def __init__(self, parent: "ExtendableGrid", face_order=False):
         self.parent = parent
         self.dim = parent.dim - 1
         self.xdim = parent.dim
         self.coords = parent.coords
-        self.cellnodes = parent.bfacenodes
+        self.cellnodes = (np.ascontiguousarray(parent.facenodes[parent.bfacefaces.astype(np.int64) - 1]) if face_order
+                          else parent.bfacenodes)
         self.cellregions = parent.bfaceregions
 
     @property

@@ -39,7 +39,8 @@ extern "C" {
 /* FEType codes (src/fedefs/{h1_p1,h1_p2,h1v_br,hdiv_rt0,hdiv_bdm1,l2_p0}.jl) */
 enum { GRMP_FE_H1P1 = 1, GRMP_FE_H1P2 = 2, GRMP_FE_H1BR = 3, GRMP_FE_HDIVRT0 = 4, GRMP_FE_HDIVBDM1 = 5, GRMP_FE_L2P0 = 6 };
 /* function operators (src/functionoperators.jl:13-153) */
-enum { GRMP_OP_ID = 1, GRMP_OP_GRAD = 2, GRMP_OP_SYMGRAD = 3, GRMP_OP_DIV = 4, GRMP_OP_RECON_ID_RT0 = 5, GRMP_OP_RECON_ID_BDM1 = 6 };
+enum { GRMP_OP_ID = 1, GRMP_OP_GRAD = 2, GRMP_OP_SYMGRAD = 3, GRMP_OP_DIV = 4, GRMP_OP_RECON_ID_RT0 = 5, GRMP_OP_RECON_ID_BDM1 = 6,
+       GRMP_OP_NORMALFLUX = 7 /* Hdiv elements on boundary-face grids only: feevaluator_hdiv.jl:42-50 */ };
 /* actions evaluated on the device (src/actions.jl:96-110 NoAction; src/pdeoperators.jl:265-270, 304-312 Hooke tensors) */
 enum { GRMP_ACT_NONE = 0, GRMP_ACT_HOOKE2D = 1, GRMP_ACT_HOOKE3D = 2,
        GRMP_ACT_CONVECTION = 3 /* needs a fixed argument, see grmp_blf_set_fixed_argument */,
@@ -108,8 +109,9 @@ int grmp_grid_create(grmp_ctx* ctx, int dim, int64_t nnodes, const double* coord
 /* The boundary faces as assembly items: AT = ON_BFACES (assemblypatterns.jl:400-440 reads BFaceNodes / BFaceVolumes /
  * BFaceRegions through GridComponent*4AssemblyType and FES[BFaceDofs] through Dofmap4AssemblyType, dofmaps.jl:45; call
  * sites: the best-approximation Dirichlet data of boundarydata.jl:297-347).  The returned grid has item dimension
- * xdim-1 (Edge1D / Triangle2D); spaces on it take FES[BFaceDofs] as `celldofs`.  Identity evaluators of H1P1 / H1P2
- * (scalar or vector valued) are admitted, everything else returns GRMP_EUNSUPPORTED and stays with the reference.
+ * xdim-1 (Edge1D / Triangle2D); spaces on it take FES[BFaceDofs] as `celldofs`.  Admitted: Identity of H1P1 / H1P2 (scalar
+ * or vector valued) and NormalFlux of HDIVRT0 / HDIVBDM1 (face bases hdiv_rt0.jl:61-65, hdiv_bdm1.jl:74-79, 109-115; 1 / 2 / 3
+ * dofs per face, evaluator tables with one component); everything else returns GRMP_EUNSUPPORTED and stays with the reference.
  * All forms on such a grid run on the bit-exact path. */
 int grmp_grid_create_bfaces(grmp_ctx* ctx, int xdim, int64_t nnodes, const double* coords, int64_t nbfaces,
                             const int32_t* bfacenodes, const double* bfacevolumes, const int32_t* bfaceregions,

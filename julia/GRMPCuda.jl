@@ -51,6 +51,7 @@ opcode(::Type{SymmetricGradient{1}}) = 3
 opcode(::Type{Divergence}) = 4
 opcode(::Type{ReconstructionIdentity{FER}}) where {FER<:HDIVRT0} = 5
 opcode(::Type{ReconstructionIdentity{FER}}) where {FER<:HDIVBDM1} = 6
+opcode(::Type{NormalFlux}) = 7                  # Hdiv spaces on boundary faces only (the library refuses it elsewhere)
 aptcode(::Type{GRMP.APT_BilinearForm}) = 0
 aptcode(::Type{GRMP.APT_SymmetricBilinearForm}) = 1
 aptcode(::Type{GRMP.APT_LumpedBilinearForm}) = 2
@@ -180,9 +181,11 @@ function device_space(FES::FESpace{Float64,Int32,FEType}, ::Type{ON_BFACES}) whe
 end
 device_space(FES::FESpace{Float64,Int32}, ::Type{ON_CELLS}) = device_space(FES)
 const DeviceAT = Union{ON_CELLS,ON_BFACES}
-# ON_BFACES: Identity of H1P1 / H1P2 (the best-approximation boundary data of boundarydata.jl:297-347); everything else on
-# boundary faces (NormalFlux, TangentFlux, face bubbles of H1BR) stays with the reference
-bface_ok(AP) = all(F -> eltype(F) <: Union{H1P1,H1P2} && !F.broken, AP.FES) && all(o -> o == Identity, AP.operators)
+# ON_BFACES: Identity of H1P1 / H1P2 and NormalFlux of HDIVRT0 / HDIVBDM1 (the best-approximation boundary data of
+# boundarydata.jl:297-347); everything else on boundary faces (TangentFlux, face bubbles of H1BR, NormalFlux of H1 spaces) stays
+# with the reference
+bface_ok(AP) = (all(F -> eltype(F) <: Union{H1P1,H1P2} && !F.broken, AP.FES) && all(o -> o == Identity, AP.operators)) ||
+               (all(F -> eltype(F) <: Union{HDIVRT0,HDIVBDM1} && !F.broken, AP.FES) && all(o -> o == NormalFlux, AP.operators))
 
 # tables straight out of the reference's FEEvaluator (feevaluator.jl:34-138): ForwardDiff's bits travel unchanged
 function evaltab(ev)   # ev::GRMP.SingleFEEvaluator
@@ -379,9 +382,11 @@ function lf_plan(AP::AssemblyPattern{APT,Tv,AT}) where {APT,Tv,AT}
     a = AP.action
     a isa NoAction && return LfPlan(o, F_NONE)
     a isa GRMP.DefaultUserAction || return nothing
-    a.argsizes[2] == 0 || return nothing                                  # fdot_action(f): the result does not depend on an input (actions.jl:119-128)
-    (GRMP.is_itemdependent(a) || GRMP.is_xrefdependent(a)) && return nothing  # "I" / "L" dependencies stay on the reference path
-    return LfPlan(o, GRMP.is_xdependent(a) ? F_QP_TABLE : F_CONST)
+    a.argsizes[2] == 0 || return nothing                                  # fdot_action(f) / fdotn_action(f): the result does not depend on an input (actions.jl:119-192)
+    GRMP.is_xrefdependent(a) && return nothing                            # the reference's LinearForm loop never sets action.xref: "L" kernels stay there
+    # x- and item-dependent kernels are tabulated on the host item by item (tabulate_action sets action.x / action.item the way the
+    # reference loop does, linearform.jl:172-201); only a kernel without any dependency is a constant
+    return LfPlan(o, (GRMP.is_xdependent(a) || GRMP.is_itemdependent(a)) ? F_QP_TABLE : F_CONST)
 end
 
 const LFS = WeakKeyDict{Any,DLf}()
@@ -396,16 +401,20 @@ function tabulate_action(AP::AssemblyPattern{APT,Tv,AT}, ev, nq::Int) where {APT
     regions = AP.regions; allitems = regions == [0]
     xreg = xgrid[GRMP.GridComponentRegions4AssemblyType(AT)]
     input = zeros(Float64, 0)
-    if !GRMP.is_xdependent(action)
+    xdep, idep = GRMP.is_xdependent(action), GRMP.is_itemdependent(action)
+    if !(xdep || idep)
         GRMP.eval_action!(action, input)
         return Vector{Float64}(action.val[1:rd])
     end
     tab = zeros(Float64, rd, nq, ncells)
     for cell = 1:ncells
         (allitems || xreg[cell] in regions) || continue
-        update_trafo!(ev.L2G, cell)
+        if idep                                   # linearform.jl:172-177 (continuous operators: the dofitem is the item, di = 1)
+            action.item[1] = cell; action.item[2] = cell; action.item[3] = xreg[cell]; action.item[4] = 1
+        end
+        xdep && update_trafo!(ev.L2G, cell)
         for i = 1:nq
-            eval_trafo!(action.x, ev.L2G, ev.xref[i])
+            xdep && eval_trafo!(action.x, ev.L2G, ev.xref[i])
             GRMP.eval_action!(action, input)
             @views tab[:, i, cell] .= action.val[1:rd]
         end

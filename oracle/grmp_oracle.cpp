@@ -61,7 +61,7 @@ inline Dual operator/(const Dual& a, double b) { Dual r; r.v = a.v / b; for (int
 // enums shared with the python wrapper (oracle/oracle.py)
 // -------------------------------------------------------------------------------------
 enum FEType { H1P1 = 1, H1P2 = 2, H1BR = 3, HDIVRT0 = 4, HDIVBDM1 = 5, L2P0 = 6 };
-enum Op { OP_ID = 1, OP_GRAD = 2, OP_SYMGRAD = 3, OP_DIV = 4, OP_RECON_ID_RT0 = 5, OP_RECON_ID_BDM1 = 6 };
+enum Op { OP_ID = 1, OP_GRAD = 2, OP_SYMGRAD = 3, OP_DIV = 4, OP_RECON_ID_RT0 = 5, OP_RECON_ID_BDM1 = 6, OP_NORMALFLUX = 7 };
 enum Action { ACT_NONE = 0, ACT_HOOKE2D = 1, ACT_HOOKE3D = 2, ACT_CONVECTION = 3 };
 enum APT { APT_GENERAL = 0, APT_SYMMETRIC = 1, APT_LUMPED = 2 };
 enum FSrc { F_NONE = 0, F_CONST = 1, F_QP_TABLE = 2 };
@@ -205,7 +205,7 @@ template <class T> void basis_L2P0(RefB<T>& rb, const T*, int ncomp) {
 struct FEInfo { int ncomp, nd, nd_all, polyorder; bool coeffs, hdiv; };
 
 // get_ndofs / get_ndofs_all / get_polynomialorder (src/fedefs/*.jl headers)
-FEInfo fe_info(int fe, int ncomp, int edim) {
+FEInfo fe_info(int fe, int ncomp, int edim, bool on_faces = false) {
   FEInfo r{};
   r.ncomp = ncomp; r.coeffs = false; r.hdiv = false;
   int nn = edim + 1, nf = edim + 1, ne = (edim == 1) ? 1 : (edim == 2) ? 3 : 6;   // Edge1D: "N1I1" (h1_p2.jl:37)
@@ -218,9 +218,22 @@ FEInfo fe_info(int fe, int ncomp, int edim) {
     case L2P0: r.nd = r.nd_all = ncomp; r.polyorder = 0; break;
     default: r.nd = -1;
   }
+  if (on_faces && (fe == HDIVRT0 || fe == HDIVBDM1)) {       // normal-flux face bases: get_ndofs / get_polynomialorder on the face geometry
+    r.ncomp = 1; r.nd = r.nd_all = (fe == HDIVRT0) ? 1 : edim + 1;      // hdiv_rt0.jl:21, 24, 26; hdiv_bdm1.jl:20-21, 26, 29
+    r.polyorder = (fe == HDIVRT0) ? 0 : 1;
+  }
   return r;
 }
 
+// normal-flux bases on faces: hdiv_rt0.jl:61-65, hdiv_bdm1.jl:74-79 (Edge1D), 109-115 (Triangle2D); one component
+template <class T> void basis_hdiv_face(int fe, RefB<T>& rb, const T* x, int fdim) {
+  rb(0, 0) = T(1.0);
+  if (fe == HDIVBDM1 && fdim == 1) rb(1, 0) = 12.0 * (x[0] - 0.5);
+  if (fe == HDIVBDM1 && fdim == 2) {
+    rb(1, 0) = 12.0 * (2.0 * x[0] + x[1] - 1.0);
+    rb(2, 0) = 12.0 * (2.0 * x[1] + x[0] - 1.0);
+  }
+}
 template <class T> void eval_basis(int fe, RefB<T>& rb, const T* x, int edim, int ncomp) {
   switch (fe) {
     case H1P1: basis_H1P1(rb, x, edim, ncomp); break;
@@ -396,7 +409,7 @@ bool make_qrule(int edim, int order, QRule& q) {
 // grid / space views (1-based Int32 arrays laid out like the Julia column-major arrays)
 // -------------------------------------------------------------------------------------
 struct Grid {
-  int dim; i64 nnodes, ncells, nfaces;
+  int dim, xdim; i64 nnodes, ncells, nfaces;      // xdim > dim: the items are boundary faces (AT = ON_BFACES), no affine inverse
   const double* coords; const i32* cellnodes; const double* vol; const i32* regions;
   const i32* cellfaces; const i32* signs; const i32* orient; const double* fnormals; const double* fvol;
 };
@@ -469,7 +482,8 @@ struct Evaluator {
 
   bool init(const Grid* g_, const Space& sp_, int op_, const QRule& q) {
     g = g_; sp = sp_; op = op_; edim = g->dim; nq = q.n();
-    fi = fe_info(sp.fe, sp.ncomp, edim);
+    const bool on_faces = g->xdim > g->dim;
+    fi = fe_info(sp.fe, sp.ncomp, edim, on_faces);
     if (fi.nd < 0) { g_err = "unknown FEType"; return false; }
     if (fi.nd != sp.nd) { g_err = "celldofs width does not match FEType"; return false; }
     ncomp = fi.ncomp; nd = fi.nd; nd_all = fi.nd_all; coeffs_flag = fi.coeffs; hdiv = fi.hdiv;
@@ -479,13 +493,16 @@ struct Evaluator {
       case OP_GRAD: resultdim = edim * ncomp; break;
       case OP_SYMGRAD: resultdim = ((edim == 2) ? 3 : 6) * ((ncomp + edim - 1) / edim); break;
       case OP_DIV: resultdim = (ncomp + edim - 1) / edim; break;
+      case OP_NORMALFLUX: resultdim = 1; break;
       default: g_err = "unknown operator"; return false;
     }
+    if ((op == OP_NORMALFLUX) != (on_faces && hdiv)) { g_err = "NormalFlux: Hdiv elements on boundary faces, and nothing else of them there"; return false; }
     if (op == OP_SYMGRAD && ncomp != edim) { g_err = "SymmetricGradient needs ncomponents == dim"; return false; }
-    if (hdiv && !(op == OP_ID || op == OP_DIV)) { g_err = "Hdiv elements: Identity/Divergence only"; return false; }
+    if (hdiv && !on_faces && !(op == OP_ID || op == OP_DIV)) { g_err = "Hdiv elements: Identity/Divergence only"; return false; }
+    if (on_faces && !hdiv && !(op == OP_ID && (sp.fe == H1P1 || sp.fe == H1P2))) { g_err = "boundary faces: Identity of H1P1 / H1P2 only"; return false; }
     if (sp.fe == L2P0 && op != OP_ID) { g_err = "L2P0: Identity only"; return false; }
     if (is_recon(op) && sp.fe != H1BR) { g_err = "ReconstructionIdentity restated for H1BR only"; return false; }
-    if ((hdiv || sp.fe == H1BR) && !(g->cellfaces && g->fnormals)) { g_err = "face data missing on grid"; return false; }
+    if ((hdiv || sp.fe == H1BR) && !on_faces && !(g->cellfaces && g->fnormals)) { g_err = "face data missing on grid"; return false; }
     cvals.assign((size_t)nq * nd * resultdim, 0.0);
     subset.resize(std::max(nd, 16)); for (size_t k = 0; k < subset.size(); k++) subset[k] = (int)k;
     if (coeffs_flag || hdiv) coeff.assign((size_t)nd * ncomp, 1.0);
@@ -505,7 +522,8 @@ struct Evaluator {
     refvals.assign((size_t)nq * nda * nc, 0.0);
     for (int i = 0; i < nq; i++) {
       RefB<double> rb(nda, nc);
-      eval_basis<double>(eval_fe, rb, &q.xref[(size_t)i * edim], edim, eval_nc);
+      if (op == OP_NORMALFLUX) basis_hdiv_face<double>(sp.fe, rb, &q.xref[(size_t)i * edim], edim);
+      else eval_basis<double>(eval_fe, rb, &q.xref[(size_t)i * edim], edim, eval_nc);
       for (int dof = 0; dof < nda; dof++) for (int c = 0; c < nc; c++) refvals[((size_t)i * nda + dof) * nc + c] = rb(dof, c);
     }
     // reference derivatives via dual numbers (feevaluator.jl:112-119, 235-293)
@@ -622,6 +640,10 @@ struct Evaluator {
         if (rc(di, dj) != 0)
           for (int i = 0; i < nq; i++) for (int k = 0; k < ncomp; k++) cv(k, di, i) += rc(di, dj) * te(k, dj, i);
       }
+      return;
+    }
+    if (op == OP_NORMALFLUX) {                              // feevaluator_hdiv.jl:42-50
+      for (int i = 0; i < nq; i++) for (int dof = 0; dof < nd; dof++) for (int k = 0; k < resultdim; k++) cv(k, dof, i) = rv(i, dof, k) / g->vol[cell];
       return;
     }
     if (hdiv) {
@@ -761,7 +783,7 @@ void apply_action(int action, const double* p, const double* in, double* out) {
   }
 }
 
-int polyorder_of(const Space& s, int edim) { return fe_info(s.fe, s.ncomp, edim).polyorder; }
+int polyorder_of(const Space& s, const Grid& g) { return fe_info(s.fe, s.ncomp, g.dim, g.xdim > g.dim).polyorder; }
 
 }  // namespace
 
@@ -774,14 +796,14 @@ const char* orc_last_error() { return g_err.c_str(); }
 void orc_set_magnitude_mode(int on) { g_magnitude_mode = on != 0; }
 
 struct orc_grid {
-  int dim; i64 nnodes, ncells, nfaces;
+  int dim, xdim; i64 nnodes, ncells, nfaces;
   const double* coords; const i32* cellnodes; const double* cellvolumes; const i32* cellregions;
   const i32* cellfaces; const i32* cellfacesigns; const i32* cellfaceorient; const double* facenormals; const double* facevolumes;
 };
 struct orc_space { int fetype, ncomp; i64 ndofs; int nd_cell; const i32* celldofs; };
 
 static Grid to_grid(const orc_grid* g) {
-  Grid r; r.dim = g->dim; r.nnodes = g->nnodes; r.ncells = g->ncells; r.nfaces = g->nfaces;
+  Grid r; r.dim = g->dim; r.xdim = g->xdim; r.nnodes = g->nnodes; r.ncells = g->ncells; r.nfaces = g->nfaces;
   r.coords = g->coords; r.cellnodes = g->cellnodes; r.vol = g->cellvolumes; r.regions = g->cellregions;
   r.cellfaces = g->cellfaces; r.signs = g->cellfacesigns; r.orient = g->cellfaceorient; r.fnormals = g->facenormals; r.fvol = g->facevolumes;
   return r;
@@ -852,9 +874,9 @@ int orc_blf_assemble(void* Aptr, const orc_grid* og, const orc_space* os1, const
   Grid g = to_grid(og); Space s1 = to_space(os1), s2 = to_space(os2);
   int edim = g.dim;
   // prepare_assembly! : quadrature order (assemblypatterns.jl:559-565)
-  int quadorder = bonus_quadorder + polyorder_of(s1, edim) + quadorder_shift(op1) + polyorder_of(s2, edim) + quadorder_shift(op2);
+  int quadorder = bonus_quadorder + polyorder_of(s1, g) + quadorder_shift(op1) + polyorder_of(s2, g) + quadorder_shift(op2);
   Space sa{}; Evaluator ea;
-  if (g_fixed_on) { sa = to_space(&g_fixed_space); quadorder += polyorder_of(sa, edim) + quadorder_shift(g_fixed_op); }   // all FE of the pattern, 559-565
+  if (g_fixed_on) { sa = to_space(&g_fixed_space); quadorder += polyorder_of(sa, g) + quadorder_shift(g_fixed_op); }   // all FE of the pattern, 559-565
   if (quadorder < 0) quadorder = 0;
   QRule q; if (!make_qrule(edim, quadorder, q)) return -1;
   Evaluator e1, e2store; Evaluator* e2 = &e2store;
@@ -989,7 +1011,7 @@ int orc_nlf_convection(void* Aptr, double* b, const orc_grid* og, const orc_spac
   ExtSparse* A = (ExtSparse*)Aptr;
   Grid g = to_grid(og); Space s = to_space(os);
   const int edim = g.dim;
-  int quadorder = bonus_quadorder + 3 * polyorder_of(s, edim) + quadorder_shift(op_a) + quadorder_shift(op_g) + quadorder_shift(op_t);
+  int quadorder = bonus_quadorder + 3 * polyorder_of(s, g) + quadorder_shift(op_a) + quadorder_shift(op_g) + quadorder_shift(op_t);
   if (quadorder < 0) quadorder = 0;
   QRule q; if (!make_qrule(edim, quadorder, q)) return -1;
   Evaluator ea, eg, etst; Evaluator* et = &etst;
@@ -1060,7 +1082,7 @@ int orc_lf_assemble(double* b, const orc_grid* og, const orc_space* os, int op, 
                     const i32* regions, int nregions, double factor, i64 offset, int bonus_quadorder, int* nq_out) {
   Grid g = to_grid(og); Space s = to_space(os);
   int edim = g.dim;
-  int quadorder = bonus_quadorder + polyorder_of(s, edim) + quadorder_shift(op);
+  int quadorder = bonus_quadorder + polyorder_of(s, g) + quadorder_shift(op);
   if (quadorder < 0) quadorder = 0;
   QRule q; if (!make_qrule(edim, quadorder, q)) return -1;
   if (nq_out) *nq_out = q.n();
@@ -1099,7 +1121,7 @@ int orc_ii_evaluate(double* b, double* total, const orc_grid* og, const orc_spac
                     int* resultdim_out) {
   Grid g = to_grid(og); Space s = to_space(os);
   int edim = g.dim;
-  int quadorder = bonus_quadorder + polyorder_of(s, edim) + quadorder_shift(op);
+  int quadorder = bonus_quadorder + polyorder_of(s, g) + quadorder_shift(op);
   if (quadorder < 0) quadorder = 0;
   QRule q; if (!make_qrule(edim, quadorder, q)) return -1;
   if (nq_out) *nq_out = q.n();

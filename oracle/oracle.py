@@ -19,7 +19,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-OP_ID, OP_GRAD, OP_SYMGRAD, OP_DIV, OP_RECON_ID_RT0, OP_RECON_ID_BDM1 = 1, 2, 3, 4, 5, 6
+OP_ID, OP_GRAD, OP_SYMGRAD, OP_DIV, OP_RECON_ID_RT0, OP_RECON_ID_BDM1, OP_NORMALFLUX = 1, 2, 3, 4, 5, 6, 7
 ACT_NONE, ACT_HOOKE2D, ACT_HOOKE3D, ACT_CONVECTION = 0, 1, 2, 3
 APT_GENERAL, APT_SYMMETRIC, APT_LUMPED = 0, 1, 2
 F_NONE, F_CONST, F_QP_TABLE = 0, 1, 2
@@ -27,7 +27,7 @@ II_NONE, II_L2NORM, II_L2ERROR = 0, 1, 2
 
 
 class _Grid(C.Structure):
-    _fields_ = [("dim", C.c_int), ("nnodes", C.c_int64), ("ncells", C.c_int64), ("nfaces", C.c_int64),
+    _fields_ = [("dim", C.c_int), ("xdim", C.c_int), ("nnodes", C.c_int64), ("ncells", C.c_int64), ("nfaces", C.c_int64),
                 ("coords", C.c_void_p), ("cellnodes", C.c_void_p), ("cellvolumes", C.c_void_p), ("cellregions", C.c_void_p),
                 ("cellfaces", C.c_void_p), ("cellfacesigns", C.c_void_p), ("cellfaceorient", C.c_void_p),
                 ("facenormals", C.c_void_p), ("facevolumes", C.c_void_p)]
@@ -102,7 +102,7 @@ def _grid_struct(grid, need_faces):
         k.fn = np.ascontiguousarray(grid.facenormals, dtype=np.float64)
         k.fv = np.ascontiguousarray(grid.facevolumes, dtype=np.float64)
         nfaces = k.fv.size
-    k.s = _Grid(grid.dim, k.coords.shape[0], k.cellnodes.shape[0], nfaces, _p(k.coords), _p(k.cellnodes), _p(k.vol), _p(k.reg),
+    k.s = _Grid(grid.dim, getattr(grid, "xdim", grid.dim), k.coords.shape[0], k.cellnodes.shape[0], nfaces, _p(k.coords), _p(k.cellnodes), _p(k.vol), _p(k.reg),
                 _p(k.cf), _p(k.sg), _p(k.ori), _p(k.fn), _p(k.fv))
     return k
 
@@ -115,7 +115,7 @@ def _space_struct(space):
 
 
 def _needs_faces(*spaces):
-    return any(s.fetype.code in (3, 4, 5) for s in spaces)
+    return any(s.fetype.code in (3, 4, 5) and not getattr(s.xgrid, "embedded", False) for s in spaces)
 
 
 class OracleMatrix:

@@ -115,8 +115,12 @@ def test_only_identity_of_h1_spaces_is_admitted():
     s = G.FESpace(G.H1P1(1), g)
     with pytest.raises(G._lib.GrmpError):
         G.assemble_csc(G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [s, s], AT="ON_BFACES"))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(G._lib.GrmpError):           # Hdiv spaces on boundary faces: NormalFlux only
         G.assemble_csc(G.DiscreteSymmetricBilinearForm([G.Identity, G.Identity], [G.FESpace(G.HDIVRT0(2), g)] * 2, AT="ON_BFACES"))
+    with pytest.raises(G._lib.GrmpError):           # NormalFlux lives on boundary faces
+        G.assemble_csc(G.DiscreteSymmetricBilinearForm([G.NormalFlux, G.NormalFlux], [G.FESpace(G.HDIVRT0(2), g)] * 2))
+    with pytest.raises(NotImplementedError):
+        G.assemble_csc(G.DiscreteSymmetricBilinearForm([G.Identity, G.Identity], [G.FESpace(G.H1BR(2), g)] * 2, AT="ON_BFACES"))
     with pytest.raises(NotImplementedError):
         G.DiscreteSymmetricBilinearForm([G.Identity, G.Identity], [s, s], AT="ON_FACES")
 
@@ -167,3 +171,68 @@ def test_homogeneous_boundary_and_order_of_fixed_dofs():
     _, first = np.unique(expect, return_index=True)
     assert np.array_equal(fixed, expect[np.sort(first)])           # Base.unique order (boundarydata.jl:246)
     assert np.all(t.entries[fixed - 1] == 0) and np.count_nonzero(t.entries == 7.0) == s.ndofs - fixed.size
+
+
+# ---- Hdiv boundary data: NormalFlux of HDIVRT0 / HDIVBDM1 on boundary faces (boundarydata.jl:301-302, 321-323; Example302's space) ----
+HDIV_CASES = [("RT0 2D", 2, 3, lambda: G.HDIVRT0(2), [0]), ("BDM1 2D regions 1,2", 2, 2, lambda: G.HDIVBDM1(2), [1, 2]),
+              ("RT0 3D regions 3,4", 3, 2, lambda: G.HDIVRT0(3), [3, 4]), ("BDM1 3D", 3, 1, lambda: G.HDIVBDM1(3), [0])]
+
+
+@pytest.mark.parametrize("case", HDIV_CASES, ids=[c[0] for c in HDIV_CASES])
+def test_normalflux_boundary_mass_and_rhs_bit_equal(case):
+    _, dim, level, fef, regions = case
+    g = _grid(dim, level, jitter=True)
+    s = G.FESpace(fef(), g)
+    AP = G.DiscreteSymmetricBilinearForm([G.NormalFlux, G.NormalFlux], [s, s], regions=regions, AT="ON_BFACES")
+    cp, rv, nz = G.assemble_csc(AP, 0.5)
+    ocp, orv, onz = oracle_blf(AP, 0.5)
+    assert np.array_equal(cp, ocp) and np.array_equal(rv, orv) and np.array_equal(nz, onz)
+    data = G.DataFunction(lambda x: np.stack([np.sin(x[0]) + x[1] * x[k % dim] for k in range(dim)]), [dim, dim], bonus_quadorder=2)
+    L = G.DiscreteLinearForm([G.NormalFlux], [s], G.fdotn_action(data, g), regions=regions, AT="ON_BFACES")
+    b = G.FEVector([s])
+    G.assemble(b[1], L, factor=2.0)
+    bs, P = s.on_bfaces(), L.AM
+    bg = bs.xgrid
+    vals = np.asarray(data.kernel(_xq(bg, P.qf).reshape(-1, dim).T), dtype=np.float64).reshape(dim, -1).T.reshape(bg.ncells, len(P.qf), dim)
+    nrm = g.facenormals[g.bfacefaces.astype(np.int64) - 1]
+    table = np.ascontiguousarray((vals * nrm[:, None, :]).sum(axis=2)[:, :, None])
+    ob = np.zeros(s.ndofs)
+    O.qrule_override(bg.dim, P.quadorder, P.qf.xref, P.qf.w)
+    try:
+        O.lf_assemble(ob, bg, bs, O.OP_NORMALFLUX, fsrc=O.F_QP_TABLE, fdata=table, regions=regions, factor=2.0, bonus_quadorder=2)
+    finally:
+        O.qrule_override(bg.dim, P.quadorder)
+    assert np.array_equal(b.entries, ob)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("fam", ["RT0", "BDM1"])
+def test_hdiv_best_approximation_boundary_data_equals_face_moments(dim, fam):
+    """the face bases are dual to the interpolation functionals (hdiv_rt0.jl:37-52, hdiv_bdm1.jl:43-66): for data whose normal flux lies in the
+    trace space the best approximation returns  int_F u.n,  int_F u.n (xref_1 - 1/d),  int_F u.n (xref_2 - 1/d)"""
+    g = _grid(dim, 2 if dim == 2 else 1, jitter=True)
+    fe = G.HDIVRT0(dim) if fam == "RT0" else G.HDIVBDM1(dim)
+    s = G.FESpace(fe, g)
+    if fam == "RT0":
+        u = lambda x: np.stack([np.full_like(x[0], 0.75 - 0.25 * k) for k in range(dim)])
+    else:
+        u = lambda x: np.stack([0.5 + x[k] - 2.0 * x[(k + 1) % dim] for k in range(dim)])
+    t = G.FEVector([s])
+    O_ = [G.BoundaryData(G.BestapproxDirichletBoundary, data=G.DataFunction(u, [dim, dim], bonus_quadorder=1), regions=list(range(1, int(g.bfaceregions.max()) + 1)))]
+    fixed = G.boundarydata(t[1], O_)
+    bs = s.on_bfaces()
+    assert np.array_equal(np.sort(fixed), np.unique(bs.celldofs))
+    # moments by quadrature on the faces (face node order = FaceNodes order)
+    bg = bs.xgrid
+    qf = G.QuadratureRule("Edge1D" if dim == 2 else "Triangle2D", 3)
+    xq = _xq(bg, qf)
+    nrm = g.facenormals[g.bfacefaces.astype(np.int64) - 1]
+    un = (np.moveaxis(u(xq.reshape(-1, dim).T).reshape(dim, bg.ncells, len(qf)), 0, 2) * nrm[:, None, :]).sum(axis=2)       # [face, q]
+    vol = bg.cellvolumes
+    mom = [vol * (un * qf.w).sum(axis=1)]
+    if fam == "BDM1":
+        for j in range(dim - 1):
+            mom.append(vol * (un * qf.w * (qf.xref[:, j] - 1.0 / dim)).sum(axis=1))
+    dofs = bs.celldofs.astype(np.int64) - 1
+    for k, m in enumerate(mom):
+        assert np.abs(t.entries[dofs[:, k]] - m).max() < 1e-12, (k, np.abs(t.entries[dofs[:, k]] - m).max())

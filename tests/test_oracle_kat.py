@@ -451,3 +451,50 @@ def test_boundary_best_approximation_oracle(dim):
     en = (g.facenodes if dim == 2 else g.edgenodes).astype(np.int64) - 1
     xdof = np.concatenate([g.coords, 0.5 * (g.coords[en[:, 0]] + g.coords[en[:, 1]])])
     assert np.abs(sol - u(xdof[bdofs].T)).max() < 100 * TOL
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("fam", ["RT0", "BDM1"])
+def test_hdiv_normalflux_face_bases_are_dual_to_the_face_moments(dim, fam):
+    """boundarydata.jl:301-302, 321-323 with NormalFlux: the face bases (hdiv_rt0.jl:61-65, hdiv_bdm1.jl:74-79, 109-115) over |F|
+    (feevaluator_hdiv.jl:42-50) are dual to the interpolation functionals int_F u.n, int_F u.n (xref_j - 1/d) (hdiv_bdm1.jl:43-66), so
+    the boundary best approximation of a field whose normal flux lies in the trace space returns exactly those moments"""
+    g = G.perturb_interior_nodes(tri_grid(1) if dim == 2 else tet_grid(1), 0.15)
+    fe = G.HDIVRT0(dim) if fam == "RT0" else G.HDIVBDM1(dim)
+    s = G.FESpace(fe, g)
+    bs = s.on_bfaces()
+    bg = bs.xgrid
+    assert bs.celldofs.shape[1] == (1 if fam == "RT0" else dim)
+    if fam == "RT0":
+        u = lambda x: np.stack([np.full_like(x[0], 0.75 - 0.25 * k) for k in range(dim)])
+    else:
+        u = lambda x: np.stack([0.5 + x[k] - 2.0 * x[(k + 1) % dim] for k in range(dim)])
+    A = O.OracleMatrix(s.ndofs, s.ndofs)
+    O.blf_assemble(A, bg, bs, bs, O.OP_NORMALFLUX, O.OP_NORMALFLUX, apt=O.APT_SYMMETRIC)
+    M = A.toscipy().tocsc()
+    qo = fe.polynomialorder(bg.dim) + 1
+    xr, w = O.qrule(bg.dim, qo)
+    x = bg.coords
+    cn = bg.cellnodes.astype(np.int64) - 1
+    xq = np.repeat(x[cn[:, 0]][:, None, :], w.size, axis=1).copy()
+    for j in range(bg.dim):
+        xq += (x[cn[:, j + 1]] - x[cn[:, 0]])[:, None, :] * xr[None, :, j, None]
+    nrm = g.facenormals[g.bfacefaces.astype(np.int64) - 1]
+    un = (np.moveaxis(u(xq.reshape(-1, dim).T).reshape(dim, bg.ncells, w.size), 0, 2) * nrm[:, None, :]).sum(axis=2)
+    b = np.zeros(s.ndofs)
+    O.lf_assemble(b, bg, bs, O.OP_NORMALFLUX, fsrc=O.F_QP_TABLE, fdata=np.ascontiguousarray(un[:, :, None]), bonus_quadorder=1)
+    keep = np.flatnonzero(np.diff(M.indptr) != 0)
+    assert np.array_equal(keep, np.unique(bs.celldofs) - 1)
+    sol = np.zeros(s.ndofs)
+    sol[keep] = spla.spsolve(M[keep][:, keep].tocsc(), b[keep])
+    vol = bg.cellvolumes
+    mom = [vol * (un * w).sum(axis=1)]
+    if fam == "BDM1":
+        for j in range(dim - 1):
+            mom.append(vol * (un * w * (xr[:, j] - 1.0 / dim)).sum(axis=1))
+    dofs = bs.celldofs.astype(np.int64) - 1
+    for k, m in enumerate(mom):
+        assert np.abs(sol[dofs[:, k]] - m).max() < TOL
+    # RT0: the moment is |F| u.n, the mass matrix is diag(1 / |F|)
+    if fam == "RT0":
+        assert np.abs(M.diagonal()[dofs[:, 0]] * vol - 1.0).max() < 1e-14
