@@ -390,8 +390,8 @@ def prepare_assembly(AP: AssemblyPattern, transposed_assembly=False):
     w = np.ascontiguousarray(P.qf.w)
     h = C.c_void_p()
     if AP.APT == APT_ItemIntegrator:
-        sp = device_space(AP.FES[0])
-        tab, keep = _tables(AP.FES[0], AP.operators[0], P.qf)
+        sp = device_space(AP.item_space(0))
+        tab, keep = _tables(AP.item_space(0), AP.operators[0], P.qf)
         P.keep.append(keep)
         _lib.check(L.grmp_ii_create(sp, AP.operators[0].code, AP.action.code, _lib.ptr(regions), regions.size, len(P.qf), _lib.ptr(w),
                                     C.byref(tab), C.byref(h)))
@@ -632,29 +632,29 @@ class _IIAction:
         self.code, self.bonus_quadorder, self.data, self.factor, self.name = code, bonus_quadorder, data, float(factor), name
 
 
-def ItemIntegrator(operators, action=None, regions=(0,), name="ItemIntegrator"):
-    """ItemIntegrator(operators, action; AT = ON_CELLS, regions) (itemintegrator.jl:18-21); one argument, NoAction or one of the
-    integrators below"""
+def ItemIntegrator(operators, action=None, regions=(0,), name="ItemIntegrator", AT="ON_CELLS"):
+    """ItemIntegrator(operators, action; AT, regions) (itemintegrator.jl:18-21); one argument, NoAction or one of the
+    integrators below; AT = ON_CELLS, or ON_BFACES for boundary integrals (Identity of H1P1 / H1P2, NormalFlux of HDIVRT0 / HDIVBDM1)"""
     if len(operators) != 1:
         raise NotImplementedError("ItemIntegrators with several arguments are a 'next' row (SURVEY.md 8f N4)")
     act = action if isinstance(action, _IIAction) else _IIAction(0)
     if action is not None and not isinstance(action, (_IIAction, NoAction)):
         raise NotImplementedError("user Actions cannot cross the C ABI: NoAction, L2NormIntegrator and L2ErrorIntegrator run on the device")
-    return AssemblyPattern(APT_ItemIntegrator, name, [], operators, act, [1], regions)
+    return AssemblyPattern(APT_ItemIntegrator, name, [], operators, act, [1], regions, AT)
 
 
-def L2NormIntegrator(ncomponents, operator, quadorder=2, regions=(0,), name="L2 norm"):
-    """L2NormIntegrator(ncomponents, operator; quadorder = 2) (itemintegrator.jl:91-110)"""
-    return ItemIntegrator([operator], _IIAction(1, bonus_quadorder=quadorder, name=name), regions=regions, name=name)
+def L2NormIntegrator(ncomponents, operator, quadorder=2, regions=(0,), name="L2 norm", AT="ON_CELLS"):
+    """L2NormIntegrator(ncomponents, operator; AT, quadorder = 2) (itemintegrator.jl:91-110)"""
+    return ItemIntegrator([operator], _IIAction(1, bonus_quadorder=quadorder, name=name), regions=regions, name=name, AT=AT)
 
 
-def L2ErrorIntegrator(compare_data: DataFunction, operator=None, quadorder="auto", factor=1, regions=(0,), name="auto"):
+def L2ErrorIntegrator(compare_data: DataFunction, operator=None, quadorder="auto", factor=1, regions=(0,), name="auto", AT="ON_CELLS"):
     """L2ErrorIntegrator(compare_data, operator; quadorder = "auto", factor) (itemintegrator.jl:33-78): || compare_data - factor u_h ||^2
     per item; "auto" = twice the bonus quadrature order of the data"""
     q = 2 * compare_data.bonus_quadorder if quadorder == "auto" else int(quadorder)
     nm = f"L2 error ({compare_data.name})" if name == "auto" else name
     return ItemIntegrator([Identity if operator is None else operator], _IIAction(2, bonus_quadorder=q, data=compare_data, factor=factor, name=nm),
-                          regions=regions, name=nm)
+                          regions=regions, name=nm, AT=AT)
 
 
 def _ii_prepare(AP, FEB, skip_preps):
@@ -670,7 +670,7 @@ def _ii_prepare(AP, FEB, skip_preps):
     if AP.action.code == 2:
         fsrc, fd = _qp_table(AP, P)                 # compare_data at the quadrature points (L2error_function, itemintegrator.jl:52-69)
         if fsrc == 1:
-            fd = np.broadcast_to(fd, (FEB.FES.xgrid.ncells, len(P.qf), fd.size))
+            fd = np.broadcast_to(fd, (AP.item_space(0).xgrid.ncells, len(P.qf), fd.size))
         data = np.ascontiguousarray(fd, dtype=np.float64)
         if data.shape[-1] != _resultdim(AP):
             raise ValueError(f"compare data has {data.shape[-1]} components, operator result has {_resultdim(AP)}")
@@ -683,7 +683,7 @@ def _ii_prepare(AP, FEB, skip_preps):
 def evaluate_itemwise(b, AP: AssemblyPattern, FEB, skip_preps=False):
     """evaluate!(b, AP, FEB) (itemintegrator.jl:160-300): b[item, j] += ... (Julia: b[j, item]); returns b"""
     P, coeffs, data, rd = _ii_prepare(AP, FEB, skip_preps)
-    assert b.dtype == np.float64 and b.flags.c_contiguous and b.shape == (AP.FES[0].xgrid.ncells, rd)
+    assert b.dtype == np.float64 and b.flags.c_contiguous and b.shape == (AP.item_space(0).xgrid.ncells, rd)
     _lib.check(_lib.lib().grmp_ii_evaluate(P.h, _lib.ptr(coeffs), AP.action.factor, _lib.ptr(data), _lib.ptr(b), None))
     return b
 
@@ -697,6 +697,6 @@ def evaluate(AP: AssemblyPattern, FEB, skip_preps=False):
 
 
 def _resultdim(AP):
-    F, o = AP.FES[-1], AP.operators[-1]
+    F, o = AP.item_space(len(AP.FES) - 1), AP.operators[-1]
     edim, nc = F.xgrid.dim, F.fetype.ncomponents
     return {1: nc, 5: nc, 6: nc, 7: 1, 2: edim * nc, 3: (3 if edim == 2 else 6), 4: max(1, nc // edim)}[o.code]

@@ -236,3 +236,33 @@ def test_hdiv_best_approximation_boundary_data_equals_face_moments(dim, fam):
     dofs = bs.celldofs.astype(np.int64) - 1
     for k, m in enumerate(mom):
         assert np.abs(t.entries[dofs[:, k]] - m).max() < 1e-12, (k, np.abs(t.entries[dofs[:, k]] - m).max())
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_boundary_item_integrators(dim):
+    """ItemIntegrator / L2ErrorIntegrator with AT = ON_BFACES (itemintegrator.jl:18-21, 33-78): boundary integrals of a P2 function and the
+    boundary L2 error, item by item against the oracle (bit-equal) and against the closed form"""
+    g = _grid(dim, 2 if dim == 2 else 1, jitter=True)
+    s = G.FESpace(G.H1P2(1, dim), g)
+    u = lambda x: 1.0 + x[0] * x[dim - 1] + 0.5 * x[1] ** 2
+    v = G.FEVector([s])
+    en = (g.facenodes if dim == 2 else g.edgenodes).astype(np.int64) - 1
+    xdof = np.concatenate([g.coords, 0.5 * (g.coords[en[:, 0]] + g.coords[en[:, 1]])])
+    v.entries[:] = u(xdof.T)                                   # nodal interpolation = u itself (P2 reproduces quadratics)
+    bs = s.on_bfaces()
+    bg = bs.xgrid
+    II = G.ItemIntegrator([G.Identity], regions=[1, 2], AT="ON_BFACES")
+    b = np.zeros((bg.ncells, 1))
+    G.evaluate_itemwise(b, II, v[1])
+    ob, _ = O.ii_evaluate(bg, bs, O.OP_ID, v.entries, regions=[1, 2], itemwise=True)
+    assert np.array_equal(b, ob)
+    assert np.all(b[~np.isin(bg.cellregions, [1, 2])] == 0)
+    tot = G.evaluate(II, v[1])
+    assert abs(tot - b.sum()) <= 1e-12 * abs(b).sum()
+    # closed form on the unit square: regions 1 (y = 0) and 2 (x = 1):  int_0^1 1 dx + int_0^1 (1 + y + y^2 / 2) dy = 1 + 5/3
+    if dim == 2:
+        assert abs(tot - (1.0 + 1.0 + 0.5 + 1.0 / 6.0)) < 1e-12
+    err = G.evaluate(G.L2ErrorIntegrator(G.DataFunction(lambda x: np.stack([u(x)]), [1, dim], bonus_quadorder=2), G.Identity, quadorder=4, AT="ON_BFACES"), v[1])
+    assert 0.0 <= err < 1e-24
+    nrm = G.evaluate(G.L2NormIntegrator(1, G.Identity, quadorder=4, AT="ON_BFACES"), v[1])
+    assert nrm > 1.0
