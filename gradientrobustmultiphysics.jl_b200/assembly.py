@@ -697,6 +697,7 @@ def evaluate(AP: AssemblyPattern, FEB, skip_preps=False):
 
 
 def _resultdim(AP):
-    F, o = AP.item_space(len(AP.FES) - 1), AP.operators[-1]
+    F = AP.item_space(len(AP.FES) - 1) if hasattr(AP, "item_space") else AP.FES[-1]
+    o = AP.operators[-1]
     edim, nc = F.xgrid.dim, F.fetype.ncomponents
     return {1: nc, 5: nc, 6: nc, 7: 1, 2: edim * nc, 3: (3 if edim == 2 else 6), 4: max(1, nc // edim)}[o.code]
