@@ -4,6 +4,7 @@ whose dof map is the node numbering itself:
   * Example202 (examples/Example202_LinearElasticity2D.jl:39-53): H1P1{2}, HookStiffnessOperator2D(mu, lambda) with
     E = 1000, nu = 0.4 on 2d_grid_cookmembrane.sg
   * P1 Laplace stiffness and P1 mass matrix on every 2D mesh file
+  * the P1 boundary mass matrix (AT = ON_BFACES, boundarydata.jl:321) on the explicit FACES list of the file (BFaceNodes, BFaceRegions)
 The reference tree is not available on the GPU box, so the vectors are committed:  python tests/golden/make_sg_fixtures.py"""
 import glob
 import os
@@ -25,6 +26,7 @@ def forms(G, g):
         "laplace": G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [s1, s1]),
         "mass": G.DiscreteSymmetricBilinearForm([G.Identity, G.Identity], [s1, s1]),
         "hooke": G.DiscreteBilinearForm([G.SymmetricGradient(1), G.SymmetricGradient(1)], [s2, s2], G.HookeAction(2, mu, lam)),
+        "bmass": G.DiscreteSymmetricBilinearForm([G.Identity, G.Identity], [s1, s1], AT="ON_BFACES"),
     }
 
 
@@ -39,7 +41,8 @@ if __name__ == "__main__":
         name = os.path.basename(path)[:-3]
         d = parse_sg(open(path).read())
         g = simplexgrid(d)
-        out = {"coords": d["coords"], "cellnodes": d["cellnodes"], "cellregions": d["cellregions"]}
+        out = {"coords": d["coords"], "cellnodes": d["cellnodes"], "cellregions": d["cellregions"],
+               "bfacenodes": d["bfacenodes"], "bfaceregions": d["bfaceregions"]}
         for fname, AP in forms(G, g).items():
             cp, rv, nz = oracle_blf(AP, 1.0)
             out[fname + "_colptr"], out[fname + "_rowval"], out[fname + "_nzval"] = cp, rv, nz

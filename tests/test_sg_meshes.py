@@ -21,7 +21,7 @@ ASSETS = "/root/reference/assets"
 
 
 def grid_of(d):
-    return G.ExtendableGrid(d["coords"], d["cellnodes"], d["cellregions"])
+    return G.ExtendableGrid(d["coords"], d["cellnodes"], d["cellregions"], d["bfacenodes"], d["bfaceregions"])
 
 
 def forms(g):
@@ -42,6 +42,7 @@ def test_reader_reproduces_the_committed_lists(path):
     p = parse_sg(open(src).read())
     assert np.array_equal(p["coords"], d["coords"]) and np.array_equal(p["cellnodes"], d["cellnodes"])
     assert np.array_equal(p["cellregions"], d["cellregions"])
+    assert np.array_equal(p["bfacenodes"], d["bfacenodes"]) and np.array_equal(p["bfaceregions"], d["bfaceregions"])
     g = simplexgrid(src)
     assert g.ncells == d["cellnodes"].shape[0] and g.bfacenodes.shape[0] > 0
 
@@ -78,6 +79,11 @@ def test_oracle_on_reference_meshes(path):
     assert abs(x @ (K @ x) - g.cellvolumes.sum()) < 1e-10 * g.cellvolumes.sum()    # |grad x|^2 = 1
     H = sp_.csc_matrix((d["hooke_nzval"], d["hooke_rowval"] - 1, d["hooke_colptr"] - 1), shape=(2 * n, 2 * n))
     assert abs(H - H.T).max() < 1e-12 * np.abs(H.data).max()
+    # boundary mass matrix on the file's explicit FACES list: 1' M 1 = measure of the listed boundary
+    B = sp_.csc_matrix((d["bmass_nzval"], d["bmass_rowval"] - 1, d["bmass_colptr"] - 1), shape=(n, n))
+    assert abs(B.sum() - g.bfacevolumes.sum()) < 1e-12 * g.bfacevolumes.sum()
+    if "cookmembrane" in path:           # perimeter of the trapezoid (0,0) (48,44) (48,60) (0,44)
+        assert abs(B.sum() - (np.hypot(48, 44) + 16 + np.hypot(48, 16) + 44)) < 1e-9
     for rigid in (np.concatenate([np.ones(n), np.zeros(n)]), np.concatenate([np.zeros(n), np.ones(n)]),
                   np.concatenate([-d["coords"][:, 1], d["coords"][:, 0]])):      # translations and the rotation carry no strain
         assert np.abs(H @ rigid).max() < 1e-9 * np.abs(H.data).max() * np.abs(rigid).max()
