@@ -621,6 +621,13 @@ bool colpath_applicable(const BlfLocalParams& p, int nq, ColPath* cp) {
       if (CFVARIANTS[v].match(cp->row, cp->col, p.action)) { cp->cf_variant = v; break; }
   for (int v = 0; v < NVARIANTS; v++)
     if (VARIANTS[v].match(cp->row, cp->col, p.action, nq) && (size_t)VARIANTS[v].tabR_per_q * nq <= TABR_MAX) { cp->variant = v; break; }
+  // Reconstruction mass forms (R u, R v): the reconstructed functions are Piola images of P1 fields, the integrand has degree 2, but the
+  // reference's rule follows the Bernardi-Raugel degree (order 4: 9 Stroud points).  Both rules are exact, so the quadrature sum equals
+  // the one of ANY exact rule up to rounding: colpath_build factors the rule's own moment matrix into 3 virtual points (GRMP_COL_NO_REDUCE=1 disables)
+  cp->variant_reduced = -1;
+  if (cp->variant >= 0 && cp->row.kind == 2 && cp->col.kind == 2 && p.same_eval && nq > 3 && !getenv("GRMP_COL_NO_REDUCE"))
+    for (int v = 0; v < NVARIANTS; v++)
+      if (VARIANTS[v].match(cp->row, cp->col, p.action, 3)) { cp->variant_reduced = v; break; }
   return cp->variant >= 0 || cp->cf_variant >= 0;
 }
 
@@ -630,14 +637,57 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
   cudaStream_t s = ctx->stream;
   cp->built = false;
   cp->uid = g_next_uid++;
-  if (quadrature_tables) cp->cf_variant = -1;       // the cell-parallel kernels evaluate the quadrature sum themselves
+  if (quadrature_tables) { cp->cf_variant = -1; cp->variant_reduced = -1; }       // the cell-parallel kernels evaluate the caller's quadrature sum themselves
   if (cp->cf_variant < 0 && cp->variant < 0) return fail(GRMP_EUNSUPPORTED, "no column / cell kernel for this form and quadrature rule");
   const bool cf = cp->cf_variant >= 0;
-  const Variant& V = VARIANTS[cf ? 0 : cp->variant];
   const bool tr = !cp->row_is_arg1;
   const EvalView& er = tr ? p.e2 : p.e1;
   const EvalView& ec = tr ? p.e1 : p.e2;
-  const int nq = p.nq;
+  int nq = p.nq;
+  cp->nq = nq;
+  // equivalent 3-point rule for reconstruction mass forms: K = sum_q w_q t_q t_q' (t_q = all table entries at point q) has rank <= 3
+  // because every table row is affine in xref; three steps of a pivoted Cholesky factorisation give K = L L', i.e. three virtual
+  // points with weight 1 whose "table values" are the columns of L.  Accepted only if the residual is at rounding level.
+  std::vector<double> redT, redW;
+  if (!cf && cp->variant_reduced >= 0) {
+    std::vector<double> T;
+    int nas = 0;
+    GRMP_TRY(make_tables(cp->row, nq, vals1, derivs1, er.tab_nd, er.tab_nc, &T, &nas));
+    const int nsf = cp->row.nds + cp->row.nbub, m = nsf * nas;
+    std::vector<double> K((size_t)m * m), L((size_t)m * 3, 0.0);
+    double kmax = 0.0;
+    for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) {
+      double v = 0.0;
+      for (int q = 0; q < nq; q++) v += w[q] * T[(size_t)i * nq + q] * T[(size_t)j * nq + q];
+      K[(size_t)i * m + j] = v;
+      kmax = std::max(kmax, std::fabs(v));
+    }
+    std::vector<double> Rm = K;
+    bool ok = kmax > 0.0;
+    for (int k = 0; k < 3 && ok; k++) {
+      int piv = 0;
+      for (int i = 1; i < m; i++) if (Rm[(size_t)i * m + i] > Rm[(size_t)piv * m + piv]) piv = i;
+      const double d = Rm[(size_t)piv * m + piv];
+      if (!(d > 1e-10 * kmax)) { ok = (k > 0); break; }      // rank < 3 (e.g. constants only): fewer virtual points carry everything
+      const double sd = std::sqrt(d);
+      for (int i = 0; i < m; i++) L[(size_t)i * 3 + k] = Rm[(size_t)i * m + piv] / sd;
+      for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) Rm[(size_t)i * m + j] -= L[(size_t)i * 3 + k] * L[(size_t)j * 3 + k];
+    }
+    double res = 0.0;
+    for (size_t i = 0; i < Rm.size(); i++) res = std::max(res, std::fabs(Rm[i]));
+    if (ok && res <= 1e-14 * kmax) {
+      redT.assign((size_t)m * 3, 0.0);                       // [s][a][q'] like make_tables
+      for (int i = 0; i < m; i++) for (int k = 0; k < 3; k++) redT[(size_t)i * 3 + k] = L[(size_t)i * 3 + k];
+      redW.assign(3, 1.0);
+      nq = 3;
+      cp->nq = 3;
+    } else {
+      cp->variant_reduced = -1;                              // not an affine table set: keep the caller's rule
+    }
+  }
+  const bool reduced = !cf && cp->variant_reduced >= 0;
+  if (reduced) cp->variant = cp->variant_reduced;
+  const Variant& V = VARIANTS[cf ? 0 : cp->variant];
   const i64 ncols = pat.ncols, ncells = p.g.ncells;
   const int v_nrow = cf ? CFVARIANTS[cp->cf_variant].nrow : V.nrow, v_nv = cf ? CFVARIANTS[cp->cf_variant].nv : V.nv;
   const int v_stride = cf ? CFVARIANTS[cp->cf_variant].stride : V.cache_stride();
@@ -674,8 +724,13 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
     const std::vector<double>& d2 = p.same_eval ? derivs1 : derivs2;
     std::vector<double> TR, TC;
     int nasR = 0, nasC = 0;
-    GRMP_TRY(make_tables(cp->row, nq, tr ? v2 : vals1, tr ? d2 : derivs1, er.tab_nd, er.tab_nc, &TR, &nasR));
-    GRMP_TRY(make_tables(cp->col, nq, tr ? vals1 : v2, tr ? derivs1 : d2, ec.tab_nd, ec.tab_nc, &TC, &nasC));
+    if (reduced) {
+      TR = redT; TC = redT;
+      nasR = nasC = (int)(redT.size() / 3) / (cp->row.nds + cp->row.nbub);
+    } else {
+      GRMP_TRY(make_tables(cp->row, nq, tr ? v2 : vals1, tr ? d2 : derivs1, er.tab_nd, er.tab_nc, &TR, &nasR));
+      GRMP_TRY(make_tables(cp->col, nq, tr ? vals1 : v2, tr ? derivs1 : d2, ec.tab_nd, ec.tab_nc, &TC, &nasC));
+    }
     const int nsfR = cp->row.nds + cp->row.nbub, nsfC = cp->col.nds + cp->col.nbub;
     cp->tabR.assign((size_t)nq * nsfR * nasR, 0.0);        // [q][s][a]
     for (int q = 0; q < nq; q++) for (int sI = 0; sI < nsfR; sI++) for (int a = 0; a < nasR; a++)
@@ -684,7 +739,7 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
     for (int a = 0; a < nasC; a++) for (int q = 0; q < nq; q++) for (int sI = 0; sI < nsfC; sI++)
       tc[((size_t)a * nq + q) * CT_PAD + sI] = TC[((size_t)sI * nasC + a) * nq + q];
     GRMP_TRY(cp->tabC.upload(tc.data(), tc.size(), s));
-    cp->wq = w;
+    cp->wq = reduced ? redW : w;
   }
   const i64 ncols_used = (ncols_owned >= 0 && ncols_owned < ncols) ? ncols_owned : ncols;
   cp->ncols_used = ncols_used;

@@ -28,6 +28,7 @@ struct ColPath {
   int nw = 4;                      // warps (= groups of 32 columns) per CTA / tile
   int nv = 1;                      // 16-byte vectors per pair record
   int nq = 0;
+  int variant_reduced = -1;        // >= 0: kernel for an equivalent 3-point rule (reconstruction mass forms, see colpath_build)
   i64 ncols_used = 0, ngroups = 0, ntiles = 0, npairs = 0;
   int max_tile_cells = 0, max_grp_nnz = 0;
   int smem_bytes = 0;              // largest class

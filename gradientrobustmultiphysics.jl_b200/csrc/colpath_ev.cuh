@@ -535,7 +535,8 @@ __device__ __forceinline__ void build_cell_cache(const GridView& g, i64 cell, do
   X((H1Ev<3, 3, 4, 0, GRMP_OP_SYMGRAD>), (H1Ev<3, 3, 4, 0, GRMP_OP_SYMGRAD>), GRMP_ACT_HOOKE3D, 1)               \
   X((H1Ev<3, 3, 10, 0, GRMP_OP_SYMGRAD>), (H1Ev<3, 3, 10, 0, GRMP_OP_SYMGRAD>), GRMP_ACT_HOOKE3D, 4)             \
   GRMP_HDIV_SQUARE(X, 2, 3, 3) GRMP_HDIV_SQUARE(X, 2, 6, 3) GRMP_HDIV_SQUARE(X, 3, 4, 4) GRMP_HDIV_SQUARE(X, 3, 16, 4)  \
-  X((ReconEv2D<3>), (ReconEv2D<3>), GRMP_ACT_NONE, 9) X((ReconEv2D<6>), (ReconEv2D<6>), GRMP_ACT_NONE, 9)
+  X((ReconEv2D<3>), (ReconEv2D<3>), GRMP_ACT_NONE, 9) X((ReconEv2D<6>), (ReconEv2D<6>), GRMP_ACT_NONE, 9)                        \
+  X((ReconEv2D<3>), (ReconEv2D<3>), GRMP_ACT_NONE, 3) X((ReconEv2D<6>), (ReconEv2D<6>), GRMP_ACT_NONE, 3)
 
 #define GRMP_RECT_FORMS(X)                                                                                       \
   GRMP_RECT(X, (H1Ev<2, 2, 3, 3, GRMP_OP_DIV>), (H1Ev<2, 1, 1, 0, GRMP_OP_ID>), 1)                               \
