@@ -625,31 +625,33 @@ struct DeviceItemIntegrator
     factor::Float64
     bonus_quadorder::Int
     regions::Vector{Int}
+    AT::DataType                   # ON_CELLS, or ON_BFACES (boundary integrals: Identity of H1P1 / H1P2, NormalFlux of HDIVRT0 / HDIVBDM1)
 end
-ItemIntegrator(operator::DataType; regions = [0]) = DeviceItemIntegrator(operator, 0, nothing, 1.0, 0, regions)
-L2NormIntegrator(ncomponents::Int, operator::DataType; quadorder = 2, regions = [0]) = DeviceItemIntegrator(operator, 1, nothing, 1.0, quadorder, regions)
-L2ErrorIntegrator(compare_data, operator::DataType = Identity; quadorder = "auto", factor = 1, regions = [0]) =
-    DeviceItemIntegrator(operator, 2, compare_data, Float64(factor), quadorder == "auto" ? 2 * compare_data.bonus_quadorder : quadorder, regions)
+ItemIntegrator(operator::DataType; AT = ON_CELLS, regions = [0]) = DeviceItemIntegrator(operator, 0, nothing, 1.0, 0, regions, AT)
+L2NormIntegrator(ncomponents::Int, operator::DataType; AT = ON_CELLS, quadorder = 2, regions = [0]) =
+    DeviceItemIntegrator(operator, 1, nothing, 1.0, quadorder, regions, AT)
+L2ErrorIntegrator(compare_data, operator::DataType = Identity; AT = ON_CELLS, quadorder = "auto", factor = 1, regions = [0]) =
+    DeviceItemIntegrator(operator, 2, compare_data, Float64(factor), quadorder == "auto" ? 2 * compare_data.bonus_quadorder : quadorder, regions, AT)
 
 function prepare(II::DeviceItemIntegrator, FES::FESpace{Float64,Int32,FEType}) where {FEType}
     xgrid = FES.xgrid
-    EG = xgrid[UniqueCellGeometries][1]
+    EG = xgrid[GRMP.GridComponentUniqueGeometries4AssemblyType(II.AT)][1]           # cells, or the boundary-face geometry
     order = max(II.bonus_quadorder + GRMP.get_polynomialorder(FEType, EG) + GRMP.QuadratureOrderShift4Operator(II.operator), 0)   # assemblypatterns.jl:559-565
     qf = QuadratureRule{Float64,EG}(order)
-    ev = FEEvaluator(FES, II.operator, qf)
+    ev = FEEvaluator(FES, II.operator, qf; AT = II.AT)
     v, dv, t = evaltab(ev)
     w = Vector{Float64}(qf.w)
     regions = II.regions == [0] ? Int32[] : Vector{Int32}(II.regions)
     h = Ref{Ptr{Cvoid}}()
     GC.@preserve v dv w regions check(ccall((:grmp_ii_create, lib), Cint,
         (Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Cint, Cint, Ptr{Float64}, Ref{EvalTab}, Ref{Ptr{Cvoid}}),
-        device_space(FES).h, opcode(II.operator), II.kind, isempty(regions) ? C_NULL : pointer(regions), length(regions), length(w), w, t, h))
+        device_space(FES, II.AT).h, opcode(II.operator), II.kind, isempty(regions) ? C_NULL : pointer(regions), length(regions), length(w), w, t, h))
     return h[], ev, qf
 end
 
 # compare_data at the quadrature points, evaluated like L2error_function does (itemintegrator.jl:52-69) -> [resultdim, nq, ncells]
-function tabulate_data(data, ev, qf, xgrid)
-    ncells = num_sources(xgrid[CellNodes]); rd = data.argsizes[1]
+function tabulate_data(data, ev, qf, xgrid, AT = ON_CELLS)
+    ncells = num_sources(xgrid[GRMP.GridComponentNodes4AssemblyType(AT)]); rd = data.argsizes[1]
     tab = zeros(Float64, rd, length(qf.w), ncells)
     x = zeros(Float64, size(xgrid[Coordinates], 1))
     for cell = 1:ncells
@@ -668,7 +670,7 @@ end
 function evaluate!(b::Matrix{Float64}, II::DeviceItemIntegrator, FEB::FEVectorBlock{Float64,Float64,Int32}; total = nothing)
     h, ev, qf = prepare(II, FEB.FES)
     try
-        data = II.kind == 2 ? tabulate_data(II.data, ev, qf, FEB.FES.xgrid) : Float64[]
+        data = II.kind == 2 ? tabulate_data(II.data, ev, qf, FEB.FES.xgrid, II.AT) : Float64[]
         coeffs = FEB.entries[FEB.offset+1:FEB.last_index]
         GC.@preserve data coeffs b check(ccall((:grmp_ii_evaluate, lib), Cint,
             (Ptr{Cvoid}, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
