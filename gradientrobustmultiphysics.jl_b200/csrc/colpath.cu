@@ -223,7 +223,7 @@ template <class F, int NV>
 __global__ void __launch_bounds__(256) cf_kernel(const ColParams p) {
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthr = blockDim.x;
-  constexpr int ntab = F::NT * F::NSF * CT_PAD;
+  constexpr int ntab = F::NSF * cf_kblock(F::NSF, F::NT);
   __shared__ u32 s_maxlen[8];
   double* const sK = sm;
   double* const img = sm + ntab;
@@ -694,7 +694,7 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
   // tables
   if (cf) {
     // K_t[s][s_col] = sum_q w_q T[s][a][q] T[s_col][b][q] from the caller's own tables and weights (t = (a, b); symmetric G: a <= b and
-    // K_ab + K_ba merged), layout [t][s][CT_PAD]
+    // K_ab + K_ba merged), layout [s_col][s][t] in blocks of cf_kblock doubles
     const CfVariant& F = CFVARIANTS[cp->cf_variant];
     std::vector<double> T;
     int nas = 0;
@@ -706,14 +706,15 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
       for (int q = 0; q < nq; q++) v += w[q] * T[((size_t)sI * nas + a) * nq + q] * T[((size_t)sJ * nas + b) * nq + q];
       return v;
     };
-    std::vector<double> K((size_t)F.nt * nsf * CT_PAD, 0.0);
+    const int kb = cf_kblock(nsf, F.nt);
+    std::vector<double> K((size_t)nsf * kb, 0.0);
     for (int t = 0; t < F.nt; t++) {
       int a = 0, b = 0;
       if (nas > 1) {
         if (F.symk) { a = sym_a(ed, t); b = sym_b(ed, t); } else { a = t / ed; b = t % ed; }
       }
       for (int sI = 0; sI < nsf; sI++) for (int sJ = 0; sJ < nsf; sJ++)
-        K[((size_t)t * nsf + sI) * CT_PAD + sJ] = Kab(a, b, sI, sJ) + ((F.symk && a != b) ? Kab(b, a, sI, sJ) : 0.0);
+        K[(size_t)sJ * kb + sI * F.nt + t] = Kab(a, b, sI, sJ) + ((F.symk && a != b) ? Kab(b, a, sI, sJ) : 0.0);
     }
     if ((nas > 1) != (F.nt > 1)) return fail(GRMP_EUNSUPPORTED, "column kernels: closed-form table shape");
     GRMP_TRY(cp->tabC.upload(K.data(), K.size(), s));
@@ -809,7 +810,7 @@ int colpath_build(grmp_ctx* ctx, const BlfLocalParams& p, const Pattern& pat, co
     GRMP_CUDA(cudaStreamSynchronize(s));
     if (hflags[0]) return fail(GRMP_EUNSUPPORTED, "column kernels: a column has more than 254 entries or 65535 cells");
     // shared-memory need of every tile; tiles are launched in classes of similar need
-    const int ntab_even = cf ? CFVARIANTS[cp->cf_variant].nt * CFVARIANTS[cp->cf_variant].nsf * CT_PAD : (V.nas_c * nq * CT_PAD + 1) & ~1;
+    const int ntab_even = cf ? CFVARIANTS[cp->cf_variant].nsf * cf_kblock(CFVARIANTS[cp->cf_variant].nsf, CFVARIANTS[cp->cf_variant].nt) : (V.nas_c * nq * CT_PAD + 1) & ~1;
     DevBuf<int> need_d;
     GRMP_TRY(need_d.alloc(ntiles));
     tile_need<<<nblk(ntiles), 256, 0, s>>>(cp->pos_len.p, ntiles, ncols_used, nw, ntab_even, need_d.p);

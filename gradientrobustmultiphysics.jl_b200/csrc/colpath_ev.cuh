@@ -564,6 +564,25 @@ template <class Ev> __host__ inline bool ev_matches(const ColEvalDesc& d) {
 namespace grmp {
 
 __host__ __device__ constexpr int nsym(int ed) { return ed * (ed + 1) / 2; }
+// reference tensors in shared memory: K[s_col][s][t] (t fastest), one block of cf_kblock doubles per column function, so that the
+// NSF * NT numbers a column thread needs are contiguous and come in as 16-byte loads (half the shared-memory wavefronts of
+// the former [t][s][s_col] layout, where every number was its own 8-byte load)
+// block size = 2 (mod 4) doubles: consecutive blocks start 4 (mod 8) banks apart, so the 16-byte chunks that lanes with different s_col
+// read in one instruction fall into different banks (up to 8 column functions)
+__host__ __device__ constexpr int cf_kblock(int nsf, int nt) { return ((nsf * nt + 1) / 4) * 4 + 2; }
+// Sc[s] = sum_t G[t] K[s_col][s][t]
+template <int NSF, int NT> __device__ __forceinline__ void cf_contract(const double* __restrict__ sK, int scol, const double (&G)[NT], double (&Sc)[NSF]) {
+  constexpr int B = cf_kblock(NSF, NT);
+  const double2* __restrict__ kc = reinterpret_cast<const double2*>(sK + scol * B);
+#pragma unroll
+  for (int s = 0; s < NSF; s++) Sc[s] = 0.0;
+#pragma unroll
+  for (int c = 0; c < B / 2; c++) {
+    const double2 kk = kc[c];
+    if (2 * c < NSF * NT) Sc[(2 * c) / NT] = fma(G[(2 * c) % NT], kk.x, Sc[(2 * c) / NT]);
+    if (2 * c + 1 < NSF * NT) Sc[(2 * c + 1) / NT] = fma(G[(2 * c + 1) % NT], kk.y, Sc[(2 * c + 1) / NT]);
+  }
+}
 __host__ __device__ constexpr int sym_a(int ed, int t) { return ed == 2 ? (t == 0 ? 0 : (t == 1 ? 0 : 1)) : (t < 3 ? 0 : (t < 5 ? 1 : 2)); }
 __host__ __device__ constexpr int sym_b(int ed, int t) { return ed == 2 ? (t == 0 ? 0 : (t == 1 ? 1 : 1)) : (t == 0 ? 0 : t == 1 ? 1 : t == 2 ? 2 : t == 3 ? 1 : t == 4 ? 2 : 2); }
 
@@ -624,13 +643,7 @@ template <int ED_, int NC_, int NDS_, int NBUB_, int OPK_> struct CfH1 {
 #pragma unroll
     for (int t = 0; t < NT; t++) G[t] = cr[t];
     double Sc[NSF];
-#pragma unroll
-    for (int s = 0; s < NSF; s++) {
-      double v = 0.0;
-#pragma unroll
-      for (int t = 0; t < NT; t++) v = fma(G[t], sK[(t * NSF + s) * CT_PAD + scol], v);
-      Sc[s] = v;
-    }
+    cf_contract<NSF, NT>(sK, scol, G, Sc);
 #pragma unroll
     for (int c = 0; c < NC; c++)
 #pragma unroll
@@ -680,13 +693,10 @@ template <int ED_, int NDALL_> struct CfHdivMass {
     double G[NT];
 #pragma unroll
     for (int t = 0; t < NT; t++) G[t] = cr[t];
+    double Sc[NSF];
+    cf_contract<NSF, NT>(sK, l, G, Sc);
 #pragma unroll
-    for (int r = 0; r < NDALL_; r++) {
-      double v = 0.0;
-#pragma unroll
-      for (int t = 0; t < NT; t++) v = fma(G[t], sK[(t * NSF + r) * CT_PAD + l], v);
-      emit(r, ((flip >> r) & 1u) ? -v : v);
-    }
+    for (int r = 0; r < NDALL_; r++) emit(r, ((flip >> r) & 1u) ? -Sc[r] : Sc[r]);
   }
 };
 
