@@ -231,3 +231,23 @@ def test_interpolated_and_homogeneous_boundary_data_host_part(dim):
     assert np.all(t.entries[reg4 - 1] == 0.0)
     untouched = np.setdiff1d(np.arange(s.ndofs), fixed - 1)
     assert np.all(t.entries[untouched] == 9.0)
+
+
+def test_julia_glue_binds_only_declared_entry_points():
+    """every `ccall((:grmp_..., lib), ...)` of julia/GRMPCuda.jl and every entry point shown in INTEGRATION.md is declared in include/grmp.h
+    (the glue cannot run here: no Julia; this keeps it from drifting away from the ABI)"""
+    hdr = open(os.path.join(ROOT, "include", "grmp.h")).read()
+    declared = set(re.findall(r"\b(grmp_[a-z_0-9]+)\s*\(", hdr))
+    jl = open(os.path.join(ROOT, "julia", "GRMPCuda.jl")).read()
+    used = set(re.findall(r":(grmp_[a-z_0-9]+)", jl))
+    assert len(used) >= 25
+    assert used <= declared, sorted(used - declared)
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    named = set(re.findall(r"`(grmp_[a-z_0-9]+)`", doc)) - {"grmp_evaltab", "grmp_b200", "grmp_stats", "grmp_ctx", "grmp_grid", "grmp_space", "grmp_blf", "grmp_lf", "grmp_ii"}
+    assert named <= declared, sorted(named - declared)
+    # operator codes of the glue agree with the header's enum
+    ops = dict(re.findall(r"(GRMP_OP_[A-Z0-9_]+) = (\d+)", hdr))
+    glue = {"Identity": "GRMP_OP_ID", "Gradient": "GRMP_OP_GRAD", "SymmetricGradient{1}": "GRMP_OP_SYMGRAD", "Divergence": "GRMP_OP_DIV",
+            "NormalFlux": "GRMP_OP_NORMALFLUX"}
+    for jname, cname in glue.items():
+        assert "opcode(::Type{%s}) = %s" % (jname, ops[cname]) in jl, jname
