@@ -134,12 +134,10 @@ __global__ void __launch_bounds__(256) col_kernel(const ColParams p) {
     for (int v = 0; v < NV; v++) { w[4 * v] = rn[v].x; w[4 * v + 1] = rn[v].y; w[4 * v + 2] = rn[v].z; w[4 * v + 3] = rn[v].w; }
     const u32 lc = w[0] >> 24;
     const bool work = k < np && lc != 255u;
-    // geometry record of this round's cell: 16-byte loads, issued before the next record is requested
+    // geometry record of this round's cell: 256-bit loads, issued before the next record is requested
     double cr[L::STRIDE];
     if (work) {
-      const double2* src = reinterpret_cast<const double2*>(p.geo + (size_t)(w[0] & 0xffffffu) * L::STRIDE);
-#pragma unroll
-      for (int i = 0; i < L::STRIDE / 2; i++) { const double2 t = __ldg(src + i); cr[2 * i] = t.x; cr[2 * i + 1] = t.y; }
+      load_record<L::STRIDE>(p.geo + (size_t)(w[0] & 0xffffffu) * L::STRIDE, cr);
     }
     {
       const u32 i1 = next_idx(k + 1);
@@ -274,9 +272,7 @@ __global__ void __launch_bounds__(256) cf_kernel(const ColParams p) {
     const bool work = k < np && lc != 255u;
     double cr[F::STRIDE];
     if (work) {
-      const double2* src = reinterpret_cast<const double2*>(p.geo + (size_t)(w[0] & 0xffffffu) * F::STRIDE);
-#pragma unroll
-      for (int i = 0; i < F::STRIDE / 2; i++) { const double2 t = __ldg(src + i); cr[2 * i] = t.x; cr[2 * i + 1] = t.y; }
+      load_record<F::STRIDE>(p.geo + (size_t)(w[0] & 0xffffffu) * F::STRIDE, cr);
     }
     {
       const u32 i1 = next_idx(k + 1);

@@ -489,6 +489,23 @@ template <int ACT, int RD> __device__ __forceinline__ void apply_action_col(cons
   }
 }
 
+// a cell's geometry record (N doubles, N even).  The lanes of a warp read records of different cells, so every load instruction costs one
+// wavefront per lane on the L1 data pipe -- which is what bounds the column kernels.  Records whose size is a multiple of 32 bytes are
+// 32-byte aligned and read with 256-bit loads (LDG.E.256 on sm_100a: half the instructions = half the wavefronts; +3 % on the P2 triangle
+// Laplacian, the RT0 mass matrix and the reconstruction mass form); padding the other records up to that size was measured and costs
+// more bytes than it saves wavefronts (Bernardi-Raugel Laplacian -5 %, Hooke -4 %), so they keep 16-byte loads.
+template <int N> __device__ __forceinline__ void load_record(const double* __restrict__ src, double (&cr)[N]) {
+  static_assert(N % 2 == 0, "record stride");
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 4; i++)
+      asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(cr[4 * i]), "=d"(cr[4 * i + 1]), "=d"(cr[4 * i + 2]), "=d"(cr[4 * i + 3]) : "l"(src + 4 * i));
+  } else {
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) { const double2 t = __ldg(reinterpret_cast<const double2*>(src) + i); cr[2 * i] = t.x; cr[2 * i + 1] = t.y; }
+  }
+}
+
 // cache record of one cell: [0] item factor (CellVolumes * factor, bilinearform.jl:320), then the row evaluator's part, then
 // the column evaluator's part unless both need the same data
 template <class RowEv, class ColEv> struct CacheLayout {
@@ -496,7 +513,7 @@ template <class RowEv, class ColEv> struct CacheLayout {
                                 RowEv::CACHE_N == ColEv::CACHE_N);
   static constexpr int OFF_R = 1, OFF_C = SAME ? 1 : 1 + RowEv::CACHE_N;
   static constexpr int N = 1 + RowEv::CACHE_N + (SAME ? 0 : ColEv::CACHE_N);
-  static constexpr int STRIDE = (N + 1) & ~1;     // even: records stay 16-byte aligned
+  static constexpr int STRIDE = (N + 1) & ~1;     // even: records stay 16-byte aligned (32-byte aligned when a multiple of 4: load_record)
 };
 
 // (the column kernels store CellVolumes here and apply `factor` when they read the record)
