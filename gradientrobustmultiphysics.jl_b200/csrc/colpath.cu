@@ -44,7 +44,7 @@ struct ColParams {
   const unsigned char* pos_len;    //   stored entries
   const i64* pos_start;            //   first nzval slot of the column (0-based)
   const i64* pos_recbeg;           //   first record (exclusive scan of pos_np); groups start at multiples of 32
-  const double* geo;        // [ncells][STRIDE] geometry records of this assembly (cell_geo_kernel)
+  const double* geo;        // geometry records of this assembly (cell_geo_kernel): [ncells][quads] then [ncells][tail pair], see load_record
   const u32* tile_list;     // tiles of this launch (one class)
   const double* tabC;
   double factor;
@@ -71,9 +71,7 @@ __global__ void __launch_bounds__(256) cell_geo_kernel(const GridView g, double*
 #pragma unroll
   for (int i = 0; i < L::STRIDE; i++) cr[i] = 0.0;
   build_cell_cache<RowEv, ColEv>(g, cell, 1.0, cr);
-  double2* dst = reinterpret_cast<double2*>(geo + cell * L::STRIDE);
-#pragma unroll
-  for (int i = 0; i < L::STRIDE / 2; i++) dst[i] = make_double2(cr[2 * i], cr[2 * i + 1]);
+  store_record<L::STRIDE>(geo, g.ncells, cell, cr);
 }
 
 template <class RowEv, class ColEv, int ACT, int NV, int NQ>
@@ -137,7 +135,7 @@ __global__ void __launch_bounds__(256) col_kernel(const ColParams p) {
     // geometry record of this round's cell: 256-bit loads, issued before the next record is requested
     double cr[L::STRIDE];
     if (work) {
-      load_record<L::STRIDE>(p.geo + (size_t)(w[0] & 0xffffffu) * L::STRIDE, cr);
+      load_record<L::STRIDE>(p.geo, p.g.ncells, (i64)(w[0] & 0xffffffu), cr);
     }
     {
       const u32 i1 = next_idx(k + 1);
@@ -212,9 +210,7 @@ __global__ void __launch_bounds__(256) cf_geo_kernel(const GridView g, double ac
   for (int i = 0; i < F::STRIDE; i++) cr[i] = 0.0;
   const double act_p[2] = {act0, act1};
   F::geo(g, cell, act_p, cr);
-  double2* dst = reinterpret_cast<double2*>(geo + cell * F::STRIDE);
-#pragma unroll
-  for (int i = 0; i < F::STRIDE / 2; i++) dst[i] = make_double2(cr[2 * i], cr[2 * i + 1]);
+  store_record<F::STRIDE>(geo, g.ncells, cell, cr);
 }
 
 template <class F, int NV>
@@ -272,7 +268,7 @@ __global__ void __launch_bounds__(256) cf_kernel(const ColParams p) {
     const bool work = k < np && lc != 255u;
     double cr[F::STRIDE];
     if (work) {
-      load_record<F::STRIDE>(p.geo + (size_t)(w[0] & 0xffffffu) * F::STRIDE, cr);
+      load_record<F::STRIDE>(p.geo, p.g.ncells, (i64)(w[0] & 0xffffffu), cr);
     }
     {
       const u32 i1 = next_idx(k + 1);

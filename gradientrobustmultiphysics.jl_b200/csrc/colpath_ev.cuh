@@ -489,21 +489,41 @@ template <int ACT, int RD> __device__ __forceinline__ void apply_action_col(cons
   }
 }
 
-// a cell's geometry record (N doubles, N even).  The lanes of a warp read records of different cells, so every load instruction costs one
-// wavefront per lane on the L1 data pipe -- which is what bounds the column kernels.  Records whose size is a multiple of 32 bytes are
-// 32-byte aligned and read with 256-bit loads (LDG.E.256 on sm_100a: half the instructions = half the wavefronts; +3 % on the P2 triangle
-// Laplacian, the RT0 mass matrix and the reconstruction mass form); padding the other records up to that size was measured and costs
-// more bytes than it saves wavefronts (Bernardi-Raugel Laplacian -5 %, Hooke -4 %), so they keep 16-byte loads.
-template <int N> __device__ __forceinline__ void load_record(const double* __restrict__ src, double (&cr)[N]) {
+// Geometry records (N doubles per cell, N even).  The lanes of a warp read records of different cells, so every load instruction costs one
+// wavefront per lane on the L1 data pipe -- which is what bounds the column kernels.  Records of 32-byte-multiple size are 32-byte aligned
+// and read with 256-bit loads (LDG.E.256 on sm_100a).  Records of N = 2 (mod 4) >= 10 doubles are stored split: the first N - 2 doubles of
+// every cell as an array of aligned quads, the last pair in a second array behind it (one 16-byte load): ceil(N/4) load instructions
+// instead of N/2, no padding bytes (P1 tetrahedron Laplacian, 24 pairs per column: 0.62 -> 0.57 ms).  Measured alternatives: padding
+// every record to a multiple of 32 bytes loses (Bernardi-Raugel Laplacian -5 %, Hooke -4 %: more bytes than saved wavefronts), and
+// splitting 6-double records loses 1.4 % on the Hooke form (a second cache line per pair for one saved instruction), so those stay
+// contiguous with 16-byte loads.
+template <int N> struct rec_layout {
+  static constexpr bool SPLIT = (N % 4 == 2) && N >= 10;
+  static constexpr int Q4 = SPLIT ? N - 2 : N;          // doubles of a cell in the first array
+};
+template <int N> __device__ __forceinline__ void load_record(const double* __restrict__ geo, i64 ncells, i64 cell, double (&cr)[N]) {
   static_assert(N % 2 == 0, "record stride");
-  if constexpr (N % 4 == 0) {
+  constexpr int Q4 = rec_layout<N>::Q4;
+  const double* __restrict__ src = geo + cell * Q4;
+  if constexpr (Q4 % 4 == 0) {
 #pragma unroll
-    for (int i = 0; i < N / 4; i++)
+    for (int i = 0; i < Q4 / 4; i++)
       asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(cr[4 * i]), "=d"(cr[4 * i + 1]), "=d"(cr[4 * i + 2]), "=d"(cr[4 * i + 3]) : "l"(src + 4 * i));
   } else {
 #pragma unroll
-    for (int i = 0; i < N / 2; i++) { const double2 t = __ldg(reinterpret_cast<const double2*>(src) + i); cr[2 * i] = t.x; cr[2 * i + 1] = t.y; }
+    for (int i = 0; i < Q4 / 2; i++) { const double2 t = __ldg(reinterpret_cast<const double2*>(src) + i); cr[2 * i] = t.x; cr[2 * i + 1] = t.y; }
   }
+  if constexpr (rec_layout<N>::SPLIT) {
+    const double2 t = __ldg(reinterpret_cast<const double2*>(geo + ncells * Q4) + cell);
+    cr[Q4] = t.x; cr[Q4 + 1] = t.y;
+  }
+}
+template <int N> __device__ __forceinline__ void store_record(double* __restrict__ geo, i64 ncells, i64 cell, const double (&cr)[N]) {
+  constexpr int Q4 = rec_layout<N>::Q4;
+  double2* dst = reinterpret_cast<double2*>(geo + cell * Q4);
+#pragma unroll
+  for (int i = 0; i < Q4 / 2; i++) dst[i] = make_double2(cr[2 * i], cr[2 * i + 1]);
+  if constexpr (rec_layout<N>::SPLIT) reinterpret_cast<double2*>(geo + ncells * Q4)[cell] = make_double2(cr[Q4], cr[Q4 + 1]);
 }
 
 // cache record of one cell: [0] item factor (CellVolumes * factor, bilinearform.jl:320), then the row evaluator's part, then
