@@ -266,3 +266,48 @@ def test_boundary_item_integrators(dim):
     assert 0.0 <= err < 1e-24
     nrm = G.evaluate(G.L2NormIntegrator(1, G.Identity, quadorder=4, AT="ON_BFACES"), v[1])
     assert nrm > 1.0
+
+
+# ---- the reference's own KAT: test/runtests.jl:481-509 "H1-Bestapproximations" ------------------------------------------------------
+def _exact(dim, order):
+    """exact_function2D / exact_function3D of test/runtests.jl:38-80 and their gradients (row-major: d_k u_c at [c * dim + k])"""
+    if dim == 2:
+        u = lambda x: np.stack([x[0] ** order + 2 * x[1] ** order + 1, 3 * x[0] ** order - x[1] ** order - 1])
+        dp = lambda t: order * t ** (order - 1) if order > 0 else 0.0 * t
+        du = lambda x: np.stack([dp(x[0]), 2 * dp(x[1]), 3 * dp(x[0]), -dp(x[1])])
+    else:
+        u = lambda x: np.stack([2 * x[2] ** order - x[1] ** order - 1, x[0] ** order + 2 * x[1] ** order + 1, 3 * x[0] ** order - x[1] ** order - 1])
+        dp = lambda t: order * t ** (order - 1) if order > 0 else 0.0 * t
+        z = lambda x: 0.0 * x[0]
+        du = lambda x: np.stack([z(x), -dp(x[1]), 2 * dp(x[2]), dp(x[0]), 2 * dp(x[1]), z(x), 3 * dp(x[0]), -dp(x[1]), z(x)])
+    return u, du
+
+
+@pytest.mark.parametrize("dim,fe,order", [(2, "P1", 1), (2, "P2", 2), (3, "P1", 1), (3, "P2", 2)])
+def test_reference_kat_h1_bestapproximation_with_bestapprox_boundary(dim, fe, order):
+    """H1BestapproximationProblem(grad u, u; bestapprox_boundary_regions = [1, 2]) (pdeprototypes.jl:170-201) on testgrid (runtests.jl:14-19),
+    FETypes of TestCatalog3D (H1P1{3}: order 1, H1P2{3,3}: order 2) and their 2D twins: LaplaceOperator + LinearForm(Gradient, grad u) assembled on the
+    device, boundary data by boundarydata (ON_BFACES forms on the device), penalties on the device, host solve, L2ErrorIntegrator on the device;
+    the reference asserts sqrt(error) < 6e-12 (runtests.jl:23, 503)"""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    g = G.uniform_refine(G.grid_unitsquare() if dim == 2 else G.grid_unitcube(), 1)
+    s = G.FESpace(G.H1P1(dim) if fe == "P1" else G.H1P2(dim, dim), g)
+    u, du = _exact(dim, order)
+    udata = G.DataFunction(u, [dim, dim], bonus_quadorder=order)
+    gdata = G.DataFunction(du, [dim * dim, dim], bonus_quadorder=max(order - 1, 0))
+    A = G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [s, s])                    # LaplaceOperator()
+    cp, rv, _ = G.assemble_csc(A, 1.0)
+    rhs = G.FEVector([s])
+    G.assemble(rhs[1], G.DiscreteLinearForm([G.Gradient], [s], G.fdot_action(gdata)))          # LinearForm(Gradient, grad u)
+    sol = G.FEVector([s])
+    fixed = G.boundarydata(sol[1], [G.BoundaryData(G.BestapproxDirichletBoundary, data=udata, regions=[1, 2])])
+    assert fixed.size > 0
+    penalty = 1e60                                                                              # solvers.jl:632-652
+    G.apply_penalties(A, fixed, penalty)
+    rhs.entries[fixed - 1] = penalty * sol.entries[fixed - 1]
+    M = sp.csc_matrix((G.fetch_values(A), rv - 1, cp - 1), shape=(s.ndofs, s.ndofs))
+    sol.entries[:] = spla.spsolve(M, rhs.entries)
+    err2 = G.evaluate(G.L2ErrorIntegrator(udata, G.Identity, quadorder=order), sol[1])
+    assert np.all(np.asarray(err2) >= -1e-30)
+    assert np.sqrt(np.abs(np.asarray(err2)).sum()) < 6e-12

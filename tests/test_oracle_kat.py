@@ -3,7 +3,8 @@
 The reference ships no golden matrices; what it pins are closed-form results:
   * quadrature exactness                                   (test/runtests.jl:81-137)
   * ExampleA01 rational P1 mass matrix |T|/12 [2 1 1;...]  (examples/ExampleA01_RationalMassMatrix.jl:17-35)
-  * L2 / H1 best-approximation reproduces polynomials      (test/runtests.jl:355-509)
+  * L2 / H1 best-approximation reproduces polynomials      (test/runtests.jl:355-509; the H1 test incl. its best-approximation
+    boundary data is replayed literally at the end of this file)
   * Stokes / reconstruction exactness                      (test/runtests.jl:606-723)
   * u'Bp = 1.5 for u=(x,y), p=x+y... on [-1 0;1 0;0 1]     (test/test_operators.jl:15-82)
 They are replayed here through quadratic forms of interpolants (no solver needed) and
@@ -498,3 +499,65 @@ def test_hdiv_normalflux_face_bases_are_dual_to_the_face_moments(dim, fam):
     # RT0: the moment is |F| u.n, the mass matrix is diag(1 / |F|)
     if fam == "RT0":
         assert np.abs(M.diagonal()[dofs[:, 0]] * vol - 1.0).max() < 1e-14
+
+
+# ---- the reference's own "H1-Bestapproximations" test (test/runtests.jl:481-509), replayed through the oracle alone ------------------
+def _xq_items(grid, xr):
+    x = grid.coords
+    cn = grid.cellnodes.astype(np.int64) - 1
+    xq = np.repeat(x[cn[:, 0]][:, None, :], xr.shape[0], axis=1).copy()
+    for j in range(grid.dim):
+        xq += (x[cn[:, j + 1]] - x[cn[:, 0]])[:, None, :] * xr[None, :, j, None]
+    return xq
+
+
+@pytest.mark.parametrize("dim,fe,order", [(2, "P1", 1), (2, "P2", 2), (3, "P1", 1), (3, "P2", 2)])
+def test_reference_h1_bestapproximation_with_bestapprox_boundary(dim, fe, order):
+    """H1BestapproximationProblem(grad u, u; bestapprox_boundary_regions = [1, 2]) (pdeprototypes.jl:170-201) with exact_function2D / 3D
+    (runtests.jl:38-80) on testgrid (runtests.jl:14-19); FETypes H1P1{3} (order 1) and H1P2{3,3} (order 2) of TestCatalog3D and their 2D
+    twins.  Every assembled object comes from the oracle: LaplaceOperator, LinearForm(Gradient, grad u), the ON_BFACES mass matrix and
+    right-hand side of the boundary best approximation (boundarydata.jl:297-347), the L2ErrorIntegrator.  The reference asserts
+    sqrt(error) < 6e-12 (runtests.jl:23, 503)."""
+    import scipy.sparse as sp_
+    g = G.uniform_refine(G.grid_unitsquare() if dim == 2 else G.grid_unitcube(), 1)
+    s = G.FESpace(G.H1P1(dim) if fe == "P1" else G.H1P2(dim, dim), g)
+    dp = lambda t: order * t ** (order - 1)
+    if dim == 2:
+        u = lambda x: np.stack([x[0] ** order + 2 * x[1] ** order + 1, 3 * x[0] ** order - x[1] ** order - 1])
+        du = lambda x: np.stack([dp(x[0]), 2 * dp(x[1]), 3 * dp(x[0]), -dp(x[1])])
+    else:
+        u = lambda x: np.stack([2 * x[2] ** order - x[1] ** order - 1, x[0] ** order + 2 * x[1] ** order + 1, 3 * x[0] ** order - x[1] ** order - 1])
+        z = lambda x: 0.0 * x[0]
+        du = lambda x: np.stack([z(x), -dp(x[1]), 2 * dp(x[2]), dp(x[0]), 2 * dp(x[1]), z(x), 3 * dp(x[0]), -dp(x[1]), z(x)])
+    pk = s.fetype.polynomialorder(dim)
+    tab = lambda f, grid, xr: np.ascontiguousarray(np.moveaxis(f(_xq_items(grid, xr).reshape(-1, dim).T).reshape(-1, grid.ncells, xr.shape[0]), 0, 2))
+    # LaplaceOperator and LinearForm(Gradient, grad u)
+    K = assemble(g, s, s, O.OP_GRAD, O.OP_GRAD, apt=O.APT_SYMMETRIC).tocsc()
+    xr, _ = O.qrule(dim, pk - 1 + order)
+    b = np.zeros(s.ndofs)
+    O.lf_assemble(b, g, s, O.OP_GRAD, fsrc=O.F_QP_TABLE, fdata=tab(du, g, xr), bonus_quadorder=order)
+    # best-approximation Dirichlet data on the boundary regions 1, 2
+    bs = s.on_bfaces()
+    bg = bs.xgrid
+    Mb = O.OracleMatrix(s.ndofs, s.ndofs)
+    O.blf_assemble(Mb, bg, bs, bs, O.OP_ID, O.OP_ID, apt=O.APT_SYMMETRIC, regions=[1, 2])
+    Mb = Mb.toscipy().tocsc()
+    xrb, _ = O.qrule(bg.dim, pk + order)
+    bb = np.zeros(s.ndofs)
+    O.lf_assemble(bb, bg, bs, O.OP_ID, fsrc=O.F_QP_TABLE, fdata=tab(u, bg, xrb), regions=[1, 2], bonus_quadorder=order)
+    keep = np.flatnonzero(np.diff(Mb.indptr) != 0)
+    fixed = np.unique(bs.celldofs[np.isin(bg.cellregions, [1, 2])].astype(np.int64).ravel() - 1)
+    assert np.array_equal(keep, fixed)
+    target = np.zeros(s.ndofs)
+    target[keep] = spla.spsolve(Mb[keep][:, keep].tocsc(), bb[keep])
+    # penalties (fematrix.jl:349-355, solvers.jl:632-652) and solve
+    penalty = 1e60
+    K = K.tolil()
+    for j in fixed:
+        K[j, j] = penalty
+    b[fixed] = penalty * target[fixed]
+    sol = spla.spsolve(K.tocsc(), b)
+    # L2ErrorIntegrator(u, Identity; quadorder = order): order of the rule = quadorder + polynomial order of the space
+    xre, _ = O.qrule(dim, order + pk)
+    _, tot = O.ii_evaluate(g, s, O.OP_ID, sol, kind=O.II_L2ERROR, data=tab(u, g, xre), bonus_quadorder=order, itemwise=False)
+    assert np.sqrt(np.abs(tot).sum()) < TOL
