@@ -561,3 +561,38 @@ def test_reference_h1_bestapproximation_with_bestapprox_boundary(dim, fe, order)
     xre, _ = O.qrule(dim, order + pk)
     _, tot = O.ii_evaluate(g, s, O.OP_ID, sol, kind=O.II_L2ERROR, data=tab(u, g, xre), bonus_quadorder=order, itemwise=False)
     assert np.sqrt(np.abs(tot).sum()) < TOL
+
+
+# ---- the reference's own "L2-Bestapproximations" test (test/runtests.jl:355-447) for every FEType of its catalogue that is on the path ----
+L2_CATALOG = [(2, "HDIVRT0", 0), (2, "HDIVBDM1", 1), (2, "L2P0", 0), (2, "H1P1", 1), (2, "H1BR", 1), (2, "H1P2", 2),
+              (3, "HDIVRT0", 0), (3, "HDIVBDM1", 1), (3, "L2P0", 0), (3, "H1P1", 1), (3, "H1BR", 1), (3, "H1P2", 2)]
+
+
+def catalog_fetype(name, dim):
+    return {"HDIVRT0": lambda: G.HDIVRT0(dim), "HDIVBDM1": lambda: G.HDIVBDM1(dim), "L2P0": lambda: G.L2P0(dim), "H1P1": lambda: G.H1P1(dim),
+            "H1BR": lambda: G.H1BR(dim), "H1P2": lambda: G.H1P2(dim, dim)}[name]()
+
+
+def exact_function(dim, order):
+    """exact_function2D / exact_function3D (runtests.jl:38-80)"""
+    if dim == 2:
+        return lambda x: np.stack([x[0] ** order + 2 * x[1] ** order + 1, 3 * x[0] ** order - x[1] ** order - 1])
+    return lambda x: np.stack([2 * x[2] ** order - x[1] ** order - 1, x[0] ** order + 2 * x[1] ** order + 1, 3 * x[0] ** order - x[1] ** order - 1])
+
+
+@pytest.mark.parametrize("dim,name,order", L2_CATALOG, ids=["%s{%d} order %d" % (n, d, o) for d, n, o in L2_CATALOG])
+def test_reference_l2_bestapproximation(dim, name, order):
+    """L2BestapproximationProblem(u; bestapprox_boundary_regions = []) = ReactionOperator + LinearForm(Identity, u) (pdeprototypes.jl:110-158), solved,
+    then sqrt(evaluate(L2ErrorIntegrator(u, Identity; quadorder = order), Solution)) < 6e-12 (runtests.jl:355-381) on testgrid (runtests.jl:14-19)"""
+    g = G.uniform_refine(G.grid_unitsquare() if dim == 2 else G.grid_unitcube(), 1)
+    s = G.FESpace(catalog_fetype(name, dim), g)
+    u = exact_function(dim, order)
+    pk = s.fetype.polynomialorder(dim)
+    tab = lambda xr: np.ascontiguousarray(np.moveaxis(u(_xq_items(g, xr).reshape(-1, dim).T).reshape(-1, g.ncells, xr.shape[0]), 0, 2))
+    M = assemble(g, s, s, O.OP_ID, O.OP_ID).tocsc()
+    xr, _ = O.qrule(dim, pk + order)
+    b = np.zeros(s.ndofs)
+    O.lf_assemble(b, g, s, O.OP_ID, fsrc=O.F_QP_TABLE, fdata=tab(xr), bonus_quadorder=order)
+    sol = spla.spsolve(M, b)
+    _, tot = O.ii_evaluate(g, s, O.OP_ID, sol, kind=O.II_L2ERROR, data=tab(xr), bonus_quadorder=order, itemwise=False)
+    assert np.sqrt(np.abs(tot).sum()) < TOL
