@@ -26,3 +26,55 @@ def test_reference_l2_bestapproximation_on_device(dim, name, order):
     sol.entries[:] = spla.spsolve(sp.csc_matrix((nz, rv - 1, cp - 1), shape=(s.ndofs, s.ndofs)), rhs.entries)
     err2 = G.evaluate(G.L2ErrorIntegrator(udata, G.Identity, quadorder=order), sol[1])
     assert np.sqrt(np.abs(np.asarray(err2)).sum()) < 6e-12
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_reference_stokes_taylor_hood_on_device(dim):
+    """"Stokes-FEM" (runtests.jl:606-672) for the Taylor-Hood pairs of its catalogues: [H1P2{2,2}, H1P1{1}] on Triangle2D and [H1P2{3,3}, H1P1{1}] on
+    Tetrahedron3D, orders (2, 1): IncompressibleNavierStokesProblem(dim; nonlinear = false) = LaplaceOperator + LagrangeMultiplier(Divergence) with the
+    transposed block (pdeprototypes.jl), BestapproxDirichletBoundary for the velocity on all boundary regions, LinearForm(Identity, rhs), pressure
+    with zero integral mean; then max(errorV, errorP) < tolerance.  Operators, boundary forms and error integrators run on the device."""
+    g = G.uniform_refine(G.grid_unitsquare() if dim == 2 else G.grid_unitcube(), 1)
+    sv, sq = G.FESpace(G.H1P2(dim, dim), g), G.FESpace(G.H1P1(1), g)
+    ov, op = 2, 1
+    if dim == 2:       # exact_functions_stokes2D (runtests.jl:522-545)
+        u = lambda x: np.stack([x[1] ** ov + 1, x[0] ** ov - 1])
+        p = lambda x: np.stack([x[0] ** op + x[1] ** op - 2.0 / (op + 1)])
+        f = lambda x: np.stack([-ov * (ov - 1) * x[1] ** (ov - 2) + op * x[0] ** (op - 1), -ov * (ov - 1) * x[0] ** (ov - 2) + op * x[1] ** (op - 1)])
+    else:              # exact_functions_stokes3D (runtests.jl:547-576)
+        u = lambda x: np.stack([x[2] ** ov + 1, x[0] ** ov - 1, x[1] ** ov])
+        p = lambda x: np.stack([x[0] ** op + x[1] ** op + x[2] ** op - 3.0 / (op + 1)])
+        f = lambda x: np.stack([-ov * (ov - 1) * x[2] ** (ov - 2) + op * x[0] ** (op - 1), -ov * (ov - 1) * x[0] ** (ov - 2) + op * x[1] ** (op - 1),
+                                -ov * (ov - 1) * x[1] ** (ov - 2) + op * x[2] ** (op - 1)])
+    udata = G.DataFunction(u, [dim, dim], bonus_quadorder=ov)
+    pdata = G.DataFunction(p, [1, dim], bonus_quadorder=op)
+    fdata = G.DataFunction(f, [dim, dim], bonus_quadorder=max(0, op - 1))
+    A = G.FEMatrix([sv, sq])
+    G.assemble_operator(A[1, 1], G.LaplaceOperator(1.0))
+    G.assemble_operator(A[1, 2], G.LagrangeMultiplier(G.Divergence), At=A[2, 1])
+    rhs = G.FEVector([sv, sq])
+    G.assemble_operator(rhs[1], G.LinearForm(G.Identity, fdata))
+    sol = G.FEVector([sv, sq])
+    fixed = G.boundarydata(sol[1], [G.BoundaryData(G.BestapproxDirichletBoundary, data=udata, regions=list(range(1, int(g.bfaceregions.max()) + 1)))])
+    assert np.array_equal(np.sort(fixed), np.unique(sv.bfacedofs))
+    # penalties for the velocity boundary dofs and for one pressure dof (FixedIntegralMean: fix, solve, shift; globalconstraints.jl)
+    M = A.tocsc().tolil()
+    b = rhs.entries.copy()
+    penalty = 1e60
+    for j in fixed - 1:
+        M[j, j] = penalty
+        b[j] = penalty * sol.entries[j]
+    jp = sv.ndofs
+    M[jp, jp] = penalty
+    b[jp] = 0.0
+    # the penalised rows are scaled back to O(1) before the factorisation: the reference's `\` (UMFPACK) equilibrates the 1e60 rows of this
+    # indefinite system, SuperLU's default does not (same equations, same solution)
+    d = np.ones(M.shape[0])
+    d[fixed - 1] = 1.0 / penalty
+    d[jp] = 1.0 / penalty
+    sol.entries[:] = spla.spsolve((sp.diags(d) @ M.tocsr()).tocsc(), d * b)
+    mean = G.evaluate(G.ItemIntegrator([G.Identity]), sol[2]) / g.cellvolumes.sum()
+    sol.entries[sv.ndofs:] -= mean
+    errV = np.sqrt(np.abs(np.asarray(G.evaluate(G.L2ErrorIntegrator(udata, G.Identity, quadorder=ov), sol[1]))).sum())
+    errP = np.sqrt(abs(G.evaluate(G.L2ErrorIntegrator(pdata, G.Identity, quadorder=op), sol[2])))
+    assert max(errV, errP) < 6e-12, (errV, errP)

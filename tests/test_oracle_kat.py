@@ -596,3 +596,61 @@ def test_reference_l2_bestapproximation(dim, name, order):
     sol = spla.spsolve(M, b)
     _, tot = O.ii_evaluate(g, s, O.OP_ID, sol, kind=O.II_L2ERROR, data=tab(xr), bonus_quadorder=order, itemwise=False)
     assert np.sqrt(np.abs(tot).sum()) < TOL
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_reference_stokes_taylor_hood(dim):
+    """"Stokes-FEM" (runtests.jl:606-672) for the Taylor-Hood pairs of its catalogues ([H1P2{2,2}, H1P1{1}] on Triangle2D, [H1P2{3,3}, H1P1{1}] on
+    Tetrahedron3D, orders (2, 1)) through the oracle alone: LaplaceOperator, LagrangeMultiplier(Divergence) and its transposed block,
+    LinearForm(Identity, rhs), BestapproxDirichletBoundary of the velocity on all boundary regions (ON_BFACES mass matrix and right-hand side),
+    pressure with zero integral mean, L2ErrorIntegrators for velocity and pressure under the reference's tolerance"""
+    import scipy.sparse as sp_
+    g = G.uniform_refine(G.grid_unitsquare() if dim == 2 else G.grid_unitcube(), 1)
+    sv, sq = G.FESpace(G.H1P2(dim, dim), g), G.FESpace(G.H1P1(1), g)
+    ov, op = 2, 1
+    if dim == 2:       # exact_functions_stokes2D (runtests.jl:522-545)
+        u = lambda x: np.stack([x[1] ** ov + 1, x[0] ** ov - 1])
+        p = lambda x: np.stack([x[0] ** op + x[1] ** op - 2.0 / (op + 1)])
+        f = lambda x: np.stack([-ov * (ov - 1) * x[1] ** (ov - 2) + op * x[0] ** (op - 1), -ov * (ov - 1) * x[0] ** (ov - 2) + op * x[1] ** (op - 1)])
+    else:              # exact_functions_stokes3D (runtests.jl:547-576)
+        u = lambda x: np.stack([x[2] ** ov + 1, x[0] ** ov - 1, x[1] ** ov])
+        p = lambda x: np.stack([x[0] ** op + x[1] ** op + x[2] ** op - 3.0 / (op + 1)])
+        f = lambda x: np.stack([-ov * (ov - 1) * x[2] ** (ov - 2) + op * x[0] ** (op - 1), -ov * (ov - 1) * x[0] ** (ov - 2) + op * x[1] ** (op - 1),
+                                -ov * (ov - 1) * x[1] ** (ov - 2) + op * x[2] ** (op - 1)])
+    tab = lambda fn, grid, xr: np.ascontiguousarray(np.moveaxis(fn(_xq_items(grid, xr).reshape(-1, dim).T).reshape(-1, grid.ncells, xr.shape[0]), 0, 2))
+    K = assemble(g, sv, sv, O.OP_GRAD, O.OP_GRAD, apt=O.APT_SYMMETRIC)
+    B = assemble(g, sv, sq, O.OP_DIV, O.OP_ID, factor=-1.0)                 # -(p, div v): rows velocity, columns pressure
+    xr, _ = O.qrule(dim, 2)
+    b = np.zeros(sv.ndofs)
+    O.lf_assemble(b, g, sv, O.OP_ID, fsrc=O.F_QP_TABLE, fdata=tab(f, g, xr), bonus_quadorder=0)
+    # velocity boundary data: best approximation on all boundary regions
+    bs = sv.on_bfaces()
+    bg = bs.xgrid
+    Mb = O.OracleMatrix(sv.ndofs, sv.ndofs)
+    O.blf_assemble(Mb, bg, bs, bs, O.OP_ID, O.OP_ID, apt=O.APT_SYMMETRIC)
+    Mb = Mb.toscipy().tocsc()
+    xrb, _ = O.qrule(bg.dim, 2 + ov)
+    bb = np.zeros(sv.ndofs)
+    O.lf_assemble(bb, bg, bs, O.OP_ID, fsrc=O.F_QP_TABLE, fdata=tab(u, bg, xrb), bonus_quadorder=ov)
+    fixed = np.flatnonzero(np.diff(Mb.indptr) != 0)
+    assert np.array_equal(fixed, np.unique(sv.bfacedofs) - 1)
+    target = np.zeros(sv.ndofs)
+    target[fixed] = spla.spsolve(Mb[fixed][:, fixed].tocsc(), bb[fixed])
+    # saddle point system with penalties (velocity boundary dofs, one pressure dof), penalised rows scaled back to O(1) for SuperLU
+    n, m = sv.ndofs, sq.ndofs
+    M = sp_.bmat([[K, B], [B.T, None]]).tolil()
+    rhs = np.concatenate([b, np.zeros(m)])
+    penalty = 1e60
+    d = np.ones(n + m)
+    for j in list(fixed) + [n]:
+        M[j, j] = penalty
+        rhs[j] = penalty * (target[j] if j < n else 0.0)
+        d[j] = 1.0 / penalty
+    sol = spla.spsolve((sp_.diags(d) @ M.tocsr()).tocsc(), d * rhs)
+    _, mean = O.ii_evaluate(g, sq, O.OP_ID, sol[n:], kind=O.II_NONE, itemwise=False)
+    sol[n:] -= mean[0] / g.cellvolumes.sum()
+    xre, _ = O.qrule(dim, ov + 2)
+    _, ev = O.ii_evaluate(g, sv, O.OP_ID, sol[:n], kind=O.II_L2ERROR, data=tab(u, g, xre), bonus_quadorder=ov, itemwise=False)
+    xrp, _ = O.qrule(dim, op + 1)
+    _, ep = O.ii_evaluate(g, sq, O.OP_ID, sol[n:], kind=O.II_L2ERROR, data=tab(p, g, xrp), bonus_quadorder=op, itemwise=False)
+    assert max(np.sqrt(np.abs(ev).sum()), np.sqrt(np.abs(ep).sum())) < TOL
