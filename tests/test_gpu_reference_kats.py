@@ -78,3 +78,38 @@ def test_reference_stokes_taylor_hood_on_device(dim):
     errV = np.sqrt(np.abs(np.asarray(G.evaluate(G.L2ErrorIntegrator(udata, G.Identity, quadorder=ov), sol[1]))).sum())
     errP = np.sqrt(abs(G.evaluate(G.L2ErrorIntegrator(pdata, G.Identity, quadorder=op), sol[2])))
     assert max(errV, errP) < 6e-12, (errV, errP)
+
+
+from test_oracle_kat import RECON_CATALOG, br_boundary_values, stokes_exact  # noqa: E402
+
+
+@pytest.mark.parametrize("dim,recon,ov,op", RECON_CATALOG, ids=["BR{%d} x P0 R=%s orders %d,%d" % (d, r, a, b) for d, r, a, b in RECON_CATALOG])
+def test_reference_pressure_robust_stokes_on_device(dim, recon, ov, op):
+    """"Reconstruction-Operators" (runtests.jl:674-723): Bernardi-Raugel x P0 Stokes with the right-hand side tested by R v (R: BR -> RT0 | BDM1) and a cubic
+    pressure: the discrete velocity is exact (errorV < tolerance on R u_h).  Laplace and divergence blocks by the column kernels, the reconstructed
+    LinearForm by the gather kernels (2D) / the bit-exact path (3D), the L2ErrorIntegrator with the reconstruction operator on the device."""
+    g = G.uniform_refine(G.grid_unitsquare() if dim == 2 else G.grid_unitcube(), 1)
+    sv, sq = G.FESpace(G.H1BR(dim), g), G.FESpace(G.L2P0(1), g)
+    u, p, f = stokes_exact(dim, ov, op)
+    R = G.ReconstructionIdentity(G.HDIVRT0(dim) if recon == "RT0" else G.HDIVBDM1(dim))
+    udata = G.DataFunction(u, [dim, dim], bonus_quadorder=ov)
+    fdata = G.DataFunction(f, [dim, dim], bonus_quadorder=max(0, op - 1))
+    A = G.FEMatrix([sv, sq])
+    G.assemble_operator(A[1, 1], G.LaplaceOperator(1.0))
+    G.assemble_operator(A[1, 2], G.LagrangeMultiplier(G.Divergence), At=A[2, 1])
+    rhs = G.FEVector([sv, sq])
+    G.assemble_operator(rhs[1], G.LinearForm(R, fdata))
+    fixed, target = br_boundary_values(sv, u)
+    n = sv.ndofs
+    M = A.tocsc().tolil()
+    b = rhs.entries.copy()
+    penalty = 1e60
+    d = np.ones(M.shape[0])
+    for j in list(fixed) + [n]:
+        M[j, j] = penalty
+        b[j] = penalty * (target[j] if j < n else 0.0)
+        d[j] = 1.0 / penalty
+    sol = G.FEVector([sv, sq])
+    sol.entries[:] = spla.spsolve((sp.diags(d) @ M.tocsr()).tocsc(), d * b)
+    err2 = G.evaluate(G.L2ErrorIntegrator(udata, R, quadorder=ov), sol[1])
+    assert np.sqrt(np.abs(np.asarray(err2)).sum()) < 6e-12

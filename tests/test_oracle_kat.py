@@ -654,3 +654,82 @@ def test_reference_stokes_taylor_hood(dim):
     xrp, _ = O.qrule(dim, op + 1)
     _, ep = O.ii_evaluate(g, sq, O.OP_ID, sol[n:], kind=O.II_L2ERROR, data=tab(p, g, xrp), bonus_quadorder=op, itemwise=False)
     assert max(np.sqrt(np.abs(ev).sum()), np.sqrt(np.abs(ep).sum())) < TOL
+
+
+# ---- "Reconstruction-Operators" (runtests.jl:674-723): the pressure-robust Stokes test -- the property the reference package is named after ------
+RECON_CATALOG = [(2, "RT0", 0, 3), (2, "BDM1", 1, 3), (3, "RT0", 0, 3), (3, "BDM1", 1, 3)]     # [H1BR, L2P0{1}, HDIVRT0 | HDIVBDM1], ExpectedOrders [[0,3],[1,3]]
+
+
+def stokes_exact(dim, ov, op):
+    """exact_functions_stokes2D / 3D (runtests.jl:522-576): velocity, pressure, rhs = -Laplace u + grad p"""
+    lap = (lambda t: ov * (ov - 1) * t ** (ov - 2)) if ov > 1 else (lambda t: 0.0 * t)
+    dpp = (lambda t: op * t ** (op - 1)) if op > 0 else (lambda t: 0.0 * t)
+    if dim == 2:
+        u = lambda x: np.stack([x[1] ** ov + 1, x[0] ** ov - 1])
+        p = lambda x: np.stack([x[0] ** op + x[1] ** op - 2.0 / (op + 1)])
+        f = lambda x: np.stack([-lap(x[1]) + dpp(x[0]), -lap(x[0]) + dpp(x[1])])
+    else:
+        u = lambda x: np.stack([x[2] ** ov + 1, x[0] ** ov - 1, x[1] ** ov])
+        p = lambda x: np.stack([x[0] ** op + x[1] ** op + x[2] ** op - 3.0 / (op + 1)])
+        f = lambda x: np.stack([-lap(x[2]) + dpp(x[0]), -lap(x[0]) + dpp(x[1]), -lap(x[1]) + dpp(x[2])])
+    return u, p, f
+
+
+def br_boundary_values(sv, u):
+    """boundary data of a Bernardi-Raugel velocity whose trace is (piecewise) linear: nodal values, face bubbles zero -- what the boundary best
+    approximation of the reference returns for such data"""
+    g = sv.xgrid
+    dim = g.dim
+    bn = np.unique(g.bfacenodes.astype(np.int64).ravel()) - 1
+    vals = u(g.coords[bn].T)
+    fixed, target = [], np.zeros(sv.ndofs)
+    for c in range(dim):
+        fixed.append(c * g.nnodes + bn)
+        target[c * g.nnodes + bn] = vals[c]
+    fixed.append(dim * g.nnodes + g.bfacefaces.astype(np.int64) - 1)
+    return np.concatenate(fixed), target
+
+
+@pytest.mark.parametrize("dim,recon,ov,op", RECON_CATALOG, ids=["BR{%d} x P0 R=%s orders %d,%d" % (d, r, a, b) for d, r, a, b in RECON_CATALOG])
+def test_reference_pressure_robust_stokes_with_reconstruction(dim, recon, ov, op):
+    """test_Stokes(xgrid, [H1BR{d}, L2P0{1}], orders, true, ReconstructionIdentity{HDIVRT0{d} | HDIVBDM1{d}}) (runtests.jl:606-640, 700-720): the right-hand
+    side (f, R v) with f = -Laplace u + grad p for a CUBIC pressure that is not in the pressure space; with the reconstruction the discrete velocity is
+    exact anyway (errorV < tolerance, measured on R u_h like the reference does).  2D runs on testgrid(Triangle2D) instead of the mixed triangle /
+    parallelogram grid of the reference (quadrilaterals are not on the path); 3D is the reference's grid."""
+    import scipy.sparse as sp_
+    g = G.uniform_refine(G.grid_unitsquare() if dim == 2 else G.grid_unitcube(), 1)
+    sv, sq = G.FESpace(G.H1BR(dim), g), G.FESpace(G.L2P0(1), g)
+    u, p, f = stokes_exact(dim, ov, op)
+    rop = O.OP_RECON_ID_RT0 if recon == "RT0" else O.OP_RECON_ID_BDM1
+    tab = lambda fn, xr: np.ascontiguousarray(np.moveaxis(fn(_xq_items(g, xr).reshape(-1, dim).T).reshape(-1, g.ncells, xr.shape[0]), 0, 2))
+    K = assemble(g, sv, sv, O.OP_GRAD, O.OP_GRAD, apt=O.APT_SYMMETRIC)
+    B = assemble(g, sv, sq, O.OP_DIV, O.OP_ID, factor=-1.0)
+    pk = sv.fetype.polynomialorder(dim)
+    bonus = max(0, op - 1)
+    xr, _ = O.qrule(dim, pk + bonus)
+    b = np.zeros(sv.ndofs)
+    O.lf_assemble(b, g, sv, rop, fsrc=O.F_QP_TABLE, fdata=tab(f, xr), bonus_quadorder=bonus)
+    fixed, target = br_boundary_values(sv, u)
+    n, m = sv.ndofs, sq.ndofs
+    M = sp_.bmat([[K, B], [B.T, None]]).tolil()
+    rhs = np.concatenate([b, np.zeros(m)])
+    penalty = 1e60
+    d = np.ones(n + m)
+    for j in list(fixed) + [n]:
+        M[j, j] = penalty
+        rhs[j] = penalty * (target[j] if j < n else 0.0)
+        d[j] = 1.0 / penalty
+    sol = spla.spsolve((sp_.diags(d) @ M.tocsr()).tocsc(), d * rhs)
+    xre, _ = O.qrule(dim, ov + pk)
+    _, ev = O.ii_evaluate(g, sv, rop, sol[:n], kind=O.II_L2ERROR, data=tab(u, xre), bonus_quadorder=ov, itemwise=False)
+    assert np.sqrt(np.abs(ev).sum()) < TOL
+    # without the reconstruction the same discretisation is NOT pressure robust: the velocity error is of the size of the pressure's
+    # best-approximation error (this is what the reconstruction operator removes)
+    b0 = np.zeros(sv.ndofs)
+    O.lf_assemble(b0, g, sv, O.OP_ID, fsrc=O.F_QP_TABLE, fdata=tab(f, xr), bonus_quadorder=bonus)
+    rhs0 = np.concatenate([b0, np.zeros(m)])
+    for j in list(fixed) + [n]:
+        rhs0[j] = penalty * (target[j] if j < n else 0.0)
+    sol0 = spla.spsolve((sp_.diags(d) @ M.tocsr()).tocsc(), d * rhs0)
+    _, e0 = O.ii_evaluate(g, sv, O.OP_ID, sol0[:n], kind=O.II_L2ERROR, data=tab(u, xre), bonus_quadorder=ov, itemwise=False)
+    assert np.sqrt(np.abs(e0).sum()) > 1e-4
