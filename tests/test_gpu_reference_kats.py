@@ -113,3 +113,41 @@ def test_reference_pressure_robust_stokes_on_device(dim, recon, ov, op):
     sol.entries[:] = spla.spsolve((sp.diags(d) @ M.tocsr()).tocsc(), d * b)
     err2 = G.evaluate(G.L2ErrorIntegrator(udata, R, quadorder=ov), sol[1])
     assert np.sqrt(np.abs(np.asarray(err2)).sum()) < 6e-12
+
+
+@pytest.mark.parametrize("recon", ["RT0", "BDM1"])
+def test_example222_hydrostatic_problem_on_device(recon):
+    """Example222_PressureRobustness2D.test() (runtests.jl:829-831: < 1e-14) = BASELINE configuration C4 on the device: Bernardi-Raugel Laplacian and
+    divergence block by the column kernels, LinearForm(ReconstructionIdentity{RT0 | BDM1}, grad p) with the 9-point Stroud rule by the gather kernel,
+    L2ErrorIntegrator on the device; u = 0, p = x^3 + y^3 - 1/2.  The pressure-robust velocity vanishes to rounding, the classical one does not."""
+    g = G.uniform_refine(G.grid_unitsquare(), 2)
+    sv, sq = G.FESpace(G.H1BR(2), g), G.FESpace(G.L2P0(1), g)
+    fdata = G.DataFunction(lambda x: np.stack([3 * x[0] ** 2, 3 * x[1] ** 2]), [2, 2], bonus_quadorder=2)
+    zero = G.DataFunction([0.0, 0.0])
+    R = G.ReconstructionIdentity(G.HDIVRT0(2) if recon == "RT0" else G.HDIVBDM1(2))
+    A = G.FEMatrix([sv, sq])
+    G.assemble_operator(A[1, 1], G.LaplaceOperator(1.0))
+    G.assemble_operator(A[1, 2], G.LagrangeMultiplier(G.Divergence), At=A[2, 1])
+    fixed, _ = br_boundary_values(sv, lambda x: np.zeros((2, x.shape[1])))
+    n = sv.ndofs
+    M = A.tocsc().tolil()
+    penalty = 1e60
+    d = np.ones(M.shape[0])
+    for j in list(fixed) + [n]:
+        M[j, j] = penalty
+        d[j] = 1.0 / penalty
+    Ms = (sp.diags(d) @ M.tocsr()).tocsc()
+    errs = {}
+    for name, op in (("robust", R), ("classical", G.Identity)):
+        rhs = G.FEVector([sv, sq])
+        Lf = G.LinearForm(op, fdata)
+        G.assemble_operator(rhs[1], Lf)
+        if name == "robust":
+            assert len(Lf._pattern.AM.qf) == 9 and G.blf_stats(Lf._pattern).path == G._lib.PATH_COLUMNS      # Stroud rule, gather kernel
+        b = rhs.entries.copy()
+        b[list(fixed) + [n]] = 0.0
+        sol = G.FEVector([sv, sq])
+        sol.entries[:] = spla.spsolve(Ms, d * b)
+        errs[name] = np.sqrt(np.abs(np.asarray(G.evaluate(G.L2ErrorIntegrator(zero, G.Identity, quadorder=0), sol[1]))).sum())
+    assert errs["robust"] < 1e-14, errs
+    assert errs["classical"] > 1e-3, errs

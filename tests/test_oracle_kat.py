@@ -733,3 +733,43 @@ def test_reference_pressure_robust_stokes_with_reconstruction(dim, recon, ov, op
     sol0 = spla.spsolve((sp_.diags(d) @ M.tocsr()).tocsc(), d * rhs0)
     _, e0 = O.ii_evaluate(g, sv, O.OP_ID, sol0[:n], kind=O.II_L2ERROR, data=tab(u, xre), bonus_quadorder=ov, itemwise=False)
     assert np.sqrt(np.abs(e0).sum()) > 1e-4
+
+
+@pytest.mark.parametrize("recon", ["RT0", "BDM1"])
+def test_example222_hydrostatic_problem_is_solved_exactly_by_the_pressure_robust_scheme(recon):
+    """Example222_PressureRobustness2D.test() (examples/Example222_PressureRobustness2D.jl:36-46, 66-132, 189-200; runtests.jl:829-831 asserts < 1e-14) --
+    BASELINE configuration C4: Stokes with u = 0, p = x^3 + y^3 - 1/2, f = grad p, viscosity 1, [H1BR{2}, L2P0{1}] and the right-hand side
+    LinearForm(ReconstructionIdentity{HDIVRT0{2} | HDIVBDM1{2}}, f): || u_h ||_L2 vanishes to rounding, while the classical right-hand side leaves a
+    velocity error of the size of the pressure error.  Triangle grid of the same refinement depth instead of the reference's mixed triangle /
+    parallelogram grid (quadrilaterals are off the path)."""
+    import scipy.sparse as sp_
+    g = G.uniform_refine(G.grid_unitsquare(), 2)
+    sv, sq = G.FESpace(G.H1BR(2), g), G.FESpace(G.L2P0(1), g)
+    f = lambda x: np.stack([3 * x[0] ** 2, 3 * x[1] ** 2])
+    rop = O.OP_RECON_ID_RT0 if recon == "RT0" else O.OP_RECON_ID_BDM1
+    tab = lambda fn, xr: np.ascontiguousarray(np.moveaxis(fn(_xq_items(g, xr).reshape(-1, 2).T).reshape(-1, g.ncells, xr.shape[0]), 0, 2))
+    K = assemble(g, sv, sv, O.OP_GRAD, O.OP_GRAD, apt=O.APT_SYMMETRIC)
+    B = assemble(g, sv, sq, O.OP_DIV, O.OP_ID, factor=-1.0)
+    xr, _ = O.qrule(2, 2 + 2)                                  # Bernardi-Raugel order 2 + bonus 2 of grad p: the 9-point Stroud rule
+    assert xr.shape[0] == 9
+    fixed, target = br_boundary_values(sv, lambda x: np.zeros((2, x.shape[1])))
+    n, m = sv.ndofs, sq.ndofs
+    M = sp_.bmat([[K, B], [B.T, None]]).tolil()
+    penalty = 1e60
+    d = np.ones(n + m)
+    for j in list(fixed) + [n]:
+        M[j, j] = penalty
+        d[j] = 1.0 / penalty
+    Ms = (sp_.diags(d) @ M.tocsr()).tocsc()
+    errs = {}
+    for name, op in (("robust", rop), ("classical", O.OP_ID)):
+        b = np.zeros(n)
+        O.lf_assemble(b, g, sv, op, fsrc=O.F_QP_TABLE, fdata=tab(f, xr), bonus_quadorder=2)
+        rhs = np.concatenate([b, np.zeros(m)])
+        rhs[list(fixed) + [n]] = 0.0
+        sol = spla.spsolve(Ms, d * rhs)
+        xre, _ = O.qrule(2, 2)
+        _, e = O.ii_evaluate(g, sv, O.OP_ID, sol[:n], kind=O.II_L2ERROR, data=np.zeros((g.ncells, xre.shape[0], 2)), bonus_quadorder=0, itemwise=False)
+        errs[name] = np.sqrt(np.abs(e).sum())
+    assert errs["robust"] < 1e-14, errs
+    assert errs["classical"] > 1e-3, errs
