@@ -151,3 +151,30 @@ def test_example222_hydrostatic_problem_on_device(recon):
         errs[name] = np.sqrt(np.abs(np.asarray(G.evaluate(G.L2ErrorIntegrator(zero, G.Identity, quadorder=0), sol[1]))).sum())
     assert errs["robust"] < 1e-14, errs
     assert errs["classical"] > 1e-3, errs
+
+
+@pytest.mark.parametrize("fam", ["RT0", "BDM1"])
+def test_example302_hdiv_bestapproximation_on_device(fam):
+    """Example302_BestapproximationHdiv3D = BASELINE configuration C5 on the device: RT0 / BDM1 mass matrix with the Piola map (column kernels), the
+    Hdiv x P0 divergence block with its transposed copy, both right-hand sides, and the per-cell ItemIntegrator of Divergence(u_h).  The example's claim
+    "the divergence of the approximation equals the piecewise integral mean of the exact divergence" holds cell by cell."""
+    g = G.uniform_refine(G.reference_domain("Tetrahedron3D"), 2)
+    sv, sq = G.FESpace((G.HDIVRT0 if fam == "RT0" else G.HDIVBDM1)(3), g), G.FESpace(G.L2P0(1), g)
+    udata = G.DataFunction(lambda x: np.stack([x[0] ** 3 + x[2] ** 2, -x[0] ** 2 + x[1] + 1, x[0] * x[1]]), [3, 3], bonus_quadorder=3)
+    ddata = G.DataFunction(lambda x: np.stack([3 * x[0] ** 2 + 1.0]), [1, 3], bonus_quadorder=2)
+    A = G.FEMatrix([sv, sq])
+    G.assemble_operator(A[1, 1], G.ReactionOperator(1.0))
+    G.assemble_operator(A[1, 2], G.LagrangeMultiplier(G.Divergence), At=A[2, 1])
+    rhs = G.FEVector([sv, sq])
+    G.assemble_operator(rhs[1], G.LinearForm(G.Identity, udata))
+    # the transposed copy of a LagrangeMultiplier block carries the opposite sign (bilinearform.jl:354-360: "sign is changed in case nonzero rhs
+    # data is applied to LagrangeMultiplier"), so the constraint row reads (div u_h, q) = (div u, q) with the example's plain right-hand side
+    G.assemble_operator(rhs[2], G.LinearForm(G.Identity, ddata))
+    b2 = rhs.entries[sv.ndofs:].copy()
+    sol = G.FEVector([sv, sq])
+    sol.entries[:] = spla.spsolve(A.tocsc(), rhs.entries)
+    cell_div = np.zeros((g.ncells, 1))
+    G.evaluate_itemwise(cell_div, G.ItemIntegrator([G.Divergence]), sol[1])
+    assert np.abs(cell_div[:, 0] - b2).max() < 1e-14
+    err = np.sqrt(np.abs(np.asarray(G.evaluate(G.L2ErrorIntegrator(udata, G.Identity, quadorder=3), sol[1]))).sum())
+    assert 1e-4 < err < 0.2                                                        # u is cubic: a genuine approximation error remains

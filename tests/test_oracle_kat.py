@@ -773,3 +773,39 @@ def test_example222_hydrostatic_problem_is_solved_exactly_by_the_pressure_robust
         errs[name] = np.sqrt(np.abs(e).sum())
     assert errs["robust"] < 1e-14, errs
     assert errs["classical"] > 1e-3, errs
+
+
+@pytest.mark.parametrize("fam", ["RT0", "BDM1"])
+def test_example302_hdiv_bestapproximation_preserves_the_divergence(fam):
+    """Example302_BestapproximationHdiv3D (BASELINE configuration C5): L2 best approximation of u = (x^3 + z^2, -x^2 + y + 1, x y) in HDIVRT0{3} / HDIVBDM1{3} with the
+    Lagrange multiplier (L2P0{1}) for the divergence constraint (examples/Example302_BestapproximationHdiv3D.jl:19-55).  The example's own claim: "the divergence of
+    the approximation equals the piecewise integral mean of the exact divergence" -- checked cell by cell; plus the saddle point identities."""
+    import scipy.sparse as sp_
+    g = G.uniform_refine(G.reference_domain("Tetrahedron3D"), 2)
+    sv, sq = G.FESpace((G.HDIVRT0 if fam == "RT0" else G.HDIVBDM1)(3), g), G.FESpace(G.L2P0(1), g)
+    u = lambda x: np.stack([x[0] ** 3 + x[2] ** 2, -x[0] ** 2 + x[1] + 1, x[0] * x[1]])
+    divu = lambda x: np.stack([3 * x[0] ** 2 + 1.0])
+    tab = lambda fn, xr: np.ascontiguousarray(np.moveaxis(fn(_xq_items(g, xr).reshape(-1, 3).T).reshape(-1, g.ncells, xr.shape[0]), 0, 2))
+    Mh = assemble(g, sv, sv, O.OP_ID, O.OP_ID)
+    # LagrangeMultiplier(Divergence): the block and its transposed copy as the reference assembles them -- the copy carries the OPPOSITE sign
+    # (bilinearform.jl:354-360: "sign is changed in case nonzero rhs data is applied to LagrangeMultiplier"), so the example's plain right-hand
+    # side LinearForm(Identity, div u) yields (div u_h, q) = (div u, q)
+    Bm, Btm = O.OracleMatrix(sv.ndofs, sq.ndofs), O.OracleMatrix(sq.ndofs, sv.ndofs)
+    O.blf_assemble(Bm, g, sv, sq, O.OP_DIV, O.OP_ID, factor=-1.0, transpose_copy=Btm)
+    B, Bt = Bm.toscipy(), Btm.toscipy()
+    assert abs(Bt + B.T).max() == 0
+    xr, _ = O.qrule(3, 1 + 3)
+    b1 = np.zeros(sv.ndofs)
+    O.lf_assemble(b1, g, sv, O.OP_ID, fsrc=O.F_QP_TABLE, fdata=tab(u, xr), bonus_quadorder=3)
+    xr2, _ = O.qrule(3, 0 + 2)
+    b2 = np.zeros(sq.ndofs)
+    O.lf_assemble(b2, g, sq, O.OP_ID, fsrc=O.F_QP_TABLE, fdata=tab(divu, xr2), bonus_quadorder=2)
+    S = sp_.bmat([[Mh, B], [Bt, None]]).tocsc()
+    sol = spla.spsolve(S, np.concatenate([b1, b2]))
+    uh = sol[: sv.ndofs]
+    # int_T div u_h = int_T div u for every cell: div u_h is piecewise constant, so it IS the cell mean of div u
+    xr1, _ = O.qrule(3, 1)
+    cell_div, _ = O.ii_evaluate(g, sv, O.OP_DIV, uh, kind=O.II_NONE, itemwise=True)
+    assert np.abs(cell_div[:, 0] - b2).max() < 1e-14
+    # the best approximation is a projection: second application reproduces it
+    assert np.abs(S @ sol - np.concatenate([b1, b2])).max() < 1e-13
