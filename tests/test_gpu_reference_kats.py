@@ -178,3 +178,31 @@ def test_example302_hdiv_bestapproximation_on_device(fam):
     assert np.abs(cell_div[:, 0] - b2).max() < 1e-14
     err = np.sqrt(np.abs(np.asarray(G.evaluate(G.L2ErrorIntegrator(udata, G.Identity, quadorder=3), sol[1]))).sum())
     assert 1e-4 < err < 0.2                                                        # u is cubic: a genuine approximation error remains
+
+
+@pytest.mark.parametrize("level", [2, 3])
+def test_example301_poisson3d_on_device_with_the_metric_kernel(level):
+    """Example301_Poisson3D = BASELINE configuration C2, the form of the headline metric, solved end to end: the P2 Laplacian by the ring-walk kernel
+    (GRMP_PATH_AUTO -> PATH_FAST), LinearForm(Identity, Laplace u; factor = -1), BestapproxDirichletBoundary on all six regions (ON_BFACES forms),
+    penalties on the device-resident matrix, host solve, L2 and H1 error integrators on the device.  u = x (z - y) + y^2 lies in H1P2{1,3}: both errors
+    vanish to rounding (the example itself uses H1P1 and reports a convergence history)."""
+    g = G.uniform_refine(G.grid_unitcube(), level)
+    s = G.FESpace(G.H1P2(1, 3), g)
+    udata = G.DataFunction(lambda x: np.stack([x[0] * (x[2] - x[1]) + x[1] * x[1]]), [1, 3], bonus_quadorder=2)
+    gdata = G.DataFunction(lambda x: np.stack([x[2] - x[1], -x[0] + 2 * x[1], x[0]]), [3, 3], bonus_quadorder=1)
+    A = G.DiscreteSymmetricBilinearForm([G.Gradient, G.Gradient], [s, s])
+    cp, rv, _ = G.assemble_csc(A, 1.0)
+    assert G.blf_stats(A).path == G._lib.PATH_FAST
+    rhs = G.FEVector([s])
+    G.assemble(rhs[1], G.DiscreteLinearForm([G.Identity], [s], G.fdot_action(G.DataFunction([2.0]))), factor=-1)
+    sol = G.FEVector([s])
+    fixed = G.boundarydata(sol[1], [G.BoundaryData(G.BestapproxDirichletBoundary, data=udata, regions=[1, 2, 3, 4, 5, 6])])
+    G.apply_penalties(A, fixed, 1e60)
+    rhs.entries[fixed - 1] = 1e60 * sol.entries[fixed - 1]
+    M = sp.csc_matrix((G.fetch_values(A), rv - 1, cp - 1), shape=(s.ndofs, s.ndofs))
+    sol.entries[:] = spla.spsolve(M, rhs.entries)
+    e0 = np.sqrt(abs(G.evaluate(G.L2ErrorIntegrator(udata, G.Identity), sol[1])))
+    e1 = np.sqrt(abs(G.evaluate(G.L2ErrorIntegrator(gdata, G.Gradient), sol[1])))
+    assert e0 < 6e-12 and e1 < 6e-11, (e0, e1)
+    _, nrm = G.residual(A, sol.entries, rhs.entries, fixed_dofs=fixed, want_vector=False)
+    assert nrm < 1e-20

@@ -809,3 +809,38 @@ def test_example302_hdiv_bestapproximation_preserves_the_divergence(fam):
     assert np.abs(cell_div[:, 0] - b2).max() < 1e-14
     # the best approximation is a projection: second application reproduces it
     assert np.abs(S @ sol - np.concatenate([b1, b2])).max() < 1e-13
+
+
+def test_example301_poisson3d_p2_reproduces_the_quadratic_solution():
+    """Example301_Poisson3D (BASELINE configuration C2, the metric form): -Laplace u = f on the unit cube, u = x (z - y) + y^2, BestapproxDirichletBoundary on all six
+    boundary regions, right-hand side LinearForm(Identity, Laplace u; factor = -1) (examples/Example301_Poisson3D.jl:23-45).  With H1P2{1,3} the exact solution is in
+    the discrete space: L2 and H1 errors (L2ErrorIntegrator(u), L2ErrorIntegrator(grad u, Gradient)) vanish to rounding."""
+    g = G.uniform_refine(G.grid_unitcube(), 1)
+    s = G.FESpace(G.H1P2(1, 3), g)
+    u = lambda x: np.stack([x[0] * (x[2] - x[1]) + x[1] * x[1]])
+    du = lambda x: np.stack([x[2] - x[1], -x[0] + 2 * x[1], x[0]])
+    tab = lambda fn, grid, xr: np.ascontiguousarray(np.moveaxis(fn(_xq_items(grid, xr).reshape(-1, 3).T).reshape(-1, grid.ncells, xr.shape[0]), 0, 2))
+    K = assemble(g, s, s, O.OP_GRAD, O.OP_GRAD, apt=O.APT_SYMMETRIC).tocsc()
+    b = np.zeros(s.ndofs)
+    O.lf_assemble(b, g, s, O.OP_ID, fsrc=O.F_CONST, fdata=[2.0], factor=-1.0)
+    bs = s.on_bfaces()
+    bg = bs.xgrid
+    Mb = O.OracleMatrix(s.ndofs, s.ndofs)
+    O.blf_assemble(Mb, bg, bs, bs, O.OP_ID, O.OP_ID, apt=O.APT_SYMMETRIC)
+    Mb = Mb.toscipy().tocsc()
+    xrb, _ = O.qrule(2, 2 + 2)
+    bb = np.zeros(s.ndofs)
+    O.lf_assemble(bb, bg, bs, O.OP_ID, fsrc=O.F_QP_TABLE, fdata=tab(u, bg, xrb), bonus_quadorder=2)
+    fixed = np.flatnonzero(np.diff(Mb.indptr) != 0)
+    target = np.zeros(s.ndofs)
+    target[fixed] = spla.spsolve(Mb[fixed][:, fixed].tocsc(), bb[fixed])
+    K = K.tolil()
+    for j in fixed:
+        K[j, j] = 1e60
+    b[fixed] = 1e60 * target[fixed]
+    sol = spla.spsolve(K.tocsc(), b)
+    xre, _ = O.qrule(3, 4 + 2)
+    _, e0 = O.ii_evaluate(g, s, O.OP_ID, sol, kind=O.II_L2ERROR, data=tab(u, g, xre), bonus_quadorder=4, itemwise=False)
+    xrg, _ = O.qrule(3, 2 + 1)
+    _, e1 = O.ii_evaluate(g, s, O.OP_GRAD, sol, kind=O.II_L2ERROR, data=tab(du, g, xrg), bonus_quadorder=2, itemwise=False)
+    assert np.sqrt(abs(e0[0])) < TOL and np.sqrt(abs(e1[0])) < 10 * TOL
